@@ -1,0 +1,164 @@
+"""Extracts the known-answer matrices that the reference's own test-suite and docs
+hold for the hot path and writes them as JSON fixtures next to this file.
+
+Run HERE (the container with /root/reference mounted):
+
+    python tests/golden/make_reference_fixtures.py
+
+The GPU box has no /root/reference; the tests only read the committed JSON.
+Sources (reference tree, CompactBases.jl v0.3.1):
+  test/bsplines/splines.jl:11-15        mass matrix, k=3, knots [0,1,1,3,4,6]
+  test/bsplines/derivatives.jl          exact rational derivative matrices (line ranges recorded per fixture)
+  docs/src/bsplines/usage.md            B[0.5,:] / sparse structure transcripts
+  docs/src/bsplines/splines.md          spline evaluation transcripts
+  README.md:160-182                     FE-DVR Laplacian printout
+"""
+import json
+import os
+import re
+from fractions import Fraction
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def parse_rational_block(lines):
+    """Rows of tokens like `-5//12`, `0//1`, `0`, `2//1`."""
+    rows = []
+    for ln in lines:
+        ln = ln.replace("[", " ").replace("]", " ")
+        ln = re.sub(r"@test.*?≈", " ", ln)
+        toks = re.findall(r"-?\d+(?://\d+)?", ln)
+        if not toks:
+            continue
+        row = []
+        for t in toks:
+            if "//" in t:
+                a, b = t.split("//")
+                row.append([int(a), int(b)])
+            else:
+                row.append([int(t), 1])
+        rows.append(row)
+    return rows
+
+
+def grab(path, first, last):
+    with open(os.path.join(REF, path), encoding="utf-8") as f:
+        src = f.read().split("\n")
+    return src[first - 1:last]
+
+
+# Numbers transcribed from REPL transcripts in the reference docs / README
+# (16-17 significant digits where the transcript shows them).
+DOCS = {
+    "usage_eval": {
+        "source": "docs/src/bsplines/usage.md:125-173 (LinearKnotSet(4,0,1,5))",
+        "k": 4, "a": 0.0, "b": 1.0, "N": 5,
+        "B_0.5_row": [0.0, 0.0, 0.020833333333333325, 0.47916666666666674,
+                      0.4791666666666666, 0.020833333333333322, 0.0, 0.0],
+        "x_quarter": [0.0, 0.25, 0.5, 0.75, 1.0],
+        # (row, col, 6-digit value) of B[0:0.25:1,:]: 14 stored entries, column-major order
+        "csc_quarter": [[1, 1, 1.0], [2, 2, 0.105469], [2, 3, 0.576823], [3, 3, 0.0208333],
+                        [2, 4, 0.315104], [3, 4, 0.479167], [4, 4, 0.00260417], [2, 5, 0.00260417],
+                        [3, 5, 0.479167], [4, 5, 0.315104], [3, 6, 0.0208333], [4, 6, 0.576823],
+                        [4, 7, 0.105469], [5, 8, 1.0]],
+        # B[0:0.1:1, 1]: 2 stored entries
+        "col1_tenths": [[1, 1.0], [2, 0.125]],
+    },
+    "spline_eval": {
+        "source": "docs/src/bsplines/splines.md:54-96 (same basis, c = sin.(1:8))",
+        "x": [0.3, 0.4, 0.5, 0.6, 0.7, 0.8],
+        "s": [-0.28804656969083225, -0.6408357079724976, -0.8250002333223664,
+              -0.8119858486932346, -0.5856964504991202, -0.15856643671353235],
+        "chi_c_quarter": [0.8414709848078965, -0.06366510061255656, -0.8250002333223664,
+                          -0.39601358159504896, 0.9893582466233818],
+    },
+    "mass_k4": {
+        "source": "docs/src/bsplines/usage.md:38-49 (first column of B'B, 6 digits)",
+        "col1": [0.0285714, 0.0175, 0.00369048, 0.000238095],
+        "diag4": 0.095873,
+    },
+    "readme_bspline_k5": {
+        "source": "README.md:200-224 (BSpline(LinearKnotSet(5,0,1,4))[:,2:end-1], 6 digits)",
+        "k": 5, "a": 0.0, "b": 1.0, "N": 4, "sel": [2, 7],
+        "mass_row1": [0.0414683, 0.0307567, 0.00934744, 0.00101411, 2.75573e-6],
+        "laplacian_row1": [-7.08571, -0.530159, 1.01587, 0.253968, 0.0031746],
+        "laplacian_row3": [1.01587, -0.26455, -1.8455, -0.310406, 0.756966, 0.253968],
+    },
+    "readme_fedvr": {
+        "source": "README.md:160-182 (FEDVR(range(0,1,length=5), 5)[:,2:end-1] Laplacian, 6 digits)",
+        "order": 5, "a": 0.0, "b": 1.0, "nel": 4, "sel": [2, 16],
+        "block": [[-746.667, 298.667, -74.6667], [298.667, -426.667, 298.667], [-74.6667, 298.667, -746.667]],
+        "east": [33.0583, -90.5097, 758.901],
+        "bridge_diag": -2240.0, "bridge_corner": -16.0,
+    },
+    "fd": {
+        "source": "test/fd/derivatives.jl:2-22, README.md:86-90,110-114",
+        "cartesian_N3_dx025": {"dv": -32.0, "ev": 16.0},
+        "staggered_N3_rho025": {"ev": [21.3333, 17.0667], "dv_1_uncorrected": -64.0,
+                                 "dv": [None, -35.5556, -33.28], "dv_1_readme_with_Z1": -65.25},
+    },
+}
+
+
+def main():
+    out = {}
+    out["mass_k3_discontinuous"] = {
+        "source": "test/bsplines/splines.jl:11-15",
+        "k": 3, "tt": [0.0, 1, 1, 3, 4, 6], "ml": 1, "mr": 3,
+        "matrix": parse_rational_block(grab("test/bsplines/splines.jl", 11, 15)),
+    }
+    d = "test/bsplines/derivatives.jl"
+    names = [
+        ("k3_D", dict(kl=3, kr=3, a=0, b=1)),
+        ("k3_DD", dict(kl=3, kr=3, a=1, b=1)),
+        ("k34_D", dict(kl=3, kr=4, a=0, b=1)),
+        ("k34_DD", dict(kl=3, kr=4, a=1, b=1)),
+        ("k43_D", dict(kl=4, kr=3, a=0, b=1)),
+        ("k43_DD", dict(kl=4, kr=3, a=1, b=1)),
+        ("k7_D", dict(kl=7, kr=7, a=0, b=1)),
+        ("k7_DD", dict(kl=7, kr=7, a=1, b=1)),
+        ("k7_12", dict(kl=7, kr=7, a=1, b=2)),
+        ("k7_22", dict(kl=7, kr=7, a=2, b=2)),
+        ("k7_23", dict(kl=7, kr=7, a=2, b=3)),
+        ("k7_33", dict(kl=7, kr=7, a=3, b=3)),
+    ]
+    with open(os.path.join(REF, d), encoding="utf-8") as f:
+        src = f.read().split("\n")
+    blocks = []
+    i = 0
+    while i < len(src):
+        if "@test" in src[i] and "[" in src[i] and "//" in src[i]:
+            j = i
+            while "]" not in src[j]:
+                j += 1
+            blocks.append((i + 1, j + 1))
+            i = j
+        elif "@test" in src[i] and src[i].rstrip().endswith("≈"):
+            # `@test diffop!(...) ≈` with the matrix starting on the next line
+            j = i + 1
+            while "]" not in src[j]:
+                j += 1
+            blocks.append((i + 2, j + 1))
+            i = j
+        i += 1
+    assert len(blocks) == len(names), (len(blocks), blocks)
+    for (name, meta), (lo, hi) in zip(names, blocks):
+        rows = parse_rational_block(src[lo - 1:hi])
+        n0 = len(rows[0])
+        assert all(len(r) == n0 for r in rows), (name, [len(r) for r in rows])
+        N = 3 if name.startswith("k7") else 2
+        out[name] = dict(source=f"{d}:{lo}-{hi}", N=N, a0=0, b0=1, matrix=rows, **meta)
+    out["docs"] = DOCS
+    with open(os.path.join(HERE, "bspline_rationals.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    for k, v in out.items():
+        if "matrix" not in v:
+            continue
+        print(k, len(v["matrix"]), "x", len(v["matrix"][0]))
+        # sanity: exact values parse
+        Fraction(*v["matrix"][0][0])
+
+
+if __name__ == "__main__":
+    main()
