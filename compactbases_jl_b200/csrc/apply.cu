@@ -1,0 +1,565 @@
+// apply.cu — Y = alpha*A*X + beta*Y for the operator containers of the hot path
+// (SURVEY §8 a17): Tridiagonal/SymTridiagonal (K9), BandedMatrix (K7), Diagonal,
+// and the FE-DVR element-block operator (K8).  The arithmetic of mul! lives in
+// LinearAlgebra / BandedMatrices / BlockBandedMatrices in the reference (call
+// sites src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46,
+// test/derivative_accuracy_utils.jl:26-37).
+//
+// All kernels are HBM-bound stencils over X (n x nvec, column-major).  Common
+// shape: a CTA owns a (row tile) x (vector tile); X is read coalesced along the
+// rows; for the wide stencils the tile is staged in shared memory with an odd
+// pitch and consumed with lanes <-> vectors, so that operator entries are
+// warp-uniform (broadcast) shared-memory reads and every X value is reused from
+// registers.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// K9: tridiagonal.  thread <-> row pair, loop over the vectors of the CTA's
+// vector group; neighbours come from warp shuffles (one 16-byte load per lane).
+// ---------------------------------------------------------------------------
+constexpr int TRI_THREADS = 256;
+constexpr int TRI_VUNROLL = 4;
+
+template <bool VEC2>
+__global__ void __launch_bounds__(TRI_THREADS)
+tridiag_apply_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                     const double *__restrict__ du, i64 n,
+                     const double *__restrict__ X, i64 ldx, i64 nvec, i64 vgroup,
+                     double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    constexpr int RPT = VEC2 ? 2 : 1;              // rows per thread
+    const int lane = threadIdx.x & 31;
+    const i64 rows_per_blk = (i64)TRI_THREADS * RPT;
+    const i64 nrblk = (n + rows_per_blk - 1) / rows_per_blk;
+    const i64 v0 = (i64)blockIdx.y * vgroup;
+    const i64 v1 = v0 + vgroup < nvec ? v0 + vgroup : nvec;
+    for (i64 rb = blockIdx.x; rb < nrblk; rb += gridDim.x) {
+        const i64 i0 = rb * rows_per_blk + (i64)threadIdx.x * RPT;   // first row of this thread
+        double cl[RPT], cd[RPT], cu[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            i64 i = i0 + r;
+            cd[r] = i < n ? d[i] : 0.0;
+            cl[r] = (i > 0 && i < n) ? dl[i - 1] : 0.0;
+            cu[r] = (i < n - 1) ? du[i] : 0.0;
+        }
+        for (i64 vb = v0; vb < v1; vb += TRI_VUNROLL) {
+            double xa[TRI_VUNROLL][RPT], xm[TRI_VUNROLL], xp[TRI_VUNROLL];
+#pragma unroll
+            for (int s = 0; s < TRI_VUNROLL; ++s) {
+                const i64 v = vb + s;
+                const double *xc = X + v * ldx;
+                xm[s] = 0.0; xp[s] = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) xa[s][r] = 0.0;
+                if (v < v1) {
+                    if (VEC2) {
+                        if (i0 + 1 < n) {
+                            double2 t = *reinterpret_cast<const double2 *>(xc + i0);
+                            xa[s][0] = t.x; xa[s][RPT - 1] = t.y;
+                        } else if (i0 < n) {
+                            xa[s][0] = xc[i0];
+                        }
+                    } else if (i0 < n) {
+                        xa[s][0] = xc[i0];
+                    }
+                    // halo rows of the warp: lane 0 needs x[i0-1], lane 31 needs x[i0+RPT]
+                    if (lane == 0 && i0 > 0 && i0 - 1 < n) xm[s] = xc[i0 - 1];
+                    if (lane == 31 && i0 + RPT < n) xp[s] = xc[i0 + RPT];
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < TRI_VUNROLL; ++s) {
+                const i64 v = vb + s;
+                double up = __shfl_up_sync(0xffffffffu, xa[s][RPT - 1], 1);
+                double dn = __shfl_down_sync(0xffffffffu, xa[s][0], 1);
+                if (lane != 0) xm[s] = up;
+                if (lane != 31) xp[s] = dn;
+                if (v < v1) {
+                    double *yc = Y + v * ldy;
+                    double yv[RPT];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        double left = r == 0 ? xm[s] : xa[s][r - 1];
+                        double right = r == RPT - 1 ? xp[s] : xa[s][r + 1];
+                        yv[r] = fma(cu[r], right, fma(cd[r], xa[s][r], cl[r] * left));
+                    }
+                    if (VEC2 && i0 + 1 < n) {
+                        double2 o;
+                        if (beta == 0.0) {
+                            o.x = alpha * yv[0]; o.y = alpha * yv[RPT - 1];
+                        } else {
+                            double2 y0 = *reinterpret_cast<const double2 *>(yc + i0);
+                            o.x = fma(alpha, yv[0], beta * y0.x); o.y = fma(alpha, yv[RPT - 1], beta * y0.y);
+                        }
+                        *reinterpret_cast<double2 *>(yc + i0) = o;
+                    } else if (i0 < n) {
+                        yc[i0] = axpby(yv[0], alpha, beta, yc + i0);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Diagonal operator.
+__global__ void diag_apply_kernel(const double *__restrict__ d, i64 n, const double *__restrict__ X, i64 ldx,
+                                  i64 nvec, double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    for (i64 v = blockIdx.y; v < nvec; v += gridDim.y)
+        for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+            Y[i + ldy * v] = axpby(d[i] * X[i + ldx * v], alpha, beta, Y + i + ldy * v);
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory tile helpers (rows x TV vectors, xs[v*pitch + row]).
+// ---------------------------------------------------------------------------
+// Loads global rows [g0, g0+rows) (zero outside [0, n)) of vectors [v0, v0+TV).
+template <int THREADS>
+__device__ __forceinline__ void load_tile(double *xs, int pitch, const double *__restrict__ X, i64 ldx, i64 n,
+                                          i64 g0, int rows, i64 v0, int tv, i64 nvec) {
+    for (int v = 0; v < tv; ++v) {
+        const i64 gv = v0 + v;
+        const double *xc = X + gv * ldx;
+        for (int r = threadIdx.x; r < rows; r += THREADS) {
+            i64 g = g0 + r;
+            xs[v * pitch + r] = (gv < nvec && g >= 0 && g < n) ? xc[g] : 0.0;
+        }
+    }
+}
+
+// Stores tile rows [r_lo, r_hi) (tile-local) to global rows g0+r with alpha/beta.
+template <int THREADS>
+__device__ __forceinline__ void store_tile(const double *ys, int pitch, double *__restrict__ Y, i64 ldy, i64 n,
+                                           i64 g0, int r_lo, int r_hi, i64 v0, int tv, i64 nvec,
+                                           double alpha, double beta) {
+    for (int v = 0; v < tv; ++v) {
+        const i64 gv = v0 + v;
+        if (gv >= nvec) break;
+        double *yc = Y + gv * ldy;
+        for (int r = r_lo + threadIdx.x; r < r_hi; r += THREADS) {
+            i64 g = g0 + r;
+            if (g >= 0 && g < n) yc[g] = axpby(ys[v * pitch + r], alpha, beta, yc + g);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x BT_VEC vectors.  Thread =
+// (vector lane, row group of BR rows): sweeps the BR+l+u window of x once,
+// each x value feeding up to BR accumulators; the band tile sits in shared
+// memory zero-padded so that no predicate is needed in the inner loop.
+// ---------------------------------------------------------------------------
+constexpr int BT_THREADS = 256;
+constexpr int BT_VEC = 32;                          // vectors per CTA (= one warp wide)
+constexpr int BR = 8;                               // rows per thread
+constexpr int BT_ROWS = (BT_THREADS / BT_VEC) * BR; // 64 rows per CTA tile
+
+__global__ void __launch_bounds__(BT_THREADS)
+banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
+                    const double *__restrict__ X, i64 ldx, i64 nvec,
+                    double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    extern __shared__ double sm[];
+    const int W = l + u + 1;
+    const int xrows = BT_ROWS + l + u;
+    const int pitch = xrows | 1;
+    double *xs = sm;                                // [BT_VEC][pitch]
+    double *as = xs + BT_VEC * pitch;               // [BT_ROWS / BR][BR + W - 1][BR], zero padded
+    const int acols = BR + W - 1;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
+    const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
+    for (i64 tile = blockIdx.x; tile < nrt * nvt; tile += gridDim.x) {
+        const i64 rt = tile / nvt, vt = tile - rt * nvt;
+        const i64 i0 = rt * BT_ROWS;                // first row of the tile
+        const i64 v0 = vt * BT_VEC;
+        __syncthreads();                            // previous tile fully consumed
+        // x window rows i0-l .. i0+BT_ROWS-1+u  (columns of A)
+        load_tile<BT_THREADS>(xs, pitch, X, ldx, n, i0 - l, xrows, v0, BT_VEC, nvec);
+        // band tile: as[g][c][r] = A(i0+g*BR+r, i0+g*BR-l+c), 0 outside band/matrix
+        for (int e = threadIdx.x; e < (BT_ROWS / BR) * acols * BR; e += BT_THREADS) {
+            int r = e % BR, c = (e / BR) % acols, g = e / (BR * acols);
+            i64 i = i0 + g * BR + r, j = i0 + g * BR - l + c;
+            double a = 0.0;
+            if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = band[(u + i - j) + (i64)W * j];
+            as[e] = a;
+        }
+        __syncthreads();
+        double acc[BR];
+#pragma unroll
+        for (int r = 0; r < BR; ++r) acc[r] = 0.0;
+        const double *xv = xs + lane * pitch + rg * BR;          // x window of this row group
+        const double *ag = as + rg * acols * BR;
+        for (int c = 0; c < acols; ++c) {
+            const double xc = xv[c];
+            const double2 *a2 = reinterpret_cast<const double2 *>(ag + c * BR);
+#pragma unroll
+            for (int r2 = 0; r2 < BR / 2; ++r2) {
+                double2 a = a2[r2];
+                acc[2 * r2] = fma(a.x, xc, acc[2 * r2]);
+                acc[2 * r2 + 1] = fma(a.y, xc, acc[2 * r2 + 1]);
+            }
+        }
+        __syncthreads();                            // everyone done reading xs
+#pragma unroll
+        for (int r = 0; r < BR; ++r) xs[lane * pitch + rg * BR + r] = acc[r];   // tile-local row index
+        __syncthreads();
+        store_tile<BT_THREADS>(xs, pitch, Y, ldy, m, i0, 0, BT_ROWS, v0, BT_VEC, nvec, alpha, beta);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K8: FE-DVR element-block operator, uniform order O (compile time).
+// CTA tile: FE_ET elements x FE_TV vectors; thread = (vector lane, element group).
+// Tile rows (local r <-> global node  gbase + r):
+//   elements eA..eA+FE_ET-1 occupy rows 0..FE_ET*(O-1); the halo element
+//   eA+FE_ET (needed for the last bridge row) adds O-1 more rows.
+// A thread owns, for each of its elements, local rows 1..O-1 (the bridge row at
+// the end is shared with the next element, whose first matrix row it adds);
+// global row 0 is owned by the very first element.
+// ---------------------------------------------------------------------------
+constexpr int FE_THREADS = 256;
+constexpr int FE_TV = 64;                           // vectors per CTA
+constexpr int FE_NG = FE_THREADS / FE_TV;           // element groups per CTA (4)
+
+template <int O, int EG>   // EG elements per thread
+__global__ void __launch_bounds__(FE_THREADS)
+fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
+                   const double *__restrict__ X, i64 ldx, i64 nvec,
+                   double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    constexpr int ET = FE_NG * EG;                  // elements per CTA tile
+    constexpr int ROWS = (ET + 1) * (O - 1) + 1;    // incl. halo element
+    constexpr int PITCH = ROWS | 1;
+    extern __shared__ double sm[];
+    double *xs = sm;                                // [FE_TV][PITCH]
+    double *bs = xs + FE_TV * PITCH;                // [(ET+1)][O*O] column-major blocks
+    const int vl = threadIdx.x % FE_TV, g = threadIdx.x / FE_TV;
+    const i64 net = (nel + ET - 1) / ET;
+    const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
+    for (i64 tile = blockIdx.x; tile < net * nvt; tile += gridDim.x) {
+        const i64 et = tile / nvt, vt = tile - et * nvt;
+        const i64 eA = et * ET;
+        const i64 v0 = vt * FE_TV;
+        const i64 gbase = eA * (O - 1);             // global node of tile row 0
+        __syncthreads();
+        // X rows are indexed relative to the restriction: X row = node - first0
+        load_tile<FE_THREADS>(xs, PITCH, X, ldx, nrows, gbase - first0, ROWS, v0, FE_TV, nvec);
+        for (int e = threadIdx.x; e < (ET + 1) * O * O; e += FE_THREADS) {
+            i64 el = eA + e / (O * O);
+            bs[e] = el < nel ? blocks[el * (O * O) + e % (O * O)] : 0.0;
+        }
+        __syncthreads();
+        double *xv = xs + vl * PITCH;
+        const int eL0 = g * EG;                     // first tile-local element of this thread
+        // phase 1: values other threads will overwrite in phase 2
+        double x0 = xv[eL0 * (O - 1)];              // x at the first node of my first element
+        double halo = 0.0;                          // first matrix row of the element after my last
+        {
+            const int eh = eL0 + EG;
+            const double *bh = bs + eh * O * O;
+            const double *xh = xv + eh * (O - 1);
+#pragma unroll
+            for (int mp = 0; mp < O; ++mp) halo = fma(bh[O * mp], xh[mp], halo);
+        }
+        __syncthreads();
+        // phase 2: own elements, results written in place over my own rows
+        double carry = 0.0;                         // contribution of the previous element to its bridge row
+        double y_first = 0.0;
+#pragma unroll
+        for (int s = 0; s < EG; ++s) {
+            const int eL = eL0 + s;
+            const double *b = bs + eL * O * O;
+            double *xe = xv + eL * (O - 1);
+            double xr[O], acc[O];
+            xr[0] = x0;
+#pragma unroll
+            for (int mp = 1; mp < O; ++mp) xr[mp] = xe[mp];
+#pragma unroll
+            for (int mm = 0; mm < O; ++mm) acc[mm] = 0.0;
+#pragma unroll
+            for (int mp = 0; mp < O; ++mp) {
+#pragma unroll
+                for (int mm = 0; mm < O; ++mm) acc[mm] = fma(b[mm + O * mp], xr[mp], acc[mm]);
+            }
+            if (s == 0) y_first = acc[0];           // row 0 of my first element (owned by the group before me)
+            else xe[0] = carry + acc[0];            // bridge row between my elements s-1 and s
+#pragma unroll
+            for (int mm = 1; mm < O - 1; ++mm) xe[mm] = acc[mm];
+            carry = acc[O - 1];
+            x0 = xr[O - 1];
+        }
+        xv[(eL0 + EG) * (O - 1)] = carry + halo;   // my last bridge row
+        // global row 0 has no previous element: only the first group of the first tile writes it
+        if (eA == 0 && g == 0) xv[0] = y_first;
+        __syncthreads();
+        // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
+        int r_lo = (eA == 0) ? 0 : 1;
+        i64 last_el = eA + ET < nel ? eA + ET : nel;            // elements actually present
+        int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
+        store_tile<FE_THREADS>(xs, PITCH, Y, ldy, nrows, gbase - first0, r_lo, r_hi, v0, FE_TV, nvec, alpha, beta);
+    }
+}
+
+// Generic FE-DVR apply (per-element orders): thread per (row, vector); each row
+// gathers from the one or two elements that contain it.  rowmap[i] = element of
+// node i as owner (the element where it is NOT the first node, except node 0).
+__global__ void fedvr_apply_generic_kernel(const double *__restrict__ blocks, const i64 *__restrict__ estart,
+                                           const int32_t *__restrict__ order, const i64 *__restrict__ boff,
+                                           i64 nel, i64 first0, i64 nrows,
+                                           const double *__restrict__ X, i64 ldx, i64 nvec,
+                                           double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    for (i64 v = blockIdx.y; v < nvec; v += gridDim.y) {
+        const double *xc = X + v * ldx;
+        for (i64 r = blockIdx.x * (i64)blockDim.x + threadIdx.x; r < nrows; r += (i64)gridDim.x * blockDim.x) {
+            const i64 node = r + first0;
+            // last element whose first node is <= node
+            i64 lo = 0, hi = nel;
+            while (lo < hi) { i64 mid = (lo + hi) >> 1; if (estart[mid] <= node) lo = mid + 1; else hi = mid; }
+            i64 e = lo - 1;
+            double s = 0.0;
+            for (int pass = 0; pass < 2; ++pass) {
+                // pass 0: element e (node is local row node-estart[e]);
+                // pass 1: element e-1 if node is also its last node (bridge)
+                i64 el = pass == 0 ? e : e - 1;
+                if (el < 0 || el >= nel) continue;
+                int o = order[el];
+                i64 loc = node - estart[el];
+                if (loc < 0 || loc >= o) continue;
+                if (pass == 1 && loc != o - 1) continue;
+                const double *b = blocks + boff[el];
+                for (int mp = 0; mp < o; ++mp) {
+                    i64 xr = estart[el] + mp - first0;
+                    double xval = (xr >= 0 && xr < nrows) ? xc[xr] : 0.0;
+                    s = fma(b[loc + (i64)o * mp], xval, s);
+                }
+            }
+            Y[r + ldy * v] = axpby(s, alpha, beta, Y + r + ldy * v);
+        }
+    }
+}
+
+// Dense export of the (restricted) operator.
+__global__ void fedvr_to_dense_kernel(const double *__restrict__ blocks, const i64 *__restrict__ estart,
+                                      const int32_t *__restrict__ order, const i64 *__restrict__ boff,
+                                      i64 nel, i64 first0, i64 nrows, double *__restrict__ A) {
+    // one block per element; A must be zero-initialised; bridge corners via atomicAdd
+    for (i64 e = blockIdx.x; e < nel; e += gridDim.x) {
+        int o = order[e];
+        const double *b = blocks + boff[e];
+        for (int t = threadIdx.x; t < o * o; t += blockDim.x) {
+            int mm = t % o, mp = t / o;
+            i64 gi = estart[e] + mm - first0, gj = estart[e] + mp - first0;
+            if (gi < 0 || gi >= nrows || gj < 0 || gj >= nrows) continue;
+            bool shared_corner = (mm == mp) && ((mm == 0 && e > 0) || (mm == o - 1 && e < nel - 1));
+            if (shared_corner) atomicAdd(&A[gi + nrows * gj], b[t]);
+            else A[gi + nrows * gj] = b[t];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int check_apply_args(const char *who, i64 m, i64 n, const double *X, i64 ldx, i64 nvec, double *Y, i64 ldy) {
+    CB_REQUIRE(m >= 0 && n >= 0 && nvec >= 0, "%s: negative size", who);
+    CB_REQUIRE(X != nullptr && Y != nullptr, "%s: NULL array", who);
+    // DimensionMismatch in the reference's mul!
+    CB_REQUIRE(ldx >= n && ldy >= m, "%s: leading dimension smaller than the number of rows (ldx=%lld n=%lld ldy=%lld m=%lld)",
+               who, (long long)ldx, (long long)n, (long long)ldy, (long long)m);
+    return CB_OK;
+}
+
+template <int O>
+static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, const double *X, i64 ldx, i64 nvec,
+                        double alpha, double beta, double *Y, i64 ldy, cudaStream_t st) {
+    // elements per thread: keep the tile near 150 rows
+    constexpr int EG = (O <= 3) ? 16 : (O <= 5) ? 8 : (O <= 10) ? 4 : 2;
+    constexpr int ET = FE_NG * EG;
+    constexpr int ROWS = (ET + 1) * (O - 1) + 1;
+    constexpr int PITCH = ROWS | 1;
+    size_t smem = sizeof(double) * ((size_t)FE_TV * PITCH + (size_t)(ET + 1) * O * O);
+    auto kern = fedvr_apply_kernel<O, EG>;
+    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
+    int grid = (int)(tiles < (i64)CB_NUM_SMS * 16 ? tiles : (i64)CB_NUM_SMS * 16);
+    kern<<<grid, FE_THREADS, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" {
+
+int cb_tridiag_apply(const double *dl, const double *d, const double *du, i64 n,
+                     const double *X, i64 ldx, i64 nvec, double alpha, double beta,
+                     double *Y, i64 ldy, void *stream) {
+    int rc = check_apply_args("cb_tridiag_apply", n, n, X, ldx, nvec, Y, ldy);
+    if (rc) return rc;
+    if (n == 0 || nvec == 0) return CB_OK;
+    CB_REQUIRE(d != nullptr && (n == 1 || (dl != nullptr && du != nullptr)), "cb_tridiag_apply: NULL diagonal");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool vec2 = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
+    i64 rows_per_blk = (i64)TRI_THREADS * (vec2 ? 2 : 1);
+    i64 nrblk = (n + rows_per_blk - 1) / rows_per_blk;
+    // vector groups: enough CTAs to fill the machine, coefficients reused across the group
+    i64 vgroup = 32;
+    while (vgroup > 4 && nrblk * ((nvec + vgroup - 1) / vgroup) < (i64)CB_NUM_SMS * 8) vgroup /= 2;
+    i64 gy = (nvec + vgroup - 1) / vgroup;
+    if (gy > 65535) { vgroup = (nvec + 65534) / 65535; vgroup = (vgroup + TRI_VUNROLL - 1) / TRI_VUNROLL * TRI_VUNROLL; gy = (nvec + vgroup - 1) / vgroup; }
+    i64 gx = nrblk;
+    i64 cap = ((i64)CB_NUM_SMS * 16 + gy - 1) / gy; if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec2)
+        tridiag_apply_kernel<true><<<grid, TRI_THREADS, 0, st>>>(dl, d, du, n, X, ldx, nvec, vgroup, alpha, beta, Y, ldy);
+    else
+        tridiag_apply_kernel<false><<<grid, TRI_THREADS, 0, st>>>(dl, d, du, n, X, ldx, nvec, vgroup, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_diag_apply(const double *d, i64 n, const double *X, i64 ldx, i64 nvec,
+                  double alpha, double beta, double *Y, i64 ldy, void *stream) {
+    int rc = check_apply_args("cb_diag_apply", n, n, X, ldx, nvec, Y, ldy);
+    if (rc) return rc;
+    if (n == 0 || nvec == 0) return CB_OK;
+    CB_REQUIRE(d != nullptr, "cb_diag_apply: NULL diagonal");
+    dim3 grid((unsigned)cb_grid_for(n, 256, 4), (unsigned)(nvec < 4096 ? nvec : 4096));
+    diag_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, n, X, ldx, nvec, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
+                    const double *X, i64 ldx, i64 nvec, double alpha, double beta,
+                    double *Y, i64 ldy, void *stream) {
+    int rc = check_apply_args("cb_banded_apply", m, n, X, ldx, nvec, Y, ldy);
+    if (rc) return rc;
+    CB_REQUIRE(band != nullptr, "cb_banded_apply: NULL band");
+    CB_REQUIRE(l + u + 1 >= 1 && l > -n - 1 && u > -m - 1, "cb_banded_apply: invalid bandwidths (%d,%d)", l, u);
+    if (m == 0 || nvec == 0) return CB_OK;
+    // BandedMatrices allows negative l or u (bands entirely above/below the diagonal, e.g.
+    // src/fd_operators.jl:16); the window arithmetic below is valid for them as long as l+u >= 0.
+    const int W = l + u + 1;
+    const int xrows = BT_ROWS + l + u;
+    const int pitch = xrows | 1;
+    size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)(BT_ROWS / BR) * (BR + W - 1) * BR);
+    if (smem > 200 * 1024) { cb_set_error("cb_banded_apply: bandwidth %d too large for the shared-memory tile", W); return CB_ERR_UNSUPPORTED; }
+    CB_CUDA(cudaFuncSetAttribute(banded_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    i64 tiles = ((m + BT_ROWS - 1) / BT_ROWS) * ((nvec + BT_VEC - 1) / BT_VEC);
+    int grid = (int)(tiles < (i64)CB_NUM_SMS * 16 ? tiles : (i64)CB_NUM_SMS * 16);
+    banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_fedvr_apply(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                   i64 nel, int uniform_order, i64 first, i64 last,
+                   const double *X, i64 ldx, i64 nvec, double alpha, double beta,
+                   double *Y, i64 ldy, void *stream) {
+    CB_REQUIRE(blocks != nullptr && nel >= 1, "cb_fedvr_apply: NULL blocks / no elements");
+    CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_apply: invalid restriction %lld..%lld", (long long)first, (long long)last);
+    const i64 nrows = last - first + 1;
+    int rc = check_apply_args("cb_fedvr_apply", nrows, nrows, X, ldx, nvec, Y, ldy);
+    if (rc) return rc;
+    if (nvec == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const i64 first0 = first - 1;
+    if (uniform_order > 0) {
+        CB_REQUIRE(uniform_order >= 2, "cb_fedvr_apply: element order must be >= 2");
+        CB_REQUIRE(last <= nel * (uniform_order - 1) + 1, "cb_fedvr_apply: restriction exceeds the basis");
+        switch (uniform_order) {
+#define CB_FE(OO) case OO: return launch_fedvr<OO>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy, st);
+            CB_FE(2) CB_FE(3) CB_FE(4) CB_FE(5) CB_FE(6) CB_FE(7) CB_FE(8) CB_FE(9) CB_FE(10)
+            CB_FE(11) CB_FE(12) CB_FE(13) CB_FE(14) CB_FE(15) CB_FE(16)
+#undef CB_FE
+            default: break;                         // fall through to the generic kernel
+        }
+    }
+    CB_REQUIRE(estart != nullptr && order != nullptr && boff != nullptr,
+               "cb_fedvr_apply: per-element arrays required for non-uniform / large orders");
+    dim3 grid((unsigned)cb_grid_for(nrows, 128, 8), (unsigned)(nvec < 2048 ? nvec : 2048));
+    fedvr_apply_generic_kernel<<<grid, 128, 0, st>>>(blocks, estart, order, boff, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                      i64 nel, i64 first, i64 last, double *A, void *stream) {
+    CB_REQUIRE(blocks && estart && order && boff && A, "cb_fedvr_to_dense: NULL argument");
+    CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_to_dense: invalid restriction");
+    const i64 nrows = last - first + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CB_CUDA(cudaMemsetAsync(A, 0, sizeof(double) * nrows * nrows, st));
+    fedvr_to_dense_kernel<<<(unsigned)(nel < 4096 ? nel : 4096), 128, 0, st>>>(blocks, estart, order, boff, nel, first - 1, nrows, A);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// ---- host-buffer forms: stream the vector batch through the device ----------
+typedef int (*apply_dev_fn)(void *ctx, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st);
+
+static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows, const double *Xh, i64 ldx, i64 nvec,
+                               double alpha, double beta, double *Yh, i64 ldy) {
+    if (nvec == 0 || nrows == 0) return CB_OK;
+    const int NBUF = 3;
+    // tile of vectors: ~64 MB per buffer
+    i64 tv = (i64)(64ll << 20) / (nrows * (i64)sizeof(double));
+    if (tv < 1) tv = 1;
+    if (tv > nvec) tv = nvec;
+    const i64 ld = nrows + (nrows & 1);             // even leading dimension on the device
+    cudaStream_t st[NBUF]; double *dX[NBUF] = {nullptr}, *dY[NBUF] = {nullptr};
+    int rc = CB_OK; cudaError_t e = cudaSuccess;
+    for (int b = 0; b < NBUF && e == cudaSuccess; ++b) {
+        e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&dX[b], sizeof(double) * ld * tv);
+        if (e == cudaSuccess) e = cudaMalloc(&dY[b], sizeof(double) * ld * tv);
+    }
+    i64 t = 0;
+    for (i64 v0 = 0; v0 < nvec && e == cudaSuccess && rc == CB_OK; v0 += tv, ++t) {
+        int b = (int)(t % NBUF);
+        i64 nv = v0 + tv <= nvec ? tv : nvec - v0;
+        e = cudaMemcpy2DAsync(dX[b], sizeof(double) * ld, Xh + v0 * ldx, sizeof(double) * ldx, sizeof(double) * nrows, nv,
+                              cudaMemcpyHostToDevice, st[b]);
+        if (e == cudaSuccess && beta != 0.0)
+            e = cudaMemcpy2DAsync(dY[b], sizeof(double) * ld, Yh + v0 * ldy, sizeof(double) * ldy, sizeof(double) * nrows, nv,
+                                  cudaMemcpyHostToDevice, st[b]);
+        if (e == cudaSuccess) rc = fn(ctx, dX[b], ld, nv, alpha, beta, dY[b], st[b]);
+        if (e == cudaSuccess && rc == CB_OK)
+            e = cudaMemcpy2DAsync(Yh + v0 * ldy, sizeof(double) * ldy, dY[b], sizeof(double) * ld, sizeof(double) * nrows, nv,
+                                  cudaMemcpyDeviceToHost, st[b]);
+    }
+    for (int b = 0; b < NBUF; ++b) {
+        if (st[b]) { cudaError_t e2 = cudaStreamSynchronize(st[b]); if (e == cudaSuccess) e = e2; cudaStreamDestroy(st[b]); }
+        cudaFree(dX[b]); cudaFree(dY[b]);
+    }
+    if (e != cudaSuccess) { cb_set_error("host pipeline: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return rc;
+}
+
+struct fedvr_ctx { const double *blocks; const i64 *estart; const int32_t *order; const i64 *boff; i64 nel; int uo; i64 first, last; };
+static int fedvr_dev(void *c, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st) {
+    fedvr_ctx *f = (fedvr_ctx *)c;
+    return cb_fedvr_apply(f->blocks, f->estart, f->order, f->boff, f->nel, f->uo, f->first, f->last, Xd, ld, nv, alpha, beta, Yd, ld, st);
+}
+
+int cb_fedvr_apply_host(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                        i64 nel, int uniform_order, i64 first, i64 last,
+                        const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy) {
+    CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_apply_host: invalid restriction");
+    CB_REQUIRE(Xh && Yh && ldx >= last - first + 1 && ldy >= last - first + 1, "cb_fedvr_apply_host: bad host arrays");
+    fedvr_ctx c{blocks, estart, order, boff, nel, uniform_order, first, last};
+    return apply_host_pipeline(fedvr_dev, &c, last - first + 1, Xh, ldx, nvec, alpha, beta, Yh, ldy);
+}
+
+struct tri_ctx { const double *dl, *d, *du; i64 n; };
+static int tri_dev(void *c, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st) {
+    tri_ctx *t = (tri_ctx *)c;
+    return cb_tridiag_apply(t->dl, t->d, t->du, t->n, Xd, ld, nv, alpha, beta, Yd, ld, st);
+}
+
+int cb_tridiag_apply_host(const double *dl, const double *d, const double *du, i64 n,
+                          const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy) {
+    CB_REQUIRE(Xh && Yh && ldx >= n && ldy >= n, "cb_tridiag_apply_host: bad host arrays");
+    tri_ctx c{dl, d, du, n};
+    return apply_host_pipeline(tri_dev, &c, n, Xh, ldx, nvec, alpha, beta, Yh, ldy);
+}
+
+}  // extern "C"

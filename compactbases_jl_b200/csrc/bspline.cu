@@ -1,0 +1,392 @@
+// bspline.cu — B-spline basis handle, lgwt, batched evaluation (K1), CSC export
+// (K1b), fused spline evaluation and quadrature tables (K2).
+#include <cub/cub.cuh>
+
+#include "bspline_core.cuh"
+
+#define CB_DISPATCH_K(kval, ...)                                                 \
+    switch (kval) {                                                              \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;                     \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;                     \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;                     \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;                     \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;                     \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;                     \
+        case 7: { constexpr int K = 7; __VA_ARGS__; } break;                     \
+        case 8: { constexpr int K = 8; __VA_ARGS__; } break;                     \
+        case 9: { constexpr int K = 9; __VA_ARGS__; } break;                     \
+        case 10: { constexpr int K = 10; __VA_ARGS__; } break;                   \
+        case 11: { constexpr int K = 11; __VA_ARGS__; } break;                   \
+        case 12: { constexpr int K = 12; __VA_ARGS__; } break;                   \
+        case 13: { constexpr int K = 13; __VA_ARGS__; } break;                   \
+        case 14: { constexpr int K = 14; __VA_ARGS__; } break;                   \
+        case 15: { constexpr int K = 15; __VA_ARGS__; } break;                   \
+        case 16: { constexpr int K = 16; __VA_ARGS__; } break;                   \
+        default:                                                                 \
+            cb_set_error("B-spline order k=%d outside compiled range 1..%d", kval, CB_KMAX); \
+            return CB_ERR_UNSUPPORTED;                                           \
+    }
+
+// ---------------------------------------------------------------------------
+// lgwt (src/quadrature.jl:60-77, change_interval! :18-23, lerp :4)
+// ---------------------------------------------------------------------------
+__global__ void lgwt_kernel(KnotView kv, const i64 *__restrict__ ivlist, i64 ni,
+                            const double *__restrict__ xi, const double *__restrict__ wr, int q,
+                            double *__restrict__ x, double *__restrict__ w) {
+    i64 tot = ni * q;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < tot; e += (i64)gridDim.x * blockDim.x) {
+        i64 c = e / q;
+        int l = (int)(e - c * q);
+        i64 I = ivlist[c];
+        double a = kv.at(I - 1), b = kv.at(I);
+        double t = (xi[l] + 1.0) / 2.0;
+        x[e] = fma(t, b, fma(-t, a, a));
+        w[e] = (b - a) * wr[l] / 2.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1: batched evaluation, one thread per point, rows staged through shared
+// memory so that the K-wide rows leave the SM as coalesced 16-byte stores.
+// ---------------------------------------------------------------------------
+constexpr int EVAL_THREADS = 256;
+
+template <int K>
+__global__ void __launch_bounds__(EVAL_THREADS)
+bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, int m,
+                    int32_t *__restrict__ interval, double *__restrict__ vals, int vec_ok) {
+    constexpr int KP = K | 1;                      // odd row pitch: conflict-free staging
+    __shared__ double stage[EVAL_THREADS / 32][32 * KP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sw = stage[warp];
+    const i64 nblk = (nx + EVAL_THREADS - 1) / EVAL_THREADS;
+    for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const i64 wbase = blk * EVAL_THREADS + warp * 32;   // first point of this warp
+        const i64 p = wbase + lane;
+        double N[K];
+        int I = 0;
+        if (p < nx) {
+            double xp = x[p];
+            I = cb_find_interval(kv.tt, kv.n_tt, kv.ml, kv.mr, kv.nt, xp);
+            if (I > 0) {
+                double tw[2 * K];
+                cb_knot_window<K>(kv.tt, kv.n_tt, kv.ml, I, tw);
+                cb_bspline_all<K>(tw, xp, m, N);
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    i64 j = (i64)I - K + 1 + r;
+                    if (j < 1 || j > nf) N[r] = 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < K; ++r) N[r] = 0.0;
+            }
+            interval[p] = I;
+        } else {
+#pragma unroll
+            for (int r = 0; r < K; ++r) N[r] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < K; ++r) sw[lane * KP + r] = N[r];
+        __syncwarp();
+        // the warp's 32 rows are 32*K contiguous doubles in vals
+        i64 npts = nx - wbase; npts = npts > 32 ? 32 : (npts < 0 ? 0 : npts);
+        const int tot = (int)npts * K;
+        double *out = vals + wbase * K;             // wbase*K*8 bytes: 16-byte aligned (wbase % 32 == 0)
+        for (int e2 = lane * 2; e2 < tot; e2 += 64) {
+            int r0 = e2 / K, c0 = e2 - r0 * K;
+            double v0 = sw[r0 * KP + c0];
+            if (e2 + 1 < tot && vec_ok) {
+                int r1 = (e2 + 1) / K, c1 = (e2 + 1) - r1 * K;
+                double2 v = make_double2(v0, sw[r1 * KP + c1]);
+                *reinterpret_cast<double2 *>(out + e2) = v;
+            } else {
+                out[e2] = v0;
+                if (e2 + 1 < tot) {
+                    int r1 = (e2 + 1) / K, c1 = (e2 + 1) - r1 * K;
+                    out[e2 + 1] = sw[r1 * KP + c1];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fused spline evaluation (B*C)[x]: thread per point, loop over vectors.
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+bspline_eval_spline_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, int m,
+                           const double *__restrict__ C, i64 ldc, i64 nvec,
+                           double *__restrict__ out, i64 ldo) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < nx; p += (i64)gridDim.x * blockDim.x) {
+        double xp = x[p];
+        int I = cb_find_interval(kv.tt, kv.n_tt, kv.ml, kv.mr, kv.nt, xp);
+        double N[K];
+        if (I > 0) {
+            double tw[2 * K];
+            cb_knot_window<K>(kv.tt, kv.n_tt, kv.ml, I, tw);
+            cb_bspline_all<K>(tw, xp, m, N);
+        }
+        for (i64 v = 0; v < nvec; ++v) {
+            double s = 0.0;
+            if (I > 0) {
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    i64 j = (i64)I - K + 1 + r;
+                    if (j >= 1 && j <= nf) s = fma(N[r], C[(j - 1) + ldc * v], s);
+                }
+            }
+            out[p + ldo * v] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: basis_functions(t, x, m) tables at the quadrature nodes
+// ---------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+bspline_table_kernel(KnotView kv, i64 nf, const i64 *__restrict__ ivlist, i64 ni, int q,
+                     const double *__restrict__ x, int m, double *__restrict__ table) {
+    i64 tot = ni * q;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < tot; e += (i64)gridDim.x * blockDim.x) {
+        i64 c = e / q;
+        int I = (int)ivlist[c];
+        double tw[2 * K], N[K];
+        cb_knot_window<K>(kv.tt, kv.n_tt, kv.ml, I, tw);
+        cb_bspline_all<K>(tw, x[e], m, N);
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            i64 j = (i64)I - K + 1 + r;
+            table[e * K + r] = (j >= 1 && j <= nf) ? N[r] : 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1b: ELL rows -> SparseMatrixCSC (1-based, zeros dropped, rows ascending)
+// ---------------------------------------------------------------------------
+__global__ void csc_keys_kernel(const int32_t *__restrict__ interval, const double *__restrict__ vals,
+                                i64 nx, int k, i64 nf, i64 col0, i64 ncols,
+                                uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    i64 tot = nx * k;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < tot; e += (i64)gridDim.x * blockDim.x) {
+        i64 p = e / k;
+        int a = (int)(e - p * k);
+        int I = interval[p];
+        uint32_t key = (uint32_t)ncols;
+        if (I > 0) {
+            i64 j = (i64)I - k + 1 + a;
+            i64 c = j - 1 - col0;
+            if (j >= 1 && j <= nf && c >= 0 && c < ncols && vals[e] != 0.0) key = (uint32_t)c;
+        }
+        keys[e] = key;
+        idx[e] = (uint32_t)e;
+    }
+}
+
+__global__ void csc_colptr_kernel(const uint32_t *__restrict__ keys_sorted, i64 tot, i64 ncols,
+                                  i64 *__restrict__ colptr) {
+    for (i64 c = blockIdx.x * (i64)blockDim.x + threadIdx.x; c <= ncols; c += (i64)gridDim.x * blockDim.x) {
+        i64 lo = 0, hi = tot;                      // first position with key >= c
+        while (lo < hi) {
+            i64 mid = (lo + hi) >> 1;
+            if (keys_sorted[mid] >= (uint32_t)c) hi = mid; else lo = mid + 1;
+        }
+        colptr[c] = lo + 1;
+    }
+}
+
+__global__ void csc_fill_kernel(const uint32_t *__restrict__ idx_sorted, const double *__restrict__ vals,
+                                const i64 *__restrict__ colptr, i64 ncols, int k,
+                                i64 *__restrict__ rowval, double *__restrict__ nzval) {
+    i64 nnz = colptr[ncols] - 1;
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x) {
+        uint32_t src = idx_sorted[e];
+        rowval[e] = (i64)(src / (uint32_t)k) + 1;
+        nzval[e] = vals[src];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int cb_bspline_create(const double *tt, i64 n_tt, int k, int ml, int mr,
+                      const double *xi, const double *wr, int q, cb_bspline **out) {
+    CB_REQUIRE(out != nullptr, "cb_bspline_create: out is NULL");
+    *out = nullptr;
+    // assert_multiplicities, src/knot_sets.jl:26-33
+    CB_REQUIRE(k > 0, "Polynomial order must be a positive integer, got k = %d", k);
+    CB_REQUIRE(ml >= 1 && ml <= k, "Left multiplicity has to be in range 1..%d, got %d", k, ml);
+    CB_REQUIRE(mr >= 1 && mr <= k, "Right multiplicity has to be in range 1..%d, got %d", k, mr);
+    i64 nreq = 2 > k + 3 - ml - mr ? 2 : k + 3 - ml - mr;
+    CB_REQUIRE(tt != nullptr && n_tt >= nreq,
+               "Polynomial order k = %d and left,right multiplicities %d,%d require a knot sequence of at least %lld points",
+               k, ml, mr, (long long)nreq);
+    CB_REQUIRE(q >= 1 && q <= 64 && xi != nullptr && wr != nullptr, "cb_bspline_create: need 1..64 reference nodes");
+    if (k > CB_KMAX) { cb_set_error("B-spline order k=%d outside compiled range 1..%d", k, CB_KMAX); return CB_ERR_UNSUPPORTED; }
+    for (i64 i = 1; i < n_tt; ++i)
+        CB_REQUIRE(tt[i] >= tt[i - 1], "cb_bspline_create: knots must be non-decreasing (index %lld)", (long long)i);
+
+    cb_bspline_s *B = new cb_bspline_s();
+    B->k = k; B->ml = ml; B->mr = mr; B->q = q;
+    B->n_tt = n_tt; B->nt = n_tt + ml + mr - 2; B->nf = B->nt - k;
+    B->h_tt.assign(tt, tt + n_tt); B->h_xi.assign(xi, xi + q); B->h_wr.assign(wr, wr + q);
+    B->d_tt = B->d_xi = B->d_wr = B->d_x = B->d_w = nullptr; B->d_ivlist = nullptr; B->d_ord = nullptr;
+    // nonempty_intervals (src/knot_sets.jl:196-198) in expanded 1-based numbering:
+    // expanded interval I <-> t.t interval I-(ml-1); the repeated end knots give empty ones.
+    std::vector<int32_t> ord((size_t)B->nt, -1);
+    for (i64 s = 0; s + 1 < n_tt; ++s)
+        if (tt[s] != tt[s + 1]) {
+            i64 I = s + 1 + (ml - 1);
+            ord[(size_t)(I - 1)] = (int32_t)B->h_ivlist.size();
+            B->h_ivlist.push_back(I);
+        }
+    B->ni = (i64)B->h_ivlist.size();
+    int rc = CB_OK;
+    auto fail = [&](int code) { cb_bspline_destroy(B); return code; };
+#define CB_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(CB_ERR_CUDA); } } while (0)
+    CB_TRY(cudaGetDevice(&B->device));
+    CB_TRY(cudaMalloc(&B->d_tt, sizeof(double) * n_tt));
+    CB_TRY(cudaMalloc(&B->d_xi, sizeof(double) * q));
+    CB_TRY(cudaMalloc(&B->d_wr, sizeof(double) * q));
+    CB_TRY(cudaMalloc(&B->d_ivlist, sizeof(i64) * (B->ni ? B->ni : 1)));
+    CB_TRY(cudaMalloc(&B->d_ord, sizeof(int32_t) * B->nt));
+    CB_TRY(cudaMalloc(&B->d_x, sizeof(double) * (B->ni * q ? B->ni * q : 1)));
+    CB_TRY(cudaMalloc(&B->d_w, sizeof(double) * (B->ni * q ? B->ni * q : 1)));
+    CB_TRY(cudaMemcpy(B->d_tt, tt, sizeof(double) * n_tt, cudaMemcpyHostToDevice));
+    CB_TRY(cudaMemcpy(B->d_xi, xi, sizeof(double) * q, cudaMemcpyHostToDevice));
+    CB_TRY(cudaMemcpy(B->d_wr, wr, sizeof(double) * q, cudaMemcpyHostToDevice));
+    if (B->ni) CB_TRY(cudaMemcpy(B->d_ivlist, B->h_ivlist.data(), sizeof(i64) * B->ni, cudaMemcpyHostToDevice));
+    CB_TRY(cudaMemcpy(B->d_ord, ord.data(), sizeof(int32_t) * B->nt, cudaMemcpyHostToDevice));
+    if (B->ni) {
+        lgwt_kernel<<<cb_grid_for(B->ni * q, 256), 256>>>(make_knot_view(B), B->d_ivlist, B->ni, B->d_xi, B->d_wr, q, B->d_x, B->d_w);
+        CB_TRY(cudaGetLastError());
+        CB_TRY(cudaDeviceSynchronize());
+    }
+#undef CB_TRY
+    *out = B;
+    return rc;
+}
+
+int cb_bspline_destroy(cb_bspline *B) {
+    if (!B) return CB_OK;
+    cudaFree(B->d_tt); cudaFree(B->d_xi); cudaFree(B->d_wr); cudaFree(B->d_ivlist);
+    cudaFree(B->d_ord); cudaFree(B->d_x); cudaFree(B->d_w);
+    delete B;
+    return CB_OK;
+}
+
+i64 cb_bspline_numfunctions(const cb_bspline *B) { return B ? B->nf : -1; }
+i64 cb_bspline_numknots(const cb_bspline *B) { return B ? B->nt : -1; }
+i64 cb_bspline_num_nonempty(const cb_bspline *B) { return B ? B->ni : -1; }
+i64 cb_bspline_numnodes(const cb_bspline *B) { return B ? B->ni * B->q : -1; }
+
+int cb_bspline_nodes(const cb_bspline *B, const double **x, const double **w) {
+    CB_REQUIRE(B != nullptr, "cb_bspline_nodes: NULL basis");
+    if (x) *x = B->d_x;
+    if (w) *w = B->d_w;
+    return CB_OK;
+}
+
+int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
+                    int32_t *interval, double *vals, void *stream) {
+    CB_REQUIRE(B != nullptr, "cb_bspline_eval: NULL basis");
+    CB_REQUIRE(nx >= 0 && m >= 0 && m < (B->k > 1 ? B->k : 2), "cb_bspline_eval: need nx >= 0 and 0 <= m < k");
+    if (nx == 0) return CB_OK;
+    CB_REQUIRE(x && interval && vals, "cb_bspline_eval: NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = cb_grid_for(nx, EVAL_THREADS, 16);
+    int vec_ok = ((uintptr_t)vals % 16) == 0;
+    CB_DISPATCH_K(B->k, (bspline_eval_kernel<K><<<grid, EVAL_THREADS, 0, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok)));
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_bspline_eval_host(const cb_bspline *B, const double *xh, i64 nx, int m,
+                         int32_t *ih, double *vh) {
+    CB_REQUIRE(B != nullptr, "cb_bspline_eval_host: NULL basis");
+    if (nx == 0) return CB_OK;
+    double *dx = nullptr, *dv = nullptr; int32_t *di = nullptr;
+    CB_CUDA(cudaMalloc(&dx, sizeof(double) * nx));
+    CB_CUDA(cudaMalloc(&dv, sizeof(double) * nx * B->k));
+    CB_CUDA(cudaMalloc(&di, sizeof(int32_t) * nx));
+    int rc = CB_OK;
+    cudaError_t e = cudaMemcpy(dx, xh, sizeof(double) * nx, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) rc = cb_bspline_eval(B, dx, nx, m, di, dv, nullptr);
+    if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpy(ih, di, sizeof(int32_t) * nx, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpy(vh, dv, sizeof(double) * nx * B->k, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dv); cudaFree(di);
+    if (e != cudaSuccess) { cb_set_error("cb_bspline_eval_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return rc;
+}
+
+int cb_bspline_eval_spline(const cb_bspline *B, const double *x, i64 nx, int m,
+                           const double *C, i64 ldc, i64 nvec, double *out, i64 ldo, void *stream) {
+    CB_REQUIRE(B != nullptr, "cb_bspline_eval_spline: NULL basis");
+    CB_REQUIRE(nx >= 0 && nvec >= 0 && m >= 0 && m < (B->k > 1 ? B->k : 2), "cb_bspline_eval_spline: bad sizes");
+    CB_REQUIRE(ldc >= B->nf && ldo >= nx, "cb_bspline_eval_spline: leading dimensions too small");
+    if (nx == 0 || nvec == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = cb_grid_for(nx, 256, 16);
+    CB_DISPATCH_K(B->k, (bspline_eval_spline_kernel<K><<<grid, 256, 0, st>>>(make_knot_view(B), B->nf, x, nx, m, C, ldc, nvec, out, ldo)));
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_bspline_quad_table(const cb_bspline *B, int m, double *table, void *stream) {
+    CB_REQUIRE(B != nullptr && table != nullptr, "cb_bspline_quad_table: NULL argument");
+    CB_REQUIRE(m >= 0 && m < (B->k > 1 ? B->k : 2), "cb_bspline_quad_table: need 0 <= m < k");
+    if (B->ni == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = cb_grid_for(B->ni * B->q, 256, 16);
+    CB_DISPATCH_K(B->k, (bspline_table_kernel<K><<<grid, 256, 0, st>>>(make_knot_view(B), B->nf, B->d_ivlist, B->ni, B->q, B->d_x, m, table)));
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_bspline_eval_csc(const cb_bspline *B, const double *x, i64 nx, i64 col0, i64 ncols,
+                        i64 *colptr, i64 *rowval, double *nzval, i64 *nnz_host, void *stream) {
+    CB_REQUIRE(B != nullptr && colptr != nullptr, "cb_bspline_eval_csc: NULL argument");
+    CB_REQUIRE(col0 >= 0 && ncols >= 0 && col0 + ncols <= B->nf, "cb_bspline_eval_csc: column range outside 1..nf");
+    i64 tot = nx * B->k;
+    if (tot >= ((i64)1 << 31)) { cb_set_error("cb_bspline_eval_csc: nx*k >= 2^31, split the point batch"); return CB_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *d_iv = nullptr; double *d_vals = nullptr; uint32_t *d_keys = nullptr, *d_idx = nullptr; void *d_tmp = nullptr;
+    i64 n1 = tot ? tot : 1;
+    CB_CUDA(cudaMallocAsync(&d_iv, sizeof(int32_t) * (nx ? nx : 1), st));
+    CB_CUDA(cudaMallocAsync(&d_vals, sizeof(double) * n1, st));
+    CB_CUDA(cudaMallocAsync(&d_keys, sizeof(uint32_t) * 2 * n1, st));
+    CB_CUDA(cudaMallocAsync(&d_idx, sizeof(uint32_t) * 2 * n1, st));
+    int rc = cb_bspline_eval(B, x, nx, 0, d_iv, d_vals, stream);
+    if (rc != CB_OK) return rc;
+    if (tot) {
+        csc_keys_kernel<<<cb_grid_for(tot, 256, 16), 256, 0, st>>>(d_iv, d_vals, nx, B->k, B->nf, col0, ncols, d_keys, d_idx);
+        CB_LAUNCH_CHECK();
+        int end_bit = 1; while (((i64)1 << end_bit) <= ncols) ++end_bit;
+        size_t tmp_bytes = 0;
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys + n1, d_idx, d_idx + n1, (int)tot, 0, end_bit, st));
+        CB_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st));
+        CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys + n1, d_idx, d_idx + n1, (int)tot, 0, end_bit, st));
+    }
+    csc_colptr_kernel<<<cb_grid_for(ncols + 1, 256), 256, 0, st>>>(d_keys + n1, tot, ncols, colptr);
+    CB_LAUNCH_CHECK();
+    if (tot && rowval && nzval) {
+        csc_fill_kernel<<<cb_grid_for(tot, 256, 16), 256, 0, st>>>(d_idx + n1, d_vals, colptr, ncols, B->k, rowval, nzval);
+        CB_LAUNCH_CHECK();
+    }
+    i64 last = 1;
+    CB_CUDA(cudaMemcpyAsync(&last, colptr + ncols, sizeof(i64), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaFreeAsync(d_iv, st)); CB_CUDA(cudaFreeAsync(d_vals, st));
+    CB_CUDA(cudaFreeAsync(d_keys, st)); CB_CUDA(cudaFreeAsync(d_idx, st));
+    if (d_tmp) CB_CUDA(cudaFreeAsync(d_tmp, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    if (nnz_host) *nnz_host = last - 1;
+    return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+/*
+ * compactbases_cuda.h — C ABI of libcompactbases_cuda.so
+ *
+ * B200 (sm_100a) implementation of the data-parallel hot path of
+ * CompactBases.jl v0.3.1.  Each entry point names the reference method(s)
+ * (file:line in the reference tree) whose body it replaces; INTEGRATION.md
+ * shows the Julia `ccall` glue.
+ *
+ * Conventions
+ *  - Every function returns an int status: CB_OK (0) or a CB_ERR_* code;
+ *    cb_last_error() gives a thread-local message.  The reference throws
+ *    before doing work (ArgumentError / DimensionMismatch / BoundsError);
+ *    the glue keeps those checks and maps a non-zero status to an exception.
+ *  - Arrays are caller-owned.  Unless the name ends in `_host`, array
+ *    arguments are DEVICE pointers (CUDA.jl CuPtr / torch data_ptr) valid on
+ *    the current device; `_host` forms take host pointers and copy in/out
+ *    internally (pinned or pageable).
+ *  - Matrices are column-major.  Coefficient batches X, Y are n x nvec with
+ *    leading dimension ldx/ldy (each coefficient vector contiguous).
+ *  - BandedMatrix storage: data[(u + i - j) + (l+u+1)*j], 0-based i, j.
+ *  - Index arguments documented as "1-based" follow Julia; `*0` offsets
+ *    (rowL0, colR0, col0) are 0-based counts of skipped functions.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls are asynchronous w.r.t. the host unless stated otherwise.
+ *  - No CPU fallback exists: without a CUDA device every compute entry
+ *    returns CB_ERR_CUDA.
+ */
+#ifndef COMPACTBASES_CUDA_H
+#define COMPACTBASES_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t cb_i64;
+
+enum {
+    CB_OK = 0,
+    CB_ERR_ARG = 1,          /* invalid argument / incompatible bases / dimension mismatch */
+    CB_ERR_CUDA = 2,         /* CUDA runtime error (message in cb_last_error) */
+    CB_ERR_UNSUPPORTED = 3,  /* valid request outside the compiled range (e.g. order > CB_KMAX) */
+    CB_ERR_ALLOC = 4
+};
+
+#define CB_KMAX 16           /* largest B-spline order with a compiled kernel */
+#define CB_FEDVR_OMAX 32     /* largest FE-DVR element order */
+
+const char *cb_version(void);
+const char *cb_last_error(void);
+int cb_device_count(int *count);
+
+/* ------------------------------------------------------------------------
+ * B-spline basis handle  ==  the reference's `BSpline(t, x, w, ...)` struct
+ * (src/bsplines.jl:9-20,95-119) minus the cached sparse table and metric.
+ * tt = t.t (host, n_tt = numintervals+1 non-decreasing knots); ml/mr are the
+ * implicit end multiplicities (src/knot_sets.jl:14,138-151); xi_ref/w_ref are
+ * the q Gauss-Legendre reference nodes/weights on [-1,1] (host;
+ * FastGaussQuadrature.gausslegendre(q), src/quadrature.jl:62).  Creation
+ * uploads the knots and runs the lgwt kernel (src/quadrature.jl:60-77).
+ * ---------------------------------------------------------------------- */
+typedef struct cb_bspline_s cb_bspline;
+
+int cb_bspline_create(const double *tt_host, cb_i64 n_tt, int k, int ml, int mr,
+                      const double *xi_ref_host, const double *w_ref_host, int q,
+                      cb_bspline **out);
+int cb_bspline_destroy(cb_bspline *B);
+cb_i64 cb_bspline_numfunctions(const cb_bspline *B);      /* src/knot_sets.jl:71 */
+cb_i64 cb_bspline_numknots(const cb_bspline *B);          /* src/knot_sets.jl:116 */
+cb_i64 cb_bspline_num_nonempty(const cb_bspline *B);      /* length(nonempty_intervals(t)), :196 */
+cb_i64 cb_bspline_numnodes(const cb_bspline *B);          /* length(B.x) */
+/* Device pointers to locs(B) / weights(B) (src/bsplines.jl:136-137), owned by the handle. */
+int cb_bspline_nodes(const cb_bspline *B, const double **x_dev, const double **w_dev);
+
+/* B[x, :] in row ("ELL") form — replaces getindex(B::BSpline, x, sel) and the
+ * scalar form (src/bsplines.jl:204-224), find_interval / within_support
+ * (src/knot_sets.jl:209-238) and deBoor (src/bsplines.jl:159-202).
+ * interval[p] (int32): 1-based knot interval containing x[p] (intervals are
+ *   [t_i, t_{i+1}), the last one closed), 0 if x[p] is outside the support.
+ * vals[p*k + a]: m-th derivative of function j = interval[p]-k+1+a at x[p]
+ *   (0 where j is not in 1..nf or the point is outside). */
+int cb_bspline_eval(const cb_bspline *B, const double *x, cb_i64 nx, int m,
+                    int32_t *interval, double *vals, void *stream);
+int cb_bspline_eval_host(const cb_bspline *B, const double *x_host, cb_i64 nx, int m,
+                         int32_t *interval_host, double *vals_host);
+
+/* B[x, col0+1 : col0+ncols] as Julia's SparseMatrixCSC{Float64,Int64}
+ * (src/bsplines.jl:217-224): 1-based colptr[ncols+1] / rowval, rows ascending
+ * within a column, exact zeros not stored.  rowval/nzval need room for
+ * k*nx entries.  *nnz_host receives the count (the call synchronises). */
+int cb_bspline_eval_csc(const cb_bspline *B, const double *x, cb_i64 nx,
+                        cb_i64 col0, cb_i64 ncols,
+                        cb_i64 *colptr, cb_i64 *rowval, double *nzval,
+                        cb_i64 *nnz_host, void *stream);
+
+/* Fused spline evaluation (B*C)[x] = B[x,:]*C for a batch of coefficient
+ * vectors (test/bsplines/splines.jl:68-88): out[p + ldo*v]. */
+int cb_bspline_eval_spline(const cb_bspline *B, const double *x, cb_i64 nx, int m,
+                           const double *C, cb_i64 ldc, cb_i64 nvec,
+                           double *out, cb_i64 ldo, void *stream);
+
+/* basis_functions(t, x, m) (src/bsplines.jl:28-52) as dense tables
+ * table[(c*q + l)*k + a] for the c-th non-empty interval. */
+int cb_bspline_quad_table(const cb_bspline *B, int m, double *table, void *stream);
+
+/* overlap_matrix! / diffop! and the copyto! bodies built on them
+ * (src/bsplines.jl:58-93,282-324; src/bspline_derivatives.jl:3-80;
+ * src/densities.jl:206-208):
+ *   band[i,j] = < (-1)^a d^a L_i | op | d^b R_j >  by Gauss-Legendre quadrature.
+ * L, R must share t.t and the nodes (ArgumentError in the reference,
+ * src/bsplines.jl:75-82).  Rows are functions rowL0+1..rowL0+m of L, columns
+ * colR0+1..colR0+n of R (restrictions B[:,a:b]); (l,u) must be the bandwidths
+ * of Matrix(undef, A, B) (src/bsplines.jl:258-270), i.e.
+ * (k-1+ij, k-1-ij), k = max(kL,kR), ij = colR0-rowL0.
+ * opvals: NULL, or the diagonal operator at the quadrature nodes
+ * (getindex.(Ref(D.diag), locs(B)), src/bsplines.jl:305). */
+int cb_bspline_assemble(const cb_bspline *L, const cb_bspline *R, int a, int b,
+                        const double *opvals,
+                        cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n,
+                        int l, int u, double *band, void *stream);
+/* Same with op(x) = -Z/x evaluated on chip (B'*QuasiDiagonal(-Z/r)*B,
+ * test/bsplines/operators.jl:19), no opvals array read. */
+int cb_bspline_assemble_coulomb(const cb_bspline *L, const cb_bspline *R, double Z,
+                                cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n,
+                                int l, int u, double *band, void *stream);
+
+/* ------------------------------------------------------------------------
+ * FE-DVR (src/fedvr*.jl).  The basis is described by the fields of the FEDVR
+ * struct (src/fedvr.jl:3-53), built on the host by the caller:
+ *   x[n]      B.x, nodes (neighbouring elements share one node)
+ *   wcat      the per-element weight vectors B.w^i concatenated (sum of orders)
+ *   nrm[n]    B.n, inverse-sqrt weights with bridge normalisation
+ *   estart[e] 0-based index in x of the first node of element e
+ *   order[e]  number of nodes of element e
+ *   boff[e]   offset of element e's o x o block in `blocks` (sum of o^2 before)
+ * `blocks` is the device-native operator layout: one dense column-major
+ * o x o matrix per element holding that element's own contribution
+ * (diff(B,n,i), src/fedvr_derivatives.jl:43-57); entries on a shared bridge
+ * node are the sum of the two neighbouring corners (src/fedvr_operators.jl:
+ * 104-130) and are added when the operator is applied or exported.
+ * ---------------------------------------------------------------------- */
+int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
+                      const cb_i64 *estart, const int32_t *order, const cb_i64 *boff,
+                      cb_i64 nel, int nder /*1: B'DB, 2: B'D'DB*/,
+                      double *blocks, void *stream);
+/* Dense (last-first+1)^2 column-major copy of the operator restricted to
+ * functions first..last (1-based), what set_elements! builds
+ * (src/fedvr_operators.jl:148-154); for export/tests on small bases. */
+int cb_fedvr_to_dense(const double *blocks, const cb_i64 *estart, const int32_t *order,
+                      const cb_i64 *boff, cb_i64 nel, cb_i64 first, cb_i64 last,
+                      double *A, void *stream);
+/* Y = alpha*A*X + beta*Y for the (restricted) FE-DVR operator: mul! on the
+ * BlockSkylineMatrix / Tridiagonal of src/fedvr_operators.jl:17-30.
+ * X, Y have last-first+1 rows.  uniform_order > 0 asserts that every element
+ * has that order (fast path); 0 = per-element orders are read. */
+int cb_fedvr_apply(const double *blocks, const cb_i64 *estart, const int32_t *order,
+                   const cb_i64 *boff, cb_i64 nel, int uniform_order,
+                   cb_i64 first, cb_i64 last,
+                   const double *X, cb_i64 ldx, cb_i64 nvec,
+                   double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+/* Host-buffer form: X_host/Y_host in (preferably pinned) host memory; the
+ * vector batch is streamed through the device in tiles. */
+int cb_fedvr_apply_host(const double *blocks_dev, const cb_i64 *estart_dev,
+                        const int32_t *order_dev, const cb_i64 *boff_dev,
+                        cb_i64 nel, int uniform_order, cb_i64 first, cb_i64 last,
+                        const double *X_host, cb_i64 ldx, cb_i64 nvec,
+                        double alpha, double beta, double *Y_host, cb_i64 ldy);
+
+/* ------------------------------------------------------------------------
+ * Finite differences (src/fd_derivatives.jl).
+ * scheme: 0 FiniteDifferences (:12-15), 1 StaggeredFiniteDifferences uniform
+ * (:20-25), 2 StaggeredFiniteDifferences non-uniform (:27-92; r[N] required;
+ * fhalf NULL or f(max(0,r_{j-1/2})), j=1..N+1, for the weighted forms).
+ * Writes rows i0+1..i0+n (restriction) of
+ *   nder=1: Tridiagonal(-delta/2h, gamma/2h, delta/2h)        (:233-237)
+ *   nder=2: (Sym)Tridiagonal(alpha/h^2, -2beta/h^2, alpha/h^2) (:265-277)
+ * into dl[n-1], d[n], du[n-1] (dl or du may be NULL).  For nder=2 with
+ * i0==0, ell==0, Z!=0 and a staggered scheme the Coulomb correction of
+ * laplacian_correction! (:542-551) is applied to d[0]. */
+int cb_fd_derivative(int scheme, int nder, const double *r, const double *fhalf,
+                     cb_i64 N, double step, cb_i64 i0, cb_i64 n,
+                     double Z, int ell,
+                     double *dl, double *d, double *du, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Operator application  Y = alpha*A*X + beta*Y  (mul!; call
+ * sites src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46).
+ * ---------------------------------------------------------------------- */
+int cb_banded_apply(const double *band, cb_i64 m, cb_i64 n, int l, int u,
+                    const double *X, cb_i64 ldx, cb_i64 nvec,
+                    double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+/* Tridiagonal(dl,d,du); SymTridiagonal(dv,ev) is dl=du=ev. */
+int cb_tridiag_apply(const double *dl, const double *d, const double *du, cb_i64 n,
+                     const double *X, cb_i64 ldx, cb_i64 nvec,
+                     double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+int cb_tridiag_apply_host(const double *dl_dev, const double *d_dev, const double *du_dev,
+                          cb_i64 n, const double *X_host, cb_i64 ldx, cb_i64 nvec,
+                          double alpha, double beta, double *Y_host, cb_i64 ldy);
+/* Diagonal (FE-DVR / FD scalar operators, src/fedvr_operators.jl:158-185,
+ * src/fd_operators.jl:3-35). */
+int cb_diag_apply(const double *d, cb_i64 n, const double *X, cb_i64 ldx, cb_i64 nvec,
+                  double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Mutual densities (src/densities.jl).  rho = C * (conj(RV f) .* (LV g)).
+ * ---------------------------------------------------------------------- */
+typedef struct cb_density_s cb_density;
+
+/* Non-orthogonal B-spline branch (src/densities.jl:92-99): one-time banded
+ * factorisation that replaces pinv(Matrix(RV)) (:96).  wvals: NULL (w=one) or
+ * the weight function at the quadrature nodes (host, numnodes).  Functions
+ * col0+1..col0+ncols (restriction). */
+int cb_density_bspline_create(const cb_bspline *B, cb_i64 col0, cb_i64 ncols,
+                              const double *wvals_host, cb_density **out);
+int cb_density_destroy(cb_density *D);
+/* copyto!(rho, f, g) (src/densities.jl:156-164).  f is nf x Pf, g is nf x Pg,
+ * Pf==Pg or one of them 1 (broadcast, :57-72); rho is nf x max(Pf,Pg).
+ * conj is accepted for ABI completeness (real Float64: no-op). */
+int cb_density_apply(const cb_density *D, const double *f, cb_i64 ldf, cb_i64 Pf,
+                     const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
+                     double *rho, cb_i64 ldr, void *stream);
+/* Orthogonal branches (src/densities.jl:166-185): rho = c .* (f .* g);
+ * c NULL for the uniform case (C = I). */
+int cb_density_orthogonal(const double *c, cb_i64 n,
+                          const double *f, cb_i64 ldf, cb_i64 Pf,
+                          const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
+                          double *rho, cb_i64 ldr, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMPACTBASES_CUDA_H */
