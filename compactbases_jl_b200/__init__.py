@@ -1,0 +1,27 @@
+"""compactbases_jl_b200 — B200 (sm_100a) implementation of the data-parallel hot path of
+CompactBases.jl behind the reference's quasi-array API.
+
+The product is ``libcompactbases_cuda.so`` (C ABI, ``include/compactbases_cuda.h``); this
+package is the host-side mirror of the reference interface for that path (Julia is not
+available in this environment; INTEGRATION.md holds the Julia ``ccall`` glue).  There is no
+CPU fallback: every compute call needs the CUDA library and a device.
+"""
+from . import _lib
+from ._lib import DimensionMismatch, CudaError
+from .knot_sets import ArbitraryKnotSet, ExpKnotSet, LinearKnotSet
+from .quadrature import gausslegendre, gausslobatto, num_quadrature_points
+from .lazy import CoulombDerivative, Derivative, QuasiDiagonal, materialize
+from .operators import (BandedMatrix, ColMajor, Diagonal, FEDVRMatrix, SymTridiagonal, Tridiagonal, mul)
+from .bsplines import BSpline, CoulombPotential, RestrictedBSpline, SparseMatrixCSC, diffop
+from .fedvr import FEDVR, RestrictedFEDVR
+from .finite_differences import (FiniteDifferences, RestrictedFiniteDifferences, StaggeredFiniteDifferences)
+from .densities import Density, FunctionProduct
+
+__all__ = [
+    "ArbitraryKnotSet", "ExpKnotSet", "LinearKnotSet", "BSpline", "RestrictedBSpline", "SparseMatrixCSC",
+    "CoulombPotential", "diffop", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
+    "RestrictedFiniteDifferences", "Derivative", "QuasiDiagonal", "CoulombDerivative", "materialize",
+    "BandedMatrix", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
+    "Density", "FunctionProduct", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
+    "num_quadrature_points",
+]

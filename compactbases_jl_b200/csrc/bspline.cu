@@ -293,6 +293,15 @@ int cb_bspline_nodes(const cb_bspline *B, const double **x, const double **w) {
     return CB_OK;
 }
 
+int cb_bspline_nodes_copy(const cb_bspline *B, double *x, double *w, void *stream) {
+    CB_REQUIRE(B != nullptr, "cb_bspline_nodes_copy: NULL basis");
+    const size_t bytes = sizeof(double) * (size_t)(B->ni * B->q);
+    if (bytes == 0) return CB_OK;
+    if (x) CB_CUDA(cudaMemcpyAsync(x, B->d_x, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (w) CB_CUDA(cudaMemcpyAsync(w, B->d_w, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CB_OK;
+}
+
 int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
                     int32_t *interval, double *vals, void *stream) {
     CB_REQUIRE(B != nullptr, "cb_bspline_eval: NULL basis");

@@ -1,0 +1,511 @@
+// density.cu — mutual-density projection (K10).
+//
+// Reference (src/densities.jl:48-101,156-164): rho = C * (conj(V f) .* (V g)),
+// V = B[locs(B), sel] the Vandermonde matrix at the quadrature nodes and
+// C = pinv(Matrix(V)) * Diagonal(w.(x)) a DENSE nf x nquad matrix (:96).  V has
+// full column rank, so pinv(V) = (V'V)^-1 V' and
+//     rho = G^-1 V' (w .* conj(V f) .* (V g)),      G = V'V
+// with G symmetric positive definite of half-bandwidth k-1.  The plan holds the
+// node table of V (K2), the banded Cholesky factor of G and nothing dense.
+//
+// Apply = three kernels over the pair batch (lanes <-> pairs so that every
+// table / factor entry is a warp-uniform load):
+//   density_rhs      r = V'(w .* Vf .* Vg)  sliding window over the knot intervals
+//   density_solve    forward + backward banded substitution, in place
+// Optional refinement (corrected semi-normal equations) repeats both on the
+// node residual s - V rho.
+#include "bspline_core.cuh"
+
+int cb_bspline_gram_internal(const cb_bspline *B, i64 col0, i64 ncols, double *band, void *stream);  // assemble.cu
+
+struct cb_density_s {
+    int k, q, ml, device;
+    i64 n_tt, nf, col0, ncols, ni;
+    double *d_table;     // [ni][q][k] values of the live functions at the nodes
+    double *d_wv;        // NULL or w(x) at the nodes [ni*q]
+    int32_t *d_ord;      // [nt] ordinal of expanded interval I (entry I-1) or -1 (copy of the basis')
+    i64 *d_ivlist;       // [ni] expanded 1-based index of each non-empty interval (copy)
+    double *d_fw;        // [ncols][k]: fw[j][0] = 1/L_jj, fw[j][p] = L_{j,j-p}/L_jj
+    double *d_bw;        // [ncols][k]: bw[j][p] = L_{j+p,j}/L_jj (p >= 1)
+    int refine;
+    int chol_status;     // 0 ok, else 1-based column where the factorisation broke down
+};
+
+// ---------------------------------------------------------------------------
+// One-time banded Cholesky of G (lower band g[j][p] = G_{j,j-p}, p = 0..k-1).
+// Sequential in j; a single warp keeps the last K rows of L in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void density_cholesky_kernel(const double *__restrict__ gband, int W /*2k-1*/, int k, i64 n,
+                                        double *__restrict__ fw, double *__restrict__ bw, int *__restrict__ status) {
+    __shared__ double ring[CB_KMAX][CB_KMAX];      // ring[j % k][p] = L_{j,j-p}
+    if (threadIdx.x != 0) return;
+    for (i64 j = 0; j < n; ++j) {
+        double row[CB_KMAX];
+        // L_{j,c}, c = j-k+1 .. j  <->  p = j-c = k-1 .. 0
+        for (int p = k - 1; p >= 0; --p) {
+            const i64 c = j - p;
+            if (c < 0) { row[p] = 0.0; continue; }
+            // G_{j,c}: BandedMatrix storage (u + i - j') + W*j' with u = k-1, i = j, j' = c
+            double s = gband[(k - 1 + p) + (i64)W * c];
+            // sum over c' < c, c' >= j-k+1: L_{j,c'} L_{c,c'}
+            for (int pp = k - 1; pp > p; --pp) {
+                const i64 cc = j - pp;
+                if (cc < 0) continue;
+                const int pc = (int)(c - cc);       // L_{c,cc} = ring[c % k][c-cc]
+                s -= row[pp] * ring[c % k][pc];
+            }
+            if (p == 0) {
+                if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
+                row[0] = sqrt(s);
+            } else {
+                row[p] = s / ring[c % k][0];
+            }
+        }
+        for (int p = 0; p < k; ++p) ring[j % k][p] = row[p];
+        const double inv = 1.0 / row[0];
+        fw[j * k] = inv;
+        for (int p = 1; p < k; ++p) fw[j * k + p] = row[p] * inv;
+        // bw[c][p] = L_{c+p,c}/L_cc : row j contributes bw[j-p][p]
+        bw[j * k] = inv;
+        for (int p = 1; p < k; ++p)
+            if (j - p >= 0) bw[(j - p) * k + p] = row[p] / ring[(j - p) % k][0];
+    }
+    // entries of bw that refer to rows beyond n
+    for (i64 j = n - k + 1 > 0 ? n - k + 1 : 0; j < n; ++j)
+        for (int p = 1; p < k; ++p)
+            if (j + p >= n) bw[j * k + p] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// MODE 0:  r = V'(w .* (V f) .* (V g))
+// MODE 1:  r = V'(w .* (V f) .* (V g) - V rho)      (refinement residual)
+//
+// A warp owns 32 pairs and a chunk of DR_CH consecutive functions.  Each lane
+// walks the knot intervals of the chunk keeping K coefficients of f and g and K
+// partial sums in registers (a function enters at window slot K-1 and leaves,
+// complete, at slot 0).  Coefficient rows are staged through shared memory in
+// 32x32 tiles so that global traffic is coalesced along the contiguous
+// (function) dimension of f, g and rho; table and weight entries are
+// warp-uniform loads.
+// ---------------------------------------------------------------------------
+constexpr int DR_WARPS = 4;
+constexpr int DR_CH = 256;
+constexpr int DR_TILE = 32 * 33;                   // doubles per warp tile (odd pitch)
+
+struct DensArgs {
+    const int32_t *ord; const double *table; const double *wv;
+    i64 n_tt, nf, col0, ncols; int ml, q;
+    const double *f; i64 ldf; i64 Pf;
+    const double *g; i64 ldg; i64 Pg;
+    const double *rho_in; i64 ldri;     // MODE 1
+    double *out; i64 ldo;               // r [ncols x P], or the nodal product [nnodes x P]
+    i64 P;
+};
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(DR_WARPS * 32)
+density_rhs_kernel(DensArgs A) {
+    extern __shared__ double sm[];
+    constexpr int NT = MODE == 1 ? 4 : 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sf = sm + (size_t)warp * NT * DR_TILE, *sg = sf + DR_TILE, *so = sg + DR_TILE;
+    double *sr = MODE == 1 ? so + DR_TILE : so;
+    const i64 nchunk = (A.ncols + DR_CH - 1) / DR_CH;
+    const i64 npg = (A.P + 31) / 32;
+    const int q = A.q, ml = A.ml;
+    for (i64 item = (i64)blockIdx.x * DR_WARPS + warp; item < nchunk * npg; item += (i64)gridDim.x * DR_WARPS) {
+        const i64 pg = item / nchunk, ch = item - pg * nchunk;
+        const i64 p0 = pg * 32;
+        const i64 fa = A.col0 + 1 + ch * DR_CH;                     // first function of the chunk (1-based, absolute)
+        i64 fb = fa + DR_CH; if (fb > A.col0 + A.ncols + 1) fb = A.col0 + A.ncols + 1;   // exclusive
+        const i64 s0 = fa - ml, s1 = (fb - 1) - ml + K - 1;         // interval range (virtual outside 0..n_tt-2)
+        double fw[K], gw[K], rw[K], acc[K];
+        i64 tile_base = fa - K + 1;                                 // function of tile row 0
+        auto load_tiles = [&]() {                                   // rows [tile_base, tile_base+32) of the 32 pairs
+            __syncwarp();
+            const i64 row = tile_base + lane - 1 - A.col0;          // row of the restricted coefficient arrays
+            for (int pp = 0; pp < 32; ++pp) {
+                const i64 p = p0 + pp;
+                const bool ok = p < A.P && row >= 0 && row < A.ncols;
+                sf[pp * 33 + lane] = ok ? A.f[row + A.ldf * (A.Pf == 1 ? 0 : p)] : 0.0;
+                sg[pp * 33 + lane] = ok ? A.g[row + A.ldg * (A.Pg == 1 ? 0 : p)] : 0.0;
+                if (MODE == 1) sr[pp * 33 + lane] = ok ? A.rho_in[row + A.ldri * p] : 0.0;
+            }
+            __syncwarp();
+        };
+        load_tiles();
+        // window before interval s0: functions fa-K+1 .. fa-1 wait in slots 1..K-1 (shifted down on entry)
+        fw[0] = gw[0] = rw[0] = acc[0] = 0.0;
+#pragma unroll
+        for (int a = 0; a < K - 1; ++a) {
+            fw[a + 1] = sf[lane * 33 + a]; gw[a + 1] = sg[lane * 33 + a];
+            rw[a + 1] = MODE == 1 ? sr[lane * 33 + a] : 0.0;
+            acc[a + 1] = 0.0;
+        }
+        int tpos = K - 1;                                           // tile row of the next entering function
+        int opos = 0;                                               // rows pending in the output tile
+        i64 obase = fa;                                             // function of output tile row 0
+        for (i64 s = s0; s <= s1; ++s) {
+#pragma unroll
+            for (int a = 0; a < K - 1; ++a) { fw[a] = fw[a + 1]; gw[a] = gw[a + 1]; rw[a] = rw[a + 1]; acc[a] = acc[a + 1]; }
+            if (tpos == 32) { tile_base += 32; load_tiles(); tpos = 0; }
+            fw[K - 1] = sf[lane * 33 + tpos]; gw[K - 1] = sg[lane * 33 + tpos];
+            rw[K - 1] = MODE == 1 ? sr[lane * 33 + tpos] : 0.0;
+            acc[K - 1] = 0.0;
+            ++tpos;
+            const int c = (s >= 0 && s <= A.n_tt - 2) ? A.ord[s + ml - 1] : -1;
+            if (c >= 0) {
+                const double *tab = A.table + (i64)c * q * K;
+                for (int l = 0; l < q; ++l) {
+                    double u = 0.0, v = 0.0, z = 0.0, tv[K];
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        tv[a] = __ldg(tab + l * K + a);
+                        u = fma(tv[a], fw[a], u);
+                        v = fma(tv[a], gw[a], v);
+                        if (MODE == 1) z = fma(tv[a], rw[a], z);
+                    }
+                    double t = u * v;
+                    if (A.wv) t *= __ldg(A.wv + (i64)c * q + l);
+                    if (MODE == 1) t -= z;
+#pragma unroll
+                    for (int a = 0; a < K; ++a) acc[a] = fma(tv[a], t, acc[a]);
+                }
+            }
+            const i64 fe = s + ml - K + 1;                          // slot 0 has seen its last interval
+            if (fe >= fa && fe < fb) {
+                so[lane * 33 + opos] = acc[0];
+                ++opos;
+                if (opos == 32 || fe == fb - 1) {
+                    __syncwarp();
+                    for (int pp = 0; pp < 32; ++pp) {
+                        const i64 p = p0 + pp;
+                        if (p < A.P && lane < opos) A.out[(obase + lane - 1 - A.col0) + A.ldo * p] = so[pp * 33 + lane];
+                    }
+                    __syncwarp();
+                    obase += opos; opos = 0;
+                }
+            }
+        }
+    }
+}
+
+// Nodal product tmp = (V f) .* (V g) (ftmp .* gtmp of src/densities.jl:158-161;
+// feeds copyto!(M, rho), :206-208).  Thread per (node, pair).
+template <int K>
+__global__ void density_nodal_kernel(DensArgs A, const i64 *__restrict__ ivlist, i64 ni) {
+    const i64 nn = ni * A.q;
+    for (i64 p = blockIdx.y; p < A.P; p += gridDim.y) {
+        const double *fc = A.f + A.ldf * (A.Pf == 1 ? 0 : p), *gc = A.g + A.ldg * (A.Pg == 1 ? 0 : p);
+        for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < nn; e += (i64)gridDim.x * blockDim.x) {
+            const i64 c = e / A.q;
+            const i64 I = ivlist[c];
+            double u = 0.0, v = 0.0;
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                const i64 row = I - K + 1 + a - 1 - A.col0;
+                if (row >= 0 && row < A.ncols) {
+                    const double tv = A.table[e * K + a];
+                    u = fma(tv, fc[row], u);
+                    v = fma(tv, gc[row], v);
+                }
+            }
+            A.out[e + A.ldo * p] = u * v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// In-place banded solve  L L' x = r  for 32 pairs per warp.
+// ---------------------------------------------------------------------------
+constexpr int DS_WARPS = 2;
+
+template <int K>
+__global__ void __launch_bounds__(DS_WARPS * 32)
+density_solve_kernel(const double *__restrict__ fwt, const double *__restrict__ bwt, i64 n,
+                     double *__restrict__ X, i64 ldx, i64 P, const double *__restrict__ addto, i64 lda) {
+    __shared__ double sx[DS_WARPS][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 npg = (P + 31) / 32;
+    const i64 ntile = (n + 31) / 32;
+    for (i64 pg = (i64)blockIdx.x * DS_WARPS + warp; pg < npg; pg += (i64)gridDim.x * DS_WARPS) {
+        const i64 p0 = pg * 32;
+        double yw[K];                                   // yw[p] = y_{j-p} (p >= 1) at row j
+#pragma unroll
+        for (int p = 0; p < K; ++p) yw[p] = 0.0;
+        // forward: y_j = r_j/L_jj - sum_p (L_{j,j-p}/L_jj) y_{j-p}
+        for (i64 t = 0; t < ntile; ++t) {
+            const i64 j0 = t * 32;
+            __syncwarp();
+            for (int pp = 0; pp < 32; ++pp) {
+                const i64 p = p0 + pp, j = j0 + lane;
+                sx[warp][pp][lane] = (p < P && j < n) ? X[j + ldx * p] : 0.0;
+            }
+            __syncwarp();
+            const int rows = n - j0 < 32 ? (int)(n - j0) : 32;
+            for (int r = 0; r < rows; ++r) {
+                const double *cf = fwt + (j0 + r) * K;
+                double acc = sx[warp][lane][r] * __ldg(cf);
+#pragma unroll
+                for (int p = K - 1; p >= 1; --p) acc = fma(-__ldg(cf + p), yw[p], acc);
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+                if (K > 1) yw[1] = acc;
+                sx[warp][lane][r] = acc;
+            }
+            __syncwarp();
+            for (int pp = 0; pp < 32; ++pp) {
+                const i64 p = p0 + pp, j = j0 + lane;
+                if (p < P && j < n) X[j + ldx * p] = sx[warp][pp][lane];
+            }
+        }
+        // backward: x_j = y_j/L_jj - sum_p (L_{j+p,j}/L_jj) x_{j+p}
+#pragma unroll
+        for (int p = 0; p < K; ++p) yw[p] = 0.0;
+        for (i64 t = ntile - 1; t >= 0; --t) {
+            const i64 j0 = t * 32;
+            __syncwarp();
+            for (int pp = 0; pp < 32; ++pp) {
+                const i64 p = p0 + pp, j = j0 + lane;
+                sx[warp][pp][lane] = (p < P && j < n) ? X[j + ldx * p] : 0.0;
+            }
+            __syncwarp();
+            const int rows = n - j0 < 32 ? (int)(n - j0) : 32;
+            for (int r = rows - 1; r >= 0; --r) {
+                const double *cb = bwt + (j0 + r) * K;
+                double acc = sx[warp][lane][r] * __ldg(cb);
+#pragma unroll
+                for (int p = K - 1; p >= 1; --p) acc = fma(-__ldg(cb + p), yw[p], acc);
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+                if (K > 1) yw[1] = acc;
+                sx[warp][lane][r] = acc;
+            }
+            __syncwarp();
+            for (int pp = 0; pp < 32; ++pp) {
+                const i64 p = p0 + pp, j = j0 + lane;
+                if (p < P && j < n) {
+                    double v = sx[warp][pp][lane];
+                    if (addto) v += addto[j + lda * p];
+                    X[j + ldx * p] = v;
+                }
+            }
+        }
+    }
+}
+
+// Orthogonal branches (src/densities.jl:166-185): rho = c .* (conj(f) .* g).
+__global__ void density_orthogonal_kernel(const double *__restrict__ c, i64 n,
+                                          const double *__restrict__ f, i64 ldf, i64 Pf,
+                                          const double *__restrict__ g, i64 ldg, i64 Pg,
+                                          double *__restrict__ rho, i64 ldr, i64 P) {
+    for (i64 p = blockIdx.y; p < P; p += gridDim.y) {
+        const double *fc = f + ldf * (Pf == 1 ? 0 : p), *gc = g + ldg * (Pg == 1 ? 0 : p);
+        for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+            double v = fc[i] * gc[i];
+            rho[i + ldr * p] = c ? c[i] * v : v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+#define CB_DISPATCH_KD(kval, ...)                                                \
+    switch (kval) {                                                              \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;                     \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;                     \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;                     \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;                     \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;                     \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;                     \
+        case 7: { constexpr int K = 7; __VA_ARGS__; } break;                     \
+        case 8: { constexpr int K = 8; __VA_ARGS__; } break;                     \
+        case 9: { constexpr int K = 9; __VA_ARGS__; } break;                     \
+        case 10: { constexpr int K = 10; __VA_ARGS__; } break;                   \
+        case 11: { constexpr int K = 11; __VA_ARGS__; } break;                   \
+        case 12: { constexpr int K = 12; __VA_ARGS__; } break;                   \
+        case 13: { constexpr int K = 13; __VA_ARGS__; } break;                   \
+        case 14: { constexpr int K = 14; __VA_ARGS__; } break;                   \
+        case 15: { constexpr int K = 15; __VA_ARGS__; } break;                   \
+        case 16: { constexpr int K = 16; __VA_ARGS__; } break;                   \
+        default:                                                                 \
+            cb_set_error("B-spline order k=%d outside compiled range 1..%d", kval, CB_KMAX); \
+            return CB_ERR_UNSUPPORTED;                                           \
+    }
+
+static int check_pairs(const char *who, const cb_density *D, const double *f, i64 ldf, i64 Pf,
+                       const double *g, i64 ldg, i64 Pg) {
+    CB_REQUIRE(D != nullptr, "%s: NULL plan", who);
+    CB_REQUIRE(f && g, "%s: NULL array", who);
+    CB_REQUIRE(Pf >= 0 && Pg >= 0, "%s: negative batch", who);
+    // src/densities.jl:57-60
+    CB_REQUIRE(Pf == Pg || Pf == 1 || Pg == 1, "DimensionMismatch: Cannot broadcast %lld LHS and %lld RHS to common size",
+               (long long)Pf, (long long)Pg);
+    CB_REQUIRE(ldf >= D->ncols && ldg >= D->ncols, "%s: leading dimension smaller than the number of functions", who);
+    return CB_OK;
+}
+
+static DensArgs make_args(const cb_density *D, const cb_bspline *, const double *f, i64 ldf, i64 Pf,
+                          const double *g, i64 ldg, i64 Pg) {
+    DensArgs A;
+    A.ord = D->d_ord; A.table = D->d_table; A.wv = D->d_wv;
+    A.n_tt = D->n_tt; A.nf = D->nf; A.col0 = D->col0; A.ncols = D->ncols; A.ml = D->ml; A.q = D->q;
+    A.f = f; A.ldf = ldf; A.Pf = Pf; A.g = g; A.ldg = ldg; A.Pg = Pg;
+    A.rho_in = nullptr; A.ldri = 0; A.out = nullptr; A.ldo = 0;
+    A.P = Pf > Pg ? Pf : Pg;
+    return A;
+}
+
+template <int K, int MODE>
+static int launch_rhs(const DensArgs &A, cudaStream_t st) {
+    i64 items = ((A.ncols + DR_CH - 1) / DR_CH) * ((A.P + 31) / 32);
+    i64 blocks = (items + DR_WARPS - 1) / DR_WARPS;
+    int grid = (int)(blocks < (i64)CB_NUM_SMS * 64 ? blocks : (i64)CB_NUM_SMS * 64);
+    size_t smem = sizeof(double) * DR_WARPS * (MODE == 1 ? 4 : 3) * DR_TILE;
+    CB_CUDA(cudaFuncSetAttribute(density_rhs_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    density_rhs_kernel<K, MODE><<<grid, DR_WARPS * 32, smem, st>>>(A);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+template <int K>
+static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const double *addto, i64 lda, cudaStream_t st) {
+    i64 blocks = ((P + 31) / 32 + DS_WARPS - 1) / DS_WARPS;
+    density_solve_kernel<K><<<(int)blocks, DS_WARPS * 32, 0, st>>>(D->d_fw, D->d_bw, D->ncols, X, ldx, P, addto, lda);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+extern "C" {
+
+int cb_density_destroy(cb_density *D) {
+    if (!D) return CB_OK;
+    cudaFree(D->d_table); cudaFree(D->d_wv); cudaFree(D->d_ord); cudaFree(D->d_ivlist);
+    cudaFree(D->d_fw); cudaFree(D->d_bw);
+    delete D;
+    return CB_OK;
+}
+
+int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const double *wvals_host, cb_density **out) {
+    CB_REQUIRE(out != nullptr, "cb_density_bspline_create: out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(B != nullptr, "cb_density_bspline_create: NULL basis");
+    CB_REQUIRE(col0 >= 0 && ncols >= 1 && col0 + ncols <= B->nf, "cb_density_bspline_create: restriction outside 1..nf");
+    cb_density_s *D = new cb_density_s();
+    D->k = B->k; D->q = B->q; D->ml = B->ml; D->n_tt = B->n_tt; D->nf = B->nf; D->ni = B->ni;
+    D->col0 = col0; D->ncols = ncols; D->device = B->device; D->refine = 0; D->chol_status = 0;
+    D->d_table = D->d_wv = D->d_fw = D->d_bw = nullptr; D->d_ord = nullptr; D->d_ivlist = nullptr;
+    const i64 nn = B->ni * B->q;
+    double *d_g = nullptr; int *d_status = nullptr;
+    int rc = CB_OK;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    step(cudaMalloc(&D->d_table, sizeof(double) * (nn * B->k ? nn * B->k : 1)));
+    step(cudaMalloc(&D->d_ord, sizeof(int32_t) * B->nt));
+    step(cudaMalloc(&D->d_ivlist, sizeof(i64) * (B->ni ? B->ni : 1)));
+    if (e == cudaSuccess && B->ni) step(cudaMemcpy(D->d_ivlist, B->d_ivlist, sizeof(i64) * B->ni, cudaMemcpyDeviceToDevice));
+    step(cudaMalloc(&D->d_fw, sizeof(double) * ncols * B->k));
+    step(cudaMalloc(&D->d_bw, sizeof(double) * ncols * B->k));
+    step(cudaMalloc(&d_g, sizeof(double) * ncols * (2 * B->k - 1)));
+    step(cudaMalloc(&d_status, sizeof(int)));
+    if (e == cudaSuccess) step(cudaMemset(d_status, 0, sizeof(int)));
+    if (e == cudaSuccess) step(cudaMemcpy(D->d_ord, B->d_ord, sizeof(int32_t) * B->nt, cudaMemcpyDeviceToDevice));
+    if (e == cudaSuccess && wvals_host) {
+        step(cudaMalloc(&D->d_wv, sizeof(double) * (nn ? nn : 1)));
+        if (e == cudaSuccess) step(cudaMemcpy(D->d_wv, wvals_host, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    }
+    if (e == cudaSuccess) rc = cb_bspline_quad_table(B, 0, D->d_table, nullptr);
+    if (e == cudaSuccess && rc == CB_OK) rc = cb_bspline_gram_internal(B, col0, ncols, d_g, nullptr);
+    if (e == cudaSuccess && rc == CB_OK) {
+        density_cholesky_kernel<<<1, 32>>>(d_g, 2 * B->k - 1, B->k, ncols, D->d_fw, D->d_bw, d_status);
+        step(cudaGetLastError());
+        step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_g); cudaFree(d_status);
+    if (e != cudaSuccess) { cb_set_error("cb_density_bspline_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }
+    if (rc != CB_OK) { cb_density_destroy(D); return rc; }
+    if (D->chol_status != 0) {
+        cb_set_error("cb_density_bspline_create: Vandermonde matrix is rank deficient at function %d", D->chol_status);
+        cb_density_destroy(D);
+        return CB_ERR_ARG;
+    }
+    *out = D;
+    return CB_OK;
+}
+
+int cb_density_set_refine(cb_density *D, int steps) {
+    CB_REQUIRE(D != nullptr && steps >= 0 && steps <= 4, "cb_density_set_refine: bad argument");
+    D->refine = steps;
+    return CB_OK;
+}
+
+int cb_density_apply(const cb_density *D, const double *f, i64 ldf, i64 Pf,
+                     const double *g, i64 ldg, i64 Pg, int conj, double *rho, i64 ldr, void *stream) {
+    (void)conj;                                    // real Float64: conj is the identity
+    int rc = check_pairs("cb_density_apply", D, f, ldf, Pf, g, ldg, Pg);
+    if (rc) return rc;
+    CB_REQUIRE(rho != nullptr && ldr >= D->ncols, "cb_density_apply: bad rho array");
+    const i64 P = Pf > Pg ? Pf : Pg;
+    if (P == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DensArgs A = make_args(D, nullptr, f, ldf, Pf, g, ldg, Pg);
+    A.out = rho; A.ldo = ldr;
+    CB_DISPATCH_KD(D->k, rc = (launch_rhs<K, 0>(A, st)));
+    if (rc) return rc;
+    CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, rho, ldr, P, nullptr, 0, st));
+    if (rc) return rc;
+    if (D->refine > 0) {
+        double *tmp = nullptr;
+        CB_CUDA(cudaMallocAsync(&tmp, sizeof(double) * D->ncols * P, st));
+        for (int it = 0; it < D->refine && rc == CB_OK; ++it) {
+            DensArgs R = A;
+            R.rho_in = rho; R.ldri = ldr; R.out = tmp; R.ldo = D->ncols;
+            CB_DISPATCH_KD(D->k, rc = (launch_rhs<K, 1>(R, st)));
+            if (rc) break;
+            // tmp <- G^-1 tmp + rho, written to tmp; then copied back
+            CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, tmp, D->ncols, P, rho, ldr, st));
+            if (rc) break;
+            cudaError_t e = cudaMemcpy2DAsync(rho, sizeof(double) * ldr, tmp, sizeof(double) * D->ncols,
+                                              sizeof(double) * D->ncols, P, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) { cb_set_error("cb_density_apply: %s", cudaGetErrorString(e)); rc = CB_ERR_CUDA; }
+        }
+        cudaFreeAsync(tmp, st);
+    }
+    return rc;
+}
+
+int cb_density_nodal_product(const cb_density *D, const double *f, i64 ldf, i64 Pf,
+                             const double *g, i64 ldg, i64 Pg, int conj, double *tmp, i64 ldt, void *stream) {
+    (void)conj;
+    int rc = check_pairs("cb_density_nodal_product", D, f, ldf, Pf, g, ldg, Pg);
+    if (rc) return rc;
+    CB_REQUIRE(tmp != nullptr && ldt >= D->ni * D->q, "cb_density_nodal_product: bad tmp array");
+    const i64 P = Pf > Pg ? Pf : Pg;
+    if (P == 0) return CB_OK;
+    DensArgs A = make_args(D, nullptr, f, ldf, Pf, g, ldg, Pg);
+    A.out = tmp; A.ldo = ldt;
+    const i64 nn = D->ni * D->q;
+    if (nn == 0) return CB_OK;
+    dim3 grid((unsigned)cb_grid_for(nn, 256, 8), (unsigned)(P < 4096 ? P : 4096));
+    CB_DISPATCH_KD(D->k, (density_nodal_kernel<K><<<grid, 256, 0, (cudaStream_t)stream>>>(A, D->d_ivlist, D->ni)));
+    CB_LAUNCH_CHECK();
+    return rc;
+}
+
+int cb_density_orthogonal(const double *c, i64 n, const double *f, i64 ldf, i64 Pf,
+                          const double *g, i64 ldg, i64 Pg, int conj, double *rho, i64 ldr, void *stream) {
+    (void)conj;
+    CB_REQUIRE(n >= 0 && f && g && rho, "cb_density_orthogonal: bad argument");
+    CB_REQUIRE(Pf == Pg || Pf == 1 || Pg == 1, "DimensionMismatch: Cannot broadcast %lld LHS and %lld RHS to common size",
+               (long long)Pf, (long long)Pg);
+    CB_REQUIRE(ldf >= n && ldg >= n && ldr >= n, "cb_density_orthogonal: leading dimension smaller than n");
+    const i64 P = Pf > Pg ? Pf : Pg;
+    if (P == 0 || n == 0) return CB_OK;
+    dim3 grid((unsigned)cb_grid_for(n, 256, 4), (unsigned)(P < 8192 ? P : 8192));
+    density_orthogonal_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, f, ldf, Pf, g, ldg, Pg, rho, ldr, P);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+}  // extern "C"

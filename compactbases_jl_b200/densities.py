@@ -1,0 +1,116 @@
+"""Mutual densities — host mirror of src/densities.jl over the CUDA C ABI.
+
+    rho = Density(B, nlhs=P, nrhs=P)        # FunctionProduct{true}(B, B, Float64, P, P)
+    rho.copyto(f, g)                        # copyto!(rho, f, g): rho.rho = coefficients of conj(f) g
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DimensionMismatch
+from .bsplines import _BSplineOrRestricted, diffop
+from .lazy import QuasiDiagonal
+from .operators import ColMajor, _ptr, _stream, to_device
+
+
+class FunctionProduct:
+    """``FunctionProduct{Conjugated}(L, R, T, nlhs, nrhs; w=one)`` (src/densities.jl:48-101).
+
+    B-spline bases take the general branch (:92-99); the dense ``pinv(Matrix(RV))`` of the
+    reference is replaced by a banded Cholesky factorisation of RV'RV held in the plan.
+    FE-DVR and finite-difference bases are orthogonal (:73-91): C is ``I`` or diagonal."""
+
+    def __init__(self, L, R=None, nlhs=None, nrhs=None, w=None, conjugated=True):
+        R = L if R is None else R
+        self.L, self.R, self.conjugated = L, R, conjugated
+        rl, rr = nlhs or 1, nrhs or 1
+        if not (rl == rr or rl == 1 or rr == 1):                         # :57-60
+            raise DimensionMismatch(f"DimensionMismatch: Cannot broadcast {rl} LHS and {rr} RHS to common size")
+        self.nrho = None if (rl == 1 and rr == 1) else max(rl, rr)
+        self.handle = None
+        self.c = None
+        P = R.parent_basis
+        self.device = P.device
+        if isinstance(R, _BSplineOrRestricted):
+            if not (isinstance(L, _BSplineOrRestricted) and L.parent_basis == P and (L.col0, L.ncols) == (R.col0, R.ncols)):
+                raise ValueError("Can only multiply B-spline bases with identical knot sets and restrictions")
+            wv = None
+            if w is not None:
+                wv = np.ascontiguousarray(w(P.x.cpu().numpy()), dtype=np.float64)
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.call("cb_density_bspline_create", P.handle, R.col0, R.ncols,
+                          None if wv is None else C.c_void_p(wv.ctypes.data), C.byref(h))
+            self.handle = h
+            self.n = R.ncols
+        else:
+            if L is not R and not (L.parent_basis == P and L.indices() == R.indices()):
+                raise ValueError("Cannot multiply functions on different grids")
+            self.n = R.size()
+            i0 = R.indices()[0] - 1
+            # C = w if the Vandermonde diagonal is all ones, else RV*w (:76-84)
+            vd = P.vandermonde_diag()
+            c = None if vd is None else np.asarray(vd, dtype=np.float64)[i0:i0 + self.n]
+            if w is not None:
+                wv = np.asarray(w(np.asarray(P.locs())[i0:i0 + self.n]), dtype=np.float64)
+                c = wv if c is None else c * wv
+            if c is not None:
+                self.c = to_device(c, self.device)
+        self.rho = None
+        self.tmp = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().cb_density_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_refine(self, steps: int):
+        """Corrected-semi-normal-equation refinement steps (0 = plain normal equations)."""
+        if self.handle:
+            _lib.call("cb_density_set_refine", self.handle, int(steps))
+
+    def copyto(self, f, g, out: ColMajor | None = None) -> ColMajor:
+        """``copyto!(rho, f, g)`` (src/densities.jl:156-185).  f, g: ColMajor coefficient batches
+        (n x Pf, n x Pg; one of them may have a single column)."""
+        f = f if isinstance(f, ColMajor) else ColMajor(f)
+        g = g if isinstance(g, ColMajor) else ColMajor(g)
+        if f.n != self.n or g.n != self.n:
+            raise DimensionMismatch(f"DimensionMismatch: basis has {self.n} functions, got {f.n} and {g.n} rows")
+        P = max(f.nvec, g.nvec)
+        rho = ColMajor.zeros(self.n, P, self.device) if out is None else out
+        if self.handle:
+            _lib.call("cb_density_apply", self.handle, _ptr(f.data), f.ld, f.nvec, _ptr(g.data), g.ld, g.nvec,
+                      int(self.conjugated), _ptr(rho.data), rho.ld, _stream())
+        else:
+            _lib.call("cb_density_orthogonal", _ptr(self.c), self.n, _ptr(f.data), f.ld, f.nvec,
+                      _ptr(g.data), g.ld, g.nvec, int(self.conjugated), _ptr(rho.data), rho.ld, _stream())
+        self.rho = rho
+        self._last = (f, g)
+        return rho
+
+    def matrix(self):
+        """``copyto!(M, rho)`` (src/densities.jl:202-208): the operator of multiplication by the
+        density, ``overlap_matrix!(M, L', R, Diagonal(rho.tmp))`` for B-splines."""
+        if not self.handle:
+            from .operators import Diagonal
+            return Diagonal(self.rho.data[0, :self.n].contiguous())
+        f, g = self._last
+        P = self.R.parent_basis
+        nn = P.ni * P.q
+        tmp = torch.empty(nn, dtype=torch.float64, device=self.device)
+        _lib.call("cb_density_nodal_product", self.handle, _ptr(f.data), f.ld, 1, _ptr(g.data), g.ld, 1,
+                  int(self.conjugated), _ptr(tmp), nn, _stream())
+        self.tmp = tmp
+        return diffop(self.L, self.R, 0, 0, [QuasiDiagonal(tmp)])
+
+
+def Density(L, R=None, nlhs=None, nrhs=None, w=None):
+    """``Density = FunctionProduct{true}`` (src/densities.jl:30)."""
+    return FunctionProduct(L, R, nlhs, nrhs, w, conjugated=True)

@@ -1,0 +1,215 @@
+"""Operator containers and ``mul`` (= Julia's ``mul!(Y, A, X, alpha, beta)``).
+
+The reference materialises its operators into ``BandedMatrix``,
+``BlockSkylineMatrix``, ``Tridiagonal``/``SymTridiagonal`` and ``Diagonal``
+ and applies them with ``mul!`` (a17; call sites
+src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46).  These classes
+hold the same storage in device memory (torch is only the allocator) and
+``mul`` routes to the CUDA kernels behind the C ABI.
+
+Coefficient batches follow Julia's layout: an ``n x nvec`` column-major matrix,
+i.e. a torch tensor of shape ``(nvec, n)`` whose rows are the coefficient
+vectors (``colmajor``/``from_colmajor`` convert from/to the (n, nvec) view).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DimensionMismatch
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_of(dev=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("compactbases_jl_b200 needs a CUDA device (no CPU fallback exists)")
+    if dev is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def to_device(a, dev=None, dtype=torch.float64) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device_of(dev), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device_of(dev))
+
+
+class ColMajor:
+    """An n x nvec column-major Float64 matrix on the device (Julia ``Matrix``).
+    ``data`` has shape (nvec, ld) with ld >= n; column v is ``data[v, :n]``."""
+
+    def __init__(self, data: torch.Tensor, n: int | None = None):
+        if data.dim() == 1:
+            data = data.unsqueeze(0)
+        assert data.dim() == 2 and data.dtype == torch.float64 and data.is_cuda and data.stride(1) == 1
+        self.data = data
+        self.n = data.shape[1] if n is None else n
+        self.nvec = data.shape[0]
+        self.ld = data.stride(0) if self.nvec > 1 else max(data.shape[1], 1)
+
+    @classmethod
+    def zeros(cls, n, nvec, dev=None):
+        return cls(torch.zeros((nvec, n), dtype=torch.float64, device=device_of(dev)))
+
+    @classmethod
+    def from_numpy(cls, a, dev=None):
+        """a: (n,) or (n, nvec) numpy array (any order)."""
+        a = np.asarray(a, dtype=np.float64)
+        if a.ndim == 1:
+            a = a[:, None]
+        return cls(to_device(np.ascontiguousarray(a.T), dev))
+
+    def numpy(self) -> np.ndarray:
+        """(n, nvec) Fortran-ordered numpy array."""
+        return np.asfortranarray(self.data[:, :self.n].cpu().numpy().T)
+
+
+def _as_colmajor(X) -> ColMajor:
+    return X if isinstance(X, ColMajor) else ColMajor(X)
+
+
+class BandedMatrix:
+    """BandedMatrices.jl storage: ``data[u + i - j, j]`` (0-based), data is (l+u+1) x n
+    column-major == torch shape (n, l+u+1)."""
+
+    def __init__(self, data: torch.Tensor, m: int, n: int, l: int, u: int):
+        assert data.shape == (n, l + u + 1) and data.is_contiguous()
+        self.data, self.m, self.n, self.l, self.u = data, m, n, l, u
+
+    @classmethod
+    def undef(cls, m, n, l, u, dev=None):
+        return cls(torch.empty((n, l + u + 1), dtype=torch.float64, device=device_of(dev)), m, n, l, u)
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def bandwidths(self):
+        return (self.l, self.u)
+
+    def dense(self) -> np.ndarray:
+        band = self.data.cpu().numpy()
+        A = np.zeros((self.m, self.n))
+        for j in range(self.n):
+            for i in range(max(0, j - self.u), min(self.m, j + self.l + 1)):
+                A[i, j] = band[j, self.u + i - j]
+        return A
+
+    def _mul(self, Y, X, alpha, beta):
+        _lib.call("cb_banded_apply", _ptr(self.data), self.m, self.n, self.l, self.u, _ptr(X.data), X.ld, X.nvec,
+                  alpha, beta, _ptr(Y.data), Y.ld, _stream())
+
+
+class Tridiagonal:
+    """LinearAlgebra.Tridiagonal(dl, d, du)."""
+
+    def __init__(self, dl, d, du):
+        self.dl, self.d, self.du = dl, d, du
+        self.n = d.numel()
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def dense(self):
+        dl, d, du = (v.cpu().numpy() for v in (self.dl, self.d, self.du))
+        return np.diag(d) + np.diag(dl, -1) + np.diag(du, 1)
+
+    def _mul(self, Y, X, alpha, beta):
+        _lib.call("cb_tridiag_apply", _ptr(self.dl), _ptr(self.d), _ptr(self.du), self.n, _ptr(X.data), X.ld, X.nvec,
+                  alpha, beta, _ptr(Y.data), Y.ld, _stream())
+
+    def mul_host(self, Yh: np.ndarray, Xh: np.ndarray, alpha=1.0, beta=0.0):
+        """Host-buffer entry (cb_tridiag_apply_host): Xh, Yh are Fortran-ordered (n, nvec) numpy arrays."""
+        assert Xh.flags.f_contiguous and Yh.flags.f_contiguous
+        _lib.call("cb_tridiag_apply_host", _ptr(self.dl), _ptr(self.d), _ptr(self.du), self.n,
+                  C.c_void_p(Xh.ctypes.data), Xh.shape[0], Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta,
+                  C.c_void_p(Yh.ctypes.data), Yh.shape[0])
+        return Yh
+
+
+class SymTridiagonal(Tridiagonal):
+    """LinearAlgebra.SymTridiagonal(dv, ev)."""
+
+    def __init__(self, dv, ev):
+        super().__init__(ev, dv, ev)
+        self.dv, self.ev = dv, ev
+
+
+class Diagonal:
+    def __init__(self, diag):
+        self.diag = diag
+        self.n = diag.numel()
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def dense(self):
+        return np.diag(self.diag.cpu().numpy())
+
+    def _mul(self, Y, X, alpha, beta):
+        _lib.call("cb_diag_apply", _ptr(self.diag), self.n, _ptr(X.data), X.ld, X.nvec, alpha, beta,
+                  _ptr(Y.data), Y.ld, _stream())
+
+
+class FEDVRMatrix:
+    """The operator that ``Matrix(undef, B)`` + ``set_elements!`` build for an FE-DVR basis
+    (src/fedvr_operators.jl:17-30,148-154), kept as one dense o x o block per element;
+    bridge corners are summed when the operator is applied or exported.  ``first..last``
+    (1-based) is the restriction ``B[:, first:last]``."""
+
+    def __init__(self, basis, blocks: torch.Tensor, first: int, last: int):
+        self.basis, self.blocks, self.first, self.last = basis, blocks, first, last
+        self.n = last - first + 1
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def block_structure(self):
+        return self.basis.block_structure(self.first, self.last)
+
+    def dense(self) -> np.ndarray:
+        b = self.basis
+        A = torch.empty((self.n, self.n), dtype=torch.float64, device=self.blocks.device)
+        _lib.call("cb_fedvr_to_dense", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                  self.first, self.last, _ptr(A), _stream())
+        return A.cpu().numpy().T.copy()
+
+    def _mul(self, Y, X, alpha, beta):
+        b = self.basis
+        _lib.call("cb_fedvr_apply", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                  b.uniform_order, self.first, self.last, _ptr(X.data), X.ld, X.nvec, alpha, beta,
+                  _ptr(Y.data), Y.ld, _stream())
+
+    def mul_host(self, Yh: np.ndarray, Xh: np.ndarray, alpha=1.0, beta=0.0):
+        """Host-buffer entry (cb_fedvr_apply_host); Fortran-ordered (n, nvec) numpy arrays."""
+        assert Xh.flags.f_contiguous and Yh.flags.f_contiguous
+        b = self.basis
+        _lib.call("cb_fedvr_apply_host", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                  b.uniform_order, self.first, self.last, C.c_void_p(Xh.ctypes.data), Xh.shape[0],
+                  Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta, C.c_void_p(Yh.ctypes.data), Yh.shape[0])
+        return Yh
+
+
+def mul(Y, A, X, alpha: float = 1.0, beta: float = 0.0):
+    """``mul!(Y, A, X, alpha, beta)``: Y = alpha*A*X + beta*Y.  X, Y: ColMajor (or torch
+    tensors of shape (nvec, n)).  Throws DimensionMismatch like the reference."""
+    X, Yc = _as_colmajor(X), _as_colmajor(Y)
+    m, n = A.shape
+    if X.n != n or Yc.n != m or X.nvec != Yc.nvec:
+        raise DimensionMismatch(f"DimensionMismatch: A has size ({m},{n}), X has size ({X.n},{X.nvec}), "
+                                f"Y has size ({Yc.n},{Yc.nvec})")
+    A._mul(Yc, X, float(alpha), float(beta))
+    return Y

@@ -72,6 +72,8 @@ cb_i64 cb_bspline_num_nonempty(const cb_bspline *B);      /* length(nonempty_int
 cb_i64 cb_bspline_numnodes(const cb_bspline *B);          /* length(B.x) */
 /* Device pointers to locs(B) / weights(B) (src/bsplines.jl:136-137), owned by the handle. */
 int cb_bspline_nodes(const cb_bspline *B, const double **x_dev, const double **w_dev);
+/* Copies locs(B) / weights(B) into caller-owned device arrays of numnodes entries (either may be NULL). */
+int cb_bspline_nodes_copy(const cb_bspline *B, double *x_dev, double *w_dev, void *stream);
 
 /* B[x, :] in row ("ELL") form — replaces getindex(B::BSpline, x, sel) and the
  * scalar form (src/bsplines.jl:204-224), find_interval / within_support
@@ -125,6 +127,22 @@ int cb_bspline_assemble_coulomb(const cb_bspline *L, const cb_bspline *R, double
                                 cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n,
                                 int l, int u, double *band, void *stream);
 
+/* Sharded form: writes only columns col_lo..col_hi-1 (0-based,
+ * within the restriction) into band_cols (column col_lo first), summing only
+ * over the t.t intervals s_lo..s_hi-1 (0-based).  coulomb: 0 = opvals/none,
+ * 1 = op(x) = -Z/x.  An interval-sharded assembly gives each rank an interval
+ * range and the columns that touch it; the k-1 boundary columns hold partial
+ * sums that the neighbours add (halo exchange), or each rank recomputes its
+ * own columns over the full interval range (no exchange). */
+int cb_bspline_assemble_part(const cb_bspline *L, const cb_bspline *R, int a, int b,
+                             const double *opvals, int coulomb, double Z,
+                             cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n, int l, int u,
+                             cb_i64 col_lo, cb_i64 col_hi, cb_i64 s_lo, cb_i64 s_hi,
+                             double *band_cols, void *stream);
+/* BandedMatrix(l=u=1) -> Tridiagonal(dl,d,du): the k == 2 && m == n case of
+ * Matrix(undef, A, B) (src/bsplines.jl:258-262). */
+int cb_band_to_tridiag(const double *band, cb_i64 n, double *dl, double *d, double *du, void *stream);
+
 /* ------------------------------------------------------------------------
  * FE-DVR (src/fedvr*.jl).  The basis is described by the fields of the FEDVR
  * struct (src/fedvr.jl:3-53), built on the host by the caller:
@@ -140,10 +158,16 @@ int cb_bspline_assemble_coulomb(const cb_bspline *L, const cb_bspline *R, double
  * node are the sum of the two neighbouring corners (src/fedvr_operators.jl:
  * 104-130) and are added when the operator is applied or exported.
  * ---------------------------------------------------------------------- */
+/* derop!(A, B, nder) / set_elements!(A, B, difffun(B, nder))
+ * (src/fedvr_derivatives.jl:15-63, src/fedvr_operators.jl:148-154).
+ * woff[e]: offset of element e's weights in wcat (sum of orders before).
+ * uniform_order > 0: every element has that order and the per-element arrays
+ * may be NULL (estart = e*(o-1), woff = e*o, boff = e*o*o); otherwise
+ * max_order = maximum(order). */
 int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
                       const cb_i64 *estart, const int32_t *order, const cb_i64 *boff,
-                      cb_i64 nel, int nder /*1: B'DB, 2: B'D'DB*/,
-                      double *blocks, void *stream);
+                      const cb_i64 *woff, cb_i64 nel, int uniform_order, int max_order,
+                      int nder /*1: B'DB, 2: B'D'DB*/, double *blocks, void *stream);
 /* Dense (last-first+1)^2 column-major copy of the operator restricted to
  * functions first..last (1-based), what set_elements! builds
  * (src/fedvr_operators.jl:148-154); for export/tests on small bases. */
@@ -214,12 +238,23 @@ typedef struct cb_density_s cb_density;
 int cb_density_bspline_create(const cb_bspline *B, cb_i64 col0, cb_i64 ncols,
                               const double *wvals_host, cb_density **out);
 int cb_density_destroy(cb_density *D);
+/* Number of corrected-semi-normal-equation refinement steps per apply
+ * (default 0: plain banded Cholesky solve of the normal equations, which
+ * agrees with the dense pinv to ~cond(V)^2 eps, < 1e-12 for k <= 10). */
+int cb_density_set_refine(cb_density *D, int steps);
 /* copyto!(rho, f, g) (src/densities.jl:156-164).  f is nf x Pf, g is nf x Pg,
  * Pf==Pg or one of them 1 (broadcast, :57-72); rho is nf x max(Pf,Pg).
  * conj is accepted for ABI completeness (real Float64: no-op). */
 int cb_density_apply(const cb_density *D, const double *f, cb_i64 ldf, cb_i64 Pf,
                      const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
                      double *rho, cb_i64 ldr, void *stream);
+/* ftmp .* gtmp at the quadrature nodes (src/densities.jl:158-161), the
+ * rho.tmp that copyto!(M, rho) (:206-208) feeds to overlap_matrix! as the
+ * diagonal operator: pass it as `opvals` to cb_bspline_assemble.
+ * tmp is numnodes x max(Pf,Pg), leading dimension ldt. */
+int cb_density_nodal_product(const cb_density *D, const double *f, cb_i64 ldf, cb_i64 Pf,
+                             const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
+                             double *tmp, cb_i64 ldt, void *stream);
 /* Orthogonal branches (src/densities.jl:166-185): rho = c .* (f .* g);
  * c NULL for the uniform case (C = I). */
 int cb_density_orthogonal(const double *c, cb_i64 n,

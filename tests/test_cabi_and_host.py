@@ -1,0 +1,125 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/*.h declares,
+compute entry points fail loudly without a device, and the host logic of the Python mirror
+(knot sets, quadrature rules, FE-DVR grid and block structure) agrees with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import cbo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "compactbases_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from compactbases_jl_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/compactbases_cuda.h but not exported"
+    # and the ctypes table covers the header, so the Python mirror cannot silently miss an entry point
+    assert set(names) == set(_lib.EXPORTS)
+    assert b"sm_100a" in lib.cb_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    import compactbases_jl_b200 as cb
+    from compactbases_jl_b200 import _lib
+    with pytest.raises(RuntimeError):
+        cb.BSpline(cb.LinearKnotSet(3, 0, 1, 4))
+    # straight through the C ABI: status CB_ERR_CUDA, never a CPU result
+    tt = np.array([0.0, 0.5, 1.0]); xi = np.array([0.0]); wr = np.array([2.0])
+    h = C.c_void_p()
+    rc = _lib.load().cb_bspline_create(C.c_void_p(tt.ctypes.data), 3, 2, 2, 2, C.c_void_p(xi.ctypes.data),
+                                       C.c_void_p(wr.ctypes.data), 1, C.byref(h))
+    assert rc == _lib.CB_ERR_CUDA and h.value is None
+    n = C.c_int(-1)
+    assert _lib.load().cb_device_count(C.byref(n)) in (_lib.CB_ERR_CUDA, _lib.CB_OK)
+
+
+def test_argument_errors_before_any_device_work():
+    from compactbases_jl_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    tt = np.array([0.0, 1.0])
+    rc = lib.cb_bspline_create(C.c_void_p(tt.ctypes.data), 2, 3, 4, 3, None, None, 0, C.byref(h))
+    assert rc == _lib.CB_ERR_ARG and b"Left multiplicity" in lib.cb_last_error()
+    rc = lib.cb_tridiag_apply(None, None, None, 5, None, 5, 1, 1.0, 0.0, None, 5, None)
+    assert rc == _lib.CB_ERR_ARG
+    rc = lib.cb_fd_derivative(7, 2, None, None, 5, 1.0, 0, 5, 0.0, 0, None, None, None, None)
+    assert rc == _lib.CB_ERR_ARG and b"unknown scheme" in lib.cb_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+
+
+def test_knot_sets_match_oracle():
+    import compactbases_jl_b200 as cb
+    t = cb.LinearKnotSet(7, 0, 100, 1000)
+    assert np.array_equal(t.t, cbo.linear_knots(0, 100, 1000))
+    assert len(t) == 1013 and t.numfunctions() == 1006
+    assert np.array_equal(t.collect(), cbo.expand_knots(t.t, 7))
+    e = cb.ExpKnotSet(10, -3.0, 2.0, 200)
+    assert np.array_equal(e.t, cbo.exp_knots(-3.0, 2.0, 200)) and e.t[0] == 0.0
+    a = cb.ArbitraryKnotSet(3, [0.0, 1, 1, 3, 4, 6], 1, 3)
+    assert list(a.collect()) == [0.0, 1, 1, 3, 4, 6, 6, 6]           # test/bsplines/knot_sets.jl:47
+    assert a[1] == 0.0 and a[8] == 6.0
+    with pytest.raises(IndexError):
+        a[9]
+    assert list(a.nonempty_intervals()) == list(cbo.nonempty_intervals(a.collect()))
+    assert cb.LinearKnotSet(2, 0, 1, 2, 1, 1).numfunctions() == 1
+    with pytest.raises(ValueError):
+        cb.ArbitraryKnotSet(3, [0.0], 1, 1)
+
+
+def test_quadrature_rules_match_oracle():
+    import compactbases_jl_b200 as cb
+    from compactbases_jl_b200.quadrature import fma, lerp
+    for n in range(1, 21):
+        x, w = cb.gausslegendre(n)
+        xo, wo = cbo.gausslegendre(n)
+        assert np.max(np.abs(x - xo)) <= 2e-16 and np.max(np.abs(w - wo)) <= 4e-16
+        assert abs(w.sum() - 2) < 1e-15
+    for n in range(2, 21):
+        x, w = cb.gausslobatto(n)
+        xo, wo = cbo.gausslobatto(n)
+        assert np.max(np.abs(x - xo)) <= 2e-16 and np.max(np.abs(w - wo)) <= 4e-16
+    # test/bsplines/knot_sets.jl:254-259: 2-point rule
+    x, w = cb.gausslegendre(2)
+    np.testing.assert_allclose(x, [-1 / np.sqrt(3), 1 / np.sqrt(3)], rtol=1e-13)
+    assert [cb.num_quadrature_points(k, 3) for k in (7, 8, 10)] == [8, 9, 11]
+    rng = np.random.default_rng(0)
+    a, b, c = rng.standard_normal(500), rng.standard_normal(500), rng.standard_normal(500)
+    exact = np.array([cbo._fma(x_, y_, z_) for x_, y_, z_ in zip(a, b, c)])
+    assert np.array_equal(fma(a, b, c), exact)
+    assert np.array_equal(lerp(np.array([1.0]), np.array([3.0]), np.array([0.5])), [2.0])
+
+
+def test_host_only_fedvr_grid_matches_oracle():
+    from compactbases_jl_b200.fedvr import FEDVR
+    for t, order in [(cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8]), (cbo.julia_range(0, 1000, 101), 10)]:
+        B = FEDVR(t, order, device="host")
+        O = cbo.FEDVROracle(t, order)
+        assert np.array_equal(B.x, O.x) and np.array_equal(B.n, O.n) and np.array_equal(B.wcat, O.wcat)
+        assert np.array_equal(B.estart, O.estart) and np.array_equal(B.boff, O.boff)
+        assert B._block_structure() == O.block_structure()
+    B = FEDVR(cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8], device="host")
+    N = B.N
+    a = int(np.floor(0.4 * N + 0.5))
+    b = int(np.floor(0.6 * N + 0.5)) + 1
+    # test/fedvr/block_structure.jl:28-80
+    assert B._block_structure(1, b) == [3, 1, 1, 1, 2, 1, 1, 3, 1, 2, 1, 1]
+    assert B._block_structure(4, b) == [2, 1, 2, 1, 1, 3, 1, 2, 1, 1]
+    assert B._block_structure(a, N - 8) == [3, 1, 2, 1, 1, 2]
+    assert B.elements(1, b) == (1, 8)

@@ -1,0 +1,257 @@
+"""GPU parity: FE-DVR / finite-difference assembly and operator application (mul!) vs the
+CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import cbo
+from tests.util import RTOL, oracle_basis, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import torch
+    assert torch.cuda.is_available()
+    import compactbases_jl_b200 as cb
+    return cb
+
+
+def apply_gpu(cb, A, X, alpha=1.0, beta=0.0, Y0=None):
+    Xc = cb.ColMajor.from_numpy(X)
+    m = A.shape[0]
+    Yc = cb.ColMajor.from_numpy(np.zeros((m, Xc.nvec)) if Y0 is None else Y0)
+    if Y0 is None and beta == 0.0:
+        Yc.data.fill_(float("nan"))          # beta == 0 must not read Y
+    cb.mul(Yc, A, Xc, alpha, beta)
+    return Yc.numpy()
+
+
+FEDVR_CASES = [
+    ("o2", lambda: (cbo.julia_range(0, 5, 12), 2)),
+    ("o3", lambda: (cbo.julia_range(0, 5, 40), 3)),
+    ("o5_readme", lambda: (cbo.julia_range(0, 10, 5), 5)),
+    ("o10", lambda: (cbo.julia_range(0, 100, 101), 10)),
+    ("o16", lambda: (cbo.julia_range(-3, 3, 9), 16)),
+    ("mixed", lambda: (cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8])),
+    ("single", lambda: (cbo.julia_range(-10.0, 10.0, 2), 8)),
+    ("o20_generic", lambda: (cbo.julia_range(0, 3, 4), 20)),
+]
+
+
+@pytest.mark.parametrize("name,make", FEDVR_CASES, ids=[c[0] for c in FEDVR_CASES])
+def test_fedvr_assemble_and_apply(cb, name, make):
+    t, order = make()
+    B = cb.FEDVR(t, order)
+    O = cbo.FEDVROracle(t, order)
+    assert np.array_equal(B.x, O.x) and np.array_equal(B.n, O.n) and np.array_equal(B.wcat, O.wcat)
+    assert B.block_structure() == O.block_structure()
+    D = cb.Derivative()
+    rng = np.random.default_rng(7)
+    for nder, A in ((1, B.T @ D @ B), (2, B.T @ D.T @ D @ B)):
+        blk = O.blocks(nder)
+        assert relerr(A.blocks.cpu().numpy(), blk) <= RTOL
+        assert relerr(A.dense(), O.dense(blk)) <= RTOL
+        for nvec in (1, 3, 70):
+            X = rng.standard_normal((B.N, nvec))
+            Y0 = rng.standard_normal((B.N, nvec))
+            ref = O.apply(blk, X)
+            assert relerr(apply_gpu(cb, A, X), ref) <= RTOL
+            ref2 = O.apply(blk, X, 0.5, -2.0, Y0.copy(order="F"))
+            assert relerr(apply_gpu(cb, A, X, 0.5, -2.0, Y0), ref2) <= RTOL
+
+
+def test_fedvr_readme_golden_and_restrictions(cb, golden):
+    g = golden["docs"]["readme_fedvr"]
+    B = cb.FEDVR(cbo.julia_range(g["a"], g["b"], g["nel"] + 1), g["order"])
+    assert B.N == 17
+    D = cb.Derivative()
+    Br = B[:, g["sel"][0]:g["sel"][1]]
+    A = (Br.T @ D.T @ D @ Br)
+    Ad = A.dense()
+    assert Ad.shape == (15, 15) and A.block_structure() == [3, 1, 3, 1, 3, 1, 3]
+    np.testing.assert_allclose(Ad[:3, :3], g["block"], rtol=6e-6)
+    np.testing.assert_allclose(Ad[:3, 3], g["east"], rtol=6e-6)
+    np.testing.assert_allclose(Ad[3, 3], g["bridge_diag"], rtol=6e-6)
+    np.testing.assert_allclose(Ad[3, 7], g["bridge_corner"], rtol=6e-6)
+    # test/fedvr/derivatives.jl:46-111: restricted == sub-block, and apply of the restriction
+    rng = np.random.default_rng(8)
+    for order, sel, N in [(4, (2, 12), 5), (4, (1, 13), 5), ([5, 4, 2, 2], (5, 9), 5), ([5, 4, 3, 2], (5, 10), 5),
+                          (2, (2, 3), 5), (2, (1, 5), 5), (5, (2, 4), 2), (10, (7, 83), 11)]:
+        Bf = cb.FEDVR(cbo.julia_range(0, 20, N), order)
+        Bs = Bf[:, sel[0]:sel[1]]
+        O = cbo.FEDVROracle(cbo.julia_range(0, 20, N), order)
+        assert Bs.block_structure() == O.block_structure(*sel)
+        for nder, mid in ((1, [D]), (2, [D.T, D])):
+            full = Bf._materialize(Bf, mid)
+            sub = Bs._materialize(Bs, mid)
+            fd, sd = full.dense(), sub.dense()
+            assert np.array_equal(fd[sel[0] - 1:sel[1], sel[0] - 1:sel[1]], sd)
+            X = rng.standard_normal((sub.n, 5))
+            assert relerr(apply_gpu(cb, sub, X), sd @ X) <= RTOL
+
+
+def test_fedvr_config2_apply_properties(cb):
+    """BASELINE config 2 at full size: linearity, symmetry <Y,AX> = <AY,X>, oracle on a vector slice."""
+    import torch
+    t = cbo.julia_range(0, 1000, 10001)
+    B = cb.FEDVR(t, 10)
+    assert B.N == 90001
+    D = cb.Derivative()
+    A = B.T @ D.T @ D @ B
+    O = cbo.FEDVROracle(t, 10)
+    blk = O.blocks(2)
+    assert relerr(A.blocks.cpu().numpy(), blk) <= RTOL
+    g = torch.Generator(device="cuda").manual_seed(2)
+    X = torch.randn((1024, B.N), dtype=torch.float64, device="cuda", generator=g)
+    Y = torch.empty_like(X)
+    cb.mul(Y, A, X)
+    ref = O.apply(blk, np.asfortranarray(X[:16].cpu().numpy().T), threads=True)
+    assert relerr(Y[:16].cpu().numpy().T, ref) <= RTOL
+    ref_last = O.apply(blk, np.asfortranarray(X[-3:].cpu().numpy().T))
+    assert relerr(Y[-3:].cpu().numpy().T, ref_last) <= RTOL
+    # symmetry of the weak Laplacian: sum(Y .* Z) == sum(X .* (A Z))
+    Z = torch.randn((1024, B.N), dtype=torch.float64, device="cuda", generator=g)
+    AZ = torch.empty_like(Z)
+    cb.mul(AZ, A, Z)
+    s1, s2 = torch.sum(Y * Z).item(), torch.sum(X * AZ).item()
+    assert abs(s1 - s2) <= 1e-10 * abs(s1)
+    # linearity with alpha/beta: Y2 = 2*A*X - Y  == Y
+    Y2 = Y.clone()
+    cb.mul(Y2, A, X, 2.0, -1.0)
+    assert torch.max(torch.abs(Y2 - Y)).item() <= 1e-10 * torch.max(torch.abs(Y)).item()
+
+
+def test_fedvr_host_pipeline(cb):
+    t = cbo.julia_range(0, 50, 501)
+    B = cb.FEDVR(t, 6)
+    D = cb.Derivative()
+    A = B.T @ D.T @ D @ B
+    O = cbo.FEDVROracle(t, 6)
+    rng = np.random.default_rng(9)
+    X = np.asfortranarray(rng.standard_normal((B.N, 37)))
+    Y = np.asfortranarray(np.zeros((B.N, 37)))
+    A.mul_host(Y, X)
+    assert relerr(Y, O.apply(O.blocks(2), X)) <= RTOL
+    Y0 = np.asfortranarray(rng.standard_normal((B.N, 37)))
+    Y1 = Y0.copy(order="F")
+    A.mul_host(Y1, X, 0.25, 3.0)
+    assert relerr(Y1, O.apply(O.blocks(2), X, 0.25, 3.0, Y0.copy(order="F"))) <= RTOL
+
+
+def test_fd_stencils_bit_exact(cb, golden):
+    D = cb.Derivative()
+    R = cb.FiniteDifferences(5, 1.0)
+    G = R.T @ D @ R
+    assert np.all(G.d.cpu().numpy() == 0) and np.all(G.du.cpu().numpy() == 0.5) and np.all(G.dl.cpu().numpy() == -0.5)
+    Lp = R.T @ D.T @ D @ R
+    assert isinstance(Lp, cb.SymTridiagonal)
+    assert np.all(Lp.dv.cpu().numpy() == -2) and np.all(Lp.ev.cpu().numpy() == 1)
+    for N, rho in ((3, 0.25), (1000, 0.1), (7, 1e-3)):
+        R = cb.StaggeredFiniteDifferences(N, rho)
+        al, be, ga, de = cbo.fd_staggered_uniform(N)
+        dv, ev = cbo.fd_laplacian(al, be, rho)
+        Lp = R.T @ D.T @ D @ R
+        assert np.array_equal(Lp.dv.cpu().numpy(), dv) and np.array_equal(Lp.ev.cpu().numpy(), ev)
+        dl, d, du = cbo.fd_gradient(de, ga, rho)
+        G = R.T @ D @ R
+        assert np.array_equal(G.dl.cpu().numpy(), dl) and np.array_equal(G.du.cpu().numpy(), du)
+        CD = cb.CoulombDerivative(D, 1.0, 0)
+        LpZ = R.T @ CD.T @ CD @ R
+        assert np.array_equal(LpZ.dv.cpu().numpy(), cbo.laplacian_correction(dv, rho, 1.0, 0))
+        CD1 = cb.CoulombDerivative(D, 1.0, 1)
+        assert np.array_equal((R.T @ CD1.T @ CD1 @ R).dv.cpu().numpy(), dv)
+        if N > 4:                                                  # restriction == sub-block
+            Rr = R[:, 2:N - 1]
+            Lr = Rr.T @ D.T @ D @ Rr
+            assert np.array_equal(Lr.dv.cpu().numpy(), dv[1:-1]) and np.array_equal(Lr.ev.cpu().numpy(), ev[1:-1])
+    g = golden["docs"]["fd"]
+    R = cb.StaggeredFiniteDifferences(3, 0.25)
+    Lp = R.T @ D.T @ D @ R
+    np.testing.assert_allclose(Lp.ev.cpu().numpy(), g["staggered_N3_rho025"]["ev"], rtol=6e-6)
+    assert Lp.dv.cpu().numpy()[0] == g["staggered_N3_rho025"]["dv_1_uncorrected"]
+    # non-uniform staggered grid (log-linear-like), with and without a weight function
+    r = np.cumsum(np.geomspace(0.01, 0.3, 60))
+    R = cb.StaggeredFiniteDifferences(r)
+    al, be, ga, de = cbo.fd_staggered_nonuniform(r)
+    dv, ev = cbo.fd_laplacian(al, be, 1.0)
+    Lp = R.T @ D.T @ D @ R
+    assert np.array_equal(Lp.dv.cpu().numpy(), dv) and np.array_equal(Lp.ev.cpu().numpy(), ev)
+    dl, d, du = cbo.fd_gradient(de, ga, 1.0)
+    G = R.T @ D @ R
+    assert np.array_equal(G.dl.cpu().numpy(), dl) and np.array_equal(G.du.cpu().numpy(), du)
+    f = lambda x: 1.0 + x * x
+    alf, bef, _, _ = cbo.fd_staggered_nonuniform(r, lambda x: float(f(x)))
+    dvf, evf = cbo.fd_laplacian(alf, bef, 1.0)
+    Lw = R.T @ D.T @ cb.QuasiDiagonal(f) @ D @ R
+    assert np.array_equal(Lw.dv.cpu().numpy(), dvf) and np.array_equal(Lw.ev.cpu().numpy(), evf)
+
+
+@pytest.mark.parametrize("n,nvec", [(1, 3), (2, 1), (10, 3), (513, 7), (4097, 33), (100000, 5)])
+def test_tridiag_apply(cb, n, nvec):
+    import torch
+    rng = np.random.default_rng(n)
+    dl, d, du = rng.standard_normal(max(n - 1, 0)), rng.standard_normal(n), rng.standard_normal(max(n - 1, 0))
+    X = rng.standard_normal((n, nvec))
+    Y0 = rng.standard_normal((n, nvec))
+    T = cb.Tridiagonal(*(torch.as_tensor(v, device="cuda") for v in (dl, d, du)))
+    assert relerr(apply_gpu(cb, T, X), cbo.tridiag_apply(dl, d, du, X)) <= RTOL
+    assert relerr(apply_gpu(cb, T, X, -1.5, 0.5, Y0), cbo.tridiag_apply(dl, d, du, X, -1.5, 0.5, Y0.copy(order="F"))) <= RTOL
+    Dg = cb.Diagonal(torch.as_tensor(d, device="cuda"))
+    assert relerr(apply_gpu(cb, Dg, X, 2.0, 0.0), 2.0 * d[:, None] * X) <= RTOL
+
+
+def test_tridiag_host_pipeline_and_staggered(cb):
+    D = cb.Derivative()
+    N = 20011
+    R = cb.StaggeredFiniteDifferences(N, 1e-3)
+    Lp = R.T @ D.T @ D @ R
+    rng = np.random.default_rng(4)
+    X = np.asfortranarray(rng.standard_normal((N, 9)))
+    Y = np.asfortranarray(np.zeros((N, 9)))
+    Lp.mul_host(Y, X)
+    al, be, _, _ = cbo.fd_staggered_uniform(N)
+    dv, ev = cbo.fd_laplacian(al, be, 1e-3)
+    assert relerr(Y, cbo.tridiag_apply(ev, dv, ev, X)) <= RTOL
+    assert relerr(apply_gpu(cb, Lp, X), Y) <= 1e-15
+
+
+BANDED = [(10, 10, 2, 2), (50, 53, 3, 6), (53, 50, 6, 3), (300, 300, 0, 0), (129, 129, 12, 12), (1006, 1006, 6, 6),
+          (40, 40, -1, 2), (40, 40, 2, -1), (7, 7, 9, 9), (2000, 2000, 9, 9)]
+
+
+@pytest.mark.parametrize("m,n,l,u", BANDED)
+def test_banded_apply(cb, m, n, l, u):
+    import torch
+    rng = np.random.default_rng(m + n + l)
+    band = rng.standard_normal((n, l + u + 1))
+    A = cb.BandedMatrix(torch.as_tensor(band, device="cuda").contiguous(), m, n, l, u)
+    for nvec in (1, 5, 67):
+        X = rng.standard_normal((n, nvec))
+        Y0 = rng.standard_normal((m, nvec))
+        assert relerr(apply_gpu(cb, A, X), cbo.banded_apply(band, m, n, l, u, X)) <= RTOL
+        ref = cbo.banded_apply(band, m, n, l, u, X, 0.3, 1.7, Y0.copy(order="F"))
+        assert relerr(apply_gpu(cb, A, X, 0.3, 1.7, Y0), ref) <= RTOL
+
+
+def test_bspline_operator_apply_end_to_end(cb):
+    """B'D'D B assembled on the GPU then applied to a coefficient batch == oracle of both steps."""
+    t = cb.LinearKnotSet(7, 0, 100, 1000)
+    B = cb.BSpline(t)
+    D = cb.Derivative()
+    T = B.T @ D.T @ D @ B
+    te, q, x, w = oracle_basis(t)
+    band, l, u = cbo.bspline_assemble(te, 7, te, 7, x, w, q, 1, 1)
+    assert relerr(T.data.cpu().numpy(), band) <= RTOL
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((B.nf, 64))
+    assert relerr(apply_gpu(cb, T, X), cbo.banded_apply(band, B.nf, B.nf, l, u, X)) <= RTOL
+
+
+def test_apply_dimension_mismatch(cb):
+    import torch
+    T = cb.Tridiagonal(*(torch.zeros(s, dtype=torch.float64, device="cuda") for s in (4, 5, 4)))
+    X = cb.ColMajor.zeros(6, 2)
+    Y = cb.ColMajor.zeros(5, 2)
+    with pytest.raises(cb.DimensionMismatch):
+        cb.mul(Y, T, X)
