@@ -51,8 +51,8 @@ __global__ void density_cholesky_kernel(const double *__restrict__ gband, int W 
             for (int pp = k - 1; pp > p; --pp) {
                 const i64 cc = j - pp;
                 if (cc < 0) continue;
-                const int pc = (int)(c - cc);       // L_{c,cc} = ring[c % k][c-cc]
-                s -= row[pp] * ring[c % k][pc];
+                const int pc = (int)(c - cc);       // L_{c,cc} = ring[c % k][c-cc]; row j itself is still in `row`
+                s -= row[pp] * (p == 0 ? row[pp] : ring[c % k][pc]);
             }
             if (p == 0) {
                 if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }

@@ -51,7 +51,11 @@ class ColMajor:
     def __init__(self, data: torch.Tensor, n: int | None = None):
         if data.dim() == 1:
             data = data.unsqueeze(0)
-        assert data.dim() == 2 and data.dtype == torch.float64 and data.is_cuda and data.stride(1) == 1
+        assert data.dim() == 2 and data.dtype == torch.float64 and data.is_cuda
+        if data.shape[1] > 1 and data.stride(1) != 1:
+            raise ValueError("coefficient vectors must be contiguous (column-major n x nvec)")
+        if data.shape[1] <= 1:
+            data = data.contiguous()
         self.data = data
         self.n = data.shape[1] if n is None else n
         self.nvec = data.shape[0]
@@ -178,7 +182,7 @@ class FEDVRMatrix:
         return (self.n, self.n)
 
     def block_structure(self):
-        return self.basis.block_structure(self.first, self.last)
+        return self.basis._block_structure(self.first, self.last)
 
     def dense(self) -> np.ndarray:
         b = self.basis

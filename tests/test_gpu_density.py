@@ -53,7 +53,9 @@ def test_density_bspline_matches_pinv_oracle(cb, name, make):
     assert relerr(got, cbo.density_bspline(V, g, f1[:, 0], wvals=wfun(x))) <= RTOL
     with pytest.raises(cb.DimensionMismatch):
         cb.Density(B, nlhs=3, nrhs=4)
-    # partition of unity: density of (1, c) reproduces c
+    if t.ml != t.k or t.mr != t.k:
+        return
+    # partition of unity (full end multiplicities): density of (1, c) reproduces c
     c = np.sin(np.arange(1, nf + 1, dtype=np.float64))
     got = cb.Density(B).copyto(cb.ColMajor.from_numpy(np.ones(nf)), cb.ColMajor.from_numpy(c)).numpy()[:, 0]
     np.testing.assert_allclose(got, c, atol=1e-12, rtol=0)
