@@ -14,7 +14,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcompactbases_cuda.so")
+# CB_CUDA_LIB overrides the path (development: kernel-variant sweeps); the default is the in-tree build
+LIB_PATH = os.environ.get("CB_CUDA_LIB") or os.path.join(_HERE, "libcompactbases_cuda.so")
 
 CB_OK, CB_ERR_ARG, CB_ERR_CUDA, CB_ERR_UNSUPPORTED, CB_ERR_ALLOC = 0, 1, 2, 3, 4
 

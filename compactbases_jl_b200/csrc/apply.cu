@@ -207,46 +207,141 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
 }
 
 // ---------------------------------------------------------------------------
-// K8: FE-DVR element-block operator, uniform order O (compile time).
-// CTA tile: FE_ET elements x FE_TV vectors; thread = (vector lane, element group).
-// Tile rows (local r <-> global node  gbase + r):
-//   elements eA..eA+FE_ET-1 occupy rows 0..FE_ET*(O-1); the halo element
-//   eA+FE_ET (needed for the last bridge row) adds O-1 more rows.
-// A thread owns, for each of its elements, local rows 1..O-1 (the bridge row at
-// the end is shared with the next element, whose first matrix row it adds);
-// global row 0 is owned by the very first element.
+// Asynchronous tile movers for interior tiles (every row and vector in range).
+//
+// cp.async (LDGSTS) copies global -> shared memory without a register round trip, so a CTA can
+// keep several tiles in flight while it computes on another one: on B200 an HBM-bound kernel needs
+// ~80 KB of loads in flight per SM at all times (6.5 TB/s x ~1.7 us / 148 SMs); a CTA that loads,
+// computes and stores one tile at a time measured 3.2 TB/s here.  8-byte copies keep the only
+// alignment requirement that of a double: Julia's column-major batches have arbitrary (often odd)
+// leading dimensions, e.g. 90 001, which also rules out TMA tensor maps (global strides must be
+// multiples of 16 bytes).
 // ---------------------------------------------------------------------------
-constexpr int FE_THREADS = 256;
-constexpr int FE_TV = 64;                           // vectors per CTA
-constexpr int FE_NG = FE_THREADS / FE_TV;           // element groups per CTA (4)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int O, int EG>   // EG elements per thread
-__global__ void __launch_bounds__(FE_THREADS)
+template <int ROWS, int TV, int NWARPS>
+__device__ __forceinline__ void load_tile_async(double *xs, int pitch, const double *__restrict__ X, i64 ldx,
+                                                i64 g0, i64 v0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NIT = (ROWS + 31) / 32;
+#pragma unroll 4
+    for (int v = warp; v < TV; v += NWARPS) {
+        const double *xc = X + (v0 + v) * ldx + g0;
+        double *xd = xs + v * pitch;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int r = lane + 32 * i;
+            if (32 * i + 31 < ROWS || r < ROWS) cp_async8(xd + r, xc + r);
+        }
+    }
+}
+
+// Stores alpha * tile rows [r_lo, r_hi) (beta == 0: Y is not read); lanes run along the rows.
+template <int TV, int NWARPS>
+__device__ __forceinline__ void store_tile_fast(const double *ys, int pitch, double *__restrict__ Y, i64 ldy,
+                                                i64 g0, int r_lo, int r_hi, i64 v0, double alpha) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 2
+    for (int v = warp; v < TV; v += NWARPS) {
+        double *yc = Y + (v0 + v) * ldy + g0;
+        for (int r = r_lo + lane; r < r_hi; r += 32) __stcs(yc + r, alpha * ys[v * pitch + r]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K8: FE-DVR element-block operator, uniform order O (compile time).
+//
+// Persistent CTAs, NS-stage shared-memory ring.  A tile is ET = NG*EG elements x 32 vectors; tile
+// rows (local r <-> global node gbase + r): elements eA..eA+ET-1 occupy rows 0..ET*(O-1); the halo
+// element eA+ET (needed for the last bridge row) adds O-1 more rows.  Each iteration issues the
+// copies of the tile NS-1 ahead, waits for the current one, computes it in place and streams the
+// result out.  In the compute phase thread = (vector lane, element group): it owns, for each of its
+// elements, local rows 1..O-1 (the bridge row at the end is shared with the next element, whose
+// first matrix row it adds); global row 0 is owned by the very first element.  Lanes run over
+// vectors, so block entries are warp-uniform (broadcast) 16-byte shared-memory loads and the x
+// values are conflict-free (odd pitch) column reads.
+// ---------------------------------------------------------------------------
+constexpr int FE_TV = 32;                           // vectors per tile (one warp wide)
+// Measured on B200 (C2: order 10, 1e4 elements, 1024 vectors; device time of one apply):
+//   EG x NG x NS = 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 2x8x3: 511 | 1x4x3: 584 | 1x8x6: 718
+// More stages cost resident warps and the kernel is bound by warp-level latency in its compute and
+// store phases, not by bytes in flight (a bare cp.async tile stream reaches 5.2 TB/s, see
+// scripts/micro/stream.cu), so the default is one stage per CTA and as many CTAs per SM as fit.
+#ifndef FEDVR_EG10
+#define FEDVR_EG10 4
+#endif
+#ifndef FEDVR_NG
+#define FEDVR_NG 4
+#endif
+#ifndef FEDVR_NS
+#define FEDVR_NS 1
+#endif
+
+template <int O, int EG, int NG, int NS>   // EG elements per thread, NG element groups (warps), NS pipeline stages
+__global__ void __launch_bounds__(32 * NG)
 fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
                    const double *__restrict__ X, i64 ldx, i64 nvec,
                    double alpha, double beta, double *__restrict__ Y, i64 ldy) {
-    constexpr int ET = FE_NG * EG;                  // elements per CTA tile
+    constexpr int THREADS = 32 * NG;
+    constexpr int ET = NG * EG;                     // elements per tile
     constexpr int ROWS = (ET + 1) * (O - 1) + 1;    // incl. halo element
     constexpr int PITCH = ROWS | 1;
-    extern __shared__ double sm[];
-    double *xs = sm;                                // [FE_TV][PITCH]
-    double *bs = xs + FE_TV * PITCH;                // [(ET+1)][O*O] column-major blocks
-    const int vl = threadIdx.x % FE_TV, g = threadIdx.x / FE_TV;
+    constexpr int OP = O + (O & 1);                 // padded column height of a block in shared memory (even)
+    constexpr int BS_SIZE = (ET + 1) * O * OP;      // [(ET+1)][O][OP] column-major blocks, 16-byte aligned columns
+    constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);   // blocks + x tile [32][PITCH]
+    extern __shared__ __align__(16) double sm[];
+    const int vl = threadIdx.x & 31, g = threadIdx.x >> 5;
     const i64 net = (nel + ET - 1) / ET;
     const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
-    for (i64 tile = blockIdx.x; tile < net * nvt; tile += gridDim.x) {
-        const i64 et = tile / nvt, vt = tile - et * nvt;
-        const i64 eA = et * ET;
-        const i64 v0 = vt * FE_TV;
-        const i64 gbase = eA * (O - 1);             // global node of tile row 0
-        __syncthreads();
-        // X rows are indexed relative to the restriction: X row = node - first0
-        load_tile<FE_THREADS>(xs, PITCH, X, ldx, nrows, gbase - first0, ROWS, v0, FE_TV, nvec);
-        for (int e = threadIdx.x; e < (ET + 1) * O * O; e += FE_THREADS) {
-            i64 el = eA + e / (O * O);
-            bs[e] = el < nel ? blocks[el * (O * O) + e % (O * O)] : 0.0;
+    const i64 ntiles = net * nvt;
+    // tile -> coordinates; element tiles vary fastest so that the CTAs running at one time stream
+    // long contiguous row ranges of a few vector groups
+    auto coords = [&](i64 tile, i64 &eA, i64 &v0, i64 &x0row, bool &interior) {
+        const i64 vt = tile / net, et = tile - vt * net;
+        eA = et * ET;
+        v0 = vt * FE_TV;
+        x0row = eA * (O - 1) - first0;              // X/Y row of tile row 0 (rows are relative to the restriction)
+        interior = x0row >= 0 && x0row + ROWS <= nrows && v0 + FE_TV <= nvec && eA + ET + 1 <= nel;
+    };
+    auto issue = [&](i64 tile, int st) {            // always commits one cp.async group
+        if (tile < ntiles) {
+            double *bs_ = sm + st * STAGE, *xs_ = bs_ + BS_SIZE;
+            i64 eA, v0, x0row; bool interior;
+            coords(tile, eA, v0, x0row, interior);
+            if (interior) load_tile_async<ROWS, FE_TV, NG>(xs_, PITCH, X, ldx, x0row, v0);
+            else load_tile<THREADS>(xs_, PITCH, X, ldx, nrows, x0row, ROWS, v0, FE_TV, nvec);
+            if (OP == O && interior) {              // same layout as in global memory: straight copy
+                const double *bsrc = blocks + eA * (O * O);
+                for (int e = threadIdx.x; e < (ET + 1) * O * O; e += THREADS) cp_async8(bs_ + e, bsrc + e);
+            } else {
+                for (int e = threadIdx.x; e < (ET + 1) * O * O; e += THREADS) {
+                    const int el = e / (O * O), rem = e - el * (O * O), mp = rem / O, mm = rem - mp * O;
+                    bs_[(el * O + mp) * OP + mm] = (eA + el < nel) ? __ldg(blocks + (eA + el) * (O * O) + rem) : 0.0;
+                }
+            }
         }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) issue((i64)blockIdx.x + (i64)p * gridDim.x, p);
+    int stage = 0;
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        {   // the stage freed at the end of the previous iteration receives the tile NS-1 ahead
+            // (NS == 1: this tile itself; other resident CTAs cover the wait)
+            int st = stage + NS - 1; if (st >= NS) st -= NS;
+            issue(tile + (i64)(NS - 1) * gridDim.x, st);
+        }
+        cp_async_wait<NS - 1>();                    // this tile's group has landed
         __syncthreads();
+        i64 eA, v0, x0row; bool interior;
+        coords(tile, eA, v0, x0row, interior);
+        double *bs = sm + stage * STAGE, *xs = bs + BS_SIZE;
         double *xv = xs + vl * PITCH;
         const int eL0 = g * EG;                     // first tile-local element of this thread
         // phase 1: values other threads will overwrite in phase 2
@@ -254,10 +349,10 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
         double halo = 0.0;                          // first matrix row of the element after my last
         {
             const int eh = eL0 + EG;
-            const double *bh = bs + eh * O * O;
+            const double *bh = bs + eh * O * OP;
             const double *xh = xv + eh * (O - 1);
 #pragma unroll
-            for (int mp = 0; mp < O; ++mp) halo = fma(bh[O * mp], xh[mp], halo);
+            for (int mp = 0; mp < O; ++mp) halo = fma(bh[OP * mp], xh[mp], halo);
         }
         __syncthreads();
         // phase 2: own elements, results written in place over my own rows
@@ -266,18 +361,23 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
 #pragma unroll
         for (int s = 0; s < EG; ++s) {
             const int eL = eL0 + s;
-            const double *b = bs + eL * O * O;
+            const double *b = bs + eL * O * OP;
             double *xe = xv + eL * (O - 1);
-            double xr[O], acc[O];
+            double xr[O], acc[OP];
             xr[0] = x0;
 #pragma unroll
             for (int mp = 1; mp < O; ++mp) xr[mp] = xe[mp];
 #pragma unroll
-            for (int mm = 0; mm < O; ++mm) acc[mm] = 0.0;
+            for (int mm = 0; mm < OP; ++mm) acc[mm] = 0.0;
 #pragma unroll
             for (int mp = 0; mp < O; ++mp) {
+                const double2 *b2 = reinterpret_cast<const double2 *>(b + OP * mp);
 #pragma unroll
-                for (int mm = 0; mm < O; ++mm) acc[mm] = fma(b[mm + O * mp], xr[mp], acc[mm]);
+                for (int m2 = 0; m2 < OP / 2; ++m2) {
+                    const double2 bb = b2[m2];
+                    acc[2 * m2] = fma(bb.x, xr[mp], acc[2 * m2]);
+                    acc[2 * m2 + 1] = fma(bb.y, xr[mp], acc[2 * m2 + 1]);
+                }
             }
             if (s == 0) y_first = acc[0];           // row 0 of my first element (owned by the group before me)
             else xe[0] = carry + acc[0];            // bridge row between my elements s-1 and s
@@ -291,11 +391,15 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
         if (eA == 0 && g == 0) xv[0] = y_first;
         __syncthreads();
         // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
-        int r_lo = (eA == 0) ? 0 : 1;
-        i64 last_el = eA + ET < nel ? eA + ET : nel;            // elements actually present
-        int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
-        store_tile<FE_THREADS>(xs, PITCH, Y, ldy, nrows, gbase - first0, r_lo, r_hi, v0, FE_TV, nvec, alpha, beta);
+        const int r_lo = (eA == 0) ? 0 : 1;
+        const i64 last_el = eA + ET < nel ? eA + ET : nel;            // elements actually present
+        const int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
+        if (interior && beta == 0.0) store_tile_fast<FE_TV, NG>(xs, PITCH, Y, ldy, x0row, r_lo, r_hi, v0, alpha);
+        else store_tile<THREADS>(xs, PITCH, Y, ldy, nrows, x0row, r_lo, r_hi, v0, FE_TV, nvec, alpha, beta);
+        __syncthreads();                            // the stage may be refilled
+        if (++stage == NS) stage = 0;
     }
+    cp_async_wait<0>();
 }
 
 // Generic FE-DVR apply (per-element orders): thread per (row, vector); each row
@@ -370,17 +474,26 @@ static int check_apply_args(const char *who, i64 m, i64 n, const double *X, i64 
 template <int O>
 static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, const double *X, i64 ldx, i64 nvec,
                         double alpha, double beta, double *Y, i64 ldy, cudaStream_t st) {
-    // elements per thread: keep the tile near 150 rows
-    constexpr int EG = (O <= 3) ? 16 : (O <= 5) ? 8 : (O <= 10) ? 4 : 2;
-    constexpr int ET = FE_NG * EG;
+    constexpr int EG = (O <= 3) ? 4 : (O <= 5) ? 2 : (O <= 10) ? FEDVR_EG10 : 1;
+    constexpr int NG = (O <= 12) ? FEDVR_NG : 4;
+    constexpr int NS = FEDVR_NS;
+    constexpr int ET = NG * EG;
     constexpr int ROWS = (ET + 1) * (O - 1) + 1;
     constexpr int PITCH = ROWS | 1;
-    size_t smem = sizeof(double) * ((size_t)FE_TV * PITCH + (size_t)(ET + 1) * O * O);
-    auto kern = fedvr_apply_kernel<O, EG>;
+    constexpr int OP = O + (O & 1);
+    constexpr int BS_SIZE = (ET + 1) * O * OP;
+    constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);
+    size_t smem = sizeof(double) * (size_t)NS * STAGE;
+    static_assert(sizeof(double) * (size_t)NS * STAGE <= 227 * 1024, "pipeline does not fit in shared memory");
+    auto kern = fedvr_apply_kernel<O, EG, NG, NS>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
-    int grid = (int)(tiles < (i64)CB_NUM_SMS * 16 ? tiles : (i64)CB_NUM_SMS * 16);
-    kern<<<grid, FE_THREADS, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? 4 : 1);   // pipelined: one persistent wave of CTAs
+    int grid = (int)(tiles < cap ? tiles : cap);
+    kern<<<grid, 32 * NG, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

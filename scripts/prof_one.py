@@ -1,0 +1,47 @@
+"""Runs ONE kernel family a few times (for ncu captures).  usage: prof_one.py {fedvr|eval|asm3|banded|density|tridiag}"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import compactbases_jl_b200 as cb
+from compactbases_jl_b200 import _lib
+from compactbases_jl_b200.operators import _ptr, _stream
+what = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+D = cb.Derivative()
+if what == "fedvr":
+    F = cb.FEDVR(np.linspace(0, 1000, 10001), 10)
+    A = F.T @ D.T @ D @ F
+    X = torch.randn((1024, F.N), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    fn = lambda: cb.mul(Y, A, X)
+elif what == "eval":
+    B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
+    nx = 16_000_000
+    x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
+    iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 7), dtype=torch.float64, device="cuda")
+    fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
+elif what == "asm3":
+    B = cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 200000))
+    fn = lambda: (B.T @ cb.CoulombPotential(1.0) @ B, B.T @ D.T @ D @ B)
+elif what == "banded":
+    B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
+    S = B.T @ D.T @ D @ B
+    X = torch.randn((65536, B.nf), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    fn = lambda: cb.mul(Y, S, X)
+elif what == "density":
+    B = cb.BSpline(cb.LinearKnotSet(8, 0, 500, 50000))
+    P = 1024
+    rho = cb.Density(B, nlhs=P, nrhs=P)
+    f = torch.randn((P, B.nf), dtype=torch.float64, device="cuda"); g = torch.randn((P, B.nf), dtype=torch.float64, device="cuda")
+    o = cb.ColMajor.zeros(B.nf, P)
+    fn = lambda: rho.copyto(cb.ColMajor(f), cb.ColMajor(g), o)
+elif what == "tridiag":
+    R = cb.StaggeredFiniteDifferences(10_000_000, 1e-3)
+    Lp = R.T @ D.T @ D @ R
+    X = torch.randn((128, 10_000_000), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    fn = lambda: cb.mul(Y, Lp, X)
+for _ in range(reps):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+print(what, "ms", e0.elapsed_time(e1))
