@@ -143,70 +143,6 @@ __device__ __forceinline__ void store_tile(const double *ys, int pitch, double *
 }
 
 // ---------------------------------------------------------------------------
-// K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x BT_VEC vectors.  Thread =
-// (vector lane, row group of BR rows): sweeps the BR+l+u window of x once,
-// each x value feeding up to BR accumulators; the band tile sits in shared
-// memory zero-padded so that no predicate is needed in the inner loop.
-// ---------------------------------------------------------------------------
-constexpr int BT_THREADS = 256;
-constexpr int BT_VEC = 32;                          // vectors per CTA (= one warp wide)
-constexpr int BR = 8;                               // rows per thread
-constexpr int BT_ROWS = (BT_THREADS / BT_VEC) * BR; // 64 rows per CTA tile
-
-__global__ void __launch_bounds__(BT_THREADS)
-banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
-                    const double *__restrict__ X, i64 ldx, i64 nvec,
-                    double alpha, double beta, double *__restrict__ Y, i64 ldy) {
-    extern __shared__ double sm[];
-    const int W = l + u + 1;
-    const int xrows = BT_ROWS + l + u;
-    const int pitch = xrows | 1;
-    double *xs = sm;                                // [BT_VEC][pitch]
-    double *as = xs + BT_VEC * pitch;               // [BT_ROWS / BR][BR + W - 1][BR], zero padded
-    const int acols = BR + W - 1;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
-    const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
-    for (i64 tile = blockIdx.x; tile < nrt * nvt; tile += gridDim.x) {
-        const i64 rt = tile / nvt, vt = tile - rt * nvt;
-        const i64 i0 = rt * BT_ROWS;                // first row of the tile
-        const i64 v0 = vt * BT_VEC;
-        __syncthreads();                            // previous tile fully consumed
-        // x window rows i0-l .. i0+BT_ROWS-1+u  (columns of A)
-        load_tile<BT_THREADS>(xs, pitch, X, ldx, n, i0 - l, xrows, v0, BT_VEC, nvec);
-        // band tile: as[g][c][r] = A(i0+g*BR+r, i0+g*BR-l+c), 0 outside band/matrix
-        for (int e = threadIdx.x; e < (BT_ROWS / BR) * acols * BR; e += BT_THREADS) {
-            int r = e % BR, c = (e / BR) % acols, g = e / (BR * acols);
-            i64 i = i0 + g * BR + r, j = i0 + g * BR - l + c;
-            double a = 0.0;
-            if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = band[(u + i - j) + (i64)W * j];
-            as[e] = a;
-        }
-        __syncthreads();
-        double acc[BR];
-#pragma unroll
-        for (int r = 0; r < BR; ++r) acc[r] = 0.0;
-        const double *xv = xs + lane * pitch + rg * BR;          // x window of this row group
-        const double *ag = as + rg * acols * BR;
-        for (int c = 0; c < acols; ++c) {
-            const double xc = xv[c];
-            const double2 *a2 = reinterpret_cast<const double2 *>(ag + c * BR);
-#pragma unroll
-            for (int r2 = 0; r2 < BR / 2; ++r2) {
-                double2 a = a2[r2];
-                acc[2 * r2] = fma(a.x, xc, acc[2 * r2]);
-                acc[2 * r2 + 1] = fma(a.y, xc, acc[2 * r2 + 1]);
-            }
-        }
-        __syncthreads();                            // everyone done reading xs
-#pragma unroll
-        for (int r = 0; r < BR; ++r) xs[lane * pitch + rg * BR + r] = acc[r];   // tile-local row index
-        __syncthreads();
-        store_tile<BT_THREADS>(xs, pitch, Y, ldy, m, i0, 0, BT_ROWS, v0, BT_VEC, nvec, alpha, beta);
-    }
-}
-
-// ---------------------------------------------------------------------------
 // Asynchronous tile movers for interior tiles (every row and vector in range).
 //
 // cp.async (LDGSTS) copies global -> shared memory without a register round trip, so a CTA can
@@ -251,6 +187,123 @@ __device__ __forceinline__ void store_tile_fast(const double *ys, int pitch, dou
     for (int v = warp; v < TV; v += NWARPS) {
         double *yc = Y + (v0 + v) * ldy + g0;
         for (int r = r_lo + lane; r < r_hi; r += 32) __stcs(yc + r, alpha * ys[v * pitch + r]);
+    }
+}
+
+// Runtime-row-count variant of load_tile_async with clipping: tile rows whose global row g0 + r
+// lies outside [0, n) and vectors >= nvec are zero-filled.
+template <int TV, int NWARPS>
+__device__ __forceinline__ void load_tile_async_rt(double *xs, int pitch, const double *__restrict__ X, i64 ldx, i64 n,
+                                                   i64 g0, int rows, i64 v0, i64 nvec) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rlo = g0 < 0 ? (int)(-g0 < rows ? -g0 : rows) : 0;
+    const int rhi = g0 + rows > n ? (int)(n - g0 > 0 ? n - g0 : 0) : rows;
+#pragma unroll 2
+    for (int v = warp; v < TV; v += NWARPS) {
+        double *xd = xs + v * pitch;
+        if (v0 + v < nvec) {
+            const double *xc = X + (v0 + v) * ldx + g0;
+            for (int r = rlo + lane; r < rhi; r += 32) cp_async8(xd + r, xc + r);
+            for (int r = lane; r < rlo; r += 32) xd[r] = 0.0;
+            for (int r = rhi + lane; r < rows; r += 32) xd[r] = 0.0;
+        } else {
+            for (int r = lane; r < rows; r += 32) xd[r] = 0.0;
+        }
+    }
+}
+
+// Clipped variant of store_tile_fast: rows [r_lo, r_hi) (already clipped by the caller), vectors < nvec.
+template <int TV, int NWARPS>
+__device__ __forceinline__ void store_tile_fast_clip(const double *ys, int pitch, double *__restrict__ Y, i64 ldy,
+                                                     i64 g0, int r_lo, int r_hi, i64 v0, i64 nvec, double alpha) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 2
+    for (int v = warp; v < TV; v += NWARPS) {
+        if (v0 + v >= nvec) break;
+        double *yc = Y + (v0 + v) * ldy + g0;
+        for (int r = r_lo + lane; r < r_hi; r += 32) __stcs(yc + r, alpha * ys[v * pitch + r]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x 32 vectors.  Thread = (vector lane, row group
+// of BR rows): it sweeps the BR+l+u window of x once, each x value feeding up to BR accumulators;
+// the band tile sits in shared memory, zero padded, so that the inner loop needs no predicate and
+// its coefficient loads are warp-uniform 16-byte broadcasts.
+// ---------------------------------------------------------------------------
+constexpr int BT_VEC = 32;                          // vectors per CTA (= one warp wide)
+constexpr int BT_NG = 8;                            // row groups (warps) per CTA
+constexpr int BR = 16;                              // rows per thread
+constexpr int BT_THREADS = 32 * BT_NG;
+constexpr int BT_ROWS = BT_NG * BR;                 // 128 rows per CTA tile
+
+__global__ void __launch_bounds__(BT_THREADS)
+banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
+                    const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk,
+                    double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    extern __shared__ __align__(16) double sm[];
+    const int W = l + u + 1;
+    const int xrows = BT_ROWS + l + u;
+    const int pitch = xrows | 1;
+    const int acols = BR + W - 1;
+    double *as = sm;                                // [BT_NG][acols][BR], zero padded (16-byte aligned rows)
+    double *xs = sm + BT_NG * acols * BR;           // [BT_VEC][pitch]
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
+    const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
+    // work item = (row tile, chunk of vchunk vector tiles): the band tile is staged once per item
+    const i64 nvc = (nvt + vchunk - 1) / vchunk;
+    for (i64 item = blockIdx.x; item < nrt * nvc; item += gridDim.x) {
+      const i64 vc = item / nrt, rt = item - vc * nrt;              // row tiles vary fastest (contiguous streams)
+      const i64 i0 = rt * BT_ROWS;                  // first row of the tile
+      __syncthreads();                              // previous item fully consumed
+      // band tile: as[g][c][r] = A(i0+g*BR+r, i0+g*BR-l+c), 0 outside band/matrix
+      {
+          const int r = threadIdx.x % BR, c0 = threadIdx.x / BR;    // no runtime divisions in the fill loops
+#pragma unroll
+          for (int g = 0; g < BT_NG; ++g) {
+              const i64 i = i0 + g * BR + r;
+              for (int c = c0; c < acols; c += BT_THREADS / BR) {
+                  const i64 j = i0 + g * BR - l + c;
+                  double a = 0.0;
+                  if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = __ldg(band + (u + i - j) + (i64)W * j);
+                  as[(g * acols + c) * BR + r] = a;
+              }
+          }
+      }
+      const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+      for (i64 vt = vc * vchunk; vt < vt_end; ++vt) {
+        const i64 v0 = vt * BT_VEC;
+        __syncthreads();                            // previous tile fully consumed
+        // x window rows i0-l .. i0+BT_ROWS-1+u  (columns of A), zero outside the matrix
+        load_tile_async_rt<BT_VEC, BT_NG>(xs, pitch, X, ldx, n, i0 - l, xrows, v0, nvec);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double acc[BR];
+#pragma unroll
+        for (int r = 0; r < BR; ++r) acc[r] = 0.0;
+        const double *xv = xs + lane * pitch + rg * BR;          // x window of this row group
+        const double *ag = as + rg * acols * BR;
+#pragma unroll 2
+        for (int c = 0; c < acols; ++c) {
+            const double xc = xv[c];
+            const double2 *a2 = reinterpret_cast<const double2 *>(ag + c * BR);
+#pragma unroll
+            for (int r2 = 0; r2 < BR / 2; ++r2) {
+                const double2 a = a2[r2];
+                acc[2 * r2] = fma(a.x, xc, acc[2 * r2]);
+                acc[2 * r2 + 1] = fma(a.y, xc, acc[2 * r2 + 1]);
+            }
+        }
+        __syncthreads();                            // everyone done reading xs
+#pragma unroll
+        for (int r = 0; r < BR; ++r) xs[lane * pitch + rg * BR + r] = acc[r];   // tile-local row index
+        __syncthreads();
+        const int r_hi = m - i0 < BT_ROWS ? (int)(m - i0) : BT_ROWS;
+        if (beta == 0.0) store_tile_fast_clip<BT_VEC, BT_NG>(xs, pitch, Y, ldy, i0, 0, r_hi, v0, nvec, alpha);
+        else store_tile<BT_THREADS>(xs, pitch, Y, ldy, m, i0, 0, BT_ROWS, v0, BT_VEC, nvec, alpha, beta);
+      }
     }
 }
 
@@ -553,12 +606,16 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     const int W = l + u + 1;
     const int xrows = BT_ROWS + l + u;
     const int pitch = xrows | 1;
-    size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)(BT_ROWS / BR) * (BR + W - 1) * BR);
+    size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)BT_NG * (BR + W - 1) * BR);
     if (smem > 200 * 1024) { cb_set_error("cb_banded_apply: bandwidth %d too large for the shared-memory tile", W); return CB_ERR_UNSUPPORTED; }
     CB_CUDA(cudaFuncSetAttribute(banded_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    i64 tiles = ((m + BT_ROWS - 1) / BT_ROWS) * ((nvec + BT_VEC - 1) / BT_VEC);
-    int grid = (int)(tiles < (i64)CB_NUM_SMS * 16 ? tiles : (i64)CB_NUM_SMS * 16);
-    banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, alpha, beta, Y, ldy);
+    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS, nvt = (nvec + BT_VEC - 1) / BT_VEC;
+    // vector tiles per work item: amortise the band-tile staging while keeping >= ~8 items per SM
+    i64 vchunk = nrt * nvt / ((i64)CB_NUM_SMS * 8);
+    vchunk = vchunk < 1 ? 1 : (vchunk > 16 ? 16 : vchunk);
+    const i64 items = nrt * ((nvt + vchunk - 1) / vchunk);
+    int grid = (int)(items < (i64)CB_NUM_SMS * 24 ? items : (i64)CB_NUM_SMS * 24);
+    banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, (int)vchunk, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

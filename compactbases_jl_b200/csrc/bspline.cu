@@ -46,45 +46,91 @@ __global__ void lgwt_kernel(KnotView kv, const i64 *__restrict__ ivlist, i64 ni,
 }
 
 // ---------------------------------------------------------------------------
-// K1: batched evaluation, one thread per point, rows staged through shared
-// memory so that the K-wide rows leave the SM as coalesced 16-byte stores.
+// K1: batched evaluation, one thread per point.
+//
+// Knots are staged in shared memory once per (persistent) CTA when they fit: with unsorted
+// points every lane of a warp looks at a different interval, and 24 scattered 8-byte reads per
+// point made the first version of this kernel L1-wavefront bound (ncu, round 1: 2.0 TB/s of 6.5).
+// The interval comes from an interpolation guess that is then checked against the actual knots, so
+// the result is exactly "last i with t[i] <= x" (find_interval, src/knot_sets.jl:209-216) for any
+// knot distribution; if the guess is off, a binary search takes over.  The K-wide rows are staged
+// through shared memory so that they leave the SM as coalesced 16-byte stores.
 // ---------------------------------------------------------------------------
 constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_SMEM_KNOTS = 6144;              // largest t.t staged in shared memory (48 KB)
 
-template <int K>
-__global__ void __launch_bounds__(EVAL_THREADS)
+// first index in [0, n_tt) with tt[idx] > x (n_tt if none), x inside [tt[0], tt[n_tt-1])
+__device__ __forceinline__ int upper_bound_guess(const double *tt, int n_tt, double x, double first, double scale) {
+    int g = (int)((x - first) * scale);
+    g = g < 0 ? 0 : (g > n_tt - 2 ? n_tt - 2 : g);
+    const double a = tt[g], b = tt[g + 1];
+    if (a <= x && b > x) return g + 1;
+    int lo, hi;
+    if (a > x) { lo = 0; hi = g; } else { lo = g + 2; hi = n_tt; }   // tt[g+1] <= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tt[mid] > x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+template <int K, bool SMEM_KNOTS, int MT>
+__global__ void __launch_bounds__(EVAL_THREADS, 4)
 bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, int m,
                     int32_t *__restrict__ interval, double *__restrict__ vals, int vec_ok) {
     constexpr int KP = K | 1;                      // odd row pitch: conflict-free staging
     __shared__ double stage[EVAL_THREADS / 32][32 * KP];
+    extern __shared__ double sknots[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *sw = stage[warp];
+    const int n_tt = (int)kv.n_tt;
+    const double *tt = kv.tt;
+    if (SMEM_KNOTS) {
+        for (int i = threadIdx.x; i < n_tt; i += EVAL_THREADS) sknots[i] = kv.tt[i];
+        __syncthreads();
+        tt = sknots;
+    }
+    const double first = kv.tt[0], last = kv.tt[n_tt - 1];
+    const double scale = (double)(n_tt - 1) / (last - first);
     const i64 nblk = (nx + EVAL_THREADS - 1) / EVAL_THREADS;
+    // the point of the next iteration is loaded before this one is evaluated (one load in flight per thread)
+    double xnext = 0.0;
+    if ((i64)blockIdx.x * EVAL_THREADS + threadIdx.x < nx) xnext = __ldcs(x + (i64)blockIdx.x * EVAL_THREADS + threadIdx.x);
     for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const i64 wbase = blk * EVAL_THREADS + warp * 32;   // first point of this warp
         const i64 p = wbase + lane;
+        const double xp = xnext;
+        {
+            const i64 pn = p + (i64)gridDim.x * EVAL_THREADS;
+            if (pn < nx) xnext = __ldcs(x + pn);
+        }
         double N[K];
-        int I = 0;
+#pragma unroll
+        for (int r = 0; r < K; ++r) N[r] = 0.0;
         if (p < nx) {
-            double xp = x[p];
-            I = cb_find_interval(kv.tt, kv.n_tt, kv.ml, kv.mr, kv.nt, xp);
+            int I = 0;
+            if (SMEM_KNOTS) {
+                if (xp >= first && xp <= last)     // also rejects NaN
+                    I = xp == last ? (int)(kv.nt - kv.mr) : upper_bound_guess(tt, n_tt, xp, first, scale) + (kv.ml - 1);
+            } else {
+                I = cb_find_interval(kv.tt, kv.n_tt, kv.ml, kv.mr, kv.nt, xp);
+            }
             if (I > 0) {
                 double tw[2 * K];
-                cb_knot_window<K>(kv.tt, kv.n_tt, kv.ml, I, tw);
-                cb_bspline_all<K>(tw, xp, m, N);
+#pragma unroll
+                for (int s = 0; s < 2 * K; ++s) {
+                    int j = I - K + s - (kv.ml - 1);       // 0-based index into t.t of expanded knot I-K+1+s
+                    j = j < 0 ? 0 : (j > n_tt - 1 ? n_tt - 1 : j);
+                    tw[s] = tt[j];
+                }
+                cb_bspline_all<K, MT>(tw, xp, m, N);
 #pragma unroll
                 for (int r = 0; r < K; ++r) {
-                    i64 j = (i64)I - K + 1 + r;
+                    const i64 j = (i64)I - K + 1 + r;
                     if (j < 1 || j > nf) N[r] = 0.0;
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < K; ++r) N[r] = 0.0;
             }
-            interval[p] = I;
-        } else {
-#pragma unroll
-            for (int r = 0; r < K; ++r) N[r] = 0.0;
+            __stcs(interval + p, I);
         }
 #pragma unroll
         for (int r = 0; r < K; ++r) sw[lane * KP + r] = N[r];
@@ -93,19 +139,19 @@ bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, i
         i64 npts = nx - wbase; npts = npts > 32 ? 32 : (npts < 0 ? 0 : npts);
         const int tot = (int)npts * K;
         double *out = vals + wbase * K;             // wbase*K*8 bytes: 16-byte aligned (wbase % 32 == 0)
-        for (int e2 = lane * 2; e2 < tot; e2 += 64) {
-            int r0 = e2 / K, c0 = e2 - r0 * K;
-            double v0 = sw[r0 * KP + c0];
-            if (e2 + 1 < tot && vec_ok) {
-                int r1 = (e2 + 1) / K, c1 = (e2 + 1) - r1 * K;
-                double2 v = make_double2(v0, sw[r1 * KP + c1]);
-                *reinterpret_cast<double2 *>(out + e2) = v;
-            } else {
-                out[e2] = v0;
-                if (e2 + 1 < tot) {
-                    int r1 = (e2 + 1) / K, c1 = (e2 + 1) - r1 * K;
-                    out[e2 + 1] = sw[r1 * KP + c1];
+        if (vec_ok && npts == 32) {
+#pragma unroll
+            for (int it = 0; it < (32 * K + 63) / 64; ++it) {
+                const int e2 = lane * 2 + 64 * it;
+                if (32 * K % 64 == 0 || e2 < 32 * K) {
+                    const int r0 = e2 / K, c0 = e2 - r0 * K, r1 = (e2 + 1) / K, c1 = (e2 + 1) - r1 * K;
+                    __stcs(reinterpret_cast<double2 *>(out + e2), make_double2(sw[r0 * KP + c0], sw[r1 * KP + c1]));
                 }
+            }
+        } else {
+            for (int e = lane; e < tot; e += 32) {
+                const int r0 = e / K, c0 = e - r0 * K;
+                out[e] = sw[r0 * KP + c0];
             }
         }
         __syncwarp();
@@ -309,9 +355,19 @@ int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
     if (nx == 0) return CB_OK;
     CB_REQUIRE(x && interval && vals, "cb_bspline_eval: NULL array");
     cudaStream_t st = (cudaStream_t)stream;
-    int grid = cb_grid_for(nx, EVAL_THREADS, 16);
     int vec_ok = ((uintptr_t)vals % 16) == 0;
-    CB_DISPATCH_K(B->k, (bspline_eval_kernel<K><<<grid, EVAL_THREADS, 0, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok)));
+    if (B->n_tt <= EVAL_SMEM_KNOTS) {
+        const size_t smem = sizeof(double) * (size_t)B->n_tt;
+        int grid = cb_grid_for(nx, EVAL_THREADS, 6);   // persistent-ish: the knot copy is amortised over several blocks
+        CB_DISPATCH_K(B->k, {
+            auto kern = m == 0 ? bspline_eval_kernel<K, true, 0> : bspline_eval_kernel<K, true, -1>;
+            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, EVAL_THREADS, smem, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok);
+        });
+    } else {
+        int grid = cb_grid_for(nx, EVAL_THREADS, 16);
+        CB_DISPATCH_K(B->k, (bspline_eval_kernel<K, false, -1><<<grid, EVAL_THREADS, 0, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok)));
+    }
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -42,9 +42,12 @@ CB_HD void cb_knot_window(const double *__restrict__ tt, i64 n_tt, int ml,
 }
 
 // N[r], r = 0..K-1: m-th derivative at x of function I-K+1+r (order K).
-template <int K>
-CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m,
+// MT >= 0 fixes the derivative order at compile time (m is then ignored): the level loops lose
+// their run-time selects, which matters in the FP64-bound evaluation kernel.
+template <int K, int MT = -1>
+CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
                                                double (&N)[K]) {
+    const int m = MT >= 0 ? MT : m_rt;
 #pragma unroll
     for (int r = 0; r < K; ++r) N[r] = 0.0;
     if (m >= K) return;                            // k == 1 && m > 0 -> 0 (src/bsplines.jl:164)
