@@ -35,45 +35,71 @@ struct cb_density_s {
 // One-time banded Cholesky of G (lower band g[j][p] = G_{j,j-p}, p = 0..k-1).
 // Sequential in j; a single warp keeps the last K rows of L in shared memory.
 // ---------------------------------------------------------------------------
-__global__ void density_cholesky_kernel(const double *__restrict__ gband, int W /*2k-1*/, int k, i64 n,
+template <int K>
+__global__ void density_cholesky_kernel(const double *__restrict__ gband, i64 n,
                                         double *__restrict__ fw, double *__restrict__ bw, int *__restrict__ status) {
-    __shared__ double ring[CB_KMAX][CB_KMAX];      // ring[j % k][p] = L_{j,j-p}
-    if (threadIdx.x != 0) return;
-    for (i64 j = 0; j < n; ++j) {
-        double row[CB_KMAX];
-        // L_{j,c}, c = j-k+1 .. j  <->  p = j-c = k-1 .. 0
-        for (int p = k - 1; p >= 0; --p) {
-            const i64 c = j - p;
-            if (c < 0) { row[p] = 0.0; continue; }
-            // G_{j,c}: BandedMatrix storage (u + i - j') + W*j' with u = k-1, i = j, j' = c
-            double s = gband[(k - 1 + p) + (i64)W * c];
-            // sum over c' < c, c' >= j-k+1: L_{j,c'} L_{c,c'}
-            for (int pp = k - 1; pp > p; --pp) {
-                const i64 cc = j - pp;
-                if (cc < 0) continue;
-                const int pc = (int)(c - cc);       // L_{c,cc} = ring[c % k][c-cc]; row j itself is still in `row`
-                s -= row[pp] * (p == 0 ? row[pp] : ring[c % k][pc]);
-            }
-            if (p == 0) {
-                if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
-                row[0] = sqrt(s);
-            } else {
-                row[p] = s / ring[c % k][0];
+    constexpr int CH = 64;                          // rows of G staged per step (lanes load, lane 0 factorises)
+    constexpr int k = K, W = 2 * K - 1;
+    __shared__ double ring[K][K];                   // ring[j % k][p] = L_{j,j-p}
+    __shared__ double sg[CH][K];                    // sg[r][p] = G_{j0+r, j0+r-p}
+    const int lane = threadIdx.x;
+    for (i64 j0 = 0; j0 < n; j0 += CH) {
+        const int rows = n - j0 < CH ? (int)(n - j0) : CH;
+        __syncwarp();
+        for (int e = lane; e < rows * k; e += 32) {
+            const int r = e / k, p = e - r * k;
+            const i64 j = j0 + r, c = j - p;
+            // BandedMatrix storage (u + i - j') + W*j' with u = k-1, i = j, j' = c
+            sg[r][p] = c >= 0 ? gband[(k - 1 + p) + (i64)W * c] : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int rr = 0; rr < rows; ++rr) {
+                const i64 j = j0 + rr;
+                double row[K];
+                // L_{j,c}, c = j-k+1 .. j  <->  p = j-c = k-1 .. 0
+#pragma unroll
+                for (int p = k - 1; p >= 0; --p) {
+                    const i64 c = j - p;
+                    if (c < 0) { row[p] = 0.0; continue; }
+                    double s = sg[rr][p];
+                    // sum over c' < c, c' >= j-k+1: L_{j,c'} L_{c,c'}
+#pragma unroll
+                    for (int pp = k - 1; pp > p; --pp) {
+                        const i64 cc = j - pp;
+                        if (cc < 0) continue;
+                        const int pc = (int)(c - cc);   // L_{c,cc} = ring[c % k][c-cc]; row j itself is still in `row`
+                        s -= row[pp] * (p == 0 ? row[pp] : ring[c % k][pc]);
+                    }
+                    if (p == 0) {
+                        if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
+                        row[0] = sqrt(s);
+                    } else {
+                        row[p] = s / ring[c % k][0];
+                    }
+                }
+                for (int p = 0; p < k; ++p) ring[j % k][p] = row[p];
+                const double inv = 1.0 / row[0];
+                fw[j * k] = inv;
+                for (int p = 1; p < k; ++p) fw[j * k + p] = row[p] * inv;
+                // bw[c][p] = L_{c+p,c}/L_cc : row j contributes bw[j-p][p]
+                bw[j * k] = inv;
+                for (int p = 1; p < k; ++p)
+                    if (j - p >= 0) bw[(j - p) * k + p] = row[p] / ring[(j - p) % k][0];
             }
         }
-        for (int p = 0; p < k; ++p) ring[j % k][p] = row[p];
-        const double inv = 1.0 / row[0];
-        fw[j * k] = inv;
-        for (int p = 1; p < k; ++p) fw[j * k + p] = row[p] * inv;
-        // bw[c][p] = L_{c+p,c}/L_cc : row j contributes bw[j-p][p]
-        bw[j * k] = inv;
-        for (int p = 1; p < k; ++p)
-            if (j - p >= 0) bw[(j - p) * k + p] = row[p] / ring[(j - p) % k][0];
     }
+    __syncwarp();
     // entries of bw that refer to rows beyond n
-    for (i64 j = n - k + 1 > 0 ? n - k + 1 : 0; j < n; ++j)
-        for (int p = 1; p < k; ++p)
-            if (j + p >= n) bw[j * k + p] = 0.0;
+    if (lane == 0)
+        for (i64 j = n - k + 1 > 0 ? n - k + 1 : 0; j < n; ++j)
+            for (int p = 1; p < k; ++p)
+                if (j + p >= n) bw[j * k + p] = 0.0;
+}
+
+__device__ __forceinline__ void ds_cp8(double *smem_dst, const double *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -108,8 +134,10 @@ density_rhs_kernel(DensArgs A) {
     extern __shared__ double sm[];
     constexpr int NT = MODE == 1 ? 4 : 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sf = sm + (size_t)warp * NT * DR_TILE, *sg = sf + DR_TILE, *so = sg + DR_TILE;
+    const int TS = A.q * K + A.q;                   // one interval's table + node weights
+    double *sf = sm + (size_t)warp * (NT * DR_TILE + 2 * TS), *sg = sf + DR_TILE, *so = sg + DR_TILE;
     double *sr = MODE == 1 ? so + DR_TILE : so;
+    double *stab = sf + NT * DR_TILE;               // [2][TS]: the interval being used and the next one (cp.async)
     const i64 nchunk = (A.ncols + DR_CH - 1) / DR_CH;
     const i64 npg = (A.P + 31) / 32;
     const int q = A.q, ml = A.ml;
@@ -145,7 +173,27 @@ density_rhs_kernel(DensArgs A) {
         int tpos = K - 1;                                           // tile row of the next entering function
         int opos = 0;                                               // rows pending in the output tile
         i64 obase = fa;                                             // function of output tile row 0
+        // The k x q table of an interval is the same for every pair: it is copied to shared memory one
+        // interval ahead (its L2 latency would otherwise stall the two resident warps per scheduler).
+        auto ordof = [&](i64 s_) -> int { return (s_ >= 0 && s_ <= A.n_tt - 2) ? A.ord[s_ + ml - 1] : -1; };
+        auto issue_tab = [&](int c_, int buf_) {
+            if (c_ >= 0) {
+                const double *src = A.table + (i64)c_ * q * K;
+                double *dst = stab + buf_ * TS;
+                for (int e = lane; e < q * K; e += 32) ds_cp8(dst + e, src + e);
+                if (A.wv) for (int e = lane; e < q; e += 32) ds_cp8(dst + q * K + e, A.wv + (i64)c_ * q + e);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        asm volatile("cp.async.wait_group 0;" ::: "memory");        // nothing of the previous item is still landing
+        __syncwarp();
+        int c = ordof(s0), c_nxt = ordof(s0 + 1), buf = 0;
+        issue_tab(c, 0);
         for (i64 s = s0; s <= s1; ++s) {
+            const int c_nn = ordof(s + 2);
+            issue_tab(c_nxt, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
 #pragma unroll
             for (int a = 0; a < K - 1; ++a) { fw[a] = fw[a + 1]; gw[a] = gw[a + 1]; rw[a] = rw[a + 1]; acc[a] = acc[a + 1]; }
             if (tpos == 32) { tile_base += 32; load_tiles(); tpos = 0; }
@@ -153,25 +201,47 @@ density_rhs_kernel(DensArgs A) {
             rw[K - 1] = MODE == 1 ? sr[lane * 33 + tpos] : 0.0;
             acc[K - 1] = 0.0;
             ++tpos;
-            const int c = (s >= 0 && s <= A.n_tt - 2) ? A.ord[s + ml - 1] : -1;
             if (c >= 0) {
-                const double *tab = A.table + (i64)c * q * K;
-                for (int l = 0; l < q; ++l) {
+                const double *tab = stab + buf * TS, *wq = tab + q * K;
+                // two nodes per iteration: independent FMA chains keep the FP64 pipe busy
+                int l = 0;
+                for (; l + 1 < q; l += 2) {
+                    double u0 = 0.0, v0 = 0.0, z0 = 0.0, u1 = 0.0, v1 = 0.0, z1 = 0.0, ta[K], tb[K];
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        ta[a] = tab[l * K + a];
+                        tb[a] = tab[(l + 1) * K + a];
+                    }
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        u0 = fma(ta[a], fw[a], u0); v0 = fma(ta[a], gw[a], v0);
+                        u1 = fma(tb[a], fw[a], u1); v1 = fma(tb[a], gw[a], v1);
+                        if (MODE == 1) { z0 = fma(ta[a], rw[a], z0); z1 = fma(tb[a], rw[a], z1); }
+                    }
+                    double t0 = u0 * v0, t1 = u1 * v1;
+                    if (A.wv) { t0 *= wq[l]; t1 *= wq[l + 1]; }
+                    if (MODE == 1) { t0 -= z0; t1 -= z1; }
+#pragma unroll
+                    for (int a = 0; a < K; ++a) acc[a] = fma(tb[a], t1, fma(ta[a], t0, acc[a]));
+                }
+                for (; l < q; ++l) {
                     double u = 0.0, v = 0.0, z = 0.0, tv[K];
 #pragma unroll
                     for (int a = 0; a < K; ++a) {
-                        tv[a] = __ldg(tab + l * K + a);
+                        tv[a] = tab[l * K + a];
                         u = fma(tv[a], fw[a], u);
                         v = fma(tv[a], gw[a], v);
                         if (MODE == 1) z = fma(tv[a], rw[a], z);
                     }
                     double t = u * v;
-                    if (A.wv) t *= __ldg(A.wv + (i64)c * q + l);
+                    if (A.wv) t *= wq[l];
                     if (MODE == 1) t -= z;
 #pragma unroll
                     for (int a = 0; a < K; ++a) acc[a] = fma(tv[a], t, acc[a]);
                 }
             }
+            __syncwarp();                                           // table buffer free for the copy after next
+            c = c_nxt; c_nxt = c_nn; buf ^= 1;
             const i64 fe = s + ml - K + 1;                          // slot 0 has seen its last interval
             if (fe >= fa && fe < fb) {
                 so[lane * 33 + opos] = acc[0];
@@ -216,81 +286,140 @@ __global__ void density_nodal_kernel(DensArgs A, const i64 *__restrict__ ivlist,
 }
 
 // ---------------------------------------------------------------------------
-// In-place banded solve  L L' x = r  for 32 pairs per warp.
+// In-place banded solve  L L' x = r  for 32 pairs per warp (one warp per CTA).
+// The substitution is sequential along the functions and independent over the pairs, so lanes
+// run over pairs; 32-row tiles of X and of the scaled factor are double-buffered in shared memory
+// with cp.async (coalesced along the rows), and the dependent chain per row is one FMA: the term
+// with the newest unknown is added last.
 // ---------------------------------------------------------------------------
-constexpr int DS_WARPS = 2;
 
 template <int K>
-__global__ void __launch_bounds__(DS_WARPS * 32)
+__global__ void __launch_bounds__(32)
 density_solve_kernel(const double *__restrict__ fwt, const double *__restrict__ bwt, i64 n,
                      double *__restrict__ X, i64 ldx, i64 P, const double *__restrict__ addto, i64 lda) {
-    __shared__ double sx[DS_WARPS][32][33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 npg = (P + 31) / 32;
+    constexpr int NB = K <= 12 ? 4 : 3;             // ring of tiles: NB-1 in flight hide the DRAM latency of one warp
+    __shared__ double sx[NB][32][33];
+    __shared__ double sc[NB][32 * K];
+    const int lane = threadIdx.x;
     const i64 ntile = (n + 31) / 32;
-    for (i64 pg = (i64)blockIdx.x * DS_WARPS + warp; pg < npg; pg += (i64)gridDim.x * DS_WARPS) {
-        const i64 p0 = pg * 32;
-        double yw[K];                                   // yw[p] = y_{j-p} (p >= 1) at row j
-#pragma unroll
-        for (int p = 0; p < K; ++p) yw[p] = 0.0;
-        // forward: y_j = r_j/L_jj - sum_p (L_{j,j-p}/L_jj) y_{j-p}
-        for (i64 t = 0; t < ntile; ++t) {
-            const i64 j0 = t * 32;
-            __syncwarp();
-            for (int pp = 0; pp < 32; ++pp) {
-                const i64 p = p0 + pp, j = j0 + lane;
-                sx[warp][pp][lane] = (p < P && j < n) ? X[j + ldx * p] : 0.0;
-            }
-            __syncwarp();
-            const int rows = n - j0 < 32 ? (int)(n - j0) : 32;
-            for (int r = 0; r < rows; ++r) {
-                const double *cf = fwt + (j0 + r) * K;
-                double acc = sx[warp][lane][r] * __ldg(cf);
-#pragma unroll
-                for (int p = K - 1; p >= 1; --p) acc = fma(-__ldg(cf + p), yw[p], acc);
-#pragma unroll
-                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
-                if (K > 1) yw[1] = acc;
-                sx[warp][lane][r] = acc;
-            }
-            __syncwarp();
-            for (int pp = 0; pp < 32; ++pp) {
-                const i64 p = p0 + pp, j = j0 + lane;
-                if (p < P && j < n) X[j + ldx * p] = sx[warp][pp][lane];
-            }
+    const i64 p0 = (i64)blockIdx.x * 32;
+    // issues the copies of tile t (rows 32t..32t+31 of the 32 pairs + the factor rows) into buffer b
+    auto issue = [&](i64 t, int b, const double *ct) {
+        const i64 j = t * 32 + lane;
+        if (j < n) {
+#pragma unroll 8
+            for (int pp = 0; pp < 32; ++pp)
+                if (p0 + pp < P) ds_cp8(&sx[b][pp][lane], X + j + ldx * (p0 + pp));
         }
-        // backward: x_j = y_j/L_jj - sum_p (L_{j+p,j}/L_jj) x_{j+p}
+        const i64 c0 = t * 32 * K, cend = n * K;
 #pragma unroll
-        for (int p = 0; p < K; ++p) yw[p] = 0.0;
-        for (i64 t = ntile - 1; t >= 0; --t) {
-            const i64 j0 = t * 32;
-            __syncwarp();
+        for (int i = 0; i < K; ++i) {
+            const i64 e = c0 + lane + 32 * i;
+            if (e < cend) ds_cp8(&sc[b][lane + 32 * i], ct + e);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto store = [&](i64 t, int b, bool last_sweep) {
+        const i64 j = t * 32 + lane;
+        if (j < n) {
+#pragma unroll 8
             for (int pp = 0; pp < 32; ++pp) {
-                const i64 p = p0 + pp, j = j0 + lane;
-                sx[warp][pp][lane] = (p < P && j < n) ? X[j + ldx * p] : 0.0;
-            }
-            __syncwarp();
-            const int rows = n - j0 < 32 ? (int)(n - j0) : 32;
-            for (int r = rows - 1; r >= 0; --r) {
-                const double *cb = bwt + (j0 + r) * K;
-                double acc = sx[warp][lane][r] * __ldg(cb);
-#pragma unroll
-                for (int p = K - 1; p >= 1; --p) acc = fma(-__ldg(cb + p), yw[p], acc);
-#pragma unroll
-                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
-                if (K > 1) yw[1] = acc;
-                sx[warp][lane][r] = acc;
-            }
-            __syncwarp();
-            for (int pp = 0; pp < 32; ++pp) {
-                const i64 p = p0 + pp, j = j0 + lane;
-                if (p < P && j < n) {
-                    double v = sx[warp][pp][lane];
-                    if (addto) v += addto[j + lda * p];
+                const i64 p = p0 + pp;
+                if (p < P) {
+                    double v = sx[b][pp][lane];
+                    if (last_sweep && addto) v += addto[j + lda * p];
                     X[j + ldx * p] = v;
                 }
             }
         }
+    };
+    double yw[K];                                   // yw[p] = y_{j-p} (p >= 1) at row j
+    // ---- forward: y_j = r_j/L_jj - sum_p (L_{j,j-p}/L_jj) y_{j-p} ----
+#pragma unroll
+    for (int p = 0; p < K; ++p) yw[p] = 0.0;
+    auto issue_or_skip = [&](i64 t, int b, const double *ct) {     // always commits a group
+        if (t >= 0 && t < ntile) issue(t, b, ct);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < NB - 1; ++i) issue_or_skip(i, i, fwt);
+    for (i64 t = 0; t < ntile; ++t) {
+        const int b = (int)(t % NB);
+        issue_or_skip(t + NB - 1, (int)((t + NB - 1) % NB), fwt);
+        asm volatile("cp.async.wait_group %0;" ::"n"(NB - 1) : "memory");
+        __syncwarp();
+        const int rows = n - t * 32 < 32 ? (int)(n - t * 32) : 32;
+        {   // the tile's rows go through registers so that no shared-memory store sits between the loads
+            double xr[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) xr[r] = sx[b][lane][r];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                if (r < rows) {
+                    const double *cf = &sc[b][r * K];
+                    // older unknowns in two independent partial sums, the newest one (yw[1]) last
+                    double acc = xr[r] * cf[0], acc2 = 0.0;
+#pragma unroll
+                    for (int p = K - 1; p >= 2; --p) {
+                        if (p & 1) acc2 = fma(-cf[p], yw[p], acc2); else acc = fma(-cf[p], yw[p], acc);
+                    }
+                    acc += acc2;
+                    if (K > 1) acc = fma(-cf[1], yw[1], acc);
+#pragma unroll
+                    for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+                    if (K > 1) yw[1] = acc;
+                    xr[r] = acc;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) sx[b][lane][r] = xr[r];
+        }
+        __syncwarp();
+        store(t, b, false);
+        __syncwarp();
+    }
+    // ---- backward: x_j = y_j/L_jj - sum_p (L_{j+p,j}/L_jj) x_{j+p} ----
+#pragma unroll
+    for (int p = 0; p < K; ++p) yw[p] = 0.0;
+    __threadfence_block();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NB - 1; ++i) issue_or_skip(ntile - 1 - i, i, bwt);
+    for (i64 t = ntile - 1, it = 0; t >= 0; --t, ++it) {
+        const int b = (int)(it % NB);
+        issue_or_skip(t - (NB - 1), (int)((it + NB - 1) % NB), bwt);
+        asm volatile("cp.async.wait_group %0;" ::"n"(NB - 1) : "memory");
+        __syncwarp();
+        const int rows = n - t * 32 < 32 ? (int)(n - t * 32) : 32;
+        {   // the tile's rows go through registers so that no shared-memory store sits between the loads
+            double xr[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) xr[r] = sx[b][lane][r];
+#pragma unroll
+            for (int r = 31; r >= 0; --r) {
+                if (r < rows) {
+                    const double *cb = &sc[b][r * K];
+                    // older unknowns in two independent partial sums, the newest one (yw[1]) last
+                    double acc = xr[r] * cb[0], acc2 = 0.0;
+#pragma unroll
+                    for (int p = K - 1; p >= 2; --p) {
+                        if (p & 1) acc2 = fma(-cb[p], yw[p], acc2); else acc = fma(-cb[p], yw[p], acc);
+                    }
+                    acc += acc2;
+                    if (K > 1) acc = fma(-cb[1], yw[1], acc);
+#pragma unroll
+                    for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+                    if (K > 1) yw[1] = acc;
+                    xr[r] = acc;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) sx[b][lane][r] = xr[r];
+        }
+        __syncwarp();
+        store(t, b, true);
+        __syncwarp();
     }
 }
 
@@ -362,7 +491,7 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
     i64 items = ((A.ncols + DR_CH - 1) / DR_CH) * ((A.P + 31) / 32);
     i64 blocks = (items + DR_WARPS - 1) / DR_WARPS;
     int grid = (int)(blocks < (i64)CB_NUM_SMS * 64 ? blocks : (i64)CB_NUM_SMS * 64);
-    size_t smem = sizeof(double) * DR_WARPS * (MODE == 1 ? 4 : 3) * DR_TILE;
+    size_t smem = sizeof(double) * DR_WARPS * ((MODE == 1 ? 4 : 3) * DR_TILE + 2 * (A.q * K + A.q));
     CB_CUDA(cudaFuncSetAttribute(density_rhs_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     density_rhs_kernel<K, MODE><<<grid, DR_WARPS * 32, smem, st>>>(A);
     CB_LAUNCH_CHECK();
@@ -371,9 +500,14 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
 
 template <int K>
 static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const double *addto, i64 lda, cudaStream_t st) {
-    i64 blocks = ((P + 31) / 32 + DS_WARPS - 1) / DS_WARPS;
-    density_solve_kernel<K><<<(int)blocks, DS_WARPS * 32, 0, st>>>(D->d_fw, D->d_bw, D->ncols, X, ldx, P, addto, lda);
+    i64 blocks = (P + 31) / 32;
+    density_solve_kernel<K><<<(int)blocks, 32, 0, st>>>(D->d_fw, D->d_bw, D->ncols, X, ldx, P, addto, lda);
     CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+static int launch_cholesky(int k, const double *g, i64 n, double *fw, double *bw, int *status) {
+    CB_DISPATCH_KD(k, (density_cholesky_kernel<K><<<1, 32>>>(g, n, fw, bw, status)));
     return CB_OK;
 }
 
@@ -418,7 +552,7 @@ int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const do
     if (e == cudaSuccess) rc = cb_bspline_quad_table(B, 0, D->d_table, nullptr);
     if (e == cudaSuccess && rc == CB_OK) rc = cb_bspline_gram_internal(B, col0, ncols, d_g, nullptr);
     if (e == cudaSuccess && rc == CB_OK) {
-        density_cholesky_kernel<<<1, 32>>>(d_g, 2 * B->k - 1, B->k, ncols, D->d_fw, D->d_bw, d_status);
+        rc = launch_cholesky(B->k, d_g, ncols, D->d_fw, D->d_bw, d_status);
         step(cudaGetLastError());
         step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
     }
