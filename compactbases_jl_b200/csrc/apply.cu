@@ -666,39 +666,60 @@ int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *or
 // ---- host-buffer forms: stream the vector batch through the device ----------
 typedef int (*apply_dev_fn)(void *ctx, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st);
 
+// Device staging buffers and streams of the host-buffer entry points, kept per device between calls
+// (allocation and stream creation cost milliseconds, a 737 MB batch over PCIe ~15 ms each way).
+struct HostPipe {
+    static constexpr int NBUF = 3;
+    bool init = false;
+    size_t bytes = 0;                               // capacity of each buffer
+    double *dX[NBUF] = {nullptr, nullptr, nullptr}, *dY[NBUF] = {nullptr, nullptr, nullptr};
+    cudaStream_t st[NBUF] = {nullptr, nullptr, nullptr};
+};
+static HostPipe g_pipes[64];
+
 static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows, const double *Xh, i64 ldx, i64 nvec,
                                double alpha, double beta, double *Yh, i64 ldy) {
     if (nvec == 0 || nrows == 0) return CB_OK;
-    const int NBUF = 3;
-    // tile of vectors: ~64 MB per buffer
-    i64 tv = (i64)(64ll << 20) / (nrows * (i64)sizeof(double));
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    CB_REQUIRE(dev >= 0 && dev < 64, "host pipeline: device index out of range");
+    HostPipe &P = g_pipes[dev];
+    // tile of vectors: ~32 MB per buffer; the device copy is dense (ld = nrows)
+    i64 tv = (i64)(32ll << 20) / (nrows * (i64)sizeof(double));
     if (tv < 1) tv = 1;
     if (tv > nvec) tv = nvec;
-    const i64 ld = nrows + (nrows & 1);             // even leading dimension on the device
-    cudaStream_t st[NBUF]; double *dX[NBUF] = {nullptr}, *dY[NBUF] = {nullptr};
-    int rc = CB_OK; cudaError_t e = cudaSuccess;
-    for (int b = 0; b < NBUF && e == cudaSuccess; ++b) {
-        e = cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc(&dX[b], sizeof(double) * ld * tv);
-        if (e == cudaSuccess) e = cudaMalloc(&dY[b], sizeof(double) * ld * tv);
+    const i64 ld = nrows;
+    const size_t need = sizeof(double) * (size_t)ld * (size_t)tv;
+    cudaError_t e = cudaSuccess;
+    if (!P.init) {
+        for (int b = 0; b < HostPipe::NBUF && e == cudaSuccess; ++b) e = cudaStreamCreateWithFlags(&P.st[b], cudaStreamNonBlocking);
+        P.init = e == cudaSuccess;
     }
+    if (e == cudaSuccess && P.bytes < need) {
+        for (int b = 0; b < HostPipe::NBUF; ++b) { cudaFree(P.dX[b]); cudaFree(P.dY[b]); P.dX[b] = P.dY[b] = nullptr; }
+        P.bytes = 0;
+        for (int b = 0; b < HostPipe::NBUF && e == cudaSuccess; ++b) {
+            e = cudaMalloc(&P.dX[b], need);
+            if (e == cudaSuccess) e = cudaMalloc(&P.dY[b], need);
+        }
+        if (e == cudaSuccess) P.bytes = need;
+    }
+    int rc = CB_OK;
+    auto copy2d = [&](double *dst, i64 ldd, const double *src, i64 lds, i64 nv, cudaMemcpyKind kind, cudaStream_t st) {
+        if (ldd == nrows && lds == nrows) return cudaMemcpyAsync(dst, src, sizeof(double) * nrows * nv, kind, st);
+        return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * nrows, nv, kind, st);
+    };
     i64 t = 0;
     for (i64 v0 = 0; v0 < nvec && e == cudaSuccess && rc == CB_OK; v0 += tv, ++t) {
-        int b = (int)(t % NBUF);
-        i64 nv = v0 + tv <= nvec ? tv : nvec - v0;
-        e = cudaMemcpy2DAsync(dX[b], sizeof(double) * ld, Xh + v0 * ldx, sizeof(double) * ldx, sizeof(double) * nrows, nv,
-                              cudaMemcpyHostToDevice, st[b]);
-        if (e == cudaSuccess && beta != 0.0)
-            e = cudaMemcpy2DAsync(dY[b], sizeof(double) * ld, Yh + v0 * ldy, sizeof(double) * ldy, sizeof(double) * nrows, nv,
-                                  cudaMemcpyHostToDevice, st[b]);
-        if (e == cudaSuccess) rc = fn(ctx, dX[b], ld, nv, alpha, beta, dY[b], st[b]);
-        if (e == cudaSuccess && rc == CB_OK)
-            e = cudaMemcpy2DAsync(Yh + v0 * ldy, sizeof(double) * ldy, dY[b], sizeof(double) * ld, sizeof(double) * nrows, nv,
-                                  cudaMemcpyDeviceToHost, st[b]);
+        const int b = (int)(t % HostPipe::NBUF);
+        const i64 nv = v0 + tv <= nvec ? tv : nvec - v0;
+        e = copy2d(P.dX[b], ld, Xh + v0 * ldx, ldx, nv, cudaMemcpyHostToDevice, P.st[b]);
+        if (e == cudaSuccess && beta != 0.0) e = copy2d(P.dY[b], ld, Yh + v0 * ldy, ldy, nv, cudaMemcpyHostToDevice, P.st[b]);
+        if (e == cudaSuccess) rc = fn(ctx, P.dX[b], ld, nv, alpha, beta, P.dY[b], P.st[b]);
+        if (e == cudaSuccess && rc == CB_OK) e = copy2d(Yh + v0 * ldy, ldy, P.dY[b], ld, nv, cudaMemcpyDeviceToHost, P.st[b]);
     }
-    for (int b = 0; b < NBUF; ++b) {
-        if (st[b]) { cudaError_t e2 = cudaStreamSynchronize(st[b]); if (e == cudaSuccess) e = e2; cudaStreamDestroy(st[b]); }
-        cudaFree(dX[b]); cudaFree(dY[b]);
+    for (int b = 0; b < HostPipe::NBUF; ++b) {
+        if (P.st[b]) { cudaError_t e2 = cudaStreamSynchronize(P.st[b]); if (e == cudaSuccess) e = e2; }
     }
     if (e != cudaSuccess) { cb_set_error("host pipeline: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     return rc;

@@ -76,20 +76,39 @@ struct AsmArgs {
 };
 
 constexpr int ASM_THREADS = 256;
+constexpr int ASM_SMAX = 32 + CB_KMAX;             // most intervals a column tile can touch
+
+// idx = j*(j-1)/2 + r  ->  (j, r) for the reciprocal table (j = 1..CB_KMAX-1, r < j)
+struct RcIndex { unsigned char j[CB_KMAX * (CB_KMAX - 1) / 2], r[CB_KMAX * (CB_KMAX - 1) / 2]; };
+static RcIndex make_rc_index() {
+    RcIndex t; int idx = 0;
+    for (int j = 1; j < CB_KMAX; ++j) for (int r = 0; r < j; ++r) { t.j[idx] = (unsigned char)j; t.r[idx] = (unsigned char)r; ++idx; }
+    return t;
+}
+__constant__ RcIndex c_rc_index;
+
+// padded node count: even (16-byte pairs) and = 2 mod 4 so that rows of different functions fall
+// into different banks for the 16-byte reads of phase 2
+__host__ __device__ inline int asm_qpad(int q) { int p = q + (q & 1); return (p & 3) == 0 ? p + 2 : p; }
 
 template <int KT>
 __global__ void __launch_bounds__(ASM_THREADS)
 bspline_assemble_kernel(AsmArgs A) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int kL = KT > 0 ? KT : A.kL, kR = KT > 0 ? KT : A.kR;
     const int q = A.q, W = A.l + A.u + 1, TJ = A.TJ;
+    const int QP = asm_qpad(q);
     const int mlL = A.kvL.ml, mlR = A.kvR.ml;
     const i64 n_tt = A.kvR.n_tt;
     const int SMAX = TJ + kR - 1;                  // intervals a column tile can touch
-    double *TL = sm;                               // [SMAX][q][kL]
-    double *TR = sm + (size_t)SMAX * q * kL;       // [SMAX][q][kR]
+    constexpr int NRC = KT > 0 ? KT * (KT - 1) / 2 : 0;            // reciprocal knot differences per interval
+    double *TL = sm;                               // [SMAX][kL][QP]  (node index fastest, zero padded)
+    double *TR = TL + (size_t)SMAX * kL * QP;      // [SMAX][kR][QP]
+    double *RC = TR + (size_t)SMAX * kR * QP;      // [SMAX][NRC]    (same-order fast path only)
     const double sgn = (A.da & 1) ? -1.0 : 1.0;    // src/bspline_derivatives.jl:14
     const i64 ntiles = (A.col_hi - A.col_lo + TJ - 1) / TJ;
+    const bool same_tab = A.da == A.db && mlL == mlR;
+    __shared__ int sOrd[ASM_SMAX];                  // ordinal of each interval of the tile among the non-empty ones, -1 if empty
 
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 j0 = A.col_lo + tile * TJ;
@@ -103,12 +122,39 @@ bspline_assemble_kernel(AsmArgs A) {
         if (sB > A.s_hi - 1) sB = A.s_hi - 1;
         const int ns = sB >= sA ? (int)(sB - sA + 1) : 0;
         __syncthreads();                            // previous tile consumed
+        for (int e = threadIdx.x; e < ns; e += ASM_THREADS) sOrd[e] = A.ordR[sA + e + mlR - 1];
+        __syncthreads();
+        // ---- phase 0: reciprocal knot differences, once per interval -----------
+        if (KT > 0) {
+            constexpr int K = KT > 0 ? KT : 1;
+            for (int e = threadIdx.x; e < ns * NRC; e += ASM_THREADS) {
+                const int sl = e / (NRC > 0 ? NRC : 1), idx = e - sl * NRC;
+                const i64 s = sA + sl;
+                if (sOrd[sl] < 0) continue;
+                const int j = c_rc_index.j[idx], r = c_rc_index.r[idx];
+                // tw[K + r] - tw[K - j + r] with tw[t] = knot (I - K + t), I = s + mlR (0-based expanded index I-K+t)
+                const i64 I = s + mlR;
+                const double hi = A.kvR.at(I - K + (K + r)), lo = A.kvR.at(I - K + (K - j + r));
+                RC[e] = fast_rcp(hi - lo);
+            }
+            // zero the node padding of both tables (never written in phase 1)
+            for (int e = threadIdx.x; e < ns * (kL + kR) * (QP - q); e += ASM_THREADS) {
+                const int row = e / (QP - q), c = e - row * (QP - q);
+                (row < ns * kL ? TL + (size_t)row * QP : TR + (size_t)(row - ns * kL) * QP)[q + c] = 0.0;
+            }
+            __syncthreads();
+        } else {
+            for (int e = threadIdx.x; e < ns * (kL + kR) * (QP - q); e += ASM_THREADS) {
+                const int row = e / (QP - q), c = e - row * (QP - q);
+                (row < ns * kL ? TL + (size_t)row * QP : TR + (size_t)(row - ns * kL) * QP)[q + c] = 0.0;
+            }
+        }
         // ---- phase 1: tables ----------------------------------------------
         for (int e = threadIdx.x; e < ns * q; e += ASM_THREADS) {
             const int sl = e / q, ll = e - sl * q;
             const i64 s = sA + sl;
-            const int c = A.ordR[s + mlR - 1];
-            double *tl = TL + (size_t)e * kL, *tr = TR + (size_t)e * kR;
+            const int c = sOrd[sl];
+            double *tl = TL + (size_t)sl * kL * QP + ll, *tr = TR + (size_t)sl * kR * QP + ll;
             if (c < 0) continue;                    // empty interval: never read in phase 2
             const double xv = A.x[(i64)c * q + ll];
             const double wv = A.coulomb == 2 ? 1.0 : A.w[(i64)c * q + ll];
@@ -118,22 +164,29 @@ bspline_assemble_kernel(AsmArgs A) {
             const int IL = (int)(s + mlL), IR = (int)(s + mlR);
             if (KT > 0) {
                 constexpr int K = KT > 0 ? KT : 1;
+                const double *rc = RC + (size_t)sl * NRC;
                 double tw[2 * K], N[K];
                 cb_knot_window<K>(A.kvR.tt, n_tt, mlR, IR, tw);
-                cb_bspline_all<K>(tw, xv, A.db, N);
+                cb_bspline_all_rc<K>(tw, rc, xv, A.db, N);
 #pragma unroll
                 for (int a = 0; a < K; ++a) {
                     i64 f = (i64)IR - K + 1 + a;
-                    tr[a] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
+                    tr[a * QP] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
                 }
-                if (A.da != A.db || mlL != mlR) {
-                    cb_knot_window<K>(A.kvL.tt, n_tt, mlL, IL, tw);
-                    cb_bspline_all<K>(tw, xv, A.da, N);
+                if (!same_tab) {
+                    // the knot window of L is the same set of knots when mlL == mlR; otherwise the
+                    // windows differ only by clamping at the ends, where the reciprocals are recomputed
+                    if (mlL == mlR) {
+                        cb_bspline_all_rc<K>(tw, rc, xv, A.da, N);
+                    } else {
+                        cb_knot_window<K>(A.kvL.tt, n_tt, mlL, IL, tw);
+                        cb_bspline_all<K>(tw, xv, A.da, N);
+                    }
                 }
 #pragma unroll
                 for (int a = 0; a < K; ++a) {
                     i64 f = (i64)IL - K + 1 + a;
-                    tl[a] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
+                    tl[a * QP] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
                 }
             } else {
                 double tw[2 * CB_KMAX], N[CB_KMAX];
@@ -141,18 +194,20 @@ bspline_assemble_kernel(AsmArgs A) {
                 bspline_all_rt(kR, tw, xv, A.db, N);
                 for (int a = 0; a < kR; ++a) {
                     i64 f = (i64)IR - kR + 1 + a;
-                    tr[a] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
+                    tr[a * QP] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
                 }
                 for (int t = 0; t < 2 * kL; ++t) tw[t] = A.kvL.at((i64)IL - kL + t);
                 bspline_all_rt(kL, tw, xv, A.da, N);
                 for (int a = 0; a < kL; ++a) {
                     i64 f = (i64)IL - kL + 1 + a;
-                    tl[a] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
+                    tl[a * QP] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
                 }
             }
         }
         __syncthreads();
         // ---- phase 2: gather into the band ----------------------------------
+        // one thread per band entry; the sum runs over the common intervals and, inside an interval,
+        // over the nodes in increasing order (two nodes per 16-byte shared-memory read)
         const int nent = (int)(j1 - j0) * W;
         for (int e = threadIdx.x; e < nent; e += ASM_THREADS) {
             const int jj = e / W, d = e - jj * W;
@@ -164,12 +219,19 @@ bspline_assemble_kernel(AsmArgs A) {
                 i64 hi = fi - mlL + kL - 1 < fj - mlR + kR - 1 ? fi - mlL + kL - 1 : fj - mlR + kR - 1;
                 if (lo < sA) lo = sA;
                 if (hi > sB) hi = sB;
-                for (i64 s = lo; s <= hi; ++s) {
-                    if (A.ordR[s + mlR - 1] < 0) continue;
-                    const int aL = (int)(fi - s - mlL) + kL - 1, aR = (int)(fj - s - mlR) + kR - 1;
-                    const double *tl = TL + (size_t)(s - sA) * q * kL + aL;
-                    const double *tr = TR + (size_t)(s - sA) * q * kR + aR;
-                    for (int ll = 0; ll < q; ++ll) acc = fma(tl[ll * kL], tr[ll * kR], acc);
+                const int sl0 = (int)(lo - sA), sl1 = (int)(hi - sA);
+                // table slot of the functions in interval slot sl: a = (f - (sA + sl) - ml) + k - 1
+                const int aL0 = (int)(fi - sA - mlL) + kL - 1, aR0 = (int)(fj - sA - mlR) + kR - 1;
+                for (int sl = sl0; sl <= sl1; ++sl) {
+                    if (sOrd[sl] < 0) continue;
+                    const double2 *tl = reinterpret_cast<const double2 *>(TL + ((size_t)sl * kL + (aL0 - sl)) * QP);
+                    const double2 *tr = reinterpret_cast<const double2 *>(TR + ((size_t)sl * kR + (aR0 - sl)) * QP);
+#pragma unroll 4
+                    for (int l2 = 0; l2 < QP / 2; ++l2) {
+                        const double2 a2 = tl[l2], b2 = tr[l2];
+                        acc = fma(a2.x, b2.x, acc);
+                        acc = fma(a2.y, b2.y, acc);
+                    }
                 }
             }
             A.band[(i64)d + (i64)W * (j - A.col_lo)] = acc;
@@ -329,6 +391,20 @@ __global__ void fd_stencil_kernel(int scheme, int nder, const double *__restrict
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+static int ensure_rc_index() {
+    static bool done = false;                       // per process; every device of the process gets its copy below
+    static int devs_done[64] = {0};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    (void)done;
+    if (dev >= 0 && dev < 64 && !devs_done[dev]) {
+        RcIndex t = make_rc_index();
+        CB_CUDA(cudaMemcpyToSymbol(c_rc_index, &t, sizeof(t)));
+        devs_done[dev] = 1;
+    }
+    return CB_OK;
+}
+
 static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
                            int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
                            i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, void *stream) {
@@ -350,6 +426,7 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     CB_REQUIRE(col_lo >= 0 && col_hi <= n && col_lo <= col_hi, "cb_bspline_assemble: column range outside 0..n");
     CB_REQUIRE(s_lo >= 0 && s_hi <= R->n_tt - 1 && s_lo <= s_hi, "cb_bspline_assemble: interval range outside 0..numintervals");
     if (col_hi == col_lo) return CB_OK;
+    { int rc_ = ensure_rc_index(); if (rc_) return rc_; }
     cudaStream_t st = (cudaStream_t)stream;
     AsmArgs A;
     A.kvL = make_knot_view(L); A.kvR = make_knot_view(R);
@@ -361,9 +438,10 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     A.l = l; A.u = u; A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
     A.band = band;
     // column tile: as many columns as fit ~96 KB (two CTAs per SM), at most 32
-    const size_t per_iv = sizeof(double) * (size_t)A.q * (A.kL + A.kR);
+    const int NRC = (L->k == R->k) ? L->k * (L->k - 1) / 2 : 0;
+    const size_t per_iv = sizeof(double) * ((size_t)asm_qpad(A.q) * (A.kL + A.kR) + NRC);
     int TJ = 32;
-    while (TJ > 1 && (size_t)(TJ + A.kR - 1) * per_iv > 96 * 1024) TJ /= 2;
+    while (TJ > 1 && (size_t)(TJ + A.kR - 1) * per_iv > 112 * 1024) TJ /= 2;   // two CTAs per SM
     size_t smem = (size_t)(TJ + A.kR - 1) * per_iv;
     if (smem > 220 * 1024) { cb_set_error("cb_bspline_assemble: k=%d, q=%d tables exceed shared memory", k, A.q); return CB_ERR_UNSUPPORTED; }
     A.TJ = TJ;

@@ -86,3 +86,52 @@ CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
         }
     }
 }
+
+// Same recursion with the reciprocal knot differences supplied by the caller:
+// rc[j*(j-1)/2 + r] = 1 / (t_{I+1+r} - t_{I+1+r-j}), j = 1..K-1, r = 0..j-1 (tw[K+r] - tw[K-j+r]).
+// They depend on the interval only, so quadrature assembly computes them once per interval and
+// shares them among its q nodes.
+template <int K>
+__device__ __forceinline__ void cb_knot_rcp(const double (&tw)[2 * K], int idx, double &out) {
+    // idx -> (j, r)
+    int j = 1, base = 0;
+    while (base + j <= idx) { base += j; ++j; }
+    const int r = idx - base;
+    out = fast_rcp(tw[K + r] - tw[K - j + r]);
+}
+
+template <int K>
+__device__ __forceinline__ void cb_bspline_all_rc(const double (&tw)[2 * K], const double *__restrict__ rc, double x, int m,
+                                                  double (&N)[K]) {
+#pragma unroll
+    for (int r = 0; r < K; ++r) N[r] = 0.0;
+    if (m >= K) return;
+    N[0] = 1.0;
+    const int jmax = K - 1 - m;
+#pragma unroll
+    for (int j = 1; j <= K - 1; ++j) {
+        if (j <= jmax) {
+            double saved = 0.0;
+#pragma unroll
+            for (int r = 0; r < j; ++r) {
+                const double term = N[r] * rc[j * (j - 1) / 2 + r];
+                N[r] = fma(tw[K + r] - x, term, saved);
+                saved = (x - tw[K - j + r]) * term;
+            }
+            N[j] = saved;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= K - 1; ++o) {
+        if (o >= K - m) {
+            double qprev = 0.0;
+#pragma unroll
+            for (int r = 0; r <= o; ++r) {
+                double qr = 0.0;
+                if (r < o) qr = N[r] * rc[o * (o - 1) / 2 + r];
+                N[r] = (double)o * (qprev - qr);
+                qprev = qr;
+            }
+        }
+    }
+}

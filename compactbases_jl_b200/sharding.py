@@ -1,0 +1,166 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, ``torch.distributed``).
+
+The reference is single-process; the partitioning follows SURVEY §8e:
+
+* point batches (``B[x,:]``), coefficient-vector batches (``mul!``) and pair batches (``Density``)
+  are split into contiguous ranges with **no exchange** (``batch_range``);
+* quadrature assembly of a B-spline band can be split by **knot interval**.  A rank sums the
+  contributions of its intervals into every column that touches them; a column (basis function)
+  lives on k consecutive intervals, so the last k-1 columns a rank *owns* (those that start in
+  its range) also receive contributions from the next rank's intervals.  Either each rank
+  recomputes its own columns over the full interval range (``halo="recompute"``, no
+  communication) or the neighbours add their partial sums: one send to the left and one
+  receive from the right of at most k-1 columns x (l+u+1) rows (``halo="exchange"``; NCCL
+  point-to-point over NVLink on GPUs, gloo in the CPU tests).
+
+Only index arithmetic and the exchange live here; the kernels are behind
+``cb_bspline_assemble_part`` in the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+def batch_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous share [lo, hi) of n independent items (points, vectors, pairs)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@dataclass
+class IntervalShard:
+    """What one rank computes in an interval-sharded assembly (0-based, half-open ranges)."""
+    s_lo: int       # t.t intervals summed by this rank
+    s_hi: int
+    own_lo: int     # columns (within the restriction) whose first interval lies in [s_lo, s_hi): complete after the exchange
+    own_hi: int
+    touch_lo: int   # columns with any support in [s_lo, s_hi): computed as partial sums
+    touch_hi: int
+
+
+def interval_shards(numintervals: int, k: int, ml: int, col0: int, ncols: int, world: int) -> list[IntervalShard]:
+    """Splits the t.t intervals evenly.  Function f (1-based, order k) lives on intervals
+    f-ml .. f-ml+k-1 clipped to 0..numintervals-1 (src/knot_sets.jl:138-151), so it *starts* in
+    interval max(0, f-ml)."""
+    out = []
+    for r in range(world):
+        s_lo, s_hi = batch_range(numintervals, r, world)
+
+        def start(j):            # first interval of column j (0-based within the restriction)
+            return max(0, (col0 + 1 + j) - ml)
+
+        def last(j):
+            return min(numintervals - 1, (col0 + 1 + j) - ml + k - 1)
+
+        # columns are ordered by start interval (non-decreasing), so the ranges are contiguous
+        own_lo = _first(ncols, lambda j: start(j) >= s_lo)
+        own_hi = _first(ncols, lambda j: start(j) >= s_hi)
+        touch_lo = _first(ncols, lambda j: last(j) >= s_lo)
+        touch_hi = own_hi
+        out.append(IntervalShard(s_lo, s_hi, own_lo, own_hi, min(touch_lo, own_lo), touch_hi))
+    return out
+
+
+def _first(n, pred):
+    """Smallest j in [0, n] with pred(j) true for all j' >= j (monotone predicate)."""
+    lo, hi = 0, n
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if pred(mid):
+            hi = mid
+        else:
+            lo = mid + 1
+    return lo
+
+
+def halo_exchange_add(partial: torch.Tensor, shard: IntervalShard, shards: list[IntervalShard], rank: int,
+                      group=None) -> torch.Tensor:
+    """``partial``: [touch_hi - touch_lo, W] partial sums of this rank (BandedMatrix columns are
+    contiguous rows of the (n, W) tensor).  Sends the columns owned by the left neighbour(s) and
+    adds what the right neighbour computed for this rank's last columns.  Returns the owned
+    columns [own_hi - own_lo, W], complete."""
+    world = len(shards)
+    W = partial.shape[1]
+    own = partial[shard.own_lo - shard.touch_lo:shard.own_hi - shard.touch_lo].clone()
+    ops = []
+    send_bufs, recv_bufs = [], []
+    # columns I touched but that start in an earlier rank's range: their owners are to the left
+    for r2 in range(rank):
+        lo, hi = max(shards[r2].own_lo, shard.touch_lo), min(shards[r2].own_hi, shard.own_lo)
+        if hi > lo:
+            buf = partial[lo - shard.touch_lo:hi - shard.touch_lo].contiguous()
+            send_bufs.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, _global_rank(r2, group), group=group))
+    # columns I own that ranks to the right touched
+    for r2 in range(rank + 1, world):
+        lo, hi = max(shard.own_lo, shards[r2].touch_lo), min(shard.own_hi, shards[r2].own_lo)
+        if hi > lo:
+            buf = torch.empty((hi - lo, W), dtype=partial.dtype, device=partial.device)
+            recv_bufs.append((lo, hi, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, _global_rank(r2, group), group=group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for lo, hi, buf in recv_bufs:
+        own[lo - shard.own_lo:hi - shard.own_lo] += buf
+    return own
+
+
+def _global_rank(r, group):
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def assemble_interval_sharded(L, R, a: int, b: int, rank: int, world: int, opvals: torch.Tensor | None = None,
+                              coulomb_Z: float | None = None, halo: str = "exchange", group=None):
+    """Interval-sharded ``diffop!`` on this rank's GPU.  Returns (own_lo, own_hi, cols) where ``cols``
+    is the [own_hi-own_lo, l+u+1] slice of the BandedMatrix data that this rank owns."""
+    from . import _lib
+    from .bsplines import band_shape
+    from .operators import _ptr, _stream
+    PL, PR = L.parent_basis, R.parent_basis
+    l, u = band_shape(L, R)
+    W = l + u + 1
+    nint = PR.t.numintervals()
+    shards = interval_shards(nint, PR.k, PR.t.ml, R.col0, R.ncols, world)
+    sh = shards[rank]
+    dev = PR.device
+    cz = 0.0 if coulomb_Z is None else float(coulomb_Z)
+    cflag = 0 if coulomb_Z is None else 1
+    if halo == "recompute" or world == 1:
+        cols = torch.empty((sh.own_hi - sh.own_lo, W), dtype=torch.float64, device=dev)
+        _lib.call("cb_bspline_assemble_part", PL.handle, PR.handle, a, b, _ptr(opvals), cflag, cz, L.col0, L.ncols,
+                  R.col0, R.ncols, l, u, sh.own_lo, sh.own_hi, 0, nint, _ptr(cols), _stream())
+        return sh.own_lo, sh.own_hi, cols
+    if halo != "exchange":
+        raise ValueError("halo must be 'exchange' or 'recompute'")
+    partial = torch.empty((sh.touch_hi - sh.touch_lo, W), dtype=torch.float64, device=dev)
+    _lib.call("cb_bspline_assemble_part", PL.handle, PR.handle, a, b, _ptr(opvals), cflag, cz, L.col0, L.ncols,
+              R.col0, R.ncols, l, u, sh.touch_lo, sh.touch_hi, sh.s_lo, sh.s_hi, _ptr(partial), _stream())
+    return sh.own_lo, sh.own_hi, halo_exchange_add(partial, sh, shards, rank, group)
+
+
+def allgather_columns(cols: torch.Tensor, shards: list[IntervalShard], group=None) -> torch.Tensor:
+    """Replicates the assembled band on every rank (optional step after a sharded assembly)."""
+    world = len(shards)
+    W = cols.shape[1]
+    parts = [torch.empty((s.own_hi - s.own_lo, W), dtype=cols.dtype, device=cols.device) for s in shards]
+    dist.all_gather(parts, cols.contiguous(), group=group) if _equal_sizes(shards) else _allgather_ragged(parts, cols, group)
+    return torch.cat(parts, dim=0)
+
+
+def _equal_sizes(shards):
+    return len({s.own_hi - s.own_lo for s in shards}) == 1
+
+
+def _allgather_ragged(parts, cols, group):
+    world = len(parts)
+    rank = dist.get_rank(group)
+    for r in range(world):
+        if r == rank:
+            parts[r].copy_(cols)
+        dist.broadcast(parts[r], _global_rank(r, group), group=group)
