@@ -307,6 +307,14 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
     }
 }
 
+// D = A(8x4, row-major fragment) * B(4x8, column fragment) + C(8x8) in FP64 on the tensor cores
+// (SASS: DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against 36.2 for DFMA, at 1/8 of the issue slots).
+// Fragments, with g = lane >> 2 and t = lane & 3:  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------
 // K8: FE-DVR element-block operator, uniform order O (compile time).
 //
@@ -322,15 +330,17 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
 // ---------------------------------------------------------------------------
 constexpr int FE_TV = 32;                           // vectors per tile (one warp wide)
 // Measured on B200 (C2: order 10, 1e4 elements, 1024 vectors; device time of one apply):
-//   EG x NG x NS = 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 2x8x3: 511 | 1x4x3: 584 | 1x8x6: 718
-// More stages cost resident warps and the kernel is bound by warp-level latency in its compute and
-// store phases, not by bytes in flight (a bare cp.async tile stream reaches 5.2 TB/s, see
-// scripts/micro/stream.cu), so the default is one stage per CTA and as many CTAs per SM as fit.
+//   DFMA compute, EG x NG x NS = 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 1x4x3: 584 | 1x8x6: 718
+//   DMMA compute, (elements per warp) x (warps) = 1x16: 404 us | 2x8: 420 | 1x12: 423 | 3x8: 478 |
+//                 4x4: 495 | 2x16: 612 | 4x8: 680;  movers only (no compute), 16-element tile: 341 us
+// More stages cost resident warps and the kernel is bound by warp-level latency in its phases, not by
+// bytes in flight (a bare cp.async tile stream reaches 5.2 TB/s, scripts/micro/stream.cu), so the
+// default is one stage, a 16-element tile and 16 warps per CTA (3 CTAs per SM).
 #ifndef FEDVR_EG10
-#define FEDVR_EG10 4
+#define FEDVR_EG10 1
 #endif
 #ifndef FEDVR_NG
-#define FEDVR_NG 4
+#define FEDVR_NG 16
 #endif
 #ifndef FEDVR_NS
 #define FEDVR_NS 1
@@ -349,7 +359,9 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
     constexpr int BS_SIZE = (ET + 1) * O * OP;      // [(ET+1)][O][OP] column-major blocks, 16-byte aligned columns
     constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);   // blocks + x tile [32][PITCH]
     extern __shared__ __align__(16) double sm[];
-    const int vl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    double *br0 = sm + NS * STAGE;                  // [(ET+1)][32] first-row products (bridge contributions)
+    double *br9 = br0 + (ET + 1) * FE_TV;           // [ET][32]     last-row products
+    const int g = threadIdx.x >> 5;
     const i64 net = (nel + ET - 1) / ET;
     const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
     const i64 ntiles = net * nvt;
@@ -395,53 +407,68 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
         i64 eA, v0, x0row; bool interior;
         coords(tile, eA, v0, x0row, interior);
         double *bs = sm + stage * STAGE, *xs = bs + BS_SIZE;
-        double *xv = xs + vl * PITCH;
-        const int eL0 = g * EG;                     // first tile-local element of this thread
-        // phase 1: values other threads will overwrite in phase 2
-        double x0 = xv[eL0 * (O - 1)];              // x at the first node of my first element
-        double halo = 0.0;                          // first matrix row of the element after my last
+#ifndef FEDVR_SKIP_COMPUTE
+        // ---- compute: y_e = B_e x_e on the FP64 tensor cores --------------------------------
+        // A warp owns EG elements; for each it multiplies the O x O block (A operand: MT x KS
+        // fragments, loaded once) with the element's O rows of 32 vectors (B operand: four 8-vector
+        // tiles).  Rows 1..O-2 are written in place (no other warp reads them); rows 0 and O-1 are
+        // contributions to the bridge rows shared with the neighbouring elements and go to side
+        // buffers that are summed after the barrier.  Operands outside the block are zeroed rather
+        // than multiplied by zero, so Inf/NaN in a neighbouring element cannot leak.
         {
-            const int eh = eL0 + EG;
-            const double *bh = bs + eh * O * OP;
-            const double *xh = xv + eh * (O - 1);
+            constexpr int MT = (O + 7) / 8, KS = (O + 3) / 4;
+            const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+            for (int job = g; job <= ET; job += NG) {           // job ET = halo element: only its row 0 is needed
+                const int eL = job;
+                const double *b = bs + eL * O * OP;
+                double af[MT][KS];
 #pragma unroll
-            for (int mp = 0; mp < O; ++mp) halo = fma(bh[OP * mp], xh[mp], halo);
-        }
-        __syncthreads();
-        // phase 2: own elements, results written in place over my own rows
-        double carry = 0.0;                         // contribution of the previous element to its bridge row
-        double y_first = 0.0;
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int s = 0; s < EG; ++s) {
-            const int eL = eL0 + s;
-            const double *b = bs + eL * O * OP;
-            double *xe = xv + eL * (O - 1);
-            double xr[O], acc[OP];
-            xr[0] = x0;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int mm = gq + 8 * mt, mp = 4 * ks + tq;
+                        af[mt][ks] = (mm < O && mp < O) ? b[mp * OP + mm] : 0.0;
+                    }
+                const int mtn = eL == ET ? 1 : MT;
 #pragma unroll
-            for (int mp = 1; mp < O; ++mp) xr[mp] = xe[mp];
+                for (int nt = 0; nt < FE_TV / 8; ++nt) {
+                    const double *xe = xs + (8 * nt + gq) * PITCH + eL * (O - 1);
+                    double bf[KS];
 #pragma unroll
-            for (int mm = 0; mm < OP; ++mm) acc[mm] = 0.0;
+                    for (int ks = 0; ks < KS; ++ks) bf[ks] = (4 * ks + tq < O) ? xe[4 * ks + tq] : 0.0;
+                    double c[MT][2];
 #pragma unroll
-            for (int mp = 0; mp < O; ++mp) {
-                const double2 *b2 = reinterpret_cast<const double2 *>(b + OP * mp);
+                    for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
 #pragma unroll
-                for (int m2 = 0; m2 < OP / 2; ++m2) {
-                    const double2 bb = b2[m2];
-                    acc[2 * m2] = fma(bb.x, xr[mp], acc[2 * m2]);
-                    acc[2 * m2 + 1] = fma(bb.y, xr[mp], acc[2 * m2 + 1]);
+                    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            if (mt < mtn) dmma884(c[mt][0], c[mt][1], af[mt][ks], bf[ks]);
+                    __syncwarp();                                // all lanes have read this vector tile's x rows
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int mm = gq + 8 * mt;
+                        const int v = 8 * nt + 2 * tq;
+                        if (mt < mtn) {
+                            if (mm == 0) { br0[eL * FE_TV + v] = c[mt][0]; br0[eL * FE_TV + v + 1] = c[mt][1]; }
+                            else if (eL < ET && mm == O - 1) { br9[eL * FE_TV + v] = c[mt][0]; br9[eL * FE_TV + v + 1] = c[mt][1]; }
+                            else if (eL < ET && mm < O - 1) {
+                                xs[v * PITCH + eL * (O - 1) + mm] = c[mt][0];
+                                xs[(v + 1) * PITCH + eL * (O - 1) + mm] = c[mt][1];
+                            }
+                        }
+                    }
                 }
             }
-            if (s == 0) y_first = acc[0];           // row 0 of my first element (owned by the group before me)
-            else xe[0] = carry + acc[0];            // bridge row between my elements s-1 and s
-#pragma unroll
-            for (int mm = 1; mm < O - 1; ++mm) xe[mm] = acc[mm];
-            carry = acc[O - 1];
-            x0 = xr[O - 1];
         }
-        xv[(eL0 + EG) * (O - 1)] = carry + halo;   // my last bridge row
-        // global row 0 has no previous element: only the first group of the first tile writes it
-        if (eA == 0 && g == 0) xv[0] = y_first;
+#endif
+        __syncthreads();
+        // bridge rows: last row of element e-1 plus first row of element e; global row 0 has no previous element
+        for (int i = threadIdx.x; i < (ET + 1) * FE_TV; i += THREADS) {
+            const int eL = i / FE_TV, v = i - eL * FE_TV;
+            if (eL == 0) { if (eA == 0) xs[v * PITCH] = br0[v]; }
+            else xs[v * PITCH + eL * (O - 1)] = br9[(eL - 1) * FE_TV + v] + br0[eL * FE_TV + v];
+        }
         __syncthreads();
         // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
         const int r_lo = (eA == 0) ? 0 : 1;
@@ -536,8 +563,8 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
     constexpr int OP = O + (O & 1);
     constexpr int BS_SIZE = (ET + 1) * O * OP;
     constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);
-    size_t smem = sizeof(double) * (size_t)NS * STAGE;
-    static_assert(sizeof(double) * (size_t)NS * STAGE <= 227 * 1024, "pipeline does not fit in shared memory");
+    size_t smem = sizeof(double) * ((size_t)NS * STAGE + (size_t)(2 * ET + 1) * FE_TV);
+    static_assert(sizeof(double) * ((size_t)NS * STAGE + (size_t)(2 * ET + 1) * FE_TV) <= 227 * 1024, "pipeline does not fit in shared memory");
     auto kern = fedvr_apply_kernel<O, EG, NG, NS>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
