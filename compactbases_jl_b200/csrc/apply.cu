@@ -225,17 +225,30 @@ __device__ __forceinline__ void store_tile_fast_clip(const double *ys, int pitch
     }
 }
 
+// D = A(8x4, row-major fragment) * B(4x8, column fragment) + C(8x8) in FP64 on the tensor cores
+// (SASS: DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against 36.2 for DFMA, at 1/8 of the issue slots).
+// Fragments, with g = lane >> 2 and t = lane & 3:  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------
-// K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x 32 vectors.  Thread = (vector lane, row group
-// of BR rows): it sweeps the BR+l+u window of x once, each x value feeding up to BR accumulators;
-// the band tile sits in shared memory, zero padded, so that the inner loop needs no predicate and
-// its coefficient loads are warp-uniform 16-byte broadcasts.
+// K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x 32 vectors, x window staged in shared memory.
+// The product runs on the FP64 tensor cores: an 8-row block of A against its window of
+// 8 + l + u columns is KS = ceil((8+l+u)/4) DMMA k-steps per 8-vector tile.  The band tile is
+// stored in shared memory directly as A fragments (one double per lane per (row block, k-step),
+// zero outside band and matrix), staged once per work item and reused for all its vector tiles.
+// Every warp keeps its results in registers until all warps have read the x window, then writes
+// them over the tile in place.  (A zero of the padded fragment multiplies x entries of the same
+// 8-row block that lie outside a row's own band: non-finite X entries therefore also reach the
+// other rows of their block, which a scalar banded product would not do.)
 // ---------------------------------------------------------------------------
-constexpr int BT_VEC = 32;                          // vectors per CTA (= one warp wide)
-constexpr int BT_NG = 8;                            // row groups (warps) per CTA
-constexpr int BR = 16;                              // rows per thread
+constexpr int BT_VEC = 32;                          // vectors per CTA tile
+constexpr int BT_NG = 8;                            // warps per CTA
+constexpr int BT_RB = 2;                            // 8-row blocks per warp
 constexpr int BT_THREADS = 32 * BT_NG;
-constexpr int BT_ROWS = BT_NG * BR;                 // 128 rows per CTA tile
+constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
 
 __global__ void __launch_bounds__(BT_THREADS)
 banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
@@ -243,12 +256,12 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
                     double alpha, double beta, double *__restrict__ Y, i64 ldy) {
     extern __shared__ __align__(16) double sm[];
     const int W = l + u + 1;
+    const int KS = (8 + W - 1 + 3) / 4;             // k-steps per 8-row block
     const int xrows = BT_ROWS + l + u;
-    const int pitch = xrows | 1;
-    const int acols = BR + W - 1;
-    double *as = sm;                                // [BT_NG][acols][BR], zero padded (16-byte aligned rows)
-    double *xs = sm + BT_NG * acols * BR;           // [BT_VEC][pitch]
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int pitch = (xrows + 4) | 1;              // + room for the k padding of the last block
+    double *as = sm;                                // [BT_ROWS/8][KS][32] A fragments
+    double *xs = sm + (BT_ROWS / 8) * KS * 32;      // [BT_VEC][pitch]; tile row r <-> matrix column i0 - l + r
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
     const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
     const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
     // work item = (row tile, chunk of vchunk vector tiles): the band tile is staged once per item
@@ -257,62 +270,54 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
       const i64 vc = item / nrt, rt = item - vc * nrt;              // row tiles vary fastest (contiguous streams)
       const i64 i0 = rt * BT_ROWS;                  // first row of the tile
       __syncthreads();                              // previous item fully consumed
-      // band tile: as[g][c][r] = A(i0+g*BR+r, i0+g*BR-l+c), 0 outside band/matrix
-      {
-          const int r = threadIdx.x % BR, c0 = threadIdx.x / BR;    // no runtime divisions in the fill loops
-#pragma unroll
-          for (int g = 0; g < BT_NG; ++g) {
-              const i64 i = i0 + g * BR + r;
-              for (int c = c0; c < acols; c += BT_THREADS / BR) {
-                  const i64 j = i0 + g * BR - l + c;
-                  double a = 0.0;
-                  if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = __ldg(band + (u + i - j) + (i64)W * j);
-                  as[(g * acols + c) * BR + r] = a;
-              }
-          }
+      // A fragments: as[rb][ks][lane] = A(i0 + 8rb + g, i0 + 8rb - l + 4ks + t), 0 outside band/matrix
+      for (int e = threadIdx.x; e < (BT_ROWS / 8) * KS * 32; e += BT_THREADS) {
+          const int ln = e & 31, ks = (e >> 5) % KS, rb = (e >> 5) / KS;
+          const i64 i = i0 + 8 * rb + (ln >> 2), j = i0 + 8 * rb - l + 4 * ks + (ln & 3);
+          double a = 0.0;
+          if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = __ldg(band + (u + i - j) + (i64)W * j);
+          as[e] = a;
       }
       const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
       for (i64 vt = vc * vchunk; vt < vt_end; ++vt) {
         const i64 v0 = vt * BT_VEC;
         __syncthreads();                            // previous tile fully consumed
-        // x window rows i0-l .. i0+BT_ROWS-1+u  (columns of A), zero outside the matrix
-        load_tile_async_rt<BT_VEC, BT_NG>(xs, pitch, X, ldx, n, i0 - l, xrows, v0, nvec);
+        // x window rows i0-l .. i0+BT_ROWS-1+u (+ k padding), zero outside the matrix
+        load_tile_async_rt<BT_VEC, BT_NG>(xs, pitch, X, ldx, n, i0 - l, xrows + 3, v0, nvec);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
-        double acc[BR];
+        double c[BT_RB][BT_VEC / 8][2];
 #pragma unroll
-        for (int r = 0; r < BR; ++r) acc[r] = 0.0;
-        const double *xv = xs + lane * pitch + rg * BR;          // x window of this row group
-        const double *ag = as + rg * acols * BR;
-#pragma unroll 2
-        for (int c = 0; c < acols; ++c) {
-            const double xc = xv[c];
-            const double2 *a2 = reinterpret_cast<const double2 *>(ag + c * BR);
+        for (int q = 0; q < BT_RB; ++q) {
+            const int rb = warp * BT_RB + q;
 #pragma unroll
-            for (int r2 = 0; r2 < BR / 2; ++r2) {
-                const double2 a = a2[r2];
-                acc[2 * r2] = fma(a.x, xc, acc[2 * r2]);
-                acc[2 * r2 + 1] = fma(a.y, xc, acc[2 * r2 + 1]);
+            for (int nt = 0; nt < BT_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
+            const double *af = as + rb * KS * 32 + lane;
+            const double *xb = xs + gq * pitch + 8 * rb + tq;        // + nt*8*pitch + 4*ks
+            for (int ks = 0; ks < KS; ++ks) {
+                const double a = af[ks * 32];
+#pragma unroll
+                for (int nt = 0; nt < BT_VEC / 8; ++nt) dmma884(c[q][nt][0], c[q][nt][1], a, xb[nt * 8 * pitch + 4 * ks]);
             }
         }
         __syncthreads();                            // everyone done reading xs
 #pragma unroll
-        for (int r = 0; r < BR; ++r) xs[lane * pitch + rg * BR + r] = acc[r];   // tile-local row index
+        for (int q = 0; q < BT_RB; ++q) {
+            const int row = (warp * BT_RB + q) * 8 + gq;             // tile-local output row
+#pragma unroll
+            for (int nt = 0; nt < BT_VEC / 8; ++nt) {
+                const int v = nt * 8 + 2 * tq;
+                xs[v * pitch + row] = c[q][nt][0];
+                xs[(v + 1) * pitch + row] = c[q][nt][1];
+            }
+        }
         __syncthreads();
         const int r_hi = m - i0 < BT_ROWS ? (int)(m - i0) : BT_ROWS;
         if (beta == 0.0) store_tile_fast_clip<BT_VEC, BT_NG>(xs, pitch, Y, ldy, i0, 0, r_hi, v0, nvec, alpha);
         else store_tile<BT_THREADS>(xs, pitch, Y, ldy, m, i0, 0, BT_ROWS, v0, BT_VEC, nvec, alpha, beta);
       }
     }
-}
-
-// D = A(8x4, row-major fragment) * B(4x8, column fragment) + C(8x8) in FP64 on the tensor cores
-// (SASS: DMMA.8x8x4; measured 37.1 TFLOP/s on B200 against 36.2 for DFMA, at 1/8 of the issue slots).
-// Fragments, with g = lane >> 2 and t = lane & 3:  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
-__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // ---------------------------------------------------------------------------
@@ -631,9 +636,10 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     // BandedMatrices allows negative l or u (bands entirely above/below the diagonal, e.g.
     // src/fd_operators.jl:16); the window arithmetic below is valid for them as long as l+u >= 0.
     const int W = l + u + 1;
+    const int KS = (8 + W - 1 + 3) / 4;
     const int xrows = BT_ROWS + l + u;
-    const int pitch = xrows | 1;
-    size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)BT_NG * (BR + W - 1) * BR);
+    const int pitch = (xrows + 4) | 1;
+    size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)(BT_ROWS / 8) * KS * 32);
     if (smem > 200 * 1024) { cb_set_error("cb_banded_apply: bandwidth %d too large for the shared-memory tile", W); return CB_ERR_UNSUPPORTED; }
     CB_CUDA(cudaFuncSetAttribute(banded_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS, nvt = (nvec + BT_VEC - 1) / BT_VEC;
