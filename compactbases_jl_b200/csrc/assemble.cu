@@ -44,19 +44,12 @@ __device__ void bspline_all_rt(int k, const double *tw, double x, int m, double 
 // ---------------------------------------------------------------------------
 // K2+K3: fused B-spline band assembly.
 //
-// A CTA owns TJ consecutive columns (functions of R).  Phase 1 evaluates, for
-// every non-empty knot interval s that one of those columns lives on and every
-// quadrature node l of it, the kL live functions of L (a-th derivative, times
-// (-1)^a w_l) and the kR live functions of R (b-th derivative, times op(x_l))
-// into shared memory — basis_functions(t, x, m), src/bsplines.jl:28-52, which
-// the reference stores as a sparse matrix in memory, never leaves the SM.
-// Phase 2 is the gather form of overlap_matrix! (src/bsplines.jl:58-73): one
-// thread per band entry sums over the common intervals and their nodes in
-// increasing node order, the order of the reference's sparse dot product, so no
-// atomics and a deterministic result.
-//
 // s is the 0-based index of an interval of t.t (shared by L and R, src/
 // bsplines.jl:75-82); its 1-based index in an expanded knot vector is s + ml.
+// A CTA owns TJ consecutive columns (functions of R) and the TJ + k - 1 knot
+// intervals those columns live on; basis_functions(t, x, m) (src/bsplines.jl:
+// 28-52), which the reference stores as a sparse matrix in memory, never
+// leaves the SM.
 // ---------------------------------------------------------------------------
 struct AsmArgs {
     KnotView kvL, kvR;
@@ -72,11 +65,12 @@ struct AsmArgs {
     i64 col_lo, col_hi;           // columns written (0-based, within the restriction)
     i64 s_lo, s_hi;               // t.t intervals summed
     int TJ;
+    int two_tab;                  // tiled kernel: L and R need different tables (da != db or different left multiplicity)
     double *band;                 // column col_lo is at band[0]
 };
 
 constexpr int ASM_THREADS = 256;
-constexpr int ASM_SMAX = 32 + CB_KMAX;             // most intervals a column tile can touch
+constexpr int ASM_SMAX = 32 + CB_KMAX;             // most intervals a column tile of the generic kernel can touch
 
 // idx = j*(j-1)/2 + r  ->  (j, r) for the reciprocal table (j = 1..CB_KMAX-1, r < j)
 struct RcIndex { unsigned char j[CB_KMAX * (CB_KMAX - 1) / 2], r[CB_KMAX * (CB_KMAX - 1) / 2]; };
@@ -87,33 +81,275 @@ static RcIndex make_rc_index() {
 }
 __constant__ RcIndex c_rc_index;
 
+// ---------------------------------------------------------------------------
+// Tiled kernel (both bases of order K, q <= 2 QH nodes per interval).  Everything below is
+// bound by shared-memory wavefronts, not by FP64 issue (ncu, profiles/r1l): the phases are laid
+// out so that every shared-memory access is a 16-byte one and every loaded value is used twice.
+//
+//   phase 0  per interval: its 2K-knot window and the K(K-1)/2 reciprocal knot differences of
+//            the Cox-de Boor recursion (shared by the interval's q nodes), one 16-byte aligned
+//            record IT[sl]
+//   phase 1  one thread per (interval, node pair): the K live functions (db-th derivative; da-th
+//            as well when the two tables differ) at both nodes by one interleaved sweep; rows
+//            of 2 QH node values, stored as 16-byte pairs; the node weight (-1)^a w_l op(x_l)
+//            is kept separately.  The pad node of an odd q gets weight and values 0.
+//   phase 2a one thread per (interval, row pair a, a + ceil(K/2)): 2K entries of the interval's
+//            local matrix  M_s[a][b] = sum_l (L_a w)_l R_b,l ; the weighted L rows stay in
+//            registers, the R rows are shared-memory broadcasts within the interval
+//   phase 2b one thread per band entry: sum of the <= K local matrices that hold it, intervals
+//            in increasing order — overlap_matrix! (src/bsplines.jl:58-73) in gather form, so
+//            no atomics, and every entry is the same sum whatever the tiling or restriction
+//
+// QP/2 is odd so that the 16-byte reads of consecutive (interval, row) threads fall into
+// different banks; local matrices have the odd row pitch K|1.
+// ---------------------------------------------------------------------------
+template <int QH> struct AsmPitch { static constexpr int QP = (QH & 1) ? 2 * QH : 2 * QH + 2; };
+
+// Knot and reciprocal tables of a tile, each in two copies so that a run starting at ANY index
+// can be read as 16-byte pairs: copy 0 holds v[0], v[1], ..., copy 1 holds v[1], v[2], ...
+// (run starting at odd p: pairs of copy 1 from index p-1).
+//   KN[c][e]      knot with expanded 0-based index sA + ml - K + e (clamped), e < NS + 2K
+//   RD[c][j][p]   1 / (KN[p + j] - KN[p]), j = 1..K-1: the reciprocal of level j, entry r of the
+//                 Cox-de Boor sweep on interval slot sl is RD[j][sl + K - j + r]
+struct AsmTab {
+    const double *kn[2], *rd[2];
+    int pitch;                                      // doubles per (copy, level) row, even
+};
+
+// Two interleaved Cox-de Boor sweeps (cb_bspline_all_rc, bspline_core.cuh) for two nodes x0, x1
+// of interval slot sl.
+template <int K>
+__device__ __forceinline__ void asm_bspline_pair(const AsmTab &T, int sl, double x0, double x1, int m,
+                                                 double (&N0)[K], double (&N1)[K]) {
+    double tw[2 * K];                               // knot window of the interval
+    {
+        const double2 *k2 = reinterpret_cast<const double2 *>(T.kn[sl & 1] + (sl & ~1));
+#pragma unroll
+        for (int t = 0; t < K; ++t) { const double2 v = k2[t]; tw[2 * t] = v.x; tw[2 * t + 1] = v.y; }
+    }
+#pragma unroll
+    for (int r = 0; r < K; ++r) { N0[r] = 0.0; N1[r] = 0.0; }
+    if (m >= K) return;
+    N0[0] = 1.0; N1[0] = 1.0;
+    const int jmax = K - 1 - m;
+#pragma unroll
+    for (int j = 1; j <= K - 1; ++j) {
+        const int p0 = sl + K - j;                  // first entry of the level's reciprocal run
+        const double2 *r2 = reinterpret_cast<const double2 *>(T.rd[p0 & 1] + (size_t)j * T.pitch + (p0 & ~1));
+        double rc[K];
+#pragma unroll
+        for (int h = 0; h < (j + 1) / 2; ++h) { const double2 v = r2[h]; rc[2 * h] = v.x; if (2 * h + 1 < K) rc[2 * h + 1] = v.y; }
+        if (j <= jmax) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < j; ++r) {
+                const double t0 = N0[r] * rc[r], t1 = N1[r] * rc[r];
+                N0[r] = fma(tw[K + r] - x0, t0, s0); N1[r] = fma(tw[K + r] - x1, t1, s1);
+                s0 = (x0 - tw[K - j + r]) * t0; s1 = (x1 - tw[K - j + r]) * t1;
+            }
+            N0[j] = s0; N1[j] = s1;
+        } else {
+            double p0_ = 0.0, p1_ = 0.0;
+#pragma unroll
+            for (int r = 0; r <= j; ++r) {
+                double q0 = 0.0, q1 = 0.0;
+                if (r < j) { q0 = N0[r] * rc[r]; q1 = N1[r] * rc[r]; }
+                N0[r] = (double)j * (p0_ - q0); N1[r] = (double)j * (p1_ - q1);
+                p0_ = q0; p1_ = q1;
+            }
+        }
+    }
+}
+
+template <int K, int QH>
+__global__ void __launch_bounds__(ASM_THREADS, 2)
+bspline_assemble_tiled_kernel(AsmArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int QP = AsmPitch<QH>::QP, KP2 = (K + 1) / 2 * 2, KH = (K + 1) / 2;
+    const int q = A.q, W = A.l + A.u + 1, TJ = A.TJ;
+    const int NS = TJ + K - 1;
+    const int NKP = (NS + 2 * K + 2) / 2 * 2;      // pitch of the knot / reciprocal rows
+    const int mlL = A.kvL.ml, mlR = A.kvR.ml;
+    const i64 n_tt = A.kvR.n_tt;
+    double *TR = sm;                               // [NS][K][QP]   raw db-th derivatives
+    double *TL = A.two_tab ? TR + (size_t)NS * K * QP : TR;   // [NS][K][QP]   raw da-th derivatives
+    double *WL = TL + (size_t)NS * K * QP;         // [NS][QP]      (-1)^a w op
+    double *MS = WL + (size_t)NS * QP;             // [NS][K][KP2]  local matrices, TRANSPOSED: MS[sl][b][a]
+    double *KN = MS + (size_t)NS * K * KP2;        // [2][NKP]
+    double *RD = KN + 2 * NKP;                     // [2][K][NKP]
+    int *sOrd = reinterpret_cast<int *>(RD + (size_t)2 * K * NKP);   // [NS] ordinal among the non-empty intervals, -1 if empty
+    AsmTab T;
+    T.kn[0] = KN; T.kn[1] = KN + NKP; T.rd[0] = RD; T.rd[1] = RD + (size_t)K * NKP; T.pitch = NKP;
+    const double sgn = (A.da & 1) ? -1.0 : 1.0;    // src/bspline_derivatives.jl:14
+    const i64 ntiles = (A.col_hi - A.col_lo + TJ - 1) / TJ;
+
+    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const i64 j0 = A.col_lo + tile * TJ;
+        const i64 j1 = j0 + TJ < A.col_hi ? j0 + TJ : A.col_hi;      // exclusive
+        // intervals of the tile's columns: function fj (1-based) lives on s = fj-mlR .. fj-mlR+K-1
+        i64 sA = (A.colR0 + 1 + j0) - mlR;
+        i64 sB = (A.colR0 + j1) - mlR + K - 1;                        // inclusive
+        if (sA < 0) sA = 0;
+        if (sB > n_tt - 2) sB = n_tt - 2;
+        if (sA < A.s_lo) sA = A.s_lo;
+        if (sB > A.s_hi - 1) sB = A.s_hi - 1;
+        const int ns = sB >= sA ? (int)(sB - sA + 1) : 0;
+        __syncthreads();                            // previous tile consumed
+        for (int e = threadIdx.x; e < ns; e += ASM_THREADS) sOrd[e] = A.ordR[sA + e + mlR - 1];
+        // ---- phase 0 ----------------------------------------------------------
+        for (int e = threadIdx.x; e < ns + 2 * K; e += ASM_THREADS) {
+            const double v = A.kvR.at(sA + mlR - K + e);
+            KN[e] = v;
+            if (e > 0) KN[NKP + e - 1] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < (K - 1) * (ns + 2 * K); e += ASM_THREADS) {
+            const int j = 1 + e / (ns + 2 * K), p = e - (j - 1) * (ns + 2 * K);
+            if (p + j < ns + 2 * K) {
+                const double dk = KN[p + j] - KN[p];
+                const double v = dk != 0.0 ? fast_rcp(dk) : 0.0;     // zero widths only feed empty intervals / absent functions
+                RD[(size_t)j * NKP + p] = v;
+                if (p > 0) RD[(size_t)(K + j) * NKP + p - 1] = v;
+            }
+        }
+        __syncthreads();
+        // ---- phase 1 ----------------------------------------------------------
+        for (int e = threadIdx.x; e < ns * QH; e += ASM_THREADS) {
+            const int sl = e / QH, lp = e - sl * QH;
+            const int c = sOrd[sl];
+            if (c < 0) continue;                    // empty interval: skipped in phase 2a
+            const int l0 = 2 * lp, l1 = 2 * lp + 1;
+            const bool has1 = l1 < q;               // the second node of the last pair is padding when q is odd
+            const i64 g0 = (i64)c * q + l0, g1 = has1 ? g0 + 1 : g0;
+            const double x0 = A.x[g0], x1 = A.x[g1];
+            double w0 = 1.0, w1 = 1.0, o0 = 1.0, o1 = 1.0;
+            if (A.coulomb != 2) { w0 = A.w[g0]; w1 = A.w[g1]; }
+            if (A.opvals) { o0 = A.opvals[g0]; o1 = A.opvals[g1]; }
+            else if (A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
+            double2 *tr2 = reinterpret_cast<double2 *>(TR + (size_t)sl * K * QP + l0);
+            double N0[K], N1[K];
+            asm_bspline_pair<K>(T, sl, x0, x1, A.db, N0, N1);
+#pragma unroll
+            for (int a = 0; a < K; ++a) tr2[a * (QP / 2)] = make_double2(N0[a], has1 ? N1[a] : 0.0);
+            *reinterpret_cast<double2 *>(WL + (size_t)sl * QP + l0) = make_double2((sgn * w0) * o0, has1 ? (sgn * w1) * o1 : 0.0);
+            if (A.two_tab) {
+                double2 *tl2 = reinterpret_cast<double2 *>(TL + (size_t)sl * K * QP + l0);
+                if (mlL == mlR) {                   // same knot window, other derivative order
+                    asm_bspline_pair<K>(T, sl, x0, x1, A.da, N0, N1);
+                } else {                            // windows differ by the clamping at the left end
+                    double tw[2 * K];
+                    cb_knot_window<K>(A.kvL.tt, n_tt, mlL, (int)(sA + sl + mlL), tw);
+                    cb_bspline_all<K>(tw, x0, A.da, N0);
+                    cb_bspline_all<K>(tw, x1, A.da, N1);
+                }
+#pragma unroll
+                for (int a = 0; a < K; ++a) tl2[a * (QP / 2)] = make_double2(N0[a], has1 ? N1[a] : 0.0);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2a: local matrices ---------------------------------------------
+        for (int e = threadIdx.x; e < ns * KH; e += ASM_THREADS) {
+            const int sl = e / KH, ap = e - sl * KH;
+            const int a0 = 2 * ap, a1 = a0 + 1;     // rows a0, a0 + 1: one 16-byte store per column of the local matrix
+            const bool has1 = a1 < K;
+            double2 *m2 = reinterpret_cast<double2 *>(MS + (size_t)sl * K * KP2 + a0);
+            if (sOrd[sl] < 0) {
+#pragma unroll
+                for (int b = 0; b < K; ++b) m2[b * (KP2 / 2)] = make_double2(0.0, 0.0);
+                continue;
+            }
+            const double2 *wl2 = reinterpret_cast<const double2 *>(WL + (size_t)sl * QP);
+            const double2 *tl0 = reinterpret_cast<const double2 *>(TL + ((size_t)sl * K + a0) * QP);
+            const double2 *tl1 = reinterpret_cast<const double2 *>(TL + ((size_t)sl * K + (has1 ? a1 : a0)) * QP);
+            double2 lw0[QH], lw1[QH];
+#pragma unroll
+            for (int h = 0; h < QH; ++h) {
+                const double2 w2 = wl2[h], t0 = tl0[h], t1 = tl1[h];
+                lw0[h] = make_double2(t0.x * w2.x, t0.y * w2.y);
+                lw1[h] = make_double2(t1.x * w2.x, t1.y * w2.y);
+            }
+            const double2 *tr2 = reinterpret_cast<const double2 *>(TR + (size_t)sl * K * QP);
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int h = 0; h < QH; ++h) {
+                    const double2 r2 = tr2[b * (QP / 2) + h];
+                    s0 = fma(lw0[h].x, r2.x, s0); s1 = fma(lw1[h].x, r2.x, s1);
+                    s0 = fma(lw0[h].y, r2.y, s0); s1 = fma(lw1[h].y, r2.y, s1);
+                }
+                m2[b * (KP2 / 2)] = make_double2(s0, has1 ? s1 : 0.0);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2b: gather into the band -------------------------------------
+        // one thread per column: column b of the local matrix of each of its K intervals is a run
+        // of K consecutive band entries; the W = 2K-1 sums stay in registers
+        for (int jj = threadIdx.x; jj < (int)(j1 - j0); jj += ASM_THREADS) {
+            const i64 j = j0 + jj, fj = A.colR0 + 1 + j;
+            double acc[2 * K - 1];
+#pragma unroll
+            for (int t = 0; t < 2 * K - 1; ++t) acc[t] = 0.0;
+            // interval r of the column: s = fj - mlR + r, column b = K-1-r of its local matrix; its row a is
+            // function fi = s + mlL - K + 1 + a, so acc[t], t = a + r, is row fi = fj - mlR + mlL - K + 1 + t
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const i64 s = fj - mlR + r;
+                if (s < sA || s > sB) continue;
+                const double2 *m2 = reinterpret_cast<const double2 *>(MS + ((size_t)(s - sA) * K + (K - 1 - r)) * KP2);
+#pragma unroll
+                for (int h = 0; h < KH; ++h) {
+                    const double2 v = m2[h];
+                    acc[2 * h + r] += v.x;
+                    if (2 * h + 1 < K) acc[2 * h + 1 + r] += v.y;
+                }
+            }
+            const i64 i_first = (fj - mlR + mlL - K + 1) - (A.rowL0 + 1);   // restricted row index of acc[0]
+            double *bc = A.band + (i64)W * (j - A.col_lo);
+            // band slot d holds row i = j - u + d
+            const i64 t_of_d0 = (j - A.u) - i_first;                 // acc index of band slot 0
+#pragma unroll
+            for (int t = 0; t < 2 * K - 1; ++t) {
+                const i64 d = t - t_of_d0, i = i_first + t;
+                if (d >= 0 && d < W && i >= 0 && i < A.mm && j < A.nn) bc[d] = acc[t];
+            }
+            // band slots not covered by the 2K-1 rows (or outside the matrix) are zero
+            for (int d = 0; d < W; ++d) {
+                const i64 t = d + t_of_d0, i = j - A.u + d;
+                if (t < 0 || t >= 2 * K - 1 || i < 0 || i >= A.mm || j >= A.nn) bc[d] = 0.0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Generic kernel: run-time orders (kL != kR, test/bsplines/derivatives.jl:36-79), unusual node
+// counts, k == 1.  Phase 1 evaluates both tables (already weighted) into shared memory, phase 2
+// is one thread per band entry summing over the common intervals and their nodes in increasing
+// node order, the order of the reference's sparse dot product.
+// ---------------------------------------------------------------------------
 // padded node count: even (16-byte pairs) and = 2 mod 4 so that rows of different functions fall
 // into different banks for the 16-byte reads of phase 2
 __host__ __device__ inline int asm_qpad(int q) { int p = q + (q & 1); return (p & 3) == 0 ? p + 2 : p; }
 
-template <int KT>
 __global__ void __launch_bounds__(ASM_THREADS)
 bspline_assemble_kernel(AsmArgs A) {
     extern __shared__ __align__(16) double sm[];
-    const int kL = KT > 0 ? KT : A.kL, kR = KT > 0 ? KT : A.kR;
+    const int kL = A.kL, kR = A.kR;
     const int q = A.q, W = A.l + A.u + 1, TJ = A.TJ;
     const int QP = asm_qpad(q);
     const int mlL = A.kvL.ml, mlR = A.kvR.ml;
     const i64 n_tt = A.kvR.n_tt;
     const int SMAX = TJ + kR - 1;                  // intervals a column tile can touch
-    constexpr int NRC = KT > 0 ? KT * (KT - 1) / 2 : 0;            // reciprocal knot differences per interval
     double *TL = sm;                               // [SMAX][kL][QP]  (node index fastest, zero padded)
     double *TR = TL + (size_t)SMAX * kL * QP;      // [SMAX][kR][QP]
-    double *RC = TR + (size_t)SMAX * kR * QP;      // [SMAX][NRC]    (same-order fast path only)
     const double sgn = (A.da & 1) ? -1.0 : 1.0;    // src/bspline_derivatives.jl:14
     const i64 ntiles = (A.col_hi - A.col_lo + TJ - 1) / TJ;
-    const bool same_tab = A.da == A.db && mlL == mlR;
     __shared__ int sOrd[ASM_SMAX];                  // ordinal of each interval of the tile among the non-empty ones, -1 if empty
 
     for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const i64 j0 = A.col_lo + tile * TJ;
         const i64 j1 = j0 + TJ < A.col_hi ? j0 + TJ : A.col_hi;      // exclusive
-        // intervals of the tile's columns: function fj (1-based) lives on s = fj-mlR .. fj-mlR+kR-1
         i64 sA = (A.colR0 + 1 + j0) - mlR;
         i64 sB = (A.colR0 + j1) - mlR + kR - 1;                       // inclusive
         if (sA < 0) sA = 0;
@@ -123,32 +359,12 @@ bspline_assemble_kernel(AsmArgs A) {
         const int ns = sB >= sA ? (int)(sB - sA + 1) : 0;
         __syncthreads();                            // previous tile consumed
         for (int e = threadIdx.x; e < ns; e += ASM_THREADS) sOrd[e] = A.ordR[sA + e + mlR - 1];
-        __syncthreads();
-        // ---- phase 0: reciprocal knot differences, once per interval -----------
-        if (KT > 0) {
-            constexpr int K = KT > 0 ? KT : 1;
-            for (int e = threadIdx.x; e < ns * NRC; e += ASM_THREADS) {
-                const int sl = e / (NRC > 0 ? NRC : 1), idx = e - sl * NRC;
-                const i64 s = sA + sl;
-                if (sOrd[sl] < 0) continue;
-                const int j = c_rc_index.j[idx], r = c_rc_index.r[idx];
-                // tw[K + r] - tw[K - j + r] with tw[t] = knot (I - K + t), I = s + mlR (0-based expanded index I-K+t)
-                const i64 I = s + mlR;
-                const double hi = A.kvR.at(I - K + (K + r)), lo = A.kvR.at(I - K + (K - j + r));
-                RC[e] = fast_rcp(hi - lo);
-            }
-            // zero the node padding of both tables (never written in phase 1)
-            for (int e = threadIdx.x; e < ns * (kL + kR) * (QP - q); e += ASM_THREADS) {
-                const int row = e / (QP - q), c = e - row * (QP - q);
-                (row < ns * kL ? TL + (size_t)row * QP : TR + (size_t)(row - ns * kL) * QP)[q + c] = 0.0;
-            }
-            __syncthreads();
-        } else {
-            for (int e = threadIdx.x; e < ns * (kL + kR) * (QP - q); e += ASM_THREADS) {
-                const int row = e / (QP - q), c = e - row * (QP - q);
-                (row < ns * kL ? TL + (size_t)row * QP : TR + (size_t)(row - ns * kL) * QP)[q + c] = 0.0;
-            }
+        // zero the node padding of both tables (never written in phase 1)
+        for (int e = threadIdx.x; e < ns * (kL + kR) * (QP - q); e += ASM_THREADS) {
+            const int row = e / (QP - q), c = e - row * (QP - q);
+            (row < ns * kL ? TL + (size_t)row * QP : TR + (size_t)(row - ns * kL) * QP)[q + c] = 0.0;
         }
+        __syncthreads();
         // ---- phase 1: tables ----------------------------------------------
         for (int e = threadIdx.x; e < ns * q; e += ASM_THREADS) {
             const int sl = e / q, ll = e - sl * q;
@@ -162,52 +378,22 @@ bspline_assemble_kernel(AsmArgs A) {
             if (A.opvals) ov = A.opvals[(i64)c * q + ll];
             else if (A.coulomb == 1) ov = -A.Z / xv;
             const int IL = (int)(s + mlL), IR = (int)(s + mlR);
-            if (KT > 0) {
-                constexpr int K = KT > 0 ? KT : 1;
-                const double *rc = RC + (size_t)sl * NRC;
-                double tw[2 * K], N[K];
-                cb_knot_window<K>(A.kvR.tt, n_tt, mlR, IR, tw);
-                cb_bspline_all_rc<K>(tw, rc, xv, A.db, N);
-#pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    i64 f = (i64)IR - K + 1 + a;
-                    tr[a * QP] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
-                }
-                if (!same_tab) {
-                    // the knot window of L is the same set of knots when mlL == mlR; otherwise the
-                    // windows differ only by clamping at the ends, where the reciprocals are recomputed
-                    if (mlL == mlR) {
-                        cb_bspline_all_rc<K>(tw, rc, xv, A.da, N);
-                    } else {
-                        cb_knot_window<K>(A.kvL.tt, n_tt, mlL, IL, tw);
-                        cb_bspline_all<K>(tw, xv, A.da, N);
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    i64 f = (i64)IL - K + 1 + a;
-                    tl[a * QP] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
-                }
-            } else {
-                double tw[2 * CB_KMAX], N[CB_KMAX];
-                for (int t = 0; t < 2 * kR; ++t) tw[t] = A.kvR.at((i64)IR - kR + t);
-                bspline_all_rt(kR, tw, xv, A.db, N);
-                for (int a = 0; a < kR; ++a) {
-                    i64 f = (i64)IR - kR + 1 + a;
-                    tr[a * QP] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
-                }
-                for (int t = 0; t < 2 * kL; ++t) tw[t] = A.kvL.at((i64)IL - kL + t);
-                bspline_all_rt(kL, tw, xv, A.da, N);
-                for (int a = 0; a < kL; ++a) {
-                    i64 f = (i64)IL - kL + 1 + a;
-                    tl[a * QP] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
-                }
+            double tw[2 * CB_KMAX], N[CB_KMAX];
+            for (int t = 0; t < 2 * kR; ++t) tw[t] = A.kvR.at((i64)IR - kR + t);
+            bspline_all_rt(kR, tw, xv, A.db, N);
+            for (int a = 0; a < kR; ++a) {
+                i64 f = (i64)IR - kR + 1 + a;
+                tr[a * QP] = (f >= 1 && f <= A.nfR) ? ov * N[a] : 0.0;
+            }
+            for (int t = 0; t < 2 * kL; ++t) tw[t] = A.kvL.at((i64)IL - kL + t);
+            bspline_all_rt(kL, tw, xv, A.da, N);
+            for (int a = 0; a < kL; ++a) {
+                i64 f = (i64)IL - kL + 1 + a;
+                tl[a * QP] = (f >= 1 && f <= A.nfL) ? (sgn * N[a]) * wv : 0.0;
             }
         }
         __syncthreads();
         // ---- phase 2: gather into the band ----------------------------------
-        // one thread per band entry; the sum runs over the common intervals and, inside an interval,
-        // over the nodes in increasing order (two nodes per 16-byte shared-memory read)
         const int nent = (int)(j1 - j0) * W;
         for (int e = threadIdx.x; e < nent; e += ASM_THREADS) {
             const int jj = e / W, d = e - jj * W;
@@ -437,37 +623,55 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     A.rowL0 = rowL0; A.mm = m; A.colR0 = colR0; A.nn = n;
     A.l = l; A.u = u; A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
     A.band = band;
+    const i64 ncol = col_hi - col_lo;
+    // ---- tiled kernel: same order 2..CB_KMAX on both sides and the default node count family ----
+    const int K = L->k, QH = (K + 2) / 2;           // q = K + 1 (num_quadrature_points(k, 3)) -> ceil(q / 2)
+    if (L->k == R->k && K >= 2 && K <= CB_KMAX && (A.q + 1) / 2 == QH) {
+        const int QP = (QH & 1) ? 2 * QH : 2 * QH + 2, KP2 = (K + 1) / 2 * 2;
+        A.two_tab = (a != b || L->ml != R->ml) ? 1 : 0;
+        const size_t per_iv = sizeof(double) * ((size_t)K * QP * (A.two_tab ? 2 : 1) + QP + K * KP2 + 2 * (K + 1)) + sizeof(int);
+        const size_t fixed = sizeof(double) * 2 * (K + 1) * (2 * K + 2) + 16;
+        // one round of 256 (interval, node pair) work items per tile; two CTAs per SM when that fits
+        int ns = ASM_THREADS / QH;
+        while (ns > 2 * K && (size_t)ns * per_iv + fixed > 112 * 1024) --ns;
+        while (ns >= K && (size_t)ns * per_iv + fixed > 220 * 1024) --ns;
+        if (ns >= K) {
+            i64 TJ = ns - K + 1;
+            if (TJ > ncol) TJ = ncol;
+            A.TJ = (int)TJ;
+            const size_t smem = ((size_t)(A.TJ + K - 1) * per_iv + fixed) / 16 * 16;
+            const i64 ntiles = (ncol + A.TJ - 1) / A.TJ;
+            const int grid = (int)(ntiles < (i64)CB_NUM_SMS * 8 ? ntiles : (i64)CB_NUM_SMS * 8);
+#define CB_ASM_TILED(KT)                                                                                     \
+    case KT: {                                                                                               \
+        auto kern = bspline_assemble_tiled_kernel<KT, (KT + 2) / 2>;                                         \
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        kern<<<grid, ASM_THREADS, smem, st>>>(A);                                                            \
+    } break;
+            switch (K) {
+                CB_ASM_TILED(2) CB_ASM_TILED(3) CB_ASM_TILED(4) CB_ASM_TILED(5) CB_ASM_TILED(6)
+                CB_ASM_TILED(7) CB_ASM_TILED(8) CB_ASM_TILED(9) CB_ASM_TILED(10) CB_ASM_TILED(11)
+                CB_ASM_TILED(12) CB_ASM_TILED(13) CB_ASM_TILED(14) CB_ASM_TILED(15) CB_ASM_TILED(16)
+                default: break;
+            }
+#undef CB_ASM_TILED
+            CB_LAUNCH_CHECK();
+            return CB_OK;
+        }
+    }
+    // ---- generic kernel ----
     // column tile: as many columns as fit ~96 KB (two CTAs per SM), at most 32
-    const int NRC = (L->k == R->k) ? L->k * (L->k - 1) / 2 : 0;
-    const size_t per_iv = sizeof(double) * ((size_t)asm_qpad(A.q) * (A.kL + A.kR) + NRC);
+    A.two_tab = 1;
+    const size_t per_iv = sizeof(double) * ((size_t)asm_qpad(A.q) * (A.kL + A.kR));
     int TJ = 32;
     while (TJ > 1 && (size_t)(TJ + A.kR - 1) * per_iv > 112 * 1024) TJ /= 2;   // two CTAs per SM
     size_t smem = (size_t)(TJ + A.kR - 1) * per_iv;
     if (smem > 220 * 1024) { cb_set_error("cb_bspline_assemble: k=%d, q=%d tables exceed shared memory", k, A.q); return CB_ERR_UNSUPPORTED; }
     A.TJ = TJ;
-    i64 ntiles = (col_hi - col_lo + TJ - 1) / TJ;
+    i64 ntiles = (ncol + TJ - 1) / TJ;
     int grid = (int)(ntiles < (i64)CB_NUM_SMS * 32 ? ntiles : (i64)CB_NUM_SMS * 32);
-#define CB_ASM_LAUNCH(KT)                                                                         \
-    do {                                                                                          \
-        CB_CUDA(cudaFuncSetAttribute(bspline_assemble_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        bspline_assemble_kernel<KT><<<grid, ASM_THREADS, smem, st>>>(A);                          \
-    } while (0)
-    if (L->k != R->k) {
-        CB_ASM_LAUNCH(0);
-    } else {
-        switch (L->k) {
-            case 1: CB_ASM_LAUNCH(1); break;   case 2: CB_ASM_LAUNCH(2); break;
-            case 3: CB_ASM_LAUNCH(3); break;   case 4: CB_ASM_LAUNCH(4); break;
-            case 5: CB_ASM_LAUNCH(5); break;   case 6: CB_ASM_LAUNCH(6); break;
-            case 7: CB_ASM_LAUNCH(7); break;   case 8: CB_ASM_LAUNCH(8); break;
-            case 9: CB_ASM_LAUNCH(9); break;   case 10: CB_ASM_LAUNCH(10); break;
-            case 11: CB_ASM_LAUNCH(11); break; case 12: CB_ASM_LAUNCH(12); break;
-            case 13: CB_ASM_LAUNCH(13); break; case 14: CB_ASM_LAUNCH(14); break;
-            case 15: CB_ASM_LAUNCH(15); break; case 16: CB_ASM_LAUNCH(16); break;
-            default: CB_ASM_LAUNCH(0); break;
-        }
-    }
-#undef CB_ASM_LAUNCH
+    CB_CUDA(cudaFuncSetAttribute(bspline_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bspline_assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(A);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

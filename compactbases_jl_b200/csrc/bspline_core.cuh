@@ -108,6 +108,8 @@ __device__ __forceinline__ void cb_bspline_all_rc(const double (&tw)[2 * K], con
     if (m >= K) return;
     N[0] = 1.0;
     const int jmax = K - 1 - m;
+    // level j is a value step (order j -> j+1) up to jmax and a derivative step after it: one
+    // warp-uniform branch per level instead of per-entry selects
 #pragma unroll
     for (int j = 1; j <= K - 1; ++j) {
         if (j <= jmax) {
@@ -119,17 +121,13 @@ __device__ __forceinline__ void cb_bspline_all_rc(const double (&tw)[2 * K], con
                 saved = (x - tw[K - j + r]) * term;
             }
             N[j] = saved;
-        }
-    }
-#pragma unroll
-    for (int o = 1; o <= K - 1; ++o) {
-        if (o >= K - m) {
+        } else {
             double qprev = 0.0;
 #pragma unroll
-            for (int r = 0; r <= o; ++r) {
+            for (int r = 0; r <= j; ++r) {
                 double qr = 0.0;
-                if (r < o) qr = N[r] * rc[o * (o - 1) / 2 + r];
-                N[r] = (double)o * (qprev - qr);
+                if (r < j) qr = N[r] * rc[j * (j - 1) / 2 + r];
+                N[r] = (double)j * (qprev - qr);
                 qprev = qr;
             }
         }
