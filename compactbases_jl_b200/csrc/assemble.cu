@@ -112,8 +112,10 @@ template <int QH> struct AsmPitch { static constexpr int QP = (QH & 1) ? 2 * QH 
 //   RD[c][j][p]   1 / (KN[p + j] - KN[p]), j = 1..K-1: the reciprocal of level j, entry r of the
 //                 Cox-de Boor sweep on interval slot sl is RD[j][sl + K - j + r]
 struct AsmTab {
-    const double *kn[2], *rd[2];
-    int pitch;                                      // doubles per (copy, level) row, even
+    double *sm;                                     // the CTA's dynamic shared memory (keeps the accesses LDS/STS)
+    int kn, rd, pitch;                              // offsets of KN / RD in doubles; doubles per level row, even
+    int kn_copy, rd_copy;                           // doubles between the two copies: an odd number of 16-byte units, so that
+                                                    // threads of neighbouring intervals (different copies) hit different banks
 };
 
 // Two interleaved Cox-de Boor sweeps (cb_bspline_all_rc, bspline_core.cuh) for two nodes x0, x1
@@ -123,7 +125,7 @@ __device__ __forceinline__ void asm_bspline_pair(const AsmTab &T, int sl, double
                                                  double (&N0)[K], double (&N1)[K]) {
     double tw[2 * K];                               // knot window of the interval
     {
-        const double2 *k2 = reinterpret_cast<const double2 *>(T.kn[sl & 1] + (sl & ~1));
+        const double2 *k2 = reinterpret_cast<const double2 *>(T.sm + T.kn + (sl & 1) * T.kn_copy + (sl & ~1));
 #pragma unroll
         for (int t = 0; t < K; ++t) { const double2 v = k2[t]; tw[2 * t] = v.x; tw[2 * t + 1] = v.y; }
     }
@@ -135,7 +137,7 @@ __device__ __forceinline__ void asm_bspline_pair(const AsmTab &T, int sl, double
 #pragma unroll
     for (int j = 1; j <= K - 1; ++j) {
         const int p0 = sl + K - j;                  // first entry of the level's reciprocal run
-        const double2 *r2 = reinterpret_cast<const double2 *>(T.rd[p0 & 1] + (size_t)j * T.pitch + (p0 & ~1));
+        const double2 *r2 = reinterpret_cast<const double2 *>(T.sm + T.rd + (p0 & 1) * T.rd_copy + j * T.pitch + (p0 & ~1));
         double rc[K];
 #pragma unroll
         for (int h = 0; h < (j + 1) / 2; ++h) { const double2 v = r2[h]; rc[2 * h] = v.x; if (2 * h + 1 < K) rc[2 * h + 1] = v.y; }
@@ -161,79 +163,147 @@ __device__ __forceinline__ void asm_bspline_pair(const AsmTab &T, int sl, double
     }
 }
 
+// Local matrices: K columns of pitch KP2 (even) per interval; the interval pitch is an odd multiple (= KH mod 8) of
+// 16 bytes so that the 16-byte stores of consecutive (interval, row pair) threads are bank-conflict free.
+template <int K> struct AsmMs {
+    static constexpr int KP2 = (K + 1) / 2 * 2, KH = (K + 1) / 2;
+    static constexpr int U0 = K * KP2 / 2;                     // 16-byte units needed
+    static constexpr int U = U0 + ((KH - U0) % 8 + 8) % 8;     // smallest U >= U0 with U = KH (mod 8)
+    static constexpr int MSP = 2 * U;
+};
+
+// Geometry of one column tile: columns [j0, j1), intervals [sA, sB] of t.t.
+struct AsmTile { i64 j0, j1, sA, sB; int ns; };
+
+template <int K>
+__device__ __forceinline__ AsmTile asm_tile(const AsmArgs &A, i64 tile) {
+    AsmTile t;
+    const int mlR = A.kvR.ml;
+    t.j0 = A.col_lo + tile * A.TJ;
+    t.j1 = t.j0 + A.TJ < A.col_hi ? t.j0 + A.TJ : A.col_hi;           // exclusive
+    // function fj (1-based) lives on s = fj-mlR .. fj-mlR+K-1
+    t.sA = (A.colR0 + 1 + t.j0) - mlR;
+    t.sB = (A.colR0 + t.j1) - mlR + K - 1;                             // inclusive
+    if (t.sA < 0) t.sA = 0;
+    if (t.sB > A.kvR.n_tt - 2) t.sB = A.kvR.n_tt - 2;
+    if (t.sA < A.s_lo) t.sA = A.s_lo;
+    if (t.sB > A.s_hi - 1) t.sB = A.s_hi - 1;
+    t.ns = t.sB >= t.sA ? (int)(t.sB - t.sA + 1) : 0;
+    return t;
+}
+
 template <int K, int QH>
 __global__ void __launch_bounds__(ASM_THREADS, 2)
 bspline_assemble_tiled_kernel(AsmArgs A) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int QP = AsmPitch<QH>::QP, KP2 = (K + 1) / 2 * 2, KH = (K + 1) / 2;
+    constexpr int QP = AsmPitch<QH>::QP, KP2 = (K + 1) / 2 * 2, KH = (K + 1) / 2, W2 = 2 * K - 1;
+    constexpr int TS = KH * QP;                    // doubles per interval in each half table: KH * QP/2 16-byte units, odd multiple per row
+    constexpr int MSP = AsmMs<K>::MSP;             // doubles per interval of the local matrices
     const int q = A.q, W = A.l + A.u + 1, TJ = A.TJ;
     const int NS = TJ + K - 1;
     const int NKP = (NS + 2 * K + 2) / 2 * 2;      // pitch of the knot / reciprocal rows
     const int mlL = A.kvL.ml, mlR = A.kvR.ml;
     const i64 n_tt = A.kvR.n_tt;
-    double *TR = sm;                               // [NS][K][QP]   raw db-th derivatives
-    double *TL = A.two_tab ? TR + (size_t)NS * K * QP : TR;   // [NS][K][QP]   raw da-th derivatives
-    double *WL = TL + (size_t)NS * K * QP;         // [NS][QP]      (-1)^a w op
-    double *MS = WL + (size_t)NS * QP;             // [NS][K][KP2]  local matrices, TRANSPOSED: MS[sl][b][a]
-    double *KN = MS + (size_t)NS * K * KP2;        // [2][NKP]
-    double *RD = KN + 2 * NKP;                     // [2][K][NKP]
-    int *sOrd = reinterpret_cast<int *>(RD + (size_t)2 * K * NKP);   // [NS] ordinal among the non-empty intervals, -1 if empty
+    // tables: row a of interval sl is at  T?[(a & 1) * NS * TS + sl * TS + (a >> 1) * QP]  — even rows and odd rows in
+    // separate halves, so that the row pairs (2 ap, 2 ap + 1) of consecutive (interval, ap) threads are QP/2 (odd) 16-byte
+    // units apart in each half
+    double *TR = sm;                               // [2][NS][KH][QP]  raw db-th derivatives
+    double *TL = A.two_tab ? TR + (size_t)2 * NS * TS : TR;   //               raw da-th derivatives
+    double *WL = TL + (size_t)2 * NS * TS;         // [NS][QP]         (-1)^a w op
+    double *MS = WL + (size_t)NS * QP;             // [NS][MSP]        local matrices, TRANSPOSED: MS[sl][b * KP2 + a]
+    double *KN = MS + (size_t)NS * MSP;            // [2][NKP + 2]
+    double *RD = KN + 2 * (NKP + 2);               // [2][K * NKP + 2]
+    int *sOrd = reinterpret_cast<int *>(RD + (size_t)2 * (K * NKP + 2));   // [NS] ordinal among the non-empty intervals, -1 if empty
+    const int HALF = NS * TS;
     AsmTab T;
-    T.kn[0] = KN; T.kn[1] = KN + NKP; T.rd[0] = RD; T.rd[1] = RD + (size_t)K * NKP; T.pitch = NKP;
+    T.sm = sm; T.kn = (int)(KN - sm); T.rd = (int)(RD - sm); T.pitch = NKP;
+    T.kn_copy = ((NKP / 2) | 1) * 2; T.rd_copy = ((K * NKP / 2) | 1) * 2;
     const double sgn = (A.da & 1) ? -1.0 : 1.0;    // src/bspline_derivatives.jl:14
     const i64 ntiles = (A.col_hi - A.col_lo + TJ - 1) / TJ;
 
-    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const i64 j0 = A.col_lo + tile * TJ;
-        const i64 j1 = j0 + TJ < A.col_hi ? j0 + TJ : A.col_hi;      // exclusive
-        // intervals of the tile's columns: function fj (1-based) lives on s = fj-mlR .. fj-mlR+K-1
-        i64 sA = (A.colR0 + 1 + j0) - mlR;
-        i64 sB = (A.colR0 + j1) - mlR + K - 1;                        // inclusive
-        if (sA < 0) sA = 0;
-        if (sB > n_tt - 2) sB = n_tt - 2;
-        if (sA < A.s_lo) sA = A.s_lo;
-        if (sB > A.s_hi - 1) sB = A.s_hi - 1;
-        const int ns = sB >= sA ? (int)(sB - sA + 1) : 0;
-        __syncthreads();                            // previous tile consumed
-        for (int e = threadIdx.x; e < ns; e += ASM_THREADS) sOrd[e] = A.ordR[sA + e + mlR - 1];
-        // ---- phase 0 ----------------------------------------------------------
-        for (int e = threadIdx.x; e < ns + 2 * K; e += ASM_THREADS) {
-            const double v = A.kvR.at(sA + mlR - K + e);
-            KN[e] = v;
-            if (e > 0) KN[NKP + e - 1] = v;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < (K - 1) * (ns + 2 * K); e += ASM_THREADS) {
-            const int j = 1 + e / (ns + 2 * K), p = e - (j - 1) * (ns + 2 * K);
-            if (p + j < ns + 2 * K) {
-                const double dk = KN[p + j] - KN[p];
-                const double v = dk != 0.0 ? fast_rcp(dk) : 0.0;     // zero widths only feed empty intervals / absent functions
-                RD[(size_t)j * NKP + p] = v;
-                if (p > 0) RD[(size_t)(K + j) * NKP + p - 1] = v;
+    // Three barriers per tile:  [gather of the previous tile | tables of this tile] -> phase 1 -> phase 2a
+    AsmTile prev; prev.ns = -1; prev.j0 = prev.j1 = prev.sA = prev.sB = 0;
+    for (i64 tile = blockIdx.x; ; tile += gridDim.x) {
+        const bool live = tile < ntiles;
+        AsmTile t = prev;
+        if (live) t = asm_tile<K>(A, tile);
+        const int ns = live ? t.ns : 0;
+        const i64 sA = t.sA;
+        // this thread's phase-1 item: its node data is fetched now and used after the barrier
+        const int e1 = threadIdx.x, sl1 = e1 / QH, lp1 = e1 - sl1 * QH;
+        int c1 = -1;
+        double x0 = 1.0, x1 = 1.0, w0 = 1.0, w1 = 1.0, o0 = 1.0, o1 = 1.0;
+        const bool has1 = 2 * lp1 + 1 < q;         // the second node of the last pair is padding when q is odd
+        if (e1 < ns * QH) {
+            c1 = A.ordR[sA + sl1 + mlR - 1];
+            if (c1 >= 0) {
+                const i64 g0 = (i64)c1 * q + 2 * lp1, g1 = has1 ? g0 + 1 : g0;
+                x0 = A.x[g0]; x1 = A.x[g1];
+                if (A.coulomb != 2) { w0 = A.w[g0]; w1 = A.w[g1]; }
+                if (A.opvals) { o0 = A.opvals[g0]; o1 = A.opvals[g1]; }
             }
         }
+        // ---- phase 0 (this tile) -------------------------------------------------
+        for (int e = threadIdx.x; e < ns; e += ASM_THREADS) sOrd[e] = A.ordR[sA + e + mlR - 1];
+        for (int j = threadIdx.x >> 5; j < K; j += ASM_THREADS / 32) {           // one warp per level
+            for (int p = threadIdx.x & 31; p < ns + 2 * K; p += 32) {
+                const double lo = A.kvR.at(sA + mlR - K + p);
+                if (j == 0) {
+                    KN[p] = lo;
+                    if (p > 0) KN[T.kn_copy + p - 1] = lo;
+                } else if (p + j < ns + 2 * K) {
+                    const double dk = A.kvR.at(sA + mlR - K + p + j) - lo;
+                    const double v = dk != 0.0 ? fast_rcp(dk) : 0.0;     // zero widths only feed empty intervals / absent functions
+                    RD[j * NKP + p] = v;
+                    if (p > 0) RD[T.rd_copy + j * NKP + p - 1] = v;
+                }
+            }
+        }
+        // ---- phase 2b (previous tile): gather into the band -------------------------
+        // one thread per band entry of the (2K-1)-row run of each column; run entry tt of a column is
+        // the sum over its intervals r of MS[slot + r][K-1-r][tt - r]
+        if (prev.ns >= 0) {
+            const int nent = (int)(prev.j1 - prev.j0) * W2;
+            for (int e = threadIdx.x; e < nent; e += ASM_THREADS) {
+                const int jj = e / W2, tt = e - jj * W2;
+                const i64 j = prev.j0 + jj, fj = A.colR0 + 1 + j;
+                const int slot0 = (int)(fj - mlR - prev.sA);          // slot of the first interval of the column (may be < 0)
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int sl = slot0 + r, a = tt - r;
+                    if (a >= 0 && a < K && sl >= 0 && sl < prev.ns)
+                        s += MS[sl * MSP + (K - 1 - r) * KP2 + a];
+                }
+                // run entry tt is row fi = fj - mlR + mlL - K + 1 + tt; band slot d holds row i = j - u + d
+                const i64 i = (fj - mlR + mlL - K + 1 + tt) - (A.rowL0 + 1);
+                const i64 d = i - j + A.u;
+                if (d >= 0 && d < W && i >= 0 && i < A.mm && j < A.nn) A.band[d + (i64)W * (j - A.col_lo)] = s;
+            }
+            // band slots outside the run or outside the matrix are zero
+            const int nz = (int)(prev.j1 - prev.j0) * W;
+            for (int e = threadIdx.x; e < nz; e += ASM_THREADS) {
+                const int jj = e / W, d = e - jj * W;
+                const i64 j = prev.j0 + jj, i = j - A.u + d;
+                const i64 tt = (i + A.rowL0 + 1) - (A.colR0 + 1 + j - mlR + mlL - K + 1);
+                if (tt < 0 || tt >= W2 || i < 0 || i >= A.mm || j >= A.nn) A.band[d + (i64)W * (j - A.col_lo)] = 0.0;
+            }
+        }
+        if (!live) break;
+        prev = t;
         __syncthreads();
         // ---- phase 1 ----------------------------------------------------------
-        for (int e = threadIdx.x; e < ns * QH; e += ASM_THREADS) {
-            const int sl = e / QH, lp = e - sl * QH;
-            const int c = sOrd[sl];
-            if (c < 0) continue;                    // empty interval: skipped in phase 2a
-            const int l0 = 2 * lp, l1 = 2 * lp + 1;
-            const bool has1 = l1 < q;               // the second node of the last pair is padding when q is odd
-            const i64 g0 = (i64)c * q + l0, g1 = has1 ? g0 + 1 : g0;
-            const double x0 = A.x[g0], x1 = A.x[g1];
-            double w0 = 1.0, w1 = 1.0, o0 = 1.0, o1 = 1.0;
-            if (A.coulomb != 2) { w0 = A.w[g0]; w1 = A.w[g1]; }
-            if (A.opvals) { o0 = A.opvals[g0]; o1 = A.opvals[g1]; }
-            else if (A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
-            double2 *tr2 = reinterpret_cast<double2 *>(TR + (size_t)sl * K * QP + l0);
+        if (c1 >= 0) {                              // empty intervals are skipped (zero local matrix in phase 2a)
+            if (!A.opvals && A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
+            const int sl = sl1, l0 = 2 * lp1;
+            double2 *tr2 = reinterpret_cast<double2 *>(TR + sl * TS + l0);
             double N0[K], N1[K];
             asm_bspline_pair<K>(T, sl, x0, x1, A.db, N0, N1);
 #pragma unroll
-            for (int a = 0; a < K; ++a) tr2[a * (QP / 2)] = make_double2(N0[a], has1 ? N1[a] : 0.0);
+            for (int a = 0; a < K; ++a) tr2[((a & 1) * HALF + (a >> 1) * QP) / 2] = make_double2(N0[a], has1 ? N1[a] : 0.0);
             *reinterpret_cast<double2 *>(WL + (size_t)sl * QP + l0) = make_double2((sgn * w0) * o0, has1 ? (sgn * w1) * o1 : 0.0);
             if (A.two_tab) {
-                double2 *tl2 = reinterpret_cast<double2 *>(TL + (size_t)sl * K * QP + l0);
+                double2 *tl2 = reinterpret_cast<double2 *>(TL + sl * TS + l0);
                 if (mlL == mlR) {                   // same knot window, other derivative order
                     asm_bspline_pair<K>(T, sl, x0, x1, A.da, N0, N1);
                 } else {                            // windows differ by the clamping at the left end
@@ -243,7 +313,7 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
                     cb_bspline_all<K>(tw, x1, A.da, N1);
                 }
 #pragma unroll
-                for (int a = 0; a < K; ++a) tl2[a * (QP / 2)] = make_double2(N0[a], has1 ? N1[a] : 0.0);
+                for (int a = 0; a < K; ++a) tl2[((a & 1) * HALF + (a >> 1) * QP) / 2] = make_double2(N0[a], has1 ? N1[a] : 0.0);
             }
         }
         __syncthreads();
@@ -251,16 +321,16 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
         for (int e = threadIdx.x; e < ns * KH; e += ASM_THREADS) {
             const int sl = e / KH, ap = e - sl * KH;
             const int a0 = 2 * ap, a1 = a0 + 1;     // rows a0, a0 + 1: one 16-byte store per column of the local matrix
-            const bool has1 = a1 < K;
-            double2 *m2 = reinterpret_cast<double2 *>(MS + (size_t)sl * K * KP2 + a0);
+            const bool two = a1 < K;
+            double2 *m2 = reinterpret_cast<double2 *>(MS + sl * MSP + a0);
             if (sOrd[sl] < 0) {
 #pragma unroll
                 for (int b = 0; b < K; ++b) m2[b * (KP2 / 2)] = make_double2(0.0, 0.0);
                 continue;
             }
             const double2 *wl2 = reinterpret_cast<const double2 *>(WL + (size_t)sl * QP);
-            const double2 *tl0 = reinterpret_cast<const double2 *>(TL + ((size_t)sl * K + a0) * QP);
-            const double2 *tl1 = reinterpret_cast<const double2 *>(TL + ((size_t)sl * K + (has1 ? a1 : a0)) * QP);
+            const double2 *tl0 = reinterpret_cast<const double2 *>(TL + sl * TS + ap * QP);          // row 2 ap
+            const double2 *tl1 = reinterpret_cast<const double2 *>(TL + (two ? HALF : 0) + sl * TS + ap * QP);   // row 2 ap + 1
             double2 lw0[QH], lw1[QH];
 #pragma unroll
             for (int h = 0; h < QH; ++h) {
@@ -268,57 +338,20 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
                 lw0[h] = make_double2(t0.x * w2.x, t0.y * w2.y);
                 lw1[h] = make_double2(t1.x * w2.x, t1.y * w2.y);
             }
-            const double2 *tr2 = reinterpret_cast<const double2 *>(TR + (size_t)sl * K * QP);
+            const double2 *tr2 = reinterpret_cast<const double2 *>(TR + sl * TS);
 #pragma unroll
             for (int b = 0; b < K; ++b) {
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int h = 0; h < QH; ++h) {
-                    const double2 r2 = tr2[b * (QP / 2) + h];
+                    const double2 r2 = tr2[((b & 1) * HALF + (b >> 1) * QP) / 2 + h];
                     s0 = fma(lw0[h].x, r2.x, s0); s1 = fma(lw1[h].x, r2.x, s1);
                     s0 = fma(lw0[h].y, r2.y, s0); s1 = fma(lw1[h].y, r2.y, s1);
                 }
-                m2[b * (KP2 / 2)] = make_double2(s0, has1 ? s1 : 0.0);
+                m2[b * (KP2 / 2)] = make_double2(s0, two ? s1 : 0.0);
             }
         }
         __syncthreads();
-        // ---- phase 2b: gather into the band -------------------------------------
-        // one thread per column: column b of the local matrix of each of its K intervals is a run
-        // of K consecutive band entries; the W = 2K-1 sums stay in registers
-        for (int jj = threadIdx.x; jj < (int)(j1 - j0); jj += ASM_THREADS) {
-            const i64 j = j0 + jj, fj = A.colR0 + 1 + j;
-            double acc[2 * K - 1];
-#pragma unroll
-            for (int t = 0; t < 2 * K - 1; ++t) acc[t] = 0.0;
-            // interval r of the column: s = fj - mlR + r, column b = K-1-r of its local matrix; its row a is
-            // function fi = s + mlL - K + 1 + a, so acc[t], t = a + r, is row fi = fj - mlR + mlL - K + 1 + t
-#pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const i64 s = fj - mlR + r;
-                if (s < sA || s > sB) continue;
-                const double2 *m2 = reinterpret_cast<const double2 *>(MS + ((size_t)(s - sA) * K + (K - 1 - r)) * KP2);
-#pragma unroll
-                for (int h = 0; h < KH; ++h) {
-                    const double2 v = m2[h];
-                    acc[2 * h + r] += v.x;
-                    if (2 * h + 1 < K) acc[2 * h + 1 + r] += v.y;
-                }
-            }
-            const i64 i_first = (fj - mlR + mlL - K + 1) - (A.rowL0 + 1);   // restricted row index of acc[0]
-            double *bc = A.band + (i64)W * (j - A.col_lo);
-            // band slot d holds row i = j - u + d
-            const i64 t_of_d0 = (j - A.u) - i_first;                 // acc index of band slot 0
-#pragma unroll
-            for (int t = 0; t < 2 * K - 1; ++t) {
-                const i64 d = t - t_of_d0, i = i_first + t;
-                if (d >= 0 && d < W && i >= 0 && i < A.mm && j < A.nn) bc[d] = acc[t];
-            }
-            // band slots not covered by the 2K-1 rows (or outside the matrix) are zero
-            for (int d = 0; d < W; ++d) {
-                const i64 t = d + t_of_d0, i = j - A.u + d;
-                if (t < 0 || t >= 2 * K - 1 || i < 0 || i >= A.mm || j >= A.nn) bc[d] = 0.0;
-            }
-        }
     }
 }
 
@@ -629,8 +662,9 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     if (L->k == R->k && K >= 2 && K <= CB_KMAX && (A.q + 1) / 2 == QH) {
         const int QP = (QH & 1) ? 2 * QH : 2 * QH + 2, KP2 = (K + 1) / 2 * 2;
         A.two_tab = (a != b || L->ml != R->ml) ? 1 : 0;
-        const size_t per_iv = sizeof(double) * ((size_t)K * QP * (A.two_tab ? 2 : 1) + QP + K * KP2 + 2 * (K + 1)) + sizeof(int);
-        const size_t fixed = sizeof(double) * 2 * (K + 1) * (2 * K + 2) + 16;
+        const int KH = (K + 1) / 2, U0 = K * KP2 / 2, MSP = 2 * (U0 + ((KH - U0) % 8 + 8) % 8);   // AsmMs<K>::MSP
+        const size_t per_iv = sizeof(double) * ((size_t)2 * KH * QP * (A.two_tab ? 2 : 1) + QP + MSP + 2 * (K + 1)) + sizeof(int);
+        const size_t fixed = sizeof(double) * (2 * (K + 1) * (2 * K + 2) + 8) + 16;
         // one round of 256 (interval, node pair) work items per tile; two CTAs per SM when that fits
         int ns = ASM_THREADS / QH;
         while (ns > 2 * K && (size_t)ns * per_iv + fixed > 112 * 1024) --ns;
