@@ -323,50 +323,64 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
 // ---------------------------------------------------------------------------
 // K8: FE-DVR element-block operator, uniform order O (compile time).
 //
-// Persistent CTAs, NS-stage shared-memory ring.  A tile is ET = NG*EG elements x 32 vectors; tile
-// rows (local r <-> global node gbase + r): elements eA..eA+ET-1 occupy rows 0..ET*(O-1); the halo
-// element eA+ET (needed for the last bridge row) adds O-1 more rows.  Each iteration issues the
-// copies of the tile NS-1 ahead, waits for the current one, computes it in place and streams the
-// result out.  In the compute phase thread = (vector lane, element group): it owns, for each of its
-// elements, local rows 1..O-1 (the bridge row at the end is shared with the next element, whose
-// first matrix row it adds); global row 0 is owned by the very first element.  Lanes run over
-// vectors, so block entries are warp-uniform (broadcast) 16-byte shared-memory loads and the x
-// values are conflict-free (odd pitch) column reads.
+// Persistent CTAs of NG warps with an NS-stage shared-memory ring of x tiles.  A tile is ET = NG - 1
+// elements x 32 vectors; tile rows (local r <-> global node eA*(O-1) + r): elements eA..eA+ET-1 occupy
+// rows 0..ET*(O-1), the halo element eA+ET — needed for the last bridge row — adds O-1 more.  Warp g
+// owns element eA + g (the last warp: row 0 of the halo element).  Per tile: the warp fetches its
+// O x O block straight from global memory (L2-resident, 8 MB at C2) into FP64 tensor-core A
+// fragments — the fetch is in flight together with the cp.async copies of the x rows — then multiplies
+// in place (DMMA 8x8x4: block fragments x four 8-vector tiles); the bridge rows shared by neighbouring
+// elements are summed from two side buffers and the tile is streamed out by a coalesced mover.
+// Lanes of the B operand run over vectors, so x reads are conflict-free (odd pitch) column reads.
 // ---------------------------------------------------------------------------
 constexpr int FE_TV = 32;                           // vectors per tile (one warp wide)
+constexpr int FE_BRP = FE_TV + 1;                   // pitch of the bridge buffers
 // Measured on B200 (C2: order 10, 1e4 elements, 1024 vectors; device time of one apply):
-//   DFMA compute, EG x NG x NS = 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 1x4x3: 584 | 1x8x6: 718
-//   DMMA compute, (elements per warp) x (warps) = 1x16: 404 us | 2x8: 420 | 1x12: 423 | 3x8: 478 |
-//                 4x4: 495 | 2x16: 612 | 4x8: 680;  movers only (no compute), 16-element tile: 341 us
-// More stages cost resident warps and the kernel is bound by warp-level latency in its phases, not by
-// bytes in flight (a bare cp.async tile stream reaches 5.2 TB/s, scripts/micro/stream.cu), so the
-// default is one stage, a 16-element tile and 16 warps per CTA (3 CTAs per SM).
-#ifndef FEDVR_EG10
-#define FEDVR_EG10 1
-#endif
+//   DFMA compute, blocks staged in shared memory per tile, (elements/thread) x warps x stages:
+//                 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 1x4x3: 584 | 1x8x6: 718
+//   DMMA compute, blocks staged per tile, (elements per warp) x (warps) = 1x16: 386-404 us | 2x8: 420 |
+//                 1x12: 423 | 3x8: 478 | 4x4: 495 | 2x16: 612;  movers only (no compute): 341 us
+//   DMMA compute, block fragments from global per tile, 15 elements + halo warp: 385 us (movers only: 289 us);
+//                 fragments kept for 2 / 4 / 8 vector tiles of the same elements: 398 / 432 / 483 us (the CTAs
+//                 running at one time then touch 2-8x as many columns of X and Y); half of the DMMAs
+//                 removed: 379 us (not FP64-bound); accumulator fragments stored straight to global
+//                 (64-byte pieces) instead of through the tile: 476 us; DMMA chains of 2 / 4 vector tiles interleaved
+//                 (a dependent DMMA has ~180 cycles of latency): 417 / 445-525 us (registers);
+//                 x-tile pitch odd -> even (any of 2, 4, 6, 12 mod 16): 386 -> 368 us.
 #ifndef FEDVR_NG
 #define FEDVR_NG 16
 #endif
+#ifndef FE_PITCH_MOD
+#define FE_PITCH_MOD 12
+#endif
+// Pitch of the x tile: = FE_PITCH_MOD (mod 16) doubles.  The B-fragment reads (lane (gq, tq) reads column gq, row 4ks + tq)
+// are bank-conflict free for 12 (mod 16); the movers run along the rows and do not care.
+__host__ __device__ constexpr int fe_pitch(int rows) { return FE_PITCH_MOD < 0 ? (rows | 1) : rows + ((FE_PITCH_MOD - rows) % 16 + 16) % 16; }
 #ifndef FEDVR_NS
 #define FEDVR_NS 1
 #endif
+#ifndef FEDVR_MINB
+#define FEDVR_MINB 3
+#endif
+#ifndef FE_NTI
+#define FE_NTI 1                                    // vector tiles (of 8) whose DMMA chains are interleaved
+#endif
 
-template <int O, int EG, int NG, int NS>   // EG elements per thread, NG element groups (warps), NS pipeline stages
-__global__ void __launch_bounds__(32 * NG)
+template <int O, int NG, int NS>
+__global__ void __launch_bounds__(32 * NG, (NG <= 8 ? 4 : NG <= 16 ? FEDVR_MINB : 1))
 fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
                    const double *__restrict__ X, i64 ldx, i64 nvec,
                    double alpha, double beta, double *__restrict__ Y, i64 ldy) {
     constexpr int THREADS = 32 * NG;
-    constexpr int ET = NG * EG;                     // elements per tile
+    constexpr int ET = NG - 1;                      // elements per tile
     constexpr int ROWS = (ET + 1) * (O - 1) + 1;    // incl. halo element
-    constexpr int PITCH = ROWS | 1;
-    constexpr int OP = O + (O & 1);                 // padded column height of a block in shared memory (even)
-    constexpr int BS_SIZE = (ET + 1) * O * OP;      // [(ET+1)][O][OP] column-major blocks, 16-byte aligned columns
-    constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);   // blocks + x tile [32][PITCH]
+    constexpr int PITCH = fe_pitch(ROWS);
+    constexpr int STAGE = (FE_TV * PITCH + 1) / 2 * 2;
+    constexpr int MT = (O + 7) / 8, KS = (O + 3) / 4;
     extern __shared__ __align__(16) double sm[];
-    double *br0 = sm + NS * STAGE;                  // [(ET+1)][32] first-row products (bridge contributions)
-    double *br9 = br0 + (ET + 1) * FE_TV;           // [ET][32]     last-row products
-    const int g = threadIdx.x >> 5;
+    double *br0 = sm + NS * STAGE;                  // [(ET+1)][33] first-row products (bridge contributions)
+    double *br9 = br0 + (ET + 1) * FE_BRP;          // [ET][33]     last-row products
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
     const i64 net = (nel + ET - 1) / ET;
     const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
     const i64 ntiles = net * nvt;
@@ -381,20 +395,11 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
     };
     auto issue = [&](i64 tile, int st) {            // always commits one cp.async group
         if (tile < ntiles) {
-            double *bs_ = sm + st * STAGE, *xs_ = bs_ + BS_SIZE;
+            double *xs_ = sm + st * STAGE;
             i64 eA, v0, x0row; bool interior;
             coords(tile, eA, v0, x0row, interior);
             if (interior) load_tile_async<ROWS, FE_TV, NG>(xs_, PITCH, X, ldx, x0row, v0);
             else load_tile<THREADS>(xs_, PITCH, X, ldx, nrows, x0row, ROWS, v0, FE_TV, nvec);
-            if (OP == O && interior) {              // same layout as in global memory: straight copy
-                const double *bsrc = blocks + eA * (O * O);
-                for (int e = threadIdx.x; e < (ET + 1) * O * O; e += THREADS) cp_async8(bs_ + e, bsrc + e);
-            } else {
-                for (int e = threadIdx.x; e < (ET + 1) * O * O; e += THREADS) {
-                    const int el = e / (O * O), rem = e - el * (O * O), mp = rem / O, mm = rem - mp * O;
-                    bs_[(el * O + mp) * OP + mm] = (eA + el < nel) ? __ldg(blocks + (eA + el) * (O * O) + rem) : 0.0;
-                }
-            }
         }
         cp_async_commit();
     };
@@ -407,61 +412,64 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
             int st = stage + NS - 1; if (st >= NS) st -= NS;
             issue(tile + (i64)(NS - 1) * gridDim.x, st);
         }
-        cp_async_wait<NS - 1>();                    // this tile's group has landed
-        __syncthreads();
         i64 eA, v0, x0row; bool interior;
         coords(tile, eA, v0, x0row, interior);
-        double *bs = sm + stage * STAGE, *xs = bs + BS_SIZE;
+        // ---- block fragments: a = B_e[mm = gq + 8 mt][mp = 4 ks + tq] (last warp: only the first 8 rows, of which
+        // row 0 is used).  Operands outside the block are zero rather than multiplied by zero, so Inf/NaN cannot leak.
+        double af[MT][KS];
+        {
+            const double *b = blocks + (eA + g) * (O * O);
+            const bool have = eA + g < nel;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int mm = gq + 8 * mt, mp = 4 * ks + tq;
+                    af[mt][ks] = (have && mm < O && mp < O && (g < ET || mt == 0)) ? __ldg(b + mp * O + mm) : 0.0;
+                }
+        }
+        cp_async_wait<NS - 1>();                    // this tile's group has landed
+        __syncthreads();
+        double *xs = sm + stage * STAGE;
 #ifndef FEDVR_SKIP_COMPUTE
         // ---- compute: y_e = B_e x_e on the FP64 tensor cores --------------------------------
-        // A warp owns EG elements; for each it multiplies the O x O block (A operand: MT x KS
-        // fragments, loaded once) with the element's O rows of 32 vectors (B operand: four 8-vector
-        // tiles).  Rows 1..O-2 are written in place (no other warp reads them); rows 0 and O-1 are
-        // contributions to the bridge rows shared with the neighbouring elements and go to side
-        // buffers that are summed after the barrier.  Operands outside the block are zeroed rather
-        // than multiplied by zero, so Inf/NaN in a neighbouring element cannot leak.
-        {
-            constexpr int MT = (O + 7) / 8, KS = (O + 3) / 4;
-            const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-            for (int job = g; job <= ET; job += NG) {           // job ET = halo element: only its row 0 is needed
-                const int eL = job;
-                const double *b = bs + eL * O * OP;
-                double af[MT][KS];
+        // Rows 1..O-2 are written in place (no other warp reads them); rows 0 and O-1 are
+        // contributions to the bridge rows shared with the neighbouring elements and go to the side
+        // buffers that are summed after the barrier.
+        // A dependent DMMA has a latency of ~180 cycles on B200 (scripts/micro/dmma_lat.cu) against 8 for a
+        // DFMA, so the k-steps of FE_NTI vector tiles are interleaved: FE_NTI * MT independent accumulator
+        // chains are in flight per warp.
+#pragma unroll
+        for (int np = 0; np < FE_TV / 8; np += FE_NTI) {
+            double c[FE_NTI][MT][2];
+#pragma unroll
+            for (int i = 0; i < FE_NTI; ++i)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] = 0.0; c[i][mt][1] = 0.0; }
+            const double *xe = xs + (8 * np + gq) * PITCH + g * (O - 1) + tq;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double bf[FE_NTI];
+#pragma unroll
+                for (int i = 0; i < FE_NTI; ++i) bf[i] = (4 * ks + tq < O) ? xe[i * 8 * PITCH + 4 * ks] : 0.0;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const int mm = gq + 8 * mt, mp = 4 * ks + tq;
-                        af[mt][ks] = (mm < O && mp < O) ? b[mp * OP + mm] : 0.0;
-                    }
-                const int mtn = eL == ET ? 1 : MT;
+                    for (int i = 0; i < FE_NTI; ++i)
+                        if (mt == 0 || g < ET) dmma884(c[i][mt][0], c[i][mt][1], af[mt][ks], bf[i]);
+            }
+            __syncwarp();                                        // all lanes have read these vector tiles' x rows
 #pragma unroll
-                for (int nt = 0; nt < FE_TV / 8; ++nt) {
-                    const double *xe = xs + (8 * nt + gq) * PITCH + eL * (O - 1);
-                    double bf[KS];
+            for (int i = 0; i < FE_NTI; ++i) {
+                const int v = 8 * (np + i) + 2 * tq;
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) bf[ks] = (4 * ks + tq < O) ? xe[4 * ks + tq] : 0.0;
-                    double c[MT][2];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-                            if (mt < mtn) dmma884(c[mt][0], c[mt][1], af[mt][ks], bf[ks]);
-                    __syncwarp();                                // all lanes have read this vector tile's x rows
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const int mm = gq + 8 * mt;
-                        const int v = 8 * nt + 2 * tq;
-                        if (mt < mtn) {
-                            if (mm == 0) { br0[eL * FE_TV + v] = c[mt][0]; br0[eL * FE_TV + v + 1] = c[mt][1]; }
-                            else if (eL < ET && mm == O - 1) { br9[eL * FE_TV + v] = c[mt][0]; br9[eL * FE_TV + v + 1] = c[mt][1]; }
-                            else if (eL < ET && mm < O - 1) {
-                                xs[v * PITCH + eL * (O - 1) + mm] = c[mt][0];
-                                xs[(v + 1) * PITCH + eL * (O - 1) + mm] = c[mt][1];
-                            }
-                        }
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int mm = gq + 8 * mt;
+                    if (mm == 0) { br0[g * FE_BRP + v] = c[i][mt][0]; br0[g * FE_BRP + v + 1] = c[i][mt][1]; }
+                    else if (g < ET && mm == O - 1) { br9[g * FE_BRP + v] = c[i][mt][0]; br9[g * FE_BRP + v + 1] = c[i][mt][1]; }
+                    else if (g < ET && mm < O - 1) {
+                        xs[v * PITCH + g * (O - 1) + mm] = c[i][mt][0];
+                        xs[(v + 1) * PITCH + g * (O - 1) + mm] = c[i][mt][1];
                     }
                 }
             }
@@ -472,7 +480,7 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
         for (int i = threadIdx.x; i < (ET + 1) * FE_TV; i += THREADS) {
             const int eL = i / FE_TV, v = i - eL * FE_TV;
             if (eL == 0) { if (eA == 0) xs[v * PITCH] = br0[v]; }
-            else xs[v * PITCH + eL * (O - 1)] = br9[(eL - 1) * FE_TV + v] + br0[eL * FE_TV + v];
+            else xs[v * PITCH + eL * (O - 1)] = br9[(eL - 1) * FE_BRP + v] + br0[eL * FE_BRP + v];
         }
         __syncthreads();
         // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
@@ -559,24 +567,20 @@ static int check_apply_args(const char *who, i64 m, i64 n, const double *X, i64 
 template <int O>
 static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, const double *X, i64 ldx, i64 nvec,
                         double alpha, double beta, double *Y, i64 ldy, cudaStream_t st) {
-    constexpr int EG = (O <= 3) ? 4 : (O <= 5) ? 2 : (O <= 10) ? FEDVR_EG10 : 1;
-    constexpr int NG = (O <= 12) ? FEDVR_NG : 4;
+    constexpr int NG = (O <= 12) ? FEDVR_NG : 8;
     constexpr int NS = FEDVR_NS;
-    constexpr int ET = NG * EG;
+    constexpr int ET = NG - 1;
     constexpr int ROWS = (ET + 1) * (O - 1) + 1;
-    constexpr int PITCH = ROWS | 1;
-    constexpr int OP = O + (O & 1);
-    constexpr int BS_SIZE = (ET + 1) * O * OP;
-    constexpr int STAGE = BS_SIZE + FE_TV * PITCH + ((BS_SIZE + FE_TV * PITCH) & 1);
-    size_t smem = sizeof(double) * ((size_t)NS * STAGE + (size_t)(2 * ET + 1) * FE_TV);
-    static_assert(sizeof(double) * ((size_t)NS * STAGE + (size_t)(2 * ET + 1) * FE_TV) <= 227 * 1024, "pipeline does not fit in shared memory");
-    auto kern = fedvr_apply_kernel<O, EG, NG, NS>;
+    constexpr int PITCH = fe_pitch(ROWS);
+    constexpr size_t smem = sizeof(double) * ((size_t)NS * ((FE_TV * PITCH + 1) / 2 * 2) + (size_t)(2 * ET + 1) * FE_BRP);
+    static_assert(smem <= 227 * 1024, "tile ring does not fit in shared memory");
+    auto kern = fedvr_apply_kernel<O, NG, NS>;
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
+    const i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
     int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 2048 / (32 * NG)) per_sm = 2048 / (32 * NG);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? 4 : 1);   // pipelined: one persistent wave of CTAs
+    const i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? 4 : 1);   // pipelined: one persistent wave of CTAs
     int grid = (int)(tiles < cap ? tiles : cap);
     kern<<<grid, 32 * NG, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();

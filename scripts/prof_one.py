@@ -50,5 +50,10 @@ for _ in range(reps):
     fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-print(what, "ms", e0.elapsed_time(e1) / (20 if what == "asm3k" else 1), "(per launch)" if what == "asm3k" else "")
+NT = 1 if os.environ.get("PROF_SINGLE") else 10
+e0.record()
+for _ in range(NT):
+    fn()
+e1.record(); torch.cuda.synchronize()
+per = e0.elapsed_time(e1) / NT / (20 if what == "asm3k" else 1)
+print(what, "ms", per, "(mean of back-to-back calls)")
