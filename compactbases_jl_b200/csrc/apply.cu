@@ -249,6 +249,12 @@ constexpr int BT_NG = 8;                            // warps per CTA
 constexpr int BT_RB = 2;                            // 8-row blocks per warp
 constexpr int BT_THREADS = 32 * BT_NG;
 constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
+#ifndef BT_PITCH_MOD
+#define BT_PITCH_MOD 12
+#endif
+// x-tile pitch = BT_PITCH_MOD (mod 16): the B-fragment reads (lane (gq, tq) reads column gq, row 4ks + tq) are then
+// bank-conflict free; the movers run along the rows and do not care
+__host__ __device__ inline int bt_pitch(int rows) { return BT_PITCH_MOD < 0 ? (rows | 1) : rows + ((BT_PITCH_MOD - rows) % 16 + 16) % 16; }
 
 __global__ void __launch_bounds__(BT_THREADS)
 banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
@@ -258,7 +264,7 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
     const int W = l + u + 1;
     const int KS = (8 + W - 1 + 3) / 4;             // k-steps per 8-row block
     const int xrows = BT_ROWS + l + u;
-    const int pitch = (xrows + 4) | 1;              // + room for the k padding of the last block
+    const int pitch = bt_pitch(xrows + 4);              // + room for the k padding of the last block
     double *as = sm;                                // [BT_ROWS/8][KS][32] A fragments
     double *xs = sm + (BT_ROWS / 8) * KS * 32;      // [BT_VEC][pitch]; tile row r <-> matrix column i0 - l + r
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
@@ -642,14 +648,14 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     const int W = l + u + 1;
     const int KS = (8 + W - 1 + 3) / 4;
     const int xrows = BT_ROWS + l + u;
-    const int pitch = (xrows + 4) | 1;
+    const int pitch = bt_pitch(xrows + 4);
     size_t smem = sizeof(double) * ((size_t)BT_VEC * pitch + (size_t)(BT_ROWS / 8) * KS * 32);
     if (smem > 200 * 1024) { cb_set_error("cb_banded_apply: bandwidth %d too large for the shared-memory tile", W); return CB_ERR_UNSUPPORTED; }
     CB_CUDA(cudaFuncSetAttribute(banded_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS, nvt = (nvec + BT_VEC - 1) / BT_VEC;
     // vector tiles per work item: amortise the band-tile staging while keeping >= ~8 items per SM
     i64 vchunk = nrt * nvt / ((i64)CB_NUM_SMS * 8);
-    vchunk = vchunk < 1 ? 1 : (vchunk > 16 ? 16 : vchunk);
+    vchunk = vchunk < 1 ? 1 : (vchunk > 8 ? 8 : vchunk);          // 3..8 measured within 2% of each other, 1-2 slower
     const i64 items = nrt * ((nvt + vchunk - 1) / vchunk);
     int grid = (int)(items < (i64)CB_NUM_SMS * 24 ? items : (i64)CB_NUM_SMS * 24);
     banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, (int)vchunk, alpha, beta, Y, ldy);

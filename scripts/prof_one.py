@@ -34,6 +34,11 @@ elif what == "banded":
     S = B.T @ D.T @ D @ B
     X = torch.randn((65536, B.nf), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
     fn = lambda: cb.mul(Y, S, X)
+elif what == "banded3":    # C3 shape: k = 10 band, 200 009 rows, 256 vectors
+    B = cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 200000))
+    S = B.T @ D.T @ D @ B
+    X = torch.randn((256, B.nf), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    fn = lambda: cb.mul(Y, S, X)
 elif what == "density":
     B = cb.BSpline(cb.LinearKnotSet(8, 0, 500, 50000))
     P = 1024
