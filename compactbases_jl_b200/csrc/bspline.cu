@@ -86,9 +86,14 @@ bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, i
     const int n_tt = (int)kv.n_tt;
     const double *tt = kv.tt;
     if (SMEM_KNOTS) {
-        for (int i = threadIdx.x; i < n_tt; i += EVAL_THREADS) sknots[i] = kv.tt[i];
+        // K-1 copies of the end knots on either side: the knot window of any interval is then read without clamping
+        for (int i = threadIdx.x; i < n_tt + 2 * (K - 1); i += EVAL_THREADS) {
+            int j = i - (K - 1);
+            j = j < 0 ? 0 : (j > n_tt - 1 ? n_tt - 1 : j);
+            sknots[i] = kv.tt[j];
+        }
         __syncthreads();
-        tt = sknots;
+        tt = sknots + (K - 1);
     }
     const double first = kv.tt[0], last = kv.tt[n_tt - 1];
     const double scale = (double)(n_tt - 1) / (last - first);
@@ -117,10 +122,11 @@ bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, i
             }
             if (I > 0) {
                 double tw[2 * K];
+                const int jb = I - K - (kv.ml - 1);        // 0-based index into t.t of expanded knot I-K+1
 #pragma unroll
                 for (int s = 0; s < 2 * K; ++s) {
-                    int j = I - K + s - (kv.ml - 1);       // 0-based index into t.t of expanded knot I-K+1+s
-                    j = j < 0 ? 0 : (j > n_tt - 1 ? n_tt - 1 : j);
+                    int j = jb + s;
+                    if (!SMEM_KNOTS) j = j < 0 ? 0 : (j > n_tt - 1 ? n_tt - 1 : j);
                     tw[s] = tt[j];
                 }
                 cb_bspline_all<K, MT>(tw, xp, m, N);
@@ -357,7 +363,7 @@ int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
     cudaStream_t st = (cudaStream_t)stream;
     int vec_ok = ((uintptr_t)vals % 16) == 0;
     if (B->n_tt <= EVAL_SMEM_KNOTS) {
-        const size_t smem = sizeof(double) * (size_t)B->n_tt;
+        const size_t smem = sizeof(double) * ((size_t)B->n_tt + 2 * (size_t)(B->k - 1));   // + the clamped copies of the end knots
         int grid = cb_grid_for(nx, EVAL_THREADS, 6);   // persistent-ish: the knot copy is amortised over several blocks
         CB_DISPATCH_K(B->k, {
             auto kern = m == 0 ? bspline_eval_kernel<K, true, 0> : bspline_eval_kernel<K, true, -1>;

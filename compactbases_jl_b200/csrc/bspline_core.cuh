@@ -44,6 +44,9 @@ CB_HD void cb_knot_window(const double *__restrict__ tt, i64 n_tt, int ml,
 // N[r], r = 0..K-1: m-th derivative at x of function I-K+1+r (order K).
 // MT >= 0 fixes the derivative order at compile time (m is then ignored): the level loops lose
 // their run-time selects, which matters in the FP64-bound evaluation kernel.
+// The sweep works on the 2(K-1) distances  dh[r] = t_{I+1+r} - x  and  dl[i] = x - t_{I-K+1+i}  (both >= 0 for x in
+// the interval): the support widths are their sums, dh[r] + dl[K-j+r] = t_{I+1+r} - t_{I+1+r-j}, so a level entry
+// costs one DADD instead of three.
 template <int K, int MT = -1>
 CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
                                                double (&N)[K]) {
@@ -52,6 +55,9 @@ CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
     for (int r = 0; r < K; ++r) N[r] = 0.0;
     if (m >= K) return;                            // k == 1 && m > 0 -> 0 (src/bsplines.jl:164)
     N[0] = 1.0;
+    double dh[K], dl[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { dh[r] = tw[K + r] - x; dl[r] = x - tw[r]; }
     const int jmax = K - 1 - m;                    // value recursion up to order K-m
 #pragma unroll
     for (int j = 1; j <= K - 1; ++j) {
@@ -59,10 +65,9 @@ CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
             double saved = 0.0;
 #pragma unroll
             for (int r = 0; r < j; ++r) {
-                double d = tw[K + r] - tw[K - j + r];
-                double term = N[r] * fast_rcp(d);
-                N[r] = fma(tw[K + r] - x, term, saved);
-                saved = (x - tw[K - j + r]) * term;
+                const double term = N[r] * fast_rcp(dh[r] + dl[K - j + r]);
+                N[r] = fma(dh[r], term, saved);
+                saved = dl[K - j + r] * term;
             }
             N[j] = saved;
         }
@@ -76,10 +81,7 @@ CB_HD void cb_bspline_all(const double (&tw)[2 * K], double x, int m_rt,
 #pragma unroll
             for (int r = 0; r <= o; ++r) {
                 double qr = 0.0;
-                if (r < o) {
-                    double d = tw[K + r] - tw[K - o + r];
-                    qr = N[r] * fast_rcp(d);
-                }
+                if (r < o) qr = N[r] * fast_rcp(dh[r] + dl[K - o + r]);
                 N[r] = (double)o * (qprev - qr);
                 qprev = qr;
             }
