@@ -27,6 +27,11 @@ struct cb_density_s {
     i64 *d_ivlist;       // [ni] expanded 1-based index of each non-empty interval (copy)
     double *d_fw;        // [ncols][k]: fw[j][0] = 1/L_jj, fw[j][p] = L_{j,j-p}/L_jj
     double *d_bw;        // [ncols][k]: bw[j][p] = L_{j+p,j}/L_jj (p >= 1)
+    // partitioned substitution (chunks of DS_CH rows), NULL when ncols < 2*DS_CH
+    i64 nchunk;
+    double *d_cfb;       // [ncols][2k-1]: bw[j][0..k-1], then the forward spikes SF[j][1..k-1]
+    double *d_sb;        // [ncols][k-1]:  backward spikes SB[j][1..k-1]
+    double *d_tf, *d_tb; // [nchunk][k-1][k-1]: incoming -> outgoing state of a chunk (forward / backward)
     int refine;
     int chol_status;     // 0 ok, else 1-based column where the factorisation broke down
 };
@@ -423,6 +428,277 @@ density_solve_kernel(const double *__restrict__ fwt, const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Partitioned banded substitution.
+//
+// The forward sweep  y_j = r_j/L_jj - sum_p (L_{j,j-p}/L_jj) y_{j-p}  is a linear recurrence of order k-1 along
+// the rows: one warp per 32 pairs walks all n rows one after the other (density_solve_kernel), which is ~50 cycles of
+// dependent FP64 latency per row and leaves the GPU empty for small pair batches (C5 tile: 50 007 rows x 1024 pairs
+// = 32 warps, 10.6 ms).  The rows are therefore cut into chunks of DS_CH; with s_c the k-1 unknowns just before chunk
+// c ("incoming state"),
+//     y_j = yloc_j + sum_i SF[j][i] s_c[i],     j in chunk c,
+// where yloc is the chunk's own sweep started from a zero state and the spikes SF (the response of the chunk to a unit
+// incoming state — a property of the factor only) are tabulated once in the plan.  So:
+//     F1  every (chunk, 32 pairs) in parallel: yloc in place, and the chunk's final state E_c
+//     F2  one thread per pair, chunk after chunk:  s_{c+1} = E_c + TF_c s_c      (TF_c = last k-1 rows of SF)
+//     FB  every (chunk, 32 pairs): rows in descending order, y_j = yloc_j + SF[j].s_c on the fly, fed straight into
+//         the chunk's local BACKWARD sweep; zloc in place, final state Eb_c
+//     B2  as F2, downwards
+//     B3  x_j = zloc_j + SB[j].sb_c  (no recurrence: one thread per entry)
+// The result is the same triangular solves (exact, no truncation of the decaying spikes); the work doubles to
+// 4(k-1) FMAs per entry and three passes over the batch, but every pass has n/DS_CH x P/32 independent warps.
+// ---------------------------------------------------------------------------
+constexpr int DS_CH = 256;                          // rows per chunk (multiple of 32); the last chunk takes the remainder
+
+__host__ __device__ inline i64 ds_chunk_begin(i64 c) { return c * DS_CH; }
+__host__ __device__ inline i64 ds_chunk_end(i64 c, i64 nchunk, i64 n) { return c == nchunk - 1 ? n : (c + 1) * DS_CH; }
+
+// Spikes and transfer matrices: one warp per chunk, lane i-1 <-> incoming state component i = 1..K-1.
+template <int K>
+__global__ void __launch_bounds__(32)
+density_spike_kernel(const double *__restrict__ fw, const double *__restrict__ bw, i64 n, i64 nchunk,
+                     double *__restrict__ cfb, double *__restrict__ sb, double *__restrict__ tf, double *__restrict__ tb) {
+    constexpr int CW = 2 * K - 1, S = K - 1;
+    const i64 c = blockIdx.x;
+    const int i = threadIdx.x + 1;
+    const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
+    // copy of the backward factor rows into the combined table
+    for (i64 e = a * K + threadIdx.x; e < b * K; e += 32) { const i64 j = e / K; cfb[j * CW + (e - j * K)] = bw[e]; }
+    if (i > S) return;
+    double w[K];                                    // w[p] = unknown p rows back (forward) / ahead (backward)
+#pragma unroll
+    for (int p = 1; p < K; ++p) w[p] = p == i ? 1.0 : 0.0;
+    for (i64 j = a; j < b; ++j) {
+        double y = 0.0;
+#pragma unroll
+        for (int p = 1; p < K; ++p) y = fma(-fw[j * K + p], w[p], y);
+#pragma unroll
+        for (int p = K - 1; p >= 2; --p) w[p] = w[p - 1];
+        if (K > 1) w[1] = y;
+        cfb[j * CW + K + (i - 1)] = y;
+    }
+#pragma unroll
+    for (int p = 1; p < K; ++p) tf[(c * S + (p - 1)) * S + (i - 1)] = w[p];       // outgoing component p <- incoming i
+#pragma unroll
+    for (int p = 1; p < K; ++p) w[p] = p == i ? 1.0 : 0.0;
+    for (i64 j = b - 1; j >= a; --j) {
+        double z = 0.0;
+#pragma unroll
+        for (int p = 1; p < K; ++p) z = fma(-bw[j * K + p], w[p], z);
+#pragma unroll
+        for (int p = K - 1; p >= 2; --p) w[p] = w[p - 1];
+        if (K > 1) w[1] = z;
+        sb[j * S + (i - 1)] = z;
+    }
+#pragma unroll
+    for (int p = 1; p < K; ++p) tb[(c * S + (p - 1)) * S + (i - 1)] = w[p];
+}
+
+// Shared-memory ring of one warp: tiles of 32 rows x 32 pairs (transposed through shared memory so that global
+// traffic runs along the contiguous row dimension) and the CW coefficients of each row.
+template <int CW, int NB>
+struct DsRing {
+    double sx[NB][32][33];
+    double sc[NB][32 * CW];
+};
+
+template <int CW, int NB>
+__device__ __forceinline__ void ds_issue(DsRing<CW, NB> &R, int b, i64 row0, i64 row_end, const double *__restrict__ X, i64 ldx,
+                                         i64 p0, i64 P, const double *__restrict__ ct) {
+    const int lane = threadIdx.x;
+    const i64 j = row0 + lane;
+    if (j < row_end) {
+#pragma unroll 8
+        for (int pp = 0; pp < 32; ++pp)
+            if (p0 + pp < P) ds_cp8(&R.sx[b][pp][lane], X + j + ldx * (p0 + pp));
+    }
+    const i64 c0 = row0 * CW, cend = row_end * CW;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+        const i64 e = c0 + lane + 32 * i;
+        if (e < cend) ds_cp8(&R.sc[b][lane + 32 * i], ct + e);
+    }
+}
+
+template <int CW, int NB>
+__device__ __forceinline__ void ds_store(const DsRing<CW, NB> &R, int b, i64 row0, i64 row_end, double *__restrict__ X, i64 ldx,
+                                         i64 p0, i64 P) {
+    const int lane = threadIdx.x;
+    const i64 j = row0 + lane;
+    if (j < row_end) {
+#pragma unroll 8
+        for (int pp = 0; pp < 32; ++pp)
+            if (p0 + pp < P) X[j + ldx * (p0 + pp)] = R.sx[b][pp][lane];
+    }
+}
+
+// F1: local forward sweep of every chunk.  grid = (pair tiles, chunks), one warp per CTA.
+template <int K>
+__global__ void __launch_bounds__(32)
+density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+                         double *__restrict__ E) {
+    constexpr int NB = 2, S = K - 1;
+    __shared__ DsRing<K, NB> R;
+    const int lane = threadIdx.x;
+    const i64 p0 = (i64)blockIdx.x * 32, c = blockIdx.y;
+    const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
+    const i64 ntile = (b - a + 31) / 32;
+    double yw[K];
+#pragma unroll
+    for (int p = 0; p < K; ++p) yw[p] = 0.0;
+    ds_issue(R, 0, a, b, X, ldx, p0, P, fwt);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (i64 t = 0; t < ntile; ++t) {
+        const int bb = (int)(t & 1);
+        if (t + 1 < ntile) ds_issue(R, bb ^ 1, a + 32 * (t + 1), b, X, ldx, p0, P, fwt);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const i64 row0 = a + 32 * t;
+        const int rows = b - row0 < 32 ? (int)(b - row0) : 32;
+        double xr[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) xr[r] = R.sx[bb][lane][r];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (r < rows) {
+                const double *cf = &R.sc[bb][r * K];
+                double acc = xr[r] * cf[0], acc2 = 0.0;
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) {
+                    if (p & 1) acc2 = fma(-cf[p], yw[p], acc2); else acc = fma(-cf[p], yw[p], acc);
+                }
+                acc += acc2;
+                if (K > 1) acc = fma(-cf[1], yw[1], acc);
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+                if (K > 1) yw[1] = acc;
+                xr[r] = acc;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) R.sx[bb][lane][r] = xr[r];
+        __syncwarp();
+        ds_store(R, bb, row0, b, X, ldx, p0, P);
+        __syncwarp();
+    }
+    if (p0 + lane < P) {
+#pragma unroll
+        for (int p = 1; p < K; ++p) E[(c * S + (p - 1)) * P + p0 + lane] = yw[p];
+    }
+}
+
+// F2 / B2: chunk-to-chunk propagation of the state, one thread per pair.  dir = +1: S_0 = 0, S_{c+1} = E_c + T_c S_c;
+// dir = -1: S_{M-1} = 0, S_{c-1} = E_c + T_c S_c.
+template <int K>
+__global__ void density_state_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const double *__restrict__ E,
+                                     double *__restrict__ St, int dir) {
+    constexpr int S = K - 1;
+    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double s[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) s[i] = 0.0;
+    i64 c = dir > 0 ? 0 : nchunk - 1;
+#pragma unroll
+    for (int i = 0; i < S; ++i) St[(c * S + i) * P + p] = 0.0;
+    for (i64 step = 0; step + 1 < nchunk; ++step, c += dir) {
+        double sn[K];
+#pragma unroll
+        for (int o = 0; o < S; ++o) {
+            double v = E[(c * S + o) * P + p];
+#pragma unroll
+            for (int i = 0; i < S; ++i) v = fma(T[(c * S + o) * S + i], s[i], v);
+            sn[o] = v;
+        }
+#pragma unroll
+        for (int o = 0; o < S; ++o) { s[o] = sn[o]; St[((c + dir) * S + o) * P + p] = sn[o]; }
+    }
+}
+
+// FB: spike correction of the forward sweep fused with the local backward sweep of every chunk.
+template <int K>
+__global__ void __launch_bounds__(32)
+density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+                         const double *__restrict__ St, double *__restrict__ E) {
+    constexpr int NB = 2, S = K - 1, CW = 2 * K - 1;
+    __shared__ DsRing<CW, NB> R;
+    const int lane = threadIdx.x;
+    const i64 p0 = (i64)blockIdx.x * 32, c = blockIdx.y;
+    const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
+    const i64 ntile = (b - a + 31) / 32;
+    double sin[K], zw[K];
+#pragma unroll
+    for (int p = 0; p < K; ++p) { zw[p] = 0.0; sin[p] = 0.0; }
+    if (p0 + lane < P) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) sin[i] = St[(c * S + i) * P + p0 + lane];
+    }
+    ds_issue(R, 0, a + 32 * (ntile - 1), b, X, ldx, p0, P, cfb);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (i64 t = ntile - 1, it = 0; t >= 0; --t, ++it) {
+        const int bb = (int)(it & 1);
+        if (t > 0) ds_issue(R, bb ^ 1, a + 32 * (t - 1), b, X, ldx, p0, P, cfb);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const i64 row0 = a + 32 * t;
+        const int rows = b - row0 < 32 ? (int)(b - row0) : 32;
+        double xr[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) xr[r] = R.sx[bb][lane][r];
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+            if (r < rows) {
+                const double *cf = &R.sc[bb][r * CW];
+                double y = xr[r], y2 = 0.0;                           // y_j = yloc_j + SF[j] . s_c
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    if (i & 1) y2 = fma(cf[K + i], sin[i], y2); else y = fma(cf[K + i], sin[i], y);
+                }
+                y += y2;
+                double acc = y * cf[0], acc2 = 0.0;
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) {
+                    if (p & 1) acc2 = fma(-cf[p], zw[p], acc2); else acc = fma(-cf[p], zw[p], acc);
+                }
+                acc += acc2;
+                if (K > 1) acc = fma(-cf[1], zw[1], acc);
+#pragma unroll
+                for (int p = K - 1; p >= 2; --p) zw[p] = zw[p - 1];
+                if (K > 1) zw[1] = acc;
+                xr[r] = acc;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) R.sx[bb][lane][r] = xr[r];
+        __syncwarp();
+        ds_store(R, bb, row0, b, X, ldx, p0, P);
+        __syncwarp();
+    }
+    if (p0 + lane < P) {
+#pragma unroll
+        for (int p = 1; p < K; ++p) E[(c * S + (p - 1)) * P + p0 + lane] = zw[p];
+    }
+}
+
+// B3: x_j = zloc_j + SB[j] . sb_c (+ addto), one thread per entry, lanes along the rows.
+template <int K>
+__global__ void density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+                                       const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
+    constexpr int S = K - 1;
+    for (i64 p = blockIdx.y; p < P; p += gridDim.y) {
+        for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
+            i64 c = j / DS_CH; if (c > nchunk - 1) c = nchunk - 1;
+            double v = X[j + ldx * p];
+#pragma unroll
+            for (int i = 0; i < S; ++i) v = fma(sb[j * S + i], St[(c * S + i) * P + p], v);
+            if (addto) v += addto[j + lda * p];
+            X[j + ldx * p] = v;
+        }
+    }
+}
+
 // Orthogonal branches (src/densities.jl:166-185): rho = c .* (conj(f) .* g).
 __global__ void density_orthogonal_kernel(const double *__restrict__ c, i64 n,
                                           const double *__restrict__ f, i64 ldf, i64 Pf,
@@ -500,8 +776,45 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
 
 template <int K>
 static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const double *addto, i64 lda, cudaStream_t st) {
-    i64 blocks = (P + 31) / 32;
-    density_solve_kernel<K><<<(int)blocks, 32, 0, st>>>(D->d_fw, D->d_bw, D->ncols, X, ldx, P, addto, lda);
+    const i64 n = D->ncols, ptiles = (P + 31) / 32;
+    if (D->d_cfb == nullptr || K == 1) {            // short problems: one warp per 32 pairs walks all rows
+        density_solve_kernel<K><<<(int)ptiles, 32, 0, st>>>(D->d_fw, D->d_bw, n, X, ldx, P, addto, lda);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
+    const i64 M = D->nchunk;
+    constexpr int S = K > 1 ? K - 1 : 1;
+    double *ws = nullptr;                           // E and the propagated states, [M][K-1][P] each
+    CB_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * M * S * P, st));
+    double *E = ws, *St = ws + M * S * P;
+    for (i64 pt0 = 0; pt0 < ptiles; pt0 += 65535 * 32) {   // (grid.x limit is far away; grid.y = chunks <= 65535 checked at plan time)
+        (void)pt0;
+    }
+    dim3 grid((unsigned)ptiles, (unsigned)M);
+    density_fwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_fw, n, M, X, ldx, P, E);
+    density_state_kernel<K><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(D->d_tf, M, P, E, St, +1);
+    density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_state_kernel<K><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(D->d_tb, M, P, E, St, -1);
+    dim3 gfix((unsigned)cb_grid_for(n, 256, 8), (unsigned)(P < 8192 ? P : 8192));
+    density_bwd_fix_kernel<K><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ws, st);
+    if (e != cudaSuccess) { cb_set_error("cb_density_apply: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return CB_OK;
+}
+
+// Spike tables of the partitioned substitution (after the Cholesky factor is known).
+template <int K>
+static int launch_spikes(cb_density_s *D) {
+    const i64 n = D->ncols;
+    D->nchunk = n / DS_CH;
+    if (D->nchunk < 2 || D->nchunk > 65535 || K == 1) { D->nchunk = 0; return CB_OK; }
+    constexpr int S = K > 1 ? K - 1 : 1;
+    CB_CUDA(cudaMalloc(&D->d_cfb, sizeof(double) * n * (2 * K - 1)));
+    CB_CUDA(cudaMalloc(&D->d_sb, sizeof(double) * n * S));
+    CB_CUDA(cudaMalloc(&D->d_tf, sizeof(double) * D->nchunk * S * S));
+    CB_CUDA(cudaMalloc(&D->d_tb, sizeof(double) * D->nchunk * S * S));
+    density_spike_kernel<K><<<(unsigned)D->nchunk, 32>>>(D->d_fw, D->d_bw, n, D->nchunk, D->d_cfb, D->d_sb, D->d_tf, D->d_tb);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
@@ -517,6 +830,7 @@ int cb_density_destroy(cb_density *D) {
     if (!D) return CB_OK;
     cudaFree(D->d_table); cudaFree(D->d_wv); cudaFree(D->d_ord); cudaFree(D->d_ivlist);
     cudaFree(D->d_fw); cudaFree(D->d_bw);
+    cudaFree(D->d_cfb); cudaFree(D->d_sb); cudaFree(D->d_tf); cudaFree(D->d_tb);
     delete D;
     return CB_OK;
 }
@@ -530,6 +844,7 @@ int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const do
     D->k = B->k; D->q = B->q; D->ml = B->ml; D->n_tt = B->n_tt; D->nf = B->nf; D->ni = B->ni;
     D->col0 = col0; D->ncols = ncols; D->device = B->device; D->refine = 0; D->chol_status = 0;
     D->d_table = D->d_wv = D->d_fw = D->d_bw = nullptr; D->d_ord = nullptr; D->d_ivlist = nullptr;
+    D->d_cfb = D->d_sb = D->d_tf = D->d_tb = nullptr; D->nchunk = 0;
     const i64 nn = B->ni * B->q;
     double *d_g = nullptr; int *d_status = nullptr;
     int rc = CB_OK;
@@ -555,6 +870,11 @@ int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const do
         rc = launch_cholesky(B->k, d_g, ncols, D->d_fw, D->d_bw, d_status);
         step(cudaGetLastError());
         step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (e == cudaSuccess && rc == CB_OK && D->chol_status == 0) {
+        const int kk = B->k;
+        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D)); return CB_OK; }();
+        step(cudaDeviceSynchronize());
     }
     cudaFree(d_g); cudaFree(d_status);
     if (e != cudaSuccess) { cb_set_error("cb_density_bspline_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }

@@ -23,6 +23,9 @@ CASES = [
     ("k3_repeated", lambda cb: cb.ArbitraryKnotSet(3, [0.0, 1, 1, 3, 4, 6], 1, 3)),
     ("k5_exp", lambda cb: cb.ExpKnotSet(5, -2.0, 1.0, 30)),
     ("k2", lambda cb: cb.LinearKnotSet(2, 0, 1, 9)),
+    # more than 2*256 functions: the partitioned (chunked, spike-corrected) substitution
+    ("k5_lin700", lambda cb: cb.LinearKnotSet(5, 0, 10, 700)),
+    ("k8_exp600", lambda cb: cb.ExpKnotSet(8, -2.0, 1.0, 600)),
 ]
 
 
