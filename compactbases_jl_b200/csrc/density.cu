@@ -589,30 +589,58 @@ density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, doub
 }
 
 // F2 / B2: chunk-to-chunk propagation of the state, one thread per pair.  dir = +1: S_0 = 0, S_{c+1} = E_c + T_c S_c;
-// dir = -1: S_{M-1} = 0, S_{c-1} = E_c + T_c S_c.
+// dir = -1: S_{M-1} = 0, S_{c-1} = E_c + T_c S_c.  The chain of nchunk-1 dependent (k-1)x(k-1) products is latency
+// bound, so nothing on it may wait for memory: the transfer matrices of DS_BATCH chunks are staged in shared memory
+// at a time and the next chunk's E is fetched while the current one is multiplied.
+constexpr int DS_STATE_THREADS = 32;
+
 template <int K>
-__global__ void density_state_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const double *__restrict__ E,
-                                     double *__restrict__ St, int dir) {
-    constexpr int S = K - 1;
-    const i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    double s[K];
+__global__ void __launch_bounds__(DS_STATE_THREADS)
+density_state_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const double *__restrict__ E,
+                     double *__restrict__ St, int dir) {
+    constexpr int S = K > 1 ? K - 1 : 1;
+    constexpr int BATCH = K <= 8 ? 16 : 8;          // chunks staged at a time (E and T together < 48 KB)
+    __shared__ double sT[BATCH * S * S];
+    __shared__ double sE[BATCH * S][DS_STATE_THREADS];
+    const i64 p = blockIdx.x * (i64)DS_STATE_THREADS + threadIdx.x;
+    const bool live = p < P;
+    double s[S];
 #pragma unroll
-    for (int i = 0; i < K; ++i) s[i] = 0.0;
-    i64 c = dir > 0 ? 0 : nchunk - 1;
+    for (int i = 0; i < S; ++i) s[i] = 0.0;
+    const i64 c0 = dir > 0 ? 0 : nchunk - 1, steps = nchunk - 1;
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < S; ++i) St[(c * S + i) * P + p] = 0.0;
-    for (i64 step = 0; step + 1 < nchunk; ++step, c += dir) {
-        double sn[K];
-#pragma unroll
-        for (int o = 0; o < S; ++o) {
-            double v = E[(c * S + o) * P + p];
-#pragma unroll
-            for (int i = 0; i < S; ++i) v = fma(T[(c * S + o) * S + i], s[i], v);
-            sn[o] = v;
+        for (int i = 0; i < S; ++i) St[(c0 * S + i) * P + p] = 0.0;
+    }
+    for (i64 base = 0; base < steps; base += BATCH) {
+        const int nb = steps - base < BATCH ? (int)(steps - base) : BATCH;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * S * S; e += DS_STATE_THREADS) {
+            const int bq = e / (S * S);
+            ds_cp8(&sT[e], T + (c0 + dir * (base + bq)) * (S * S) + (e - bq * S * S));
         }
+        if (live) {
+            for (int e = 0; e < nb * S; ++e) {
+                const int bq = e / S, o = e - bq * S;
+                ds_cp8(&sE[e][threadIdx.x], E + ((c0 + dir * (base + bq)) * S + o) * P + p);
+            }
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (!live) continue;
+        for (int bq = 0; bq < nb; ++bq) {
+            const i64 c = c0 + dir * (base + bq);
+            double sn[S];
 #pragma unroll
-        for (int o = 0; o < S; ++o) { s[o] = sn[o]; St[((c + dir) * S + o) * P + p] = sn[o]; }
+            for (int o = 0; o < S; ++o) {
+                double v = sE[bq * S + o][threadIdx.x];
+#pragma unroll
+                for (int i = 0; i < S; ++i) v = fma(sT[(bq * S + o) * S + i], s[i], v);
+                sn[o] = v;
+            }
+#pragma unroll
+            for (int o = 0; o < S; ++o) { s[o] = sn[o]; St[((c + dir) * S + o) * P + p] = sn[o]; }
+        }
     }
 }
 
@@ -682,19 +710,32 @@ density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, doub
     }
 }
 
-// B3: x_j = zloc_j + SB[j] . sb_c (+ addto), one thread per entry, lanes along the rows.
+// B3: x_j = zloc_j + SB[j] . sb_c (+ addto): no recurrence.  One thread per row and DS_FIXP pairs: the spike row
+// stays in registers, the states are warp-uniform loads, X is read and written along the rows.
+constexpr int DS_FIXP = 16;
+
 template <int K>
-__global__ void density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
-                                       const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
-    constexpr int S = K - 1;
-    for (i64 p = blockIdx.y; p < P; p += gridDim.y) {
+__global__ void __launch_bounds__(256)
+density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+                       const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
+    constexpr int S = K > 1 ? K - 1 : 1;
+    const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
+    for (i64 pg = blockIdx.y; pg < npg; pg += gridDim.y) {
+        const i64 pa = pg * DS_FIXP, pb = pa + DS_FIXP < P ? pa + DS_FIXP : P;
         for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
             i64 c = j / DS_CH; if (c > nchunk - 1) c = nchunk - 1;
-            double v = X[j + ldx * p];
+            double sr[S];
 #pragma unroll
-            for (int i = 0; i < S; ++i) v = fma(sb[j * S + i], St[(c * S + i) * P + p], v);
-            if (addto) v += addto[j + lda * p];
-            X[j + ldx * p] = v;
+            for (int i = 0; i < S; ++i) sr[i] = sb[j * S + i];
+            const double *st = St + c * S * P;
+#pragma unroll 4
+            for (i64 p = pa; p < pb; ++p) {
+                double v = X[j + ldx * p];
+#pragma unroll
+                for (int i = 0; i < S; ++i) v = fma(sr[i], st[i * P + p], v);
+                if (addto) v += addto[j + lda * p];
+                X[j + ldx * p] = v;
+            }
         }
     }
 }
@@ -787,15 +828,15 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     double *ws = nullptr;                           // E and the propagated states, [M][K-1][P] each
     CB_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * M * S * P, st));
     double *E = ws, *St = ws + M * S * P;
-    for (i64 pt0 = 0; pt0 < ptiles; pt0 += 65535 * 32) {   // (grid.x limit is far away; grid.y = chunks <= 65535 checked at plan time)
-        (void)pt0;
-    }
+    // grid.y = chunks <= 65535 is checked at plan time
     dim3 grid((unsigned)ptiles, (unsigned)M);
     density_fwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_fw, n, M, X, ldx, P, E);
-    density_state_kernel<K><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(D->d_tf, M, P, E, St, +1);
+    const unsigned sblocks = (unsigned)((P + DS_STATE_THREADS - 1) / DS_STATE_THREADS);
+    density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tf, M, P, E, St, +1);
     density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
-    density_state_kernel<K><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(D->d_tb, M, P, E, St, -1);
-    dim3 gfix((unsigned)cb_grid_for(n, 256, 8), (unsigned)(P < 8192 ? P : 8192));
+    density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
+    const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
+    dim3 gfix((unsigned)cb_grid_for(n, 256, 2), (unsigned)(npg < 4096 ? npg : 4096));
     density_bwd_fix_kernel<K><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(ws, st);
