@@ -219,6 +219,10 @@ def other_kernels(torch, cb, peak_gbs):
 
 
 def run_gpu(args):
+    # exactly one line may reach stdout (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -336,7 +340,8 @@ def run_gpu(args):
             "clocks": clocks,
             "kernels": kernels,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

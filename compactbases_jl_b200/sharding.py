@@ -19,6 +19,7 @@ Only index arithmetic and the exchange live here; the kernels are behind
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 
 import torch
@@ -43,6 +44,7 @@ class IntervalShard:
     touch_hi: int
 
 
+@functools.lru_cache(maxsize=256)
 def interval_shards(numintervals: int, k: int, ml: int, col0: int, ncols: int, world: int) -> list[IntervalShard]:
     """Splits the t.t intervals evenly.  Function f (1-based, order k) lives on intervals
     f-ml .. f-ml+k-1 clipped to 0..numintervals-1 (src/knot_sets.jl:138-151), so it *starts* in
