@@ -147,6 +147,30 @@ class _BSplineOrRestricted:
         return out
 
 
+    # -- function interpolation B \ f (src/bsplines.jl:329-343) -------------
+    def ldiv(self, f) -> ColMajor:
+        r"""``B \ f``: least-squares fit of f at the quadrature nodes of the parent basis (the reference
+        solves ``B.B \ f.(B.x)``, restricted: ``B[x,:] \ f.(x)``).  f: a callable, or its nodal values as a
+        tensor of shape (P, nquad) / (nquad,).  Returns the ncols x P coefficients."""
+        P = self.parent_basis
+        if callable(f):
+            vals = P.nodal_values(f).reshape(1, -1)
+        else:
+            vals = f if isinstance(f, torch.Tensor) else to_device(np.atleast_2d(np.asarray(f, dtype=np.float64)), P.device)
+            vals = vals.reshape(1, -1) if vals.dim() == 1 else vals
+        nq = P.ni * P.q
+        if vals.shape[1] != nq:
+            raise DimensionMismatch(f"DimensionMismatch: the function must be given at the {nq} quadrature nodes")
+        vals = vals.to(P.device, torch.float64).contiguous()
+        plan = getattr(self, "_ldiv_plan", None)
+        if plan is None:
+            from .densities import FunctionProduct
+            plan = self._ldiv_plan = FunctionProduct(self)
+        out = ColMajor.zeros(self.ncols, vals.shape[0], P.device)
+        _lib.call("cb_density_project", plan.handle, _ptr(vals), vals.shape[1], vals.shape[0], _ptr(out.data), out.ld, _stream())
+        return out
+
+
 def band_shape(L, R):
     """(l, u) of ``Matrix(undef, A, B)`` (src/bsplines.jl:264-269)."""
     k = max(L.order(), R.order())

@@ -740,6 +740,33 @@ density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double 
     }
 }
 
+// r = V' fvals for B \ f: one thread per (function, column).  table[(c*q + l)*K + a] is the value at node l of the
+// non-empty interval with ordinal c of its a-th live function.
+template <int K>
+__global__ void density_project_rhs_kernel(const double *__restrict__ table, const int32_t *__restrict__ ord, i64 n_tt, int ml,
+                                           int q, i64 col0, i64 ncols, const double *__restrict__ fvals, i64 ldf, i64 P,
+                                           double *__restrict__ out, i64 ldo) {
+    for (i64 p = blockIdx.y; p < P; p += gridDim.y) {
+        const double *fc = fvals + ldf * p;
+        for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < ncols; j += (i64)gridDim.x * blockDim.x) {
+            const i64 fj = col0 + 1 + j;            // 1-based function of the parent basis
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const i64 sv = fj - ml + r;         // 0-based interval of t.t; expanded 1-based index sv + ml
+                if (sv < 0 || sv > n_tt - 2) continue;
+                const int c = ord[sv + ml - 1];
+                if (c < 0) continue;
+                const int a = K - 1 - r;            // slot of function fj among the K live functions of the interval
+                const double *tb = table + (i64)c * q * K + a;
+                const double *fv = fc + (i64)c * q;
+                for (int l = 0; l < q; ++l) s = fma(tb[l * K], fv[l], s);
+            }
+            out[j + ldo * p] = s;
+        }
+    }
+}
+
 // Orthogonal branches (src/densities.jl:166-185): rho = c .* (conj(f) .* g).
 __global__ void density_orthogonal_kernel(const double *__restrict__ c, i64 n,
                                           const double *__restrict__ f, i64 ldf, i64 Pf,
@@ -969,6 +996,78 @@ int cb_density_apply(const cb_density *D, const double *f, i64 ldf, i64 Pf,
     }
     return rc;
 }
+
+// B \ f (src/bsplines.jl:329-343): the reference solves the sparse least-squares problem  V c = f(x)  at the
+// quadrature nodes (unweighted), i.e. c = (V'V)^-1 V' f(x) — the plan's Gram factor with a plain V' f right-hand side.
+int cb_density_project(const cb_density *D, const double *fvals, i64 ldf, i64 P, double *coef, i64 ldc, void *stream) {
+    CB_REQUIRE(D != nullptr && fvals != nullptr && coef != nullptr, "cb_density_project: NULL argument");
+    CB_REQUIRE(P >= 0 && ldf >= D->ni * D->q && ldc >= D->ncols, "cb_density_project: leading dimension too small");
+    if (P == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = CB_OK;
+    dim3 grid((unsigned)cb_grid_for(D->ncols, 128, 16), (unsigned)(P < 16384 ? P : 16384));
+    CB_DISPATCH_KD(D->k, (density_project_rhs_kernel<K><<<grid, 128, 0, st>>>(D->d_table, D->d_ord, D->n_tt, D->ml, D->q, D->col0,
+                                                                                D->ncols, fvals, ldf, P, coef, ldc)));
+    CB_LAUNCH_CHECK();
+    CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, coef, ldc, P, nullptr, 0, st));
+    return rc;
+}
+
+// ---- SPD banded factor / batched solve: the metric inverse of LinearOperator (src/linear_operators.jl:38-48,
+// factorize(B'B) + ldiv!) ------------------------------------------------------------------------------------
+int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) {
+    CB_REQUIRE(out != nullptr, "cb_bandchol_create: out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(band != nullptr && n >= 1 && l >= 0, "cb_bandchol_create: bad argument");
+    if (l + 1 > CB_KMAX) { cb_set_error("cb_bandchol_create: half-bandwidth %d outside compiled range 0..%d", l, CB_KMAX - 1); return CB_ERR_UNSUPPORTED; }
+    cb_density_s *D = new cb_density_s();
+    D->k = l + 1; D->q = 0; D->ml = 0; D->n_tt = 0; D->nf = n; D->ni = 0; D->col0 = 0; D->ncols = n; D->refine = 0; D->chol_status = 0;
+    D->d_table = D->d_wv = D->d_fw = D->d_bw = nullptr; D->d_ord = nullptr; D->d_ivlist = nullptr;
+    D->d_cfb = D->d_sb = D->d_tf = D->d_tb = nullptr; D->nchunk = 0;
+    cudaGetDevice(&D->device);
+    int *d_status = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    step(cudaMalloc(&D->d_fw, sizeof(double) * n * D->k));
+    step(cudaMalloc(&D->d_bw, sizeof(double) * n * D->k));
+    step(cudaMalloc(&d_status, sizeof(int)));
+    if (e == cudaSuccess) step(cudaMemset(d_status, 0, sizeof(int)));
+    int rc = CB_OK;
+    if (e == cudaSuccess) {
+        rc = launch_cholesky(D->k, band, n, D->d_fw, D->d_bw, d_status);
+        step(cudaGetLastError());
+        step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (e == cudaSuccess && rc == CB_OK && D->chol_status == 0) {
+        const int kk = D->k;
+        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D)); return CB_OK; }();
+        step(cudaDeviceSynchronize());
+    }
+    cudaFree(d_status);
+    if (e != cudaSuccess) { cb_set_error("cb_bandchol_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }
+    if (rc != CB_OK) { cb_density_destroy(D); return rc; }
+    if (D->chol_status != 0) {
+        // PosDefException of cholesky in the reference
+        cb_set_error("cb_bandchol_create: matrix is not positive definite (leading minor %d)", D->chol_status);
+        cb_density_destroy(D);
+        return CB_ERR_ARG;
+    }
+    *out = reinterpret_cast<cb_bandchol *>(D);
+    return CB_OK;
+}
+
+int cb_bandchol_solve(const cb_bandchol *F, double *X, i64 ldx, i64 nvec, void *stream) {
+    const cb_density_s *D = reinterpret_cast<const cb_density_s *>(F);
+    CB_REQUIRE(D != nullptr && X != nullptr, "cb_bandchol_solve: NULL argument");
+    CB_REQUIRE(nvec >= 0 && ldx >= D->ncols, "DimensionMismatch: cb_bandchol_solve: leading dimension %lld smaller than the matrix order %lld",
+               (long long)ldx, (long long)D->ncols);
+    if (nvec == 0) return CB_OK;
+    int rc = CB_OK;
+    CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, X, ldx, nvec, nullptr, 0, (cudaStream_t)stream));
+    return rc;
+}
+
+int cb_bandchol_destroy(cb_bandchol *F) { return cb_density_destroy(reinterpret_cast<cb_density_s *>(F)); }
 
 int cb_density_nodal_product(const cb_density *D, const double *f, i64 ldf, i64 Pf,
                              const double *g, i64 ldg, i64 Pg, int conj, double *tmp, i64 ldt, void *stream) {

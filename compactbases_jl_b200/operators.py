@@ -113,6 +113,89 @@ class BandedMatrix:
         _lib.call("cb_banded_apply", _ptr(self.data), self.m, self.n, self.l, self.u, _ptr(X.data), X.ld, X.nvec,
                   alpha, beta, _ptr(Y.data), Y.ld, _stream())
 
+    def cholesky(self) -> "BandCholesky":
+        """``factorize(S)`` / ``cholesky(S)`` of a symmetric positive definite band (the metric B'B)."""
+        return BandCholesky(self)
+
+
+class BandCholesky:
+    """Cholesky factor of an SPD ``BandedMatrix`` held on the device (``cb_bandchol_*``); ``ldiv``
+    is the batched ``ldiv!`` of the reference's ``LinearOperator`` (src/linear_operators.jl:38-48)."""
+
+    def __init__(self, A: BandedMatrix):
+        if A.m != A.n or A.l != A.u:
+            raise DimensionMismatch("DimensionMismatch: cholesky needs a square band with equal bandwidths")
+        h = C.c_void_p()
+        with torch.cuda.device(A.data.device):
+            _lib.call("cb_bandchol_create", _ptr(A.data), A.n, A.l, C.byref(h))
+        self.handle, self.n, self.device = h, A.n, A.data.device
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().cb_bandchol_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def ldiv(self, X):
+        """In place ``ldiv!(F, X)``: X <- A^-1 X for a ColMajor batch (or a (nvec, n) tensor)."""
+        Xc = _as_colmajor(X)
+        if Xc.n != self.n:
+            raise DimensionMismatch(f"DimensionMismatch: factor has order {self.n}, X has {Xc.n} rows")
+        _lib.call("cb_bandchol_solve", self.handle, _ptr(Xc.data), Xc.ld, Xc.nvec, _stream())
+        return X
+
+
+class LinearOperator:
+    """``LinearOperator(A, R)`` (src/linear_operators.jl:26-75): the action of the operator with matrix A in the
+    basis R, i.e. ``y = S^-1 (A x)`` with the metric S = R'R for non-orthogonal bases (B-splines) and ``y = A x``
+    for FE-DVR and finite differences (``operator_metric`` is ``I``, :4-17)."""
+
+    def __init__(self, A, R=None):
+        self.A = A
+        self.Binv = None
+        self.temp = None
+        metric = None
+        if R is not None:
+            from .bsplines import _BSplineOrRestricted
+            if isinstance(R, _BSplineOrRestricted):                  # operator_metric(B) = B'B
+                metric = R.S if hasattr(R, "S") else R.T @ R
+        if isinstance(metric, BandedMatrix):
+            self.Binv = metric.cholesky()
+        elif isinstance(metric, Tridiagonal):                        # k = 2 B-splines: the metric is SymTridiagonal
+            n = metric.d.shape[0]
+            band = torch.zeros((n, 3), dtype=torch.float64, device=metric.d.device)
+            band[:, 1] = metric.d
+            band[1:, 0] = metric.du
+            band[:-1, 2] = metric.dl
+            self.Binv = BandedMatrix(band.contiguous(), n, n, 1, 1).cholesky()
+
+    @property
+    def shape(self):
+        return self.A.shape
+
+    def mul(self, Y, X, alpha: float = 1.0, beta: float = 0.0):
+        """``mul!(y, M, x, alpha, beta)`` (src/linear_operators.jl:38-52)."""
+        if self.Binv is None:
+            return mul(Y, self.A, X, alpha, beta)
+        Xc, Yc = _as_colmajor(X), _as_colmajor(Y)
+        if self.temp is None or self.temp.data.shape != Yc.data.shape or self.temp.data.device != Yc.data.device:
+            self.temp = ColMajor(torch.empty_like(Yc.data))
+        mul(self.temp, self.A, Xc, alpha, 0.0)
+        self.Binv.ldiv(self.temp)
+        if beta == 0.0:
+            Yc.data.copy_(self.temp.data)
+        else:
+            Yc.data.mul_(beta).add_(self.temp.data)
+        return Y
+
+    def __matmul__(self, X):
+        Xc = _as_colmajor(X)
+        Y = ColMajor(torch.empty((Xc.nvec, self.shape[0]), dtype=torch.float64, device=Xc.data.device))
+        self.mul(Y, Xc)
+        return Y
+
 
 class Tridiagonal:
     """LinearAlgebra.Tridiagonal(dl, d, du)."""

@@ -262,6 +262,22 @@ int cb_density_orthogonal(const double *c, cb_i64 n,
                           const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
                           double *rho, cb_i64 ldr, void *stream);
 
+/* ---- "next" rows of the scope table --------------------------------------------------
+ * B \ f for B-splines, Base.:(\)(B::BSpline, f) src/bsplines.jl:329-343: the least-squares fit V c = f(x) at the
+ * quadrature nodes, c = (V'V)^-1 V' f(x).  fvals: f at the nodes of the PARENT basis, (ni*q) x P column-major
+ * (device); coef: ncols x P (device).  Uses the Gram factor of a plan made by cb_density_bspline_create. */
+int cb_density_project(const cb_density *D, const double *fvals, cb_i64 ldf, cb_i64 P,
+                       double *coef, cb_i64 ldc, void *stream);
+
+/* Metric inverse of LinearOperator, src/linear_operators.jl:26-48 (factorize(B'B) once, ldiv! per application):
+ * Cholesky factor of a symmetric positive definite BandedMatrix with l = u ((2l+1) x n column-major, device) and
+ * the in-place batched solve X <- A^-1 X for n x nvec column-major batches (partitioned substitution: every
+ * chunk of rows x 32 vectors is an independent warp).  Not positive definite -> CB_ERR_ARG (PosDefException). */
+typedef struct cb_bandchol_s cb_bandchol;
+int cb_bandchol_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
+int cb_bandchol_solve(const cb_bandchol *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
+int cb_bandchol_destroy(cb_bandchol *F);
+
 #ifdef __cplusplus
 }
 #endif

@@ -625,3 +625,21 @@ def density_orthogonal(f, g, c=None, conj=True):
     if c is not None:
         out = (c[:, None] if out.ndim == 2 else c) * out
     return out
+
+
+# ---------------------------------------------------------------------------
+# Function interpolation and the metric inverse ("next" rows)
+# ---------------------------------------------------------------------------
+
+def bspline_ldiv(V, fvals):
+    """``B \\ f`` for B-splines, src/bsplines.jl:329-343: ``B.B \\ getindex.(Ref(f), B.x)`` — the sparse
+    least-squares solve of V c = f(x) at the quadrature nodes (restricted bases: V = B[x, :] over all
+    nodes of the parent).  V dense [nquad, n]; fvals [nquad] or [nquad, P]."""
+    return np.linalg.lstsq(V, fvals, rcond=None)[0]
+
+
+def linear_operator_apply(A, S, X, alpha=1.0, beta=0.0, Y=None):
+    """``mul!(y, LinearOperator(A, factorize(S)), x, alpha, beta)``, src/linear_operators.jl:38-48:
+    temp = alpha*A*x, then y = S \\ temp (beta == 0) or y = beta*y + S \\ temp.  A, S dense."""
+    t = np.linalg.solve(S, alpha * (A @ X))
+    return t if beta == 0.0 or Y is None else beta * Y + t

@@ -101,6 +101,21 @@ DOCS = {
 }
 
 
+def density_transcript():
+    """docs/src/densities.md: cf = R \\ f, cg = R \\ g, rho = Density(R*cf, R*cg) for k = 7, 71 intervals on 0..10,
+    f = sin(2 pi x), g = x exp(-x): the first and last 16 of the 77 coefficients and norm(rho - R \\ (f g))."""
+    path = "docs/src/densities.md"
+    with open(os.path.join(REF, path), encoding="utf-8") as fh:
+        src = fh.read().split("\n")
+    lo = next(i for i, ln in enumerate(src) if ln.startswith("julia> ρ.ρ # Expansion coefficients"))
+    hi = next(i for i, ln in enumerate(src) if ln.startswith("julia> norm(ρ.ρ - ch)"))
+    vals = [float(ln) for ln in src[lo + 2:hi] if re.fullmatch(r"\s*-?\d[\d.e+-]*\s*", ln)]
+    assert len(vals) == 32, len(vals)
+    return {"source": f"{path}:{lo + 1}-{hi + 2}", "k": 7, "a": 0.0, "b": 10.0, "N": 71,
+            "f": "sin(2*pi*x)", "g": "x*exp(-x)", "first16": vals[:16], "last16": vals[16:],
+            "norm_rho_minus_ch": float(src[hi + 1])}
+
+
 def main():
     out = {}
     out["mass_k3_discontinuous"] = {
@@ -150,6 +165,7 @@ def main():
         N = 3 if name.startswith("k7") else 2
         out[name] = dict(source=f"{d}:{lo}-{hi}", N=N, a0=0, b0=1, matrix=rows, **meta)
     out["docs"] = DOCS
+    out["docs"]["density_k7"] = density_transcript()
     with open(os.path.join(HERE, "bspline_rationals.json"), "w") as f:
         json.dump(out, f, indent=0)
     for k, v in out.items():

@@ -366,3 +366,20 @@ def test_density_pinv_branch_projects_products():
     c = np.sin(np.arange(1, nf + 1))
     rho = cbo.density_bspline(V, one, c)
     np.testing.assert_allclose(rho, c, rtol=0, atol=1e-13)
+
+
+def test_density_docs_transcript(golden):
+    """docs/src/densities.md:119-182: cf = R \\ f, cg = R \\ g, rho = Density(R*cf, R*cg) (k = 7, 71 intervals on
+    0..10): the printed first / last 16 coefficients and norm(rho - R \\ (f g)).  Pins ``B \\ f`` (bspline_ldiv) and
+    the general Density branch end to end; the transcript went through a sparse QR, so agreement is ~1e-10."""
+    g = golden["docs"]["density_k7"]
+    tt = cbo.linear_knots(g["a"], g["b"], g["N"])
+    t, q, x, w = bspline(tt, g["k"])
+    V = cbo.basis_matrix(t, g["k"], x, q)
+    f, h = np.sin(2 * np.pi * x), x * np.exp(-x)
+    cf, cg, ch = cbo.bspline_ldiv(V, f), cbo.bspline_ldiv(V, h), cbo.bspline_ldiv(V, f * h)
+    rho = cbo.density_bspline(V, cf, cg)
+    assert rho.shape == (77,)
+    np.testing.assert_allclose(rho[:16], g["first16"], rtol=0, atol=2e-10)
+    np.testing.assert_allclose(rho[-16:], g["last16"], rtol=0, atol=2e-10)
+    assert abs(np.linalg.norm(rho - ch) - g["norm_rho_minus_ch"]) <= 1e-9
