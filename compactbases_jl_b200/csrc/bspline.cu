@@ -364,7 +364,10 @@ int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
     int vec_ok = ((uintptr_t)vals % 16) == 0;
     if (B->n_tt <= EVAL_SMEM_KNOTS) {
         const size_t smem = sizeof(double) * ((size_t)B->n_tt + 2 * (size_t)(B->k - 1));   // + the clamped copies of the end knots
-        int grid = cb_grid_for(nx, EVAL_THREADS, 6);   // persistent-ish: the knot copy is amortised over several blocks
+#ifndef EVAL_WAVES
+#define EVAL_WAVES 8
+#endif
+        int grid = cb_grid_for(nx, EVAL_THREADS, EVAL_WAVES);   // a whole number of waves of the 4 resident CTAs per SM; the knot copy is amortised over many blocks
         CB_DISPATCH_K(B->k, {
             auto kern = m == 0 ? bspline_eval_kernel<K, true, 0> : bspline_eval_kernel<K, true, -1>;
             CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -19,6 +19,12 @@ elif what == "eval":
     x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
     iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 7), dtype=torch.float64, device="cuda")
     fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
+elif what == "eval1m":     # C1 size: 1e6 points
+    B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
+    nx = 1_000_000
+    x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
+    iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 7), dtype=torch.float64, device="cuda")
+    fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
 elif what == "asm3":
     B = cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 200000))
     fn = lambda: (B.T @ cb.CoulombPotential(1.0) @ B, B.T @ D.T @ D @ B)
