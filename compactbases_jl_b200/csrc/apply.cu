@@ -293,18 +293,24 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
+        // A dependent DMMA has ~180 cycles of latency (scripts/micro/dmma_lat.cu): the k-steps of the warp's BT_RB row
+        // blocks advance together, BT_RB * 4 independent accumulator chains in flight
         double c[BT_RB][BT_VEC / 8][2];
 #pragma unroll
-        for (int q = 0; q < BT_RB; ++q) {
-            const int rb = warp * BT_RB + q;
+        for (int q = 0; q < BT_RB; ++q)
 #pragma unroll
             for (int nt = 0; nt < BT_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
-            const double *af = as + rb * KS * 32 + lane;
-            const double *xb = xs + gq * pitch + 8 * rb + tq;        // + nt*8*pitch + 4*ks
+        {
+            const double *af = as + warp * BT_RB * KS * 32 + lane;
+            const double *xb = xs + gq * pitch + 8 * warp * BT_RB + tq;   // + q*8 + nt*8*pitch + 4*ks
             for (int ks = 0; ks < KS; ++ks) {
-                const double a = af[ks * 32];
 #pragma unroll
-                for (int nt = 0; nt < BT_VEC / 8; ++nt) dmma884(c[q][nt][0], c[q][nt][1], a, xb[nt * 8 * pitch + 4 * ks]);
+                for (int q = 0; q < BT_RB; ++q) {
+                    const double a = af[(q * KS + ks) * 32];
+#pragma unroll
+                    for (int nt = 0; nt < BT_VEC / 8; ++nt)
+                        dmma884(c[q][nt][0], c[q][nt][1], a, xb[q * 8 + nt * 8 * pitch + 4 * ks]);
+                }
             }
         }
         __syncthreads();                            // everyone done reading xs
