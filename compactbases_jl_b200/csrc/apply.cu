@@ -252,13 +252,19 @@ constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
 #ifndef BT_PITCH_MOD
 #define BT_PITCH_MOD 12
 #endif
+#ifndef BT_TAIL_PCT
+#define BT_TAIL_PCT 0                               // share of the vector tiles handed out as single-tile items at the end
+#endif
+#ifndef BT_GRIDCAP
+#define BT_GRIDCAP 1024                             // CTAs per SM in the grid at most (items beyond that are strided)
+#endif
 // x-tile pitch = BT_PITCH_MOD (mod 16): the B-fragment reads (lane (gq, tq) reads column gq, row 4ks + tq) are then
 // bank-conflict free; the movers run along the rows and do not care
 __host__ __device__ inline int bt_pitch(int rows) { return BT_PITCH_MOD < 0 ? (rows | 1) : rows + ((BT_PITCH_MOD - rows) % 16 + 16) % 16; }
 
 __global__ void __launch_bounds__(BT_THREADS)
 banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
-                    const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk,
+                    const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk, i64 nvc_big,
                     double alpha, double beta, double *__restrict__ Y, i64 ldy) {
     extern __shared__ __align__(16) double sm[];
     const int W = l + u + 1;
@@ -271,9 +277,13 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
     const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
     const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
     // work item = (row tile, chunk of vchunk vector tiles): the band tile is staged once per item
-    const i64 nvc = (nvt + vchunk - 1) / vchunk;
-    for (i64 item = blockIdx.x; item < nrt * nvc; item += gridDim.x) {
+    // the first nvc_big chunks take vchunk vector tiles each, the remaining vector tiles are items of their own: the
+    // hardware hands the small items out last, so the SMs run dry within one small item of each other
+    const i64 nitems = nrt * (nvc_big + (nvt - nvc_big * vchunk));
+    for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
       const i64 vc = item / nrt, rt = item - vc * nrt;              // row tiles vary fastest (contiguous streams)
+      const i64 vt_begin = vc < nvc_big ? vc * vchunk : nvc_big * vchunk + (vc - nvc_big);
+      const i64 vt_end = vc < nvc_big ? vt_begin + vchunk : vt_begin + 1;
       const i64 i0 = rt * BT_ROWS;                  // first row of the tile
       __syncthreads();                              // previous item fully consumed
       // A fragments: as[rb][ks][lane] = A(i0 + 8rb + g, i0 + 8rb - l + 4ks + t), 0 outside band/matrix
@@ -284,8 +294,7 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
           if (i < m && j >= 0 && j < n && j - i <= u && i - j <= l) a = __ldg(band + (u + i - j) + (i64)W * j);
           as[e] = a;
       }
-      const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
-      for (i64 vt = vc * vchunk; vt < vt_end; ++vt) {
+      for (i64 vt = vt_begin; vt < vt_end; ++vt) {
         const i64 v0 = vt * BT_VEC;
         __syncthreads();                            // previous tile fully consumed
         // x window rows i0-l .. i0+BT_ROWS-1+u (+ k padding), zero outside the matrix
@@ -373,6 +382,15 @@ __host__ __device__ constexpr int fe_pitch(int rows) { return FE_PITCH_MOD < 0 ?
 #endif
 #ifndef FEDVR_MINB
 #define FEDVR_MINB 3
+#endif
+#ifndef FEDVR_LEAN
+#define FEDVR_LEAN 1
+#endif
+#ifndef FEDVR_PIPE
+#define FEDVR_PIPE 1
+#endif
+#ifndef FEDVR_WAVES
+#define FEDVR_WAVES 4                               // waves of resident CTAs in the grid (NS == 1)
 #endif
 #ifndef FE_NTI
 #define FE_NTI 1                                    // vector tiles (of 8) whose DMMA chains are interleaved
@@ -507,6 +525,542 @@ fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-ba
     cp_async_wait<0>();
 }
 
+#ifdef FEDVR_PHASE_PROF
+__device__ unsigned long long fe_prof[8];
+#define FE_PROF_T(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
+#define FE_PROF_L(i) do { if (lane == 0 && (w == 0 || w == NG || w == NG + 1)) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
+#else
+#define FE_PROF_T(i) do { } while (0)
+#define FE_PROF_L(i) do { } while (0)
+#endif
+// K8, lean form.  Same tiling and arithmetic as fedvr_apply_kernel (NS = 1); what changed is the instruction count:
+// the ncu source page of that kernel (profiles/r1t) showed 10.5 k warp instructions per tile of which ~1.4 k were the
+// copies, DMMAs and fragment traffic — the rest was 64-bit tile arithmetic done twice per tile, divergence bookkeeping
+// around every predicated DMMA (the warp index was not known to be warp-uniform), runtime-bounded mover loops and
+// three-way branches in the write-back.  Here interior tiles (every element, row and vector present, beta == 0, not
+// the first tile of a vector group) take a straight-line path: warp index through a shuffle (uniform), tile
+// coordinates carried incrementally, compile-time mover loops with immediate offsets, per-lane write-back
+// destinations computed once per tile.  Every other tile runs the clipped path of the original kernel.
+template <int O, int NG>
+__global__ void __launch_bounds__(32 * NG, (NG <= 8 ? 4 : FEDVR_MINB))
+fedvr_apply_lean_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
+                        const double *__restrict__ X, i64 ldx, i64 nvec,
+                        double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    constexpr int THREADS = 32 * NG;
+    constexpr int ET = NG - 1;                      // elements per tile
+    constexpr int ROWS = (ET + 1) * (O - 1) + 1;    // incl. halo element
+    constexpr int PITCH = fe_pitch(ROWS);
+    constexpr int STAGE = (FE_TV * PITCH + 1) / 2 * 2;
+    constexpr int MT = (O + 7) / 8, KS = (O + 3) / 4;
+    constexpr int VPW = FE_TV / NG;                 // vectors per warp in the movers
+    constexpr int NIT = (ROWS + 31) / 32;
+    constexpr int NR = ET * (O - 1);                // rows an interior tile owns: tile rows 1 .. NR
+    constexpr int NSI = (NR + 31) / 32;
+    static_assert(FE_TV % NG == 0, "movers assign whole vectors to warps");
+    extern __shared__ __align__(16) double sm[];
+    double *xs = sm;
+    double *br0 = sm + STAGE;                       // [(ET+1)][33] first-row products (bridge contributions)
+    double *br9 = br0 + (ET + 1) * FE_BRP;          // [ET][33]     last-row products
+    const int g = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler as well
+    const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+    const i64 net = (nel + ET - 1) / ET;
+    const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
+    // tile = vt * net + et: element tiles vary fastest so that the CTAs running at one time stream long contiguous row
+    // ranges of a few vector groups; (et, vt) advance by gridDim.x tiles without a division
+    i64 vt = (i64)blockIdx.x / net, et = (i64)blockIdx.x - vt * net;
+#ifdef FEDVR_PHASE_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    for (; vt < nvt;) {
+        const i64 eA = et * ET, v0 = vt * FE_TV;
+        const i64 x0row = eA * (O - 1) - first0;    // X/Y row of tile row 0 (rows are relative to the restriction)
+        const bool interior = x0row >= 0 && x0row + ROWS <= nrows && v0 + FE_TV <= nvec && eA + ET + 1 <= nel;
+        if (interior && eA > 0 && beta == 0.0) {
+            // ---- x tile: warp g copies vectors g, g + NG, ... ----------------------------------
+            {
+                const double *xc = X + (v0 + g) * ldx + x0row + lane;
+                double *xd = xs + g * PITCH + lane;
+#pragma unroll
+                for (int h = 0; h < VPW; ++h)
+#pragma unroll
+                    for (int i = 0; i < NIT; ++i)
+                        if (32 * i + 31 < ROWS || lane + 32 * i < ROWS)
+                            cp_async8(xd + h * NG * PITCH + 32 * i, xc + (i64)h * NG * ldx + 32 * i);
+                cp_async_commit();
+            }
+            // ---- block fragments a = B_e[gq + 8 mt][4 ks + tq], zero outside the block ---------
+            double af[MT][KS];
+            {
+                const double *b = blocks + (eA + g) * (O * O) + tq * O + gq;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+                        af[mt][ks] = (gq + 8 * mt < O && 4 * ks + tq < O) ? __ldg(b + 4 * ks * O + 8 * mt) : 0.0;
+            }
+            FE_PROF_T(0);
+            cp_async_wait<0>();
+            FE_PROF_T(1);
+            __syncthreads();
+            FE_PROF_T(2);
+            if (g < ET) {
+                // write-back destination of this lane's accumulator rows gq + 8 mt: row 0 and row O-1 are bridge
+                // contributions (side buffers), rows 1..O-2 go back into the tile in place
+                int dst[MT], str[MT], nst[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int mm = gq + 8 * mt;
+                    const bool side = (mm == 0) || (mm == O - 1);
+                    dst[mt] = mm == 0 ? STAGE + g * FE_BRP + 2 * tq
+                            : mm == O - 1 ? STAGE + (ET + 1) * FE_BRP + g * FE_BRP + 2 * tq
+                            : 2 * tq * PITCH + g * (O - 1) + mm;
+                    str[mt] = side ? 1 : PITCH;
+                    nst[mt] = side ? 8 : 8 * PITCH;
+                }
+#pragma unroll
+                for (int np = 0; np < FE_TV / 8; ++np) {
+                    double c[MT][2];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
+                    const double *xe = xs + (8 * np + gq) * PITCH + g * (O - 1) + tq;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const double bf = (4 * ks + 3 < O || 4 * ks + tq < O) ? xe[4 * ks] : 0.0;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma884(c[mt][0], c[mt][1], af[mt][ks], bf);
+                    }
+                    __syncwarp();                   // all lanes have read this vector tile's x rows
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        if (8 * mt + 7 < O || gq + 8 * mt < O) {
+                            sm[dst[mt] + np * nst[mt]] = c[mt][0];
+                            sm[dst[mt] + np * nst[mt] + str[mt]] = c[mt][1];
+                        }
+                }
+            } else {
+                // halo element: only its first row (the contribution to the tile's last bridge row)
+#pragma unroll
+                for (int np = 0; np < FE_TV / 8; ++np) {
+                    double c0 = 0.0, c1 = 0.0;
+                    const double *xe = xs + (8 * np + gq) * PITCH + ET * (O - 1) + tq;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const double bf = (4 * ks + 3 < O || 4 * ks + tq < O) ? xe[4 * ks] : 0.0;
+                        dmma884(c0, c1, af[0][ks], bf);
+                    }
+                    if (gq == 0) { br0[ET * FE_BRP + 8 * np + 2 * tq] = c0; br0[ET * FE_BRP + 8 * np + 2 * tq + 1] = c1; }
+                }
+            }
+            FE_PROF_T(3);
+            __syncthreads();
+            FE_PROF_T(4);
+            // bridge rows: last row of element g-1 plus first row of element g (tile row 0 belongs to the previous tile)
+            if (g >= 1) xs[lane * PITCH + g * (O - 1)] = br9[(g - 1) * FE_BRP + lane] + br0[g * FE_BRP + lane];
+            __syncthreads();
+            FE_PROF_T(5);
+            {
+                double *yc = Y + (v0 + g) * ldy + x0row + 1 + lane;
+                const double *ys = xs + g * PITCH + 1 + lane;
+#pragma unroll
+                for (int h = 0; h < VPW; ++h)
+#pragma unroll
+                    for (int i = 0; i < NSI; ++i)
+                        if (32 * i + 31 < NR || lane + 32 * i < NR)
+                            __stcs(yc + (i64)h * NG * ldy + 32 * i, alpha * ys[h * NG * PITCH + 32 * i]);
+            }
+            FE_PROF_T(6);
+            __syncthreads();                        // the tile may be refilled
+            FE_PROF_T(7);
+        } else {
+            // ---- clipped path: first tile of a vector group, partial tiles, beta != 0 ----------
+            load_tile<THREADS>(xs, PITCH, X, ldx, nrows, x0row, ROWS, v0, FE_TV, nvec);
+            double af[MT][KS];
+            {
+                const double *b = blocks + (eA + g) * (O * O);
+                const bool have = eA + g < nel;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int mm = gq + 8 * mt, mp = 4 * ks + tq;
+                        af[mt][ks] = (have && mm < O && mp < O && (g < ET || mt == 0)) ? __ldg(b + mp * O + mm) : 0.0;
+                    }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int np = 0; np < FE_TV / 8; ++np) {
+                double c[MT][2];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.0; c[mt][1] = 0.0; }
+                const double *xe = xs + (8 * np + gq) * PITCH + g * (O - 1) + tq;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double bf = (4 * ks + tq < O) ? xe[4 * ks] : 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) dmma884(c[mt][0], c[mt][1], af[mt][ks], bf);
+                }
+                __syncwarp();
+                const int v = 8 * np + 2 * tq;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int mm = gq + 8 * mt;
+                    if (mm == 0) { br0[g * FE_BRP + v] = c[mt][0]; br0[g * FE_BRP + v + 1] = c[mt][1]; }
+                    else if (g < ET && mm == O - 1) { br9[g * FE_BRP + v] = c[mt][0]; br9[g * FE_BRP + v + 1] = c[mt][1]; }
+                    else if (g < ET && mm < O - 1) {
+                        xs[v * PITCH + g * (O - 1) + mm] = c[mt][0];
+                        xs[(v + 1) * PITCH + g * (O - 1) + mm] = c[mt][1];
+                    }
+                }
+            }
+            __syncthreads();
+            // global row 0 has no previous element
+            if (g == 0) { if (eA == 0) xs[lane * PITCH] = br0[lane]; }
+            else xs[lane * PITCH + g * (O - 1)] = br9[(g - 1) * FE_BRP + lane] + br0[g * FE_BRP + lane];
+            __syncthreads();
+            // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
+            const int r_lo = (eA == 0) ? 0 : 1;
+            const i64 last_el = eA + ET < nel ? eA + ET : nel;            // elements actually present
+            const int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
+            store_tile<THREADS>(xs, PITCH, Y, ldy, nrows, x0row, r_lo, r_hi, v0, FE_TV, nvec, alpha, beta);
+            __syncthreads();
+        }
+        et += gridDim.x;
+        while (et >= net) { et -= net; ++vt; }
+    }
+#ifdef FEDVR_PHASE_PROF
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&fe_prof[i], (unsigned long long)pf[i]);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// K8, warp-specialised TMA pipeline.
+//
+// The phase clocks of the kernels above (scripts/fe_phase.py) showed where a tile's 14.6 k cycles go when every
+// warp loads, computes and stores in turn: 2.6 k issuing 10 cp.async + 6 LDG per warp against a backed-up LSU,
+// 2.6 k waiting for them, 3.0 k in the dependent DMMA chains, 2.9 k issuing 10 LDS + 10 STG, 3.5 k in four CTA
+// barriers.  Splitting the roles over warps with LSU movers (cp.async loaders, LDS/STG storers) did not help: the
+// movers' instructions share the LSU queue with the compute warps' LDS/STS, which then stall behind global-memory
+// back-pressure.  Here the tiles move through the TMA unit instead (cp.async.bulk, one 1-D bulk copy per vector
+// column issued by one lane each), so the LSU only sees the compute warps:
+//   * one loader warp keeps a ring of x tiles filled (completion: expect_tx / complete_tx on an mbarrier),
+//   * NG compute warps multiply a tile in place (all four 8-vector tiles interleaved: one DMMA latency chain per
+//     tile instead of four; a thread may use ~110 registers now) and sum the bridge rows,
+//   * one storer warp streams finished tiles out (bulk stores) and frees the stage.
+// Stages hand over through mbarriers (full -> done -> empty); the only wider construct left is a named barrier among
+// the compute warps between the products and the sums of the bridge rows.
+//
+// Bulk copies need 16-byte aligned addresses and sizes, Julia's columns are 8-byte aligned (odd leading dimensions):
+// a column whose tile starts on an odd element is copied from one element earlier, i.e. tile row r of column v sits
+// at xs[col(v) + p_v + r] with p_v the parity of the element address; the storer writes the one unaligned element at
+// the head or tail of each column with an ordinary store.  X and Y must have the same parity per column (same
+// alignment class and leading dimensions of equal parity), otherwise the launcher takes the lean kernel.
+//
+// Tile columns are swizzled, col(v) = v * P0 + 4 * ((v & 3) ^ ((v >> 2) & 1)) with P0 = 0 (mod 16): the B-fragment
+// reads (lane (gq, tq): column gq, row 4 ks + tq) and the accumulator write-back (rows gq, columns 2 tq, 2 tq + 1)
+// are then free of bank conflicts per half-warp up to the parity shift, which no plain pitch achieves.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// global -> shared bulk copy (TMA unit), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(__cvta_generic_to_global(gdst)), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders this thread's shared-memory writes before later accesses by the TMA unit (async proxy)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef FEDVR_PNTI
+#define FEDVR_PNTI 4                                // 8-vector tiles whose DMMA chains are interleaved
+#endif
+constexpr int FP_NTI = FEDVR_PNTI;
+template <int O, int NG> struct FePipe {
+    static constexpr int ET = NG - 1;
+    static constexpr int ROWS = (ET + 1) * (O - 1) + 1;
+    static constexpr int KS = (O + 3) / 4, MT = (O + 7) / 8;
+    // rows a column holds: the tile (+ parity shift, rounded to 16 bytes) or the k padding read by the halo warp; + skew
+    static constexpr int NEED = (ROWS + 2 > ET * (O - 1) + 4 * KS + 1 ? ROWS + 2 : ET * (O - 1) + 4 * KS + 1) + 12;
+    static constexpr int P0 = (NEED + 15) / 16 * 16;
+    static constexpr int STAGE = FE_TV * P0;                             // doubles per stage
+    static constexpr int BR = (2 * ET + 1) * FE_BRP;                     // one bridge buffer set (br0 + br9)
+    static constexpr int THREADS = 32 * (NG + 2);
+    static constexpr int max_stages() {
+        int n = (int)((227 * 1024 - 2 * BR * 8 - 256) / (STAGE * 8));
+        return n > 6 ? 6 : n;
+    }
+    static constexpr int NSTG = max_stages();
+    static constexpr size_t SMEM = (size_t)NSTG * STAGE * 8 + 2 * BR * 8 + 256;
+};
+__host__ __device__ constexpr int fe_swz(int v) { return 4 * ((v & 3) ^ ((v >> 2) & 1)); }
+
+template <int O, int NG>
+__global__ void __launch_bounds__(FePipe<O, NG>::THREADS, 1)
+fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
+                        const double *__restrict__ X, i64 ldx, i64 nvec,
+                        double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    using P = FePipe<O, NG>;
+    constexpr int ET = P::ET, ROWS = P::ROWS, P0 = P::P0, STAGE = P::STAGE, NSTG = P::NSTG, MT = P::MT, KS = P::KS;
+    constexpr int NR = ET * (O - 1);                // rows an interior tile owns: tile rows 1 .. NR
+    extern __shared__ __align__(128) double sm[];
+    double *brbuf = sm + (size_t)NSTG * STAGE;      // [2][br0 (ET+1) x 33 | br9 ET x 33]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(brbuf + 2 * P::BR);    // full[NSTG], done[NSTG], empty[NSTG]
+    uint64_t *full = bars, *done = bars + NSTG, *empty = bars + 2 * NSTG;
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler as well
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTG; ++s) {
+            mbar_init(full + s, 1);                 // the loader's lane 0 (+ the bytes of the bulk copies)
+            mbar_init(done + s, NG);                // one lane per compute warp
+            mbar_init(empty + s, 1);                // the storer's lane 0
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const i64 net = (nel + ET - 1) / ET;
+    const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
+    const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);        // element address of X[0] (parity is what counts)
+    // tile = vt * net + et, element tiles fastest; every role walks the same sequence blockIdx.x, + gridDim.x, ...
+    i64 vt = (i64)blockIdx.x / net, et = (i64)blockIdx.x - vt * net;
+    int stage = 0;
+    unsigned phase = 0;
+#ifdef FEDVR_PHASE_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    auto advance = [&]() {
+        et += gridDim.x;
+        while (et >= net) { et -= net; ++vt; }
+        if (++stage == NSTG) { stage = 0; phase ^= 1; }
+    };
+    // parity shift of column v of the current tile: tile row r of column v sits at xs[col(v) + par(v) + r]
+    auto col_parity = [&](i64 x0row, i64 v0, int v) { return (int)((xbase + (v0 + v) * ldx + x0row) & 1); };
+    if (w < NG) {
+        // ================= compute warps: y_e = B_e x_e in place ==============================
+        const int g = w, gq = lane >> 2, tq = lane & 3;
+        const int swz_r = fe_swz(gq);               // column skew of the B-fragment reads (vector 8 np + gq)
+        const int swz_c0 = fe_swz(2 * tq), swz_c1 = fe_swz(2 * tq + 1);   // of the accumulator columns 8 np + 2 tq (+ 1)
+        const double wscale = beta == 0.0 ? alpha : 1.0;   // alpha is folded into the tile when Y is not read
+        int parity = 0;                             // bridge buffer set
+        // block fragments a = B_e[gq + 8 mt][4 ks + tq], zero outside the block / beyond the last element; the
+        // fragments of the next tile are requested as soon as the last DMMA of this one has been issued, so their L2
+        // latency hides behind the write-back, the barrier and the bridge sums
+        double af[MT][KS];
+        auto load_frags = [&](i64 eA_) {
+            const bool have = eA_ + g < nel;
+            const double *b = blocks + (eA_ + g) * (O * O) + tq * O + gq;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    af[mt][ks] = (have && gq + 8 * mt < O && 4 * ks + tq < O && (mt == 0 || g < ET))
+                                     ? __ldg(b + 4 * ks * O + 8 * mt) : 0.0;
+        };
+        if (vt < nvt) load_frags(et * ET);
+        for (; vt < nvt; parity ^= 1) {
+            const i64 eA = et * ET;
+            const i64 x0row = eA * (O - 1) - first0;
+            double *xs = sm + (size_t)stage * STAGE;
+            double *br0 = brbuf + parity * P::BR, *br9 = br0 + (ET + 1) * FE_BRP;
+            const int cur_stage = stage;
+            const int par_r = col_parity(x0row, vt * FE_TV, gq);          // columns 8 np + gq
+            const int par_c0 = col_parity(x0row, vt * FE_TV, 2 * tq), par_c1 = col_parity(x0row, vt * FE_TV, 2 * tq + 1);
+            const int par_l = col_parity(x0row, vt * FE_TV, lane);
+            FE_PROF_L(7);
+            mbar_wait(full + stage, phase);
+            FE_PROF_L(2);
+            advance();                              // (et, vt, stage, phase) now describe the next tile
+#pragma unroll
+            for (int np0 = 0; np0 < FE_TV / 8; np0 += FP_NTI) {
+                double c[FP_NTI][MT][2];
+#pragma unroll
+                for (int i = 0; i < FP_NTI; ++i)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] = 0.0; c[i][mt][1] = 0.0; }
+                const double *xe = xs + (8 * np0 + gq) * P0 + swz_r + par_r + g * (O - 1) + tq;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    double bf[FP_NTI];
+#pragma unroll
+                    for (int i = 0; i < FP_NTI; ++i)
+                        bf[i] = (4 * ks + 3 < O || 4 * ks + tq < O) ? xe[i * 8 * P0 + 4 * ks] : 0.0;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        if (mt == 0 || g < ET) {
+#pragma unroll
+                            for (int i = 0; i < FP_NTI; ++i) dmma884(c[i][mt][0], c[i][mt][1], af[mt][ks], bf[i]);
+                        }
+                }
+                if (np0 + FP_NTI >= FE_TV / 8 && vt < nvt) load_frags(et * ET);   // next tile's fragments
+                if (wscale != 1.0) {
+#pragma unroll
+                    for (int i = 0; i < FP_NTI; ++i)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] *= wscale; c[i][mt][1] *= wscale; }
+                }
+                __syncwarp();                       // all lanes have read these vector tiles' x rows
+                // rows 1..O-2 go back in place (no other warp reads them); rows 0 and O-1 are contributions to the
+                // bridge rows shared with the neighbouring elements and go to the side buffers
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int mm = gq + 8 * mt;
+                    if (mm == 0) {
+#pragma unroll
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            br0[g * FE_BRP + 8 * (np0 + i) + 2 * tq] = c[i][mt][0];
+                            br0[g * FE_BRP + 8 * (np0 + i) + 2 * tq + 1] = c[i][mt][1];
+                        }
+                    } else if (g < ET && mm == O - 1) {
+#pragma unroll
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            br9[g * FE_BRP + 8 * (np0 + i) + 2 * tq] = c[i][mt][0];
+                            br9[g * FE_BRP + 8 * (np0 + i) + 2 * tq + 1] = c[i][mt][1];
+                        }
+                    } else if (g < ET && mm < O - 1) {
+                        double *y0 = xs + (8 * np0 + 2 * tq) * P0 + swz_c0 + par_c0 + g * (O - 1) + mm;
+                        double *y1 = xs + (8 * np0 + 2 * tq + 1) * P0 + swz_c1 + par_c1 + g * (O - 1) + mm;
+#pragma unroll
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            y0[i * 8 * P0] = c[i][mt][0];
+                            y1[i * 8 * P0] = c[i][mt][1];
+                        }
+                    }
+                }
+            }
+            FE_PROF_L(3);
+            named_bar_sync(1, 32 * NG);             // every product of the tile is in place
+            FE_PROF_L(4);
+            // bridge rows: last row of element g-1 plus first row of element g; global row 0 has no previous element
+            {
+                double *col = xs + lane * P0 + fe_swz(lane) + par_l;
+                if (g == 0) { if (eA == 0) col[0] = br0[lane]; }
+                else col[g * (O - 1)] = br9[(g - 1) * FE_BRP + lane] + br0[g * FE_BRP + lane];
+            }
+            fence_proxy_async();                    // the storer's bulk copies read what this thread wrote
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done + cur_stage);
+        }
+    } else if (w == NG) {
+        // ================= loader warp: x tiles into the ring, lane <-> vector column ==========
+        for (; vt < nvt; advance()) {
+            const i64 eA = et * ET, v0 = vt * FE_TV;
+            const i64 x0row = eA * (O - 1) - first0;    // X/Y row of tile row 0 (rows are relative to the restriction)
+            double *xs = sm + (size_t)stage * STAGE;
+            mbar_wait(empty + stage, phase ^ 1);
+            FE_PROF_L(0);
+            if (x0row >= 1 && x0row + ROWS + 1 <= nrows && v0 + FE_TV <= nvec) {
+                // copy rows x0row - par .. of column lane: 16-byte aligned start, an even number of elements
+                const int par = col_parity(x0row, v0, lane);
+                const unsigned bytes = 8u * (unsigned)((ROWS + par + 1) & ~1);
+                const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+                if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
+                __syncwarp();
+                bulk_load(xs + lane * P0 + fe_swz(lane), X + (v0 + lane) * ldx + x0row - par, bytes, full + stage);
+            } else {
+                // clipped tile (the first and last of a vector group, partial vector groups): per-element cp.async so
+                // that all of the tile is in flight at once; rows / vectors outside are zero
+                for (int h = 0; h < FE_TV; ++h) {
+                    const i64 gv = v0 + h;
+                    double *xd = xs + h * P0 + fe_swz(h) + col_parity(x0row, v0, h);
+#pragma unroll
+                    for (int i = 0; i < (ROWS + 31) / 32; ++i) {
+                        const int r = lane + 32 * i;
+                        const i64 gr = x0row + r;
+                        if (r < ROWS) {
+                            if (gv < nvec && gr >= 0 && gr < nrows) cp_async8(xd + r, X + gv * ldx + gr);
+                            else xd[r] = 0.0;
+                        }
+                    }
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + stage);
+            }
+            FE_PROF_L(1);
+        }
+    } else {
+        // ================= storer warp: finished tiles out, lane <-> vector column ============
+        for (; vt < nvt; advance()) {
+            const i64 eA = et * ET, v0 = vt * FE_TV;
+            const i64 x0row = eA * (O - 1) - first0;
+            const double *xs = sm + (size_t)stage * STAGE;
+            mbar_wait(done + stage, phase);
+            FE_PROF_L(5);
+            if (eA > 0 && x0row >= 0 && x0row + ROWS <= nrows && v0 + FE_TV <= nvec && eA + ET + 1 <= nel && beta == 0.0) {
+                // rows 1..NR of column lane: one unaligned element at the head or the tail, the rest as a bulk copy
+                // (X and Y columns have the same parity, checked by the launcher)
+                const int par = col_parity(x0row, v0, lane);
+                const int q = par ^ 1;              // 1: row 1 is not 16-byte aligned
+                constexpr int NB = (NR - 1) & ~1;   // bulk elements: NR - q rounded down to even is NR-1 or NR (NR odd/even)
+                const int nb = (NR - q) & ~1;
+                const double *ys = xs + lane * P0 + fe_swz(lane) + par;
+                double *yc = Y + (v0 + lane) * ldy + x0row;
+                (void)NB;
+                bulk_store(yc + 1 + q, ys + 1 + q, 8u * (unsigned)nb);
+                bulk_commit();
+                if (q) yc[1] = ys[1];
+                if (1 + q + nb <= NR) yc[1 + q + nb] = ys[1 + q + nb];
+                bulk_wait_read0();
+            } else {
+                // rows owned by this tile: 1 .. (elements present)*(O-1), plus row 0 for the first tile
+                const int r_lo = (eA == 0) ? 0 : 1;
+                const i64 last_el = eA + ET < nel ? eA + ET : nel;
+                const int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
+                const double a1 = beta == 0.0 ? 1.0 : alpha;             // alpha is already in the tile when beta == 0
+                for (int h = 0; h < FE_TV; ++h) {
+                    const i64 gv = v0 + h;
+                    if (gv >= nvec) break;
+                    const double *ys = xs + h * P0 + fe_swz(h) + col_parity(x0row, v0, h);
+                    double *yc = Y + gv * ldy;
+#pragma unroll
+                    for (int i = 0; i < (ROWS + 31) / 32; ++i) {
+                        const int r = lane + 32 * i;
+                        const i64 gr = x0row + r;
+                        if (r >= r_lo && r < r_hi && gr >= 0 && gr < nrows) yc[gr] = axpby(ys[r], a1, beta, yc + gr);
+                    }
+                }
+            }
+            __syncwarp();                           // every lane has read its part of the tile
+            if (lane == 0) mbar_arrive(empty + stage);
+            FE_PROF_L(6);
+        }
+        bulk_wait0();
+    }
+#ifdef FEDVR_PHASE_PROF
+    if (lane == 0 && (w == 0 || w == NG || w == NG + 1))
+        for (int i = 0; i < 8; ++i) atomicAdd(&fe_prof[i], (unsigned long long)pf[i]);
+#endif
+}
+
 // Generic FE-DVR apply (per-element orders): thread per (row, vector); each row
 // gathers from the one or two elements that contain it.  rowmap[i] = element of
 // node i as owner (the element where it is NOT the first node, except node 0).
@@ -586,18 +1140,50 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
     constexpr int PITCH = fe_pitch(ROWS);
     constexpr size_t smem = sizeof(double) * ((size_t)NS * ((FE_TV * PITCH + 1) / 2 * 2) + (size_t)(2 * ET + 1) * FE_BRP);
     static_assert(smem <= 227 * 1024, "tile ring does not fit in shared memory");
+#if FEDVR_PIPE
+    // the TMA pipeline needs X and Y columns of equal 16-byte phase (see the kernel comment)
+    if (((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && ((ldx ^ ldy) & 1) == 0) {
+        using P = FePipe<O, NG>;
+        static_assert(P::NSTG >= 2, "tile ring does not fit in shared memory");
+        auto pk = fedvr_apply_pipe_kernel<O, NG>;
+        CB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+        const i64 ntiles = ((nel + P::ET - 1) / P::ET) * ((nvec + FE_TV - 1) / FE_TV);
+        const int pgrid = (int)(ntiles < CB_NUM_SMS ? ntiles : CB_NUM_SMS);
+        pk<<<pgrid, P::THREADS, P::SMEM, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
+#endif
+#if FEDVR_LEAN
+    static_assert(NS == 1, "the lean kernel has no tile ring");
+    auto kern = fedvr_apply_lean_kernel<O, NG>;
+#else
     auto kern = fedvr_apply_kernel<O, NG, NS>;
+#endif
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 2048 / (32 * NG)) per_sm = 2048 / (32 * NG);
-    if (per_sm < 1) per_sm = 1;
-    const i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? 4 : 1);   // pipelined: one persistent wave of CTAs
+    // CTAs the machine holds at once (registers limit this kernel to 3 per SM at NG = 16, not shared memory); the grid is
+    // a whole number of such waves so that no SM idles while the last CTAs finish
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int occ = 0;
+        CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NG, smem));
+        per_sm = occ < 1 ? 1 : occ;
+    }
+    const i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? FEDVR_WAVES : 1);   // pipelined: one persistent wave of CTAs
     int grid = (int)(tiles < cap ? tiles : cap);
     kern<<<grid, 32 * NG, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
+
+#ifdef FEDVR_PHASE_PROF
+extern "C" int cb_debug_fedvr_prof(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, fe_prof, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(fe_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" {
 
@@ -662,9 +1248,18 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     // vector tiles per work item: amortise the band-tile staging while keeping >= ~8 items per SM
     i64 vchunk = nrt * nvt / ((i64)CB_NUM_SMS * 8);
     vchunk = vchunk < 1 ? 1 : (vchunk > 8 ? 8 : vchunk);          // 3..8 measured within 2% of each other, 1-2 slower
-    const i64 items = nrt * ((nvt + vchunk - 1) / vchunk);
-    int grid = (int)(items < (i64)CB_NUM_SMS * 24 ? items : (i64)CB_NUM_SMS * 24);
-    banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, (int)vchunk, alpha, beta, Y, ldy);
+    // big items first, then single-tile items for the last ~BT_TAIL_PCT % of the vector tiles (tail balancing: one CTA
+    // per item, handed out in order by the hardware)
+    i64 nvc_big = nvt / vchunk;
+    if (vchunk > 1) {
+        const i64 tail = (nvt * BT_TAIL_PCT + 99) / 100;
+        const i64 big = nvt - tail;                                // vector tiles covered by the big items
+        if (big < vchunk) vchunk = big < 1 ? 1 : big;
+        nvc_big = big < 1 ? 0 : big / vchunk;
+    }
+    const i64 items = nrt * (nvc_big + (nvt - nvc_big * vchunk));
+    int grid = (int)(items < (i64)CB_NUM_SMS * BT_GRIDCAP ? items : (i64)CB_NUM_SMS * BT_GRIDCAP);
+    banded_apply_kernel<<<grid, BT_THREADS, smem, (cudaStream_t)stream>>>(band, m, n, l, u, X, ldx, nvec, (int)vchunk, nvc_big, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -68,3 +68,11 @@ for _ in range(NT):
 e1.record(); torch.cuda.synchronize()
 per = e0.elapsed_time(e1) / NT / (20 if what == "asm3k" else 1)
 print(what, "ms", per, "(mean of back-to-back calls)")
+if os.environ.get("PROF_TIME"):
+    ts = []
+    for _ in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / (20 if what == "asm3k" else 1))
+    ts.sort()
+    print(f"{what}: mean-b2b {per*1e3:.1f} us  min {ts[0]*1e3:.1f} us  med {ts[len(ts)//2]*1e3:.1f} us")
