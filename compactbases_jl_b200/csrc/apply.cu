@@ -234,6 +234,85 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // ---------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives of the warp-specialised pipelines (K7, K8).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// global -> shared bulk copy (TMA unit), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global bulk copy
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(__cvta_generic_to_global(gdst)), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// orders this thread's shared-memory writes before later accesses by the TMA unit (async proxy)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Column swizzle of the pipelines' tiles: col(v) = v * P0 + fe_swz(v) with P0 = 0 (mod 16).
+__host__ __device__ constexpr int fe_swz(int v) { return 4 * ((v & 3) ^ ((v >> 2) & 1)); }
+
+// One column of a pipeline tile through the TMA unit, executed by the loader / storer warp with lane <-> column.
+// scol[r] / gcol[r] address row r of the column in shared / global memory; shared offset and global address have the
+// same parity (the tile is laid out that way), so the 16-byte aligned part of rows [ra, rb) is one bulk copy and at
+// most one element at either end moves through the lane.  Rows outside [ra, rb) (outside the matrix, or a vector
+// beyond the batch: ra == rb) are zero-filled up to nrows_tile.
+//   phase 1 (tma_col_load_prepare): zero fill, end elements, returns the bytes the bulk copy will bring;
+//   the caller sums them over the warp, arms the mbarrier (release: the plain stores above become visible with it);
+//   phase 2 (tma_col_load_issue): the bulk copy.
+struct ColPlan { int a, cnt; };
+__device__ __forceinline__ ColPlan col_plan(int par0, int ra, int rb) {
+    ColPlan p;
+    p.a = ra + ((par0 + ra) & 1);                   // first 16-byte aligned row
+    p.cnt = rb > p.a ? (rb - p.a) & ~1 : 0;
+    return p;
+}
+__device__ __forceinline__ ColPlan tma_col_load_prepare(double *scol, const double *gcol, int par0, int ra, int rb,
+                                                        int nrows_tile) {
+    const ColPlan p = col_plan(par0, ra, rb);
+    for (int r = 0; r < ra; ++r) scol[r] = 0.0;
+    for (int r = rb; r < nrows_tile; ++r) scol[r] = 0.0;
+    if (p.a > ra && ra < rb) scol[ra] = gcol[ra];
+    for (int r = p.a + p.cnt; r < rb; ++r) scol[r] = gcol[r];       // at most one row (two when the range is short)
+    return p;
+}
+__device__ __forceinline__ void tma_col_store(double *gcol, const double *scol, int par0, int ra, int rb) {
+    const ColPlan p = col_plan(par0, ra, rb);
+    if (p.cnt) bulk_store(gcol + p.a, scol + p.a, 8u * (unsigned)p.cnt);
+    bulk_commit();
+    if (p.a > ra && ra < rb) gcol[ra] = scol[ra];
+    for (int r = p.a + p.cnt; r < rb; ++r) gcol[r] = scol[r];
+    bulk_wait_read0();
+}
+
+// ---------------------------------------------------------------------------
 // K7: BandedMatrix (l,u).  CTA tile: BT_ROWS rows x 32 vectors, x window staged in shared memory.
 // The product runs on the FP64 tensor cores: an 8-row block of A against its window of
 // 8 + l + u columns is KS = ceil((8+l+u)/4) DMMA k-steps per 8-vector tile.  The band tile is
@@ -255,6 +334,11 @@ constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
 #ifndef BT_TAIL_PCT
 #define BT_TAIL_PCT 0                               // share of the vector tiles handed out as single-tile items at the end
 #endif
+#ifndef BT_PIPE
+#define BT_PIPE 1
+#endif
+constexpr int BT_KSMAX = 8;                         // k-steps the pipelined kernel supports (l + u + 1 <= 25)
+constexpr int BT_NAV = (BT_ROWS / 8) * BT_KSMAX * 32 / (32 * BT_NG);   // A-fragment entries per compute thread
 #ifndef BT_GRIDCAP
 #define BT_GRIDCAP 1024                             // CTAs per SM in the grid at most (items beyond that are strided)
 #endif
@@ -341,200 +425,253 @@ banded_apply_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
     }
 }
 
+#ifdef FEDVR_PHASE_PROF
+__device__ unsigned long long fe_prof[8];
+#define FE_PROF_T(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
+#define FE_PROF_L(i) do { if (lane == 0 && (w == 0 || w == PROF_NG || w == PROF_NG + 1)) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
+#else
+#define FE_PROF_T(i) do { } while (0)
+#define FE_PROF_L(i) do { } while (0)
+#endif
+// ---------------------------------------------------------------------------
+// K7, warp-specialised TMA pipeline (same structure as the K8 pipeline below, which has the measurements): one
+// persistent CTA per SM; a loader warp keeps a ring of x windows filled with one bulk copy per vector column, BT_NG
+// compute warps multiply a window by the band tile's A fragments (staged once per work item) and write the 128 result
+// rows over the window in place (rows l .. l+127 of the window are the tile's own rows), a storer warp streams them
+// out with bulk copies.  Work item = (row tile, chunk of vector tiles) as in banded_apply_kernel; items are dealt
+// round-robin to the CTAs.  Columns whose window starts on an odd element are copied from one element earlier
+// (16-byte alignment of bulk copies): window row r of column v sits at xs[col(v) + par_v + r].  Requires l, u >= 0,
+// l + u + 1 <= 25, beta == 0 and X, Y of equal 16-byte phase per column; the launcher falls back to
+// banded_apply_kernel otherwise.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * (BT_NG + 2), 1)
+banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
+                         const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk, int P0, int nstg,
+                         double alpha, double beta, double *__restrict__ Y, i64 ldy) {
+    extern __shared__ __align__(128) double sm[];
+    const int W = l + u + 1;
+    const int KS = (8 + W - 1 + 3) / 4;             // k-steps per 8-row block
+    const int xrows = BT_ROWS + l + u;
+    const int wrows = xrows + 3;                    // + the k padding of the last row block
+    const int STAGE = BT_VEC * P0;
+    double *as = sm + (size_t)nstg * STAGE;         // [BT_ROWS/8][KS][32] A fragments of the current item
+    uint64_t *bars = reinterpret_cast<uint64_t *>(as + (BT_ROWS / 8) * KS * 32);
+    uint64_t *full = bars, *done = bars + nstg, *empty = bars + 2 * nstg;
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstg; ++s) { mbar_init(full + s, 1); mbar_init(done + s, BT_NG); mbar_init(empty + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
+    const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
+    const i64 nvc = (nvt + vchunk - 1) / vchunk;
+    const i64 nitems = nrt * nvc;
+    const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);
+    int stage = 0;
+    unsigned phase = 0;
+    constexpr int PROF_NG = BT_NG; (void)PROF_NG;
+#ifdef FEDVR_PHASE_PROF
+    long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    auto next_stage = [&]() { if (++stage == nstg) { stage = 0; phase ^= 1; } };
+    // parity shift of column v: window row r (matrix column g0 + r) of vector v sits at xs[col(v) + par + r]
+    auto col_parity = [&](i64 g0, i64 v) { return (int)((xbase + v * ldx + g0) & 1); };
+    if (w < BT_NG) {
+        // ================= compute warps ======================================================
+        const int gq = lane >> 2, tq = lane & 3;
+        const double wscale = alpha;                // beta == 0 (launcher): alpha is folded into the tile
+        // A fragments of a row tile: as[rb][ks][lane] = A(i0 + 8rb + g, i0 + 8rb - l + 4ks + t), 0 outside band/matrix.
+        // Each thread fetches its BT_NAV entries of the NEXT item into registers while the last vector tile of the
+        // current item is multiplied, so the band's memory latency is off the tile loop.
+        double av[BT_NAV];
+        auto fetch_frags = [&](i64 item_) {
+            const i64 vc_ = item_ / nrt, i0_ = (item_ - vc_ * nrt) * BT_ROWS;
+#pragma unroll
+            for (int t = 0; t < BT_NAV; ++t) {
+                const int e = threadIdx.x + t * 32 * BT_NG;
+                const int ln = e & 31, ks = (e >> 5) % KS, rb = (e >> 5) / KS;
+                const i64 i = i0_ + 8 * rb + (ln >> 2), j = i0_ + 8 * rb - l + 4 * ks + (ln & 3);
+                av[t] = (e < (BT_ROWS / 8) * KS * 32 && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
+                            ? __ldg(band + (u + i - j) + (i64)W * j) : 0.0;
+            }
+        };
+        if ((i64)blockIdx.x < nitems) fetch_frags(blockIdx.x);
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;              // row tiles vary fastest (contiguous streams)
+            const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
+            named_bar_sync(1, 32 * BT_NG);          // the previous item's fragments are no longer read
+#pragma unroll
+            for (int t = 0; t < BT_NAV; ++t) {
+                const int e = threadIdx.x + t * 32 * BT_NG;
+                if (e < (BT_ROWS / 8) * KS * 32) as[e] = av[t];
+            }
+            named_bar_sync(1, 32 * BT_NG);
+            FE_PROF_L(7);
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const i64 v0 = vt * BT_VEC;
+                double *xs = sm + (size_t)stage * STAGE;
+                const int par_r = col_parity(g0, v0 + gq);
+                const int par_c0 = col_parity(g0, v0 + 2 * tq), par_c1 = col_parity(g0, v0 + 2 * tq + 1);
+                if (vt + 1 == vt_end && item + gridDim.x < nitems) fetch_frags(item + gridDim.x);
+                mbar_wait(full + stage, phase);
+                FE_PROF_L(2);
+                // A dependent DMMA has ~180 cycles of latency: the k-steps of the warp's BT_RB row blocks advance
+                // together, BT_RB * 4 independent accumulator chains in flight
+                double c[BT_RB][BT_VEC / 8][2];
+#pragma unroll
+                for (int q = 0; q < BT_RB; ++q)
+#pragma unroll
+                    for (int nt = 0; nt < BT_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
+                {
+                    const double *af = as + w * BT_RB * KS * 32 + lane;
+                    const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * w * BT_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
+                    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                        for (int q = 0; q < BT_RB; ++q) {
+                            const double a = af[(q * KS + ks) * 32];
+#pragma unroll
+                            for (int nt = 0; nt < BT_VEC / 8; ++nt)
+                                dmma884(c[q][nt][0], c[q][nt][1], a, xb[q * 8 + nt * 8 * P0 + 4 * ks]);
+                        }
+                    }
+                }
+                FE_PROF_L(3);
+                named_bar_sync(1, 32 * BT_NG);      // every warp has read the window
+                FE_PROF_L(4);
+#pragma unroll
+                for (int q = 0; q < BT_RB; ++q) {
+                    const int row = l + (w * BT_RB + q) * 8 + gq;         // window row of the output row
+                    double *y0 = xs + (2 * tq) * P0 + fe_swz(2 * tq) + par_c0 + row;
+                    double *y1 = xs + (2 * tq + 1) * P0 + fe_swz(2 * tq + 1) + par_c1 + row;
+#pragma unroll
+                    for (int nt = 0; nt < BT_VEC / 8; ++nt) {
+                        y0[nt * 8 * P0] = wscale * c[q][nt][0];
+                        y1[nt * 8 * P0] = wscale * c[q][nt][1];
+                    }
+                }
+                fence_proxy_async();                // the storer's bulk copies read what this thread wrote
+                __syncwarp();
+                if (lane == 0) mbar_arrive(done + stage);
+                FE_PROF_L(7);
+            }
+        }
+    } else if (w == BT_NG) {
+        // ================= loader warp: lane <-> vector column ================================
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;
+            const i64 g0 = rt * BT_ROWS - l;        // matrix column of window row 0
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const i64 v0 = vt * BT_VEC;
+                double *xs = sm + (size_t)stage * STAGE;
+                mbar_wait(empty + stage, phase ^ 1);
+                FE_PROF_L(0);
+                if (g0 >= 1 && g0 + wrows + 1 <= n && v0 + BT_VEC <= nvec) {
+                    const int par = col_parity(g0, v0 + lane);
+                    const unsigned bytes = 8u * (unsigned)((wrows + par + 1) & ~1);
+                    const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+                    if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
+                    __syncwarp();
+                    bulk_load(xs + lane * P0 + fe_swz(lane), X + (v0 + lane) * ldx + g0 - par, bytes, full + stage);
+                } else {
+                    // clipped window (first / last row tiles, partial vector tile): valid rows through the TMA unit as
+                    // well, the rest zero
+                    const bool vok = v0 + lane < nvec;
+                    const int par = col_parity(g0, v0 + lane);
+                    int ra = g0 < 0 ? (int)(-g0 < wrows ? -g0 : wrows) : 0;
+                    int rb = g0 + wrows > n ? (int)(n - g0 > ra ? n - g0 : ra) : wrows;
+                    if (!vok) { ra = 0; rb = 0; }
+                    double *scol = xs + lane * P0 + fe_swz(lane) + par;
+                    const double *gcol = X + (vok ? v0 + lane : 0) * ldx + g0;
+                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, wrows);
+                    const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
+                    __syncwarp();
+                    if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
+                    __syncwarp();
+                    if (cp.cnt) bulk_load(scol + cp.a, gcol + cp.a, 8u * (unsigned)cp.cnt, full + stage);
+                }
+                FE_PROF_L(1);
+            }
+        }
+    } else {
+        // ================= storer warp: lane <-> vector column ================================
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;
+            const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const i64 v0 = vt * BT_VEC;
+                const double *xs = sm + (size_t)stage * STAGE;
+                mbar_wait(done + stage, phase);
+                FE_PROF_L(5);
+                {
+                    // rows i0 .. of column lane: the 16-byte aligned part as a bulk copy, an odd end element through the
+                    // lane (X, Y and the window have the same parity per column, checked by the launcher)
+                    const bool vok = v0 + lane < nvec;
+                    const int par = col_parity(g0, v0 + lane);
+                    const int r_hi = !vok ? 0 : m - i0 < BT_ROWS ? (int)(m - i0) : BT_ROWS;
+                    const double *ys = xs + lane * P0 + fe_swz(lane) + par + l;
+                    double *yc = Y + (vok ? v0 + lane : 0) * ldy + i0;
+                    tma_col_store(yc, ys, par + l, 0, r_hi);
+                }
+                __syncwarp();                       // every lane has read its part of the tile
+                if (lane == 0) mbar_arrive(empty + stage);
+                FE_PROF_L(6);
+            }
+        }
+        bulk_wait0();
+    }
+#ifdef FEDVR_PHASE_PROF
+    if (lane == 0 && (w == 0 || w == PROF_NG || w == PROF_NG + 1))
+        for (int i = 0; i < 8; ++i) atomicAdd(&fe_prof[i], (unsigned long long)pf[i]);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // K8: FE-DVR element-block operator, uniform order O (compile time).
 //
-// Persistent CTAs of NG warps with an NS-stage shared-memory ring of x tiles.  A tile is ET = NG - 1
-// elements x 32 vectors; tile rows (local r <-> global node eA*(O-1) + r): elements eA..eA+ET-1 occupy
-// rows 0..ET*(O-1), the halo element eA+ET — needed for the last bridge row — adds O-1 more.  Warp g
-// owns element eA + g (the last warp: row 0 of the halo element).  Per tile: the warp fetches its
-// O x O block straight from global memory (L2-resident, 8 MB at C2) into FP64 tensor-core A
-// fragments — the fetch is in flight together with the cp.async copies of the x rows — then multiplies
-// in place (DMMA 8x8x4: block fragments x four 8-vector tiles); the bridge rows shared by neighbouring
-// elements are summed from two side buffers and the tile is streamed out by a coalesced mover.
-// Lanes of the B operand run over vectors, so x reads are conflict-free (odd pitch) column reads.
+// A tile is ET = NG - 1 elements x 32 vectors; tile rows (local r <-> global node eA*(O-1) + r): elements
+// eA..eA+ET-1 occupy rows 0..ET*(O-1), the halo element eA+ET — needed for the last bridge row — adds O-1 more.
+// Warp g owns element eA + g (the last warp: row 0 of the halo element).  Per tile the warp fetches its O x O block
+// straight from global memory (L2-resident, 8 MB at C2) into FP64 tensor-core A fragments, multiplies in place
+// (DMMA 8x8x4: block fragments x four 8-vector tiles); the bridge rows shared by neighbouring elements are summed
+// from two side buffers.  Two kernels share this arithmetic: the warp-specialised TMA pipeline (default) and the
+// "lean" kernel whose warps load, compute and store in turn (fallback when X and Y differ in 16-byte phase).
+//
+// History of the design, device time of one C2 apply (order 10, 1e4 elements, 1024 vectors) on B200:
+//   DFMA compute, blocks staged in shared memory per tile: 458 us;  DMMA compute, one element per warp, 16 warps: 386;
+//   block fragments from global, even x-tile pitch: 368 (movers only: 289);  fragments kept for 2/4/8 vector tiles:
+//   398/432/483;  half of the DMMAs removed: 379;  accumulators stored straight to global: 476;  cp.async tile ring of
+//   2/3 stages per CTA: 390/520;  grid of 1/2/3/6 waves of resident CTAs: 381/371/363/362;  instruction count halved
+//   (lean kernel): 364;  warp-specialised with cp.async loader and LDS/STG storer warps: 378-409 (the movers fill the
+//   LSU queue the compute warps' LDS/STS need);  warp-specialised with TMA bulk copies: 267.
 // ---------------------------------------------------------------------------
 constexpr int FE_TV = 32;                           // vectors per tile (one warp wide)
 constexpr int FE_BRP = FE_TV + 1;                   // pitch of the bridge buffers
-// Measured on B200 (C2: order 10, 1e4 elements, 1024 vectors; device time of one apply):
-//   DFMA compute, blocks staged in shared memory per tile, (elements/thread) x warps x stages:
-//                 4x4x1: 458 us | 2x4x1: 460 | 1x8x3: 504 | 1x4x3: 584 | 1x8x6: 718
-//   DMMA compute, blocks staged per tile, (elements per warp) x (warps) = 1x16: 386-404 us | 2x8: 420 |
-//                 1x12: 423 | 3x8: 478 | 4x4: 495 | 2x16: 612;  movers only (no compute): 341 us
-//   DMMA compute, block fragments from global per tile, 15 elements + halo warp: 385 us (movers only: 289 us);
-//                 fragments kept for 2 / 4 / 8 vector tiles of the same elements: 398 / 432 / 483 us (the CTAs
-//                 running at one time then touch 2-8x as many columns of X and Y); half of the DMMAs
-//                 removed: 379 us (not FP64-bound); accumulator fragments stored straight to global
-//                 (64-byte pieces) instead of through the tile: 476 us; DMMA chains of 2 / 4 vector tiles interleaved
-//                 (a dependent DMMA has ~180 cycles of latency): 417 / 445-525 us (registers);
-//                 x-tile pitch odd -> even (any of 2, 4, 6, 12 mod 16): 386 -> 368 us.
 #ifndef FEDVR_NG
 #define FEDVR_NG 16
 #endif
 #ifndef FE_PITCH_MOD
 #define FE_PITCH_MOD 12
 #endif
-// Pitch of the x tile: = FE_PITCH_MOD (mod 16) doubles.  The B-fragment reads (lane (gq, tq) reads column gq, row 4ks + tq)
-// are bank-conflict free for 12 (mod 16); the movers run along the rows and do not care.
+// Pitch of the lean kernel's x tile: = FE_PITCH_MOD (mod 16) doubles.  The B-fragment reads (lane (gq, tq) reads column
+// gq, row 4ks + tq) are bank-conflict free for 12 (mod 16); the movers run along the rows and do not care.
 __host__ __device__ constexpr int fe_pitch(int rows) { return FE_PITCH_MOD < 0 ? (rows | 1) : rows + ((FE_PITCH_MOD - rows) % 16 + 16) % 16; }
-#ifndef FEDVR_NS
-#define FEDVR_NS 1
-#endif
 #ifndef FEDVR_MINB
 #define FEDVR_MINB 3
-#endif
-#ifndef FEDVR_LEAN
-#define FEDVR_LEAN 1
 #endif
 #ifndef FEDVR_PIPE
 #define FEDVR_PIPE 1
 #endif
 #ifndef FEDVR_WAVES
-#define FEDVR_WAVES 4                               // waves of resident CTAs in the grid (NS == 1)
-#endif
-#ifndef FE_NTI
-#define FE_NTI 1                                    // vector tiles (of 8) whose DMMA chains are interleaved
+#define FEDVR_WAVES 4                               // waves of resident CTAs in the lean kernel's grid
 #endif
 
-template <int O, int NG, int NS>
-__global__ void __launch_bounds__(32 * NG, (NG <= 8 ? 4 : NG <= 16 ? FEDVR_MINB : 1))
-fedvr_apply_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /*0-based first function*/, i64 nrows,
-                   const double *__restrict__ X, i64 ldx, i64 nvec,
-                   double alpha, double beta, double *__restrict__ Y, i64 ldy) {
-    constexpr int THREADS = 32 * NG;
-    constexpr int ET = NG - 1;                      // elements per tile
-    constexpr int ROWS = (ET + 1) * (O - 1) + 1;    // incl. halo element
-    constexpr int PITCH = fe_pitch(ROWS);
-    constexpr int STAGE = (FE_TV * PITCH + 1) / 2 * 2;
-    constexpr int MT = (O + 7) / 8, KS = (O + 3) / 4;
-    extern __shared__ __align__(16) double sm[];
-    double *br0 = sm + NS * STAGE;                  // [(ET+1)][33] first-row products (bridge contributions)
-    double *br9 = br0 + (ET + 1) * FE_BRP;          // [ET][33]     last-row products
-    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-    const i64 net = (nel + ET - 1) / ET;
-    const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
-    const i64 ntiles = net * nvt;
-    // tile -> coordinates; element tiles vary fastest so that the CTAs running at one time stream
-    // long contiguous row ranges of a few vector groups
-    auto coords = [&](i64 tile, i64 &eA, i64 &v0, i64 &x0row, bool &interior) {
-        const i64 vt = tile / net, et = tile - vt * net;
-        eA = et * ET;
-        v0 = vt * FE_TV;
-        x0row = eA * (O - 1) - first0;              // X/Y row of tile row 0 (rows are relative to the restriction)
-        interior = x0row >= 0 && x0row + ROWS <= nrows && v0 + FE_TV <= nvec && eA + ET + 1 <= nel;
-    };
-    auto issue = [&](i64 tile, int st) {            // always commits one cp.async group
-        if (tile < ntiles) {
-            double *xs_ = sm + st * STAGE;
-            i64 eA, v0, x0row; bool interior;
-            coords(tile, eA, v0, x0row, interior);
-            if (interior) load_tile_async<ROWS, FE_TV, NG>(xs_, PITCH, X, ldx, x0row, v0);
-            else load_tile<THREADS>(xs_, PITCH, X, ldx, nrows, x0row, ROWS, v0, FE_TV, nvec);
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int p = 0; p < NS - 1; ++p) issue((i64)blockIdx.x + (i64)p * gridDim.x, p);
-    int stage = 0;
-    for (i64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        {   // the stage freed at the end of the previous iteration receives the tile NS-1 ahead
-            // (NS == 1: this tile itself; other resident CTAs cover the wait)
-            int st = stage + NS - 1; if (st >= NS) st -= NS;
-            issue(tile + (i64)(NS - 1) * gridDim.x, st);
-        }
-        i64 eA, v0, x0row; bool interior;
-        coords(tile, eA, v0, x0row, interior);
-        // ---- block fragments: a = B_e[mm = gq + 8 mt][mp = 4 ks + tq] (last warp: only the first 8 rows, of which
-        // row 0 is used).  Operands outside the block are zero rather than multiplied by zero, so Inf/NaN cannot leak.
-        double af[MT][KS];
-        {
-            const double *b = blocks + (eA + g) * (O * O);
-            const bool have = eA + g < nel;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int mm = gq + 8 * mt, mp = 4 * ks + tq;
-                    af[mt][ks] = (have && mm < O && mp < O && (g < ET || mt == 0)) ? __ldg(b + mp * O + mm) : 0.0;
-                }
-        }
-        cp_async_wait<NS - 1>();                    // this tile's group has landed
-        __syncthreads();
-        double *xs = sm + stage * STAGE;
-#ifndef FEDVR_SKIP_COMPUTE
-        // ---- compute: y_e = B_e x_e on the FP64 tensor cores --------------------------------
-        // Rows 1..O-2 are written in place (no other warp reads them); rows 0 and O-1 are
-        // contributions to the bridge rows shared with the neighbouring elements and go to the side
-        // buffers that are summed after the barrier.
-        // A dependent DMMA has a latency of ~180 cycles on B200 (scripts/micro/dmma_lat.cu) against 8 for a
-        // DFMA, so the k-steps of FE_NTI vector tiles are interleaved: FE_NTI * MT independent accumulator
-        // chains are in flight per warp.
-#pragma unroll
-        for (int np = 0; np < FE_TV / 8; np += FE_NTI) {
-            double c[FE_NTI][MT][2];
-#pragma unroll
-            for (int i = 0; i < FE_NTI; ++i)
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] = 0.0; c[i][mt][1] = 0.0; }
-            const double *xe = xs + (8 * np + gq) * PITCH + g * (O - 1) + tq;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                double bf[FE_NTI];
-#pragma unroll
-                for (int i = 0; i < FE_NTI; ++i) bf[i] = (4 * ks + tq < O) ? xe[i * 8 * PITCH + 4 * ks] : 0.0;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int i = 0; i < FE_NTI; ++i)
-                        if (mt == 0 || g < ET) dmma884(c[i][mt][0], c[i][mt][1], af[mt][ks], bf[i]);
-            }
-            __syncwarp();                                        // all lanes have read these vector tiles' x rows
-#pragma unroll
-            for (int i = 0; i < FE_NTI; ++i) {
-                const int v = 8 * (np + i) + 2 * tq;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int mm = gq + 8 * mt;
-                    if (mm == 0) { br0[g * FE_BRP + v] = c[i][mt][0]; br0[g * FE_BRP + v + 1] = c[i][mt][1]; }
-                    else if (g < ET && mm == O - 1) { br9[g * FE_BRP + v] = c[i][mt][0]; br9[g * FE_BRP + v + 1] = c[i][mt][1]; }
-                    else if (g < ET && mm < O - 1) {
-                        xs[v * PITCH + g * (O - 1) + mm] = c[i][mt][0];
-                        xs[(v + 1) * PITCH + g * (O - 1) + mm] = c[i][mt][1];
-                    }
-                }
-            }
-        }
-#endif
-        __syncthreads();
-        // bridge rows: last row of element e-1 plus first row of element e; global row 0 has no previous element
-        for (int i = threadIdx.x; i < (ET + 1) * FE_TV; i += THREADS) {
-            const int eL = i / FE_TV, v = i - eL * FE_TV;
-            if (eL == 0) { if (eA == 0) xs[v * PITCH] = br0[v]; }
-            else xs[v * PITCH + eL * (O - 1)] = br9[(eL - 1) * FE_BRP + v] + br0[eL * FE_BRP + v];
-        }
-        __syncthreads();
-        // rows owned by this tile: 1 .. ET*(O-1), plus row 0 for the first tile
-        const int r_lo = (eA == 0) ? 0 : 1;
-        const i64 last_el = eA + ET < nel ? eA + ET : nel;            // elements actually present
-        const int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
-        if (interior && beta == 0.0) store_tile_fast<FE_TV, NG>(xs, PITCH, Y, ldy, x0row, r_lo, r_hi, v0, alpha);
-        else store_tile<THREADS>(xs, PITCH, Y, ldy, nrows, x0row, r_lo, r_hi, v0, FE_TV, nvec, alpha, beta);
-        __syncthreads();                            // the stage may be refilled
-        if (++stage == NS) stage = 0;
-    }
-    cp_async_wait<0>();
-}
-
-#ifdef FEDVR_PHASE_PROF
-__device__ unsigned long long fe_prof[8];
-#define FE_PROF_T(i) do { if (threadIdx.x == 0) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
-#define FE_PROF_L(i) do { if (lane == 0 && (w == 0 || w == NG || w == NG + 1)) { long long t__ = clock64(); pf[i] += t__ - tprev; tprev = t__; } } while (0)
-#else
-#define FE_PROF_T(i) do { } while (0)
-#define FE_PROF_L(i) do { } while (0)
-#endif
-// K8, lean form.  Same tiling and arithmetic as fedvr_apply_kernel (NS = 1); what changed is the instruction count:
-// the ncu source page of that kernel (profiles/r1t) showed 10.5 k warp instructions per tile of which ~1.4 k were the
+// K8, lean form.  Its predecessor spent most of its issue slots on bookkeeping:
+// the ncu source page (profiles/r1t) showed 10.5 k warp instructions per tile of which ~1.4 k were the
 // copies, DMMAs and fragment traffic — the rest was 64-bit tile arithmetic done twice per tile, divergence bookkeeping
 // around every predicated DMMA (the warp index was not known to be warp-uniform), runtime-bounded mover loops and
 // three-way branches in the write-back.  Here interior tiles (every element, row and vector present, beta == 0, not
@@ -754,52 +891,13 @@ fedvr_apply_lean_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
 // a column whose tile starts on an odd element is copied from one element earlier, i.e. tile row r of column v sits
 // at xs[col(v) + p_v + r] with p_v the parity of the element address; the storer writes the one unaligned element at
 // the head or tail of each column with an ordinary store.  X and Y must have the same parity per column (same
-// alignment class and leading dimensions of equal parity), otherwise the launcher takes the lean kernel.
+// alignment class and leading dimensions of equal parity) and beta must be 0 (bulk stores do not read Y), otherwise
+// the launcher takes the lean kernel.
 //
 // Tile columns are swizzled, col(v) = v * P0 + 4 * ((v & 3) ^ ((v >> 2) & 1)) with P0 = 0 (mod 16): the B-fragment
 // reads (lane (gq, tq): column gq, row 4 ks + tq) and the accumulator write-back (rows gq, columns 2 tq, 2 tq + 1)
 // are then free of bank conflicts per half-warp up to the parity shift, which no plain pitch achieves.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// global -> shared bulk copy (TMA unit), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(sdst)), "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// shared -> global bulk copy
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(__cvta_generic_to_global(gdst)), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// orders this thread's shared-memory writes before later accesses by the TMA unit (async proxy)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 #ifndef FEDVR_PNTI
 #define FEDVR_PNTI 4                                // 8-vector tiles whose DMMA chains are interleaved
 #endif
@@ -821,7 +919,6 @@ template <int O, int NG> struct FePipe {
     static constexpr int NSTG = max_stages();
     static constexpr size_t SMEM = (size_t)NSTG * STAGE * 8 + 2 * BR * 8 + 256;
 };
-__host__ __device__ constexpr int fe_swz(int v) { return 4 * ((v & 3) ^ ((v >> 2) & 1)); }
 
 template <int O, int NG>
 __global__ void __launch_bounds__(FePipe<O, NG>::THREADS, 1)
@@ -831,6 +928,7 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
     using P = FePipe<O, NG>;
     constexpr int ET = P::ET, ROWS = P::ROWS, P0 = P::P0, STAGE = P::STAGE, NSTG = P::NSTG, MT = P::MT, KS = P::KS;
     constexpr int NR = ET * (O - 1);                // rows an interior tile owns: tile rows 1 .. NR
+    constexpr int PROF_NG = NG; (void)PROF_NG;
     extern __shared__ __align__(128) double sm[];
     double *brbuf = sm + (size_t)NSTG * STAGE;      // [2][br0 (ET+1) x 33 | br9 ET x 33]
     uint64_t *bars = reinterpret_cast<uint64_t *>(brbuf + 2 * P::BR);    // full[NSTG], done[NSTG], empty[NSTG]
@@ -868,7 +966,7 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
         const int g = w, gq = lane >> 2, tq = lane & 3;
         const int swz_r = fe_swz(gq);               // column skew of the B-fragment reads (vector 8 np + gq)
         const int swz_c0 = fe_swz(2 * tq), swz_c1 = fe_swz(2 * tq + 1);   // of the accumulator columns 8 np + 2 tq (+ 1)
-        const double wscale = beta == 0.0 ? alpha : 1.0;   // alpha is folded into the tile when Y is not read
+        const double wscale = alpha;                // beta == 0 (launcher): alpha is folded into the tile
         int parity = 0;                             // bridge buffer set
         // block fragments a = B_e[gq + 8 mt][4 ks + tq], zero outside the block / beyond the last element; the
         // fragments of the next tile are requested as soon as the last DMMA of this one has been issued, so their L2
@@ -985,25 +1083,21 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
                 __syncwarp();
                 bulk_load(xs + lane * P0 + fe_swz(lane), X + (v0 + lane) * ldx + x0row - par, bytes, full + stage);
             } else {
-                // clipped tile (the first and last of a vector group, partial vector groups): per-element cp.async so
-                // that all of the tile is in flight at once; rows / vectors outside are zero
-                for (int h = 0; h < FE_TV; ++h) {
-                    const i64 gv = v0 + h;
-                    double *xd = xs + h * P0 + fe_swz(h) + col_parity(x0row, v0, h);
-#pragma unroll
-                    for (int i = 0; i < (ROWS + 31) / 32; ++i) {
-                        const int r = lane + 32 * i;
-                        const i64 gr = x0row + r;
-                        if (r < ROWS) {
-                            if (gv < nvec && gr >= 0 && gr < nrows) cp_async8(xd + r, X + gv * ldx + gr);
-                            else xd[r] = 0.0;
-                        }
-                    }
-                }
-                cp_async_commit();
-                cp_async_wait<0>();
+                // clipped tile (the first and last of a vector group, partial vector groups): valid rows through the TMA
+                // unit as well, the rest zero
+                const bool vok = v0 + lane < nvec;
+                const int par = col_parity(x0row, v0, lane);
+                int ra = x0row < 0 ? (int)(-x0row < ROWS ? -x0row : ROWS) : 0;
+                int rb = x0row + ROWS > nrows ? (int)(nrows - x0row > ra ? nrows - x0row : ra) : ROWS;
+                if (!vok) { ra = 0; rb = 0; }
+                double *scol = xs + lane * P0 + fe_swz(lane) + par;
+                const double *gcol = X + (vok ? v0 + lane : 0) * ldx + x0row;
+                const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, ROWS);
+                const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full + stage);
+                if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
+                __syncwarp();
+                if (cp.cnt) bulk_load(scol + cp.a, gcol + cp.a, 8u * (unsigned)cp.cnt, full + stage);
             }
             FE_PROF_L(1);
         }
@@ -1015,39 +1109,20 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
             const double *xs = sm + (size_t)stage * STAGE;
             mbar_wait(done + stage, phase);
             FE_PROF_L(5);
-            if (eA > 0 && x0row >= 0 && x0row + ROWS <= nrows && v0 + FE_TV <= nvec && eA + ET + 1 <= nel && beta == 0.0) {
-                // rows 1..NR of column lane: one unaligned element at the head or the tail, the rest as a bulk copy
-                // (X and Y columns have the same parity, checked by the launcher)
+            {
+                // rows owned by this tile: 1 .. (elements present)*(O-1), plus row 0 for the first tile, clipped to the
+                // restriction; the 16-byte aligned part of column lane as a bulk copy, an odd end element through the
+                // lane (X and Y columns have the same parity, checked by the launcher)
+                const bool vok = v0 + lane < nvec;
                 const int par = col_parity(x0row, v0, lane);
-                const int q = par ^ 1;              // 1: row 1 is not 16-byte aligned
-                constexpr int NB = (NR - 1) & ~1;   // bulk elements: NR - q rounded down to even is NR-1 or NR (NR odd/even)
-                const int nb = (NR - q) & ~1;
-                const double *ys = xs + lane * P0 + fe_swz(lane) + par;
-                double *yc = Y + (v0 + lane) * ldy + x0row;
-                (void)NB;
-                bulk_store(yc + 1 + q, ys + 1 + q, 8u * (unsigned)nb);
-                bulk_commit();
-                if (q) yc[1] = ys[1];
-                if (1 + q + nb <= NR) yc[1 + q + nb] = ys[1 + q + nb];
-                bulk_wait_read0();
-            } else {
-                // rows owned by this tile: 1 .. (elements present)*(O-1), plus row 0 for the first tile
-                const int r_lo = (eA == 0) ? 0 : 1;
                 const i64 last_el = eA + ET < nel ? eA + ET : nel;
-                const int r_hi = (int)((last_el - eA) * (O - 1)) + 1;
-                const double a1 = beta == 0.0 ? 1.0 : alpha;             // alpha is already in the tile when beta == 0
-                for (int h = 0; h < FE_TV; ++h) {
-                    const i64 gv = v0 + h;
-                    if (gv >= nvec) break;
-                    const double *ys = xs + h * P0 + fe_swz(h) + col_parity(x0row, v0, h);
-                    double *yc = Y + gv * ldy;
-#pragma unroll
-                    for (int i = 0; i < (ROWS + 31) / 32; ++i) {
-                        const int r = lane + 32 * i;
-                        const i64 gr = x0row + r;
-                        if (r >= r_lo && r < r_hi && gr >= 0 && gr < nrows) yc[gr] = axpby(ys[r], a1, beta, yc + gr);
-                    }
-                }
+                int ra = (eA == 0) ? 0 : 1, rb = (int)((last_el - eA) * (O - 1)) + 1;
+                if (x0row + ra < 0) ra = (int)(-x0row);
+                if (x0row + rb > nrows) rb = (int)(nrows - x0row);
+                if (!vok || rb < ra) rb = ra;
+                const double *ys = xs + lane * P0 + fe_swz(lane) + par;
+                double *yc = Y + (vok ? v0 + lane : 0) * ldy + x0row;
+                tma_col_store(yc, ys, par, ra, rb);
             }
             __syncwarp();                           // every lane has read its part of the tile
             if (lane == 0) mbar_arrive(empty + stage);
@@ -1056,7 +1131,7 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
         bulk_wait0();
     }
 #ifdef FEDVR_PHASE_PROF
-    if (lane == 0 && (w == 0 || w == NG || w == NG + 1))
+    if (lane == 0 && (w == 0 || w == PROF_NG || w == PROF_NG + 1))
         for (int i = 0; i < 8; ++i) atomicAdd(&fe_prof[i], (unsigned long long)pf[i]);
 #endif
 }
@@ -1134,15 +1209,15 @@ template <int O>
 static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, const double *X, i64 ldx, i64 nvec,
                         double alpha, double beta, double *Y, i64 ldy, cudaStream_t st) {
     constexpr int NG = (O <= 12) ? FEDVR_NG : 8;
-    constexpr int NS = FEDVR_NS;
     constexpr int ET = NG - 1;
     constexpr int ROWS = (ET + 1) * (O - 1) + 1;
     constexpr int PITCH = fe_pitch(ROWS);
-    constexpr size_t smem = sizeof(double) * ((size_t)NS * ((FE_TV * PITCH + 1) / 2 * 2) + (size_t)(2 * ET + 1) * FE_BRP);
+    constexpr size_t smem = sizeof(double) * ((size_t)((FE_TV * PITCH + 1) / 2 * 2) + (size_t)(2 * ET + 1) * FE_BRP);
     static_assert(smem <= 227 * 1024, "tile ring does not fit in shared memory");
 #if FEDVR_PIPE
     // the TMA pipeline needs X and Y columns of equal 16-byte phase (see the kernel comment)
-    if (((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && ((ldx ^ ldy) & 1) == 0) {
+    if (beta == 0.0 && ((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 &&
+        ((ldx ^ ldy) & 1) == 0) {
         using P = FePipe<O, NG>;
         static_assert(P::NSTG >= 2, "tile ring does not fit in shared memory");
         auto pk = fedvr_apply_pipe_kernel<O, NG>;
@@ -1154,12 +1229,7 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
         return CB_OK;
     }
 #endif
-#if FEDVR_LEAN
-    static_assert(NS == 1, "the lean kernel has no tile ring");
     auto kern = fedvr_apply_lean_kernel<O, NG>;
-#else
-    auto kern = fedvr_apply_kernel<O, NG, NS>;
-#endif
     CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 tiles = ((nel + ET - 1) / ET) * ((nvec + FE_TV - 1) / FE_TV);
     // CTAs the machine holds at once (registers limit this kernel to 3 per SM at NG = 16, not shared memory); the grid is
@@ -1170,7 +1240,7 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
         CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NG, smem));
         per_sm = occ < 1 ? 1 : occ;
     }
-    const i64 cap = (i64)CB_NUM_SMS * per_sm * (NS == 1 ? FEDVR_WAVES : 1);   // pipelined: one persistent wave of CTAs
+    const i64 cap = (i64)CB_NUM_SMS * per_sm * FEDVR_WAVES;
     int grid = (int)(tiles < cap ? tiles : cap);
     kern<<<grid, 32 * NG, smem, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
@@ -1245,6 +1315,38 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     if (smem > 200 * 1024) { cb_set_error("cb_banded_apply: bandwidth %d too large for the shared-memory tile", W); return CB_ERR_UNSUPPORTED; }
     CB_CUDA(cudaFuncSetAttribute(banded_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS, nvt = (nvec + BT_VEC - 1) / BT_VEC;
+#if BT_PIPE
+    // warp-specialised TMA pipeline: needs non-negative bandwidths and X, Y columns of equal 16-byte phase
+    if (l >= 0 && u >= 0 && KS <= BT_KSMAX && beta == 0.0 &&
+        ((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && ((ldx ^ ldy) & 1) == 0) {
+        const int P0 = (xrows + 3 + 2 + 12 + 15) / 16 * 16;      // window + k padding + parity shift / rounding + skew
+        const size_t stage_b = sizeof(double) * BT_VEC * P0, as_b = sizeof(double) * (BT_ROWS / 8) * KS * 32;
+        int nstg = (int)((227 * 1024 - as_b - 256) / stage_b);
+        if (nstg > 6) nstg = 6;
+        if (nstg >= 2) {
+            const size_t psmem = nstg * stage_b + as_b + 256;
+            CB_CUDA(cudaFuncSetAttribute(banded_apply_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            // vector tiles per work item: the one of 8..4 (1 if there are few) that deals the items most evenly
+            i64 best = 1;
+            if (nrt * nvt >= (i64)CB_NUM_SMS * 8) {
+                double best_eff = 0.0;
+                for (i64 vcn = 8; vcn >= 4; --vcn) {
+                    const i64 it = nrt * ((nvt + vcn - 1) / vcn);
+                    const i64 per = (it + CB_NUM_SMS - 1) / CB_NUM_SMS;
+                    // tiles the busiest CTA runs against the mean (the last chunk of a row tile may be short)
+                    const double eff = (double)(nrt * nvt) / ((double)per * vcn * CB_NUM_SMS);
+                    if (eff > best_eff + 1e-9) { best_eff = eff; best = vcn; }
+                }
+            }
+            const i64 pitems = nrt * ((nvt + best - 1) / best);
+            const int pgrid = (int)(pitems < CB_NUM_SMS ? pitems : CB_NUM_SMS);
+            banded_apply_pipe_kernel<<<pgrid, 32 * (BT_NG + 2), psmem, (cudaStream_t)stream>>>(
+                band, m, n, l, u, X, ldx, nvec, (int)best, P0, nstg, alpha, beta, Y, ldy);
+            CB_LAUNCH_CHECK();
+            return CB_OK;
+        }
+    }
+#endif
     // vector tiles per work item: amortise the band-tile staging while keeping >= ~8 items per SM
     i64 vchunk = nrt * nvt / ((i64)CB_NUM_SMS * 8);
     vchunk = vchunk < 1 ? 1 : (vchunk > 8 ? 8 : vchunk);          // 3..8 measured within 2% of each other, 1-2 slower
