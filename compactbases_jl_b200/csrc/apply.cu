@@ -478,6 +478,10 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     auto next_stage = [&]() { if (++stage == nstg) { stage = 0; phase ^= 1; } };
     // parity shift of column v: window row r (matrix column g0 + r) of vector v sits at xs[col(v) + par + r]
     auto col_parity = [&](i64 g0, i64 v) { return (int)((xbase + v * ldx + g0) & 1); };
+    // item -> (vector chunk, row tile): row tiles vary fastest (CTAs running at one time stream contiguous rows of the
+    // same columns); the row tile is rotated by the chunk index so that a CTA's items (stride gridDim.x) do not keep
+    // hitting the same residue of row tiles — the clipped first / last row tiles then spread evenly over the CTAs
+    auto item_coords = [&](i64 item, i64 &vc, i64 &rt) { vc = item / nrt; rt = (item - vc * nrt + vc) % nrt; };
     if (w < BT_NG) {
         // ================= compute warps ======================================================
         const int gq = lane >> 2, tq = lane & 3;
@@ -487,7 +491,8 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         // current item is multiplied, so the band's memory latency is off the tile loop.
         double av[BT_NAV];
         auto fetch_frags = [&](i64 item_) {
-            const i64 vc_ = item_ / nrt, i0_ = (item_ - vc_ * nrt) * BT_ROWS;
+            i64 vc_, rt_; item_coords(item_, vc_, rt_);
+            const i64 i0_ = rt_ * BT_ROWS;
 #pragma unroll
             for (int t = 0; t < BT_NAV; ++t) {
                 const int e = threadIdx.x + t * 32 * BT_NG;
@@ -499,7 +504,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         };
         if ((i64)blockIdx.x < nitems) fetch_frags(blockIdx.x);
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const i64 vc = item / nrt, rt = item - vc * nrt;              // row tiles vary fastest (contiguous streams)
+            i64 vc, rt; item_coords(item, vc, rt);
             const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
             named_bar_sync(1, 32 * BT_NG);          // the previous item's fragments are no longer read
 #pragma unroll
@@ -561,7 +566,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     } else if (w == BT_NG) {
         // ================= loader warp: lane <-> vector column ================================
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const i64 vc = item / nrt, rt = item - vc * nrt;
+            i64 vc, rt; item_coords(item, vc, rt);
             const i64 g0 = rt * BT_ROWS - l;        // matrix column of window row 0
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
@@ -599,7 +604,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     } else {
         // ================= storer warp: lane <-> vector column ================================
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const i64 vc = item / nrt, rt = item - vc * nrt;
+            i64 vc, rt; item_coords(item, vc, rt);
             const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {

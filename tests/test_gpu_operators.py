@@ -255,3 +255,68 @@ def test_apply_dimension_mismatch(cb):
     Y = cb.ColMajor.zeros(5, 2)
     with pytest.raises(cb.DimensionMismatch):
         cb.mul(Y, T, X)
+
+
+# ---------------------------------------------------------------------------
+# The warp-specialised TMA pipelines (banded, FE-DVR): enough tiles per CTA for the stage ring to wrap several times,
+# odd and even leading dimensions (both 16-byte phases of the columns), partial last vector tile, and X / Y pairs
+# whose columns differ in phase (the launcher must then take the non-TMA kernel and still be exact).
+# ---------------------------------------------------------------------------
+def _shifted_colmajor(cb, a, shift):
+    """(n, nvec) numpy -> ColMajor whose storage starts `shift` doubles into a 16-byte aligned allocation."""
+    import torch
+    n, nvec = a.shape
+    buf = torch.zeros(nvec * n + shift + 1, dtype=torch.float64, device="cuda")
+    view = buf[shift:shift + nvec * n].view(nvec, n)
+    view.copy_(torch.as_tensor(np.ascontiguousarray(a.T), device="cuda"))
+    return cb.ColMajor(view)
+
+
+@pytest.mark.parametrize("n,l,u,nvec,xshift,yshift", [
+    (20001, 9, 9, 400, 0, 0),        # odd leading dimension: columns alternate in phase; ring wraps (2 041 tiles)
+    (20000, 6, 6, 390, 0, 0),        # even leading dimension, partial last vector tile
+    (4099, 3, 5, 130, 1, 1),         # both arrays start on an odd element
+    (4099, 3, 5, 130, 0, 1),         # X and Y differ in phase: non-TMA kernel
+    (1006, 6, 6, 4096, 0, 0),        # C1-like: few row tiles, first and last clipped
+])
+def test_banded_apply_pipeline_at_scale(cb, n, l, u, nvec, xshift, yshift):
+    import torch
+    rng = np.random.default_rng(n + nvec)
+    band = rng.standard_normal((n, l + u + 1))
+    A = cb.BandedMatrix(torch.as_tensor(band, device="cuda").contiguous(), n, n, l, u)
+    X = rng.standard_normal((n, nvec))
+    Xc = _shifted_colmajor(cb, X, xshift)
+    Yc = _shifted_colmajor(cb, np.full((n, nvec), np.nan), yshift)
+    cb.mul(Yc, A, Xc, 1.25, 0.0)
+    ref = cbo.banded_apply(band, n, n, l, u, X, 1.25, 0.0, np.zeros((n, nvec), order="F"))
+    assert relerr(Yc.numpy(), ref) <= RTOL
+
+
+@pytest.mark.parametrize("order,nel,nvec,restrict,xshift,yshift", [
+    (7, 3000, 330, None, 0, 0),          # 18 001 rows (odd), partial last vector tile, ring wraps
+    (10, 1200, 200, (2, 10800), 0, 0),   # restricted basis: first and last functions dropped
+    (4, 5001, 96, None, 1, 1),           # 15 004 rows (even), storage starting on an odd element
+    (10, 1200, 64, None, 0, 1),          # X and Y differ in phase: lean kernel
+])
+def test_fedvr_apply_pipeline_at_scale(cb, order, nel, nvec, restrict, xshift, yshift):
+    t = cbo.julia_range(0, float(nel), nel + 1)
+    B = cb.FEDVR(t, order)
+    O = cbo.FEDVROracle(t, order)
+    D = cb.Derivative()
+    blk = O.blocks(2)
+    rng = np.random.default_rng(order + nel)
+    if restrict is None:
+        A = B.T @ D.T @ D @ B
+        nfun, lo = B.N, 0
+    else:
+        Br = B[:, restrict[0]:restrict[1]]
+        A = Br.T @ D.T @ D @ Br
+        nfun, lo = restrict[1] - restrict[0] + 1, restrict[0] - 1
+    X = rng.standard_normal((nfun, nvec))
+    Xfull = np.zeros((B.N, nvec), order="F")
+    Xfull[lo:lo + nfun] = X
+    ref = O.apply(blk, Xfull, threads=True)[lo:lo + nfun] * 0.75
+    Xc = _shifted_colmajor(cb, X, xshift)
+    Yc = _shifted_colmajor(cb, np.full((nfun, nvec), np.nan), yshift)
+    cb.mul(Yc, A, Xc, 0.75, 0.0)
+    assert relerr(Yc.numpy(), ref) <= RTOL
