@@ -329,7 +329,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "n_functions": N_FUN, "vectors_per_gpu": NVEC, "bytes_per_step_per_gpu": BYTES_STEP,
                        "l2": "inputs larger than L2 (X and Y are 737 MB each)", "sharding": "vector batch per rank, operator replicated, no collective"},
             "roofline": {"bound": "hbm", "achieved": BYTES_APPLY / apply_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": BYTES_APPLY / apply_s / 1e9 / peak_gbs, "traffic": traffic, "kernel": "fedvr_apply_kernel<10,16,1>",
+                         "frac": BYTES_APPLY / apply_s / 1e9 / peak_gbs, "traffic": traffic, "kernel": "fedvr_apply_pipe_kernel<10,16>",
                          "algorithmic_bytes_per_launch": BYTES_APPLY, "kernel_ms": apply_s * 1e3, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"},
             "cpu_baseline": {"value": cpu_v, "unit": "GB/s", "cores": cores, "kind": "port",
                              "sample": "assemble + apply on 128 of the 1024 vectors, best of 2 (oracle/, OpenMP)"},

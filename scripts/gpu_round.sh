@@ -2,7 +2,7 @@
 # One GPU round: parity tests, bench, ncu launch list, ncu full capture of the top kernel.
 # usage: scripts/gpu_round.sh <tag> [kernel-regex]
 TAG=${1:-r1}
-KREGEX=${2:-fedvr_apply_kernel}
+KREGEX=${2:-fedvr_apply_pipe_kernel}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/tests_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
