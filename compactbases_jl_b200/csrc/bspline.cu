@@ -58,9 +58,23 @@ __global__ void lgwt_kernel(KnotView kv, const i64 *__restrict__ ivlist, i64 ni,
 // ---------------------------------------------------------------------------
 constexpr int EVAL_THREADS = 256;
 constexpr int EVAL_SMEM_KNOTS = 6144;              // largest t.t staged in shared memory (48 KB)
+#ifndef EVAL_REP
+#define EVAL_REP 16                                // bank-private copies of a small knot table
+#endif
+
+// Knot table view: entry j of the (padded) table.  With REP > 1 the table is replicated REP times in shared memory,
+// copy c at the addresses = c (mod REP) doubles, and a lane reads copy lane % REP: the 16 lanes of a half-warp then
+// hit 16 different 8-byte banks whatever their intervals are (REP = 16), where a single copy read at 32 unrelated
+// indices costs ~4.6 wavefronts per LDS.64 instead of 2 — the profile of the single-copy kernel
+// (profiles/r1u_bspline_eval_summary.txt) had the shared-memory pipe at 80 %, 35.8 M of its 65 M wavefronts conflicts.
+template <int REP> struct KnotTab {
+    const double *base;                            // REP == 1: plain array;  else base already includes the lane's copy
+    __device__ __forceinline__ double operator[](int j) const { return base[j * REP]; }
+};
 
 // first index in [0, n_tt) with tt[idx] > x (n_tt if none), x inside [tt[0], tt[n_tt-1])
-__device__ __forceinline__ int upper_bound_guess(const double *tt, int n_tt, double x, double first, double scale) {
+template <class Tab>
+__device__ __forceinline__ int upper_bound_guess(const Tab &tt, int n_tt, double x, double first, double scale) {
     int g = (int)((x - first) * scale);
     g = g < 0 ? 0 : (g > n_tt - 2 ? n_tt - 2 : g);
     const double a = tt[g], b = tt[g + 1];
@@ -74,39 +88,40 @@ __device__ __forceinline__ int upper_bound_guess(const double *tt, int n_tt, dou
     return lo;
 }
 
-template <int K, bool SMEM_KNOTS, int MT>
-__global__ void __launch_bounds__(EVAL_THREADS, 4)
+template <int K, bool SMEM_KNOTS, int MT, int REP, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 bspline_eval_kernel(KnotView kv, i64 nf, const double *__restrict__ x, i64 nx, int m,
                     int32_t *__restrict__ interval, double *__restrict__ vals, int vec_ok) {
     constexpr int KP = K | 1;                      // odd row pitch: conflict-free staging
-    __shared__ double stage[EVAL_THREADS / 32][32 * KP];
-    extern __shared__ double sknots[];
+    extern __shared__ double esm[];                // [NT/32][32*KP] row staging, then the knot table(s)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sw = stage[warp];
+    double *sw = esm + warp * (32 * KP);
+    double *sknots = esm + (NT / 32) * (32 * KP);
     const int n_tt = (int)kv.n_tt;
-    const double *tt = kv.tt;
+    KnotTab<SMEM_KNOTS ? REP : 1> tt;
+    tt.base = kv.tt;
     if (SMEM_KNOTS) {
         // K-1 copies of the end knots on either side: the knot window of any interval is then read without clamping
-        for (int i = threadIdx.x; i < n_tt + 2 * (K - 1); i += EVAL_THREADS) {
-            int j = i - (K - 1);
+        for (int i = threadIdx.x; i < (n_tt + 2 * (K - 1)) * REP; i += NT) {
+            int j = i / REP - (K - 1);
             j = j < 0 ? 0 : (j > n_tt - 1 ? n_tt - 1 : j);
             sknots[i] = kv.tt[j];
         }
         __syncthreads();
-        tt = sknots + (K - 1);
+        tt.base = sknots + (K - 1) * REP + (lane & (REP - 1));
     }
     const double first = kv.tt[0], last = kv.tt[n_tt - 1];
     const double scale = (double)(n_tt - 1) / (last - first);
-    const i64 nblk = (nx + EVAL_THREADS - 1) / EVAL_THREADS;
+    const i64 nblk = (nx + NT - 1) / NT;
     // the point of the next iteration is loaded before this one is evaluated (one load in flight per thread)
     double xnext = 0.0;
-    if ((i64)blockIdx.x * EVAL_THREADS + threadIdx.x < nx) xnext = __ldcs(x + (i64)blockIdx.x * EVAL_THREADS + threadIdx.x);
+    if ((i64)blockIdx.x * NT + threadIdx.x < nx) xnext = __ldcs(x + (i64)blockIdx.x * NT + threadIdx.x);
     for (i64 blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const i64 wbase = blk * EVAL_THREADS + warp * 32;   // first point of this warp
+        const i64 wbase = blk * NT + warp * 32;     // first point of this warp
         const i64 p = wbase + lane;
         const double xp = xnext;
         {
-            const i64 pn = p + (i64)gridDim.x * EVAL_THREADS;
+            const i64 pn = p + (i64)gridDim.x * NT;
             if (pn < nx) xnext = __ldcs(x + pn);
         }
         double N[K];
@@ -362,20 +377,33 @@ int cb_bspline_eval(const cb_bspline *B, const double *x, i64 nx, int m,
     CB_REQUIRE(x && interval && vals, "cb_bspline_eval: NULL array");
     cudaStream_t st = (cudaStream_t)stream;
     int vec_ok = ((uintptr_t)vals % 16) == 0;
-    if (B->n_tt <= EVAL_SMEM_KNOTS) {
-        const size_t smem = sizeof(double) * ((size_t)B->n_tt + 2 * (size_t)(B->k - 1));   // + the clamped copies of the end knots
+    const size_t ktab = (size_t)B->n_tt + 2 * (size_t)(B->k - 1);   // + the clamped copies of the end knots
+    const size_t kp = (size_t)(B->k | 1);
+    if (ktab * EVAL_REP * 8 + (1024 / 32) * 32 * kp * 8 <= 200 * 1024) {
+        // small knot sets (<= ~1100 knots at k = 7): one 1024-thread CTA per SM with bank-private knot replicas
+        const size_t smem = sizeof(double) * (ktab * EVAL_REP + (1024 / 32) * 32 * kp);
+        const i64 nblk = (nx + 1023) / 1024;
+        const int grid = (int)(nblk < CB_NUM_SMS ? nblk : CB_NUM_SMS);
+        CB_DISPATCH_K(B->k, {
+            auto kern = m == 0 ? bspline_eval_kernel<K, true, 0, EVAL_REP, 1024> : bspline_eval_kernel<K, true, -1, EVAL_REP, 1024>;
+            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 1024, smem, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok);
+        });
+    } else if (B->n_tt <= EVAL_SMEM_KNOTS) {
+        const size_t smem = sizeof(double) * (ktab + (EVAL_THREADS / 32) * 32 * kp);
 #ifndef EVAL_WAVES
 #define EVAL_WAVES 8
 #endif
         int grid = cb_grid_for(nx, EVAL_THREADS, EVAL_WAVES);   // a whole number of waves of the 4 resident CTAs per SM; the knot copy is amortised over many blocks
         CB_DISPATCH_K(B->k, {
-            auto kern = m == 0 ? bspline_eval_kernel<K, true, 0> : bspline_eval_kernel<K, true, -1>;
+            auto kern = m == 0 ? bspline_eval_kernel<K, true, 0, 1, EVAL_THREADS> : bspline_eval_kernel<K, true, -1, 1, EVAL_THREADS>;
             CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, EVAL_THREADS, smem, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok);
         });
     } else {
+        const size_t smem = sizeof(double) * (EVAL_THREADS / 32) * 32 * kp;
         int grid = cb_grid_for(nx, EVAL_THREADS, 16);
-        CB_DISPATCH_K(B->k, (bspline_eval_kernel<K, false, -1><<<grid, EVAL_THREADS, 0, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok)));
+        CB_DISPATCH_K(B->k, (bspline_eval_kernel<K, false, -1, 1, EVAL_THREADS><<<grid, EVAL_THREADS, smem, st>>>(make_knot_view(B), B->nf, x, nx, m, interval, vals, vec_ok)));
     }
     CB_LAUNCH_CHECK();
     return CB_OK;
