@@ -109,6 +109,14 @@ __global__ void diag_apply_kernel(const double *__restrict__ d, i64 n, const dou
             Y[i + ldy * v] = axpby(d[i] * X[i + ldx * v], alpha, beta, Y + i + ldy * v);
 }
 
+// Y = alpha X + beta Y (DiagonalOperator's update of y with the density coefficients).
+__global__ void axpby_kernel(i64 n, i64 nvec, double alpha, const double *__restrict__ X, i64 ldx,
+                             double beta, double *__restrict__ Y, i64 ldy) {
+    for (i64 v = blockIdx.y; v < nvec; v += gridDim.y)
+        for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+            Y[i + ldy * v] = axpby(X[i + ldx * v], alpha, beta, Y + i + ldy * v);
+}
+
 // ---------------------------------------------------------------------------
 // Shared-memory tile helpers (rows x TV vectors, xs[v*pitch + row]).
 // ---------------------------------------------------------------------------
@@ -1298,6 +1306,16 @@ int cb_diag_apply(const double *d, i64 n, const double *X, i64 ldx, i64 nvec,
     CB_REQUIRE(d != nullptr, "cb_diag_apply: NULL diagonal");
     dim3 grid((unsigned)cb_grid_for(n, 256, 4), (unsigned)(nvec < 4096 ? nvec : 4096));
     diag_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, n, X, ldx, nvec, alpha, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_axpby(i64 n, i64 nvec, double alpha, const double *X, i64 ldx, double beta, double *Y, i64 ldy, void *stream) {
+    int rc = check_apply_args("cb_axpby", n, n, X, ldx, nvec, Y, ldy);
+    if (rc) return rc;
+    if (n == 0 || nvec == 0) return CB_OK;
+    dim3 grid((unsigned)cb_grid_for(n, 256, 4), (unsigned)(nvec < 4096 ? nvec : 4096));
+    axpby_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, nvec, alpha, X, ldx, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

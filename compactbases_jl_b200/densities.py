@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import DimensionMismatch
 from .bsplines import _BSplineOrRestricted, diffop
 from .lazy import QuasiDiagonal
-from .operators import ColMajor, _ptr, _stream, to_device
+from .operators import ColMajor, _ptr, _stream, axpby, to_device
 
 
 class FunctionProduct:
@@ -114,3 +114,59 @@ class FunctionProduct:
 def Density(L, R=None, nlhs=None, nrhs=None, w=None):
     """``Density = FunctionProduct{true}`` (src/densities.jl:30)."""
     return FunctionProduct(L, R, nlhs, nrhs, w, conjugated=True)
+
+
+class DiagonalOperator:
+    """``DiagonalOperator(f)`` (src/linear_operators.jl:85-173): multiplication by the function ``f = R*c`` in
+    coefficient space, ``y = alpha * (coefficients of f*x) + beta * y``, through the ``FunctionProduct{false}`` of the
+    two expansions instead of an assembled matrix.  diag: the coefficients c (length n); nrhs: the number of vectors
+    ``mul`` is applied to at once (the reference applies one)."""
+
+    def __init__(self, R, diag, nrhs=None, w=None):
+        self.R = R
+        self.rho = FunctionProduct(R, R, 1, nrhs, w, conjugated=False)
+        self.n = self.rho.n
+        self.diag = None
+        self.copyto(diag)
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def copyto(self, diag):
+        """``copyto!(o, diag)`` (:121-124): represent multiplication by the function with coefficients diag."""
+        d = diag if isinstance(diag, ColMajor) else ColMajor(to_device(np.asarray(diag, dtype=np.float64).reshape(1, -1), self.rho.device)
+                                                             if not isinstance(diag, torch.Tensor) else diag.reshape(1, -1))
+        if d.n != self.n or d.nvec != 1:
+            raise DimensionMismatch(f"DimensionMismatch: the basis has {self.n} functions, diag has {d.n} x {d.nvec}")
+        self.diag = d
+        return self
+
+    def mul(self, Y, X, alpha: float = 1.0, beta: float = 0.0):
+        """``mul!(y, L, x, alpha, beta)`` (:129-138)."""
+        Xc = X if isinstance(X, ColMajor) else ColMajor(X)
+        Yc = Y if isinstance(Y, ColMajor) else ColMajor(Y)
+        if Xc.n != self.n or Yc.n != self.n or Xc.nvec != Yc.nvec:
+            raise DimensionMismatch(f"DimensionMismatch: operator of order {self.n}, X {Xc.n}x{Xc.nvec}, Y {Yc.n}x{Yc.nvec}")
+        if alpha == 1.0 and beta == 0.0:
+            self.rho.copyto(self.diag, Xc, out=Yc)                   # the density lands in y directly
+        else:
+            rho = self.rho.copyto(self.diag, Xc)
+            axpby(Yc, rho, alpha, beta)
+        return Y
+
+    def __matmul__(self, X):
+        Xc = X if isinstance(X, ColMajor) else ColMajor(X)
+        Y = ColMajor.zeros(self.n, Xc.nvec, self.rho.device)
+        self.mul(Y, Xc)
+        return Y
+
+    def matrix(self, x=None):
+        r"""``Matrix(L[, x])`` (:143-173): the matrix of the operator, optionally weighted by the function with
+        coefficients x (default ``R \ 1``): ``copyto!(L.rho, L.diag, x); copyto!(M, L.rho)``."""
+        if x is None:
+            x = self.R.ldiv(lambda r: np.ones_like(r))
+        xc = x if isinstance(x, ColMajor) else ColMajor(to_device(np.asarray(x, dtype=np.float64).reshape(1, -1), self.rho.device)
+                                                        if not isinstance(x, torch.Tensor) else x.reshape(1, -1))
+        self.rho.copyto(self.diag, xc)
+        return self.rho.matrix()

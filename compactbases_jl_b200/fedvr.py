@@ -45,6 +45,15 @@ class _FEDVROrRestricted:
     def block_structure(self):
         return self.parent_basis._block_structure(self.first, self.last)
 
+    def ldiv(self, f):
+        r"""``B \ f`` (src/fedvr.jl:369-412): quadrature projection, ``v_j = n_j * (sum of the element weights at node
+        j) * f(x_j) = f(x_j) / n_j``.  Host glue (pointwise); returns the size() x 1 coefficients on the device."""
+        from .operators import ColMajor, to_device
+        P = self.parent_basis
+        x = np.asarray(P.x)[self.first - 1:self.last]
+        n = np.asarray(P.n)[self.first - 1:self.last]
+        return ColMajor(to_device((np.asarray(f(x), dtype=np.float64) / n).reshape(1, -1), P.device))
+
     def _materialize(self, L, middle):
         if not isinstance(L, _FEDVROrRestricted) or L.parent_basis is not self.parent_basis:
             raise ValueError("Cannot multiply functions on different grids")

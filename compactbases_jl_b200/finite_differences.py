@@ -40,6 +40,19 @@ class _FDOrRestricted:
             raise IndexError(f"BoundsError: restriction {a}:{b} outside 1:{self.size()}")
         return RestrictedFiniteDifferences(self.parent_basis, self.first + a - 1, self.first + b - 1)
 
+    def ldiv(self, f):
+        r"""``B \ f`` (src/finite_differences.jl:448-458): the function on the grid points over ``weights(B)``.
+        Host glue (pointwise); returns the size() x 1 coefficients on the device."""
+        from .operators import ColMajor, to_device
+        P = self.parent_basis
+        a, b = self.indices()
+        x = np.asarray(P.locs())[a - 1:b]
+        vd = P.vandermonde_diag()
+        v = np.asarray(f(x), dtype=np.float64)
+        if vd is not None:
+            v = v / np.asarray(vd)[a - 1:b]
+        return ColMajor(to_device(v.reshape(1, -1), P.device))
+
     def _materialize(self, L, middle):
         P = self.parent_basis
         # derivative_matrix, src/fd_derivatives.jl:200-203

@@ -117,6 +117,38 @@ class BandedMatrix:
         """``factorize(S)`` / ``cholesky(S)`` of a symmetric positive definite band (the metric B'B)."""
         return BandCholesky(self)
 
+    # -- the little band algebra the reference's drivers use (``T / -2``, ``A - sigma*B``); host glue on the
+    #    band storage, the Julia side keeps BandedMatrices' own broadcasting for it ------------------------
+    def scaled(self, a: float) -> "BandedMatrix":
+        return BandedMatrix(self.data * float(a), self.m, self.n, self.l, self.u)
+
+    def __mul__(self, a):
+        return self.scaled(a)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, a):
+        return self.scaled(1.0 / float(a))
+
+    def __neg__(self):
+        return self.scaled(-1.0)
+
+    def widened(self, l: int, u: int) -> "BandedMatrix":
+        """The same matrix stored with bandwidths (l, u) >= (self.l, self.u)."""
+        if l < self.l or u < self.u:
+            raise DimensionMismatch("DimensionMismatch: cannot narrow a band")
+        if (l, u) == (self.l, self.u):
+            return self
+        data = torch.zeros((self.n, l + u + 1), dtype=torch.float64, device=self.data.device)
+        data[:, u - self.u:u - self.u + self.l + self.u + 1] = self.data
+        return BandedMatrix(data, self.m, self.n, l, u)
+
+    def __sub__(self, other):
+        return _band_axpy(self, other, -1.0)
+
+    def __add__(self, other):
+        return _band_axpy(self, other, 1.0)
+
 
 class BandCholesky:
     """Cholesky factor of an SPD ``BandedMatrix`` held on the device (``cb_bandchol_*``); ``ldiv``
@@ -145,6 +177,87 @@ class BandCholesky:
             raise DimensionMismatch(f"DimensionMismatch: factor has order {self.n}, X has {Xc.n} rows")
         _lib.call("cb_bandchol_solve", self.handle, _ptr(Xc.data), Xc.ld, Xc.nvec, _stream())
         return X
+
+
+def as_banded(A) -> BandedMatrix:
+    """BandedMatrix view of a Tridiagonal / SymTridiagonal / Diagonal / BandedMatrix operator."""
+    if isinstance(A, BandedMatrix):
+        return A
+    if isinstance(A, Tridiagonal):
+        n = A.d.shape[0]
+        band = torch.zeros((n, 3), dtype=torch.float64, device=A.d.device)
+        band[:, 1] = A.d
+        band[1:, 0] = A.du                           # column j holds A[j-1, j] = du[j-1] in band row u + i - j = 0
+        band[:-1, 2] = A.dl
+        return BandedMatrix(band.contiguous(), n, n, 1, 1)
+    if isinstance(A, Diagonal):
+        n = A.diag.shape[0]
+        return BandedMatrix(A.diag.reshape(n, 1).contiguous(), n, n, 0, 0)
+    raise NotImplementedError(f"no band storage for {type(A).__name__}")
+
+
+def _band_axpy(A: BandedMatrix, B, s: float) -> BandedMatrix:
+    """A + s*B for band operators of equal shape (bandwidths are merged)."""
+    B = as_banded(B)
+    if (A.m, A.n) != (B.m, B.n):
+        raise DimensionMismatch(f"DimensionMismatch: {A.shape} and {B.shape}")
+    l, u = max(A.l, B.l), max(A.u, B.u)
+    Aw, Bw = A.widened(l, u), B.widened(l, u)
+    return BandedMatrix(Aw.data + float(s) * Bw.data, A.m, A.n, l, u)
+
+
+class ShiftAndInvert:
+    r"""``ShiftAndInvert(A, B_or_R, sigma)`` (src/linear_operators.jl:185-236): the operator
+    ``x -> (A - sigma*B)^-1 B x`` of the generalised eigenproblem ``A x = lambda B x``, with B the operator metric of
+    the basis R (``B'B`` for B-splines, ``I`` for FE-DVR / finite differences), a band matrix, or None (``I``).
+
+    ``factorize(A - sigma*B)`` is the banded Cholesky factorisation of the C ABI (``cb_bandchol_create``), so the
+    shifted operator has to be symmetric positive definite — true for the reference's own use (kinetic operator,
+    sigma below the spectrum; test/linear_operators.jl:72-88).  An indefinite shift raises the PosDefException
+    analogue (``ValueError``); a pivoted band LU for it is not built yet.  ``mul`` is batched
+    over the columns of X."""
+
+    def __init__(self, A, B=None, sigma: float = 0.0):
+        from .bsplines import _BSplineOrRestricted
+        metric = B
+        if isinstance(B, _BSplineOrRestricted):                      # operator_metric(R) = R'R
+            metric = B.S if hasattr(B, "S") else B.T @ B
+        elif B is not None and not isinstance(B, (BandedMatrix, Tridiagonal, Diagonal)):
+            metric = None                                            # FE-DVR, finite differences: I
+        if isinstance(A, FEDVRMatrix):
+            raise NotImplementedError("ShiftAndInvert of a BlockSkylineMatrix (FE-DVR) is outside the accelerated path")
+        Ab = as_banded(A)
+        if Ab.m != Ab.n:
+            raise DimensionMismatch("DimensionMismatch: ShiftAndInvert needs a square operator")
+        if metric is None:
+            shifted = Ab if sigma == 0.0 else _band_axpy(Ab, Diagonal(torch.ones(Ab.n, dtype=torch.float64, device=Ab.data.device)), -sigma)
+        else:
+            shifted = Ab if sigma == 0.0 else _band_axpy(Ab, metric, -sigma)
+        lu = max(shifted.l, shifted.u)
+        self.Ainv = shifted.widened(lu, lu).cholesky()
+        self.B = metric
+        self.n = Ab.n
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def mul(self, Y, X):
+        """``mul!(y, M, x)`` (src/linear_operators.jl:229-236): ``temp = B x``, ``y = A^-1 temp``."""
+        Xc, Yc = _as_colmajor(X), _as_colmajor(Y)
+        if self.B is None:
+            if Yc.data.data_ptr() != Xc.data.data_ptr():
+                Yc.data[:, :self.n].copy_(Xc.data[:, :self.n])
+        else:
+            mul(Yc, self.B, Xc)
+        self.Ainv.ldiv(Yc)
+        return Y
+
+    def __matmul__(self, X):
+        Xc = _as_colmajor(X)
+        Y = ColMajor(torch.empty((Xc.nvec, self.n), dtype=torch.float64, device=Xc.data.device))
+        self.mul(Y, Xc)
+        return Y
 
 
 class LinearOperator:
@@ -208,6 +321,21 @@ class Tridiagonal:
     def shape(self):
         return (self.n, self.n)
 
+    def scaled(self, a: float) -> "Tridiagonal":
+        a = float(a)
+        return Tridiagonal(self.dl * a, self.d * a, self.du * a)
+
+    def __mul__(self, a):
+        return self.scaled(a)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, a):
+        return self.scaled(1.0 / float(a))
+
+    def __neg__(self):
+        return self.scaled(-1.0)
+
     def dense(self):
         dl, d, du = (v.cpu().numpy() for v in (self.dl, self.d, self.du))
         return np.diag(d) + np.diag(dl, -1) + np.diag(du, 1)
@@ -223,6 +351,15 @@ class Tridiagonal:
                   C.c_void_p(Xh.ctypes.data), Xh.shape[0], Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta,
                   C.c_void_p(Yh.ctypes.data), Yh.shape[0])
         return Yh
+
+
+def axpby(Y, X, alpha: float = 1.0, beta: float = 0.0):
+    """``Y .= alpha .* X .+ beta .* Y`` for ColMajor batches (``cb_axpby``)."""
+    Xc, Yc = _as_colmajor(X), _as_colmajor(Y)
+    if (Xc.n, Xc.nvec) != (Yc.n, Yc.nvec):
+        raise DimensionMismatch(f"DimensionMismatch: X is {Xc.n}x{Xc.nvec}, Y is {Yc.n}x{Yc.nvec}")
+    _lib.call("cb_axpby", Xc.n, Xc.nvec, float(alpha), _ptr(Xc.data), Xc.ld, float(beta), _ptr(Yc.data), Yc.ld, _stream())
+    return Y
 
 
 class SymTridiagonal(Tridiagonal):

@@ -225,6 +225,10 @@ int cb_tridiag_apply_host(const double *dl_dev, const double *d_dev, const doubl
  * src/fd_operators.jl:3-35). */
 int cb_diag_apply(const double *d, cb_i64 n, const double *X, cb_i64 ldx, cb_i64 nvec,
                   double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+/* Y = alpha*X + beta*Y for n x nvec column-major batches (beta == 0: Y is not read): the update
+ * `y .= beta .* y .+ alpha .* rho` of DiagonalOperator's mul!, src/linear_operators.jl:129-138. */
+int cb_axpby(cb_i64 n, cb_i64 nvec, double alpha, const double *X, cb_i64 ldx,
+             double beta, double *Y, cb_i64 ldy, void *stream);
 
 /* ------------------------------------------------------------------------
  * Mutual densities (src/densities.jl).  rho = C * (conj(RV f) .* (LV g)).

@@ -643,3 +643,26 @@ def linear_operator_apply(A, S, X, alpha=1.0, beta=0.0, Y=None):
     temp = alpha*A*x, then y = S \\ temp (beta == 0) or y = beta*y + S \\ temp.  A, S dense."""
     t = np.linalg.solve(S, alpha * (A @ X))
     return t if beta == 0.0 or Y is None else beta * Y + t
+
+
+# ---------------------------------------------------------------------------
+# "Next" rows: DiagonalOperator and ShiftAndInvert (src/linear_operators.jl:85-236)
+# ---------------------------------------------------------------------------
+
+def diagonal_operator_apply(density, diag, X, alpha=1.0, beta=0.0, Y=None):
+    """mul!(y, L::DiagonalOperator, x, alpha, beta), src/linear_operators.jl:129-138:
+    copyto!(L.rho, L.diag, x) with the FunctionProduct{false} of the basis (``density(diag, x)`` is one of
+    density_bspline / density_orthogonal with conj=False), then y = beta*y + alpha*rho."""
+    rho = density(diag, X)
+    if beta == 0.0:
+        return alpha * rho
+    return beta * np.asarray(Y) + alpha * rho
+
+
+def shift_invert_apply(A, B, sigma, X):
+    """mul!(y, M::ShiftAndInvert, x), src/linear_operators.jl:229-236: temp = B x; y = factorize(A - sigma*B) \\ temp,
+    on dense copies of the operators (B = None: identity metric)."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    Bm = np.eye(n) if B is None else np.asarray(B, dtype=np.float64)
+    return np.linalg.solve(A - sigma * Bm, Bm @ np.asarray(X, dtype=np.float64))

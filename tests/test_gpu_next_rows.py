@@ -121,3 +121,123 @@ def test_density_docs_transcript_on_gpu(cb):
     np.testing.assert_allclose(rho[:16], g["first16"], rtol=0, atol=2e-10)
     np.testing.assert_allclose(rho[-16:], g["last16"], rtol=0, atol=2e-10)
     assert abs(np.linalg.norm(rho - ch) - g["norm_rho_minus_ch"]) <= 1e-9
+
+
+# ---------------------------------------------------------------------------
+# DiagonalOperator (rank 3) and ShiftAndInvert (rank 2), src/linear_operators.jl:85-236
+# ---------------------------------------------------------------------------
+def test_diagonal_operator_bspline(cb):
+    """mul!(y, DiagonalOperator(f), x, alpha, beta) == coefficients of f*x through the FunctionProduct{false};
+    Matrix(L) == R' diag(f) R weighted by the unit function (test/linear_operators.jl:38-70)."""
+    t = cb.LinearKnotSet(7, 0, 1.5, 71)
+    B = cb.BSpline(t)
+    te, q, x, w = oracle_basis(t)
+    V = cbo.basis_matrix(te, 7, x, q)
+    f = lambda r: np.sin(2 * np.pi * r)
+    c = B.ldiv(f)
+    rng = np.random.default_rng(41)
+    X = rng.standard_normal((B.nf, 5))
+    Y0 = rng.standard_normal((B.nf, 5))
+    dens = lambda a, b: cbo.density_bspline(V, a, b, conj=False)
+    cn = c.numpy()[:, 0]
+    L = cb.DiagonalOperator(B, c, nrhs=5)
+    assert L.shape == (B.nf, B.nf)
+    got = (L @ cb.ColMajor.from_numpy(X)).numpy()
+    assert relerr(got, cbo.diagonal_operator_apply(dens, cn, X)) <= RTOL
+    Yc = cb.ColMajor.from_numpy(Y0)
+    L.mul(Yc, cb.ColMajor.from_numpy(X), 0.5, -2.0)
+    assert relerr(Yc.numpy(), cbo.diagonal_operator_apply(dens, cn, X, 0.5, -2.0, Y0)) <= RTOL
+    # copyto!(o, diag): the operator now multiplies by another function
+    c2 = B.ldiv(lambda r: r * np.exp(-r))
+    L.copyto(c2)
+    got = (L @ cb.ColMajor.from_numpy(X)).numpy()
+    assert relerr(got, dens(c2.numpy()[:, 0], X)) <= RTOL
+    # Matrix(L): overlap matrix with the nodal values of f * 1 as diagonal operator
+    L1 = cb.DiagonalOperator(B, c)
+    M = L1.matrix()
+    ones = cbo.bspline_ldiv(V, np.ones_like(x))
+    tmp = (V @ cn) * (V @ ones)
+    band, l, u = cbo.bspline_assemble(te, 7, te, 7, x, w, q, op=tmp)
+    assert relerr(M.dense(), cbo.band_to_dense(band, B.nf, B.nf, l, u)) <= 1e-11
+    with pytest.raises(cb.DimensionMismatch):
+        L.mul(cb.ColMajor.zeros(B.nf, 5), cb.ColMajor.zeros(B.nf + 1, 5))
+
+
+def test_diagonal_operator_orthogonal_bases(cb):
+    rng = np.random.default_rng(42)
+    R = cb.StaggeredFiniteDifferences(300, 0.1)
+    c = R.ldiv(lambda r: r ** 2)
+    assert np.array_equal(c.numpy()[:, 0], np.asarray(R.locs()) ** 2)       # test/fd/scalar_operators.jl:30-36
+    X = rng.standard_normal((300, 4))
+    L = cb.DiagonalOperator(R, c, nrhs=4)
+    dens = lambda a, b: cbo.density_orthogonal(a, b, conj=False)
+    assert np.array_equal((L @ cb.ColMajor.from_numpy(X)).numpy(), cbo.diagonal_operator_apply(dens, c.numpy()[:, 0], X))
+    Fb = cb.FEDVR(cbo.julia_range(0, 10, 8), 5)
+    cf = Fb.ldiv(lambda r: np.exp(-r))
+    assert relerr(cf.numpy()[:, 0], np.exp(-Fb.x) / Fb.n) <= 1e-15
+    Xf = rng.standard_normal((Fb.N, 3))
+    Y0 = rng.standard_normal((Fb.N, 3))
+    Lf = cb.DiagonalOperator(Fb, cf, nrhs=3)
+    densf = lambda a, b: cbo.density_orthogonal(a, b, c=Fb.n, conj=False)
+    Yc = cb.ColMajor.from_numpy(Y0)
+    Lf.mul(Yc, cb.ColMajor.from_numpy(Xf), 2.0, 1.0)
+    assert relerr(Yc.numpy(), cbo.diagonal_operator_apply(densf, cf.numpy()[:, 0], Xf, 2.0, 1.0, Y0)) <= 1e-15
+    D = Lf.matrix()
+    assert isinstance(D, cb.Diagonal)
+
+
+def _subspace_eigs(M, n, nev, iters, seed):
+    """Orthogonal iteration with the batched shift-and-invert operator (the reference's driver is ArnoldiMethod,
+    test/derivative_accuracy_utils.jl:130-148): returns the nev largest eigenvalues theta of M."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    Q = torch.linalg.qr(torch.randn((n, nev + 4), dtype=torch.float64, device="cuda", generator=g))[0]
+    import compactbases_jl_b200 as cb
+    for _ in range(iters):
+        Z = (M @ cb.ColMajor(Q.T.contiguous())).data.T
+        Q = torch.linalg.qr(Z)[0]
+    Z = (M @ cb.ColMajor(Q.T.contiguous())).data.T
+    H = (Q.T @ Z).cpu().numpy()
+    return np.sort(np.linalg.eigvals(H).real)[::-1][:nev]
+
+
+def test_shift_and_invert_bspline_particle_in_a_box(cb):
+    """test/linear_operators.jl:72-88 (B-splines): (T - sigma S)^-1 S x against a dense solve, and the lowest
+    particle-in-a-box levels through sigma + 1/theta."""
+    Lbox, N = 10.0, 100
+    t = cb.LinearKnotSet(5, 0, Lbox, N)
+    B = cb.BSpline(t)
+    Br = B[:, 2:B.nf - 1]
+    D = cb.Derivative()
+    T = (Br.T @ D.T @ D @ Br) / -2
+    S = Br.T @ Br
+    n = Br.size()
+    rng = np.random.default_rng(43)
+    X = rng.standard_normal((n, 6))
+    for sigma in (0.0, -0.7):
+        M = cb.ShiftAndInvert(T, Br, sigma)
+        got = (M @ cb.ColMajor.from_numpy(X)).numpy()
+        ref = cbo.shift_invert_apply(T.dense(), S.dense(), sigma, X)
+        # the shifted operator has condition number ~1e6: two exact factorisations agree to ~cond * eps
+        assert relerr(got, ref) <= 1e-9
+    theta = _subspace_eigs(cb.ShiftAndInvert(T, Br, 0.0), n, 5, 40, 1)
+    lam = 1.0 / theta
+    exact = (np.arange(1, 6) * np.pi / Lbox) ** 2 / 2
+    assert np.linalg.norm(lam - exact) < 5e-9                      # k = 5, 100 intervals: discretisation error ~1e-10
+    with pytest.raises(ValueError):                                   # indefinite shift: PosDefException analogue
+        cb.ShiftAndInvert(T, Br, 1.0)
+
+
+def test_shift_and_invert_finite_differences(cb):
+    Lbox, N = 10.0, 100
+    R = cb.FiniteDifferences(N, Lbox / (N + 1))
+    D = cb.Derivative()
+    T = (R.T @ D.T @ D @ R) / -2
+    rng = np.random.default_rng(44)
+    X = rng.standard_normal((N, 3))
+    M = cb.ShiftAndInvert(T, R, -0.25)
+    got = (M @ cb.ColMajor.from_numpy(X)).numpy()
+    assert relerr(got, cbo.shift_invert_apply(T.dense(), None, -0.25, X)) <= 1e-11
+    theta = _subspace_eigs(cb.ShiftAndInvert(T, R, 0.0), N, 5, 60, 2)
+    exact = (np.arange(1, 6) * np.pi / Lbox) ** 2 / 2
+    assert np.linalg.norm(1.0 / theta - exact) < 0.004                # the reference's tolerance for this scheme
