@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from .lazy import AdjointBasis, CoulombDerivative, Derivative, QuasiDiagonal
-from .operators import Diagonal, SymTridiagonal, Tridiagonal, _ptr, _stream, device_of, to_device
+from .operators import Diagonal, ImplicitDerivative, SymTridiagonal, Tridiagonal, _ptr, _stream, device_of, to_device
 
 CARTESIAN, STAGGERED_UNIFORM, STAGGERED_NONUNIFORM = 0, 1, 2
 
@@ -94,9 +94,17 @@ class _FDOrRestricted:
         du = dl if nder == 2 else torch.empty_like(dl)
         _lib.call("cb_fd_derivative", P.scheme, nder, _ptr(P.d_r), _ptr(fhalf), P.N, P.step, i0, n, Z, ell,
                   _ptr(dl), _ptr(d), None if nder == 2 else _ptr(du), _stream())
-        if nder == 2:
-            return SymTridiagonal(d, dl)
-        return Tridiagonal(dl, d, du)
+        Delta = SymTridiagonal(d, dl) if nder == 2 else Tridiagonal(dl, d, du)
+        if getattr(P, "implicit", False):
+            # implicit_derivative, src/fd_derivatives.jl:426-432: the explicit stencil becomes the right-hand side
+            # Delta, implicit_lhs (:402-424, uniform grids) the left-hand side M
+            if Z != 0.0:
+                raise NotImplementedError("CoulombDerivative corrections of the implicit scheme (src/fd_derivatives.jl:553-667)")
+            dv, ev = (4.0 / 6.0, 1.0 / 6.0) if nder == 1 else (10.0 / 12.0, 1.0 / 12.0)
+            M = SymTridiagonal(torch.full((n,), dv, dtype=torch.float64, device=P.device),
+                               torch.full((max(n - 1, 0),), ev, dtype=torch.float64, device=P.device))
+            return ImplicitDerivative(Delta, M)
+        return Delta
 
 
 class AbstractFiniteDifferences(_FDOrRestricted):
@@ -154,6 +162,17 @@ class FiniteDifferences(AbstractFiniteDifferences):
 
     def __init__(self, n, dx, device=None):
         self._setup(np.arange(1, n + 1, dtype=np.float64) * dx, dx, device)
+
+
+class ImplicitFiniteDifferences(AbstractFiniteDifferences):
+    """``ImplicitFiniteDifferences(n, rho)``: compact (implicit) finite differences on the uniform grid rho*(1:n)
+    (src/finite_differences.jl:303-342).  Derivatives materialise to ``ImplicitDerivative``.  Non-uniform grids
+    (Patchkovskii 2016: a non-symmetric tridiagonal left-hand side) are not built."""
+    scheme = CARTESIAN
+    implicit = True
+
+    def __init__(self, n, rho, device=None):
+        self._setup(np.arange(1, n + 1, dtype=np.float64) * rho, rho, device)
 
 
 class StaggeredFiniteDifferences(AbstractFiniteDifferences):

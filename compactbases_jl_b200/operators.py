@@ -226,6 +226,16 @@ class ShiftAndInvert:
             metric = None                                            # FE-DVR, finite differences: I
         if isinstance(A, FEDVRMatrix):
             raise NotImplementedError("ShiftAndInvert of a BlockSkylineMatrix (FE-DVR) is outside the accelerated path")
+        if isinstance(A, ImplicitDerivative):
+            # factorize(d - sigma*I) = ImplicitFactorization(factorize(c*Delta - sigma*M), M), ldiv!: y = M x, then the
+            # tridiagonal solve (src/finite_differences.jl:398-444)
+            if metric is not None:
+                raise NotImplementedError("ShiftAndInvert of an ImplicitDerivative with a non-trivial metric")
+            shifted = _band_axpy(as_banded(A.Delta.scaled(A.c)), A.M, -sigma)
+            self.Ainv = shifted.cholesky()
+            self.B = A.M
+            self.n = A.n
+            return
         Ab = as_banded(A)
         if Ab.m != Ab.n:
             raise DimensionMismatch("DimensionMismatch: ShiftAndInvert needs a square operator")
@@ -368,6 +378,47 @@ class SymTridiagonal(Tridiagonal):
     def __init__(self, dv, ev):
         super().__init__(ev, dv, ev)
         self.dv, self.ev = dv, ev
+
+
+class ImplicitDerivative:
+    """``ImplicitDerivative(Delta, M, c)`` (src/finite_differences.jl:356-413): the compact finite-difference
+    derivative ``c * M^-1 * Delta`` with tridiagonal Delta and symmetric positive definite tridiagonal M (uniform grids:
+    M1 = SymTridiagonal(4, 1)/6, M2 = SymTridiagonal(10, 1)/12, src/fd_derivatives.jl:402-424).  ``factorize(M)`` is the
+    banded Cholesky of the C ABI; ``mul!`` = tridiagonal apply + batched partitioned solve + scaling."""
+
+    def __init__(self, Delta, M, c: float = 1.0, Minv=None):
+        self.Delta, self.M, self.c = Delta, M, float(c)
+        self.Minv = as_banded(M).cholesky() if Minv is None else Minv
+        self.n = Delta.n
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def scaled(self, a: float) -> "ImplicitDerivative":           # Base.:(*)(d, a), :376-383
+        return ImplicitDerivative(self.Delta, self.M, self.c * float(a), self.Minv)
+
+    def __mul__(self, a):
+        return self.scaled(a)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, a):
+        return self.scaled(1.0 / float(a))
+
+    def __neg__(self):
+        return self.scaled(-1.0)
+
+    def dense(self):
+        return self.c * np.linalg.solve(self.M.dense(), self.Delta.dense())
+
+    def _mul(self, Y, X, alpha, beta):
+        """``mul!(y, d, x, alpha, beta)`` (:388-396): ``mul!(y, Delta, x, alpha, beta); ldiv!(M^-1, y); lmul!(c, y)``
+        (beta*y passes through M^-1 as well, as in the reference)."""
+        self.Delta._mul(Y, X, alpha, beta)
+        self.Minv.ldiv(Y)
+        if self.c != 1.0:
+            axpby(Y, Y, self.c, 0.0)
 
 
 class Diagonal:

@@ -666,3 +666,21 @@ def shift_invert_apply(A, B, sigma, X):
     n = A.shape[0]
     Bm = np.eye(n) if B is None else np.asarray(B, dtype=np.float64)
     return np.linalg.solve(A - sigma * Bm, Bm @ np.asarray(X, dtype=np.float64))
+
+
+def implicit_lhs_uniform(n, difforder):
+    """implicit_lhs(::Uniform, B, difforder), src/fd_derivatives.jl:402-424: SymTridiagonal (dv, ev) of the compact
+    scheme, M1 = (4, 1)/6 (Eq. 19), M2 = (10, 1)/12 (Eq. 13)."""
+    dv, ev = (4.0 / 6.0, 1.0 / 6.0) if difforder == 1 else (10.0 / 12.0, 1.0 / 12.0)
+    return np.full(n, dv), np.full(max(n - 1, 0), ev)
+
+
+def implicit_derivative_apply(dl, d, du, mdv, mev, c, X, alpha=1.0, beta=0.0, Y=None):
+    """mul!(y, d::ImplicitDerivative, x, alpha, beta), src/finite_differences.jl:388-396:
+    mul!(y, Delta, x, alpha, beta); ldiv!(M^-1, y); lmul!(c, y) — on dense copies."""
+    Delta = np.diag(d) + np.diag(dl, -1) + np.diag(du, 1)
+    M = np.diag(mdv) + np.diag(mev, -1) + np.diag(mev, 1)
+    rhs = alpha * (Delta @ np.asarray(X, dtype=np.float64))
+    if beta != 0.0:
+        rhs = rhs + beta * np.asarray(Y, dtype=np.float64)
+    return c * np.linalg.solve(M, rhs)

@@ -241,3 +241,66 @@ def test_shift_and_invert_finite_differences(cb):
     theta = _subspace_eigs(cb.ShiftAndInvert(T, R, 0.0), N, 5, 60, 2)
     exact = (np.arange(1, 6) * np.pi / Lbox) ** 2 / 2
     assert np.linalg.norm(1.0 / theta - exact) < 0.004                # the reference's tolerance for this scheme
+
+
+# ---------------------------------------------------------------------------
+# ImplicitFiniteDifferences (rank 4, uniform grids), src/finite_differences.jl:303-444, src/fd_derivatives.jl:402-432
+# ---------------------------------------------------------------------------
+def test_implicit_finite_differences_structure_and_apply(cb):
+    """The stencil values the reference's tests pin (test/fd/derivatives.jl:63-105, non-singular case) and
+    mul!(y, d, x, alpha, beta) against the dense restatement."""
+    N, rho = 10, 0.3
+    R = cb.ImplicitFiniteDifferences(N, rho)
+    D = cb.Derivative()
+    d1 = R.T @ D @ R
+    assert isinstance(d1, cb.ImplicitDerivative) and isinstance(d1.Delta, cb.Tridiagonal)
+    assert np.all(d1.Delta.d.cpu().numpy() == 0.0)
+    assert np.allclose(d1.Delta.dl.cpu().numpy(), -1 / (2 * rho), rtol=1e-15)
+    assert np.allclose(d1.Delta.du.cpu().numpy(), 1 / (2 * rho), rtol=1e-15)
+    mdv, mev = cbo.implicit_lhs_uniform(N, 1)
+    assert np.array_equal(d1.M.dv.cpu().numpy(), mdv) and np.array_equal(d1.M.ev.cpu().numpy(), mev)
+    d2 = R.T @ D.T @ D @ R
+    assert isinstance(d2, cb.ImplicitDerivative) and isinstance(d2.Delta, cb.SymTridiagonal)
+    assert np.allclose(d2.Delta.dv.cpu().numpy(), -2 / rho ** 2, rtol=1e-15)
+    assert np.allclose(d2.Delta.ev.cpu().numpy(), 1 / rho ** 2, rtol=1e-15)
+    mdv2, mev2 = cbo.implicit_lhs_uniform(N, 2)
+    assert np.allclose(d2.M.dv.cpu().numpy(), (-1 / 2) * (-10 / 6), rtol=1e-15)
+    assert np.array_equal(d2.M.dv.cpu().numpy(), mdv2) and np.array_equal(d2.M.ev.cpu().numpy(), mev2)
+    Rr = R[:, 1:5]
+    assert (Rr.T @ D @ Rr).shape == (5, 5) and (Rr.T @ D.T @ D @ Rr).shape == (5, 5)
+    # apply at a size where the batched solve is partitioned, with the scalar factor of T = d2 / -2
+    N = 3000
+    R = cb.ImplicitFiniteDifferences(N, 10.0 / (N + 1))
+    T = (R.T @ D.T @ D @ R) / -2
+    rng = np.random.default_rng(51)
+    X, Y0 = rng.standard_normal((N, 37)), rng.standard_normal((N, 37))
+    dlt = T.Delta
+    args = (dlt.dl.cpu().numpy(), dlt.d.cpu().numpy(), dlt.du.cpu().numpy(), *cbo.implicit_lhs_uniform(N, 2), -0.5)
+    Yc = cb.ColMajor.zeros(N, 37)
+    cb.mul(Yc, T, cb.ColMajor.from_numpy(X))
+    assert relerr(Yc.numpy(), cbo.implicit_derivative_apply(*args, X)) <= 1e-11
+    Yc = cb.ColMajor.from_numpy(Y0)
+    cb.mul(Yc, T, cb.ColMajor.from_numpy(X), 0.5, -2.0)
+    assert relerr(Yc.numpy(), cbo.implicit_derivative_apply(*args, X, 0.5, -2.0, Y0)) <= 1e-11
+    # fourth-order accuracy of the compact second derivative on a smooth function (test/fd/derivatives.jl:135-170)
+    r = np.asarray(R.locs())
+    f = np.sin(np.pi * r / 10.0)
+    d2f = cb.ColMajor.zeros(N, 1)
+    cb.mul(d2f, R.T @ D.T @ D @ R, cb.ColMajor.from_numpy(f))
+    assert np.max(np.abs(d2f.numpy()[:, 0] + (np.pi / 10.0) ** 2 * f)) < 1e-9
+
+
+def test_shift_and_invert_implicit_finite_differences(cb):
+    """test/linear_operators.jl:72-88, "Implicit finite-differences" (tolerance 5e-6)."""
+    Lbox, N = 10.0, 100
+    R = cb.ImplicitFiniteDifferences(N, Lbox / (N + 1))
+    D = cb.Derivative()
+    T = (R.T @ D.T @ D @ R) / -2
+    rng = np.random.default_rng(52)
+    X = rng.standard_normal((N, 3))
+    M = cb.ShiftAndInvert(T, R, -0.25)
+    got = (M @ cb.ColMajor.from_numpy(X)).numpy()
+    assert relerr(got, cbo.shift_invert_apply(T.dense(), None, -0.25, X)) <= 1e-10
+    theta = _subspace_eigs(cb.ShiftAndInvert(T, R, 0.0), N, 5, 60, 3)
+    exact = (np.arange(1, 6) * np.pi / Lbox) ** 2 / 2
+    assert np.linalg.norm(1.0 / theta - exact) < 5e-6
