@@ -76,6 +76,9 @@ _SIGNATURES = {
     "cb_bandchol_create": (cint, [vp, i64, cint, C.POINTER(vp)]),
     "cb_bandchol_solve": (cint, [vp, vp, i64, i64, vp]),
     "cb_bandchol_destroy": (cint, [vp]),
+    "cb_bandlu_create": (cint, [vp, i64, cint, cint, C.POINTER(vp)]),
+    "cb_bandlu_solve": (cint, [vp, vp, i64, i64, vp]),
+    "cb_bandlu_destroy": (cint, [vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -346,7 +346,11 @@ constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
 #define BT_PIPE 1
 #endif
 constexpr int BT_KSMAX = 8;                         // k-steps the pipelined kernel supports (l + u + 1 <= 25)
-constexpr int BT_NAV = (BT_ROWS / 8) * BT_KSMAX * 32 / (32 * BT_NG);   // A-fragment entries per compute thread
+#ifndef BTP_NG
+#define BTP_NG 8                                    // compute warps of the pipelined kernel
+#endif
+constexpr int BTP_RB = BT_ROWS / 8 / BTP_NG;        // 8-row blocks per compute warp
+constexpr int BTP_NAV = (BT_ROWS / 8) * BT_KSMAX * 32 / (32 * BTP_NG);   // A-fragment entries per compute thread
 #ifndef BT_GRIDCAP
 #define BT_GRIDCAP 1024                             // CTAs per SM in the grid at most (items beyond that are strided)
 #endif
@@ -452,7 +456,7 @@ __device__ unsigned long long fe_prof[8];
 // l + u + 1 <= 25, beta == 0 and X, Y of equal 16-byte phase per column; the launcher falls back to
 // banded_apply_kernel otherwise.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32 * (BT_NG + 2), 1)
+__global__ void __launch_bounds__(32 * (BTP_NG + 2), 1)
 banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, int u,
                          const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk, int P0, int nstg,
                          double alpha, double beta, double *__restrict__ Y, i64 ldy) {
@@ -468,7 +472,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nstg; ++s) { mbar_init(full + s, 1); mbar_init(done + s, BT_NG); mbar_init(empty + s, 1); }
+        for (int s = 0; s < nstg; ++s) { mbar_init(full + s, 1); mbar_init(done + s, BTP_NG); mbar_init(empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -479,7 +483,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);
     int stage = 0;
     unsigned phase = 0;
-    constexpr int PROF_NG = BT_NG; (void)PROF_NG;
+    constexpr int PROF_NG = BTP_NG; (void)PROF_NG;
 #ifdef FEDVR_PHASE_PROF
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
@@ -490,20 +494,20 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     // same columns); the row tile is rotated by the chunk index so that a CTA's items (stride gridDim.x) do not keep
     // hitting the same residue of row tiles — the clipped first / last row tiles then spread evenly over the CTAs
     auto item_coords = [&](i64 item, i64 &vc, i64 &rt) { vc = item / nrt; rt = (item - vc * nrt + vc) % nrt; };
-    if (w < BT_NG) {
+    if (w < BTP_NG) {
         // ================= compute warps ======================================================
         const int gq = lane >> 2, tq = lane & 3;
         const double wscale = alpha;                // beta == 0 (launcher): alpha is folded into the tile
         // A fragments of a row tile: as[rb][ks][lane] = A(i0 + 8rb + g, i0 + 8rb - l + 4ks + t), 0 outside band/matrix.
-        // Each thread fetches its BT_NAV entries of the NEXT item into registers while the last vector tile of the
+        // Each thread fetches its BTP_NAV entries of the NEXT item into registers while the last vector tile of the
         // current item is multiplied, so the band's memory latency is off the tile loop.
-        double av[BT_NAV];
+        double av[BTP_NAV];
         auto fetch_frags = [&](i64 item_) {
             i64 vc_, rt_; item_coords(item_, vc_, rt_);
             const i64 i0_ = rt_ * BT_ROWS;
 #pragma unroll
-            for (int t = 0; t < BT_NAV; ++t) {
-                const int e = threadIdx.x + t * 32 * BT_NG;
+            for (int t = 0; t < BTP_NAV; ++t) {
+                const int e = threadIdx.x + t * 32 * BTP_NG;
                 const int ln = e & 31, ks = (e >> 5) % KS, rb = (e >> 5) / KS;
                 const i64 i = i0_ + 8 * rb + (ln >> 2), j = i0_ + 8 * rb - l + 4 * ks + (ln & 3);
                 av[t] = (e < (BT_ROWS / 8) * KS * 32 && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
@@ -514,13 +518,13 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
             const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
-            named_bar_sync(1, 32 * BT_NG);          // the previous item's fragments are no longer read
+            named_bar_sync(1, 32 * BTP_NG);          // the previous item's fragments are no longer read
 #pragma unroll
-            for (int t = 0; t < BT_NAV; ++t) {
-                const int e = threadIdx.x + t * 32 * BT_NG;
+            for (int t = 0; t < BTP_NAV; ++t) {
+                const int e = threadIdx.x + t * 32 * BTP_NG;
                 if (e < (BT_ROWS / 8) * KS * 32) as[e] = av[t];
             }
-            named_bar_sync(1, 32 * BT_NG);
+            named_bar_sync(1, 32 * BTP_NG);
             FE_PROF_L(7);
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
@@ -531,19 +535,19 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                 if (vt + 1 == vt_end && item + gridDim.x < nitems) fetch_frags(item + gridDim.x);
                 mbar_wait(full + stage, phase);
                 FE_PROF_L(2);
-                // A dependent DMMA has ~180 cycles of latency: the k-steps of the warp's BT_RB row blocks advance
-                // together, BT_RB * 4 independent accumulator chains in flight
-                double c[BT_RB][BT_VEC / 8][2];
+                // A dependent DMMA has ~180 cycles of latency: the k-steps of the warp's BTP_RB row blocks advance
+                // together, BTP_RB * 4 independent accumulator chains in flight
+                double c[BTP_RB][BT_VEC / 8][2];
 #pragma unroll
-                for (int q = 0; q < BT_RB; ++q)
+                for (int q = 0; q < BTP_RB; ++q)
 #pragma unroll
                     for (int nt = 0; nt < BT_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
                 {
-                    const double *af = as + w * BT_RB * KS * 32 + lane;
-                    const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * w * BT_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
+                    const double *af = as + w * BTP_RB * KS * 32 + lane;
+                    const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * w * BTP_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
                     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-                        for (int q = 0; q < BT_RB; ++q) {
+                        for (int q = 0; q < BTP_RB; ++q) {
                             const double a = af[(q * KS + ks) * 32];
 #pragma unroll
                             for (int nt = 0; nt < BT_VEC / 8; ++nt)
@@ -552,11 +556,11 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                     }
                 }
                 FE_PROF_L(3);
-                named_bar_sync(1, 32 * BT_NG);      // every warp has read the window
+                named_bar_sync(1, 32 * BTP_NG);      // every warp has read the window
                 FE_PROF_L(4);
 #pragma unroll
-                for (int q = 0; q < BT_RB; ++q) {
-                    const int row = l + (w * BT_RB + q) * 8 + gq;         // window row of the output row
+                for (int q = 0; q < BTP_RB; ++q) {
+                    const int row = l + (w * BTP_RB + q) * 8 + gq;         // window row of the output row
                     double *y0 = xs + (2 * tq) * P0 + fe_swz(2 * tq) + par_c0 + row;
                     double *y1 = xs + (2 * tq + 1) * P0 + fe_swz(2 * tq + 1) + par_c1 + row;
 #pragma unroll
@@ -571,7 +575,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                 FE_PROF_L(7);
             }
         }
-    } else if (w == BT_NG) {
+    } else if (w == BTP_NG) {
         // ================= loader warp: lane <-> vector column ================================
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
@@ -1363,7 +1367,7 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
             }
             const i64 pitems = nrt * ((nvt + best - 1) / best);
             const int pgrid = (int)(pitems < CB_NUM_SMS ? pitems : CB_NUM_SMS);
-            banded_apply_pipe_kernel<<<pgrid, 32 * (BT_NG + 2), psmem, (cudaStream_t)stream>>>(
+            banded_apply_pipe_kernel<<<pgrid, 32 * (BTP_NG + 2), psmem, (cudaStream_t)stream>>>(
                 band, m, n, l, u, X, ldx, nvec, (int)best, P0, nstg, alpha, beta, Y, ldy);
             CB_LAUNCH_CHECK();
             return CB_OK;

@@ -211,13 +211,14 @@ class ShiftAndInvert:
     ``x -> (A - sigma*B)^-1 B x`` of the generalised eigenproblem ``A x = lambda B x``, with B the operator metric of
     the basis R (``B'B`` for B-splines, ``I`` for FE-DVR / finite differences), a band matrix, or None (``I``).
 
-    ``factorize(A - sigma*B)`` is the banded Cholesky factorisation of the C ABI (``cb_bandchol_create``), so the
-    shifted operator has to be symmetric positive definite — true for the reference's own use (kinetic operator,
-    sigma below the spectrum; test/linear_operators.jl:72-88).  An indefinite shift raises the PosDefException
-    analogue (``ValueError``); a pivoted band LU for it is not built yet.  ``mul`` is batched
-    over the columns of X."""
+    ``factorize(A - sigma*B)``: the banded Cholesky factorisation of the C ABI (``cb_bandchol_create``, partitioned
+    batched solve) when the shifted operator is positive definite — the reference's own tests (kinetic operator, sigma
+    below the spectrum; test/linear_operators.jl:72-88) — and otherwise the pivoted band LU ``cb_bandlu_create`` (what
+    BandedMatrices' ``factorize`` calls: LAPACK gbtrf), e.g. for the interior shift of
+    docs/src/bsplines/eigenproblems.md:96-110.  ``method`` = "auto" | "cholesky" | "lu".  ``mul`` is batched over the
+    columns of X."""
 
-    def __init__(self, A, B=None, sigma: float = 0.0):
+    def __init__(self, A, B=None, sigma: float = 0.0, method: str = "auto"):
         from .bsplines import _BSplineOrRestricted
         metric = B
         if isinstance(B, _BSplineOrRestricted):                      # operator_metric(R) = R'R
@@ -232,7 +233,7 @@ class ShiftAndInvert:
             if metric is not None:
                 raise NotImplementedError("ShiftAndInvert of an ImplicitDerivative with a non-trivial metric")
             shifted = _band_axpy(as_banded(A.Delta.scaled(A.c)), A.M, -sigma)
-            self.Ainv = shifted.cholesky()
+            self.Ainv = factorize(shifted, method)
             self.B = A.M
             self.n = A.n
             return
@@ -243,8 +244,7 @@ class ShiftAndInvert:
             shifted = Ab if sigma == 0.0 else _band_axpy(Ab, Diagonal(torch.ones(Ab.n, dtype=torch.float64, device=Ab.data.device)), -sigma)
         else:
             shifted = Ab if sigma == 0.0 else _band_axpy(Ab, metric, -sigma)
-        lu = max(shifted.l, shifted.u)
-        self.Ainv = shifted.widened(lu, lu).cholesky()
+        self.Ainv = factorize(shifted, method)
         self.B = metric
         self.n = Ab.n
 
@@ -268,6 +268,51 @@ class ShiftAndInvert:
         Y = ColMajor(torch.empty((Xc.nvec, self.n), dtype=torch.float64, device=Xc.data.device))
         self.mul(Y, Xc)
         return Y
+
+
+class BandLU:
+    """``lu(A)`` / ``factorize(A)`` of a general ``BandedMatrix`` held on the device (``cb_bandlu_*``: LAPACK gbtrf /
+    gbtrs semantics, partial pivoting); ``ldiv`` is the batched in-place solve."""
+
+    def __init__(self, A: BandedMatrix):
+        if A.m != A.n:
+            raise DimensionMismatch("DimensionMismatch: lu needs a square band")
+        h = C.c_void_p()
+        with torch.cuda.device(A.data.device):
+            _lib.call("cb_bandlu_create", _ptr(A.data), A.n, A.l, A.u, C.byref(h))
+        self.handle, self.n, self.device = h, A.n, A.data.device
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().cb_bandlu_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def ldiv(self, X):
+        Xc = _as_colmajor(X)
+        if Xc.n != self.n:
+            raise DimensionMismatch(f"DimensionMismatch: factor has order {self.n}, X has {Xc.n} rows")
+        _lib.call("cb_bandlu_solve", self.handle, _ptr(Xc.data), Xc.ld, Xc.nvec, _stream())
+        return X
+
+
+def factorize(A: BandedMatrix, method: str = "auto"):
+    """``factorize(A)``: "cholesky" (SPD bands, partitioned batched solve), "lu" (pivoted band LU, any non-singular
+    band) or "auto" = Cholesky when the band is symmetric in shape and the factorisation succeeds, else LU."""
+    if method == "lu":
+        return BandLU(A)
+    if method == "cholesky":
+        lu = max(A.l, A.u)
+        return A.widened(lu, lu).cholesky()
+    if A.m == A.n:
+        try:
+            lu = max(A.l, A.u)
+            return A.widened(lu, lu).cholesky()
+        except ValueError:                                           # not positive definite
+            pass
+    return BandLU(A)
 
 
 class LinearOperator:

@@ -282,6 +282,15 @@ int cb_bandchol_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
 int cb_bandchol_solve(const cb_bandchol *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
 int cb_bandchol_destroy(cb_bandchol *F);
 
+/* factorize(A - sigma*B) of ShiftAndInvert for a general (indefinite) BandedMatrix, src/linear_operators.jl:203-236:
+ * banded LU with partial pivoting (the LAPACK gbtrf / gbtrs that BandedMatrices' `factorize` / `ldiv!` call) and the
+ * in-place batched solve X <- A^-1 X.  band: (l+u+1) x n column-major (device), l + u <= 31.  Exactly singular ->
+ * CB_ERR_ARG (SingularException).  Positive definite operators should prefer cb_bandchol_* (partitioned solve). */
+typedef struct cb_bandlu_s cb_bandlu;
+int cb_bandlu_create(const double *band, cb_i64 n, int l, int u, cb_bandlu **out);
+int cb_bandlu_solve(const cb_bandlu *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
+int cb_bandlu_destroy(cb_bandlu *F);
+
 #ifdef __cplusplus
 }
 #endif

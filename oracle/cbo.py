@@ -684,3 +684,25 @@ def implicit_derivative_apply(dl, d, du, mdv, mev, c, X, alpha=1.0, beta=0.0, Y=
     if beta != 0.0:
         rhs = rhs + beta * np.asarray(Y, dtype=np.float64)
     return c * np.linalg.solve(M, rhs)
+
+
+def bandlu_factor(band, n, l, u):
+    """factorize(A) of a general BandedMatrix = LAPACK dgbtrf (BandedMatrices 0.16 -> LAPACK, un-vendored; this is the
+    routine itself, through SciPy).  band: BandedMatrices data as (n, l+u+1) rows [column j -> band[j, u + i - j]].
+    Returns (ab, ipiv, info) with ab the (2l+u+1) x n LAPACK band array and 0-based pivots."""
+    from scipy.linalg import lapack
+    band = np.asarray(band, dtype=np.float64)
+    ab = np.zeros((2 * l + u + 1, n), order="F")
+    ab[l:, :] = band.T
+    lu, piv, info = lapack.dgbtrf(ab, l, u)
+    return lu, piv, info
+
+
+def bandlu_solve(band, n, l, u, X):
+    """ldiv!(factorize(A), X): LAPACK dgbtrf + dgbtrs."""
+    from scipy.linalg import lapack
+    lu, piv, info = bandlu_factor(band, n, l, u)
+    if info != 0:
+        raise np.linalg.LinAlgError(f"singular band (info = {info})")
+    x, info = lapack.dgbtrs(lu, l, u, np.asfortranarray(X, dtype=np.float64), piv)
+    return x
