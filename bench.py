@@ -181,13 +181,36 @@ def other_kernels(torch, cb, peak_gbs):
         out[tag] = {"us": mn * 1e6, "evals_per_s": 7 * nx / mn, "points_per_s": nx / mn, "GBps": 68 * nx / mn / 1e9,
                     "hbm_frac": 68 * nx / mn / 1e9 / peak_gbs}
         del x, iv, vals
+    # B[x,:] as Julia's SparseMatrixCSC (Int64 colptr/rowval, zeros dropped): evaluation + radix sort by column
+    nx = 1_000_000
+    x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
+    mean, mn = ev_time(torch, lambda: B.eval_csc(x), 5)
+    out["c1_eval_csc_1e6"] = {"us": mn * 1e6, "points_per_s": nx / mn, "note": "includes allocation of the CSC arrays and the nnz read-back"}
+    del x
     mean, mn = ev_time(torch, lambda: (B.T @ B, B.T @ D.T @ D @ B), 10)
     out["c1_assemble_mass_laplacian"] = {"us": mn * 1e6, "note": "launch-latency bound (0.22 MB)"}
+    # banded apply at the C1 basis: k = 7 band (l = u = 6), 1006 x 65 536 vectors
+    S1 = B.T @ D.T @ D @ B
+    nv = 65536
+    X = torch.randn((nv, B.nf), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    mean, mn = ev_time(torch, lambda: cb.mul(Y, S1, X), 5)
+    byt = 2 * 8 * B.nf * nv
+    out["c1_banded_apply_65536vec"] = {"us": mn * 1e6, "GBps": byt / mn / 1e9, "hbm_frac": byt / mn / 1e9 / peak_gbs}
+    del X, Y
     # C3: k = 10 exponential knots, 2e5 intervals, Coulomb + Laplacian bands (62.4 MB, ~1.6 GFLOP)
     B3 = cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 200_000))
     mean, mn = ev_time(torch, lambda: (B3.T @ cb.CoulombPotential(1.0) @ B3, B3.T @ D.T @ D @ B3), 5)
     out["c3_assemble_coulomb_laplacian"] = {"us": mn * 1e6, "GBps": 62.4e6 / mn / 1e9, "hbm_frac": 62.4e6 / mn / 1e9 / peak_gbs,
                                             "fp64_tflops": 1.6e9 / mn / 1e12}
+    # the two assembly kernels alone (C ABI, preallocated band: no Python operator glue in the timed region)
+    band3 = torch.empty((B3.nf, 19), dtype=torch.float64, device="cuda")
+    def asm_pair():
+        _lib.call("cb_bspline_assemble_coulomb", B3.handle, B3.handle, 1.0, 0, B3.nf, 0, B3.nf, 9, 9, _ptr(band3), _stream())
+        _lib.call("cb_bspline_assemble", B3.handle, B3.handle, 1, 1, None, 0, B3.nf, 0, B3.nf, 9, 9, _ptr(band3), _stream())
+    mean, mn = ev_time(torch, asm_pair, 5)
+    out["c3_assemble_coulomb_laplacian_cabi"] = {"us": mn * 1e6, "GBps": 62.4e6 / mn / 1e9, "hbm_frac": 62.4e6 / mn / 1e9 / peak_gbs,
+                                                 "fp64_tflops": 1.6e9 / mn / 1e12}
+    del band3
     T3 = B3.T @ D.T @ D @ B3
     nv = 256
     X = torch.randn((nv, B3.nf), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)

@@ -484,8 +484,9 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
                       i64 nel, int nder, int omax, double *__restrict__ blocks) {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *Lp = sm + (size_t)warp * (omax * omax + 3 * omax);   // [o][o] column-major L'[m + o*m']
-    double *xe = Lp + omax * omax, *we = xe + omax, *ne = we + omax;
+    double *Lp = sm + (size_t)warp * (2 * omax * omax + 3 * omax);   // [o][o] column-major L'[m + o*m']
+    double *rd = Lp + omax * omax;                  // [o][o] 1 / (x_m - x_k), m != k
+    double *xe = rd + omax * omax, *we = xe + omax, *ne = we + omax;
     for (i64 e = (i64)blockIdx.x * FEA_WARPS + warp; e < nel; e += (i64)gridDim.x * FEA_WARPS) {
         const int o = uniform_order > 0 ? uniform_order : order[e];
         const i64 es = uniform_order > 0 ? e * (o - 1) : estart[e];
@@ -494,6 +495,14 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
         __syncwarp();
         for (int t = lane; t < o; t += 32) { xe[t] = x[es + t]; we[t] = wcat[ws + t]; ne[t] = nrm[es + t]; }
         __syncwarp();
+        // the o(o-1) reciprocal node differences once per element: the product form of lagrangeder!
+        // (src/fedvr_derivatives.jl:15-31) divides by them o-2 times per entry, which made this kernel issue-bound on
+        // FP64 divisions (27 M warp instructions at C2)
+        for (int t = lane; t < o * o; t += 32) {
+            const int m = t % o, kk = t / o;
+            rd[m * o + kk] = m == kk ? 0.0 : 1.0 / (xe[m] - xe[kk]);
+        }
+        __syncwarp();
         for (int t = lane; t < o * o; t += 32) {
             const int m = t % o, mp = t / o;
             double v;
@@ -501,11 +510,13 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
                 v = (double)((m == o - 1) - (m == 0)) / (2 * we[m]);
             } else {
                 double f = 1.0;
+                const double xmp = xe[mp];
+                const double *rm = rd + m * o;
                 for (int kk = 0; kk < o; ++kk) {
                     if (kk == m || kk == mp) continue;
-                    f *= (xe[mp] - xe[kk]) / (xe[m] - xe[kk]);
+                    f *= (xmp - xe[kk]) * rm[kk];
                 }
-                v = f / (xe[m] - xe[mp]);
+                v = f * rm[mp];
             }
             Lp[t] = v;
         }
@@ -756,7 +767,8 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
     CB_REQUIRE(omax >= 2, "cb_fedvr_assemble: element order must be >= 2");
     if (omax > CB_FEDVR_OMAX) { cb_set_error("cb_fedvr_assemble: element order %d > %d", omax, CB_FEDVR_OMAX); return CB_ERR_UNSUPPORTED; }
     if (uniform_order <= 0) CB_REQUIRE(estart && order && boff && woff, "cb_fedvr_assemble: per-element arrays required");
-    size_t smem = sizeof(double) * FEA_WARPS * ((size_t)omax * omax + 3 * omax);
+    size_t smem = sizeof(double) * FEA_WARPS * ((size_t)2 * omax * omax + 3 * omax);
+    CB_CUDA(cudaFuncSetAttribute(fedvr_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cb_grid_for(nel, FEA_WARPS, 16);
     fedvr_assemble_kernel<<<grid, FEA_WARPS * 32, smem, (cudaStream_t)stream>>>(x, wcat, nrm, estart, order, boff, woff,
                                                                                 uniform_order, nel, nder, omax, blocks);

@@ -13,6 +13,11 @@ if what == "fedvr":
     A = F.T @ D.T @ D @ F
     X = torch.randn((1024, F.N), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
     fn = lambda: cb.mul(Y, A, X)
+elif what == "fedvr_asm":  # K4 alone: C2 element blocks (order 10, 1e4 elements)
+    F = cb.FEDVR(np.linspace(0, 1000, 10001), 10)
+    def fn():
+        F._ops.clear()
+        return F.T @ D.T @ D @ F
 elif what == "eval":
     B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
     nx = 16_000_000
