@@ -24,6 +24,18 @@ elif what == "eval":
     x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
     iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 7), dtype=torch.float64, device="cuda")
     fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
+elif what == "eval5":      # evaluation on the C5 basis: 5e4 intervals (knots do not fit the shared-memory table), k = 8
+    B = cb.BSpline(cb.LinearKnotSet(8, 0, 500, 50000))
+    nx = 16_000_000
+    x = torch.rand(nx, dtype=torch.float64, device="cuda") * 500
+    iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 8), dtype=torch.float64, device="cuda")
+    fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
+elif what == "eval3":      # evaluation on the C3 basis: 2e5 exponential intervals, k = 10
+    B = cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 200000))
+    nx = 16_000_000
+    x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
+    iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 10), dtype=torch.float64, device="cuda")
+    fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
 elif what == "eval1m":     # C1 size: 1e6 points
     B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
     nx = 1_000_000

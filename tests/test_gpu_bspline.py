@@ -39,6 +39,15 @@ KNOTSETS = [
 ]
 
 
+# knot sets beyond the bank-private replicas (~1100 knots) and beyond the shared-memory table (6144 knots: bucket
+# table + global knots)
+LARGE_KNOTSETS = [
+    ("lin_k5_3000", lambda cb: cb.LinearKnotSet(5, 0, 10, 3000)),
+    ("lin_k4_7000", lambda cb: cb.LinearKnotSet(4, -1, 1, 7000)),
+    ("exp_k3_9000", lambda cb: cb.ExpKnotSet(3, -3.0, 2.0, 9000)),
+]
+
+
 def edge_points(tt, rng, n=400):
     lo, hi = tt[0], tt[-1]
     span = hi - lo
@@ -47,7 +56,7 @@ def edge_points(tt, rng, n=400):
     return np.concatenate([np.asarray(p, dtype=np.float64) for p in pts])
 
 
-@pytest.mark.parametrize("name,make", KNOTSETS, ids=[k[0] for k in KNOTSETS])
+@pytest.mark.parametrize("name,make", KNOTSETS + LARGE_KNOTSETS, ids=[k[0] for k in KNOTSETS + LARGE_KNOTSETS])
 def test_eval_matches_oracle(cb, name, make):
     t = make(cb)
     B = cb.BSpline(t)
