@@ -458,6 +458,7 @@ int cb_bspline_eval_csc(const cb_bspline *B, const double *x, i64 nx, i64 col0, 
     i64 tot = nx * B->k;
     if (tot >= ((i64)1 << 31)) { cb_set_error("cb_bspline_eval_csc: nx*k >= 2^31, split the point batch"); return CB_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
     int32_t *d_iv = nullptr; double *d_vals = nullptr; uint32_t *d_keys = nullptr, *d_idx = nullptr; void *d_tmp = nullptr;
     i64 n1 = tot ? tot : 1;
     CB_CUDA(cudaMallocAsync(&d_iv, sizeof(int32_t) * (nx ? nx : 1), st));

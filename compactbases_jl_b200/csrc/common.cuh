@@ -16,6 +16,7 @@ typedef int64_t i64;
 
 // ---- error plumbing -------------------------------------------------------
 void cb_set_error(const char *fmt, ...);
+int cb_keep_scratch_pool();                    // errors.cu: keep the stream-ordered pool's memory between calls
 
 #define CB_CUDA(call)                                                            \
     do {                                                                         \

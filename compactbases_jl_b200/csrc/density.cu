@@ -881,6 +881,7 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     const i64 M = D->nchunk;
     constexpr int S = K > 1 ? K - 1 : 1;
     double *ws = nullptr;                           // E and the propagated states, [M][K-1][P] each
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
     CB_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * M * S * P, st));
     double *E = ws, *St = ws + M * S * P;
     // grid.y = chunks <= 65535 is checked at plan time
@@ -1007,6 +1008,7 @@ int cb_density_apply(const cb_density *D, const double *f, i64 ldf, i64 Pf,
     if (rc) return rc;
     if (D->refine > 0) {
         double *tmp = nullptr;
+        { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
         CB_CUDA(cudaMallocAsync(&tmp, sizeof(double) * D->ncols * P, st));
         for (int it = 0; it < D->refine && rc == CB_OK; ++it) {
             DensArgs R = A;

@@ -36,6 +36,10 @@ elif what == "eval3":      # evaluation on the C3 basis: 2e5 exponential interva
     x = torch.rand(nx, dtype=torch.float64, device="cuda") * 100
     iv = torch.empty(nx, dtype=torch.int32, device="cuda"); vals = torch.empty((nx, 10), dtype=torch.float64, device="cuda")
     fn = lambda: _lib.call("cb_bspline_eval", B.handle, _ptr(x), nx, 0, _ptr(iv), _ptr(vals), _stream())
+elif what == "csc1m":      # B[x,:] as SparseMatrixCSC, C1 size
+    B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
+    x = torch.rand(1_000_000, dtype=torch.float64, device="cuda") * 100
+    fn = lambda: B.eval_csc(x)
 elif what == "eval1m":     # C1 size: 1e6 points
     B = cb.BSpline(cb.LinearKnotSet(7, 0, 100, 1000))
     nx = 1_000_000
