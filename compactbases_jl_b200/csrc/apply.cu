@@ -345,6 +345,9 @@ constexpr int BT_ROWS = BT_NG * BT_RB * 8;          // 128 rows per CTA tile
 #ifndef BT_PIPE
 #define BT_PIPE 1
 #endif
+#ifndef TP_PIPE
+#define TP_PIPE 1
+#endif
 constexpr int BT_KSMAX = 8;                         // k-steps the pipelined kernel supports (l + u + 1 <= 25)
 #ifndef BTP_NG
 #define BTP_NG 8                                    // compute warps of the pipelined kernel
@@ -645,6 +648,130 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     if (lane == 0 && (w == 0 || w == PROF_NG || w == PROF_NG + 1))
         for (int i = 0; i < 8; ++i) atomicAdd(&fe_prof[i], (unsigned long long)pf[i]);
 #endif
+}
+
+// ---------------------------------------------------------------------------
+// K9, warp-specialised TMA pipeline (same roles as the K7 / K8 pipelines): a loader warp fills a ring of x windows
+// (TP_ROWS + 2 rows x 32 vectors, one bulk copy per column), TP_CW compute warps apply the three-point stencil with
+// lane <-> row (the coefficients of a row stay in registers for all the vector tiles of a work item) into a separate
+// y tile, a storer warp streams the y tiles out.  x buffer of a stage: free again once the compute warps are done
+// (the loader waits on `done`); y buffer: free once the storer has read it (the compute warps wait on `empty`).
+// Same arithmetic, in the same order, as tridiag_apply_kernel.  Requires beta == 0 and X, Y of equal 16-byte phase.
+// ---------------------------------------------------------------------------
+constexpr int TP_CW = 4;                            // compute warps
+constexpr int TP_ROWS = 32 * TP_CW;                 // rows per tile
+constexpr int TP_VEC = 32;                          // vectors per tile
+constexpr int TP_PX = TP_ROWS + 4;                  // x column pitch: halo rows + parity shift, even
+constexpr int TP_PY = TP_ROWS + 2;                  // y column pitch: parity shift, even
+constexpr int TP_STAGE = TP_VEC * (TP_PX + TP_PY);  // doubles per stage
+constexpr int TP_NSTG = 3;
+
+__global__ void __launch_bounds__(32 * (TP_CW + 2), 1)
+tridiag_apply_pipe_kernel(const double *__restrict__ dl, const double *__restrict__ d, const double *__restrict__ du,
+                          i64 n, const double *__restrict__ X, i64 ldx, i64 nvec, int vchunk,
+                          double alpha, double *__restrict__ Y, i64 ldy) {
+    extern __shared__ __align__(128) double sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + (size_t)TP_NSTG * TP_STAGE);
+    uint64_t *full = bars, *done = bars + TP_NSTG, *empty = bars + 2 * TP_NSTG;
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TP_NSTG; ++s) { mbar_init(full + s, 1); mbar_init(done + s, TP_CW); mbar_init(empty + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const i64 nrt = (n + TP_ROWS - 1) / TP_ROWS;
+    const i64 nvt = (nvec + TP_VEC - 1) / TP_VEC;
+    const i64 nvc = (nvt + vchunk - 1) / vchunk;
+    const i64 nitems = nrt * nvc;
+    const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);
+    const int ldodd = (int)(ldx & 1);
+    int stage = 0;
+    unsigned phase = 0;
+    auto next_stage = [&]() { if (++stage == TP_NSTG) { stage = 0; phase ^= 1; } };
+    // window row 0 of a tile is global row g0 = i0 - 1; it sits at xs[c * TP_PX + par_c], par_c = parity of its address
+    auto col_parity = [&](i64 g0, i64 v) { return (int)((xbase + v * ldx + g0) & 1); };
+    if (w < TP_CW) {
+        // ================= compute warps: lane <-> row =========================================
+        const int r = 32 * w + lane;
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;             // row tiles vary fastest
+            const i64 i0 = rt * TP_ROWS, i = i0 + r;
+            const double cd = i < n ? __ldg(d + i) : 0.0;
+            const double cl = (i > 0 && i < n) ? __ldg(dl + i - 1) : 0.0;
+            const double cu = (i < n - 1) ? __ldg(du + i) : 0.0;
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const double *xs = sm + (size_t)stage * TP_STAGE;
+                double *ys = sm + (size_t)stage * TP_STAGE + TP_VEC * TP_PX;
+                const int par0 = col_parity(i0 - 1, vt * TP_VEC);
+                mbar_wait(full + stage, phase);
+                mbar_wait(empty + stage, phase ^ 1);                      // the y buffer's previous tile has left
+#pragma unroll 8
+                for (int c = 0; c < TP_VEC; ++c) {
+                    const int par = (par0 + c * ldodd) & 1;
+                    const double *xc = xs + c * TP_PX + par + r;
+                    const double left = xc[0], mid = xc[1], right = xc[2];
+                    ys[c * TP_PY + (par ^ 1) + r] = alpha * fma(cu, right, fma(cd, mid, cl * left));
+                }
+                fence_proxy_async();                // the storer's bulk copies read what this thread wrote
+                __syncwarp();
+                if (lane == 0) mbar_arrive(done + stage);
+            }
+        }
+    } else if (w == TP_CW) {
+        // ================= loader warp: lane <-> vector column ================================
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;
+            const i64 g0 = rt * TP_ROWS - 1;
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const i64 v0 = vt * TP_VEC;
+                double *xs = sm + (size_t)stage * TP_STAGE;
+                mbar_wait(done + stage, phase ^ 1);                       // the x buffer's previous tile has been consumed
+                const bool vok = v0 + lane < nvec;
+                const int par = col_parity(g0, v0 + lane);
+                double *scol = xs + lane * TP_PX + par;
+                const double *gcol = X + (vok ? v0 + lane : 0) * ldx + g0;
+                if (g0 >= 1 && g0 + TP_ROWS + 2 + 1 <= n && v0 + TP_VEC <= nvec) {
+                    const unsigned bytes = 8u * (unsigned)((TP_ROWS + 2 + par + 1) & ~1);
+                    const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+                    if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
+                    __syncwarp();
+                    bulk_load(scol - par, gcol - par, bytes, full + stage);
+                } else {
+                    int ra = g0 < 0 ? (int)(-g0 < TP_ROWS + 2 ? -g0 : TP_ROWS + 2) : 0;
+                    int rb = g0 + TP_ROWS + 2 > n ? (int)(n - g0 > ra ? n - g0 : ra) : TP_ROWS + 2;
+                    if (!vok) { ra = 0; rb = 0; }
+                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, TP_ROWS + 2);
+                    const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
+                    __syncwarp();
+                    if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
+                    __syncwarp();
+                    if (cp.cnt) bulk_load(scol + cp.a, gcol + cp.a, 8u * (unsigned)cp.cnt, full + stage);
+                }
+            }
+        }
+    } else {
+        // ================= storer warp: lane <-> vector column ================================
+        for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const i64 vc = item / nrt, rt = item - vc * nrt;
+            const i64 i0 = rt * TP_ROWS;
+            const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+                const i64 v0 = vt * TP_VEC;
+                const double *ys = sm + (size_t)stage * TP_STAGE + TP_VEC * TP_PX;
+                mbar_wait(done + stage, phase);
+                const bool vok = v0 + lane < nvec;
+                const int pary = col_parity(i0 - 1, v0 + lane) ^ 1;       // parity of row i0 in X, Y and the y tile
+                const int r_hi = !vok ? 0 : n - i0 < TP_ROWS ? (int)(n - i0) : TP_ROWS;
+                tma_col_store(Y + (vok ? v0 + lane : 0) * ldy + i0, ys + lane * TP_PY + pary, pary, 0, r_hi);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+            }
+        }
+        bulk_wait0();
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1282,6 +1409,22 @@ int cb_tridiag_apply(const double *dl, const double *d, const double *du, i64 n,
     if (n == 0 || nvec == 0) return CB_OK;
     CB_REQUIRE(d != nullptr && (n == 1 || (dl != nullptr && du != nullptr)), "cb_tridiag_apply: NULL diagonal");
     cudaStream_t st = (cudaStream_t)stream;
+#if TP_PIPE
+    // warp-specialised TMA pipeline: beta == 0 (bulk stores do not read Y), X and Y columns of equal 16-byte phase
+    if (beta == 0.0 && n >= 2 * TP_ROWS && ((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 &&
+        ((ldx ^ ldy) & 1) == 0) {
+        const size_t psmem = sizeof(double) * (size_t)TP_NSTG * TP_STAGE + 256;
+        CB_CUDA(cudaFuncSetAttribute(tridiag_apply_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        const i64 nrt = (n + TP_ROWS - 1) / TP_ROWS, nvt = (nvec + TP_VEC - 1) / TP_VEC;
+        i64 vchunk = nrt * nvt / ((i64)CB_NUM_SMS * 8);
+        vchunk = vchunk < 1 ? 1 : (vchunk > 8 ? 8 : vchunk);
+        const i64 pitems = nrt * ((nvt + vchunk - 1) / vchunk);
+        const int pgrid = (int)(pitems < CB_NUM_SMS ? pitems : CB_NUM_SMS);
+        tridiag_apply_pipe_kernel<<<pgrid, 32 * (TP_CW + 2), psmem, st>>>(dl ? dl : d, d, du ? du : d, n, X, ldx, nvec, (int)vchunk, alpha, Y, ldy);
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
+#endif
     bool vec2 = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
     i64 rows_per_blk = (i64)TRI_THREADS * (vec2 ? 2 : 1);
     i64 nrblk = (n + rows_per_blk - 1) / rows_per_blk;

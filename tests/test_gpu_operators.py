@@ -320,3 +320,21 @@ def test_fedvr_apply_pipeline_at_scale(cb, order, nel, nvec, restrict, xshift, y
     Yc = _shifted_colmajor(cb, np.full((nfun, nvec), np.nan), yshift)
     cb.mul(Yc, A, Xc, 0.75, 0.0)
     assert relerr(Yc.numpy(), ref) <= RTOL
+
+
+@pytest.mark.parametrize("n,nvec,xshift,yshift", [
+    (300001, 200, 0, 0),      # odd leading dimension, partial vector tile, the stage ring wraps many times
+    (65536, 96, 0, 0),        # even leading dimension, whole tiles only
+    (5000, 70, 1, 1),         # storage starting on an odd element
+    (5000, 70, 0, 1),         # X and Y differ in phase: non-TMA kernel
+])
+def test_tridiag_apply_pipeline_at_scale(cb, n, nvec, xshift, yshift):
+    import torch
+    rng = np.random.default_rng(n + nvec)
+    dl, d, du = rng.standard_normal(n - 1), rng.standard_normal(n), rng.standard_normal(n - 1)
+    X = rng.standard_normal((n, nvec))
+    T = cb.Tridiagonal(*(torch.as_tensor(v, device="cuda") for v in (dl, d, du)))
+    Xc = _shifted_colmajor(cb, X, xshift)
+    Yc = _shifted_colmajor(cb, np.full((n, nvec), np.nan), yshift)
+    cb.mul(Yc, T, Xc, -0.75, 0.0)
+    assert relerr(Yc.numpy(), cbo.tridiag_apply(dl, d, du, X, -0.75, 0.0, np.zeros((n, nvec), order="F"))) <= RTOL
