@@ -658,13 +658,22 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
 // (the loader waits on `done`); y buffer: free once the storer has read it (the compute warps wait on `empty`).
 // Same arithmetic, in the same order, as tridiag_apply_kernel.  Requires beta == 0 and X, Y of equal 16-byte phase.
 // ---------------------------------------------------------------------------
-constexpr int TP_CW = 4;                            // compute warps
+// Measured (N = 1e7 x 128 vectors, device time): rows x vectors per tile 64x32: 5.96 ms | 96x32: 4.24 | 128x32: 3.45 |
+// 160x32: 3.59 | 192x32: 3.30 | 256x16: 3.28 | 512x8: 3.25 | 384x16: 3.13 (previous kernel: 3.71) — the longer the bulk copies
+// (3 KB per column at 384 rows) the better the TMA unit does, as long as two stages still fit.
+#ifndef TP_CWARPS
+#define TP_CWARPS 12
+#endif
+constexpr int TP_CW = TP_CWARPS;                    // compute warps
 constexpr int TP_ROWS = 32 * TP_CW;                 // rows per tile
-constexpr int TP_VEC = 32;                          // vectors per tile
+#ifndef TP_NVEC
+#define TP_NVEC 16
+#endif
+constexpr int TP_VEC = TP_NVEC;                     // vectors per tile (<= 32: one loader / storer lane per column)
 constexpr int TP_PX = TP_ROWS + 4;                  // x column pitch: halo rows + parity shift, even
 constexpr int TP_PY = TP_ROWS + 2;                  // y column pitch: parity shift, even
 constexpr int TP_STAGE = TP_VEC * (TP_PX + TP_PY);  // doubles per stage
-constexpr int TP_NSTG = 3;
+constexpr int TP_NSTG = (227 * 1024 - 256) / (TP_STAGE * 8) > 6 ? 6 : (227 * 1024 - 256) / (TP_STAGE * 8);
 
 __global__ void __launch_bounds__(32 * (TP_CW + 2), 1)
 tridiag_apply_pipe_kernel(const double *__restrict__ dl, const double *__restrict__ d, const double *__restrict__ du,
@@ -729,21 +738,21 @@ tridiag_apply_pipe_kernel(const double *__restrict__ dl, const double *__restric
                 const i64 v0 = vt * TP_VEC;
                 double *xs = sm + (size_t)stage * TP_STAGE;
                 mbar_wait(done + stage, phase ^ 1);                       // the x buffer's previous tile has been consumed
-                const bool vok = v0 + lane < nvec;
+                const bool vok = lane < TP_VEC && v0 + lane < nvec;
                 const int par = col_parity(g0, v0 + lane);
-                double *scol = xs + lane * TP_PX + par;
+                double *scol = xs + (lane < TP_VEC ? lane : 0) * TP_PX + par;
                 const double *gcol = X + (vok ? v0 + lane : 0) * ldx + g0;
                 if (g0 >= 1 && g0 + TP_ROWS + 2 + 1 <= n && v0 + TP_VEC <= nvec) {
-                    const unsigned bytes = 8u * (unsigned)((TP_ROWS + 2 + par + 1) & ~1);
+                    const unsigned bytes = lane < TP_VEC ? 8u * (unsigned)((TP_ROWS + 2 + par + 1) & ~1) : 0u;
                     const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
                     if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
                     __syncwarp();
-                    bulk_load(scol - par, gcol - par, bytes, full + stage);
+                    if (lane < TP_VEC) bulk_load(scol - par, gcol - par, bytes, full + stage);
                 } else {
                     int ra = g0 < 0 ? (int)(-g0 < TP_ROWS + 2 ? -g0 : TP_ROWS + 2) : 0;
                     int rb = g0 + TP_ROWS + 2 > n ? (int)(n - g0 > ra ? n - g0 : ra) : TP_ROWS + 2;
                     if (!vok) { ra = 0; rb = 0; }
-                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, TP_ROWS + 2);
+                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, lane < TP_VEC ? TP_ROWS + 2 : 0);
                     const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
                     __syncwarp();
                     if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
@@ -762,10 +771,10 @@ tridiag_apply_pipe_kernel(const double *__restrict__ dl, const double *__restric
                 const i64 v0 = vt * TP_VEC;
                 const double *ys = sm + (size_t)stage * TP_STAGE + TP_VEC * TP_PX;
                 mbar_wait(done + stage, phase);
-                const bool vok = v0 + lane < nvec;
+                const bool vok = lane < TP_VEC && v0 + lane < nvec;
                 const int pary = col_parity(i0 - 1, v0 + lane) ^ 1;       // parity of row i0 in X, Y and the y tile
                 const int r_hi = !vok ? 0 : n - i0 < TP_ROWS ? (int)(n - i0) : TP_ROWS;
-                tma_col_store(Y + (vok ? v0 + lane : 0) * ldy + i0, ys + lane * TP_PY + pary, pary, 0, r_hi);
+                tma_col_store(Y + (vok ? v0 + lane : 0) * ldy + i0, ys + (lane < TP_VEC ? lane : 0) * TP_PY + pary, pary, 0, r_hi);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + stage);
             }
