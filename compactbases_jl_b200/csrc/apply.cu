@@ -352,8 +352,16 @@ constexpr int BT_KSMAX = 8;                         // k-steps the pipelined ker
 #ifndef BTP_NG
 #define BTP_NG 8                                    // compute warps of the pipelined kernel
 #endif
-constexpr int BTP_RB = BT_ROWS / 8 / BTP_NG;        // 8-row blocks per compute warp
-constexpr int BTP_NAV = (BT_ROWS / 8) * BT_KSMAX * 32 / (32 * BTP_NG);   // A-fragment entries per compute thread
+#ifndef BTP_NROWS
+#define BTP_NROWS 128
+#endif
+#ifndef BTP_NVEC
+#define BTP_NVEC 32
+#endif
+constexpr int BTP_ROWS = BTP_NROWS;                 // rows per tile of the pipelined kernel
+constexpr int BTP_VEC = BTP_NVEC;                   // vectors per tile (<= 32: one loader / storer lane per column)
+constexpr int BTP_RB = BTP_ROWS / 8 / BTP_NG;       // 8-row blocks per compute warp
+constexpr int BTP_NAV = (BTP_ROWS / 8) * BT_KSMAX * 32 / (32 * BTP_NG);   // A-fragment entries per compute thread
 #ifndef BT_GRIDCAP
 #define BT_GRIDCAP 1024                             // CTAs per SM in the grid at most (items beyond that are strided)
 #endif
@@ -466,11 +474,11 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     extern __shared__ __align__(128) double sm[];
     const int W = l + u + 1;
     const int KS = (8 + W - 1 + 3) / 4;             // k-steps per 8-row block
-    const int xrows = BT_ROWS + l + u;
+    const int xrows = BTP_ROWS + l + u;
     const int wrows = xrows + 3;                    // + the k padding of the last row block
-    const int STAGE = BT_VEC * P0;
-    double *as = sm + (size_t)nstg * STAGE;         // [BT_ROWS/8][KS][32] A fragments of the current item
-    uint64_t *bars = reinterpret_cast<uint64_t *>(as + (BT_ROWS / 8) * KS * 32);
+    const int STAGE = BTP_VEC * P0;
+    double *as = sm + (size_t)nstg * STAGE;         // [BTP_ROWS/8][KS][32] A fragments of the current item
+    uint64_t *bars = reinterpret_cast<uint64_t *>(as + (BTP_ROWS / 8) * KS * 32);
     uint64_t *full = bars, *done = bars + nstg, *empty = bars + 2 * nstg;
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -479,8 +487,8 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const i64 nrt = (m + BT_ROWS - 1) / BT_ROWS;
-    const i64 nvt = (nvec + BT_VEC - 1) / BT_VEC;
+    const i64 nrt = (m + BTP_ROWS - 1) / BTP_ROWS;
+    const i64 nvt = (nvec + BTP_VEC - 1) / BTP_VEC;
     const i64 nvc = (nvt + vchunk - 1) / vchunk;
     const i64 nitems = nrt * nvc;
     const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);
@@ -507,31 +515,31 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         double av[BTP_NAV];
         auto fetch_frags = [&](i64 item_) {
             i64 vc_, rt_; item_coords(item_, vc_, rt_);
-            const i64 i0_ = rt_ * BT_ROWS;
+            const i64 i0_ = rt_ * BTP_ROWS;
 #pragma unroll
             for (int t = 0; t < BTP_NAV; ++t) {
                 const int e = threadIdx.x + t * 32 * BTP_NG;
                 const int ln = e & 31, ks = (e >> 5) % KS, rb = (e >> 5) / KS;
                 const i64 i = i0_ + 8 * rb + (ln >> 2), j = i0_ + 8 * rb - l + 4 * ks + (ln & 3);
-                av[t] = (e < (BT_ROWS / 8) * KS * 32 && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
+                av[t] = (e < (BTP_ROWS / 8) * KS * 32 && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
                             ? __ldg(band + (u + i - j) + (i64)W * j) : 0.0;
             }
         };
         if ((i64)blockIdx.x < nitems) fetch_frags(blockIdx.x);
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
-            const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
+            const i64 i0 = rt * BTP_ROWS, g0 = i0 - l;
             named_bar_sync(1, 32 * BTP_NG);          // the previous item's fragments are no longer read
 #pragma unroll
             for (int t = 0; t < BTP_NAV; ++t) {
                 const int e = threadIdx.x + t * 32 * BTP_NG;
-                if (e < (BT_ROWS / 8) * KS * 32) as[e] = av[t];
+                if (e < (BTP_ROWS / 8) * KS * 32) as[e] = av[t];
             }
             named_bar_sync(1, 32 * BTP_NG);
             FE_PROF_L(7);
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
-                const i64 v0 = vt * BT_VEC;
+                const i64 v0 = vt * BTP_VEC;
                 double *xs = sm + (size_t)stage * STAGE;
                 const int par_r = col_parity(g0, v0 + gq);
                 const int par_c0 = col_parity(g0, v0 + 2 * tq), par_c1 = col_parity(g0, v0 + 2 * tq + 1);
@@ -540,11 +548,11 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                 FE_PROF_L(2);
                 // A dependent DMMA has ~180 cycles of latency: the k-steps of the warp's BTP_RB row blocks advance
                 // together, BTP_RB * 4 independent accumulator chains in flight
-                double c[BTP_RB][BT_VEC / 8][2];
+                double c[BTP_RB][BTP_VEC / 8][2];
 #pragma unroll
                 for (int q = 0; q < BTP_RB; ++q)
 #pragma unroll
-                    for (int nt = 0; nt < BT_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
+                    for (int nt = 0; nt < BTP_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
                 {
                     const double *af = as + w * BTP_RB * KS * 32 + lane;
                     const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * w * BTP_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
@@ -553,7 +561,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                         for (int q = 0; q < BTP_RB; ++q) {
                             const double a = af[(q * KS + ks) * 32];
 #pragma unroll
-                            for (int nt = 0; nt < BT_VEC / 8; ++nt)
+                            for (int nt = 0; nt < BTP_VEC / 8; ++nt)
                                 dmma884(c[q][nt][0], c[q][nt][1], a, xb[q * 8 + nt * 8 * P0 + 4 * ks]);
                         }
                     }
@@ -567,7 +575,7 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                     double *y0 = xs + (2 * tq) * P0 + fe_swz(2 * tq) + par_c0 + row;
                     double *y1 = xs + (2 * tq + 1) * P0 + fe_swz(2 * tq + 1) + par_c1 + row;
 #pragma unroll
-                    for (int nt = 0; nt < BT_VEC / 8; ++nt) {
+                    for (int nt = 0; nt < BTP_VEC / 8; ++nt) {
                         y0[nt * 8 * P0] = wscale * c[q][nt][0];
                         y1[nt * 8 * P0] = wscale * c[q][nt][1];
                     }
@@ -582,31 +590,32 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         // ================= loader warp: lane <-> vector column ================================
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
-            const i64 g0 = rt * BT_ROWS - l;        // matrix column of window row 0
+            const i64 g0 = rt * BTP_ROWS - l;        // matrix column of window row 0
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
-                const i64 v0 = vt * BT_VEC;
+                const i64 v0 = vt * BTP_VEC;
                 double *xs = sm + (size_t)stage * STAGE;
                 mbar_wait(empty + stage, phase ^ 1);
                 FE_PROF_L(0);
-                if (g0 >= 1 && g0 + wrows + 1 <= n && v0 + BT_VEC <= nvec) {
-                    const int par = col_parity(g0, v0 + lane);
-                    const unsigned bytes = 8u * (unsigned)((wrows + par + 1) & ~1);
+                const int cl = lane < BTP_VEC ? lane : 0;             // lanes beyond the tile's columns idle
+                if (g0 >= 1 && g0 + wrows + 1 <= n && v0 + BTP_VEC <= nvec) {
+                    const int par = col_parity(g0, v0 + cl);
+                    const unsigned bytes = lane < BTP_VEC ? 8u * (unsigned)((wrows + par + 1) & ~1) : 0u;
                     const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
                     if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
                     __syncwarp();
-                    bulk_load(xs + lane * P0 + fe_swz(lane), X + (v0 + lane) * ldx + g0 - par, bytes, full + stage);
+                    if (lane < BTP_VEC) bulk_load(xs + cl * P0 + fe_swz(cl), X + (v0 + cl) * ldx + g0 - par, bytes, full + stage);
                 } else {
                     // clipped window (first / last row tiles, partial vector tile): valid rows through the TMA unit as
                     // well, the rest zero
-                    const bool vok = v0 + lane < nvec;
-                    const int par = col_parity(g0, v0 + lane);
+                    const bool vok = lane < BTP_VEC && v0 + lane < nvec;
+                    const int par = col_parity(g0, v0 + cl);
                     int ra = g0 < 0 ? (int)(-g0 < wrows ? -g0 : wrows) : 0;
                     int rb = g0 + wrows > n ? (int)(n - g0 > ra ? n - g0 : ra) : wrows;
                     if (!vok) { ra = 0; rb = 0; }
-                    double *scol = xs + lane * P0 + fe_swz(lane) + par;
+                    double *scol = xs + cl * P0 + fe_swz(cl) + par;
                     const double *gcol = X + (vok ? v0 + lane : 0) * ldx + g0;
-                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, wrows);
+                    const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, lane < BTP_VEC ? wrows : 0);
                     const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
                     __syncwarp();
                     if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
@@ -620,20 +629,21 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
         // ================= storer warp: lane <-> vector column ================================
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
-            const i64 i0 = rt * BT_ROWS, g0 = i0 - l;
+            const i64 i0 = rt * BTP_ROWS, g0 = i0 - l;
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
             for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
-                const i64 v0 = vt * BT_VEC;
+                const i64 v0 = vt * BTP_VEC;
                 const double *xs = sm + (size_t)stage * STAGE;
                 mbar_wait(done + stage, phase);
                 FE_PROF_L(5);
                 {
                     // rows i0 .. of column lane: the 16-byte aligned part as a bulk copy, an odd end element through the
                     // lane (X, Y and the window have the same parity per column, checked by the launcher)
-                    const bool vok = v0 + lane < nvec;
-                    const int par = col_parity(g0, v0 + lane);
-                    const int r_hi = !vok ? 0 : m - i0 < BT_ROWS ? (int)(m - i0) : BT_ROWS;
-                    const double *ys = xs + lane * P0 + fe_swz(lane) + par + l;
+                    const int cl = lane < BTP_VEC ? lane : 0;
+                    const bool vok = lane < BTP_VEC && v0 + lane < nvec;
+                    const int par = col_parity(g0, v0 + cl);
+                    const int r_hi = !vok ? 0 : m - i0 < BTP_ROWS ? (int)(m - i0) : BTP_ROWS;
+                    const double *ys = xs + cl * P0 + fe_swz(cl) + par + l;
                     double *yc = Y + (vok ? v0 + lane : 0) * ldy + i0;
                     tma_col_store(yc, ys, par + l, 0, r_hi);
                 }
@@ -1516,14 +1526,15 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     // warp-specialised TMA pipeline: needs non-negative bandwidths and X, Y columns of equal 16-byte phase
     if (l >= 0 && u >= 0 && KS <= BT_KSMAX && beta == 0.0 &&
         ((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && ((ldx ^ ldy) & 1) == 0) {
-        const int P0 = (xrows + 3 + 2 + 12 + 15) / 16 * 16;      // window + k padding + parity shift / rounding + skew
-        const size_t stage_b = sizeof(double) * BT_VEC * P0, as_b = sizeof(double) * (BT_ROWS / 8) * KS * 32;
+        const int P0 = (BTP_ROWS + l + u + 3 + 2 + 12 + 15) / 16 * 16;      // window + k padding + parity shift / rounding + skew
+        const size_t stage_b = sizeof(double) * BTP_VEC * P0, as_b = sizeof(double) * (BTP_ROWS / 8) * KS * 32;
         int nstg = (int)((227 * 1024 - as_b - 256) / stage_b);
         if (nstg > 6) nstg = 6;
         if (nstg >= 2) {
             const size_t psmem = nstg * stage_b + as_b + 256;
             CB_CUDA(cudaFuncSetAttribute(banded_apply_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
             // vector tiles per work item: the one of 8..4 (1 if there are few) that deals the items most evenly
+            const i64 nrt = (m + BTP_ROWS - 1) / BTP_ROWS, nvt = (nvec + BTP_VEC - 1) / BTP_VEC;
             i64 best = 1;
             if (nrt * nvt >= (i64)CB_NUM_SMS * 8) {
                 double best_eff = 0.0;
