@@ -12,7 +12,7 @@ from .knot_sets import ArbitraryKnotSet, ExpKnotSet, LinearKnotSet
 from .quadrature import gausslegendre, gausslobatto, num_quadrature_points
 from .lazy import CoulombDerivative, Derivative, QuasiDiagonal, materialize
 from .operators import (BandCholesky, BandLU, BandedMatrix, ColMajor, Diagonal, FEDVRMatrix, ImplicitDerivative, LinearOperator, ShiftAndInvert,
-                        SymTridiagonal, Tridiagonal, as_banded, axpby, factorize, mul)
+                        SymTridiagonal, Tridiagonal, as_banded, axpby, batched_dot, factorize, inner_product, mul, norm)
 from .bsplines import BSpline, CoulombPotential, RestrictedBSpline, SparseMatrixCSC, diffop
 from .fedvr import FEDVR, RestrictedFEDVR
 from .finite_differences import (FiniteDifferences, ImplicitFiniteDifferences, RestrictedFiniteDifferences,
@@ -24,6 +24,6 @@ __all__ = [
     "CoulombPotential", "diffop", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
     "RestrictedFiniteDifferences", "Derivative", "QuasiDiagonal", "CoulombDerivative", "materialize",
     "BandedMatrix", "BandCholesky", "LinearOperator", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
-    "Density", "FunctionProduct", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
+    "Density", "FunctionProduct", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "batched_dot", "inner_product", "norm", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
     "num_quadrature_points",
 ]

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "cb_tridiag_apply_host": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64]),
     "cb_diag_apply": (cint, [vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_axpby": (cint, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
+    "cb_batched_dot": (cint, [vp, i64, vp, i64, i64, i64, dbl, vp, vp]),
     "cb_density_bspline_create": (cint, [vp, i64, i64, vp, C.POINTER(vp)]),
     "cb_density_destroy": (cint, [vp]),
     "cb_density_set_refine": (cint, [vp, cint]),

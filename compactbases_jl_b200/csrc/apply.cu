@@ -117,6 +117,41 @@ __global__ void axpby_kernel(i64 n, i64 nvec, double alpha, const double *__rest
             Y[i + ldy * v] = axpby(X[i + ldx * v], alpha, beta, Y + i + ldy * v);
 }
 
+// out[p] = scale * sum_i U[i, p] * W[i, p]: the pairwise inner products u_p' (S v_p) once W = S V has been applied
+// (src/inner_products.jl:22-46; FE-DVR / finite differences: W = V, scale = 1 or the grid step, :3-4).  One CTA per
+// pair; every thread sums a strided slice in row order, then a fixed shuffle / shared-memory tree: the result does not
+// depend on the launch geometry of other pairs and is reproducible run to run.
+constexpr int DOT_THREADS = 512;
+__global__ void __launch_bounds__(DOT_THREADS)
+batched_dot_kernel(const double *__restrict__ U, i64 ldu, const double *__restrict__ Wm, i64 ldw, i64 n, i64 P,
+                   double scale, double *__restrict__ out) {
+    __shared__ double part[DOT_THREADS / 32];
+    for (i64 p = blockIdx.x; p < P; p += gridDim.x) {
+        const double *u = U + p * ldu, *w = Wm + p * ldw;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;           // four chains: loads of four rows in flight per thread
+        i64 i = threadIdx.x;
+        for (; i + 3 * DOT_THREADS < n; i += 4 * DOT_THREADS) {
+            s0 = fma(u[i], w[i], s0);
+            s1 = fma(u[i + DOT_THREADS], w[i + DOT_THREADS], s1);
+            s2 = fma(u[i + 2 * DOT_THREADS], w[i + 2 * DOT_THREADS], s2);
+            s3 = fma(u[i + 3 * DOT_THREADS], w[i + 3 * DOT_THREADS], s3);
+        }
+        for (; i < n; i += DOT_THREADS) s0 = fma(u[i], w[i], s0);
+        double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();                            // part[] of the previous pair has been read
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double t = threadIdx.x < DOT_THREADS / 32 ? part[threadIdx.x] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) out[p] = scale * t;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Shared-memory tile helpers (rows x TV vectors, xs[v*pitch + row]).
 // ---------------------------------------------------------------------------
@@ -1500,6 +1535,17 @@ int cb_axpby(i64 n, i64 nvec, double alpha, const double *X, i64 ldx, double bet
     if (n == 0 || nvec == 0) return CB_OK;
     dim3 grid((unsigned)cb_grid_for(n, 256, 4), (unsigned)(nvec < 4096 ? nvec : 4096));
     axpby_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, nvec, alpha, X, ldx, beta, Y, ldy);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_batched_dot(const double *U, i64 ldu, const double *W, i64 ldw, i64 n, i64 P, double scale, double *out, void *stream) {
+    CB_REQUIRE(n >= 0 && P >= 0, "cb_batched_dot: negative size");
+    if (P == 0) return CB_OK;
+    CB_REQUIRE(U != nullptr && W != nullptr && out != nullptr, "cb_batched_dot: NULL array");
+    CB_REQUIRE(ldu >= n && ldw >= n, "DimensionMismatch: cb_batched_dot: leading dimension smaller than the number of rows");
+    const i64 grid = P < (i64)CB_NUM_SMS * 16 ? P : (i64)CB_NUM_SMS * 16;
+    batched_dot_kernel<<<(unsigned)grid, DOT_THREADS, 0, (cudaStream_t)stream>>>(U, ldu, W, ldw, n, P, scale, out);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

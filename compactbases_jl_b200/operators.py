@@ -533,3 +533,34 @@ def mul(Y, A, X, alpha: float = 1.0, beta: float = 0.0):
                                 f"Y has size ({Yc.n},{Yc.nvec})")
     A._mul(Yc, X, float(alpha), float(beta))
     return Y
+
+
+def batched_dot(U, W, scale: float = 1.0) -> torch.Tensor:
+    """``out[p] = scale * sum_i U[i,p] W[i,p]`` for ColMajor batches of equal shape (``cb_batched_dot``); returns a
+    device tensor of P doubles."""
+    Uc, Wc = _as_colmajor(U), _as_colmajor(W)
+    if (Uc.n, Uc.nvec) != (Wc.n, Wc.nvec):
+        raise DimensionMismatch(f"DimensionMismatch: U is {Uc.n}x{Uc.nvec}, W is {Wc.n}x{Wc.nvec}")
+    out = torch.empty(Uc.nvec, dtype=torch.float64, device=Uc.data.device)
+    _lib.call("cb_batched_dot", _ptr(Uc.data), Uc.ld, _ptr(Wc.data), Wc.ld, Uc.n, Uc.nvec, float(scale), _ptr(out), _stream())
+    return out
+
+
+def inner_product(u, R, v) -> torch.Tensor:
+    """Pairwise ``(R*u_p)' (R*v_p)`` for coefficient batches u, v in the basis R (src/inner_products.jl:3-46):
+    ``u_p' S v_p`` with the metric S = R'R for B-splines (banded apply + batched dot), ``step(R) * u_p' v_p`` for finite
+    differences, ``u_p' v_p`` for FE-DVR.  Returns P doubles on the device."""
+    from .bsplines import _BSplineOrRestricted
+    uc, vc = _as_colmajor(u), _as_colmajor(v)
+    if isinstance(R, _BSplineOrRestricted):
+        S = R.S if hasattr(R, "S") else R.T @ R
+        W = ColMajor(torch.empty_like(vc.data))
+        mul(W, S, vc)
+        return batched_dot(uc, W)
+    scale = R.parent_basis.mass_value() if hasattr(R.parent_basis, "mass_value") else 1.0
+    return batched_dot(uc, vc, scale)
+
+
+def norm(v, R) -> torch.Tensor:
+    """``norm(R*v_p)`` per column (src/inner_products.jl:60-84)."""
+    return torch.sqrt(inner_product(v, R, v))

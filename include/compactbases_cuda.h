@@ -229,6 +229,12 @@ int cb_diag_apply(const double *d, cb_i64 n, const double *X, cb_i64 ldx, cb_i64
  * `y .= beta .* y .+ alpha .* rho` of DiagonalOperator's mul!, src/linear_operators.jl:129-138. */
 int cb_axpby(cb_i64 n, cb_i64 nvec, double alpha, const double *X, cb_i64 ldx,
              double beta, double *Y, cb_i64 ldy, void *stream);
+/* Pairwise inner products of coefficient batches, src/inner_products.jl:3-46 (`u' * (S*v)`, `dot(u, S, v)`, `norm`):
+ * out[p] = scale * sum_i U[i,p] * W[i,p] with W = S*V already applied (cb_banded_apply for B-splines; W = V and
+ * scale = step(B) for finite differences, scale = 1 for FE-DVR).  out: P doubles on the device; the summation order
+ * is fixed (reproducible). */
+int cb_batched_dot(const double *U, cb_i64 ldu, const double *W, cb_i64 ldw, cb_i64 n, cb_i64 P,
+                   double scale, double *out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Mutual densities (src/densities.jl).  rho = C * (conj(RV f) .* (LV g)).

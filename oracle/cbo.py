@@ -706,3 +706,11 @@ def bandlu_solve(band, n, l, u, X):
         raise np.linalg.LinAlgError(f"singular band (info = {info})")
     x, info = lapack.dgbtrs(lu, l, u, np.asfortranarray(X, dtype=np.float64), piv)
     return x
+
+
+def inner_products(U, V, S=None, scale=1.0):
+    """Pairwise u_p' S v_p (src/inner_products.jl:22-46; S = None: orthogonal bases, scale = step(B) for finite
+    differences, :3-4) on dense copies."""
+    U, V = np.asarray(U, dtype=np.float64), np.asarray(V, dtype=np.float64)
+    W = V if S is None else np.asarray(S) @ V
+    return scale * np.einsum("ip,ip->p", U, W)

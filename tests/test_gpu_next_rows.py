@@ -392,3 +392,37 @@ def test_shift_and_invert_hydrogen_docs_table(cb):
     X = np.random.default_rng(61).standard_normal((Br.size(), 4))
     got = (Mi @ cb.ColMajor.from_numpy(X)).numpy()
     assert relerr(got, cbo.shift_invert_apply(H.dense(), S.dense(), -0.1, X)) <= 1e-10
+
+
+# ---------------------------------------------------------------------------
+# Inner products and norms of coefficient batches (src/inner_products.jl)
+# ---------------------------------------------------------------------------
+def test_inner_products_and_norms(cb):
+    """test/inner_products.jl:1-68: f = sin(2 pi r), g = cos(2 pi r) on [0, 1]: <f|f> = <g|g> = 1/2, <f|g> = 0, for
+    every basis; plus the pairwise batch form against the dense restatement."""
+    rmax, rho, k = 1.0, 0.1, 7
+    N = int(np.ceil(rmax / rho))
+    f = lambda r: np.sin(2 * np.pi * r)
+    g = lambda r: np.cos(2 * np.pi * r)
+    bases = [cb.FiniteDifferences(N, rho), cb.StaggeredFiniteDifferences(N, rho), cb.ImplicitFiniteDifferences(N, rho),
+             cb.FEDVR(cbo.julia_range(0, rmax, 3), k), cb.BSpline(cb.LinearKnotSet(k, 0, rmax, 3))]
+    for R in bases:
+        c, d = R.ldiv(f), R.ldiv(g)
+        ff = cb.inner_product(c, R, c).item()
+        gg = cb.inner_product(d, R, d).item()
+        fg = cb.inner_product(c, R, d).item()
+        # the reference's own tolerances; the coarse finite-difference grids carry the quadrature error of 10 points
+        assert abs(ff - 0.5) <= (1e-3 * 0.5 if not isinstance(R, cb.StaggeredFiniteDifferences) else 0.06), (type(R).__name__, ff)
+        assert abs(gg - 0.5) <= 0.06 and abs(fg) <= 1e-13, (type(R).__name__, gg, fg)
+        assert abs(cb.norm(c, R).item() - np.sqrt(ff)) <= 1e-15
+    # batch form at a size with many rows per thread
+    B = cb.BSpline(cb.LinearKnotSet(5, 0, 10, 3000))
+    rng = np.random.default_rng(71)
+    U, V = rng.standard_normal((B.nf, 21)), rng.standard_normal((B.nf, 21))
+    got = cb.inner_product(cb.ColMajor.from_numpy(U), B, cb.ColMajor.from_numpy(V)).cpu().numpy()
+    S = (B.T @ B).dense()
+    assert relerr(got, cbo.inner_products(U, V, S)) <= 1e-12
+    R = cb.StaggeredFiniteDifferences(100000, 1e-3)
+    U, V = rng.standard_normal((100000, 5)), rng.standard_normal((100000, 5))
+    got = cb.inner_product(cb.ColMajor.from_numpy(U), R, cb.ColMajor.from_numpy(V)).cpu().numpy()
+    assert relerr(got, cbo.inner_products(U, V, None, 1e-3)) <= 1e-12
