@@ -477,6 +477,8 @@ __global__ void band_to_tridiag_kernel(const double *__restrict__ band, i64 n, d
 // ---------------------------------------------------------------------------
 constexpr int FEA_WARPS = 4;
 
+// OT > 0: the (uniform) element order at compile time — index arithmetic without integer divisions, unrolled sums.
+template <int OT>
 __global__ void __launch_bounds__(FEA_WARPS * 32)
 fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ wcat, const double *__restrict__ nrm,
                       const i64 *__restrict__ estart, const int32_t *__restrict__ order,
@@ -488,7 +490,7 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
     double *rd = Lp + omax * omax;                  // [o][o] 1 / (x_m - x_k), m != k
     double *xe = rd + omax * omax, *we = xe + omax, *ne = we + omax;
     for (i64 e = (i64)blockIdx.x * FEA_WARPS + warp; e < nel; e += (i64)gridDim.x * FEA_WARPS) {
-        const int o = uniform_order > 0 ? uniform_order : order[e];
+        const int o = OT > 0 ? OT : (uniform_order > 0 ? uniform_order : order[e]);
         const i64 es = uniform_order > 0 ? e * (o - 1) : estart[e];
         const i64 ws = uniform_order > 0 ? e * o : woff[e];
         const i64 bo = uniform_order > 0 ? e * (i64)o * o : boff[e];
@@ -512,7 +514,8 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
                 double f = 1.0;
                 const double xmp = xe[mp];
                 const double *rm = rd + m * o;
-                for (int kk = 0; kk < o; ++kk) {
+#pragma unroll
+                for (int kk = 0; kk < (OT > 0 ? OT : o); ++kk) {
                     if (kk == m || kk == mp) continue;
                     f *= (xmp - xe[kk]) * rm[kk];
                 }
@@ -528,7 +531,8 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
                 s = we[m] * Lp[mp + o * m];
             } else {
                 s = 0.0;
-                for (int qd = 0; qd < o; ++qd) s += (-Lp[m + o * qd]) * (we[qd] * Lp[mp + o * qd]);
+#pragma unroll
+                for (int qd = 0; qd < (OT > 0 ? OT : o); ++qd) s += (-Lp[m + o * qd]) * (we[qd] * Lp[mp + o * qd]);
             }
             blocks[bo + t] = ne[m] * ne[mp] * s;
         }
@@ -768,10 +772,22 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
     if (omax > CB_FEDVR_OMAX) { cb_set_error("cb_fedvr_assemble: element order %d > %d", omax, CB_FEDVR_OMAX); return CB_ERR_UNSUPPORTED; }
     if (uniform_order <= 0) CB_REQUIRE(estart && order && boff && woff, "cb_fedvr_assemble: per-element arrays required");
     size_t smem = sizeof(double) * FEA_WARPS * ((size_t)2 * omax * omax + 3 * omax);
-    CB_CUDA(cudaFuncSetAttribute(fedvr_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = cb_grid_for(nel, FEA_WARPS, 16);
-    fedvr_assemble_kernel<<<grid, FEA_WARPS * 32, smem, (cudaStream_t)stream>>>(x, wcat, nrm, estart, order, boff, woff,
-                                                                                uniform_order, nel, nder, omax, blocks);
+    auto launch = [&](auto kern) -> int {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, FEA_WARPS * 32, smem, (cudaStream_t)stream>>>(x, wcat, nrm, estart, order, boff, woff,
+                                                                   uniform_order, nel, nder, omax, blocks);
+        return CB_OK;
+    };
+    int lrc = CB_OK;
+    switch (uniform_order) {
+#define CB_FEA(OO) case OO: lrc = launch(fedvr_assemble_kernel<OO>); break;
+        CB_FEA(2) CB_FEA(3) CB_FEA(4) CB_FEA(5) CB_FEA(6) CB_FEA(7) CB_FEA(8) CB_FEA(9) CB_FEA(10)
+        CB_FEA(11) CB_FEA(12) CB_FEA(13) CB_FEA(14) CB_FEA(15) CB_FEA(16)
+#undef CB_FEA
+        default: lrc = launch(fedvr_assemble_kernel<0>); break;
+    }
+    if (lrc) return lrc;
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
