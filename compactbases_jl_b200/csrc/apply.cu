@@ -845,7 +845,9 @@ tridiag_apply_pipe_kernel(const double *__restrict__ dl, const double *__restric
 //   398/432/483;  half of the DMMAs removed: 379;  accumulators stored straight to global: 476;  cp.async tile ring of
 //   2/3 stages per CTA: 390/520;  grid of 1/2/3/6 waves of resident CTAs: 381/371/363/362;  instruction count halved
 //   (lean kernel): 364;  warp-specialised with cp.async loader and LDS/STG storer warps: 378-409 (the movers fill the
-//   LSU queue the compute warps' LDS/STS need);  warp-specialised with TMA bulk copies: 267.
+//   LSU queue the compute warps' LDS/STS need);  warp-specialised with TMA bulk copies: 267, clipped tiles through the
+//   TMA unit too: 254;  two element slots per warp x 16 vectors (2.3 KB bulk copies instead of 1.2 KB, half the halo
+//   share, same registers and DMMA count): 274 — the longer copies that carry K9 do not pay here.
 // ---------------------------------------------------------------------------
 constexpr int FE_TV = 32;                           // vectors per tile (one warp wide)
 constexpr int FE_BRP = FE_TV + 1;                   // pitch of the bridge buffers
@@ -1096,26 +1098,19 @@ fedvr_apply_lean_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
 // reads (lane (gq, tq): column gq, row 4 ks + tq) and the accumulator write-back (rows gq, columns 2 tq, 2 tq + 1)
 // are then free of bank conflicts per half-warp up to the parity shift, which no plain pitch achieves.
 // ---------------------------------------------------------------------------
-#ifndef FEDVR_SPW
-#define FEDVR_SPW 1                                 // element slots per compute warp
+#ifndef FEDVR_PNTI
+#define FEDVR_PNTI 4                                // 8-vector tiles whose DMMA chains are interleaved
 #endif
-constexpr int FP_SPW = FEDVR_SPW;
-constexpr int FP_TV = 32 / FP_SPW;                  // vectors per tile: the warp's accumulators cover FP_SPW slots x FP_TV vectors
-constexpr int FP_BRP = FP_TV + 1;                   // pitch of the bridge buffers
-// Tile = NG * FP_SPW element slots (the last one is the halo element: only its first row) x FP_TV vectors.  Two slots
-// per warp and 16 vectors (FEDVR_SPW = 2) double the length of the bulk copies (2.3 KB per column at order 10) and halve
-// the share of halo rows at an unchanged register budget — which helps K9 (see its tile-shape table) but not here:
-// 274 us against 254-258 us for one slot x 32 vectors on C2.
+constexpr int FP_NTI = FEDVR_PNTI;
 template <int O, int NG> struct FePipe {
-    static constexpr int SLOTS = NG * FP_SPW;
-    static constexpr int ET = SLOTS - 1;            // elements a tile owns
+    static constexpr int ET = NG - 1;
     static constexpr int ROWS = (ET + 1) * (O - 1) + 1;
     static constexpr int KS = (O + 3) / 4, MT = (O + 7) / 8;
-    // rows a column holds: the tile (+ parity shift, rounded to 16 bytes) or the k padding read by the halo slot; + skew
+    // rows a column holds: the tile (+ parity shift, rounded to 16 bytes) or the k padding read by the halo warp; + skew
     static constexpr int NEED = (ROWS + 2 > ET * (O - 1) + 4 * KS + 1 ? ROWS + 2 : ET * (O - 1) + 4 * KS + 1) + 12;
     static constexpr int P0 = (NEED + 15) / 16 * 16;
-    static constexpr int STAGE = FP_TV * P0;                             // doubles per stage
-    static constexpr int BR = (2 * ET + 1) * FP_BRP;                     // one bridge buffer set (br0 + br9)
+    static constexpr int STAGE = FE_TV * P0;                             // doubles per stage
+    static constexpr int BR = (2 * ET + 1) * FE_BRP;                     // one bridge buffer set (br0 + br9)
     static constexpr int THREADS = 32 * (NG + 2);
     static constexpr int max_stages() {
         int n = (int)((227 * 1024 - 2 * BR * 8 - 256) / (STAGE * 8));
@@ -1132,10 +1127,10 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
                         double alpha, double beta, double *__restrict__ Y, i64 ldy) {
     using P = FePipe<O, NG>;
     constexpr int ET = P::ET, ROWS = P::ROWS, P0 = P::P0, STAGE = P::STAGE, NSTG = P::NSTG, MT = P::MT, KS = P::KS;
-    constexpr int NPT = FP_TV / 8;                  // 8-vector tiles per slot
+    constexpr int NR = ET * (O - 1);                // rows an interior tile owns: tile rows 1 .. NR
     constexpr int PROF_NG = NG; (void)PROF_NG;
     extern __shared__ __align__(128) double sm[];
-    double *brbuf = sm + (size_t)NSTG * STAGE;      // [2][br0 (ET+1) x FP_BRP | br9 ET x FP_BRP]
+    double *brbuf = sm + (size_t)NSTG * STAGE;      // [2][br0 (ET+1) x 33 | br9 ET x 33]
     uint64_t *bars = reinterpret_cast<uint64_t *>(brbuf + 2 * P::BR);    // full[NSTG], done[NSTG], empty[NSTG]
     uint64_t *full = bars, *done = bars + NSTG, *empty = bars + 2 * NSTG;
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler as well
@@ -1150,7 +1145,7 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
     }
     __syncthreads();
     const i64 net = (nel + ET - 1) / ET;
-    const i64 nvt = (nvec + FP_TV - 1) / FP_TV;
+    const i64 nvt = (nvec + FE_TV - 1) / FE_TV;
     const i64 xbase = (i64)(reinterpret_cast<uintptr_t>(X) >> 3);        // element address of X[0] (parity is what counts)
     // tile = vt * net + et, element tiles fastest; every role walks the same sequence blockIdx.x, + gridDim.x, ...
     i64 vt = (i64)blockIdx.x / net, et = (i64)blockIdx.x - vt * net;
@@ -1173,95 +1168,87 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
         const int swz_c0 = fe_swz(2 * tq), swz_c1 = fe_swz(2 * tq + 1);   // of the accumulator columns 8 np + 2 tq (+ 1)
         const double wscale = alpha;                // beta == 0 (launcher): alpha is folded into the tile
         int parity = 0;                             // bridge buffer set
-        // block fragments a = B_e[gq + 8 mt][4 ks + tq] of the warp's slots, zero outside the block / beyond the last
-        // element; the fragments of the next tile are requested as soon as the last DMMA of this one has been issued,
-        // so their L2 latency hides behind the write-back, the barrier and the bridge sums
-        double af[FP_SPW][MT][KS];
+        // block fragments a = B_e[gq + 8 mt][4 ks + tq], zero outside the block / beyond the last element; the
+        // fragments of the next tile are requested as soon as the last DMMA of this one has been issued, so their L2
+        // latency hides behind the write-back, the barrier and the bridge sums
+        double af[MT][KS];
         auto load_frags = [&](i64 eA_) {
+            const bool have = eA_ + g < nel;
+            const double *b = blocks + (eA_ + g) * (O * O) + tq * O + gq;
 #pragma unroll
-            for (int sl = 0; sl < FP_SPW; ++sl) {
-                const int slot = g * FP_SPW + sl;
-                const bool have = eA_ + slot < nel;
-                const double *b = blocks + (eA_ + slot) * (O * O) + tq * O + gq;
+            for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-                        af[sl][mt][ks] = (have && gq + 8 * mt < O && 4 * ks + tq < O && (mt == 0 || slot < ET))
-                                             ? __ldg(b + 4 * ks * O + 8 * mt) : 0.0;
-            }
+                for (int ks = 0; ks < KS; ++ks)
+                    af[mt][ks] = (have && gq + 8 * mt < O && 4 * ks + tq < O && (mt == 0 || g < ET))
+                                     ? __ldg(b + 4 * ks * O + 8 * mt) : 0.0;
         };
         if (vt < nvt) load_frags(et * ET);
         for (; vt < nvt; parity ^= 1) {
             const i64 eA = et * ET;
             const i64 x0row = eA * (O - 1) - first0;
             double *xs = sm + (size_t)stage * STAGE;
-            double *br0 = brbuf + parity * P::BR, *br9 = br0 + (ET + 1) * FP_BRP;
+            double *br0 = brbuf + parity * P::BR, *br9 = br0 + (ET + 1) * FE_BRP;
             const int cur_stage = stage;
-            const i64 v0 = vt * FP_TV;
-            const int par_r = col_parity(x0row, v0, gq);                  // columns 8 np + gq
-            const int par_c0 = col_parity(x0row, v0, 2 * tq), par_c1 = col_parity(x0row, v0, 2 * tq + 1);
-            const int bcol = threadIdx.x % FP_TV, bslot = threadIdx.x / FP_TV;   // this thread's bridge entry
-            const int par_b = col_parity(x0row, v0, bcol);
+            const int par_r = col_parity(x0row, vt * FE_TV, gq);          // columns 8 np + gq
+            const int par_c0 = col_parity(x0row, vt * FE_TV, 2 * tq), par_c1 = col_parity(x0row, vt * FE_TV, 2 * tq + 1);
+            const int par_l = col_parity(x0row, vt * FE_TV, lane);
             FE_PROF_L(7);
             mbar_wait(full + stage, phase);
             FE_PROF_L(2);
             advance();                              // (et, vt, stage, phase) now describe the next tile
-            double c[FP_SPW][NPT][MT][2];
 #pragma unroll
-            for (int sl = 0; sl < FP_SPW; ++sl)
+            for (int np0 = 0; np0 < FE_TV / 8; np0 += FP_NTI) {
+                double c[FP_NTI][MT][2];
 #pragma unroll
-                for (int np = 0; np < NPT; ++np)
+                for (int i = 0; i < FP_NTI; ++i)
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) { c[sl][np][mt][0] = 0.0; c[sl][np][mt][1] = 0.0; }
-            {
-                const double *xe = xs + gq * P0 + swz_r + par_r + g * FP_SPW * (O - 1) + tq;
+                    for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] = 0.0; c[i][mt][1] = 0.0; }
+                const double *xe = xs + (8 * np0 + gq) * P0 + swz_r + par_r + g * (O - 1) + tq;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
+                    double bf[FP_NTI];
 #pragma unroll
-                    for (int sl = 0; sl < FP_SPW; ++sl) {
-                        double bf[NPT];
+                    for (int i = 0; i < FP_NTI; ++i)
+                        bf[i] = (4 * ks + 3 < O || 4 * ks + tq < O) ? xe[i * 8 * P0 + 4 * ks] : 0.0;
 #pragma unroll
-                        for (int np = 0; np < NPT; ++np)
-                            bf[np] = (4 * ks + 3 < O || 4 * ks + tq < O) ? xe[sl * (O - 1) + np * 8 * P0 + 4 * ks] : 0.0;
+                    for (int mt = 0; mt < MT; ++mt)
+                        if (mt == 0 || g < ET) {
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-                            if (mt == 0 || g * FP_SPW + sl < ET) {
-#pragma unroll
-                                for (int np = 0; np < NPT; ++np) dmma884(c[sl][np][mt][0], c[sl][np][mt][1], af[sl][mt][ks], bf[np]);
-                            }
-                    }
+                            for (int i = 0; i < FP_NTI; ++i) dmma884(c[i][mt][0], c[i][mt][1], af[mt][ks], bf[i]);
+                        }
                 }
-            }
-            if (vt < nvt) load_frags(et * ET);      // next tile's fragments
-            __syncwarp();                           // all lanes have read the slots' x rows
-            // rows 1..O-2 go back in place (no other warp reads them); rows 0 and O-1 are contributions to the bridge
-            // rows shared with the neighbouring elements and go to the side buffers
+                if (np0 + FP_NTI >= FE_TV / 8 && vt < nvt) load_frags(et * ET);   // next tile's fragments
+                if (wscale != 1.0) {
 #pragma unroll
-            for (int sl = 0; sl < FP_SPW; ++sl) {
-                const int slot = g * FP_SPW + sl;
+                    for (int i = 0; i < FP_NTI; ++i)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) { c[i][mt][0] *= wscale; c[i][mt][1] *= wscale; }
+                }
+                __syncwarp();                       // all lanes have read these vector tiles' x rows
+                // rows 1..O-2 go back in place (no other warp reads them); rows 0 and O-1 are contributions to the
+                // bridge rows shared with the neighbouring elements and go to the side buffers
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const int mm = gq + 8 * mt;
                     if (mm == 0) {
 #pragma unroll
-                        for (int np = 0; np < NPT; ++np) {
-                            br0[slot * FP_BRP + 8 * np + 2 * tq] = wscale * c[sl][np][mt][0];
-                            br0[slot * FP_BRP + 8 * np + 2 * tq + 1] = wscale * c[sl][np][mt][1];
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            br0[g * FE_BRP + 8 * (np0 + i) + 2 * tq] = c[i][mt][0];
+                            br0[g * FE_BRP + 8 * (np0 + i) + 2 * tq + 1] = c[i][mt][1];
                         }
-                    } else if (slot < ET && mm == O - 1) {
+                    } else if (g < ET && mm == O - 1) {
 #pragma unroll
-                        for (int np = 0; np < NPT; ++np) {
-                            br9[slot * FP_BRP + 8 * np + 2 * tq] = wscale * c[sl][np][mt][0];
-                            br9[slot * FP_BRP + 8 * np + 2 * tq + 1] = wscale * c[sl][np][mt][1];
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            br9[g * FE_BRP + 8 * (np0 + i) + 2 * tq] = c[i][mt][0];
+                            br9[g * FE_BRP + 8 * (np0 + i) + 2 * tq + 1] = c[i][mt][1];
                         }
-                    } else if (slot < ET && mm < O - 1) {
-                        double *y0 = xs + (2 * tq) * P0 + swz_c0 + par_c0 + slot * (O - 1) + mm;
-                        double *y1 = xs + (2 * tq + 1) * P0 + swz_c1 + par_c1 + slot * (O - 1) + mm;
+                    } else if (g < ET && mm < O - 1) {
+                        double *y0 = xs + (8 * np0 + 2 * tq) * P0 + swz_c0 + par_c0 + g * (O - 1) + mm;
+                        double *y1 = xs + (8 * np0 + 2 * tq + 1) * P0 + swz_c1 + par_c1 + g * (O - 1) + mm;
 #pragma unroll
-                        for (int np = 0; np < NPT; ++np) {
-                            y0[np * 8 * P0] = wscale * c[sl][np][mt][0];
-                            y1[np * 8 * P0] = wscale * c[sl][np][mt][1];
+                        for (int i = 0; i < FP_NTI; ++i) {
+                            y0[i * 8 * P0] = c[i][mt][0];
+                            y1[i * 8 * P0] = c[i][mt][1];
                         }
                     }
                 }
@@ -1269,12 +1256,11 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
             FE_PROF_L(3);
             named_bar_sync(1, 32 * NG);             // every product of the tile is in place
             FE_PROF_L(4);
-            // bridge rows: last row of slot s-1 plus first row of slot s; global row 0 has no previous element
-            // (NG * 32 compute threads = SLOTS * FP_TV bridge entries)
+            // bridge rows: last row of element g-1 plus first row of element g; global row 0 has no previous element
             {
-                double *col = xs + bcol * P0 + fe_swz(bcol) + par_b;
-                if (bslot == 0) { if (eA == 0) col[0] = br0[bcol]; }
-                else col[bslot * (O - 1)] = br9[(bslot - 1) * FP_BRP + bcol] + br0[bslot * FP_BRP + bcol];
+                double *col = xs + lane * P0 + fe_swz(lane) + par_l;
+                if (g == 0) { if (eA == 0) col[0] = br0[lane]; }
+                else col[g * (O - 1)] = br9[(g - 1) * FE_BRP + lane] + br0[g * FE_BRP + lane];
             }
             fence_proxy_async();                    // the storer's bulk copies read what this thread wrote
             __syncwarp();
@@ -1283,31 +1269,30 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
     } else if (w == NG) {
         // ================= loader warp: x tiles into the ring, lane <-> vector column ==========
         for (; vt < nvt; advance()) {
-            const i64 eA = et * ET, v0 = vt * FP_TV;
+            const i64 eA = et * ET, v0 = vt * FE_TV;
             const i64 x0row = eA * (O - 1) - first0;    // X/Y row of tile row 0 (rows are relative to the restriction)
             double *xs = sm + (size_t)stage * STAGE;
-            const int cl = lane < FP_TV ? lane : 0;     // lanes beyond the tile's columns idle
             mbar_wait(empty + stage, phase ^ 1);
             FE_PROF_L(0);
-            if (x0row >= 1 && x0row + ROWS + 1 <= nrows && v0 + FP_TV <= nvec) {
+            if (x0row >= 1 && x0row + ROWS + 1 <= nrows && v0 + FE_TV <= nvec) {
                 // copy rows x0row - par .. of column lane: 16-byte aligned start, an even number of elements
-                const int par = col_parity(x0row, v0, cl);
-                const unsigned bytes = lane < FP_TV ? 8u * (unsigned)((ROWS + par + 1) & ~1) : 0u;
+                const int par = col_parity(x0row, v0, lane);
+                const unsigned bytes = 8u * (unsigned)((ROWS + par + 1) & ~1);
                 const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
                 if (lane == 0) mbar_arrive_expect_tx(full + stage, total);
                 __syncwarp();
-                if (lane < FP_TV) bulk_load(xs + cl * P0 + fe_swz(cl), X + (v0 + cl) * ldx + x0row - par, bytes, full + stage);
+                bulk_load(xs + lane * P0 + fe_swz(lane), X + (v0 + lane) * ldx + x0row - par, bytes, full + stage);
             } else {
                 // clipped tile (the first and last of a vector group, partial vector groups): valid rows through the TMA
                 // unit as well, the rest zero
-                const bool vok = lane < FP_TV && v0 + lane < nvec;
-                const int par = col_parity(x0row, v0, cl);
+                const bool vok = v0 + lane < nvec;
+                const int par = col_parity(x0row, v0, lane);
                 int ra = x0row < 0 ? (int)(-x0row < ROWS ? -x0row : ROWS) : 0;
                 int rb = x0row + ROWS > nrows ? (int)(nrows - x0row > ra ? nrows - x0row : ra) : ROWS;
                 if (!vok) { ra = 0; rb = 0; }
-                double *scol = xs + cl * P0 + fe_swz(cl) + par;
+                double *scol = xs + lane * P0 + fe_swz(lane) + par;
                 const double *gcol = X + (vok ? v0 + lane : 0) * ldx + x0row;
-                const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, lane < FP_TV ? ROWS : 0);
+                const ColPlan cp = tma_col_load_prepare(scol, gcol, par, ra, rb, ROWS);
                 const unsigned total = __reduce_add_sync(0xffffffffu, 8u * (unsigned)cp.cnt);
                 __syncwarp();
                 if (lane == 0) { if (total) mbar_arrive_expect_tx(full + stage, total); else mbar_arrive(full + stage); }
@@ -1319,24 +1304,23 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
     } else {
         // ================= storer warp: finished tiles out, lane <-> vector column ============
         for (; vt < nvt; advance()) {
-            const i64 eA = et * ET, v0 = vt * FP_TV;
+            const i64 eA = et * ET, v0 = vt * FE_TV;
             const i64 x0row = eA * (O - 1) - first0;
             const double *xs = sm + (size_t)stage * STAGE;
-            const int cl = lane < FP_TV ? lane : 0;
             mbar_wait(done + stage, phase);
             FE_PROF_L(5);
             {
                 // rows owned by this tile: 1 .. (elements present)*(O-1), plus row 0 for the first tile, clipped to the
                 // restriction; the 16-byte aligned part of column lane as a bulk copy, an odd end element through the
                 // lane (X and Y columns have the same parity, checked by the launcher)
-                const bool vok = lane < FP_TV && v0 + lane < nvec;
-                const int par = col_parity(x0row, v0, cl);
+                const bool vok = v0 + lane < nvec;
+                const int par = col_parity(x0row, v0, lane);
                 const i64 last_el = eA + ET < nel ? eA + ET : nel;
                 int ra = (eA == 0) ? 0 : 1, rb = (int)((last_el - eA) * (O - 1)) + 1;
                 if (x0row + ra < 0) ra = (int)(-x0row);
                 if (x0row + rb > nrows) rb = (int)(nrows - x0row);
                 if (!vok || rb < ra) rb = ra;
-                const double *ys = xs + cl * P0 + fe_swz(cl) + par;
+                const double *ys = xs + lane * P0 + fe_swz(lane) + par;
                 double *yc = Y + (vok ? v0 + lane : 0) * ldy + x0row;
                 tma_col_store(yc, ys, par, ra, rb);
             }
@@ -1438,7 +1422,7 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
         static_assert(P::NSTG >= 2, "tile ring does not fit in shared memory");
         auto pk = fedvr_apply_pipe_kernel<O, NG>;
         CB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-        const i64 ntiles = ((nel + P::ET - 1) / P::ET) * ((nvec + FP_TV - 1) / FP_TV);
+        const i64 ntiles = ((nel + P::ET - 1) / P::ET) * ((nvec + FE_TV - 1) / FE_TV);
         const int pgrid = (int)(ntiles < CB_NUM_SMS ? ntiles : CB_NUM_SMS);
         pk<<<pgrid, P::THREADS, P::SMEM, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
         CB_LAUNCH_CHECK();
