@@ -11,6 +11,8 @@
 // pitch and consumed with lanes <-> vectors, so that operator entries are
 // warp-uniform (broadcast) shared-memory reads and every X value is reused from
 // registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -1668,8 +1670,14 @@ static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows, const doub
     CB_CUDA(cudaGetDevice(&dev));
     CB_REQUIRE(dev >= 0 && dev < 64, "host pipeline: device index out of range");
     HostPipe &P = g_pipes[dev];
-    // tile of vectors: ~32 MB per buffer; the device copy is dense (ld = nrows)
-    i64 tv = (i64)(32ll << 20) / (nrows * (i64)sizeof(double));
+    // tile of vectors: ~32 MB per buffer (CB_HOST_CHUNK_MB overrides, for tuning); the device copy is dense (ld = nrows)
+    static i64 chunk_mb = 0;
+    if (chunk_mb == 0) {
+        const char *env = getenv("CB_HOST_CHUNK_MB");
+        chunk_mb = env ? atoll(env) : 32;
+        if (chunk_mb < 1 || chunk_mb > 1024) chunk_mb = 32;
+    }
+    i64 tv = (chunk_mb << 20) / (nrows * (i64)sizeof(double));
     if (tv < 1) tv = 1;
     if (tv > nvec) tv = nvec;
     const i64 ld = nrows;
