@@ -84,6 +84,20 @@ class _FDOrRestricted:
             nder = 2
         else:
             raise NotImplementedError(f"no materialiser for {middle}")
+        if getattr(P, "implicit", False) and not P.uniform:
+            # non-uniform compact scheme (Patchkovskii 2016, Eq. 33): both sides come from the three local steps
+            # a, b, c around a node (implicit_stencil_common, src/fd_derivatives.jl:105-150, :410-424)
+            if nder != 2:
+                raise NotImplementedError("the reference has no first-derivative left-hand side on non-uniform grids (src/fd_derivatives.jl:411)")
+            if Z != 0.0:
+                raise NotImplementedError("CoulombDerivative corrections of the implicit scheme (src/fd_derivatives.jl:553-667)")
+            st = P.nonuniform_stencils()
+            sl = slice(i0, i0 + n)
+            so = slice(i0, i0 + n - 1)
+            dev = lambda a: to_device(np.ascontiguousarray(a), P.device)
+            Delta = Tridiagonal(dev(st["alpha_t"][so]), dev(-2.0 * st["beta"][sl]), dev(st["alpha"][so]))   # step = 1
+            M = Tridiagonal(dev(st["m_dl"][so]), dev(st["m_d"][sl]), dev(st["m_du"][so]))
+            return ImplicitDerivative(Delta, M)
         fhalf = None
         if weights:                                   # src/fd_derivatives.jl:292-319
             if P.scheme != STAGGERED_NONUNIFORM or len(weights) != 1:
@@ -135,6 +149,9 @@ class AbstractFiniteDifferences(_FDOrRestricted):
         uniform grids, 1/sqrt(local_step) (:30, :278-288) on non-uniform ones."""
         if self.scheme != STAGGERED_NONUNIFORM:
             return None
+        return self._nonuniform_weights()
+
+    def _nonuniform_weights(self):
         r = self.r
         h = np.empty_like(r)
         h[0], h[-1] = r[1] - r[0], r[-1] - r[-2]
@@ -164,15 +181,62 @@ class FiniteDifferences(AbstractFiniteDifferences):
         self._setup(np.arange(1, n + 1, dtype=np.float64) * dx, dx, device)
 
 
+def implicit_stencil_common(r, fun, s=1, dN=0):
+    """``implicit_stencil_common(fun, B, s, dN)`` (src/fd_derivatives.jl:105-125): ``fun(a, b, c)`` of the three
+    consecutive local steps around every node, the grid continued by one mirrored point at the end and starting from
+    the origin."""
+    r = np.asarray(r, dtype=np.float64)
+    N = r.size
+    v = np.zeros(N + dN)
+    rt = np.concatenate([r[s - 1:], [2 * r[-1] - r[-2]]])
+    a = rt[0] - (r[s - 2] if s > 1 else 0.0)
+    b = rt[1] - rt[0]
+    c = 0.0
+    for j in range(1, N + dN + 1):
+        if j < N - (s - 1):
+            c = rt[j + 1] - rt[j]
+        v[j - 1] = fun(a, b, c)
+        a, b = b, c
+    return v
+
+
 class ImplicitFiniteDifferences(AbstractFiniteDifferences):
-    """``ImplicitFiniteDifferences(n, rho)``: compact (implicit) finite differences on the uniform grid rho*(1:n)
-    (src/finite_differences.jl:303-342).  Derivatives materialise to ``ImplicitDerivative``.  Non-uniform grids
-    (Patchkovskii 2016: a non-symmetric tridiagonal left-hand side) are not built."""
+    """``ImplicitFiniteDifferences(n, rho)``: compact (implicit) finite differences on the uniform grid rho*(1:n), or
+    ``ImplicitFiniteDifferences(r)`` on arbitrary non-decreasing nodes (src/finite_differences.jl:303-342).  Derivatives
+    materialise to ``ImplicitDerivative``; on non-uniform grids (Patchkovskii 2016) only the second derivative exists,
+    as in the reference, and its left-hand side is a non-symmetric tridiagonal matrix (band LU)."""
     scheme = CARTESIAN
     implicit = True
 
-    def __init__(self, n, rho, device=None):
-        self._setup(np.arange(1, n + 1, dtype=np.float64) * rho, rho, device)
+    def __init__(self, n_or_r, rho=None, device=None):
+        if rho is not None:
+            self.uniform = True
+            self._setup(np.arange(1, int(n_or_r) + 1, dtype=np.float64) * rho, rho, device)
+        else:
+            r = np.asarray(n_or_r, dtype=np.float64)
+            if np.any(np.diff(r) < 0):
+                raise ValueError("Node locations must be non-decreasing")
+            self.uniform = False
+            self._setup(r, 1.0, device)                # step(::NonUniform) = 1
+        self._stencils = None
+
+    def nonuniform_stencils(self):
+        """alpha~, alpha, beta (Eq. 33; src/fd_derivatives.jl:127-143) and the left-hand side of the second derivative
+        (implicit_lhs, :410-424)."""
+        if self._stencils is None:
+            r = self.r
+            self._stencils = {
+                "alpha_t": implicit_stencil_common(r, lambda a, b, c: 2 / (a * (a + b)), 2, -1),
+                "alpha": implicit_stencil_common(r, lambda a, b, c: 2 / (b * (a + b)), 1, -1),
+                "beta": implicit_stencil_common(r, lambda a, b, c: 1 / (a * b)),
+                "m_dl": implicit_stencil_common(r, lambda a, b, c: (a * a + a * b - b * b) / (6 * a * (a + b)), 2, -1),
+                "m_d": implicit_stencil_common(r, lambda a, b, c: (a * a + 3 * a * b + b * b) / (6 * a * b)),
+                "m_du": implicit_stencil_common(r, lambda a, b, c: (-a * a + a * b + b * b) / (6 * b * (a + b)), 1, -1),
+            }
+        return self._stencils
+
+    def vandermonde_diag(self):
+        return None if self.uniform else self._nonuniform_weights()
 
 
 class StaggeredFiniteDifferences(AbstractFiniteDifferences):

@@ -298,18 +298,27 @@ class BandLU:
         return X
 
 
+def _band_is_symmetric(A: BandedMatrix) -> bool:
+    """True if the band is symmetric (square, l == u, A[j+d, j] == A[j, j+d] bit for bit)."""
+    if A.m != A.n or A.l != A.u:
+        return False
+    for d in range(1, A.l + 1):
+        if not torch.equal(A.data[:A.n - d, A.u + d], A.data[d:, A.u - d]):
+            return False
+    return True
+
+
 def factorize(A: BandedMatrix, method: str = "auto"):
     """``factorize(A)``: "cholesky" (SPD bands, partitioned batched solve), "lu" (pivoted band LU, any non-singular
-    band) or "auto" = Cholesky when the band is symmetric in shape and the factorisation succeeds, else LU."""
+    band) or "auto" = Cholesky when the band is symmetric and the factorisation succeeds, else LU."""
     if method == "lu":
         return BandLU(A)
     if method == "cholesky":
         lu = max(A.l, A.u)
         return A.widened(lu, lu).cholesky()
-    if A.m == A.n:
+    if _band_is_symmetric(A):
         try:
-            lu = max(A.l, A.u)
-            return A.widened(lu, lu).cholesky()
+            return A.cholesky()
         except ValueError:                                           # not positive definite
             pass
     return BandLU(A)
@@ -427,13 +436,14 @@ class SymTridiagonal(Tridiagonal):
 
 class ImplicitDerivative:
     """``ImplicitDerivative(Delta, M, c)`` (src/finite_differences.jl:356-413): the compact finite-difference
-    derivative ``c * M^-1 * Delta`` with tridiagonal Delta and symmetric positive definite tridiagonal M (uniform grids:
-    M1 = SymTridiagonal(4, 1)/6, M2 = SymTridiagonal(10, 1)/12, src/fd_derivatives.jl:402-424).  ``factorize(M)`` is the
-    banded Cholesky of the C ABI; ``mul!`` = tridiagonal apply + batched partitioned solve + scaling."""
+    derivative ``c * M^-1 * Delta`` with tridiagonal Delta and M (uniform grids: M1 = SymTridiagonal(4, 1)/6,
+    M2 = SymTridiagonal(10, 1)/12; non-uniform grids: Patchkovskii's non-symmetric Tridiagonal,
+    src/fd_derivatives.jl:395-424).  ``factorize(M)`` is the banded Cholesky of the C ABI for the symmetric case and the
+    pivoted band LU otherwise; ``mul!`` = tridiagonal apply + batched solve + scaling."""
 
     def __init__(self, Delta, M, c: float = 1.0, Minv=None):
         self.Delta, self.M, self.c = Delta, M, float(c)
-        self.Minv = as_banded(M).cholesky() if Minv is None else Minv
+        self.Minv = factorize(as_banded(M)) if Minv is None else Minv       # Cholesky (uniform grids) or band LU
         self.n = Delta.n
 
     @property

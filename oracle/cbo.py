@@ -714,3 +714,33 @@ def inner_products(U, V, S=None, scale=1.0):
     U, V = np.asarray(U, dtype=np.float64), np.asarray(V, dtype=np.float64)
     W = V if S is None else np.asarray(S) @ V
     return scale * np.einsum("ip,ip->p", U, W)
+
+
+def implicit_stencils_nonuniform(r):
+    """Patchkovskii's non-uniform compact stencils (src/fd_derivatives.jl:105-143 alpha~, alpha, beta of Eq. 33 and
+    implicit_lhs :410-424) in closed form on the local steps h_j = r_j - r_{j-1}, r_0 = 0, r_{N+1} = 2 r_N - r_{N-1}."""
+    r = np.asarray(r, dtype=np.float64)
+    h = np.diff(np.concatenate([[0.0], r, [2 * r[-1] - r[-2]]]))      # h[j-1] = h_j, j = 1..N+1
+    a, b = h[:-1], h[1:]                                              # node j: a = h_j, b = h_{j+1}
+    out = {
+        "beta": 1 / (a * b),
+        "alpha": (2 / (b * (a + b)))[:-1],
+        "m_d": (a * a + 3 * a * b + b * b) / (6 * a * b),
+        "m_du": ((-a * a + a * b + b * b) / (6 * b * (a + b)))[:-1],
+    }
+    a2, b2 = h[1:-1], np.concatenate([h[2:-1], [h[-1]]])              # entry j: a = h_{j+1}, b = h_{j+2} (mirrored end)
+    out["alpha_t"] = 2 / (a2 * (a2 + b2))
+    out["m_dl"] = (a2 * a2 + a2 * b2 - b2 * b2) / (6 * a2 * (a2 + b2))
+    return out
+
+
+def tridiag_dense(dl, d, du):
+    return np.diag(d) + np.diag(dl, -1) + np.diag(du, 1)
+
+
+def implicit_derivative_apply_general(Delta, M, c, X, alpha=1.0, beta=0.0, Y=None):
+    """mul!(y, d::ImplicitDerivative, x, alpha, beta) with dense Delta and M (src/finite_differences.jl:388-396)."""
+    rhs = alpha * (Delta @ np.asarray(X, dtype=np.float64))
+    if beta != 0.0:
+        rhs = rhs + beta * np.asarray(Y, dtype=np.float64)
+    return c * np.linalg.solve(M, rhs)

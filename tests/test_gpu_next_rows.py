@@ -426,3 +426,38 @@ def test_inner_products_and_norms(cb):
     U, V = rng.standard_normal((100000, 5)), rng.standard_normal((100000, 5))
     got = cb.inner_product(cb.ColMajor.from_numpy(U), R, cb.ColMajor.from_numpy(V)).cpu().numpy()
     assert relerr(got, cbo.inner_products(U, V, None, 1e-3)) <= 1e-12
+
+
+def test_implicit_finite_differences_nonuniform(cb):
+    """Patchkovskii's non-uniform compact second derivative (src/fd_derivatives.jl:105-143, :410-424): stencils against
+    the closed-form restatement, mul! (tridiagonal apply + band LU solve) against a dense solve, fourth-order accuracy."""
+    N = 2500
+    j = np.arange(1, N + 1)
+    r = 0.002 * j + 4e-7 * j ** 2                                     # smoothly stretched grid, r_N ~ 7.5
+    R = cb.ImplicitFiniteDifferences(r)
+    D = cb.Derivative()
+    d2 = R.T @ D.T @ D @ R
+    assert isinstance(d2, cb.ImplicitDerivative) and isinstance(d2.Minv, cb.BandLU)
+    st = cbo.implicit_stencils_nonuniform(r)
+    for got, want in ((d2.Delta.dl, st["alpha_t"]), (d2.Delta.d, -2 * st["beta"]), (d2.Delta.du, st["alpha"]),
+                      (d2.M.dl, st["m_dl"]), (d2.M.d, st["m_d"]), (d2.M.du, st["m_du"])):
+        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=4e-16, atol=0)
+    with pytest.raises(NotImplementedError):
+        R.T @ D @ R
+    rng = np.random.default_rng(81)
+    X, Y0 = rng.standard_normal((N, 19)), rng.standard_normal((N, 19))
+    Dl = cbo.tridiag_dense(st["alpha_t"], -2 * st["beta"], st["alpha"])
+    Mm = cbo.tridiag_dense(st["m_dl"], st["m_d"], st["m_du"])
+    T = d2 / -2
+    Yc = cb.ColMajor.from_numpy(Y0)
+    cb.mul(Yc, T, cb.ColMajor.from_numpy(X), 0.5, -2.0)
+    assert relerr(Yc.numpy(), cbo.implicit_derivative_apply_general(Dl, Mm, -0.5, X, 0.5, -2.0, Y0)) <= 1e-11
+    # f(r) = r^3 exp(-r): f and f'' vanish at the origin (what the truncated first row of the scheme assumes);
+    # f'' = (6r - 6r^2 + r^3) exp(-r).  The mirrored last point is a crude outer boundary: its error decays inwards.
+    f = r ** 3 * np.exp(-r)
+    out = cb.ColMajor.zeros(N, 1)
+    cb.mul(out, d2, cb.ColMajor.from_numpy(f))
+    err = np.abs(out.numpy()[:, 0] - (6 * r - 6 * r ** 2 + r ** 3) * np.exp(-r))[:-60]
+    assert err.max() < 1e-8, err.max()
+    Rr = R[:, 2:N - 1]
+    assert (Rr.T @ D.T @ D @ Rr).shape == (N - 2, N - 2)
