@@ -116,6 +116,47 @@ def density_transcript():
             "norm_rho_minus_ch": float(src[hi + 1])}
 
 
+# Further REPL transcripts (6 significant digits as printed).
+MORE_DOCS = {
+    "diag_op_k7": {
+        "source": "docs/src/diagonal_operators.md:100-138: R'*QuasiDiagonal(sin.(2pi r))*R, LinearKnotSet(7, 0, 10, 71), 77x77",
+        "k": 7, "a": 0.0, "b": 10.0, "N": 71,
+        # top-left corner: rows 1..7, columns 1..6
+        "top_left": [
+            [0.000682615, 0.000987306, 0.00043971, 8.7846e-5, 8.60727e-6, 3.99159e-7],
+            [0.000987306, 0.00413625, 0.00468984, 0.00232941, 0.000573453, 6.82737e-5],
+            [0.00043971, 0.00468984, 0.0114273, 0.0114915, 0.00562534, 0.00134742],
+            [8.7846e-5, 0.00232941, 0.0114915, 0.021737, 0.0194201, 0.00849555],
+            [8.60727e-6, 0.000573453, 0.00562534, 0.0194201, 0.0303017, 0.0226904],
+            [3.99159e-7, 6.82737e-5, 0.00134742, 0.00849555, 0.0226904, 0.0273211],
+            [6.92763e-9, 3.1258e-6, 0.000131733, 0.0016054, 0.0074447, 0.0129012]],
+        # bottom-right corner: rows 74..77, columns 74..77 (the integrand is odd about the midpoint)
+        "bottom_right": [
+            [-0.021737, -0.0114915, -0.00232941, -8.7846e-5],
+            [-0.0114915, -0.0114273, -0.00468984, -0.00043971],
+            [-0.00232941, -0.00468984, -0.00413625, -0.000987306],
+            [-8.7846e-5, -0.00043971, -0.000987306, -0.000682615]],
+    },
+    "grad_k3": {
+        "source": "docs/src/bsplines/operators.md:31-37: B'D*B, LinearKnotSet(3, 0, 1, 3), 5x5",
+        "k": 3, "a": 0.0, "b": 1.0, "N": 3,
+        "matrix": [[-0.5, 0.416667, 0.0833333, 0.0, 0.0],
+                   [-0.416667, 0.0, 0.375, 0.0416667, 0.0],
+                   [-0.0833333, -0.375, 0.0, 0.375, 0.0833333],
+                   [0.0, -0.0416667, -0.375, 0.0, 0.416667],
+                   [0.0, 0.0, -0.0833333, -0.416667, 0.5]],
+    },
+    "expknots_k5": {
+        "source": "docs/src/index.md:68-92: ExpKnotSet(5, -2.0, log10(1.0), 14), 23 knots",
+        "k": 5, "a": -2.0, "b": 0.0, "N": 14,
+        "knots": [0.0, 0.0, 0.0, 0.0, 0.0, 0.01, 0.014251026703029978, 0.020309176209047358, 0.028942661247167503,
+                  0.04124626382901352, 0.05878016072274912, 0.0837677640068292, 0.11937766417144363,
+                  0.17012542798525887, 0.24244620170823283, 0.3455107294592219, 0.4923882631706739,
+                  0.7017038286703828, 1.0, 1.0, 1.0, 1.0, 1.0],
+    },
+}
+
+
 def main():
     out = {}
     out["mass_k3_discontinuous"] = {
@@ -166,6 +207,7 @@ def main():
         out[name] = dict(source=f"{d}:{lo}-{hi}", N=N, a0=0, b0=1, matrix=rows, **meta)
     out["docs"] = DOCS
     out["docs"]["density_k7"] = density_transcript()
+    out["docs"].update(MORE_DOCS)
     with open(os.path.join(HERE, "bspline_rationals.json"), "w") as f:
         json.dump(out, f, indent=0)
     for k, v in out.items():

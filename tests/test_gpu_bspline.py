@@ -252,6 +252,21 @@ def test_readme_and_docs_matrices(cb, golden):
     B4 = cb.BSpline(cb.LinearKnotSet(g4["k"], g4["a"], g4["b"], g4["N"]))
     S4 = (B4.T @ B4).dense()
     np.testing.assert_allclose(S4[:4, 0], golden["docs"]["mass_k4"]["col1"], rtol=6e-6)
+    # R'*QuasiDiagonal(sin 2 pi r)*R, docs/src/diagonal_operators.md:100-138
+    g = golden["docs"]["diag_op_k7"]
+    R = cb.BSpline(cb.LinearKnotSet(g["k"], g["a"], g["b"], g["N"]))
+    F = (R.T @ cb.QuasiDiagonal(lambda r: np.sin(2 * np.pi * r)) @ R).dense()
+    assert F.shape == (77, 77)
+    np.testing.assert_allclose(F[:7, :6], g["top_left"], rtol=6e-6)
+    np.testing.assert_allclose(F[73:, 73:], g["bottom_right"], rtol=6e-6)
+    # B'D*B for k = 3, docs/src/bsplines/operators.md:31-37
+    g = golden["docs"]["grad_k3"]
+    B3 = cb.BSpline(cb.LinearKnotSet(g["k"], g["a"], g["b"], g["N"]))
+    np.testing.assert_allclose((B3.T @ D @ B3).dense(), g["matrix"], rtol=6e-6, atol=1e-15)
+    # ExpKnotSet knots to 17 digits, docs/src/index.md:68-92
+    g = golden["docs"]["expknots_k5"]
+    te = cb.ExpKnotSet(g["k"], g["a"], g["b"], g["N"])
+    np.testing.assert_allclose(cbo.expand_knots(te.t, te.k, te.ml, te.mr), g["knots"], rtol=4e-16, atol=0)
 
 
 def test_coulomb_on_chip_equals_opvals(cb):

@@ -383,3 +383,29 @@ def test_density_docs_transcript(golden):
     np.testing.assert_allclose(rho[:16], g["first16"], rtol=0, atol=2e-10)
     np.testing.assert_allclose(rho[-16:], g["last16"], rtol=0, atol=2e-10)
     assert abs(np.linalg.norm(rho - ch) - g["norm_rho_minus_ch"]) <= 1e-9
+
+
+def test_more_docs_transcripts(golden):
+    """Further REPL transcripts of the reference docs: the B-spline matrix of sin(2 pi r) (docs/src/diagonal_operators.md),
+    the first-derivative matrix for k = 3 (docs/src/bsplines/operators.md), 17-digit ExpKnotSet knots (docs/src/index.md)."""
+    g = golden["docs"]["diag_op_k7"]
+    k = g["k"]
+    t = cbo.expand_knots(cbo.linear_knots(g["a"], g["b"], g["N"]), k)
+    q = cbo.num_quadrature_points(k, 3)
+    x, w = cbo.lgwt(t, q)
+    nf = len(t) - k
+    assert nf == 77
+    band, l, u = cbo.bspline_assemble(t, k, t, k, x, w, q, op=np.sin(2 * np.pi * x))
+    F = cbo.band_to_dense(band, nf, nf, l, u)
+    np.testing.assert_allclose(F[:7, :6], g["top_left"], rtol=6e-6)
+    np.testing.assert_allclose(F[73:, 73:], g["bottom_right"], rtol=6e-6)
+    g = golden["docs"]["grad_k3"]
+    t = cbo.expand_knots(cbo.linear_knots(g["a"], g["b"], g["N"]), g["k"])
+    q = cbo.num_quadrature_points(g["k"], 3)
+    x, w = cbo.lgwt(t, q)
+    band, l, u = cbo.bspline_assemble(t, g["k"], t, g["k"], x, w, q, 0, 1)
+    G = cbo.band_to_dense(band, 5, 5, l, u)
+    np.testing.assert_allclose(G, g["matrix"], rtol=6e-6, atol=1e-15)      # the printed diagonal is 1e-17 round-off
+    g = golden["docs"]["expknots_k5"]
+    t = cbo.expand_knots(cbo.exp_knots(g["a"], g["b"], g["N"]), g["k"])
+    np.testing.assert_allclose(t, g["knots"], rtol=4e-16, atol=0)
