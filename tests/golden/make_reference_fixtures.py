@@ -137,6 +137,24 @@ MORE_DOCS = {
             [-0.00232941, -0.00468984, -0.00413625, -0.000987306],
             [-8.7846e-5, -0.00043971, -0.000987306, -0.000682615]],
     },
+    "basis_table_k7": {
+        "source": "docs/src/bsplines/inner_products.md:33-90: B.B (80x16, values at the 8 nodes of interval 1 / 10) and B.S, LinearKnotSet(7, 0, 1, 10)",
+        "k": 7, "a": 0.0, "b": 1.0, "N": 10,
+        # B.B[1:8, 1] and B.B[1:8, 2]: functions 1 and 2 at the eight nodes of the first interval; mirrored in B.B[73:80, 16], [.., 15]
+        "col1_rows1_8": [0.886629, 0.525563, 0.196947, 0.0429226, 0.00463197, 0.000178262, 1.10427e-6, 6.12673e-11],
+        "col2_rows1_8": [0.11053, 0.411336, 0.543708, 0.422368, 0.234511, 0.111732, 0.0558643, 0.0351626],
+        "nnz": 560,
+        # first six columns of the first eight rows of B.S
+        "S_top_left": [
+            [0.00769231, 0.00492814, 0.00142795, 0.000218646, 1.79179e-5, 7.31907e-7],
+            [0.00492814, 0.0110567, 0.00855534, 0.00328365, 0.000674239, 7.04773e-5],
+            [0.00142795, 0.00855534, 0.0147851, 0.0118803, 0.00501486, 0.00109218],
+            [0.000218646, 0.00328365, 0.0118803, 0.0187451, 0.015232, 0.00647614],
+            [1.79179e-5, 0.000674239, 0.00501486, 0.015232, 0.0232999, 0.0188319],
+            [7.31907e-7, 7.04773e-5, 0.00109218, 0.00647614, 0.0188319, 0.0289487],
+            [1.15625e-8, 2.93435e-6, 0.000100846, 0.00126285, 0.0074747, 0.0228901],
+            [0.0, 3.61328e-10, 5.83108e-7, 4.39448e-5, 0.000854471, 0.00665362]],
+    },
     "grad_k3": {
         "source": "docs/src/bsplines/operators.md:31-37: B'D*B, LinearKnotSet(3, 0, 1, 3), 5x5",
         "k": 3, "a": 0.0, "b": 1.0, "N": 3,

@@ -263,6 +263,14 @@ def test_readme_and_docs_matrices(cb, golden):
     g = golden["docs"]["grad_k3"]
     B3 = cb.BSpline(cb.LinearKnotSet(g["k"], g["a"], g["b"], g["N"]))
     np.testing.assert_allclose((B3.T @ D @ B3).dense(), g["matrix"], rtol=6e-6, atol=1e-15)
+    # B.B (basis functions at the nodes) and B.S for k = 7, 10 intervals, docs/src/bsplines/inner_products.md:33-90
+    g = golden["docs"]["basis_table_k7"]
+    B7 = cb.BSpline(cb.LinearKnotSet(g["k"], g["a"], g["b"], g["N"]))
+    tab = B7.basis_functions(0).cpu().numpy()                       # [interval][node][live function]
+    assert tab.shape == (10, 8, 7) and np.count_nonzero(tab) == g["nnz"]
+    np.testing.assert_allclose(tab[0, :, 0], g["col1_rows1_8"], rtol=6e-6)
+    np.testing.assert_allclose(tab[0, :, 1], g["col2_rows1_8"], rtol=6e-6)
+    np.testing.assert_allclose((B7.T @ B7).dense()[:8, :6], g["S_top_left"], rtol=6e-6, atol=1e-300)
     # ExpKnotSet knots to 17 digits, docs/src/index.md:68-92
     g = golden["docs"]["expknots_k5"]
     te = cb.ExpKnotSet(g["k"], g["a"], g["b"], g["N"])

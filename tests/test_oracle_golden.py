@@ -409,3 +409,22 @@ def test_more_docs_transcripts(golden):
     g = golden["docs"]["expknots_k5"]
     t = cbo.expand_knots(cbo.exp_knots(g["a"], g["b"], g["N"]), g["k"])
     np.testing.assert_allclose(t, g["knots"], rtol=4e-16, atol=0)
+
+
+def test_docs_basis_table_and_mass_k7(golden):
+    """docs/src/bsplines/inner_products.md:33-90: the basis functions at the quadrature nodes (B.B, 560 stored entries)
+    and the mass matrix B.S for k = 7 on 10 intervals (q = 8 nodes per interval)."""
+    g = golden["docs"]["basis_table_k7"]
+    k = g["k"]
+    t = cbo.expand_knots(cbo.linear_knots(g["a"], g["b"], g["N"]), k)
+    q = cbo.num_quadrature_points(k, 3)
+    assert q == 8
+    x, w = cbo.lgwt(t, q)
+    V = cbo.basis_matrix(t, k, x, q)
+    assert V.shape == (80, 16) and np.count_nonzero(V) == g["nnz"]
+    np.testing.assert_allclose(V[:8, 0], g["col1_rows1_8"], rtol=6e-6)
+    np.testing.assert_allclose(V[:8, 1], g["col2_rows1_8"], rtol=6e-6)
+    np.testing.assert_allclose(V[72:, 15][::-1], g["col1_rows1_8"], rtol=6e-6)      # mirror image
+    band, l, u = cbo.bspline_assemble(t, k, t, k, x, w, q)
+    S = cbo.band_to_dense(band, 16, 16, l, u)
+    np.testing.assert_allclose(S[:8, :6], g["S_top_left"], rtol=6e-6, atol=1e-300)
