@@ -338,3 +338,56 @@ def test_tridiag_apply_pipeline_at_scale(cb, n, nvec, xshift, yshift):
     Yc = _shifted_colmajor(cb, np.full((n, nvec), np.nan), yshift)
     cb.mul(Yc, T, Xc, -0.75, 0.0)
     assert relerr(Yc.numpy(), cbo.tridiag_apply(dl, d, du, X, -0.75, 0.0, np.zeros((n, nvec), order="F"))) <= RTOL
+
+
+def test_pipelines_random_shapes(cb):
+    """Randomised shapes around the tile sizes of the three TMA pipelines (128-row / 384-row / element tiles, 32- and
+    16-vector tiles): clipped first / last tiles, partial vector tiles, both column phases, restrictions."""
+    import torch
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        # banded
+        n = int(rng.choice([127, 128, 129, 255, 257, 300, 385, 513, 1000, 1025]))
+        l, u = int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        nvec = int(rng.choice([1, 7, 31, 32, 33, 64, 95]))
+        shift = int(rng.integers(0, 2))
+        band = rng.standard_normal((n, l + u + 1))
+        A = cb.BandedMatrix(torch.as_tensor(band, device="cuda").contiguous(), n, n, l, u)
+        X = rng.standard_normal((n, nvec))
+        Yc = _shifted_colmajor(cb, np.full((n, nvec), np.nan), shift)
+        cb.mul(Yc, A, _shifted_colmajor(cb, X, shift), 1.5, 0.0)
+        ref = cbo.banded_apply(band, n, n, l, u, X, 1.5, 0.0, np.zeros((n, nvec), order="F"))
+        assert relerr(Yc.numpy(), ref) <= RTOL, ("banded", n, l, u, nvec, shift)
+        # tridiagonal
+        n = int(rng.choice([256, 257, 383, 384, 385, 767, 769, 1153, 5000]))
+        nvec = int(rng.choice([1, 15, 16, 17, 48, 50]))
+        dl, d, du = rng.standard_normal(n - 1), rng.standard_normal(n), rng.standard_normal(n - 1)
+        T = cb.Tridiagonal(*(torch.as_tensor(v, device="cuda") for v in (dl, d, du)))
+        X = rng.standard_normal((n, nvec))
+        Yc = _shifted_colmajor(cb, np.full((n, nvec), np.nan), shift)
+        cb.mul(Yc, T, _shifted_colmajor(cb, X, shift), 2.0, 0.0)
+        assert relerr(Yc.numpy(), cbo.tridiag_apply(dl, d, du, X, 2.0, 0.0, np.zeros((n, nvec), order="F"))) <= RTOL, ("tridiag", n, nvec, shift)
+    for case in range(10):
+        # FE-DVR, with and without a restriction
+        order = int(rng.choice([2, 3, 5, 8, 10, 13, 16]))
+        nel = int(rng.choice([1, 2, 14, 15, 16, 17, 31, 46, 100]))
+        nvec = int(rng.choice([1, 31, 32, 33, 70]))
+        t = cbo.julia_range(0, float(nel), nel + 1)
+        B = cb.FEDVR(t, order)
+        O = cbo.FEDVROracle(t, order)
+        D = cb.Derivative()
+        blk = O.blocks(2)
+        a, b = 1, B.N
+        if B.N > 4 and rng.integers(0, 2):
+            a, b = 2, B.N - 1
+        R = B if (a, b) == (1, B.N) else B[:, a:b]
+        A = R.T @ D.T @ D @ R
+        nfun = b - a + 1
+        X = rng.standard_normal((nfun, nvec))
+        Xfull = np.zeros((B.N, nvec), order="F")
+        Xfull[a - 1:b] = X
+        ref = O.apply(blk, Xfull)[a - 1:b]
+        shift = int(rng.integers(0, 2))
+        Yc = _shifted_colmajor(cb, np.full((nfun, nvec), np.nan), shift)
+        cb.mul(Yc, A, _shifted_colmajor(cb, X, shift))
+        assert relerr(Yc.numpy(), ref) <= RTOL, ("fedvr", order, nel, nvec, a, b, shift)
