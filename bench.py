@@ -238,6 +238,15 @@ def other_kernels(torch, cb, peak_gbs):
     byt = 3 * 8 * B5.nf * P
     out["c5_density_1024pair_tile"] = {"ms": mn * 1e3, "GBps": byt / mn / 1e9, "hbm_frac": byt / mn / 1e9 / peak_gbs,
                                        "fp64_tflops": 2.3e11 * P / 1e4 / mn / 1e12}
+    # metric inverse / shift-and-invert solves on the C5 basis: banded Cholesky (partitioned) and pivoted band LU,
+    # 50 007 rows x 1024 vectors in place (410 MB read + written once, algorithmically)
+    S5 = B5.T @ B5
+    Xs = torch.randn((P, B5.nf), dtype=torch.float64, device="cuda")
+    byt = 2 * 8 * B5.nf * P
+    for tag, F in (("c5_bandchol_solve_1024vec", S5.cholesky()), ("c5_bandlu_solve_1024vec", cb.BandLU(S5))):
+        mean, mn = ev_time(torch, lambda: F.ldiv(Xs), 3, warm=1)
+        out[tag] = {"ms": mn * 1e3, "GBps": byt / mn / 1e9, "hbm_frac": byt / mn / 1e9 / peak_gbs}
+        Xs.normal_()
     return out
 
 
