@@ -118,17 +118,29 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
     const int kv = l + u, ld = 2 * l + u + 1;
     const int reach = kv > l ? kv : l;              // rows beyond the chunk a step touches (forward: l, backward: kv)
     const int rows_s = LU_R + reach;
-    double *xs = sm + (size_t)warp * rows_s * 33;
+    const int fw = kv + 1 > l ? kv + 1 : l;         // factor entries staged per row: l multipliers or kv + 1 entries of U
+    const size_t per_warp = (size_t)rows_s * 33 + (size_t)LU_R * fw + LU_R / 2;
+    double *xs = sm + (size_t)warp * per_warp;
+    // the factor columns and pivots of the chunk's rows, staged per chunk with coalesced, independent loads: read per row
+    // from global memory they put two L2 round trips on every step of the recurrence (130 ms for 50 007 x 1024)
+    double *fac = xs + (size_t)rows_s * 33;
+    int *piv = reinterpret_cast<int *>(fac + (size_t)LU_R * fw);
     const i64 ngroups = (nvec + 31) / 32;
     for (i64 grp = (i64)blockIdx.x * LU_WARPS + warp; grp < ngroups; grp += (i64)gridDim.x * LU_WARPS) {
         const i64 v0 = grp * 32;
         const int nv = (int)(nvec - v0 < 32 ? nvec - v0 : 32);
         // rows [g0, g0 + cnt) of the group's vectors <-> xs rows [s0, s0 + cnt); lanes run along the rows
+        // (cp.async: all of a chunk's loads are in flight at once; a plain load-then-store loop had one load per lane
+        // in flight and spent ~700 cycles of memory latency per row of the recurrence)
         auto load_rows = [&](i64 g0, int s0, int cnt) {
             for (int v = 0; v < nv; ++v) {
                 const double *xc = X + (v0 + v) * ldx + g0;
-                for (int r = lane; r < cnt; r += 32) xs[(s0 + r) * 33 + v] = xc[r];
+                for (int r = lane; r < cnt; r += 32) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&xs[(s0 + r) * 33 + v]);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xc + r) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         };
         auto store_rows = [&](i64 g0, int s0, int cnt) {
             for (int v = 0; v < nv; ++v) {
@@ -143,6 +155,16 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
             int have = (int)(n < rows_s ? n : rows_s);
             load_rows(0, 0, have);
             __syncwarp();
+            auto stage_L = [&](i64 r0) {            // multipliers and pivots of rows r0 .. r0 + LU_R - 1
+                for (int e = lane; e < LU_R * l; e += 32) {
+                    const int rr = e / l, i = e - rr * l;
+                    const i64 jj = r0 + rr;
+                    fac[rr * l + i] = jj < n ? __ldg(ab + (i64)ld * jj + kv + 1 + i) : 0.0;
+                }
+                for (int rr = lane; rr < LU_R; rr += 32) piv[rr] = r0 + rr < n ? ipiv[r0 + rr] - (int)(r0 + rr) : 0;
+            };
+            stage_L(0);
+            __syncwarp();
             for (i64 j = 0; j < n - 1; ++j) {
                 if (j - c0 == LU_R) {               // rows [c0, c0 + LU_R) are final: write them out, move the rest up
                     store_rows(c0, 0, LU_R);
@@ -154,12 +176,13 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
                     const int more = (int)(n - next < LU_R ? (n - next > 0 ? n - next : 0) : LU_R);
                     __syncwarp();
                     load_rows(next, keep, more);
+                    stage_L(c0);
                     have = keep + more;
                     __syncwarp();
                 }
                 const int s = (int)(j - c0);
                 const int lm = (int)(l < n - 1 - j ? l : n - 1 - j);
-                const int p = ipiv[j] - (int)j;      // 0 .. l
+                const int p = piv[s];               // 0 .. l
                 double xj = xs[s * 33 + lane];
                 if (p != 0) {
                     const double xp = xs[(s + p) * 33 + lane];
@@ -167,8 +190,8 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
                     xs[s * 33 + lane] = xp;
                     xj = xp;
                 }
-                const double *lj = ab + (i64)ld * j + kv;
-                for (int r = 1; r <= lm; ++r) xs[(s + r) * 33 + lane] -= __ldg(lj + r) * xj;
+                const double *lj = fac + s * l - 1;
+                for (int r = 1; r <= lm; ++r) xs[(s + r) * 33 + lane] -= lj[r] * xj;
             }
             __syncwarp();
             store_rows(c0, 0, have);
@@ -180,6 +203,16 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
             i64 hi = n - 1;
             int have = (int)(n < rows_s ? n : rows_s);
             load_rows(hi - have + 1, rows_s - have, have);
+            __syncwarp();
+            auto stage_U = [&](i64 top) {           // U columns of rows top, top - 1, ..., top - LU_R + 1: fac[(top - j)][d] = U(j - d, j)
+                for (int e = lane; e < LU_R * (kv + 1); e += 32) {
+                    const int rr = e / (kv + 1), dd = e - rr * (kv + 1);
+                    const i64 jj = top - rr;
+                    fac[rr * (kv + 1) + dd] = jj >= 0 ? __ldg(ab + (i64)ld * jj + kv - dd) : 1.0;
+                }
+            };
+            __syncwarp();
+            stage_U(hi);
             __syncwarp();
             for (i64 j = n - 1; j >= 0; --j) {
                 if (hi - j == LU_R) {               // rows (hi - LU_R, hi] are final
@@ -193,15 +226,16 @@ bandlu_solve_kernel(const double *__restrict__ ab, const int *__restrict__ ipiv,
                     const int more = (int)(top + 1 < LU_R ? (top + 1 > 0 ? top + 1 : 0) : LU_R);
                     __syncwarp();
                     load_rows(top - more + 1, rows_s - keep - more, more);
+                    stage_U(hi);
                     have = keep + more;
                     __syncwarp();
                 }
                 const int s = rows_s - 1 - (int)(hi - j);
-                const double *uj = ab + (i64)ld * j + kv;            // uj[-d] = U(j - d, j)
-                const double xj = xs[s * 33 + lane] / __ldg(uj);
+                const double *uj = fac + (int)(hi - j) * (kv + 1);   // uj[d] = U(j - d, j)
+                const double xj = xs[s * 33 + lane] / uj[0];
                 xs[s * 33 + lane] = xj;
                 const int um = (int)(kv < j ? kv : j);
-                for (int d = 1; d <= um; ++d) xs[(s - d) * 33 + lane] -= __ldg(uj - d) * xj;
+                for (int d = 1; d <= um; ++d) xs[(s - d) * 33 + lane] -= uj[d] * xj;
             }
             __syncwarp();
             store_rows(hi - have + 1, rows_s - have, have);
@@ -258,7 +292,8 @@ int cb_bandlu_solve(const cb_bandlu *F, double *X, i64 ldx, i64 nvec, void *stre
                (long long)ldx, (long long)F->n);
     if (nvec == 0) return CB_OK;
     const int kv = F->l + F->u, reach = kv > F->l ? kv : F->l;
-    const size_t smem = sizeof(double) * (size_t)LU_WARPS * (LU_R + reach) * 33;
+    const int fw = kv + 1 > F->l ? kv + 1 : F->l;
+    const size_t smem = sizeof(double) * (size_t)LU_WARPS * ((size_t)(LU_R + reach) * 33 + (size_t)LU_R * fw + LU_R / 2);
     CB_CUDA(cudaFuncSetAttribute(bandlu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 ngroups = (nvec + 31) / 32;
     i64 grid = (ngroups + LU_WARPS - 1) / LU_WARPS;
