@@ -75,6 +75,7 @@ _SIGNATURES = {
     "cb_density_orthogonal": (cint, [vp, i64, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_project": (cint, [vp, vp, i64, i64, vp, i64, vp]),
     "cb_bandchol_create": (cint, [vp, i64, cint, C.POINTER(vp)]),
+    "cb_bandldl_create": (cint, [vp, i64, cint, C.POINTER(vp)]),
     "cb_bandchol_solve": (cint, [vp, vp, i64, i64, vp]),
     "cb_bandchol_destroy": (cint, [vp]),
     "cb_bandlu_create": (cint, [vp, i64, cint, cint, C.POINTER(vp)]),

@@ -40,12 +40,18 @@ struct cb_density_s {
 // One-time banded Cholesky of G (lower band g[j][p] = G_{j,j-p}, p = 0..k-1).
 // Sequential in j; a single warp keeps the last K rows of L in shared memory.
 // ---------------------------------------------------------------------------
+// indef != 0: symmetric indefinite band, G = L Sigma L' with Sigma = diag(+-1) (the L D L' factorisation without pivoting,
+// written so that the tables keep their meaning: forward solve with L, the sign folded into bw[j][0], backward solve with
+// L').  A pivot that has lost its digits against the terms it was formed from is reported as a breakdown (status): the
+// caller then falls back to the pivoted band LU.
 template <int K>
 __global__ void density_cholesky_kernel(const double *__restrict__ gband, i64 n,
-                                        double *__restrict__ fw, double *__restrict__ bw, int *__restrict__ status) {
+                                        double *__restrict__ fw, double *__restrict__ bw, int *__restrict__ status,
+                                        int indef) {
     constexpr int CH = 64;                          // rows of G staged per step (lanes load, lane 0 factorises)
     constexpr int k = K, W = 2 * K - 1;
     __shared__ double ring[K][K];                   // ring[j % k][p] = L_{j,j-p}
+    __shared__ double rsign[K];                     // rsign[j % k] = Sigma_j
     __shared__ double sg[CH][K];                    // sg[r][p] = G_{j0+r, j0+r-p}
     const int lane = threadIdx.x;
     for (i64 j0 = 0; j0 < n; j0 += CH) {
@@ -62,33 +68,43 @@ __global__ void density_cholesky_kernel(const double *__restrict__ gband, i64 n,
             for (int rr = 0; rr < rows; ++rr) {
                 const i64 j = j0 + rr;
                 double row[K];
+                double sgn = 1.0;
                 // L_{j,c}, c = j-k+1 .. j  <->  p = j-c = k-1 .. 0
 #pragma unroll
                 for (int p = k - 1; p >= 0; --p) {
                     const i64 c = j - p;
                     if (c < 0) { row[p] = 0.0; continue; }
-                    double s = sg[rr][p];
-                    // sum over c' < c, c' >= j-k+1: L_{j,c'} L_{c,c'}
+                    double s = sg[rr][p], mag = fabs(s);
+                    // sum over c' < c, c' >= j-k+1: L_{j,c'} Sigma_c' L_{c,c'}
 #pragma unroll
                     for (int pp = k - 1; pp > p; --pp) {
                         const i64 cc = j - pp;
                         if (cc < 0) continue;
                         const int pc = (int)(c - cc);   // L_{c,cc} = ring[c % k][c-cc]; row j itself is still in `row`
-                        s -= row[pp] * (p == 0 ? row[pp] : ring[c % k][pc]);
+                        const double term = row[pp] * (p == 0 ? row[pp] : ring[c % k][pc]);
+                        s -= indef ? rsign[cc % k] * term : term;
+                        mag += fabs(term);
                     }
                     if (p == 0) {
-                        if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
-                        row[0] = sqrt(s);
+                        if (indef) {
+                            sgn = s < 0.0 ? -1.0 : 1.0;
+                            if (!(fabs(s) > 1e-12 * mag)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
+                            row[0] = sqrt(fabs(s));
+                        } else {
+                            if (!(s > 0.0)) { if (*status == 0) *status = (int)(j + 1); s = 1.0; }
+                            row[0] = sqrt(s);
+                        }
                     } else {
-                        row[p] = s / ring[c % k][0];
+                        row[p] = s / (indef ? rsign[c % k] * ring[c % k][0] : ring[c % k][0]);
                     }
                 }
                 for (int p = 0; p < k; ++p) ring[j % k][p] = row[p];
+                rsign[j % k] = sgn;
                 const double inv = 1.0 / row[0];
                 fw[j * k] = inv;
                 for (int p = 1; p < k; ++p) fw[j * k + p] = row[p] * inv;
-                // bw[c][p] = L_{c+p,c}/L_cc : row j contributes bw[j-p][p]
-                bw[j * k] = inv;
+                // bw[c][p] = L_{c+p,c}/L_cc : row j contributes bw[j-p][p]; the sign of the pivot rides on bw[j][0]
+                bw[j * k] = sgn * inv;
                 for (int p = 1; p < k; ++p)
                     if (j - p >= 0) bw[(j - p) * k + p] = row[p] / ring[(j - p) % k][0];
             }
@@ -916,8 +932,8 @@ static int launch_spikes(cb_density_s *D) {
     return CB_OK;
 }
 
-static int launch_cholesky(int k, const double *g, i64 n, double *fw, double *bw, int *status) {
-    CB_DISPATCH_KD(k, (density_cholesky_kernel<K><<<1, 32>>>(g, n, fw, bw, status)));
+static int launch_cholesky(int k, const double *g, i64 n, double *fw, double *bw, int *status, int indef = 0) {
+    CB_DISPATCH_KD(k, (density_cholesky_kernel<K><<<1, 32>>>(g, n, fw, bw, status, indef)));
     return CB_OK;
 }
 
@@ -1045,7 +1061,14 @@ int cb_density_project(const cb_density *D, const double *fvals, i64 ldf, i64 P,
 
 // ---- SPD banded factor / batched solve: the metric inverse of LinearOperator (src/linear_operators.jl:38-48,
 // factorize(B'B) + ldiv!) ------------------------------------------------------------------------------------
-int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) {
+static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out);
+
+int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) { return bandchol_create(band, n, l, 0, out); }
+int cb_bandldl_create(const double *band, i64 n, int l, cb_bandchol **out) { return bandchol_create(band, n, l, 1, out); }
+
+}  // extern "C"
+
+static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out) {
     CB_REQUIRE(out != nullptr, "cb_bandchol_create: out is NULL");
     *out = nullptr;
     CB_REQUIRE(band != nullptr && n >= 1 && l >= 0, "cb_bandchol_create: bad argument");
@@ -1064,7 +1087,7 @@ int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) {
     if (e == cudaSuccess) step(cudaMemset(d_status, 0, sizeof(int)));
     int rc = CB_OK;
     if (e == cudaSuccess) {
-        rc = launch_cholesky(D->k, band, n, D->d_fw, D->d_bw, d_status);
+        rc = launch_cholesky(D->k, band, n, D->d_fw, D->d_bw, d_status, indef);
         step(cudaGetLastError());
         step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
     }
@@ -1077,14 +1100,17 @@ int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) {
     if (e != cudaSuccess) { cb_set_error("cb_bandchol_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }
     if (rc != CB_OK) { cb_density_destroy(D); return rc; }
     if (D->chol_status != 0) {
-        // PosDefException of cholesky in the reference
-        cb_set_error("cb_bandchol_create: matrix is not positive definite (leading minor %d)", D->chol_status);
+        // PosDefException of cholesky in the reference / breakdown of the unpivoted L D L'
+        cb_set_error(indef ? "cb_bandldl_create: pivot breakdown at column %d (use the pivoted band LU)"
+                           : "cb_bandchol_create: matrix is not positive definite (leading minor %d)", D->chol_status);
         cb_density_destroy(D);
         return CB_ERR_ARG;
     }
     *out = reinterpret_cast<cb_bandchol *>(D);
     return CB_OK;
 }
+
+extern "C" {
 
 int cb_bandchol_solve(const cb_bandchol *F, double *X, i64 ldx, i64 nvec, void *stream) {
     const cb_density_s *D = reinterpret_cast<const cb_density_s *>(F);

@@ -154,13 +154,15 @@ class BandCholesky:
     """Cholesky factor of an SPD ``BandedMatrix`` held on the device (``cb_bandchol_*``); ``ldiv``
     is the batched ``ldiv!`` of the reference's ``LinearOperator`` (src/linear_operators.jl:38-48)."""
 
-    def __init__(self, A: BandedMatrix):
+    def __init__(self, A: BandedMatrix, indefinite: bool = False):
+        """indefinite=True: ``L D L'`` without pivoting of a symmetric indefinite band (``cb_bandldl_create``), same
+        partitioned solve; raises ValueError on a pivot breakdown."""
         if A.m != A.n or A.l != A.u:
             raise DimensionMismatch("DimensionMismatch: cholesky needs a square band with equal bandwidths")
         h = C.c_void_p()
         with torch.cuda.device(A.data.device):
-            _lib.call("cb_bandchol_create", _ptr(A.data), A.n, A.l, C.byref(h))
-        self.handle, self.n, self.device = h, A.n, A.data.device
+            _lib.call("cb_bandldl_create" if indefinite else "cb_bandchol_create", _ptr(A.data), A.n, A.l, C.byref(h))
+        self.handle, self.n, self.device, self.indefinite = h, A.n, A.data.device, bool(indefinite)
 
     def __del__(self):
         try:
@@ -299,27 +301,46 @@ class BandLU:
 
 
 def _band_is_symmetric(A: BandedMatrix) -> bool:
-    """True if the band is symmetric (square, l == u, A[j+d, j] == A[j, j+d] bit for bit)."""
+    """True if the band is symmetric to rounding (square, l == u, |A[j+d, j] - A[j, j+d]| <= 1e-13 max|A|: assembled
+    operators sum their quadrature terms per entry, so the two triangles may differ in the last bits)."""
     if A.m != A.n or A.l != A.u:
         return False
+    tol = 1e-13 * float(A.data.abs().max()) if A.data.numel() else 0.0
     for d in range(1, A.l + 1):
-        if not torch.equal(A.data[:A.n - d, A.u + d], A.data[d:, A.u - d]):
+        if float((A.data[:A.n - d, A.u + d] - A.data[d:, A.u - d]).abs().max()) > tol:
             return False
     return True
 
 
 def factorize(A: BandedMatrix, method: str = "auto"):
-    """``factorize(A)``: "cholesky" (SPD bands, partitioned batched solve), "lu" (pivoted band LU, any non-singular
-    band) or "auto" = Cholesky when the band is symmetric and the factorisation succeeds, else LU."""
+    """``factorize(A)``: "cholesky" (SPD bands, partitioned batched solve), "ldl" (symmetric indefinite, unpivoted
+    L D L', same solve), "lu" (pivoted band LU, any non-singular band) or "auto" = for a symmetric band Cholesky, then
+    L D L' if it passes a residual probe, else LU."""
     if method == "lu":
         return BandLU(A)
     if method == "cholesky":
         lu = max(A.l, A.u)
         return A.widened(lu, lu).cholesky()
+    if method == "ldl":
+        return BandCholesky(A, indefinite=True)
     if _band_is_symmetric(A):
         try:
             return A.cholesky()
         except ValueError:                                           # not positive definite
+            pass
+        try:
+            # symmetric indefinite: L D L' without pivoting keeps the partitioned solve; there is no growth bound
+            # without pivoting, so the factor is accepted only if it solves a probe system to working accuracy
+            F = BandCholesky(A, indefinite=True)
+            g = torch.Generator(device=A.data.device).manual_seed(1234)
+            b = torch.randn((1, A.n), dtype=torch.float64, device=A.data.device, generator=g)
+            x = ColMajor(b.clone())
+            F.ldiv(x)
+            r = ColMajor(torch.empty_like(b))
+            mul(r, A, x)
+            if float(torch.linalg.norm(r.data - b) / torch.linalg.norm(b)) <= 1e-9:
+                return F
+        except ValueError:                                           # pivot breakdown
             pass
     return BandLU(A)
 

@@ -285,6 +285,10 @@ int cb_density_project(const cb_density *D, const double *fvals, cb_i64 ldf, cb_
  * chunk of rows x 32 vectors is an independent warp).  Not positive definite -> CB_ERR_ARG (PosDefException). */
 typedef struct cb_bandchol_s cb_bandchol;
 int cb_bandchol_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
+/* Same handle and solve for a symmetric INDEFINITE band (the shifted operator A - sigma*B of ShiftAndInvert with an
+ * interior shift): L D L' without pivoting, so that the partitioned batched solve applies.  A pivot breakdown ->
+ * CB_ERR_ARG; callers should check a residual (no pivoting: no growth bound) and fall back to cb_bandlu_*. */
+int cb_bandldl_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
 int cb_bandchol_solve(const cb_bandchol *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
 int cb_bandchol_destroy(cb_bandchol *F);
 

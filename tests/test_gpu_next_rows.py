@@ -387,11 +387,42 @@ def test_shift_and_invert_hydrogen_docs_table(cb):
     D = cb.Derivative()
     H = (Br.T @ D.T @ D @ Br) / -2 + Br.T @ cb.CoulombPotential(1.0) @ Br
     S = Br.T @ Br
-    Mi = cb.ShiftAndInvert(H, Br, -0.1)
-    assert isinstance(Mi.Ainv, cb.BandLU)
     X = np.random.default_rng(61).standard_normal((Br.size(), 4))
-    got = (Mi @ cb.ColMajor.from_numpy(X)).numpy()
-    assert relerr(got, cbo.shift_invert_apply(H.dense(), S.dense(), -0.1, X)) <= 1e-10
+    ref = cbo.shift_invert_apply(H.dense(), S.dense(), -0.1, X)
+    Mi = cb.ShiftAndInvert(H, Br, -0.1)                                 # auto: L D L' (partitioned solve) if it passes its probe
+    assert isinstance(Mi.Ainv, cb.BandLU) or Mi.Ainv.indefinite
+    assert relerr((Mi @ cb.ColMajor.from_numpy(X)).numpy(), ref) <= 1e-9
+    for method in ("lu", "ldl"):
+        Mm = cb.ShiftAndInvert(H, Br, -0.1, method=method)
+        assert relerr((Mm @ cb.ColMajor.from_numpy(X)).numpy(), ref) <= 1e-9, method
+
+
+def test_bandldl_partitioned_solve_indefinite(cb):
+    """Unpivoted L D L' of a symmetric indefinite band at a size where the solve is partitioned (> 2 chunks of 256 rows):
+    the shifted kinetic operator T - sigma*S of a k = 5 basis with sigma inside the spectrum, against LAPACK's pivoted
+    band LU (SciPy) and through factorize(auto)."""
+    import torch
+    B = cb.BSpline(cb.LinearKnotSet(5, 0, 50, 1200))
+    Br = B[:, 2:B.nf - 1]
+    D = cb.Derivative()
+    T = (Br.T @ D.T @ D @ Br) / -2
+    S = Br.T @ Br
+    A = T - 3.7 * S                                                   # ~ 43 eigenvalues below the shift
+    n = Br.size()
+    X = np.random.default_rng(62).standard_normal((n, 40))
+    band = A.data.cpu().numpy()
+    ref = cbo.bandlu_solve(band, n, A.l, A.u, X)
+    F = cb.factorize(A)
+    assert isinstance(F, cb.BandCholesky) and F.indefinite
+    Xc = cb.ColMajor.from_numpy(X)
+    F.ldiv(Xc)
+    cond = np.linalg.cond(A.dense())
+    assert relerr(Xc.numpy(), ref) <= max(1e-10, 100 * cond * 2.2e-16)
+    with pytest.raises(ValueError):                                   # a zero leading pivot breaks the unpivoted factorisation
+        z = torch.zeros((4, 3), dtype=torch.float64, device="cuda")
+        z[:, 0] = 1.0
+        z[:, 2] = 1.0
+        cb.BandCholesky(cb.BandedMatrix(z, 4, 4, 1, 1), indefinite=True)
 
 
 # ---------------------------------------------------------------------------
