@@ -636,6 +636,9 @@ density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, doub
 // bound, so nothing on it may wait for memory: the transfer matrices of DS_BATCH chunks are staged in shared memory
 // at a time and the next chunk's E is fetched while the current one is multiplied.
 constexpr int DS_STATE_THREADS = 32;
+#ifndef DS_STATE_CP
+#define DS_STATE_CP 1                             // component-parallel state propagation (density_state_cp_kernel)
+#endif
 
 template <int K>
 __global__ void __launch_bounds__(DS_STATE_THREADS)
@@ -683,6 +686,58 @@ density_state_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const doub
             }
 #pragma unroll
             for (int o = 0; o < S; ++o) { s[o] = sn[o]; St[((c + dir) * S + o) * P + p] = sn[o]; }
+        }
+    }
+}
+
+// F2 / B2, component-parallel form: one thread per (pair, state component).  A warp holds 32 / G pairs (G = 8 for
+// K <= 9, else 16: the K-1 components of a pair padded to a power of two); a step is K-1 FMAs per thread with the old
+// state gathered by shuffles, instead of (K-1)^2 FMAs and as many shared-memory reads in one thread.  The chain was
+// issue-bound on that single warp per SM (93 us per sweep at C5: ~470 cycles per chunk); here it is K-1 times shorter
+// and spread over K-1 times as many warps.
+template <int K>
+__global__ void __launch_bounds__(32)
+density_state_cp_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const double *__restrict__ E,
+                        double *__restrict__ St, int dir) {
+    constexpr int S = K > 1 ? K - 1 : 1;
+    constexpr int G = S <= 8 ? 8 : 16;              // lanes per pair
+    constexpr int PPW = 32 / G;                     // pairs per warp
+    constexpr int BATCH = 16;                       // chunks of transfer matrices staged at a time
+    __shared__ double sT[BATCH * S * S];
+    const int lane = threadIdx.x, o = lane % G, pl = lane / G;
+    const i64 p = (i64)blockIdx.x * PPW + pl;
+    const bool live = p < P && o < S;
+    const int gbase = pl * G;
+    double s = 0.0;                                 // component o of the state of pair p
+    const i64 c0 = dir > 0 ? 0 : nchunk - 1, steps = nchunk - 1;
+    if (live) St[(c0 * S + o) * P + p] = 0.0;
+    for (i64 base = 0; base < steps; base += BATCH) {
+        const int nb = steps - base < BATCH ? (int)(steps - base) : BATCH;
+        __syncwarp();
+        for (int e = lane; e < nb * S * S; e += 32) {
+            const int bq = e / (S * S);
+            ds_cp8(&sT[e], T + (c0 + dir * (base + bq)) * (S * S) + (e - bq * S * S));
+        }
+        // this lane's E of the batch: independent loads, issued before the chain needs them
+        double ev[BATCH];
+#pragma unroll
+        for (int bq = 0; bq < BATCH; ++bq)
+            ev[bq] = (live && bq < nb) ? E[((c0 + dir * (base + bq)) * S + o) * P + p] : 0.0;
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int bq = 0; bq < BATCH; ++bq) {
+            if (bq < nb) {
+                const i64 c = c0 + dir * (base + bq);
+                double v = ev[bq];
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const double si = __shfl_sync(0xffffffffu, s, gbase + i);
+                    if (o < S) v = fma(sT[(bq * S + o) * S + i], si, v);
+                }
+                s = v;
+                if (live) St[((c + dir) * S + o) * P + p] = v;
+            }
         }
     }
 }
@@ -903,10 +958,18 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     // grid.y = chunks <= 65535 is checked at plan time
     dim3 grid((unsigned)ptiles, (unsigned)M);
     density_fwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_fw, n, M, X, ldx, P, E);
+#if DS_STATE_CP
+    constexpr int PPW = 32 / ((K > 1 ? K - 1 : 1) <= 8 ? 8 : 16);
+    const unsigned sblocks = (unsigned)((P + PPW - 1) / PPW);
+    density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tf, M, P, E, St, +1);
+    density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tb, M, P, E, St, -1);
+#else
     const unsigned sblocks = (unsigned)((P + DS_STATE_THREADS - 1) / DS_STATE_THREADS);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tf, M, P, E, St, +1);
     density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
+#endif
     const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
     dim3 gfix((unsigned)cb_grid_for(n, 256, 2), (unsigned)(npg < 4096 ? npg : 4096));
     density_bwd_fix_kernel<K><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
