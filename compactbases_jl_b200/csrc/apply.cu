@@ -1566,6 +1566,8 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
             const size_t psmem = nstg * stage_b + as_b + 256;
             CB_CUDA(cudaFuncSetAttribute(banded_apply_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
             // vector tiles per work item: the one of 8..4 (1 if there are few) that deals the items most evenly
+            // (measured, C3 / k = 7: 1 tile per item 301 / 350 us, 2: 227 / 243, 4: 194 / 197, 8: 180 / 191, 16: - / 220,
+            // 32: - / 249 — few tiles per item expose the staging of the A fragments, many unbalance the CTAs)
             const i64 nrt = (m + BTP_ROWS - 1) / BTP_ROWS, nvt = (nvec + BTP_VEC - 1) / BTP_VEC;
             i64 best = 1;
             if (nrt * nvt >= (i64)CB_NUM_SMS * 8) {
@@ -1578,6 +1580,9 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
                     if (eff > best_eff + 1e-9) { best_eff = eff; best = vcn; }
                 }
             }
+#ifdef BTP_VCHUNK
+            best = BTP_VCHUNK;
+#endif
             const i64 pitems = nrt * ((nvt + best - 1) / best);
             const int pgrid = (int)(pitems < CB_NUM_SMS ? pitems : CB_NUM_SMS);
             banded_apply_pipe_kernel<<<pgrid, 32 * (BTP_NG + 2), psmem, (cudaStream_t)stream>>>(
