@@ -492,3 +492,31 @@ def test_implicit_finite_differences_nonuniform(cb):
     assert err.max() < 1e-8, err.max()
     Rr = R[:, 2:N - 1]
     assert (Rr.T @ D.T @ D @ Rr).shape == (N - 2, N - 2)
+
+
+def test_hydrogen_staggered_fd_reference_levels(cb):
+    """test/fd/derivatives.jl:182-208: hydrogen on StaggeredFiniteDifferences(N, 0.25), r_max = 300, with the
+    CoulombDerivative correction of the Laplacian at the origin: |E_1 + 1/2| < 3e-5 and the ten lowest levels to 1e-3
+    relative — pins the assembled operators; the lowest levels then through ShiftAndInvert on the device."""
+    from scipy.linalg import eigvalsh_tridiagonal
+    rmax, rho = 300, 0.25
+    N = int(np.ceil(rmax / rho + 0.5))
+    R = cb.StaggeredFiniteDifferences(N, rho)
+    D = cb.Derivative()
+    Dc = cb.CoulombDerivative(D, 1, 0)
+    Tm = (R.T @ Dc.T @ Dc @ R) / -2
+    V = R.T @ cb.QuasiDiagonal(lambda r: -1.0 / r) @ R
+    dv = Tm.d.cpu().numpy() + V.diag.cpu().numpy()
+    ev = Tm.dl.cpu().numpy()
+    assert np.array_equal(ev, Tm.du.cpu().numpy())                   # Tm isa SymTridiagonal
+    vals = eigvalsh_tridiagonal(dv, ev, select="i", select_range=(0, 9))
+    lam = -1.0 / (2.0 * np.arange(1, 11) ** 2)
+    abs_err = vals - lam
+    assert abs(abs_err[0]) < 3e-5
+    assert np.all(np.abs(abs_err) / np.abs(1e-10 + np.abs(lam)) < 1e-3)
+    H = cb.as_banded(Tm) + V
+    sigma = 1.1 * lam[0]
+    M = cb.ShiftAndInvert(H, R, sigma)
+    # orthogonal iteration converges like (theta_7 / theta_k)^iterations: fast for the two lowest levels only
+    theta = _subspace_eigs(M, N, 2, 150, 5)
+    np.testing.assert_allclose(sigma + 1.0 / theta, vals[:2], rtol=0, atol=1e-9)
