@@ -123,3 +123,64 @@ def test_host_only_fedvr_grid_matches_oracle():
     assert B._block_structure(4, b) == [2, 1, 2, 1, 1, 3, 1, 2, 1, 1]
     assert B._block_structure(a, N - 8) == [3, 1, 2, 1, 1, 2]
     assert B.elements(1, b) == (1, 8)
+
+
+def test_band_algebra_host_logic():
+    """The band arithmetic of the host mirror (A - sigma*B, widening, symmetry test, Tridiagonal -> band) needs no
+    device: checked on CPU tensors against dense numpy."""
+    import torch
+    import compactbases_jl_b200 as cb
+    from compactbases_jl_b200.operators import _band_axpy, _band_is_symmetric
+
+    def band_of(A, l, u):
+        n = A.shape[0]
+        data = np.zeros((n, l + u + 1))
+        for j in range(n):
+            for i in range(max(0, j - u), min(n, j + l + 1)):
+                data[j, u + i - j] = A[i, j]
+        return cb.BandedMatrix(torch.as_tensor(data), n, n, l, u)
+
+    rng = np.random.default_rng(5)
+    n = 9
+    A = np.triu(np.tril(rng.standard_normal((n, n)), 2), -1)          # l = 1, u = 2
+    B = np.triu(np.tril(rng.standard_normal((n, n)), 1), -3)          # l = 3, u = 1
+    Ab, Bb = band_of(A, 1, 2), band_of(B, 3, 1)
+    assert np.array_equal(Ab.dense(), A) and np.array_equal(Bb.dense(), B)
+    C = _band_axpy(Ab, Bb, -0.7)
+    assert (C.l, C.u) == (3, 2) and np.allclose(C.dense(), A - 0.7 * B, rtol=0, atol=1e-15)
+    assert np.array_equal(Ab.widened(4, 4).dense(), A)
+    assert np.allclose((Ab / -2).dense(), A / -2) and np.allclose((3 * Ab).dense(), 3 * A) and np.allclose((-Ab).dense(), -A)
+    S = A + A.T
+    assert _band_is_symmetric(band_of(S, 2, 2)) and not _band_is_symmetric(band_of(A, 2, 2)) and not _band_is_symmetric(Ab)
+    S2 = S.copy(); S2[3, 4] *= 1 + 1e-15                              # rounding-level asymmetry is accepted
+    assert _band_is_symmetric(band_of(S2, 2, 2))
+    dl, d, du = rng.standard_normal(n - 1), rng.standard_normal(n), rng.standard_normal(n - 1)
+    T = cb.Tridiagonal(*(torch.as_tensor(v) for v in (dl, d, du)))
+    assert np.array_equal(cb.as_banded(T).dense(), np.diag(d) + np.diag(dl, -1) + np.diag(du, 1))
+    assert np.allclose((T / 4).dense(), T.dense() / 4)
+    Dg = cb.Diagonal(torch.as_tensor(d))
+    assert np.allclose((cb.as_banded(T) + Dg).dense(), T.dense() + np.diag(d))
+
+
+def test_implicit_stencils_host_equals_closed_form():
+    """implicit_stencil_common (the reference's loop, src/fd_derivatives.jl:105-125, in the host mirror) against the
+    oracle's closed form on the local steps, and the uniform-grid limits alpha = beta = 1/h^2, M = (1, 10, 1)/12."""
+    from compactbases_jl_b200.finite_differences import implicit_stencil_common
+    j = np.arange(1, 60)
+    r = 0.05 * j + 0.002 * j ** 2
+    st = cbo.implicit_stencils_nonuniform(r)
+    funs = {"alpha_t": (lambda a, b, c: 2 / (a * (a + b)), 2, -1), "alpha": (lambda a, b, c: 2 / (b * (a + b)), 1, -1),
+            "beta": (lambda a, b, c: 1 / (a * b), 1, 0),
+            "m_dl": (lambda a, b, c: (a * a + a * b - b * b) / (6 * a * (a + b)), 2, -1),
+            "m_d": (lambda a, b, c: (a * a + 3 * a * b + b * b) / (6 * a * b), 1, 0),
+            "m_du": (lambda a, b, c: (-a * a + a * b + b * b) / (6 * b * (a + b)), 1, -1)}
+    for name, (f, s, dn) in funs.items():
+        np.testing.assert_array_equal(implicit_stencil_common(r, f, s, dn), st[name])
+    h = 0.25
+    u = cbo.implicit_stencils_nonuniform(h * np.arange(1, 12))
+    np.testing.assert_allclose(u["alpha"], 1 / h ** 2, rtol=1e-14)
+    np.testing.assert_allclose(u["alpha_t"], 1 / h ** 2, rtol=1e-14)
+    np.testing.assert_allclose(u["beta"], 1 / h ** 2, rtol=1e-14)
+    np.testing.assert_allclose(u["m_d"], 10 / 12, rtol=1e-14)
+    np.testing.assert_allclose(u["m_dl"], 1 / 12, rtol=1e-13)
+    np.testing.assert_allclose(u["m_du"], 1 / 12, rtol=1e-13)
