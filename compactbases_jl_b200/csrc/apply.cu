@@ -1,16 +1,16 @@
 // apply.cu — Y = alpha*A*X + beta*Y for the operator containers of the hot path
 // (SURVEY §8 a17): Tridiagonal/SymTridiagonal (K9), BandedMatrix (K7), Diagonal,
-// and the FE-DVR element-block operator (K8).  The arithmetic of mul! lives in
-// LinearAlgebra / BandedMatrices / BlockBandedMatrices in the reference (call
-// sites src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46,
-// test/derivative_accuracy_utils.jl:26-37).
+// and the FE-DVR element-block operator (K8); plus the BLAS-1 helpers around them (axpby, batched dot).
+// The arithmetic of mul! lives in LinearAlgebra / BandedMatrices / BlockBandedMatrices in the reference (call
+// sites src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46, test/derivative_accuracy_utils.jl:26-37).
 //
-// All kernels are HBM-bound stencils over X (n x nvec, column-major).  Common
-// shape: a CTA owns a (row tile) x (vector tile); X is read coalesced along the
-// rows; for the wide stencils the tile is staged in shared memory with an odd
-// pitch and consumed with lanes <-> vectors, so that operator entries are
-// warp-uniform (broadcast) shared-memory reads and every X value is reused from
-// registers.
+// All kernels are HBM-bound stencils over X (n x nvec, column-major).  Each of K7, K8, K9 exists twice:
+//   * a warp-specialised TMA pipeline (one persistent CTA per SM: a loader warp and a storer warp move tiles with
+//     cp.async.bulk — one 1-D bulk copy per vector column — through a ring of shared-memory stages handed over by
+//     mbarriers; the other warps compute in shared memory: DMMA for K7 / K8, plain FMAs for K9).  Taken when
+//     beta == 0 and X, Y agree in 16-byte phase per column;
+//   * the earlier kernel whose warps load, compute and store in turn (cp.async / register staging), for every
+//     other call.  Both give the same results; the parity tests run both.
 #include <stdlib.h>
 
 #include "common.cuh"
