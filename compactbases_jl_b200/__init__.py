@@ -11,7 +11,7 @@ from ._lib import DimensionMismatch, CudaError
 from .knot_sets import ArbitraryKnotSet, ExpKnotSet, LinearKnotSet
 from .quadrature import gausslegendre, gausslobatto, num_quadrature_points
 from .lazy import CoulombDerivative, Derivative, QuasiDiagonal, materialize
-from .operators import (BandCholesky, BandLU, BandedMatrix, ColMajor, Diagonal, FEDVRMatrix, ImplicitDerivative, LinearOperator, ShiftAndInvert,
+from .operators import (BandCholesky, BandLU, BandedMatrix, BlockSkylineMatrix, ColMajor, Diagonal, FEDVRMatrix, ImplicitDerivative, LinearOperator, ShiftAndInvert,
                         SymTridiagonal, Tridiagonal, as_banded, axpby, batched_dot, factorize, inner_product, mul, norm)
 from .bsplines import BSpline, CoulombPotential, RestrictedBSpline, SparseMatrixCSC, diffop
 from .fedvr import FEDVR, RestrictedFEDVR
@@ -23,7 +23,7 @@ __all__ = [
     "ArbitraryKnotSet", "ExpKnotSet", "LinearKnotSet", "BSpline", "RestrictedBSpline", "SparseMatrixCSC",
     "CoulombPotential", "diffop", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
     "RestrictedFiniteDifferences", "Derivative", "QuasiDiagonal", "CoulombDerivative", "materialize",
-    "BandedMatrix", "BandCholesky", "LinearOperator", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
+    "BandedMatrix", "BlockSkylineMatrix", "BandCholesky", "LinearOperator", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
     "Density", "FunctionProduct", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "batched_dot", "inner_product", "norm", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
     "num_quadrature_points",
 ]

@@ -58,27 +58,32 @@ _SIGNATURES = {
     "cb_band_to_tridiag": (cint, [vp, i64, vp, vp, vp, vp]),
     "cb_fedvr_assemble": (cint, [vp, vp, vp, vp, vp, vp, vp, i64, cint, cint, cint, vp, vp]),
     "cb_fedvr_to_dense": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp]),
+    "cb_fedvr_to_skyline": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "cb_fedvr_to_tridiag": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     "cb_fedvr_apply": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
-    "cb_fedvr_apply_host": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64]),
+    "cb_fedvr_apply_host": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_fd_derivative": (cint, [cint, cint, vp, vp, i64, dbl, i64, i64, dbl, cint, vp, vp, vp, vp]),
     "cb_banded_apply": (cint, [vp, i64, i64, cint, cint, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_tridiag_apply": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
-    "cb_tridiag_apply_host": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64]),
+    "cb_tridiag_apply_host": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
+    "cb_banded_apply_host": (cint, [vp, i64, i64, cint, cint, vp, i64, i64, dbl, dbl, vp, i64, vp]),
+    "cb_host_register": (cint, [vp, C.c_size_t]),
+    "cb_host_unregister": (cint, [vp]),
     "cb_diag_apply": (cint, [vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_axpby": (cint, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
     "cb_batched_dot": (cint, [vp, i64, vp, i64, i64, i64, dbl, vp, vp]),
-    "cb_density_bspline_create": (cint, [vp, i64, i64, vp, C.POINTER(vp)]),
+    "cb_density_bspline_create": (cint, [vp, i64, i64, vp, C.POINTER(vp), vp]),
     "cb_density_destroy": (cint, [vp]),
     "cb_density_set_refine": (cint, [vp, cint]),
     "cb_density_apply": (cint, [vp, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_nodal_product": (cint, [vp, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_orthogonal": (cint, [vp, i64, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_project": (cint, [vp, vp, i64, i64, vp, i64, vp]),
-    "cb_bandchol_create": (cint, [vp, i64, cint, C.POINTER(vp)]),
-    "cb_bandldl_create": (cint, [vp, i64, cint, C.POINTER(vp)]),
+    "cb_bandchol_create": (cint, [vp, i64, cint, C.POINTER(vp), vp]),
+    "cb_bandldl_create": (cint, [vp, i64, cint, C.POINTER(vp), vp]),
     "cb_bandchol_solve": (cint, [vp, vp, i64, i64, vp]),
     "cb_bandchol_destroy": (cint, [vp]),
-    "cb_bandlu_create": (cint, [vp, i64, cint, cint, C.POINTER(vp)]),
+    "cb_bandlu_create": (cint, [vp, i64, cint, cint, C.POINTER(vp), vp]),
     "cb_bandlu_solve": (cint, [vp, vp, i64, i64, vp]),
     "cb_bandlu_destroy": (cint, [vp]),
 }

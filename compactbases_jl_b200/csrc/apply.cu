@@ -12,6 +12,7 @@
 //   * the earlier kernel whose warps load, compute and store in turn (cp.async / register staging), for every
 //     other call.  Both give the same results; the parity tests run both.
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -1395,6 +1396,57 @@ __global__ void fedvr_to_dense_kernel(const double *__restrict__ blocks, const i
     }
 }
 
+// Export into BlockBandedMatrices' BlockSkylineMatrix storage (Matrix(undef, B) + set_elements!,
+// src/fedvr_operators.jl:17-30,87-134,148-154).  The skyline keeps, per block column J, the block rows kfirst[J]..klast[J]
+// stacked into one dense column-major panel of cstride[J] rows that begins at data[cstart[J]]; blk_cum are the
+// cumulative block sizes (block b = functions blk_cum[b]..blk_cum[b+1]-1 of the restriction).  data must be zero; one
+// CTA per element scatters its block, the two corners that meet on a bridge function are added atomically (two
+// addends: the sum does not depend on their order).  Entries outside the skyline can only be structural zeros of
+// the block pattern; a non-zero one raises the error flag.
+__global__ void fedvr_to_skyline_kernel(const double *__restrict__ blocks, const i64 *__restrict__ estart,
+                                        const int32_t *__restrict__ order, const i64 *__restrict__ boff,
+                                        i64 nel, i64 first0, i64 nrows,
+                                        const i64 *__restrict__ blk_cum, i64 nblk, const i64 *__restrict__ kfirst,
+                                        const i64 *__restrict__ klast, const i64 *__restrict__ cstart,
+                                        const i64 *__restrict__ cstride, double *__restrict__ data, i64 ndata,
+                                        int *__restrict__ err) {
+    auto block_of = [&](i64 i) {                    // last b with blk_cum[b] <= i
+        i64 lo = 0, hi = nblk;
+        while (lo < hi) { const i64 mid = (lo + hi) >> 1; if (blk_cum[mid] <= i) lo = mid + 1; else hi = mid; }
+        return lo - 1;
+    };
+    for (i64 e = blockIdx.x; e < nel; e += gridDim.x) {
+        const int o = order[e];
+        const double *b = blocks + boff[e];
+        for (int t = threadIdx.x; t < o * o; t += blockDim.x) {
+            const int mm = t % o, mp = t / o;
+            const i64 gi = estart[e] + mm - first0, gj = estart[e] + mp - first0;
+            if (gi < 0 || gi >= nrows || gj < 0 || gj >= nrows) continue;
+            const i64 K = block_of(gi), J = block_of(gj);
+            if (K < kfirst[J] || K > klast[J]) { if (b[t] != 0.0) atomicOr(err, 1); continue; }
+            const i64 idx = cstart[J] + (gi - blk_cum[kfirst[J]]) + (gj - blk_cum[J]) * cstride[J];
+            if (idx < 0 || idx >= ndata) { atomicOr(err, 2); continue; }
+            const bool shared_corner = (mm == mp) && ((mm == 0 && e > 0) || (mm == o - 1 && e < nel - 1));
+            if (shared_corner) atomicAdd(&data[idx], b[t]);
+            else data[idx] = b[t];
+        }
+    }
+}
+
+// All orders 2: Matrix(undef, B) is a Tridiagonal (src/fedvr_operators.jl:18-23), filled by set_element!(::Tridiagonal)
+// (:136-146).  d must be zero.
+__global__ void fedvr_to_tridiag_kernel(const double *__restrict__ blocks, const i64 *__restrict__ estart,
+                                        const i64 *__restrict__ boff, i64 nel, i64 first0, i64 nrows,
+                                        double *__restrict__ dl, double *__restrict__ d, double *__restrict__ du) {
+    for (i64 e = blockIdx.x * (i64)blockDim.x + threadIdx.x; e < nel; e += (i64)gridDim.x * blockDim.x) {
+        const double *b = blocks + boff[e];         // 2 x 2, column-major
+        const i64 g0 = estart[e] - first0, g1 = g0 + 1;
+        if (g0 >= 0 && g0 < nrows) atomicAdd(&d[g0], b[0]);
+        if (g1 >= 0 && g1 < nrows) atomicAdd(&d[g1], b[3]);
+        if (g0 >= 0 && g1 < nrows) { dl[g0] = b[1]; du[g0] = b[2]; }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1654,42 +1706,91 @@ int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *or
     return CB_OK;
 }
 
+int cb_fedvr_to_skyline(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                        i64 nel, i64 first, i64 last, const i64 *blk_cum, i64 nblk, const i64 *col_kfirst,
+                        const i64 *col_klast, const i64 *col_start, const i64 *col_stride, double *data, i64 ndata,
+                        void *stream) {
+    CB_REQUIRE(blocks && estart && order && boff && data, "cb_fedvr_to_skyline: NULL argument");
+    CB_REQUIRE(blk_cum && col_kfirst && col_klast && col_start && col_stride && nblk >= 1, "cb_fedvr_to_skyline: NULL block structure");
+    CB_REQUIRE(first >= 1 && last >= first && ndata >= 0, "cb_fedvr_to_skyline: invalid restriction");
+    const i64 nrows = last - first + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
+    int *d_err = nullptr;
+    CB_CUDA(cudaMallocAsync(&d_err, sizeof(int), st));
+    CB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    CB_CUDA(cudaMemsetAsync(data, 0, sizeof(double) * (size_t)ndata, st));      // A .= false, src/fedvr_operators.jl:149
+    fedvr_to_skyline_kernel<<<(unsigned)(nel < 8192 ? nel : 8192), 128, 0, st>>>(blocks, estart, order, boff, nel, first - 1, nrows,
+                                                                                 blk_cum, nblk, col_kfirst, col_klast, col_start,
+                                                                                 col_stride, data, ndata, d_err);
+    cudaError_t e = cudaGetLastError();
+    int herr = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(d_err, st);
+    if (e != cudaSuccess) { cb_set_error("cb_fedvr_to_skyline: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    CB_REQUIRE(herr == 0, "cb_fedvr_to_skyline: the block structure does not hold the element blocks (%s)",
+               (herr & 2) ? "index outside data" : "non-zero entry outside the skyline");
+    return CB_OK;
+}
+
+int cb_fedvr_to_tridiag(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                        i64 nel, i64 first, i64 last, double *dl, double *d, double *du, void *stream) {
+    (void)order;                                    // all orders are 2 (the caller's Matrix(undef, B) is a Tridiagonal)
+    CB_REQUIRE(blocks && estart && boff && d, "cb_fedvr_to_tridiag: NULL argument");
+    CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_to_tridiag: invalid restriction");
+    const i64 nrows = last - first + 1;
+    CB_REQUIRE(nrows == 1 || (dl && du), "cb_fedvr_to_tridiag: NULL off-diagonal");
+    cudaStream_t st = (cudaStream_t)stream;
+    CB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)nrows, st));
+    fedvr_to_tridiag_kernel<<<cb_grid_for(nel, 256), 256, 0, st>>>(blocks, estart, boff, nel, first - 1, nrows, dl, d, du);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 // ---- host-buffer forms: stream the vector batch through the device ----------
 typedef int (*apply_dev_fn)(void *ctx, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st);
 
 // Device staging buffers and streams of the host-buffer entry points, kept per device between calls
 // (allocation and stream creation cost milliseconds, a 737 MB batch over PCIe ~15 ms each way).
+// The entry points are serialised per device by `mu` (the staging ring is shared state).
 struct HostPipe {
     static constexpr int NBUF = 3;
+    std::mutex mu;
     bool init = false;
     size_t bytes = 0;                               // capacity of each buffer
     double *dX[NBUF] = {nullptr, nullptr, nullptr}, *dY[NBUF] = {nullptr, nullptr, nullptr};
     cudaStream_t st[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t producer = nullptr;                 // "the operator arrays are ready" on the caller's stream
 };
 static HostPipe g_pipes[64];
 
-static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows, const double *Xh, i64 ldx, i64 nvec,
-                               double alpha, double beta, double *Yh, i64 ldy) {
-    if (nvec == 0 || nrows == 0) return CB_OK;
+// `producer`: the stream on which the caller enqueued the work that produces the operator arrays (assembly kernels);
+// the staging streams wait for everything enqueued on it so far before their first kernel.
+static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows_in, i64 nrows_out, const double *Xh, i64 ldx, i64 nvec,
+                               double alpha, double beta, double *Yh, i64 ldy, cudaStream_t producer) {
+    if (nvec == 0 || nrows_out == 0) return CB_OK;
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     CB_REQUIRE(dev >= 0 && dev < 64, "host pipeline: device index out of range");
     HostPipe &P = g_pipes[dev];
-    // tile of vectors: ~32 MB per buffer (CB_HOST_CHUNK_MB overrides, for tuning); the device copy is dense (ld = nrows)
+    std::lock_guard<std::mutex> lock(P.mu);
+    // tile of vectors: ~32 MB per buffer (CB_HOST_CHUNK_MB overrides, for tuning); the device copy is dense (ld = rows)
     static i64 chunk_mb = 0;
     if (chunk_mb == 0) {
         const char *env = getenv("CB_HOST_CHUNK_MB");
         chunk_mb = env ? atoll(env) : 32;
         if (chunk_mb < 1 || chunk_mb > 1024) chunk_mb = 32;
     }
-    i64 tv = (chunk_mb << 20) / (nrows * (i64)sizeof(double));
+    const i64 nrmax = nrows_in > nrows_out ? nrows_in : nrows_out;
+    i64 tv = (chunk_mb << 20) / (nrmax * (i64)sizeof(double));
     if (tv < 1) tv = 1;
     if (tv > nvec) tv = nvec;
-    const i64 ld = nrows;
-    const size_t need = sizeof(double) * (size_t)ld * (size_t)tv;
+    const size_t need = sizeof(double) * (size_t)nrmax * (size_t)tv;
     cudaError_t e = cudaSuccess;
     if (!P.init) {
         for (int b = 0; b < HostPipe::NBUF && e == cudaSuccess; ++b) e = cudaStreamCreateWithFlags(&P.st[b], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.producer, cudaEventDisableTiming);
         P.init = e == cudaSuccess;
     }
     if (e == cudaSuccess && P.bytes < need) {
@@ -1701,19 +1802,23 @@ static int apply_host_pipeline(apply_dev_fn fn, void *ctx, i64 nrows, const doub
         }
         if (e == cudaSuccess) P.bytes = need;
     }
+    // order the staging streams after the producer of the operator arrays (they are non-blocking streams: not even the
+    // legacy default stream orders them implicitly)
+    if (e == cudaSuccess) e = cudaEventRecord(P.producer, producer);
+    for (int b = 0; b < HostPipe::NBUF && e == cudaSuccess; ++b) e = cudaStreamWaitEvent(P.st[b], P.producer, 0);
     int rc = CB_OK;
-    auto copy2d = [&](double *dst, i64 ldd, const double *src, i64 lds, i64 nv, cudaMemcpyKind kind, cudaStream_t st) {
-        if (ldd == nrows && lds == nrows) return cudaMemcpyAsync(dst, src, sizeof(double) * nrows * nv, kind, st);
-        return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * nrows, nv, kind, st);
+    auto copy2d = [&](double *dst, i64 ldd, const double *src, i64 lds, i64 nr, i64 nv, cudaMemcpyKind kind, cudaStream_t st) {
+        if (ldd == nr && lds == nr) return cudaMemcpyAsync(dst, src, sizeof(double) * nr * nv, kind, st);
+        return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * nr, nv, kind, st);
     };
     i64 t = 0;
     for (i64 v0 = 0; v0 < nvec && e == cudaSuccess && rc == CB_OK; v0 += tv, ++t) {
         const int b = (int)(t % HostPipe::NBUF);
         const i64 nv = v0 + tv <= nvec ? tv : nvec - v0;
-        e = copy2d(P.dX[b], ld, Xh + v0 * ldx, ldx, nv, cudaMemcpyHostToDevice, P.st[b]);
-        if (e == cudaSuccess && beta != 0.0) e = copy2d(P.dY[b], ld, Yh + v0 * ldy, ldy, nv, cudaMemcpyHostToDevice, P.st[b]);
-        if (e == cudaSuccess) rc = fn(ctx, P.dX[b], ld, nv, alpha, beta, P.dY[b], P.st[b]);
-        if (e == cudaSuccess && rc == CB_OK) e = copy2d(Yh + v0 * ldy, ldy, P.dY[b], ld, nv, cudaMemcpyDeviceToHost, P.st[b]);
+        e = copy2d(P.dX[b], nrows_in, Xh + v0 * ldx, ldx, nrows_in, nv, cudaMemcpyHostToDevice, P.st[b]);
+        if (e == cudaSuccess && beta != 0.0) e = copy2d(P.dY[b], nrows_out, Yh + v0 * ldy, ldy, nrows_out, nv, cudaMemcpyHostToDevice, P.st[b]);
+        if (e == cudaSuccess) rc = fn(ctx, P.dX[b], nrows_in, nv, alpha, beta, P.dY[b], P.st[b]);
+        if (e == cudaSuccess && rc == CB_OK) e = copy2d(Yh + v0 * ldy, ldy, P.dY[b], nrows_out, nrows_out, nv, cudaMemcpyDeviceToHost, P.st[b]);
     }
     for (int b = 0; b < HostPipe::NBUF; ++b) {
         if (P.st[b]) { cudaError_t e2 = cudaStreamSynchronize(P.st[b]); if (e == cudaSuccess) e = e2; }
@@ -1730,11 +1835,11 @@ static int fedvr_dev(void *c, const double *Xd, i64 ld, i64 nv, double alpha, do
 
 int cb_fedvr_apply_host(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
                         i64 nel, int uniform_order, i64 first, i64 last,
-                        const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy) {
+                        const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy, void *stream) {
     CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_apply_host: invalid restriction");
     CB_REQUIRE(Xh && Yh && ldx >= last - first + 1 && ldy >= last - first + 1, "cb_fedvr_apply_host: bad host arrays");
     fedvr_ctx c{blocks, estart, order, boff, nel, uniform_order, first, last};
-    return apply_host_pipeline(fedvr_dev, &c, last - first + 1, Xh, ldx, nvec, alpha, beta, Yh, ldy);
+    return apply_host_pipeline(fedvr_dev, &c, last - first + 1, last - first + 1, Xh, ldx, nvec, alpha, beta, Yh, ldy, (cudaStream_t)stream);
 }
 
 struct tri_ctx { const double *dl, *d, *du; i64 n; };
@@ -1744,10 +1849,36 @@ static int tri_dev(void *c, const double *Xd, i64 ld, i64 nv, double alpha, doub
 }
 
 int cb_tridiag_apply_host(const double *dl, const double *d, const double *du, i64 n,
-                          const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy) {
+                          const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy, void *stream) {
     CB_REQUIRE(Xh && Yh && ldx >= n && ldy >= n, "cb_tridiag_apply_host: bad host arrays");
     tri_ctx c{dl, d, du, n};
-    return apply_host_pipeline(tri_dev, &c, n, Xh, ldx, nvec, alpha, beta, Yh, ldy);
+    return apply_host_pipeline(tri_dev, &c, n, n, Xh, ldx, nvec, alpha, beta, Yh, ldy, (cudaStream_t)stream);
+}
+
+struct band_ctx { const double *band; i64 m, n; int l, u; };
+static int band_dev(void *c, const double *Xd, i64 ld, i64 nv, double alpha, double beta, double *Yd, cudaStream_t st) {
+    band_ctx *b = (band_ctx *)c;
+    return cb_banded_apply(b->band, b->m, b->n, b->l, b->u, Xd, b->n, nv, alpha, beta, Yd, b->m, st);
+}
+
+int cb_banded_apply_host(const double *band, i64 m, i64 n, int l, int u,
+                         const double *Xh, i64 ldx, i64 nvec, double alpha, double beta, double *Yh, i64 ldy, void *stream) {
+    CB_REQUIRE(band && Xh && Yh && m >= 0 && n >= 0 && ldx >= n && ldy >= m, "cb_banded_apply_host: bad arguments");
+    band_ctx c{band, m, n, l, u};
+    return apply_host_pipeline(band_dev, &c, n, m, Xh, ldx, nvec, alpha, beta, Yh, ldy, (cudaStream_t)stream);
+}
+
+// cudaHostRegister / cudaHostUnregister for caller-owned host arrays (a Julia `Array` is pageable: registering it once
+// lets the host-buffer entries copy at PCIe speed; CUDA.jl's `CUDA.pin` does the same).
+int cb_host_register(void *ptr, size_t bytes) {
+    CB_REQUIRE(ptr != nullptr && bytes > 0, "cb_host_register: bad argument");
+    CB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return CB_OK;
+}
+int cb_host_unregister(void *ptr) {
+    CB_REQUIRE(ptr != nullptr, "cb_host_unregister: NULL");
+    CB_CUDA(cudaHostUnregister(ptr));
+    return CB_OK;
 }
 
 }  // extern "C"

@@ -298,11 +298,23 @@ int cb_bandlu_destroy(cb_bandlu *F) {
     return CB_OK;
 }
 
-int cb_bandlu_create(const double *band, i64 n, int l, int u, cb_bandlu **out) {
+static size_t bandlu_solve_smem(int l, int u) {
+    const int kv = l + u, reach = kv > l ? kv : l;
+    const int fw = kv + 1 > l ? kv + 1 : l;
+    return sizeof(double) * (size_t)LU_WARPS * ((size_t)(LU_R + reach) * 33 + (size_t)LU_R * fw + LU_R / 2);
+}
+
+int cb_bandlu_create(const double *band, i64 n, int l, int u, cb_bandlu **out, void *stream) {
     CB_REQUIRE(out != nullptr, "cb_bandlu_create: out is NULL");
     *out = nullptr;
     CB_REQUIRE(band != nullptr && n >= 1 && l >= 0 && u >= 0, "cb_bandlu_create: bad argument");
-    if (l + u > 31) { cb_set_error("cb_bandlu_create: l + u = %d outside the supported range 0..31", l + u); return CB_ERR_UNSUPPORTED; }
+    // the factorisation's lanes cover l + 1 pivot candidates and l + u trailing columns; the solve's row chunk must fit
+    // the 227 KB of shared memory a CTA can opt into (l + u = 31 does not) — refuse here, not at the first solve
+    if (l + u > 31 || bandlu_solve_smem(l, u) > 227 * 1024) {
+        cb_set_error("cb_bandlu_create: l + u = %d outside the supported range 0..30", l + u);
+        return CB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
     cb_bandlu_s *F = new cb_bandlu_s();
     F->n = n; F->l = l; F->u = u; F->ld = 2 * l + u + 1; F->d_ab = nullptr; F->d_ipiv = nullptr; F->info = 0;
     cudaGetDevice(&F->device);
@@ -315,9 +327,10 @@ int cb_bandlu_create(const double *band, i64 n, int l, int u, cb_bandlu **out) {
     if (e == cudaSuccess) {
         const size_t smem = sizeof(double) * (size_t)(LU_NB + l + u) * F->ld;
         step(cudaFuncSetAttribute(bandlu_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (e == cudaSuccess) bandlu_factor_kernel<<<1, 32, smem>>>(band, n, l, u, F->d_ab, F->d_ipiv, d_info);
+        if (e == cudaSuccess) bandlu_factor_kernel<<<1, 32, smem, st>>>(band, n, l, u, F->d_ab, F->d_ipiv, d_info);
         step(cudaGetLastError());
-        step(cudaMemcpy(&F->info, d_info, sizeof(int), cudaMemcpyDeviceToHost));
+        step(cudaMemcpyAsync(&F->info, d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
     }
     cudaFree(d_info);
     if (e != cudaSuccess) { cb_set_error("cb_bandlu_create: %s", cudaGetErrorString(e)); cb_bandlu_destroy(F); return CB_ERR_CUDA; }
@@ -336,9 +349,7 @@ int cb_bandlu_solve(const cb_bandlu *F, double *X, i64 ldx, i64 nvec, void *stre
     CB_REQUIRE(nvec >= 0 && ldx >= F->n, "DimensionMismatch: cb_bandlu_solve: leading dimension %lld smaller than the matrix order %lld",
                (long long)ldx, (long long)F->n);
     if (nvec == 0) return CB_OK;
-    const int kv = F->l + F->u, reach = kv > F->l ? kv : F->l;
-    const int fw = kv + 1 > F->l ? kv + 1 : F->l;
-    const size_t smem = sizeof(double) * (size_t)LU_WARPS * ((size_t)(LU_R + reach) * 33 + (size_t)LU_R * fw + LU_R / 2);
+    const size_t smem = bandlu_solve_smem(F->l, F->u);
     const i64 ngroups = (nvec + 31) / 32;
     i64 grid = (ngroups + LU_WARPS - 1) / LU_WARPS;
     if (grid > (i64)CB_NUM_SMS * 4) grid = (i64)CB_NUM_SMS * 4;

@@ -981,7 +981,7 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
 
 // Spike tables of the partitioned substitution (after the Cholesky factor is known).
 template <int K>
-static int launch_spikes(cb_density_s *D) {
+static int launch_spikes(cb_density_s *D, cudaStream_t st) {
     const i64 n = D->ncols;
     D->nchunk = n / DS_CH;
     if (D->nchunk < 2 || D->nchunk > 65535 || K == 1) { D->nchunk = 0; return CB_OK; }
@@ -990,13 +990,13 @@ static int launch_spikes(cb_density_s *D) {
     CB_CUDA(cudaMalloc(&D->d_sb, sizeof(double) * n * S));
     CB_CUDA(cudaMalloc(&D->d_tf, sizeof(double) * D->nchunk * S * S));
     CB_CUDA(cudaMalloc(&D->d_tb, sizeof(double) * D->nchunk * S * S));
-    density_spike_kernel<K><<<(unsigned)D->nchunk, 32>>>(D->d_fw, D->d_bw, n, D->nchunk, D->d_cfb, D->d_sb, D->d_tf, D->d_tb);
+    density_spike_kernel<K><<<(unsigned)D->nchunk, 32, 0, st>>>(D->d_fw, D->d_bw, n, D->nchunk, D->d_cfb, D->d_sb, D->d_tf, D->d_tb);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }
 
-static int launch_cholesky(int k, const double *g, i64 n, double *fw, double *bw, int *status, int indef = 0) {
-    CB_DISPATCH_KD(k, (density_cholesky_kernel<K><<<1, 32>>>(g, n, fw, bw, status, indef)));
+static int launch_cholesky(int k, const double *g, i64 n, double *fw, double *bw, int *status, cudaStream_t st, int indef = 0) {
+    CB_DISPATCH_KD(k, (density_cholesky_kernel<K><<<1, 32, 0, st>>>(g, n, fw, bw, status, indef)));
     return CB_OK;
 }
 
@@ -1011,7 +1011,9 @@ int cb_density_destroy(cb_density *D) {
     return CB_OK;
 }
 
-int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const double *wvals_host, cb_density **out) {
+int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const double *wvals_host, cb_density **out,
+                              void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
     CB_REQUIRE(out != nullptr, "cb_density_bspline_create: out is NULL");
     *out = nullptr;
     CB_REQUIRE(B != nullptr, "cb_density_bspline_create: NULL basis");
@@ -1029,28 +1031,30 @@ int cb_density_bspline_create(const cb_bspline *B, i64 col0, i64 ncols, const do
     step(cudaMalloc(&D->d_table, sizeof(double) * (nn * B->k ? nn * B->k : 1)));
     step(cudaMalloc(&D->d_ord, sizeof(int32_t) * B->nt));
     step(cudaMalloc(&D->d_ivlist, sizeof(i64) * (B->ni ? B->ni : 1)));
-    if (e == cudaSuccess && B->ni) step(cudaMemcpy(D->d_ivlist, B->d_ivlist, sizeof(i64) * B->ni, cudaMemcpyDeviceToDevice));
+    if (e == cudaSuccess && B->ni) step(cudaMemcpyAsync(D->d_ivlist, B->d_ivlist, sizeof(i64) * B->ni, cudaMemcpyDeviceToDevice, st));
     step(cudaMalloc(&D->d_fw, sizeof(double) * ncols * B->k));
     step(cudaMalloc(&D->d_bw, sizeof(double) * ncols * B->k));
     step(cudaMalloc(&d_g, sizeof(double) * ncols * (2 * B->k - 1)));
     step(cudaMalloc(&d_status, sizeof(int)));
-    if (e == cudaSuccess) step(cudaMemset(d_status, 0, sizeof(int)));
-    if (e == cudaSuccess) step(cudaMemcpy(D->d_ord, B->d_ord, sizeof(int32_t) * B->nt, cudaMemcpyDeviceToDevice));
+    if (e == cudaSuccess) step(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    if (e == cudaSuccess) step(cudaMemcpyAsync(D->d_ord, B->d_ord, sizeof(int32_t) * B->nt, cudaMemcpyDeviceToDevice, st));
     if (e == cudaSuccess && wvals_host) {
         step(cudaMalloc(&D->d_wv, sizeof(double) * (nn ? nn : 1)));
-        if (e == cudaSuccess) step(cudaMemcpy(D->d_wv, wvals_host, sizeof(double) * nn, cudaMemcpyHostToDevice));
+        if (e == cudaSuccess) step(cudaMemcpyAsync(D->d_wv, wvals_host, sizeof(double) * nn, cudaMemcpyHostToDevice, st));
+        if (e == cudaSuccess) step(cudaStreamSynchronize(st));          // wvals_host may be pageable / freed by the caller
     }
-    if (e == cudaSuccess) rc = cb_bspline_quad_table(B, 0, D->d_table, nullptr);
-    if (e == cudaSuccess && rc == CB_OK) rc = cb_bspline_gram_internal(B, col0, ncols, d_g, nullptr);
+    if (e == cudaSuccess) rc = cb_bspline_quad_table(B, 0, D->d_table, stream);
+    if (e == cudaSuccess && rc == CB_OK) rc = cb_bspline_gram_internal(B, col0, ncols, d_g, stream);
     if (e == cudaSuccess && rc == CB_OK) {
-        rc = launch_cholesky(B->k, d_g, ncols, D->d_fw, D->d_bw, d_status);
+        rc = launch_cholesky(B->k, d_g, ncols, D->d_fw, D->d_bw, d_status, st);
         step(cudaGetLastError());
-        step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+        step(cudaMemcpyAsync(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
     }
     if (e == cudaSuccess && rc == CB_OK && D->chol_status == 0) {
         const int kk = B->k;
-        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D)); return CB_OK; }();
-        step(cudaDeviceSynchronize());
+        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D, st)); return CB_OK; }();
+        step(cudaStreamSynchronize(st));
     }
     cudaFree(d_g); cudaFree(d_status);
     if (e != cudaSuccess) { cb_set_error("cb_density_bspline_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }
@@ -1124,14 +1128,14 @@ int cb_density_project(const cb_density *D, const double *fvals, i64 ldf, i64 P,
 
 // ---- SPD banded factor / batched solve: the metric inverse of LinearOperator (src/linear_operators.jl:38-48,
 // factorize(B'B) + ldiv!) ------------------------------------------------------------------------------------
-static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out);
+static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out, cudaStream_t st);
 
-int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out) { return bandchol_create(band, n, l, 0, out); }
-int cb_bandldl_create(const double *band, i64 n, int l, cb_bandchol **out) { return bandchol_create(band, n, l, 1, out); }
+int cb_bandchol_create(const double *band, i64 n, int l, cb_bandchol **out, void *stream) { return bandchol_create(band, n, l, 0, out, (cudaStream_t)stream); }
+int cb_bandldl_create(const double *band, i64 n, int l, cb_bandchol **out, void *stream) { return bandchol_create(band, n, l, 1, out, (cudaStream_t)stream); }
 
 }  // extern "C"
 
-static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out) {
+static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandchol **out, cudaStream_t st) {
     CB_REQUIRE(out != nullptr, "cb_bandchol_create: out is NULL");
     *out = nullptr;
     CB_REQUIRE(band != nullptr && n >= 1 && l >= 0, "cb_bandchol_create: bad argument");
@@ -1147,17 +1151,18 @@ static int bandchol_create(const double *band, i64 n, int l, int indef, cb_bandc
     step(cudaMalloc(&D->d_fw, sizeof(double) * n * D->k));
     step(cudaMalloc(&D->d_bw, sizeof(double) * n * D->k));
     step(cudaMalloc(&d_status, sizeof(int)));
-    if (e == cudaSuccess) step(cudaMemset(d_status, 0, sizeof(int)));
+    if (e == cudaSuccess) step(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     int rc = CB_OK;
     if (e == cudaSuccess) {
-        rc = launch_cholesky(D->k, band, n, D->d_fw, D->d_bw, d_status, indef);
+        rc = launch_cholesky(D->k, band, n, D->d_fw, D->d_bw, d_status, st, indef);
         step(cudaGetLastError());
-        step(cudaMemcpy(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost));
+        step(cudaMemcpyAsync(&D->chol_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
     }
     if (e == cudaSuccess && rc == CB_OK && D->chol_status == 0) {
         const int kk = D->k;
-        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D)); return CB_OK; }();
-        step(cudaDeviceSynchronize());
+        rc = [&]() -> int { CB_DISPATCH_KD(kk, return launch_spikes<K>(D, st)); return CB_OK; }();
+        step(cudaStreamSynchronize(st));
     }
     cudaFree(d_status);
     if (e != cudaSuccess) { cb_set_error("cb_bandchol_create: %s", cudaGetErrorString(e)); cb_density_destroy(D); return CB_ERR_CUDA; }

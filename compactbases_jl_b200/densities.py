@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import DimensionMismatch
 from .bsplines import _BSplineOrRestricted, diffop
 from .lazy import QuasiDiagonal
-from .operators import ColMajor, _ptr, _stream, axpby, to_device
+from .operators import ColMajor, _overlaps, _ptr, _stream, axpby, to_device
 
 
 class FunctionProduct:
@@ -44,7 +44,7 @@ class FunctionProduct:
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.call("cb_density_bspline_create", P.handle, R.col0, R.ncols,
-                          None if wv is None else C.c_void_p(wv.ctypes.data), C.byref(h))
+                          None if wv is None else C.c_void_p(wv.ctypes.data), C.byref(h), _stream())
             self.handle = h
             self.n = R.ncols
         else:
@@ -99,8 +99,11 @@ class FunctionProduct:
         """``copyto!(M, rho)`` (src/densities.jl:202-208): the operator of multiplication by the
         density, ``overlap_matrix!(M, L', R, Diagonal(rho.tmp))`` for B-splines."""
         if not self.handle:
+            # copyto!(M::Diagonal, rho) = mul!(M.diag, rho.C, rho.rho) (:202-204): the nodal values of the product,
+            # i.e. C .* rho.rho once more (C = Diagonal(B.n) for FE-DVR, 1/sqrt(h) on non-uniform grids, I otherwise)
             from .operators import Diagonal
-            return Diagonal(self.rho.data[0, :self.n].contiguous())
+            d = self.rho.data[0, :self.n]
+            return Diagonal((self.c * d if self.c is not None else d).contiguous())
         f, g = self._last
         P = self.R.parent_basis
         nn = P.ni * P.q
@@ -148,7 +151,7 @@ class DiagonalOperator:
         Yc = Y if isinstance(Y, ColMajor) else ColMajor(Y)
         if Xc.n != self.n or Yc.n != self.n or Xc.nvec != Yc.nvec:
             raise DimensionMismatch(f"DimensionMismatch: operator of order {self.n}, X {Xc.n}x{Xc.nvec}, Y {Yc.n}x{Yc.nvec}")
-        if alpha == 1.0 and beta == 0.0:
+        if alpha == 1.0 and beta == 0.0 and not _overlaps(Yc.data, Xc.data):
             self.rho.copyto(self.diag, Xc, out=Yc)                   # the density lands in y directly
         else:
             rho = self.rho.copyto(self.diag, Xc)

@@ -45,6 +45,23 @@ class _FEDVROrRestricted:
     def block_structure(self):
         return self.parent_basis._block_structure(self.first, self.last)
 
+    def block_bandwidths(self, rows=None):
+        """``block_bandwidths(B, rows)`` (src/fedvr.jl:159-176): per-block-column (l, u) of the skyline."""
+        P = self.parent_basis
+        rows = self.block_structure() if rows is None else rows
+        nrows = len(rows)
+        if nrows <= 1:
+            return [0], [0]
+        o, _, _ = P.block_orders(self.first, self.last)
+        bws = [[2, 1] if oo > 2 else [1] for oo in o]
+        l = [1] + [v for bw in bws[1:] for v in bw]
+        u = [v for bw in bws[:-1] for v in reversed(bw)] + [1]
+        if len(l) < nrows:
+            l = l + [0]
+        if len(u) < nrows:
+            u = [0] + u
+        return l[:nrows], u[:nrows]
+
     def ldiv(self, f):
         r"""``B \ f`` (src/fedvr.jl:369-412): quadrature projection, ``v_j = n_j * (sum of the element weights at node
         j) * f(x_j) = f(x_j) / n_j``.  Host glue (pointwise); returns the size() x 1 coefficients on the device."""

@@ -82,6 +82,20 @@ def _as_colmajor(X) -> ColMajor:
     return X if isinstance(X, ColMajor) else ColMajor(X)
 
 
+def _overlaps(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """True if the storage ranges of two device tensors intersect (an output aliasing an input: the apply and density
+    kernels read X while they write Y, whereas the reference goes through ``M.temp`` / ``rho.rho`` and tolerates
+    ``y === x``)."""
+    if a.numel() == 0 or b.numel() == 0 or a.device != b.device:
+        return False
+    def span(t):
+        lo = t.data_ptr()
+        ext = sum((sz - 1) * st for sz, st in zip(t.shape, t.stride())) + 1
+        return lo, lo + ext * t.element_size()
+    (a0, a1), (b0, b1) = span(a), span(b)
+    return a0 < b1 and b0 < a1
+
+
 class BandedMatrix:
     """BandedMatrices.jl storage: ``data[u + i - j, j]`` (0-based), data is (l+u+1) x n
     column-major == torch shape (n, l+u+1)."""
@@ -112,6 +126,15 @@ class BandedMatrix:
     def _mul(self, Y, X, alpha, beta):
         _lib.call("cb_banded_apply", _ptr(self.data), self.m, self.n, self.l, self.u, _ptr(X.data), X.ld, X.nvec,
                   alpha, beta, _ptr(Y.data), Y.ld, _stream())
+
+    def mul_host(self, Yh: np.ndarray, Xh: np.ndarray, alpha=1.0, beta=0.0):
+        """Host-buffer entry (cb_banded_apply_host): Xh (n, nvec), Yh (m, nvec) Fortran-ordered numpy arrays; the
+        operator arrays may still be in flight on the current stream (the entry orders itself after it)."""
+        assert Xh.flags.f_contiguous and Yh.flags.f_contiguous
+        _lib.call("cb_banded_apply_host", _ptr(self.data), self.m, self.n, self.l, self.u, C.c_void_p(Xh.ctypes.data),
+                  Xh.shape[0], Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta, C.c_void_p(Yh.ctypes.data), Yh.shape[0],
+                  _stream())
+        return Yh
 
     def cholesky(self) -> "BandCholesky":
         """``factorize(S)`` / ``cholesky(S)`` of a symmetric positive definite band (the metric B'B)."""
@@ -161,7 +184,7 @@ class BandCholesky:
             raise DimensionMismatch("DimensionMismatch: cholesky needs a square band with equal bandwidths")
         h = C.c_void_p()
         with torch.cuda.device(A.data.device):
-            _lib.call("cb_bandldl_create" if indefinite else "cb_bandchol_create", _ptr(A.data), A.n, A.l, C.byref(h))
+            _lib.call("cb_bandldl_create" if indefinite else "cb_bandchol_create", _ptr(A.data), A.n, A.l, C.byref(h), _stream())
         self.handle, self.n, self.device, self.indefinite = h, A.n, A.data.device, bool(indefinite)
 
     def __del__(self):
@@ -260,6 +283,10 @@ class ShiftAndInvert:
         if self.B is None:
             if Yc.data.data_ptr() != Xc.data.data_ptr():
                 Yc.data[:, :self.n].copy_(Xc.data[:, :self.n])
+        elif _overlaps(Yc.data, Xc.data):                            # mul!(x, M, x): the reference's M.temp
+            tmp = ColMajor(torch.empty((Xc.nvec, self.n), dtype=torch.float64, device=Xc.data.device))
+            mul(tmp, self.B, Xc)
+            Yc.data[:, :self.n].copy_(tmp.data)
         else:
             mul(Yc, self.B, Xc)
         self.Ainv.ldiv(Yc)
@@ -281,7 +308,7 @@ class BandLU:
             raise DimensionMismatch("DimensionMismatch: lu needs a square band")
         h = C.c_void_p()
         with torch.cuda.device(A.data.device):
-            _lib.call("cb_bandlu_create", _ptr(A.data), A.n, A.l, A.u, C.byref(h))
+            _lib.call("cb_bandlu_create", _ptr(A.data), A.n, A.l, A.u, C.byref(h), _stream())
         self.handle, self.n, self.device = h, A.n, A.data.device
 
     def __del__(self):
@@ -434,7 +461,7 @@ class Tridiagonal:
         assert Xh.flags.f_contiguous and Yh.flags.f_contiguous
         _lib.call("cb_tridiag_apply_host", _ptr(self.dl), _ptr(self.d), _ptr(self.du), self.n,
                   C.c_void_p(Xh.ctypes.data), Xh.shape[0], Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta,
-                  C.c_void_p(Yh.ctypes.data), Yh.shape[0])
+                  C.c_void_p(Yh.ctypes.data), Yh.shape[0], _stream())
         return Yh
 
 
@@ -514,6 +541,60 @@ class Diagonal:
                   _ptr(Y.data), Y.ld, _stream())
 
 
+class BlockSkylineMatrix:
+    """BlockBandedMatrices' ``BlockSkylineMatrix(undef, rows, cols, (l, u))`` (the destination of
+    ``Matrix(undef, B)`` for FE-DVR, src/fedvr_operators.jl:24-28): one flat ``data`` vector; block column J keeps
+    the block rows ``max(1, J-u[J]) : min(J+l[J], N)`` stacked into one dense column-major panel.  ``block_starts``
+    / ``block_strides`` follow BlockBandedMatrices' ``BlockSkylineSizes`` (0-based offsets here).  Host integer
+    logic only; the data lives on the device."""
+
+    def __init__(self, rows, l, u, dev=None):
+        self.rows = [int(r) for r in rows]
+        self.l, self.u = [int(v) for v in l], [int(v) for v in u]
+        nb = len(self.rows)
+        if len(self.l) != nb or len(self.u) != nb:
+            raise DimensionMismatch("DimensionMismatch: one (l, u) pair per block column")
+        self.cum = np.concatenate([[0], np.cumsum(self.rows)]).astype(np.int64)
+        self.n = int(self.cum[-1])
+        self.kfirst = np.array([max(0, J - self.u[J]) for J in range(nb)], dtype=np.int64)
+        self.klast = np.array([min(nb - 1, J + self.l[J]) for J in range(nb)], dtype=np.int64)
+        self.stride = (self.cum[self.klast + 1] - self.cum[self.kfirst]).astype(np.int64)     # bb_blockstrides
+        sizes = self.stride * np.asarray(self.rows, dtype=np.int64)
+        self.start = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)            # bb_blockstarts (first K)
+        self.ndata = int(np.sum(sizes))
+        self.data = torch.empty(self.ndata, dtype=torch.float64, device="cpu" if dev == "cpu" else device_of(dev))
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def block_start(self, K, J):
+        """0-based offset in ``data`` of block (K, J) (0-based block indices) or None outside the skyline."""
+        if K < self.kfirst[J] or K > self.klast[J]:
+            return None
+        return int(self.start[J] + self.cum[K] - self.cum[self.kfirst[J]])
+
+    def block(self, K, J) -> np.ndarray:
+        """``A[Block(K+1, J+1)]`` as a dense numpy array (zeros outside the skyline)."""
+        r, c = self.rows[K], self.rows[J]
+        st = self.block_start(K, J)
+        if st is None:
+            return np.zeros((r, c))
+        d = self.data.cpu().numpy()
+        sd = int(self.stride[J])
+        return np.array([[d[st + i + j * sd] for j in range(c)] for i in range(r)])
+
+    def dense(self) -> np.ndarray:
+        A = np.zeros((self.n, self.n))
+        d = self.data.cpu().numpy()
+        for J in range(len(self.rows)):
+            r0, r1 = int(self.cum[self.kfirst[J]]), int(self.cum[self.klast[J] + 1])
+            sd = int(self.stride[J])
+            for j in range(self.rows[J]):
+                A[r0:r1, int(self.cum[J]) + j] = d[int(self.start[J]) + j * sd:int(self.start[J]) + j * sd + (r1 - r0)]
+        return A
+
+
 class FEDVRMatrix:
     """The operator that ``Matrix(undef, B)`` + ``set_elements!`` build for an FE-DVR basis
     (src/fedvr_operators.jl:17-30,148-154), kept as one dense o x o block per element;
@@ -538,6 +619,32 @@ class FEDVRMatrix:
                   self.first, self.last, _ptr(A), _stream())
         return A.cpu().numpy().T.copy()
 
+    def skyline(self):
+        """The operator as the reference's own destination: ``BlockSkylineMatrix`` of ``Matrix(undef, B)``
+        (src/fedvr_operators.jl:17-30) filled by ``set_elements!`` (:148-154), or ``Tridiagonal`` when every element
+        has order 2."""
+        b = self.basis
+        R = b if (self.first, self.last) == (1, b.N) else b.restrict(self.first, self.last)
+        dev = self.blocks.device
+        if np.all(b.order == 2):
+            n = self.n
+            dl = torch.zeros(max(n - 1, 0), dtype=torch.float64, device=dev)
+            du = torch.zeros(max(n - 1, 0), dtype=torch.float64, device=dev)
+            d = torch.empty(n, dtype=torch.float64, device=dev)
+            _lib.call("cb_fedvr_to_tridiag", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                      self.first, self.last, _ptr(dl), _ptr(d), _ptr(du), _stream())
+            return Tridiagonal(dl, d, du)
+        rows = R.block_structure()
+        l, u = R.block_bandwidths(rows)
+        A = BlockSkylineMatrix(rows, l, u, dev)
+        assert A.n == self.n
+        tod = lambda a: to_device(a, dev, torch.int64)
+        cum, kf, kl, st, sd = (tod(a) for a in (A.cum, A.kfirst, A.klast, A.start, A.stride))
+        _lib.call("cb_fedvr_to_skyline", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                  self.first, self.last, _ptr(cum), len(rows), _ptr(kf), _ptr(kl), _ptr(st), _ptr(sd), _ptr(A.data),
+                  A.ndata, _stream())
+        return A
+
     def _mul(self, Y, X, alpha, beta):
         b = self.basis
         _lib.call("cb_fedvr_apply", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
@@ -550,7 +657,7 @@ class FEDVRMatrix:
         b = self.basis
         _lib.call("cb_fedvr_apply_host", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
                   b.uniform_order, self.first, self.last, C.c_void_p(Xh.ctypes.data), Xh.shape[0],
-                  Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta, C.c_void_p(Yh.ctypes.data), Yh.shape[0])
+                  Xh.shape[1] if Xh.ndim > 1 else 1, alpha, beta, C.c_void_p(Yh.ctypes.data), Yh.shape[0], _stream())
         return Yh
 
 

@@ -174,6 +174,29 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
 int cb_fedvr_to_dense(const double *blocks, const cb_i64 *estart, const int32_t *order,
                       const cb_i64 *boff, cb_i64 nel, cb_i64 first, cb_i64 last,
                       double *A, void *stream);
+/* The same operator in the reference's own destination types (the body of derop!(A, B, n) =
+ * set_elements!(difffun(B, n), A, B), src/fedvr_derivatives.jl:62-63, src/fedvr_operators.jl:40-154):
+ *
+ * BlockSkylineMatrix (BlockBandedMatrices 0.10), what Matrix(undef, B) allocates (src/fedvr_operators.jl:24-28) from
+ * rows = block_structure(B), (l, u) = block_bandwidths(B, rows) (src/fedvr.jl:121-176).  Its storage is one flat
+ * `data` vector; block column J keeps the block rows max(1, J-u[J]) : min(J+l[J], N) stacked into one dense
+ * column-major panel of block_strides[J] rows whose first entry is data[block_starts[first K, J]].  Passed 0-based:
+ *   blk_cum[b]     cumulative block sizes, b = 0..nblk (block b holds functions blk_cum[b]..blk_cum[b+1]-1)
+ *   col_kfirst[J]  first / last stored block row of block column J
+ *   col_klast[J]
+ *   col_start[J]   index in data of the first entry of the panel of block column J
+ *   col_stride[J]  rows of that panel
+ * (device arrays of nblk (+1) entries; INTEGRATION.md derives them from A.block_sizes).  data (ndata doubles,
+ * device) is zeroed (A .= false, :149) and filled; shared bridge entries are the sums of two corners (:108-130).
+ * The call synchronises `stream`; a block structure that cannot hold the element blocks -> CB_ERR_ARG. */
+int cb_fedvr_to_skyline(const double *blocks, const cb_i64 *estart, const int32_t *order, const cb_i64 *boff,
+                        cb_i64 nel, cb_i64 first, cb_i64 last,
+                        const cb_i64 *blk_cum, cb_i64 nblk, const cb_i64 *col_kfirst, const cb_i64 *col_klast,
+                        const cb_i64 *col_start, const cb_i64 *col_stride,
+                        double *data, cb_i64 ndata, void *stream);
+/* Tridiagonal(dl, d, du): the destination when every element has order 2 (src/fedvr_operators.jl:18-23,136-146). */
+int cb_fedvr_to_tridiag(const double *blocks, const cb_i64 *estart, const int32_t *order, const cb_i64 *boff,
+                        cb_i64 nel, cb_i64 first, cb_i64 last, double *dl, double *d, double *du, void *stream);
 /* Y = alpha*A*X + beta*Y for the (restricted) FE-DVR operator: mul! on the
  * BlockSkylineMatrix / Tridiagonal of src/fedvr_operators.jl:17-30.
  * X, Y have last-first+1 rows.  uniform_order > 0 asserts that every element
@@ -183,13 +206,18 @@ int cb_fedvr_apply(const double *blocks, const cb_i64 *estart, const int32_t *or
                    cb_i64 first, cb_i64 last,
                    const double *X, cb_i64 ldx, cb_i64 nvec,
                    double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
-/* Host-buffer form: X_host/Y_host in (preferably pinned) host memory; the
- * vector batch is streamed through the device in tiles. */
+/* Host-buffer forms (`*_apply_host`): X_host/Y_host in host memory (pinned for PCIe speed, see
+ * cb_host_register; pageable arrays work, staged by the driver); the vector batch is streamed through the
+ * device in tiles on the library's own copy streams (H2D, kernel, D2H of consecutive tiles overlap).
+ * `stream` is the PRODUCER stream: the one on which the caller enqueued the work that fills the operator
+ * arrays (cb_fedvr_assemble, cb_fd_derivative, ...); the copy streams wait for everything enqueued on it so
+ * far.  The call returns when Y_host is complete.  Calls on one device are serialised by the library (the
+ * staging ring is shared), so the entries are thread-safe but not concurrent. */
 int cb_fedvr_apply_host(const double *blocks_dev, const cb_i64 *estart_dev,
                         const int32_t *order_dev, const cb_i64 *boff_dev,
                         cb_i64 nel, int uniform_order, cb_i64 first, cb_i64 last,
                         const double *X_host, cb_i64 ldx, cb_i64 nvec,
-                        double alpha, double beta, double *Y_host, cb_i64 ldy);
+                        double alpha, double beta, double *Y_host, cb_i64 ldy, void *stream);
 
 /* ------------------------------------------------------------------------
  * Finite differences (src/fd_derivatives.jl).
@@ -220,7 +248,14 @@ int cb_tridiag_apply(const double *dl, const double *d, const double *du, cb_i64
                      double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
 int cb_tridiag_apply_host(const double *dl_dev, const double *d_dev, const double *du_dev,
                           cb_i64 n, const double *X_host, cb_i64 ldx, cb_i64 nvec,
-                          double alpha, double beta, double *Y_host, cb_i64 ldy);
+                          double alpha, double beta, double *Y_host, cb_i64 ldy, void *stream);
+int cb_banded_apply_host(const double *band_dev, cb_i64 m, cb_i64 n, int l, int u,
+                         const double *X_host, cb_i64 ldx, cb_i64 nvec,
+                         double alpha, double beta, double *Y_host, cb_i64 ldy, void *stream);
+/* Page-locks / releases a caller-owned host array (cudaHostRegister): a Julia `Array` is pageable, and the
+ * `_host` entries reach PCIe speed only from pinned memory (CUDA.jl: `CUDA.pin(A)`). */
+int cb_host_register(void *ptr, size_t bytes);
+int cb_host_unregister(void *ptr);
 /* Diagonal (FE-DVR / FD scalar operators, src/fedvr_operators.jl:158-185,
  * src/fd_operators.jl:3-35). */
 int cb_diag_apply(const double *d, cb_i64 n, const double *X, cb_i64 ldx, cb_i64 nvec,
@@ -246,7 +281,7 @@ typedef struct cb_density_s cb_density;
  * the weight function at the quadrature nodes (host, numnodes).  Functions
  * col0+1..col0+ncols (restriction). */
 int cb_density_bspline_create(const cb_bspline *B, cb_i64 col0, cb_i64 ncols,
-                              const double *wvals_host, cb_density **out);
+                              const double *wvals_host, cb_density **out, void *stream);
 int cb_density_destroy(cb_density *D);
 /* Number of corrected-semi-normal-equation refinement steps per apply
  * (default 0: plain banded Cholesky solve of the normal equations, which
@@ -284,20 +319,22 @@ int cb_density_project(const cb_density *D, const double *fvals, cb_i64 ldf, cb_
  * the in-place batched solve X <- A^-1 X for n x nvec column-major batches (partitioned substitution: every
  * chunk of rows x 32 vectors is an independent warp).  Not positive definite -> CB_ERR_ARG (PosDefException). */
 typedef struct cb_bandchol_s cb_bandchol;
-int cb_bandchol_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
+/* `stream` (all *_create entries that read device arrays): the factorisation kernels run on it, so that a band
+ * produced by earlier work on that stream is complete before it is read; the call synchronises that stream. */
+int cb_bandchol_create(const double *band, cb_i64 n, int l, cb_bandchol **out, void *stream);
 /* Same handle and solve for a symmetric INDEFINITE band (the shifted operator A - sigma*B of ShiftAndInvert with an
  * interior shift): L D L' without pivoting, so that the partitioned batched solve applies.  A pivot breakdown ->
  * CB_ERR_ARG; callers should check a residual (no pivoting: no growth bound) and fall back to cb_bandlu_*. */
-int cb_bandldl_create(const double *band, cb_i64 n, int l, cb_bandchol **out);
+int cb_bandldl_create(const double *band, cb_i64 n, int l, cb_bandchol **out, void *stream);
 int cb_bandchol_solve(const cb_bandchol *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
 int cb_bandchol_destroy(cb_bandchol *F);
 
 /* factorize(A - sigma*B) of ShiftAndInvert for a general (indefinite) BandedMatrix, src/linear_operators.jl:203-236:
  * banded LU with partial pivoting (the LAPACK gbtrf / gbtrs that BandedMatrices' `factorize` / `ldiv!` call) and the
- * in-place batched solve X <- A^-1 X.  band: (l+u+1) x n column-major (device), l + u <= 31.  Exactly singular ->
+ * in-place batched solve X <- A^-1 X.  band: (l+u+1) x n column-major (device), l + u <= 30.  Exactly singular ->
  * CB_ERR_ARG (SingularException).  Positive definite operators should prefer cb_bandchol_* (partitioned solve). */
 typedef struct cb_bandlu_s cb_bandlu;
-int cb_bandlu_create(const double *band, cb_i64 n, int l, int u, cb_bandlu **out);
+int cb_bandlu_create(const double *band, cb_i64 n, int l, int u, cb_bandlu **out, void *stream);
 int cb_bandlu_solve(const cb_bandlu *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
 int cb_bandlu_destroy(cb_bandlu *F);
 

@@ -313,17 +313,24 @@ i64 cbo_lgwt(const double *t, i64 nt, const double *xi, const double *wr, int q,
 void cbo_basis_table(const double *t, i64 nt, int k, const double *x, int q,
                      int m, double *table)
 {
-    i64 nf = nt - k, c = 0;
-    for (i64 i = 1; i <= nt - 1; ++i) {
-        if (t[i - 1] == t[i]) continue;
+    extern int cbo_get_threads(void);
+    i64 nf = nt - k;
+    i64 ni = cbo_nonempty_intervals(t, nt, NULL);
+    i64 *iv = (i64 *)malloc(sizeof(i64) * (size_t)(ni ? ni : 1));
+    cbo_nonempty_intervals(t, nt, iv);
+    int nthreads = cbo_get_threads();
+    (void)nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (i64 c = 0; c < ni; ++c) {
+        i64 i = iv[c];
         for (int l = 0; l < q; ++l)
             for (int a = 0; a < k; ++a) {
                 i64 j = i - k + 1 + a;
                 table[(c * q + l) * k + a] = (j >= 1 && j <= nf)
                     ? cbo_deboor_unit(t, nt, k, nf, j, x[c * q + l], i, m) : 0.0;
             }
-        ++c;
     }
+    free(iv);
 }
 
 /* ------------------------------------------------------------------ */
@@ -338,6 +345,13 @@ void cbo_basis_table(const double *t, i64 nt, int k, const double *x, int q,
  * tL/tR are the expanded knot vectors of the two bases (same t.t, same nodes;
  * src/bsplines.jl:75-82).  band is (l+u+1) x n column-major,
  * band[(u+i-j) + (l+u+1)*j] (0-based i,j); slots outside the matrix are 0. */
+/* Number of threads the *_mt entry points and the table / assembly loops may use (1 = the single-threaded
+ * reference; bench.py raises it for the "OpenMP over all host cores" baseline).  Results do not depend on it:
+ * every output entry is computed by one thread with the reference's summation order. */
+static int g_threads = 1;
+void cbo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+int cbo_get_threads(void) { return g_threads; }
+
 void cbo_bspline_assemble(const double *tL, i64 ntL, int kL,
                           const double *tR, i64 ntR, int kR,
                           const double *x, const double *w, int q,
@@ -358,6 +372,11 @@ void cbo_bspline_assemble(const double *tL, i64 ntL, int kL,
     i64 *ivR = (i64 *)malloc(sizeof(i64) * (size_t)(niR ? niR : 1));
     cbo_nonempty_intervals(tL, ntL, ivL);
     cbo_nonempty_intervals(tR, ntR, ivR);
+    /* first ordinal c with ivL[c] >= I, for every expanded interval index I of L: the reference's sparse dot
+     * product (src/bsplines.jl:67-71) only meets the stored rows of column i, i.e. the intervals of function fi;
+     * visiting exactly those, in increasing order, gives the same sum at linear instead of quadratic cost */
+    i64 *firstL = (i64 *)malloc(sizeof(i64) * (size_t)(ntL + 2));
+    { i64 c = 0; for (i64 I = 0; I <= ntL + 1; ++I) { while (c < niL && ivL[c] < I) ++c; firstL[I] = c; } }
     double *TL = (double *)malloc(sizeof(double) * (size_t)(niL ? niL : 1) * q * kL);
     double *TR = (double *)malloc(sizeof(double) * (size_t)(niR ? niR : 1) * q * kR);
     cbo_basis_table(tL, ntL, kL, x, q, da, TL);
@@ -366,12 +385,69 @@ void cbo_bspline_assemble(const double *tL, i64 ntL, int kL,
     int p = l > u ? l : u;
     i64 mm = m < nfL - rowL0 ? m : nfL - rowL0;    /* min(size(S,1), size(chi,2)) */
     i64 nn = n < nfR - colR0 ? n : nfR - colR0;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
     for (i64 i = 0; i < mm; ++i) {
         i64 jlo = i - p < 0 ? 0 : i - p;
         i64 jhi = i + p > nn - 1 ? nn - 1 : i + p;
-        i64 fi = rowL0 + 1 + i;                    /* 1-based function of L */
+        i64 fi = rowL0 + 1 + i;                    /* 1-based function of L: lives on expanded intervals fi..fi+kL-1 */
+        i64 Ihi = fi + kL > ntL + 1 ? ntL + 1 : fi + kL;
+        i64 c0 = firstL[fi], c1 = firstL[Ihi];
+        if (c1 > ni) c1 = ni;
         for (i64 j = jlo; j <= jhi; ++j) {
             if (j - i > u || i - j > l) continue;  /* outside the band: zero */
+            i64 fj = colR0 + 1 + j;
+            double s = 0.0;
+            for (i64 c = c0; c < c1; ++c) {
+                i64 aL = fi - (ivL[c] - kL + 1), aR = fj - (ivR[c] - kR + 1);
+                if (aL < 0 || aL >= kL || aR < 0 || aR >= kR) continue;
+                for (int ll = 0; ll < q; ++ll) {
+                    double ch = sgn * TL[(c * q + ll) * kL + aL];
+                    double xv = TR[(c * q + ll) * kR + aR];
+                    if (op) xv = op[c * q + ll] * xv;
+                    s += (ch * w[c * q + ll]) * xv;
+                }
+            }
+            band[(u + i - j) + (i64)ld * j] = s;
+        }
+    }
+    free(ivL); free(ivR); free(firstL); free(TL); free(TR);
+}
+
+/* The literal loop of overlap_matrix! (src/bsplines.jl:58-73) on sparse tables costs, per band entry, a sparse
+ * column copy and a sparse dot over ALL stored rows; restated here as the scan over every non-empty interval
+ * (quadratic in the number of intervals).  Kept for the reduced-size "literal algorithm" baseline of bench.py
+ * and to pin the linear-cost form above (tests/test_oracle_golden.py). */
+void cbo_bspline_assemble_literal(const double *tL, i64 ntL, int kL,
+                                  const double *tR, i64 ntR, int kR,
+                                  const double *x, const double *w, int q,
+                                  int da, int db, const double *op,
+                                  i64 rowL0, i64 m, i64 colR0, i64 n,
+                                  int l, int u, double *band)
+{
+    i64 nfL = ntL - kL, nfR = ntR - kR;
+    int ld = l + u + 1;
+    memset(band, 0, sizeof(double) * (size_t)ld * (size_t)n);
+    i64 niL = cbo_nonempty_intervals(tL, ntL, NULL);
+    i64 niR = cbo_nonempty_intervals(tR, ntR, NULL);
+    i64 ni = niL < niR ? niL : niR;
+    i64 *ivL = (i64 *)malloc(sizeof(i64) * (size_t)(niL ? niL : 1));
+    i64 *ivR = (i64 *)malloc(sizeof(i64) * (size_t)(niR ? niR : 1));
+    cbo_nonempty_intervals(tL, ntL, ivL);
+    cbo_nonempty_intervals(tR, ntR, ivR);
+    double *TL = (double *)malloc(sizeof(double) * (size_t)(niL ? niL : 1) * q * kL);
+    double *TR = (double *)malloc(sizeof(double) * (size_t)(niR ? niR : 1) * q * kR);
+    cbo_basis_table(tL, ntL, kL, x, q, da, TL);
+    cbo_basis_table(tR, ntR, kR, x, q, db, TR);
+    double sgn = (da % 2 == 0) ? 1.0 : -1.0;
+    int p = l > u ? l : u;
+    i64 mm = m < nfL - rowL0 ? m : nfL - rowL0;
+    i64 nn = n < nfR - colR0 ? n : nfR - colR0;
+    for (i64 i = 0; i < mm; ++i) {
+        i64 jlo = i - p < 0 ? 0 : i - p;
+        i64 jhi = i + p > nn - 1 ? nn - 1 : i + p;
+        i64 fi = rowL0 + 1 + i;
+        for (i64 j = jlo; j <= jhi; ++j) {
+            if (j - i > u || i - j > l) continue;
             i64 fj = colR0 + 1 + j;
             double s = 0.0;
             for (i64 c = 0; c < ni; ++c) {
@@ -541,6 +617,99 @@ void cbo_fedvr_apply(const double *blocks, const i64 *boff, const i64 *estart,
         for (i64 i = 0; i < n; ++i) axpby_store(&yv[i], tmp[i], alpha, beta);
     }
     free(tmp);
+}
+
+/* ------------------------------------------------------------------ */
+/* a18 at scale: pinv(V) * b by a banded QR                             */
+/* ------------------------------------------------------------------ */
+
+/* The reference forms C = pinv(Matrix(RV)) * w as a DENSE nf x nquad matrix (src/densities.jl:96) and applies
+ * it with a dense product (:163).  V = B[locs, sel] has full column rank, so pinv(V) b is the least-squares
+ * solution of V c = b, which this routine computes at linear cost by a row-sequential Givens QR of V (each node
+ * row holds the k live functions of its interval, so R stays upper banded with k diagonals) — the algorithm
+ * class of Julia's sparse `\` (SPQR), not the normal equations the CUDA path uses: an independent check.
+ *   table[(c*q + l)*k + a]: basis_functions table (cbo_basis_table, m = 0)
+ *   iv[c]: 1-based expanded index of the c-th non-empty interval
+ *   columns col0+1 .. col0+ncols of the basis (restriction)
+ *   B: nquad x P column-major right-hand sides (ldb), overwritten;  out: ncols x P (ldo). */
+void cbo_banded_lstsq(const double *table, const i64 *iv, i64 ni, int q, int k,
+                      i64 col0, i64 ncols, const double *Bm, i64 ldb, i64 P, double *out, i64 ldo)
+{
+    double *R = (double *)calloc((size_t)ncols * k, sizeof(double));      /* R[j*k + d] = R(j, j+d) */
+    double *y = (double *)calloc((size_t)ncols * P, sizeof(double));      /* (Q'b)[j], row-major [j][p] */
+    double *row = (double *)malloc(sizeof(double) * (size_t)(k + 1));
+    double *br = (double *)malloc(sizeof(double) * (size_t)(P ? P : 1));
+    for (i64 c = 0; c < ni; ++c) {
+        for (int l = 0; l < q; ++l) {
+            const i64 e = c * q + l;
+            /* the row's k entries at absolute (restricted, 0-based) columns j0 .. j0+k-1 */
+            const i64 j0 = iv[c] - k + 1 - 1 - col0;
+            for (int a = 0; a < k; ++a) {
+                const i64 j = j0 + a;
+                row[a] = (j >= 0 && j < ncols) ? table[e * k + a] : 0.0;
+            }
+            for (i64 p = 0; p < P; ++p) br[p] = Bm[e + ldb * p];
+            for (int a = 0; a < k; ++a) {
+                const i64 j = j0 + a;
+                if (j < 0 || j >= ncols || row[a] == 0.0) continue;
+                double *Rj = R + j * k;
+                const double r0 = Rj[0], v = row[a];
+                const double h = hypot(r0, v);
+                const double cs = r0 / h, sn = v / h;
+                /* rotate (R row j, working row) over columns j .. j+k-1; the working row's entries live at a.. */
+                Rj[0] = h;
+                for (int d = 1; d < k; ++d) {
+                    const int aa = a + d;
+                    const double rv = Rj[d], wv = aa < k ? row[aa] : 0.0;
+                    Rj[d] = cs * rv + sn * wv;
+                    if (aa < k) row[aa] = -sn * rv + cs * wv;
+                }
+                double *yj = y + j * P;
+                for (i64 p = 0; p < P; ++p) {
+                    const double yv = yj[p], bv = br[p];
+                    yj[p] = cs * yv + sn * bv;
+                    br[p] = -sn * yv + cs * bv;
+                }
+                row[a] = 0.0;
+            }
+        }
+    }
+    /* back substitution R c = Q'b */
+    for (i64 j = ncols - 1; j >= 0; --j) {
+        const double *Rj = R + j * k;
+        for (i64 p = 0; p < P; ++p) {
+            double sacc = y[j * P + p];
+            for (int d = 1; d < k && j + d < ncols; ++d) sacc -= Rj[d] * out[(j + d) + ldo * p];
+            out[j + ldo * p] = sacc / Rj[0];
+        }
+    }
+    free(R); free(y); free(row); free(br);
+}
+
+/* b = w .* conj(V f) .* (V g) at the nodes (src/densities.jl:158-162), V restricted to columns col0+1..col0+ncols;
+ * f: ncols x Pf, g: ncols x Pg with Pf == Pg or one of them 1 (:57-72).  Bm: nquad x max(Pf,Pg). */
+void cbo_density_nodal(const double *table, const i64 *iv, i64 ni, int q, int k, i64 col0, i64 ncols,
+                       const double *wvals, const double *f, i64 ldf, i64 Pf, const double *g, i64 ldg, i64 Pg,
+                       double *Bm, i64 ldb)
+{
+    const i64 P = Pf > Pg ? Pf : Pg;
+    for (i64 p = 0; p < P; ++p) {
+        const double *fc = f + ldf * (Pf == 1 ? 0 : p), *gc = g + ldg * (Pg == 1 ? 0 : p);
+        for (i64 c = 0; c < ni; ++c)
+            for (int l = 0; l < q; ++l) {
+                const i64 e = c * q + l, j0 = iv[c] - k + 1 - 1 - col0;
+                double uf = 0.0, ug = 0.0;
+                for (int a = 0; a < k; ++a) {
+                    const i64 j = j0 + a;
+                    if (j < 0 || j >= ncols) continue;
+                    uf += table[e * k + a] * fc[j];
+                    ug += table[e * k + a] * gc[j];
+                }
+                double t = uf * ug;
+                if (wvals) t = wvals[e] * t;
+                Bm[e + ldb * p] = t;
+            }
+    }
 }
 
 /* Multi-threaded variants for the CPU baseline (split the vector batch). */

@@ -333,6 +333,27 @@ def bspline_assemble(tL, kL, tR, kR, x, w, q, a=0, b=0, op=None,
     return band, l, u
 
 
+def bspline_assemble_literal(tL, kL, tR, kR, x, w, q, a=0, b=0, op=None, rowL0=0, m=None, colR0=0, n=None):
+    """The quadratic-cost literal form (every band entry scans all intervals, like the reference's sparse column
+    dot products on its whole table); reduced sizes only."""
+    tL, tLp = _d(tL)
+    tR, tRp = _d(tR)
+    x, xp = _d(x)
+    w, wp = _d(w)
+    nfL, nfR = len(tL) - kL, len(tR) - kR
+    m = nfL - rowL0 if m is None else m
+    n = nfR - colR0 if n is None else n
+    l, u = band_shape(kL, kR, rowL0, colR0)
+    band = np.zeros((n, l + u + 1))
+    opp = None
+    if op is not None:
+        op, opp = _d(op)
+    lib().cbo_bspline_assemble_literal(tLp, i64(len(tL)), C.c_int(kL), tRp, i64(len(tR)), C.c_int(kR),
+                                       xp, wp, C.c_int(q), C.c_int(a), C.c_int(b), opp,
+                                       i64(rowL0), i64(m), i64(colR0), i64(n), C.c_int(l), C.c_int(u), _p(band))
+    return band, l, u
+
+
 def band_to_dense(band, m, n, l, u):
     """BandedMatrix data[(u+i-j), j] -> dense m x n."""
     A = np.zeros((m, n))
@@ -611,6 +632,55 @@ def density_bspline(V, f, g, wvals=None, conj=True):
     if gt.ndim == 1 and ft.ndim == 2:
         gt = gt[:, None]
     return Cm @ (ft * gt)
+
+
+def density_bspline_qr(t, k, x, q, f, g, wvals=None, col0=0, ncols=None):
+    """The same projection at linear cost (full BASELINE sizes): the nodal product w .* (V f) .* (V g) followed by
+    the least-squares solve V rho = b through a banded Givens QR (cbo_banded_lstsq) instead of the dense pinv of
+    src/densities.jl:96.  t: expanded knots; f, g: [ncols, P] (or [ncols]); returns [ncols, P]."""
+    tab = basis_table(t, k, x, q, 0)
+    return density_from_table(tab, nonempty_intervals(t), k, q, f, g, wvals, col0, len(t) - k - col0 if ncols is None else ncols)
+
+
+def density_from_table(tab, iv, k, q, f, g, wvals=None, col0=0, ncols=None):
+    f = np.asfortranarray(np.atleast_2d(np.asarray(f, dtype=np.float64).T).T)
+    g = np.asfortranarray(np.atleast_2d(np.asarray(g, dtype=np.float64).T).T)
+    ncols = f.shape[0] if ncols is None else ncols
+    iv = np.ascontiguousarray(iv, dtype=np.int64)
+    ni = len(iv)
+    Pf, Pg = f.shape[1], g.shape[1]
+    P = max(Pf, Pg)
+    nq = ni * q
+    Bm = np.zeros((nq, P), order="F")
+    wp = None
+    if wvals is not None:
+        wvals, wp = _d(wvals)
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    lib().cbo_density_nodal(_p(tab), _p(iv, ip), i64(ni), C.c_int(q), C.c_int(k), i64(col0), i64(ncols), wp,
+                            _p(f), i64(f.shape[0]), i64(Pf), _p(g), i64(g.shape[0]), i64(Pg), _p(Bm), i64(nq))
+    return banded_lstsq(tab, iv, k, q, Bm, col0, ncols)
+
+
+def banded_lstsq(tab, iv, k, q, Bm, col0, ncols):
+    """argmin_c |V c - b| for every column b of Bm, V the (restricted) Vandermonde matrix at the nodes given by its
+    [ni, q, k] table: ``B \\ f`` (src/bsplines.jl:329-343) and pinv(V) b (src/densities.jl:96) at linear cost."""
+    tab = np.ascontiguousarray(tab, dtype=np.float64)
+    iv = np.ascontiguousarray(iv, dtype=np.int64)
+    Bm = np.asfortranarray(np.atleast_2d(np.asarray(Bm, dtype=np.float64).T).T).copy(order="F")
+    nq, P = Bm.shape
+    out = np.zeros((ncols, P), order="F")
+    lib().cbo_banded_lstsq(_p(tab), _p(iv, ip), i64(len(iv)), C.c_int(q), C.c_int(k), i64(col0), i64(ncols),
+                           _p(Bm), i64(nq), i64(P), _p(out), i64(ncols))
+    return out
+
+
+def set_threads(n: int):
+    """Threads for the table / assembly / *_mt loops (1 = single-threaded like the reference)."""
+    lib().cbo_set_threads(C.c_int(int(n)))
+
+
+def max_threads() -> int:
+    return int(lib().cbo_max_threads())
 
 
 def density_orthogonal(f, g, c=None, conj=True):

@@ -209,3 +209,41 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                         capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_block_skyline_layout_host_logic():
+    """BlockSkylineMatrix index arithmetic (BlockBandedMatrices' bb_blockstarts / bb_blockstrides restated): every
+    non-zero of the oracle's dense FE-DVR operator lies inside the skyline of block_structure / block_bandwidths
+    (src/fedvr.jl:121-176), panels tile `data` without gaps, and dense() inverts the placement."""
+    import compactbases_jl_b200 as cb
+    from oracle import cbo
+    cases = [([4, 3, 4, 2, 5, 4, 2, 4, 8], None), ([2, 2, 3, 4, 2, 4], None), (4, (2, 12)), ([5, 4, 2, 2], (5, 9)), (10, (3, 40)),
+             ([3, 3], None), (6, (6, 6))]
+    for orders, sel in cases:
+        nel = len(orders) if not np.isscalar(orders) else 5
+        t = cbo.julia_range(0.0, 20.0, nel + 1)
+        O = cbo.FEDVROracle(t, orders)
+        F = cb.FEDVR(t, orders, device="host")
+        a, b = (1, O.N) if sel is None else sel
+        R = F if sel is None else F.restrict(a, b)
+        rows = R.block_structure()
+        assert rows == O.block_structure(a, b)
+        l, u = R.block_bandwidths(rows)
+        S = cb.BlockSkylineMatrix(rows, l, u, "cpu")
+        assert S.n == b - a + 1
+        # panels are contiguous and cover data exactly
+        ends = S.start + S.stride * np.asarray(rows)
+        assert S.start[0] == 0 and np.array_equal(S.start[1:], ends[:-1]) and ends[-1] == S.ndata
+        A = O.dense(O.blocks(2), a, b)
+        S.data.zero_()
+        d = S.data.numpy()
+        for J in range(len(rows)):
+            for K in range(len(rows)):
+                blkA = A[S.cum[K]:S.cum[K + 1], S.cum[J]:S.cum[J + 1]]
+                st = S.block_start(K, J)
+                if st is None:
+                    assert not np.any(blkA), (orders, sel, K, J)      # nothing of the operator outside the skyline
+                    continue
+                for j in range(rows[J]):
+                    d[st + j * S.stride[J]:st + j * S.stride[J] + rows[K]] = blkA[:, j]
+        assert np.array_equal(S.dense(), A)

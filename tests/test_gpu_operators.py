@@ -391,3 +391,72 @@ def test_pipelines_random_shapes(cb):
         Yc = _shifted_colmajor(cb, np.full((nfun, nvec), np.nan), shift)
         cb.mul(Yc, A, _shifted_colmajor(cb, X, shift))
         assert relerr(Yc.numpy(), ref) <= RTOL, ("fedvr", order, nel, nvec, a, b, shift)
+
+
+# ----------------------------------------------------------------------------------------------
+# BlockSkylineMatrix / Tridiagonal export (the reference's own destination types)
+# ----------------------------------------------------------------------------------------------
+def _fedvr_with_int_blocks(cb, t, orders):
+    """An FEDVRMatrix whose element i (1-based) is i*ones(o, o): the fills of test/fedvr/block_structure.jl."""
+    import torch
+    B = cb.FEDVR(t, orders)
+    blk = np.concatenate([np.full(int(o) ** 2, float(i + 1)) for i, o in enumerate(B.order)])
+    return B, torch.as_tensor(blk, device="cuda")
+
+
+def test_fedvr_skyline_set_blocks_2(cb):
+    """test/fedvr/block_structure.jl:122-164: B[:, 1:round(0.6N)+1] of orders [4,3,4,2,5,4,2,4,8], element i filled
+    with i; the value of every listed Block(i, j), and the 4:end-1 restriction == sub-matrix."""
+    B, blk = _fedvr_with_int_blocks(cb, cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8])
+    N = B.N
+    b = int(np.floor(0.6 * N + 0.5)) + 1
+    M = cb.FEDVRMatrix(B, blk, 1, b).skyline()
+    assert isinstance(M, cb.BlockSkylineMatrix) and M.shape == (18, 18)
+    expect = {1: [(1, 1), (1, 2), (2, 1)], 3: [(2, 2)], 2: [(2, 3), (2, 4), (3, 2), (4, 2), (3, 3), (3, 4), (4, 3)],
+              5: [(4, 4)], 7: [(6, 6)], 4: [(7, 6), (6, 7)], 9: [(7, 7)],
+              11: [(9, 9)], 6: [(10, 9), (11, 9), (9, 10), (9, 11), (10, 10), (11, 10), (10, 11)], 13: [(11, 11)],
+              15: [(12, 12)]}
+    expect3 = [(5, 4), (6, 4), (4, 5), (4, 6), (5, 5), (6, 5), (5, 6)]
+    expect5 = [(8, 7), (9, 7), (7, 8), (7, 9), (8, 8), (9, 8), (8, 9)]
+    expect7 = [(12, 11), (11, 12)]
+    for v, ijs in list(expect.items()) + [(3, expect3), (5, expect5), (7, expect7)]:
+        for i, j in ijs:
+            assert np.all(M.block(i - 1, j - 1) == v), (v, i, j)
+    M2 = cb.FEDVRMatrix(B, blk, 4, b - 1).skyline()
+    assert np.array_equal(M2.dense(), M.dense()[3:-1, 3:-1])
+    # and against the oracle's placement (set_elements! restated on a dense matrix)
+    O = cbo.FEDVROracle(cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8])
+    assert np.array_equal(M.dense(), O.dense(blk.cpu().numpy(), 1, b))
+
+
+@pytest.mark.parametrize("orders,sel", [([2, 3], None), ([2, 2, 3, 4, 2, 4], None), ([5, 6, 7, 8, 9, 10], None),
+                                        (4, (2, 12)), ([5, 4, 2, 2], (5, 9)), ([5, 4, 3, 2], (5, 10)), (10, (2, 45)), (7, (7, 13))])
+def test_fedvr_skyline_equals_dense_operator(cb, orders, sel):
+    """derop! into the BlockSkylineMatrix destination == the dense operator, for the order mixes of
+    test/fedvr/block_structure.jl:96-120 and the restrictions of test/fedvr/derivatives.jl:46-111; block sizes and
+    bandwidths are those of the oracle's restatement of src/fedvr.jl:121-176."""
+    nel = len(orders) if not np.isscalar(orders) else 5
+    t = cbo.julia_range(0.0, 20.0, nel + 1)
+    B = cb.FEDVR(t, orders)
+    O = cbo.FEDVROracle(t, orders)
+    D = cb.Derivative()
+    R = B if sel is None else B[:, sel[0]:sel[1]]
+    a, b = (1, B.N) if sel is None else sel
+    for A in (R.T @ D @ R, R.T @ D.T @ D @ R):
+        S = A.skyline()
+        assert S.rows == O.block_structure(a, b)
+        lo, uo = O.block_bandwidths(a, b)
+        assert (S.l, S.u) == (lo[:len(S.rows)], uo[:len(S.rows)])
+        assert np.array_equal(S.dense(), A.dense())
+
+
+def test_fedvr_tridiagonal_destination(cb):
+    """All orders 2: Matrix(undef, B) isa Tridiagonal (test/fedvr/block_structure.jl:26, src/fedvr_operators.jl:136-146)."""
+    t = cbo.julia_range(1.0, 7.0, 7)
+    B = cb.FEDVR(t, 2)
+    D = cb.Derivative()
+    for R in (B, B[:, 2:6]):
+        for A in (R.T @ D @ R, R.T @ D.T @ D @ R):
+            T = A.skyline()
+            assert isinstance(T, cb.Tridiagonal)
+            assert np.array_equal(T.dense(), A.dense())

@@ -450,3 +450,119 @@ def test_hydrogen_staggered_fd_levels_oracle():
     dv0, _ = cbo.fd_laplacian(al, be, rho)
     v0 = eigvalsh_tridiagonal(dv0 / -2 - 1.0 / r, ev / -2, select="i", select_range=(0, 0))
     assert abs(v0[0] - lam[0]) > 1e-3
+
+
+# ----------------------------------------------------------------------------------------------
+# FE-DVR element arithmetic pinned against a 50-digit evaluation of the same formulas
+# ----------------------------------------------------------------------------------------------
+def _mp_gausslobatto(n, mp):
+    """Gauss-Lobatto rule with n points in 50-digit arithmetic: -1, the roots of P'_{n-1}, 1;
+    w = 2 / (n (n-1) P_{n-1}(x)^2) (what FastGaussQuadrature.gausslobatto tabulates)."""
+    N = n - 1
+    if n == 2:
+        return [mp.mpf(-1), mp.mpf(1)], [mp.mpf(1), mp.mpf(1)]
+    guess = np.sort(np.polynomial.legendre.Legendre.basis(N).deriv().roots().real)     # independent of the oracle
+    # P'_N = N (P_{N-1} - x P_N) / (1 - x^2): Newton on the numerator from the float64 guesses
+    dP = lambda x: mp.legendre(N - 1, x) - x * mp.legendre(N, x)
+    inner = [mp.findroot(dP, mp.mpf(float(g))) for g in guess]
+    assert all(inner[i] < inner[i + 1] for i in range(len(inner) - 1)) and all(abs(float(r) - g) < 1e-8 for r, g in zip(inner, guess))
+    xs = [mp.mpf(-1)] + inner + [mp.mpf(1)]
+    ws = [2 / (N * (N + 1) * mp.legendre(N, x) ** 2) for x in xs]
+    return xs, ws
+
+
+@pytest.mark.parametrize("order", list(range(2, 17)))
+def test_fedvr_element_matrices_pinned_to_mpmath(order):
+    """cbo_lagrangeder / cbo_fedvr_element (src/fedvr_derivatives.jl:15-57) and the Gauss-Lobatto grid
+    (src/quadrature.jl:81-85, src/fedvr.jl:25-37) against mpmath at 50 digits: <= 1e-13 relative for
+    orders 2..16 (round 1 pinned these to 6 digits through the README printout only)."""
+    import mpmath as mp
+    mp.mp.dps = 50
+    a, b, c = 0.3, 1.7, 2.9                              # two elements of different width: one bridge
+    O = cbo.FEDVROracle(np.array([a, b, c]), order)
+    xi, wi = _mp_gausslobatto(order, mp)
+    xg, wg = cbo.gausslobatto(order)
+    assert max(abs(mp.mpf(float(v)) - r) for v, r in zip(xg, xi)) < mp.mpf("2e-16")
+    assert max(abs(mp.mpf(float(v)) - r) / r for v, r in zip(wg, wi)) < mp.mpf("1e-14")
+    els = []
+    for lo, hi in ((a, b), (b, c)):
+        lo, hi = mp.mpf(lo), mp.mpf(hi)
+        els.append(([lo + (hi - lo) * (x + 1) / 2 for x in xi], [(hi - lo) * w / 2 for w in wi]))
+    bridge = 1 / mp.sqrt(els[0][1][-1] + els[1][1][0])
+    for e, (xe, we) in enumerate(els):
+        ne = [1 / mp.sqrt(w) for w in we]
+        if e == 0:
+            ne[-1] = bridge
+        else:
+            ne[0] = bridge
+        o = order
+        Lp = [[None] * o for _ in range(o)]
+        for m in range(o):
+            Lp[m][m] = (int(m == o - 1) - int(m == 0)) / (2 * we[m])
+            for mp_ in range(o):
+                if mp_ == m:
+                    continue
+                f = mp.mpf(1)
+                for kk in range(o):
+                    if kk in (m, mp_):
+                        continue
+                    f *= (xe[mp_] - xe[kk]) / (xe[m] - xe[kk])
+                Lp[m][mp_] = f / (xe[m] - xe[mp_])
+        for nder in (1, 2):
+            D = np.zeros((o, o))
+            for m in range(o):
+                for mp_ in range(o):
+                    s = mp.mpf(0)
+                    for qd in range(o):
+                        lt = (mp.mpf(1) if m == qd else mp.mpf(0)) if nder == 1 else -Lp[m][qd]
+                        s += lt * we[qd] * Lp[mp_][qd]
+                    D[m, mp_] = float(ne[m] * ne[mp_] * s)
+            blk = O.blocks(nder)[O.boff[e]:O.boff[e] + o * o].reshape(o, o).T     # column-major o x o
+            err = np.max(np.abs(blk - D)) / np.max(np.abs(D))
+            assert err <= 1e-13, (order, e, nder, err)
+        # nodes and normalisation too
+        xs = O.x[O.estart[e]:O.estart[e] + o]
+        assert max(abs(mp.mpf(float(v)) - r) for v, r in zip(xs, xe)) < mp.mpf("1e-15")
+        ns = O.n[O.estart[e]:O.estart[e] + o]
+        assert max(abs(mp.mpf(float(v)) - r) / r for v, r in zip(ns, ne)) < mp.mpf("1e-14")
+
+
+def test_linear_cost_assembly_equals_literal_scan():
+    """cbo_bspline_assemble visits only the intervals of the row function; the literal all-interval scan
+    (cbo_bspline_assemble_literal) must give bit-identical bands (same terms, same order)."""
+    for k, ni, ml, mr in [(4, 30, 4, 4), (7, 25, 7, 7), (3, 12, 1, 3), (5, 20, 2, 5)]:
+        tt = np.sort(np.random.default_rng(k).uniform(0, 5, ni + 1))
+        tt[3] = tt[4]                                    # an empty interior interval
+        t = cbo.expand_knots(tt, k, ml, mr)
+        q = cbo.num_quadrature_points(k, 3)
+        x, w = cbo.lgwt(t, q)
+        op = np.cos(x)
+        for a, b, o in [(0, 0, None), (1, 1, None), (0, 1, None), (0, 0, op), (1, 1, op)]:
+            b1, l, u = cbo.bspline_assemble(t, k, t, k, x, w, q, a, b, o)
+            b2, _, _ = cbo.bspline_assemble_literal(t, k, t, k, x, w, q, a, b, o)
+            assert np.array_equal(b1, b2), (k, a, b)
+        b1, _, _ = cbo.bspline_assemble(t, k, t, k, x, w, q, 1, 1, None, 1, len(t) - k - 3, 2, len(t) - k - 4)
+        b2, _, _ = cbo.bspline_assemble_literal(t, k, t, k, x, w, q, 1, 1, None, 1, len(t) - k - 3, 2, len(t) - k - 4)
+        assert np.array_equal(b1, b2)
+
+
+def test_density_banded_qr_equals_dense_pinv():
+    """The linear-cost least-squares oracle used at BASELINE sizes (Givens QR of the banded Vandermonde matrix)
+    against the literal dense pinv of src/densities.jl:96, incl. weights, broadcasting and a restriction."""
+    rng = np.random.default_rng(7)
+    for k, ni, ml, mr in [(4, 30, 4, 4), (7, 25, 7, 7), (3, 12, 1, 3), (8, 40, 8, 8)]:
+        tt = np.sort(rng.uniform(0, 5, ni + 1))
+        t = cbo.expand_knots(tt, k, ml, mr)
+        q = cbo.num_quadrature_points(k, 3)
+        x, w = cbo.lgwt(t, q)
+        nf = len(t) - k
+        V = cbo.basis_matrix(t, k, x, q)
+        f, g = rng.standard_normal((2, nf, 3))
+        wv = rng.uniform(0.5, 1.5, len(x))
+        for ww in (None, wv):
+            r1 = cbo.density_bspline(V, f, g, ww)
+            r2 = cbo.density_bspline_qr(t, k, x, q, f, g, ww)
+            assert np.max(np.abs(r1 - r2)) <= 1e-12 * np.max(np.abs(r1))
+        r1 = cbo.density_bspline(V[:, 1:nf - 2], f[:nf - 3], g[:nf - 3, :1])
+        r2 = cbo.density_bspline_qr(t, k, x, q, f[:nf - 3], g[:nf - 3, :1], None, 1, nf - 3)
+        assert np.max(np.abs(r1 - r2)) <= 1e-12 * np.max(np.abs(r1))
