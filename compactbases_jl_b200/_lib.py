@@ -55,6 +55,7 @@ _SIGNATURES = {
     "cb_bspline_assemble_coulomb": (cint, [vp, vp, dbl, i64, i64, i64, i64, cint, cint, vp, vp]),
     "cb_bspline_assemble_part": (cint, [vp, vp, cint, cint, vp, cint, dbl, i64, i64, i64, i64, cint, cint,
                                         i64, i64, i64, i64, vp, vp]),
+    "cb_bspline_assemble_host": (cint, [vp, vp, cint, cint, vp, cint, dbl, i64, i64, i64, i64, cint, cint, vp, vp]),
     "cb_band_to_tridiag": (cint, [vp, i64, vp, vp, vp, vp]),
     "cb_fedvr_assemble": (cint, [vp, vp, vp, vp, vp, vp, vp, i64, cint, cint, cint, vp, vp]),
     "cb_fedvr_to_dense": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp]),
@@ -63,6 +64,8 @@ _SIGNATURES = {
     "cb_fedvr_apply": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_fedvr_apply_host": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_fd_derivative": (cint, [cint, cint, vp, vp, i64, dbl, i64, i64, dbl, cint, vp, vp, vp, vp]),
+    "cb_fd_derivative_banded": (cint, [cint, cint, vp, vp, i64, dbl, i64, i64, i64, i64, dbl, cint, vp, vp]),
+    "cb_fd_implicit_stencils": (cint, [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp]),
     "cb_banded_apply": (cint, [vp, i64, i64, cint, cint, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_tridiag_apply": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_tridiag_apply_host": (cint, [vp, vp, vp, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
@@ -76,6 +79,7 @@ _SIGNATURES = {
     "cb_density_destroy": (cint, [vp]),
     "cb_density_set_refine": (cint, [vp, cint]),
     "cb_density_apply": (cint, [vp, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
+    "cb_density_apply_host": (cint, [vp, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_nodal_product": (cint, [vp, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_orthogonal": (cint, [vp, i64, vp, i64, i64, vp, i64, i64, cint, vp, i64, vp]),
     "cb_density_project": (cint, [vp, vp, i64, i64, vp, i64, vp]),
@@ -86,6 +90,15 @@ _SIGNATURES = {
     "cb_bandlu_create": (cint, [vp, i64, cint, cint, C.POINTER(vp), vp]),
     "cb_bandlu_solve": (cint, [vp, vp, i64, i64, vp]),
     "cb_bandlu_destroy": (cint, [vp]),
+    "cb_batch_range": (cint, [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]),
+    "cb_comm_create": (cint, [cint, cint, C.POINTER(vp)]),
+    "cb_comm_export": (cint, [vp, vp]),
+    "cb_comm_connect": (cint, [vp, vp]),
+    "cb_comm_connect_local": (cint, [C.POINTER(vp), cint]),
+    "cb_comm_status": (cint, [vp, C.POINTER(cint), vp]),
+    "cb_comm_destroy": (cint, [vp]),
+    "cb_interval_shard": (cint, [vp, i64, i64, cint, cint] + [C.POINTER(i64)] * 5),
+    "cb_bspline_assemble_sharded": (cint, [vp, vp, vp, cint, cint, vp, cint, dbl, i64, i64, i64, i64, cint, cint, cint, vp, vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

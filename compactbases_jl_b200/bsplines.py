@@ -211,6 +211,29 @@ def diffop(L, R, a: int, b: int, ops=()):
     return dest
 
 
+def diffop_host(L, R, a: int, b: int, ops=()) -> np.ndarray:
+    """``diffop!`` into a HOST BandedMatrix (``cb_bspline_assemble_host``): returns the band data as an (n, l+u+1)
+    numpy array (column-major (l+u+1) x n).  ops: QuasiDiagonal factors (callables are evaluated on the host at
+    ``locs(B)``) or one CoulombPotential."""
+    PL, PR = L.parent_basis, R.parent_basis
+    l, u = band_shape(L, R)
+    m, n = L.ncols, R.ncols
+    out = np.empty((n, l + u + 1), dtype=np.float64)
+    opvals, coulomb, Z = None, 0, 0.0
+    for f in ops:
+        if isinstance(f, CoulombPotential) and len(ops) == 1:
+            coulomb, Z = 1, f.Z
+            break
+        v = PR.nodal_values(f.diag).cpu().numpy()
+        opvals = v if opvals is None else opvals * v
+    if opvals is not None:
+        opvals = np.ascontiguousarray(opvals, dtype=np.float64)
+    _lib.call("cb_bspline_assemble_host", PL.handle, PR.handle, a, b,
+              None if opvals is None else C.c_void_p(opvals.ctypes.data), coulomb, Z, L.col0, m, R.col0, n, l, u,
+              C.c_void_p(out.ctypes.data), _stream())
+    return out
+
+
 class BSpline(_BSplineOrRestricted):
     """``BSpline(t[, N]; k'=3)`` (src/bsplines.jl:95-119): the basis on knot set ``t`` with N
     Gauss-Legendre points per interval.  Construction uploads the knots and runs ``lgwt`` on
@@ -291,6 +314,16 @@ class BSpline(_BSplineOrRestricted):
         iv = torch.empty(nx, dtype=torch.int32, device=self.device)
         vals = torch.empty((nx, self.k), dtype=torch.float64, device=self.device)
         _lib.call("cb_bspline_eval", self.handle, _ptr(xd), nx, m, _ptr(iv), _ptr(vals), _stream())
+        return iv, vals
+
+    def eval_ell_host(self, x: np.ndarray, m=0):
+        """Host-pointer form (``cb_bspline_eval_host``): numpy in, numpy out."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        iv = np.empty(x.size, dtype=np.int32)
+        vals = np.empty((x.size, self.k), dtype=np.float64)
+        with torch.cuda.device(self.device):
+            _lib.call("cb_bspline_eval_host", self.handle, C.c_void_p(x.ctypes.data), x.size, m, C.c_void_p(iv.ctypes.data),
+                      C.c_void_p(vals.ctypes.data))
         return iv, vals
 
     def eval_csc(self, x, col0=0, ncols=None) -> SparseMatrixCSC:

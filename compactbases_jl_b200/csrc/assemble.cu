@@ -51,6 +51,45 @@ __device__ void bspline_all_rt(int k, const double *tw, double x, int m, double 
 // 28-52), which the reference stores as a sparse matrix in memory, never
 // leaves the SM.
 // ---------------------------------------------------------------------------
+// Fused halo exchange of an interval-sharded assembly.  A rank sums its own intervals into every
+// column that touches them.  Its first n_push columns belong to the LEFT neighbour: they are stored straight into that
+// neighbour's mailbox over NVLink (peer-mapped memory) and, once every tile that holds such a column has finished, a
+// flag is raised there.  Its last n_recv columns also live on the RIGHT neighbour's intervals: the tiles that hold them
+// wait for the local flag (the right neighbour handles its pushed tiles first, these tiles come last, so the wait is
+// normally over before it starts) and add the mailbox to their own sums.  No host round trip, no collective launch.
+// Mailboxes are double-buffered by call parity; `ack` words tell the pusher that the buffer of two calls ago has been
+// consumed.  Every spin is bounded (status word).
+struct AsmHalo {
+    int n_push, n_recv;
+    int n_push_tiles, n_recv_tiles;
+    double *push_cols;                      // peer: left neighbour's mailbox columns of this parity
+    unsigned long long *push_flag;          // peer: its flag of this parity
+    const double *recv_cols;                // local mailbox columns of this parity
+    unsigned long long *recv_flag;          // local flag of this parity (written by the right neighbour)
+    unsigned long long *ack_out;            // peer: right neighbour's ack word of this parity (we write the epoch after consuming)
+    unsigned long long *ack_in;             // local ack word of this parity (the left neighbour consumed that epoch)
+    unsigned long long epoch;
+    unsigned int *counters;                 // local: [0] pushed tiles finished, [1] receiving tiles finished
+    int *status;                            // local: non-zero after a spin timeout
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// waits until *p >= want; gives up after ~2 s (a peer that never launched must not hang the GPU)
+__device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long want, int *status) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > 4000000000ll) { atomicExch(status, 1); break; }
+        __nanosleep(64);
+    }
+}
+
 struct AsmArgs {
     KnotView kvL, kvR;
     int kL, kR;
@@ -67,6 +106,7 @@ struct AsmArgs {
     int TJ;
     int two_tab;                  // tiled kernel: L and R need different tables (da != db or different left multiplicity)
     double *band;                 // column col_lo is at band[0]
+    AsmHalo H;                    // interval-sharded assembly: fused halo exchange over peer memory (all zero: none)
 };
 
 constexpr int ASM_THREADS = 256;
@@ -175,6 +215,50 @@ template <int K> struct AsmMs {
 // Geometry of one column tile: columns [j0, j1), intervals [sA, sB] of t.t.
 struct AsmTile { i64 j0, j1, sA, sB; int ns; };
 
+// Halo hooks of a column tile [j0, j1) (CTA-uniform; contain CTA barriers).
+__device__ __forceinline__ bool halo_tile_pushes(const AsmArgs &A, i64 j0) { return A.H.n_push > 0 && j0 < A.col_lo + A.H.n_push; }
+__device__ __forceinline__ bool halo_tile_receives(const AsmArgs &A, i64 j1) { return A.H.n_recv > 0 && j1 > A.col_hi - A.H.n_recv; }
+
+__device__ __forceinline__ void halo_before_stores(const AsmArgs &A, i64 j0, i64 j1) {
+    const bool rcv = halo_tile_receives(A, j1), psh = halo_tile_pushes(A, j0) && A.H.epoch > 2;
+    if (!rcv && !psh) return;
+    if (threadIdx.x == 0) {
+        if (rcv) halo_spin(A.H.recv_flag, A.H.epoch, A.H.status);
+        if (psh) halo_spin(A.H.ack_in, A.H.epoch - 2, A.H.status);     // the buffer of this parity has been consumed
+    }
+    __syncthreads();
+}
+
+// band entry (d, j): pushed columns go to the neighbour's mailbox, receiving columns add what the neighbour sent
+__device__ __forceinline__ void halo_store(const AsmArgs &A, int W, i64 j, int d, double v, bool in_run) {
+    if (A.H.n_push > 0 && j < A.col_lo + A.H.n_push) {
+        A.H.push_cols[d + (i64)W * (j - A.col_lo)] = v;
+        return;
+    }
+    if (in_run && A.H.n_recv > 0 && j >= A.col_hi - A.H.n_recv)
+        v += __ldcv(A.H.recv_cols + d + (i64)W * (j - (A.col_hi - A.H.n_recv)));
+    A.band[d + (i64)W * (j - A.col_lo)] = v;
+}
+
+__device__ __forceinline__ void halo_after_stores(const AsmArgs &A, i64 j0, i64 j1) {
+    const bool rcv = halo_tile_receives(A, j1), psh = halo_tile_pushes(A, j0);
+    if (!rcv && !psh) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (psh && atomicAdd(&A.H.counters[0], 1u) == (unsigned)(A.H.n_push_tiles - 1)) {
+            A.H.counters[0] = 0;
+            __threadfence_system();
+            st_release_sys(A.H.push_flag, A.H.epoch);
+        }
+        if (rcv && atomicAdd(&A.H.counters[1], 1u) == (unsigned)(A.H.n_recv_tiles - 1)) {
+            A.H.counters[1] = 0;
+            __threadfence_system();
+            st_release_sys(A.H.ack_out, A.H.epoch);
+        }
+    }
+}
+
 template <int K>
 __device__ __forceinline__ AsmTile asm_tile(const AsmArgs &A, i64 tile) {
     AsmTile t;
@@ -263,6 +347,7 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
         // one thread per band entry of the (2K-1)-row run of each column; run entry tt of a column is
         // the sum over its intervals r of MS[slot + r][K-1-r][tt - r]
         if (prev.ns >= 0) {
+            halo_before_stores(A, prev.j0, prev.j1);
             const int nent = (int)(prev.j1 - prev.j0) * W2;
             for (int e = threadIdx.x; e < nent; e += ASM_THREADS) {
                 const int jj = e / W2, tt = e - jj * W2;
@@ -278,7 +363,7 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
                 // run entry tt is row fi = fj - mlR + mlL - K + 1 + tt; band slot d holds row i = j - u + d
                 const i64 i = (fj - mlR + mlL - K + 1 + tt) - (A.rowL0 + 1);
                 const i64 d = i - j + A.u;
-                if (d >= 0 && d < W && i >= 0 && i < A.mm && j < A.nn) A.band[d + (i64)W * (j - A.col_lo)] = s;
+                if (d >= 0 && d < W && i >= 0 && i < A.mm && j < A.nn) halo_store(A, W, j, (int)d, s, true);
             }
             // band slots outside the run or outside the matrix are zero
             const int nz = (int)(prev.j1 - prev.j0) * W;
@@ -286,8 +371,9 @@ bspline_assemble_tiled_kernel(AsmArgs A) {
                 const int jj = e / W, d = e - jj * W;
                 const i64 j = prev.j0 + jj, i = j - A.u + d;
                 const i64 tt = (i + A.rowL0 + 1) - (A.colR0 + 1 + j - mlR + mlL - K + 1);
-                if (tt < 0 || tt >= W2 || i < 0 || i >= A.mm || j >= A.nn) A.band[d + (i64)W * (j - A.col_lo)] = 0.0;
+                if (tt < 0 || tt >= W2 || i < 0 || i >= A.mm || j >= A.nn) halo_store(A, W, j, d, 0.0, false);
             }
+            halo_after_stores(A, prev.j0, prev.j1);
         }
         if (!live) break;
         prev = t;
@@ -428,6 +514,7 @@ bspline_assemble_kernel(AsmArgs A) {
         __syncthreads();
         // ---- phase 2: gather into the band ----------------------------------
         const int nent = (int)(j1 - j0) * W;
+        halo_before_stores(A, j0, j1);
         for (int e = threadIdx.x; e < nent; e += ASM_THREADS) {
             const int jj = e / W, d = e - jj * W;
             const i64 j = j0 + jj, i = j - A.u + d;
@@ -453,8 +540,9 @@ bspline_assemble_kernel(AsmArgs A) {
                     }
                 }
             }
-            A.band[(i64)d + (i64)W * (j - A.col_lo)] = acc;
+            halo_store(A, W, j, d, acc, true);
         }
+        halo_after_stores(A, j0, j1);
     }
 }
 
@@ -553,71 +641,147 @@ __device__ __forceinline__ double rext(const double *__restrict__ r, i64 N, i64 
     return r[j - 1];
 }
 
+// alpha_j, beta_j, gamma_j, delta_j of node j (1-based) of the parent grid.
+__device__ __forceinline__ void fd_coeffs(int scheme, const double *__restrict__ r, const double *__restrict__ fhalf, i64 N,
+                                          i64 j, double &al, double &be, double &ga, double &de) {
+    al = 1.0; be = 1.0; ga = 0.0; de = 1.0;        // Cartesian, src/fd_derivatives.jl:12-15
+    if (scheme == 1) {                              // :20-25
+        const double j2 = (double)(j * j);
+        al = __ddiv_rn(j2, __dsub_rn(j2, 0.25));
+        de = al;
+        const double t = (double)(j * j - j);
+        be = __ddiv_rn(__dadd_rn(t, 0.5), __dadd_rn(t, 0.25));
+    } else if (scheme == 2) {                       // :27-92
+        const double a = rext(r, N, j - 1), b = rext(r, N, j), c = rext(r, N, j + 1);
+        const double dd = rext(r, N, j + 2 > N + 1 ? N + 1 : j + 2);
+        const double rp = __ddiv_rn(__dadd_rn(b, c), 2.0);
+        if (j < N) {
+            const double root = __dsqrt_rn(__dmul_rn(__dsub_rn(dd, b), __dsub_rn(c, a)));
+            // delta: 2/sqrt(..)*((b+c)/2)^2/(b*c)
+            de = __ddiv_rn(__dmul_rn(__ddiv_rn(2.0, root), sq_(rp)), __dmul_rn(b, c));
+            if (fhalf) al = __ddiv_rn(__dmul_rn(__ddiv_rn(__dmul_rn(2.0, fhalf[j]), __dmul_rn(__dsub_rn(c, b), root)), sq_(rp)), __dmul_rn(b, c));
+            else al = __ddiv_rn(__dmul_rn(__ddiv_rn(2.0, __dmul_rn(__dsub_rn(c, b), root)), sq_(rp)), __dmul_rn(b, c));
+        }
+        if (fhalf) {
+            const double bm2 = __ddiv_rn(1.0, sq_(b));
+            const double rm = __ddiv_rn(__dadd_rn(a, b), 2.0);
+            const double fp = __dmul_rn(sq_(rp), bm2), fm = __dmul_rn(sq_(rm), bm2);
+            const double t1 = __dmul_rn(__ddiv_rn(fhalf[j], __dsub_rn(c, b)), fp);
+            const double t2 = __dmul_rn(__ddiv_rn(fhalf[j - 1], __dsub_rn(b, a)), fm);
+            be = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, a)), __dadd_rn(t1, t2));
+        } else {
+            const double tb = __dmul_rn(2.0, b);
+            const double fp = sq_(__ddiv_rn(__dadd_rn(c, b), tb));
+            const double fm = sq_(__ddiv_rn(__dadd_rn(b, a), tb));
+            const double t1 = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, b)), fp);
+            const double t2 = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(b, a)), fm);
+            be = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, a)), __dadd_rn(t1, t2));
+        }
+    }
+}
+
+// The three entries of row/column j (1-based parent node) of the parent operator:
+//   dg = A[j, j], up = A[j, j+1] (du[j]), lo = A[j+1, j] (dl[j])        (src/fd_derivatives.jl:233-237, :265-277)
+__device__ __forceinline__ void fd_entries(int scheme, int nder, const double *__restrict__ r, const double *__restrict__ fhalf,
+                                           i64 N, double step, i64 j, double Z, int ell, double &dg, double &up, double &lo) {
+    double al, be, ga, de;
+    fd_coeffs(scheme, r, fhalf, N, j, al, be, ga, de);
+    if (nder == 1) {                                // :233-237
+        const double mu = __dmul_rn(2.0, step);
+        dg = __ddiv_rn(ga, mu);
+        up = __ddiv_rn(de, mu);
+        lo = __ddiv_rn(-de, mu);
+    } else {                                        // :265-277
+        const double h2 = sq_(step);
+        double dv = __ddiv_rn(__dmul_rn(-2.0, be), h2);
+        if (j == 1 && scheme != 0 && ell == 0 && Z != 0.0) {   // laplacian_correction!, :542-551
+            const double rho = scheme == 1 ? step : __dsub_rn(r[1], r[0]);
+            // 1/rho^2*Z*rho/8*(1 + Z*rho), left to right
+            double db = __ddiv_rn(1.0, sq_(rho));
+            db = __dmul_rn(db, Z);
+            db = __dmul_rn(db, rho);
+            db = __ddiv_rn(db, 8.0);
+            db = __dmul_rn(db, __dadd_rn(1.0, __dmul_rn(Z, rho)));
+            dv = __dsub_rn(dv, __dmul_rn(2.0, db));
+        }
+        dg = dv;
+        up = lo = __ddiv_rn(al, h2);
+    }
+}
+
 __global__ void fd_stencil_kernel(int scheme, int nder, const double *__restrict__ r, const double *__restrict__ fhalf,
                                   i64 N, double step, i64 i0, i64 n, double Z, int ell,
                                   double *__restrict__ dl, double *__restrict__ d, double *__restrict__ du) {
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         const i64 j = i0 + i + 1;                   // 1-based node of the parent grid
-        double al = 1.0, be = 1.0, ga = 0.0, de = 1.0;   // Cartesian, src/fd_derivatives.jl:12-15
-        if (scheme == 1) {                          // :20-25
-            const double j2 = (double)(j * j);
-            al = __ddiv_rn(j2, __dsub_rn(j2, 0.25));
-            de = al;
-            const double t = (double)(j * j - j);
-            be = __ddiv_rn(__dadd_rn(t, 0.5), __dadd_rn(t, 0.25));
-        } else if (scheme == 2) {                   // :27-92
-            const double a = rext(r, N, j - 1), b = rext(r, N, j), c = rext(r, N, j + 1);
-            const double dd = rext(r, N, j + 2 > N + 1 ? N + 1 : j + 2);
-            const double rp = __ddiv_rn(__dadd_rn(b, c), 2.0);
-            if (j < N) {
-                const double root = __dsqrt_rn(__dmul_rn(__dsub_rn(dd, b), __dsub_rn(c, a)));
-                // delta: 2/sqrt(..)*((b+c)/2)^2/(b*c)
-                de = __ddiv_rn(__dmul_rn(__ddiv_rn(2.0, root), sq_(rp)), __dmul_rn(b, c));
-                if (fhalf) al = __ddiv_rn(__dmul_rn(__ddiv_rn(__dmul_rn(2.0, fhalf[j]), __dmul_rn(__dsub_rn(c, b), root)), sq_(rp)), __dmul_rn(b, c));
-                else al = __ddiv_rn(__dmul_rn(__ddiv_rn(2.0, __dmul_rn(__dsub_rn(c, b), root)), sq_(rp)), __dmul_rn(b, c));
-            }
-            if (fhalf) {
-                const double bm2 = __ddiv_rn(1.0, sq_(b));
-                const double rm = __ddiv_rn(__dadd_rn(a, b), 2.0);
-                const double fp = __dmul_rn(sq_(rp), bm2), fm = __dmul_rn(sq_(rm), bm2);
-                const double t1 = __dmul_rn(__ddiv_rn(fhalf[j], __dsub_rn(c, b)), fp);
-                const double t2 = __dmul_rn(__ddiv_rn(fhalf[j - 1], __dsub_rn(b, a)), fm);
-                be = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, a)), __dadd_rn(t1, t2));
-            } else {
-                const double tb = __dmul_rn(2.0, b);
-                const double fp = sq_(__ddiv_rn(__dadd_rn(c, b), tb));
-                const double fm = sq_(__ddiv_rn(__dadd_rn(b, a), tb));
-                const double t1 = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, b)), fp);
-                const double t2 = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(b, a)), fm);
-                be = __dmul_rn(__ddiv_rn(1.0, __dsub_rn(c, a)), __dadd_rn(t1, t2));
+        double dg, up, lo;
+        fd_entries(scheme, nder, r, fhalf, N, step, j, Z, ell, dg, up, lo);
+        d[i] = dg;
+        if (i < n - 1) {
+            if (du) du[i] = up;
+            if (dl) dl[i] = lo;
+        }
+    }
+}
+
+// Operators between DIFFERENT restrictions A = R[:, ra0+1 : ra0+m], B = R[:, cb0+1 : cb0+n] (derivative_matrix,
+// src/fd_derivatives.jl:214-219): the m x n sub-block of the parent tridiagonal operator as a BandedMatrix with
+// bandwidths (1 - offset, 1 + offset), offset = ra0 - cb0, filled band by band (:244-249, :278-289).  In
+// BandedMatrices storage band[(u + i - j) + 3 j] the three rows are du, d, dl of the parent at the column's node.
+// One thread per column.
+__global__ void fd_band_kernel(int scheme, int nder, const double *__restrict__ r, const double *__restrict__ fhalf,
+                               i64 N, double step, i64 ra0, i64 m, i64 cb0, i64 n, double Z, int ell,
+                               double *__restrict__ band) {
+    for (i64 jc = blockIdx.x * (i64)blockDim.x + threadIdx.x; jc < n; jc += (i64)gridDim.x * blockDim.x) {
+        const i64 pj = cb0 + jc + 1;                // parent node of this column (1-based)
+        double dg, up, lo, t0, t1;
+        fd_entries(scheme, nder, r, fhalf, N, step, pj, Z, ell, dg, up, lo);
+        double above = 0.0;                         // A[pj-1, pj] = up of node pj-1
+        if (pj >= 2) fd_entries(scheme, nder, r, fhalf, N, step, pj - 1, Z, ell, t0, above, t1);
+        auto row_in = [&](i64 p) { return p >= ra0 + 1 && p <= ra0 + m; };
+        band[0 + 3 * jc] = (pj >= 2 && row_in(pj - 1)) ? above : 0.0;
+        band[1 + 3 * jc] = row_in(pj) ? dg : 0.0;
+        band[2 + 3 * jc] = (pj + 1 <= N && row_in(pj + 1)) ? lo : 0.0;
+    }
+}
+
+// Non-uniform compact scheme (Patchkovskii & Muller 2016, Eq. 33): implicit_stencil_common (src/fd_derivatives.jl:105-125)
+// feeds fun(a, b, c) the consecutive local steps of the grid continued to the origin on the left and by one mirrored
+// point on the right; with R_0 = 0, R_i = r_i, R_{N+1} = 2 r_N - r_{N-1} the call with shift s gives, at index j,
+// a = R_{j+s-1} - R_{j+s-2}, b = R_{j+s} - R_{j+s-1}.  One thread per node writes the three right-hand-side stencils
+// (:127-143) and the left-hand side of the second derivative (implicit_lhs, :410-424) with the reference's order of
+// operations.
+__device__ __forceinline__ double rext0(const double *__restrict__ r, i64 N, i64 i) {
+    if (i <= 0) return 0.0;
+    if (i > N) return __dsub_rn(__dmul_rn(2.0, r[N - 1]), r[N - 2]);
+    return r[i - 1];
+}
+
+__global__ void fd_implicit_stencil_kernel(const double *__restrict__ r, i64 N, i64 i0, i64 n,
+                                           double *__restrict__ alpha_t, double *__restrict__ alpha, double *__restrict__ beta,
+                                           double *__restrict__ m_dl, double *__restrict__ m_d, double *__restrict__ m_du) {
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 j = i0 + i + 1;
+        {   // s = 1: beta_j, m_d_j (j = 1..N), alpha_j, m_du_j (j = 1..N-1)
+            const double R0 = rext0(r, N, j - 1), R1 = rext0(r, N, j), R2 = rext0(r, N, j + 1);
+            const double a = __dsub_rn(R1, R0), b = __dsub_rn(R2, R1);
+            const double ab = __dmul_rn(a, b), apb = __dadd_rn(a, b);
+            beta[i] = __ddiv_rn(1.0, ab);
+            // (a^2 + 3a*b + b^2)/(6*a*b)
+            m_d[i] = __ddiv_rn(__dadd_rn(__dadd_rn(sq_(a), __dmul_rn(__dmul_rn(3.0, a), b)), sq_(b)), __dmul_rn(__dmul_rn(6.0, a), b));
+            if (i < n - 1) {
+                alpha[i] = __ddiv_rn(2.0, __dmul_rn(b, apb));
+                // (-a^2 + a*b + b^2)/(6*b*(a+b))
+                m_du[i] = __ddiv_rn(__dadd_rn(__dadd_rn(-sq_(a), ab), sq_(b)), __dmul_rn(__dmul_rn(6.0, b), apb));
             }
         }
-        if (nder == 1) {                            // :233-237
-            const double mu = __dmul_rn(2.0, step);
-            d[i] = __ddiv_rn(ga, mu);
-            if (i < n - 1) {
-                if (du) du[i] = __ddiv_rn(de, mu);
-                if (dl) dl[i] = __ddiv_rn(-de, mu);
-            }
-        } else {                                    // :265-277
-            const double h2 = sq_(step);
-            double dv = __ddiv_rn(__dmul_rn(-2.0, be), h2);
-            if (j == 1 && scheme != 0 && ell == 0 && Z != 0.0) {   // laplacian_correction!, :542-551
-                const double rho = scheme == 1 ? step : __dsub_rn(r[1], r[0]);
-                // 1/rho^2*Z*rho/8*(1 + Z*rho), left to right
-                double db = __ddiv_rn(1.0, sq_(rho));
-                db = __dmul_rn(db, Z);
-                db = __dmul_rn(db, rho);
-                db = __ddiv_rn(db, 8.0);
-                db = __dmul_rn(db, __dadd_rn(1.0, __dmul_rn(Z, rho)));
-                dv = __dsub_rn(dv, __dmul_rn(2.0, db));
-            }
-            d[i] = dv;
-            if (i < n - 1) {
-                const double ev = __ddiv_rn(al, h2);
-                if (du) du[i] = ev;
-                if (dl) dl[i] = ev;
-            }
+        if (i < n - 1) {   // s = 2: alpha~_j, m_dl_j (j = 1..N-1)
+            const double R0 = rext0(r, N, j), R1 = rext0(r, N, j + 1), R2 = rext0(r, N, j + 2);
+            const double a = __dsub_rn(R1, R0), b = __dsub_rn(R2, R1);
+            const double apb = __dadd_rn(a, b);
+            alpha_t[i] = __ddiv_rn(2.0, __dmul_rn(a, apb));
+            // (a^2 + a*b - b^2)/(6*a*(a+b))
+            m_dl[i] = __ddiv_rn(__dsub_rn(__dadd_rn(sq_(a), __dmul_rn(a, b)), sq_(b)), __dmul_rn(__dmul_rn(6.0, a), apb));
         }
     }
 }
@@ -641,7 +805,8 @@ static int ensure_rc_index() {
 
 static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
                            int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
-                           i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, void *stream) {
+                           i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, void *stream,
+                           const AsmHalo *halo = nullptr) {
     CB_REQUIRE(L != nullptr && R != nullptr && band != nullptr, "cb_bspline_assemble: NULL argument");
     // assert_compatible_bases, src/bsplines.jl:75-82
     // (the same handle on both sides needs no look at the knots: comparing 1.6e6 of them cost more than the kernel)
@@ -672,7 +837,17 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     A.rowL0 = rowL0; A.mm = m; A.colR0 = colR0; A.nn = n;
     A.l = l; A.u = u; A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
     A.band = band;
+    memset(&A.H, 0, sizeof(A.H));
+    if (halo) A.H = *halo;
     const i64 ncol = col_hi - col_lo;
+    // tiles that hold pushed / receiving columns (the kernels count them down to raise the flags)
+    auto halo_tiles = [&](int TJ) {
+        if (!halo) return;
+        const i64 ntl = (ncol + TJ - 1) / TJ;
+        A.H.n_push_tiles = A.H.n_push > 0 ? (int)((A.H.n_push + TJ - 1) / TJ) : 0;
+        const i64 first_recv_tile = A.H.n_recv > 0 ? (ncol - A.H.n_recv) / TJ : ntl;
+        A.H.n_recv_tiles = (int)(ntl - first_recv_tile);
+    };
     // ---- tiled kernel: same order 2..CB_KMAX on both sides and the default node count family ----
     const int K = L->k, QH = (K + 2) / 2;           // q = K + 1 (num_quadrature_points(k, 3)) -> ceil(q / 2)
     if (L->k == R->k && K >= 2 && K <= CB_KMAX && (A.q + 1) / 2 == QH) {
@@ -691,6 +866,7 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
             A.TJ = (int)TJ;
             const size_t smem = ((size_t)(A.TJ + K - 1) * per_iv + fixed) / 16 * 16;
             const i64 ntiles = (ncol + A.TJ - 1) / A.TJ;
+            halo_tiles(A.TJ);
             const int grid = (int)(ntiles < (i64)CB_NUM_SMS * 8 ? ntiles : (i64)CB_NUM_SMS * 8);
 #define CB_ASM_TILED(KT)                                                                                     \
     case KT: {                                                                                               \
@@ -718,12 +894,22 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     size_t smem = (size_t)(TJ + A.kR - 1) * per_iv;
     if (smem > 220 * 1024) { cb_set_error("cb_bspline_assemble: k=%d, q=%d tables exceed shared memory", k, A.q); return CB_ERR_UNSUPPORTED; }
     A.TJ = TJ;
+    halo_tiles(TJ);
     i64 ntiles = (ncol + TJ - 1) / TJ;
     int grid = (int)(ntiles < (i64)CB_NUM_SMS * 32 ? ntiles : (i64)CB_NUM_SMS * 32);
     CB_CUDA(cudaFuncSetAttribute(bspline_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bspline_assemble_kernel<<<grid, ASM_THREADS, smem, st>>>(A);
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+// Interval-sharded assembly with the fused halo (comm.cu).
+int cb_bspline_assemble_halo_internal(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
+                                      int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
+                                      i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, void *stream,
+                                      const void *halo) {
+    return assemble_common(L, R, a, b, opvals, coulomb, Z, rowL0, m, colR0, n, l, u, col_lo, col_hi, s_lo, s_hi, band, stream,
+                           static_cast<const AsmHalo *>(halo));
 }
 
 // Gram matrix V'V of the restricted Vandermonde matrix at the nodes (density.cu).
@@ -751,6 +937,35 @@ int cb_bspline_assemble_part(const cb_bspline *L, const cb_bspline *R, int a, in
                              i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band_cols, void *stream) {
     return assemble_common(L, R, a, b, opvals, coulomb, Z, rowL0, m, colR0, n, l, u, col_lo, col_hi, s_lo, s_hi,
                            band_cols, stream);
+}
+
+// Host-pointer convenience form: the band is assembled on the device and copied into a host
+// BandedMatrix' data; opvals_host (numnodes doubles) is uploaded if given.  Synchronous.
+int cb_bspline_assemble_host(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals_host,
+                             int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
+                             double *band_host, void *stream) {
+    CB_REQUIRE(R != nullptr && band_host != nullptr, "cb_bspline_assemble_host: NULL argument");
+    CB_REQUIRE(n >= 0 && l + u + 1 >= 1, "cb_bspline_assemble_host: bad shape");
+    if (n == 0) return CB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
+    const size_t bytes = sizeof(double) * (size_t)(l + u + 1) * (size_t)n, nb = sizeof(double) * (size_t)(R->ni * R->q);
+    double *d_band = nullptr, *d_op = nullptr;
+    CB_CUDA(cudaMallocAsync(&d_band, bytes, st));
+    cudaError_t e = cudaSuccess;
+    if (opvals_host) {
+        e = cudaMallocAsync(&d_op, nb ? nb : 8, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_op, opvals_host, nb, cudaMemcpyHostToDevice, st);
+    }
+    int rc = CB_OK;
+    if (e == cudaSuccess) rc = assemble_common(L, R, a, b, d_op, coulomb, Z, rowL0, m, colR0, n, l, u, 0, n, 0, R->n_tt - 1, d_band, stream);
+    if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpyAsync(band_host, d_band, bytes, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_band, st);
+    if (d_op) cudaFreeAsync(d_op, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) { cb_set_error("cb_bspline_assemble_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return rc;
 }
 
 int cb_band_to_tridiag(const double *band, i64 n, double *dl, double *d, double *du, void *stream) {
@@ -805,6 +1020,36 @@ int cb_fd_derivative(int scheme, int nder, const double *r, const double *fhalf,
     if (n == 0) return CB_OK;
     CB_REQUIRE(d != nullptr, "cb_fd_derivative: NULL diagonal");
     fd_stencil_kernel<<<cb_grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(scheme, nder, r, fhalf, N, step, i0, n, Z, ell, dl, d, du);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// derivative_matrix / materialisers between different restrictions (src/fd_derivatives.jl:214-219,244-249,278-289).
+int cb_fd_derivative_banded(int scheme, int nder, const double *r, const double *fhalf, i64 N, double step,
+                            i64 rowi0, i64 m, i64 colj0, i64 n, double Z, int ell, double *band, void *stream) {
+    CB_REQUIRE(scheme >= 0 && scheme <= 2, "cb_fd_derivative_banded: unknown scheme %d", scheme);
+    CB_REQUIRE(nder == 1 || nder == 2, "cb_fd_derivative_banded: derivative order must be 1 or 2");
+    CB_REQUIRE(N >= 1 && rowi0 >= 0 && m >= 0 && rowi0 + m <= N && colj0 >= 0 && n >= 0 && colj0 + n <= N,
+               "cb_fd_derivative_banded: restriction outside 1..N");
+    CB_REQUIRE(scheme != 2 || (r != nullptr && N >= 3), "cb_fd_derivative_banded: non-uniform scheme needs the node vector (N >= 3)");
+    CB_REQUIRE(fhalf == nullptr, "cb_fd_derivative_banded: the reference has no weighted form between different restrictions (src/fd_derivatives.jl:320-331)");
+    CB_REQUIRE(step > 0.0, "cb_fd_derivative_banded: step must be positive");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(band != nullptr, "cb_fd_derivative_banded: NULL band");
+    // the Coulomb correction of the [1,1] entry is applied only when both restrictions start at the first node (:620-622)
+    const double Zc = (rowi0 == 0 && colj0 == 0) ? Z : 0.0;
+    fd_band_kernel<<<cb_grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(scheme, nder, r, fhalf, N, step, rowi0, m, colj0, n, Zc, ell, band);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+// Stencils of the non-uniform compact scheme for nodes i0+1 .. i0+n (src/fd_derivatives.jl:105-143, :410-424).
+int cb_fd_implicit_stencils(const double *r, i64 N, i64 i0, i64 n, double *alpha_t, double *alpha, double *beta,
+                            double *m_dl, double *m_d, double *m_du, void *stream) {
+    CB_REQUIRE(r != nullptr && N >= 2 && i0 >= 0 && n >= 0 && i0 + n <= N, "cb_fd_implicit_stencils: restriction outside 1..N");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(beta && m_d && (n == 1 || (alpha_t && alpha && m_dl && m_du)), "cb_fd_implicit_stencils: NULL output");
+    fd_implicit_stencil_kernel<<<cb_grid_for(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(r, N, i0, n, alpha_t, alpha, beta, m_dl, m_d, m_du);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

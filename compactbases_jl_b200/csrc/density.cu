@@ -1110,6 +1110,62 @@ int cb_density_apply(const cb_density *D, const double *f, i64 ldf, i64 Pf,
     return rc;
 }
 
+// Host-pointer form of copyto!(rho, f, g): the pair batch is streamed through the device in tiles on three private
+// streams (H2D of tile t+1, the kernels of tile t and D2H of tile t-1 overlap).  f / g with a single column are
+// uploaded once.  `stream`: producer stream of the plan (see the *_apply_host entries).  Returns when rho_host is done.
+int cb_density_apply_host(const cb_density *D, const double *f_host, i64 ldf, i64 Pf, const double *g_host, i64 ldg, i64 Pg,
+                          int conj, double *rho_host, i64 ldr, void *stream) {
+    int rc = check_pairs("cb_density_apply_host", D, f_host, ldf, Pf, g_host, ldg, Pg);
+    if (rc) return rc;
+    CB_REQUIRE(rho_host != nullptr && ldr >= D->ncols, "cb_density_apply_host: bad rho array");
+    const i64 P = Pf > Pg ? Pf : Pg, n = D->ncols;
+    if (P == 0) return CB_OK;
+    constexpr int NB = 3;
+    i64 tp = (i64)(48 << 20) / (n * (i64)sizeof(double));           // ~48 MB per array and buffer
+    tp = tp < 32 ? 32 : tp / 32 * 32;
+    if (tp > P) tp = P;
+    cudaStream_t st[NB] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    double *df[NB] = {nullptr, nullptr, nullptr}, *dg[NB] = {nullptr, nullptr, nullptr}, *dr[NB] = {nullptr, nullptr, nullptr};
+    double *f1 = nullptr, *g1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    const size_t tile_b = sizeof(double) * (size_t)n * (size_t)tp, col_b = sizeof(double) * (size_t)n;
+    for (int b = 0; b < NB; ++b) {
+        step(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
+        if (Pf > 1) step(cudaMalloc(&df[b], tile_b));
+        if (Pg > 1) step(cudaMalloc(&dg[b], tile_b));
+        step(cudaMalloc(&dr[b], tile_b));
+    }
+    step(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    if (Pf == 1) { step(cudaMalloc(&f1, col_b)); if (e == cudaSuccess) step(cudaMemcpyAsync(f1, f_host, col_b, cudaMemcpyHostToDevice, (cudaStream_t)stream)); }
+    if (Pg == 1) { step(cudaMalloc(&g1, col_b)); if (e == cudaSuccess) step(cudaMemcpyAsync(g1, g_host, col_b, cudaMemcpyHostToDevice, (cudaStream_t)stream)); }
+    if (e == cudaSuccess) step(cudaEventRecord(ready, (cudaStream_t)stream));
+    for (int b = 0; b < NB && e == cudaSuccess; ++b) step(cudaStreamWaitEvent(st[b], ready, 0));
+    auto copy2d = [&](double *dst, i64 ldd, const double *src, i64 lds, i64 nv, cudaMemcpyKind kind, cudaStream_t s_) {
+        if (ldd == n && lds == n) return cudaMemcpyAsync(dst, src, sizeof(double) * n * nv, kind, s_);
+        return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * n, nv, kind, s_);
+    };
+    i64 t = 0;
+    for (i64 p0 = 0; p0 < P && e == cudaSuccess && rc == CB_OK; p0 += tp, ++t) {
+        const int b = (int)(t % NB);
+        const i64 np = p0 + tp <= P ? tp : P - p0;
+        if (Pf > 1) step(copy2d(df[b], n, f_host + p0 * ldf, ldf, np, cudaMemcpyHostToDevice, st[b]));
+        if (Pg > 1 && e == cudaSuccess) step(copy2d(dg[b], n, g_host + p0 * ldg, ldg, np, cudaMemcpyHostToDevice, st[b]));
+        if (e == cudaSuccess)
+            rc = cb_density_apply(D, Pf > 1 ? df[b] : f1, n, Pf > 1 ? np : 1, Pg > 1 ? dg[b] : g1, n, Pg > 1 ? np : 1, conj, dr[b], n, st[b]);
+        if (e == cudaSuccess && rc == CB_OK) step(copy2d(rho_host + p0 * ldr, ldr, dr[b], n, np, cudaMemcpyDeviceToHost, st[b]));
+    }
+    for (int b = 0; b < NB; ++b) {
+        if (st[b]) { cudaError_t e2 = cudaStreamSynchronize(st[b]); if (e == cudaSuccess) e = e2; cudaStreamDestroy(st[b]); }
+        cudaFree(df[b]); cudaFree(dg[b]); cudaFree(dr[b]);
+    }
+    cudaFree(f1); cudaFree(g1);
+    if (ready) cudaEventDestroy(ready);
+    if (e != cudaSuccess) { cb_set_error("cb_density_apply_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return rc;
+}
+
 // B \ f (src/bsplines.jl:329-343): the reference solves the sparse least-squares problem  V c = f(x)  at the
 // quadrature nodes (unweighted), i.e. c = (V'V)^-1 V' f(x) — the plan's Gram factor with a plain V' f right-hand side.
 int cb_density_project(const cb_density *D, const double *fvals, i64 ldf, i64 P, double *coef, i64 ldc, void *stream) {

@@ -95,6 +95,22 @@ class FunctionProduct:
         self._last = (f, g)
         return rho
 
+    def copyto_host(self, f: np.ndarray, g: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Host-buffer form (``cb_density_apply_host``, B-spline branch): Fortran-ordered (n, P) numpy arrays (pinned
+        for PCIe speed); the pair batch is streamed through the device in tiles."""
+        if not self.handle:
+            raise NotImplementedError("host-buffer form exists for the B-spline branch")
+        f = np.asfortranarray(f.reshape(self.n, -1), dtype=np.float64) if not f.flags.f_contiguous else f.reshape(self.n, -1, order="F")
+        g = np.asfortranarray(g.reshape(self.n, -1), dtype=np.float64) if not g.flags.f_contiguous else g.reshape(self.n, -1, order="F")
+        P = max(f.shape[1], g.shape[1])
+        out = np.empty((self.n, P), order="F") if out is None else out
+        assert out.flags.f_contiguous and out.shape == (self.n, P)
+        with torch.cuda.device(self.device):
+            _lib.call("cb_density_apply_host", self.handle, C.c_void_p(f.ctypes.data), f.shape[0], f.shape[1],
+                      C.c_void_p(g.ctypes.data), g.shape[0], g.shape[1], int(self.conjugated), C.c_void_p(out.ctypes.data),
+                      out.shape[0], _stream())
+        return out
+
     def matrix(self):
         """``copyto!(M, rho)`` (src/densities.jl:202-208): the operator of multiplication by the
         density, ``overlap_matrix!(M, L', R, Diagonal(rho.tmp))`` for B-splines."""

@@ -12,7 +12,9 @@ import torch
 
 from . import _lib
 from .lazy import AdjointBasis, CoulombDerivative, Derivative, QuasiDiagonal
-from .operators import Diagonal, ImplicitDerivative, SymTridiagonal, Tridiagonal, _ptr, _stream, device_of, to_device
+from ._lib import DimensionMismatch
+from .operators import (BandedMatrix, Diagonal, ImplicitDerivative, SymTridiagonal, Tridiagonal, _ptr, _stream, device_of,
+                        to_device)
 
 CARTESIAN, STAGGERED_UNIFORM, STAGGERED_NONUNIFORM = 0, 1, 2
 
@@ -58,66 +60,112 @@ class _FDOrRestricted:
         # derivative_matrix, src/fd_derivatives.jl:200-203
         if not isinstance(L, _FDOrRestricted) or L.parent_basis != P:
             raise ValueError("Cannot multiply functions on different grids")
-        if (L.first, L.last) != (self.first, self.last):
-            raise NotImplementedError("FD operators between different restrictions (3-band BandedMatrix)")
+        same = (L.first, L.last) == (self.first, self.last)
         mid = list(middle)
         n, i0 = self.size(), self.first - 1
+        m, r0 = L.size(), L.first - 1
+        implicit = getattr(P, "implicit", False)
         if not mid:                                   # src/finite_differences.jl:141-143
+            if not same:
+                raise NotImplementedError("mass matrix between different restrictions")
             return Diagonal(torch.full((n,), P.mass_value(), dtype=torch.float64, device=P.device))
         if all(isinstance(f, QuasiDiagonal) for f in mid):   # src/fd_operators.jl:3-35
             d = None
             for f in mid:
-                v = P.nodal_values(f.diag)[i0:i0 + n]
+                v = P.nodal_values(f.diag)
                 d = v if d is None else d * v
-            return Diagonal(d.contiguous())
+            if same:
+                return Diagonal(d[i0:i0 + n].contiguous())
+            # different restrictions (:20-35): a single-band BandedMatrix with (l, u) = (-offset, offset),
+            # offset = first(A) - first(B), holding the function at the common nodes
+            off = r0 - i0
+            lo, hi = max(r0, i0), min(r0 + m, i0 + n)
+            band = torch.zeros((n, 1), dtype=torch.float64, device=P.device)
+            if hi > lo:
+                band[lo - i0:hi - i0, 0] = d[lo:hi]
+            return BandedMatrix(band.contiguous(), m, n, -off, off)
         Z, ell = 0.0, 0
         ders = [f for f in mid if isinstance(f, (Derivative, CoulombDerivative))]
+        coulomb = any(isinstance(f, CoulombDerivative) for f in ders)
         for f in ders:
             if isinstance(f, CoulombDerivative):
                 Z, ell = f.Z, f.ell
         weights = [f for f in mid if isinstance(f, QuasiDiagonal)]
         if len(ders) == 1 and not ders[0].adjoint and not weights:
             nder = 1
-            if Z != 0.0:
-                raise NotImplementedError("gradient_correction! (CoulombDerivative of first order)")
         elif len(ders) == 2 and ders[0].adjoint and not ders[1].adjoint and mid[0] is ders[0] and mid[-1] is ders[1]:
             nder = 2
         else:
             raise NotImplementedError(f"no materialiser for {middle}")
-        if getattr(P, "implicit", False) and not P.uniform:
-            # non-uniform compact scheme (Patchkovskii 2016, Eq. 33): both sides come from the three local steps
-            # a, b, c around a node (implicit_stencil_common, src/fd_derivatives.jl:105-150, :410-424)
+        at_origin = L.first == 1 and self.first == 1   # corrections only touch the [1,1] corner (:521-534, :596-643)
+        # explicit schemes: gradient_correction! is the identity (:485), laplacian_correction! exists for the staggered
+        # grids (:542-551) and is applied on the device
+        Zdev = Z if (nder == 2 and at_origin) else 0.0
+        if implicit and not same:                     # implicit_derivative, :426-430
+            raise DimensionMismatch("DimensionMismatch: Implicit finite-differences does not support different restrictions")
+        if implicit and not P.uniform:
+            # non-uniform compact scheme (Patchkovskii 2016, Eq. 33): both sides come from the local steps around a
+            # node (implicit_stencil_common, src/fd_derivatives.jl:105-150, :410-424), computed by cb_fd_implicit_stencils
             if nder != 2:
                 raise NotImplementedError("the reference has no first-derivative left-hand side on non-uniform grids (src/fd_derivatives.jl:411)")
-            if Z != 0.0:
-                raise NotImplementedError("CoulombDerivative corrections of the implicit scheme (src/fd_derivatives.jl:553-667)")
-            st = P.nonuniform_stencils()
-            sl = slice(i0, i0 + n)
-            so = slice(i0, i0 + n - 1)
-            dev = lambda a: to_device(np.ascontiguousarray(a), P.device)
-            Delta = Tridiagonal(dev(st["alpha_t"][so]), dev(-2.0 * st["beta"][sl]), dev(st["alpha"][so]))   # step = 1
-            M = Tridiagonal(dev(st["m_dl"][so]), dev(st["m_d"][sl]), dev(st["m_du"][so]))
+            new = lambda k: torch.empty(max(k, 0), dtype=torch.float64, device=P.device)
+            at, al, be, mdl, md, mdu = new(n - 1), new(n - 1), new(n), new(n - 1), new(n), new(n - 1)
+            _lib.call("cb_fd_implicit_stencils", _ptr(P.d_nodes), P.N, i0, n, _ptr(at), _ptr(al), _ptr(be), _ptr(mdl), _ptr(md),
+                      _ptr(mdu), _stream())
+            Delta = Tridiagonal(at, -2.0 * be, al)                     # step(::NonUniform) = 1
+            M = Tridiagonal(mdl, md, mdu)
+            if coulomb and at_origin and Z != 0.0:
+                # laplacian_correction!(::ImplicitDerivative, ::NonUniform, ...), :573-593, Eq. (34)
+                if ell != 0:
+                    raise NotImplementedError("the reference's Eq. (35) branch (l != 0) throws UndefVarError (src/fd_derivatives.jl:587)")
+                a = float(P.r[0])
+                b = float(P.r[1]) - a
+                num = b * (a * (3 * a + 4 * b) * Z - 6 * (a + b))
+                Delta.d[0] = 2 * (a + b) * (6 * a - (3 * a - b) * (a + b) * Z) / (a ** 2 * num)
+                M.d[0] = (a + b) * (a * (a + b) * (a + 3 * b) * Z - 3 * (a ** 2 + 3 * b * a + b ** 2)) / (3 * a * num)
+                if n > 1:
+                    M.du[0] = (a ** 3 * (-Z) + a ** 2 * (b * Z + 3) + b * a * (2 * b * Z - 3) - 3 * b ** 2) / (3 * num)
             return ImplicitDerivative(Delta, M)
         fhalf = None
         if weights:                                   # src/fd_derivatives.jl:292-319
             if P.scheme != STAGGERED_NONUNIFORM or len(weights) != 1:
                 raise NotImplementedError("weighted Laplacian exists for non-uniform staggered grids only")
+            if not same:
+                raise NotImplementedError("the reference's weighted Laplacian between different restrictions is commented out (src/fd_derivatives.jl:320-331)")
             fhalf = P.half_node_values(weights[0].diag)
+        if not same:
+            # derivative_matrix (:214-219): BandedMatrix{T}(undef, (m, n), (1 - offset, 1 + offset)), filled band by
+            # band from the parent's stencils (:244-249, :278-289)
+            off = r0 - i0
+            dest = BandedMatrix.undef(m, n, 1 - off, 1 + off, P.device)
+            _lib.call("cb_fd_derivative_banded", P.scheme, nder, _ptr(P.d_r), None, P.N, P.step, r0, m, i0, n, Zdev, ell,
+                      _ptr(dest.data), _stream())
+            return dest
         dl = torch.empty(max(n - 1, 0), dtype=torch.float64, device=P.device)
         d = torch.empty(n, dtype=torch.float64, device=P.device)
         du = dl if nder == 2 else torch.empty_like(dl)
-        _lib.call("cb_fd_derivative", P.scheme, nder, _ptr(P.d_r), _ptr(fhalf), P.N, P.step, i0, n, Z, ell,
+        _lib.call("cb_fd_derivative", P.scheme, nder, _ptr(P.d_r), _ptr(fhalf), P.N, P.step, i0, n, Zdev, ell,
                   _ptr(dl), _ptr(d), None if nder == 2 else _ptr(du), _stream())
         Delta = SymTridiagonal(d, dl) if nder == 2 else Tridiagonal(dl, d, du)
-        if getattr(P, "implicit", False):
+        if implicit:
             # implicit_derivative, src/fd_derivatives.jl:426-432: the explicit stencil becomes the right-hand side
             # Delta, implicit_lhs (:402-424, uniform grids) the left-hand side M
-            if Z != 0.0:
-                raise NotImplementedError("CoulombDerivative corrections of the implicit scheme (src/fd_derivatives.jl:553-667)")
             dv, ev = (4.0 / 6.0, 1.0 / 6.0) if nder == 1 else (10.0 / 12.0, 1.0 / 12.0)
-            M = SymTridiagonal(torch.full((n,), dv, dtype=torch.float64, device=P.device),
-                               torch.full((max(n - 1, 0),), ev, dtype=torch.float64, device=P.device))
-            return ImplicitDerivative(Delta, M)
+            Md = torch.full((n,), dv, dtype=torch.float64, device=P.device)
+            Me = torch.full((max(n - 1, 0),), ev, dtype=torch.float64, device=P.device)
+            if coulomb and at_origin:
+                rho = P.step
+                if nder == 1:
+                    # gradient_correction!(::ImplicitDerivative, ::Uniform, ...), :487-499 (Muller 1999, Eq. 20ff):
+                    # applied whatever Z and l are
+                    Delta.d[0] += (np.sqrt(3.0) - 2) / (2 * rho)
+                    Md[0] += (np.sqrt(3.0) - 2) / 6
+                elif ell == 0 and Z != 0.0:
+                    # laplacian_correction!(::ImplicitDerivative, ::Uniform, ...), :553-565 (Muller 1999, Eq. 17)
+                    db1 = -Z * rho / (12 - 10 * Z * rho)
+                    Delta.d[0] -= 2 * db1 / rho ** 2
+                    Md[0] -= 2 * db1 / ((-6) * (-2))
+            return ImplicitDerivative(Delta, SymTridiagonal(Md, Me))
         return Delta
 
 
@@ -137,6 +185,13 @@ class AbstractFiniteDifferences(_FDOrRestricted):
         """Node vector on the device (only the non-uniform scheme reads it)."""
         if self.scheme != STAGGERED_NONUNIFORM:
             return None
+        if self._d_r is None:
+            self._d_r = to_device(self.r, self.device)
+        return self._d_r
+
+    @property
+    def d_nodes(self):
+        """Node vector on the device (any scheme)."""
         if self._d_r is None:
             self._d_r = to_device(self.r, self.device)
         return self._d_r
@@ -181,25 +236,6 @@ class FiniteDifferences(AbstractFiniteDifferences):
         self._setup(np.arange(1, n + 1, dtype=np.float64) * dx, dx, device)
 
 
-def implicit_stencil_common(r, fun, s=1, dN=0):
-    """``implicit_stencil_common(fun, B, s, dN)`` (src/fd_derivatives.jl:105-125): ``fun(a, b, c)`` of the three
-    consecutive local steps around every node, the grid continued by one mirrored point at the end and starting from
-    the origin."""
-    r = np.asarray(r, dtype=np.float64)
-    N = r.size
-    v = np.zeros(N + dN)
-    rt = np.concatenate([r[s - 1:], [2 * r[-1] - r[-2]]])
-    a = rt[0] - (r[s - 2] if s > 1 else 0.0)
-    b = rt[1] - rt[0]
-    c = 0.0
-    for j in range(1, N + dN + 1):
-        if j < N - (s - 1):
-            c = rt[j + 1] - rt[j]
-        v[j - 1] = fun(a, b, c)
-        a, b = b, c
-    return v
-
-
 class ImplicitFiniteDifferences(AbstractFiniteDifferences):
     """``ImplicitFiniteDifferences(n, rho)``: compact (implicit) finite differences on the uniform grid rho*(1:n), or
     ``ImplicitFiniteDifferences(r)`` on arbitrary non-decreasing nodes (src/finite_differences.jl:303-342).  Derivatives
@@ -218,22 +254,6 @@ class ImplicitFiniteDifferences(AbstractFiniteDifferences):
                 raise ValueError("Node locations must be non-decreasing")
             self.uniform = False
             self._setup(r, 1.0, device)                # step(::NonUniform) = 1
-        self._stencils = None
-
-    def nonuniform_stencils(self):
-        """alpha~, alpha, beta (Eq. 33; src/fd_derivatives.jl:127-143) and the left-hand side of the second derivative
-        (implicit_lhs, :410-424)."""
-        if self._stencils is None:
-            r = self.r
-            self._stencils = {
-                "alpha_t": implicit_stencil_common(r, lambda a, b, c: 2 / (a * (a + b)), 2, -1),
-                "alpha": implicit_stencil_common(r, lambda a, b, c: 2 / (b * (a + b)), 1, -1),
-                "beta": implicit_stencil_common(r, lambda a, b, c: 1 / (a * b)),
-                "m_dl": implicit_stencil_common(r, lambda a, b, c: (a * a + a * b - b * b) / (6 * a * (a + b)), 2, -1),
-                "m_d": implicit_stencil_common(r, lambda a, b, c: (a * a + 3 * a * b + b * b) / (6 * a * b)),
-                "m_du": implicit_stencil_common(r, lambda a, b, c: (-a * a + a * b + b * b) / (6 * b * (a + b)), 1, -1),
-            }
-        return self._stencils
 
     def vandermonde_diag(self):
         return None if self.uniform else self._nonuniform_weights()

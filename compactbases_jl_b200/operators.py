@@ -113,7 +113,13 @@ class BandedMatrix:
         return (self.m, self.n)
 
     def bandwidths(self):
-        return (self.l, self.u)
+        """``bandwidths(A)`` as BandedMatrices reports them: clamped to the matrix size (a band that lies entirely
+        outside an m x n matrix gives an empty ``bandrange``; test/fd/derivatives.jl:36-59 counts on it)."""
+        return (min(self.l, self.m - 1), min(self.u, self.n - 1))
+
+    def bandrange(self):
+        l, u = self.bandwidths()
+        return range(-l, u + 1)
 
     def dense(self) -> np.ndarray:
         band = self.data.cpu().numpy()

@@ -117,10 +117,72 @@ def _global_rank(r, group):
     return r if group is None else dist.get_global_rank(group, r)
 
 
+class Comm:
+    """``cb_comm`` of this rank: the peer-mapped mailboxes of the fused halo exchange (``csrc/comm.cu``).  With one
+    process per GPU the 64-byte handles are all-gathered through ``torch.distributed`` (any backend; the data path
+    itself is plain stores over NVLink from inside the assembly kernel)."""
+
+    def __init__(self, rank: int, world: int, group=None, connect: bool = True):
+        from . import _lib
+        self.rank, self.world = rank, world
+        h = C.c_void_p()
+        _lib.call("cb_comm_create", rank, world, C.byref(h))
+        self.handle = h
+        if connect and world > 1:
+            buf = (C.c_char * 64)()
+            _lib.call("cb_comm_export", self.handle, C.cast(buf, C.c_void_p))
+            mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            backend = dist.get_backend(group)
+            dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            parts = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(parts, mine.to(dev), group=group)
+            allh = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+            self._handles = C.create_string_buffer(allh, 64 * world)
+            _lib.call("cb_comm_connect", self.handle, C.cast(self._handles, C.c_void_p))
+            dist.barrier(group=group)               # every mailbox is mapped before anyone pushes
+
+    @staticmethod
+    def connect_local(comms):
+        """Single-process form: ``comms[r]`` was created (``connect=False``) with the device of rank r current."""
+        from . import _lib
+        arr = (C.c_void_p * len(comms))(*[c.handle for c in comms])
+        _lib.call("cb_comm_connect_local", arr, len(comms))
+
+    def status(self) -> int:
+        from . import _lib
+        from .operators import _stream
+        st = C.c_int(0)
+        _lib.call("cb_comm_status", self.handle, C.byref(st), _stream())
+        return st.value
+
+    def shard(self, R, rank=None) -> IntervalShard:
+        """``cb_interval_shard`` of this (or another) rank for the columns of the (restricted) basis R."""
+        from . import _lib
+        v = [C.c_int64() for _ in range(5)]
+        _lib.call("cb_interval_shard", R.parent_basis.handle, R.col0, R.ncols, self.rank if rank is None else rank, self.world,
+                  *[C.byref(x) for x in v])
+        s_lo, s_hi, own_lo, own_hi, touch_lo = (x.value for x in v)
+        return IntervalShard(s_lo, s_hi, own_lo, own_hi, touch_lo, own_hi)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                from . import _lib
+                _lib.load().cb_comm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
 def assemble_interval_sharded(L, R, a: int, b: int, rank: int, world: int, opvals: torch.Tensor | None = None,
-                              coulomb_Z: float | None = None, halo: str = "exchange", group=None):
+                              coulomb_Z: float | None = None, halo: str = "exchange", group=None, comm: Comm | None = None,
+                              out: torch.Tensor | None = None):
     """Interval-sharded ``diffop!`` on this rank's GPU.  Returns (own_lo, own_hi, cols) where ``cols``
-    is the [own_hi-own_lo, l+u+1] slice of the BandedMatrix data that this rank owns."""
+    is the [own_hi-own_lo, l+u+1] slice of the BandedMatrix data that this rank owns.
+
+    halo: "fused" — the exchange happens inside the assembly kernel through peer-mapped mailboxes
+    (``cb_bspline_assemble_sharded``, needs ``comm``); "recompute" — no communication; "exchange" — the library-external
+    baseline: partial bands + one NCCL send/recv per neighbour + add (kept for comparison and for the CPU tests)."""
     from . import _lib
     from .bsplines import band_shape
     from .operators import _ptr, _stream
@@ -133,6 +195,13 @@ def assemble_interval_sharded(L, R, a: int, b: int, rank: int, world: int, opval
     dev = PR.device
     cz = 0.0 if coulomb_Z is None else float(coulomb_Z)
     cflag = 0 if coulomb_Z is None else 1
+    if comm is not None and halo in ("fused", "recompute"):
+        cols = out if out is not None else torch.empty((sh.own_hi - sh.own_lo, W), dtype=torch.float64, device=dev)
+        _lib.call("cb_bspline_assemble_sharded", comm.handle, PL.handle, PR.handle, a, b, _ptr(opvals), cflag, cz, L.col0, L.ncols,
+                  R.col0, R.ncols, l, u, 0 if halo == "fused" else 1, _ptr(cols), _stream())
+        return sh.own_lo, sh.own_hi, cols
+    if halo == "fused":
+        raise ValueError("halo='fused' needs a Comm")
     if halo == "recompute" or world == 1:
         cols = torch.empty((sh.own_hi - sh.own_lo, W), dtype=torch.float64, device=dev)
         _lib.call("cb_bspline_assemble_part", PL.handle, PR.handle, a, b, _ptr(opvals), cflag, cz, L.col0, L.ncols,

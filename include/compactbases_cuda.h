@@ -139,6 +139,11 @@ int cb_bspline_assemble_part(const cb_bspline *L, const cb_bspline *R, int a, in
                              cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n, int l, int u,
                              cb_i64 col_lo, cb_i64 col_hi, cb_i64 s_lo, cb_i64 s_hi,
                              double *band_cols, void *stream);
+/* Host-pointer form: band_host is the data of a host BandedMatrix ((l+u+1) x n), opvals_host NULL or numnodes
+ * doubles; coulomb 0 / 1 as in cb_bspline_assemble_part.  Synchronous (returns when band_host is complete). */
+int cb_bspline_assemble_host(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals_host,
+                             int coulomb, double Z, cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n, int l, int u,
+                             double *band_host, void *stream);
 /* BandedMatrix(l=u=1) -> Tridiagonal(dl,d,du): the k == 2 && m == n case of
  * Matrix(undef, A, B) (src/bsplines.jl:258-262). */
 int cb_band_to_tridiag(const double *band, cb_i64 n, double *dl, double *d, double *du, void *stream);
@@ -235,6 +240,23 @@ int cb_fd_derivative(int scheme, int nder, const double *r, const double *fhalf,
                      double Z, int ell,
                      double *dl, double *d, double *du, void *stream);
 
+/* The same operators between DIFFERENT restrictions A = R[:, rowi0+1 : rowi0+m] and B = R[:, colj0+1 : colj0+n]
+ * (derivative_matrix, src/fd_derivatives.jl:214-219; band fills :244-249, :278-289): the destination is a
+ * BandedMatrix{T}(undef, (m, n), (1 - offset, 1 + offset)), offset = rowi0 - colj0; band is its data, 3 x n
+ * column-major (slots outside the matrix are zeroed).  The Coulomb correction is applied only when both
+ * restrictions start at the first node (:620-622). */
+int cb_fd_derivative_banded(int scheme, int nder, const double *r, const double *fhalf, cb_i64 N, double step,
+                            cb_i64 rowi0, cb_i64 m, cb_i64 colj0, cb_i64 n, double Z, int ell,
+                            double *band, void *stream);
+/* ImplicitFiniteDifferences on a non-uniform grid (Patchkovskii & Muller 2016): implicit_stencil_common and its
+ * callers (src/fd_derivatives.jl:105-143, implicit_lhs :410-424) for nodes i0+1 .. i0+n of r[N]:
+ *   alpha_t[n-1], alpha[n-1], beta[n]   right-hand side  Tridiagonal(alpha_t, -2 beta, alpha)
+ *   m_dl[n-1], m_d[n], m_du[n-1]        left-hand side   Tridiagonal(m_dl, m_d, m_du)
+ * with the reference's order of operations (bit-identical to a scalar evaluation). */
+int cb_fd_implicit_stencils(const double *r, cb_i64 N, cb_i64 i0, cb_i64 n,
+                            double *alpha_t, double *alpha, double *beta,
+                            double *m_dl, double *m_d, double *m_du, void *stream);
+
 /* ------------------------------------------------------------------------
  * Operator application  Y = alpha*A*X + beta*Y  (mul!; call
  * sites src/linear_operators.jl:40,50-52, src/inner_products.jl:30,46).
@@ -293,6 +315,12 @@ int cb_density_set_refine(cb_density *D, int steps);
 int cb_density_apply(const cb_density *D, const double *f, cb_i64 ldf, cb_i64 Pf,
                      const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
                      double *rho, cb_i64 ldr, void *stream);
+/* Host-pointer form: f_host, g_host, rho_host in (preferably pinned) host memory; the pair batch is streamed through
+ * the device in tiles (copies and kernels of consecutive tiles overlap).  `stream`: producer stream, see
+ * cb_fedvr_apply_host.  Returns when rho_host is complete. */
+int cb_density_apply_host(const cb_density *D, const double *f_host, cb_i64 ldf, cb_i64 Pf,
+                          const double *g_host, cb_i64 ldg, cb_i64 Pg, int conj,
+                          double *rho_host, cb_i64 ldr, void *stream);
 /* ftmp .* gtmp at the quadrature nodes (src/densities.jl:158-161), the
  * rho.tmp that copyto!(M, rho) (:206-208) feeds to overlap_matrix! as the
  * diagonal operator: pass it as `opvals` to cb_bspline_assemble.
@@ -337,6 +365,39 @@ typedef struct cb_bandlu_s cb_bandlu;
 int cb_bandlu_create(const double *band, cb_i64 n, int l, int u, cb_bandlu **out, void *stream);
 int cb_bandlu_solve(const cb_bandlu *F, double *X, cb_i64 ldx, cb_i64 nvec, void *stream);
 int cb_bandlu_destroy(cb_bandlu *F);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU (the reference is single-process, so these entries have no reference counterpart).
+ * Point, vector and pair batches are split into contiguous ranges with no communication (cb_batch_range).  Only the
+ * interval-sharded band assembly exchanges data: the k-1 boundary columns of neighbouring interval ranges.  That
+ * exchange is fused into the assembly kernel: a rank stores the partial columns of its left neighbour directly into
+ * the neighbour's mailbox (peer GPU memory mapped into this process, NVLink / NVSwitch) and raises a flag; the owner's
+ * last tiles add the mailbox.  No NCCL call, no host round trip.
+ *
+ * One process per GPU:   cb_comm_create -> cb_comm_export (64 bytes) -> host all-gather -> cb_comm_connect.
+ * One process, N GPUs:   cb_comm_create per device -> cb_comm_connect_local.
+ * ---------------------------------------------------------------------- */
+typedef struct cb_comm_s cb_comm;
+int cb_batch_range(cb_i64 n, int rank, int world, cb_i64 *lo, cb_i64 *hi);
+int cb_comm_create(int rank, int world, cb_comm **out);          /* on the current device */
+int cb_comm_export(const cb_comm *c, void *handle64);            /* cudaIpcMemHandle_t of this rank's mailbox */
+int cb_comm_connect(cb_comm *c, const void *all_handles);        /* world x 64 bytes, rank order */
+int cb_comm_connect_local(cb_comm **comms, int world);
+int cb_comm_status(const cb_comm *c, int *status, void *stream); /* non-zero: a wait for a neighbour timed out */
+int cb_comm_destroy(cb_comm *c);
+/* The share of rank `rank`: t.t intervals [s_lo, s_hi), owned columns [own_lo, own_hi) (those whose first interval
+ * lies in the range), and touch_lo <= own_lo, the first column with any support in the range (0-based, relative to
+ * the restriction colR0+1 .. colR0+n of R). */
+int cb_interval_shard(const cb_bspline *R, cb_i64 colR0, cb_i64 n, int rank, int world,
+                      cb_i64 *s_lo, cb_i64 *s_hi, cb_i64 *own_lo, cb_i64 *own_hi, cb_i64 *touch_lo);
+/* cb_bspline_assemble for this rank's share: own_cols = columns own_lo .. own_hi-1 of the BandedMatrix data.
+ * halo 0: exchange fused into the kernel (every rank must make the same sequence of such calls; needs at least k
+ * intervals per rank); halo 1: recompute the k-1 boundary intervals instead (no communication).
+ * coulomb: 0 = opvals / none, 1 = op(x) = -Z/x. */
+int cb_bspline_assemble_sharded(cb_comm *c, const cb_bspline *L, const cb_bspline *R, int a, int b,
+                                const double *opvals, int coulomb, double Z,
+                                cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n, int l, int u,
+                                int halo, double *own_cols, void *stream);
 
 #ifdef __cplusplus
 }

@@ -786,6 +786,38 @@ def inner_products(U, V, S=None, scale=1.0):
     return scale * np.einsum("ip,ip->p", U, W)
 
 
+def implicit_stencil_common(r, fun, s=1, dN=0):
+    """``implicit_stencil_common(fun, B, s, dN)`` (src/fd_derivatives.jl:105-125), the reference's own loop: ``fun(a, b, c)``
+    of the three consecutive local steps around every node, the grid continued by one mirrored point at the end and
+    starting from the origin."""
+    r = np.asarray(r, dtype=np.float64)
+    N = r.size
+    v = np.zeros(N + dN)
+    rt = np.concatenate([r[s - 1:], [2 * r[-1] - r[-2]]])
+    a = rt[0] - (r[s - 2] if s > 1 else 0.0)
+    b = rt[1] - rt[0]
+    c = 0.0
+    for j in range(1, N + dN + 1):
+        if j < N - (s - 1):
+            c = rt[j + 1] - rt[j]
+        v[j - 1] = fun(a, b, c)
+        a, b = b, c
+    return v
+
+
+IMPLICIT_STENCIL_FUNS = {   # name -> (fun, s, dN): src/fd_derivatives.jl:127-143 (Eq. 33) and implicit_lhs :410-424
+    "alpha_t": (lambda a, b, c: 2 / (a * (a + b)), 2, -1), "alpha": (lambda a, b, c: 2 / (b * (a + b)), 1, -1),
+    "beta": (lambda a, b, c: 1 / (a * b), 1, 0),
+    "m_dl": (lambda a, b, c: (a * a + a * b - b * b) / (6 * a * (a + b)), 2, -1),
+    "m_d": (lambda a, b, c: (a * a + 3 * a * b + b * b) / (6 * a * b), 1, 0),
+    "m_du": (lambda a, b, c: (-a * a + a * b + b * b) / (6 * b * (a + b)), 1, -1)}
+
+
+def implicit_stencils_loop(r):
+    """All six stencil vectors by the reference's loop."""
+    return {k: implicit_stencil_common(r, f, s, dn) for k, (f, s, dn) in IMPLICIT_STENCIL_FUNS.items()}
+
+
 def implicit_stencils_nonuniform(r):
     """Patchkovskii's non-uniform compact stencils (src/fd_derivatives.jl:105-143 alpha~, alpha, beta of Eq. 33 and
     implicit_lhs :410-424) in closed form on the local steps h_j = r_j - r_{j-1}, r_0 = 0, r_{N+1} = 2 r_N - r_{N-1}."""

@@ -162,20 +162,16 @@ def test_band_algebra_host_logic():
     assert np.allclose((cb.as_banded(T) + Dg).dense(), T.dense() + np.diag(d))
 
 
-def test_implicit_stencils_host_equals_closed_form():
-    """implicit_stencil_common (the reference's loop, src/fd_derivatives.jl:105-125, in the host mirror) against the
-    oracle's closed form on the local steps, and the uniform-grid limits alpha = beta = 1/h^2, M = (1, 10, 1)/12."""
-    from compactbases_jl_b200.finite_differences import implicit_stencil_common
+def test_implicit_stencils_loop_equals_closed_form():
+    """The oracle's restatement of the reference's loop (implicit_stencil_common, src/fd_derivatives.jl:105-125) against
+    its closed form on the local steps, and the uniform-grid limits alpha = beta = 1/h^2, M = (1, 10, 1)/12.  (The
+    product computes these on the device: cb_fd_implicit_stencils, checked bit for bit in tests/test_gpu_next_rows.py.)"""
     j = np.arange(1, 60)
     r = 0.05 * j + 0.002 * j ** 2
     st = cbo.implicit_stencils_nonuniform(r)
-    funs = {"alpha_t": (lambda a, b, c: 2 / (a * (a + b)), 2, -1), "alpha": (lambda a, b, c: 2 / (b * (a + b)), 1, -1),
-            "beta": (lambda a, b, c: 1 / (a * b), 1, 0),
-            "m_dl": (lambda a, b, c: (a * a + a * b - b * b) / (6 * a * (a + b)), 2, -1),
-            "m_d": (lambda a, b, c: (a * a + 3 * a * b + b * b) / (6 * a * b), 1, 0),
-            "m_du": (lambda a, b, c: (-a * a + a * b + b * b) / (6 * b * (a + b)), 1, -1)}
-    for name, (f, s, dn) in funs.items():
-        np.testing.assert_array_equal(implicit_stencil_common(r, f, s, dn), st[name])
+    lp = cbo.implicit_stencils_loop(r)
+    for name in st:
+        np.testing.assert_array_equal(lp[name], st[name])
     h = 0.25
     u = cbo.implicit_stencils_nonuniform(h * np.arange(1, 12))
     np.testing.assert_allclose(u["alpha"], 1 / h ** 2, rtol=1e-14)

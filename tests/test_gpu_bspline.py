@@ -327,3 +327,42 @@ def test_errors(cb):
         cb.BSpline(cb.LinearKnotSet(17, 0, 1, 4))
     with pytest.raises(IndexError):
         B3[:, 0:3]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_fused_halo_exchange_single_device_emulation(cb, world):
+    """cb_bspline_assemble_sharded with halo = exchange (the in-kernel mailbox exchange of csrc/comm.cu): all ranks'
+    communicators live on this one GPU (cb_comm_connect_local) and the ranks run one after the other from right to
+    left, so that no kernel ever waits for one that has not run (a rank's pushes only go left).  Several rounds
+    exercise the double-buffered mailboxes and the ack words.  The real concurrent multi-GPU run is
+    scripts/mgpu_check.py (gpurun --gpus N)."""
+    import torch
+    from compactbases_jl_b200.sharding import Comm, assemble_interval_sharded, interval_shards
+    D = cb.Derivative()
+    cases = [(cb.BSpline(cb.ExpKnotSet(10, -3.0, 2.0, 3000)), None), (cb.BSpline(cb.LinearKnotSet(7, 0, 10, 400)), (2, 390)),
+             (cb.BSpline(cb.LinearKnotSet(4, 0, 1, 64, ml=1, mr=4)), None)]
+    for B, sel in cases:
+        R = B if sel is None else B[:, sel[0]:sel[1]]
+        comms = [Comm(r, world, connect=False) for r in range(world)]
+        Comm.connect_local(comms)
+        full = {"T": (R.T @ D.T @ D @ R).data, "V": (R.T @ cb.CoulombPotential(1.0) @ R).data}
+        shards = interval_shards(B.t.numintervals(), B.k, B.t.ml, R.col0, R.ncols, world)
+        for rnd in range(5):
+            for name, (a, b_, cz) in (("T", (1, 1, None)), ("V", (0, 0, 1.0))):
+                got = torch.full_like(full[name], float("nan"))
+                for r in reversed(range(world)):
+                    sh = comms[r].shard(R)
+                    assert (sh.s_lo, sh.s_hi, sh.own_lo, sh.own_hi, sh.touch_lo) == \
+                        (shards[r].s_lo, shards[r].s_hi, shards[r].own_lo, shards[r].own_hi, shards[r].touch_lo)
+                    lo, hi, cols = assemble_interval_sharded(R, R, a, b_, r, world, coulomb_Z=cz, halo="fused", comm=comms[r])
+                    got[lo:hi] = cols
+                torch.cuda.synchronize()
+                assert all(c.status() == 0 for c in comms)
+                err = float((got - full[name]).abs().max() / full[name].abs().max())
+                assert err <= 1e-14, (B.k, world, rnd, name, err)
+        # recompute mode through the same entry: bit-identical to the single-GPU band
+        got = torch.empty_like(full["T"])
+        for r in range(world):
+            lo, hi, cols = assemble_interval_sharded(R, R, 1, 1, r, world, halo="recompute", comm=comms[r])
+            got[lo:hi] = cols
+        assert torch.equal(got, full["T"])

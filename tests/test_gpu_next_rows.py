@@ -520,3 +520,253 @@ def test_hydrogen_staggered_fd_reference_levels(cb):
     # orthogonal iteration converges like (theta_7 / theta_k)^iterations: fast for the two lowest levels only
     theta = _subspace_eigs(M, N, 2, 150, 5)
     np.testing.assert_allclose(sigma + 1.0 / theta, vals[:2], rtol=0, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------------------------
+# Finite differences: operators between different restrictions, Coulomb corrections of the implicit scheme,
+# device stencils of the non-uniform compact scheme
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("make", [lambda cb: cb.StaggeredFiniteDifferences(10, 1.0),
+                                  lambda cb: cb.FiniteDifferences(10, 0.7),
+                                  lambda cb: cb.StaggeredFiniteDifferences(0.1 * np.arange(1, 11) ** 1.5)],
+                         ids=["staggered", "cartesian", "staggered-nonuniform"])
+def test_fd_operators_between_different_restrictions(cb, make):
+    """test/fd/derivatives.jl:24-61: Ra'D*Rb == Matrix(grad)[sela, selb] (same for the Laplacian) for every pair of the
+    five restrictions, a BandedMatrix whose bandrange has min(3, |overlap| + 1) bands (0 without overlap)."""
+    R = make(cb)
+    D = cb.Derivative()
+    grad, lap = (R.T @ D @ R).dense(), (R.T @ D.T @ D @ R).dense()
+    sels = [(1, 10), (3, 6), (8, 10), (5, 10), (4, 5)]
+    for sa in sels:
+        for sb in sels:
+            Ra, Rb = R[:, sa[0]:sa[1]], R[:, sb[0]:sb[1]]
+            ov = len(set(range(sa[0], sa[1] + 1)) & set(range(sb[0], sb[1] + 1)))
+            expected = 0 if ov == 0 else min(3, ov + 1)
+            for full, A in ((grad, Ra.T @ D @ Rb), (lap, Ra.T @ D.T @ D @ Rb)):
+                sub = full[sa[0] - 1:sa[1], sb[0] - 1:sb[1]]
+                assert np.array_equal(A.dense(), sub), (sa, sb)
+                if sa != sb:
+                    assert isinstance(A, cb.BandedMatrix) and len(A.bandrange()) == expected, (sa, sb, A.bandwidths())
+                    # and it applies like the sub-block
+                    X = np.random.default_rng(3).standard_normal((A.n, 3))
+                    Y = cb.ColMajor.zeros(A.m, 3)
+                    cb.mul(Y, A, cb.ColMajor.from_numpy(X))
+                    assert relerr(Y.numpy(), sub @ X) <= 1e-13 or not np.any(sub)
+    # scalar operators between different restrictions: a single band holding f at the common nodes (src/fd_operators.jl:20-35)
+    Ra, Rb = R[:, 3:6], R[:, 5:10]
+    V = Ra.T @ cb.QuasiDiagonal(lambda r: r ** 2) @ Rb
+    assert isinstance(V, cb.BandedMatrix) and V.data.shape == (6, 1)
+    assert np.array_equal(V.dense(), np.diag(np.asarray(R.locs()) ** 2)[2:6, 4:10])
+
+
+def test_fd_coulomb_derivative_corrections(cb):
+    """test/fd/derivatives.jl:63-105 (implicit scheme, uniform grid: Muller's corrections of the first row) and the
+    identity gradient correction of the explicit schemes (src/fd_derivatives.jl:485)."""
+    N, rho, Z = 10, 0.3, 1.0
+    R = cb.ImplicitFiniteDifferences(N, rho)
+    for singular in (True, False):
+        D = cb.CoulombDerivative(cb.Derivative(), Z, 0) if singular else cb.Derivative()
+        lam, db1 = (np.sqrt(3) - 2, -Z * rho / (12 - 10 * Z * rho)) if singular else (0.0, 0.0)
+        d1 = R.T @ D @ R
+        assert isinstance(d1, cb.ImplicitDerivative)
+        Dl, M = d1.Delta, d1.M
+        np.testing.assert_allclose(Dl.d.cpu().numpy()[0], lam / (2 * rho), rtol=1e-14, atol=1e-300)
+        assert not np.any(Dl.d.cpu().numpy()[1:])
+        np.testing.assert_allclose(Dl.dl.cpu().numpy(), -1 / (2 * rho), rtol=1e-14)
+        np.testing.assert_allclose(Dl.du.cpu().numpy(), 1 / (2 * rho), rtol=1e-14)
+        np.testing.assert_allclose(M.d.cpu().numpy()[0], (4 + lam) / 6, rtol=1e-14)
+        np.testing.assert_allclose(M.d.cpu().numpy()[1:], 4 / 6, rtol=1e-14)
+        np.testing.assert_allclose(M.du.cpu().numpy(), 1 / 6, rtol=1e-14)
+        d2 = R.T @ D.T @ D @ R
+        Dl, M = d2.Delta, d2.M
+        np.testing.assert_allclose(Dl.d.cpu().numpy()[0], -2 * (1 + db1) / rho ** 2, rtol=1e-14)
+        np.testing.assert_allclose(Dl.d.cpu().numpy()[1:], -2 / rho ** 2, rtol=1e-14)
+        np.testing.assert_allclose(Dl.du.cpu().numpy(), 1 / rho ** 2, rtol=1e-14)
+        np.testing.assert_allclose(M.d.cpu().numpy()[0], (-1 / 2) * (-(10 - 2 * db1) / 6), rtol=1e-14)
+        np.testing.assert_allclose(M.d.cpu().numpy()[1:], (-1 / 2) * (-10 / 6), rtol=1e-14)
+        np.testing.assert_allclose(M.du.cpu().numpy(), (-1 / 2) * (-1 / 6), rtol=1e-14)
+        # the factorisation was redone with the corrected left-hand side: mul! == dense M^-1 Delta
+        X = np.random.default_rng(4).standard_normal((N, 3))
+        Y = cb.ColMajor.zeros(N, 3)
+        cb.mul(Y, d2, cb.ColMajor.from_numpy(X))
+        assert relerr(Y.numpy(), np.linalg.solve(M.dense(), Dl.dense() @ X)) <= 1e-12
+    # restrictions that do not start at the origin are not corrected (:527-529)
+    Dc = cb.CoulombDerivative(cb.Derivative(), Z, 0)
+    Rr = R[:, 2:N]
+    assert float((Rr.T @ Dc @ Rr).Delta.d.abs().max()) == 0.0
+    with pytest.raises(cb.DimensionMismatch):
+        R[:, 1:5].T @ Dc @ R[:, 2:6]
+    # explicit schemes: the first-order CoulombDerivative is the plain gradient
+    for S in (cb.StaggeredFiniteDifferences(12, 0.25), cb.FiniteDifferences(12, 0.25)):
+        assert np.array_equal((S.T @ Dc @ S).dense(), (S.T @ cb.Derivative() @ S).dense())
+    # non-uniform compact scheme with a singular origin: Eq. (34) of Patchkovskii & Muller replaces the first row
+    r = 0.05 * np.arange(1, 40) + 0.002 * np.arange(1, 40) ** 2
+    Rn = cb.ImplicitFiniteDifferences(r)
+    d2 = Rn.T @ Dc.T @ Dc @ Rn
+    a, b = r[0], r[1] - r[0]
+    num = b * (a * (3 * a + 4 * b) * Z - 6 * (a + b))
+    np.testing.assert_allclose(d2.Delta.d.cpu().numpy()[0], 2 * (a + b) * (6 * a - (3 * a - b) * (a + b) * Z) / (a ** 2 * num), rtol=1e-14)
+    np.testing.assert_allclose(d2.M.d.cpu().numpy()[0], (a + b) * (a * (a + b) * (a + 3 * b) * Z - 3 * (a ** 2 + 3 * b * a + b ** 2)) / (3 * a * num), rtol=1e-14)
+    np.testing.assert_allclose(d2.M.du.cpu().numpy()[0], (a ** 3 * (-Z) + a ** 2 * (b * Z + 3) + b * a * (2 * b * Z - 3) - 3 * b ** 2) / (3 * num), rtol=1e-14)
+    plain = Rn.T @ cb.Derivative().T @ cb.Derivative() @ Rn
+    assert np.array_equal(d2.Delta.d.cpu().numpy()[1:], plain.Delta.d.cpu().numpy()[1:])
+    # hydrogen 1s on that grid: u = r exp(-r), u'' = (r - 2) exp(-r); the corrected first row knows u ~ r (1 - Z r)
+    out = cb.ColMajor.zeros(len(r), 1)
+    cb.mul(out, d2, cb.ColMajor.from_numpy(r * np.exp(-r)))
+    err = np.abs(out.numpy()[:, 0] - (r - 2) * np.exp(-r))
+    assert err[:20].max() < 2e-4, err[:20].max()
+
+
+def test_fd_implicit_stencils_on_device_bit_exact(cb):
+    """cb_fd_implicit_stencils against the oracle's restatement of the reference's loop (implicit_stencil_common,
+    src/fd_derivatives.jl:105-143, :410-424): bit for bit, full grid and a restriction."""
+    j = np.arange(1, 5001)
+    r = 0.002 * j + 4e-7 * j ** 2 + 1e-3 * np.sin(j)
+    R = cb.ImplicitFiniteDifferences(r)
+    D = cb.Derivative()
+    st = cbo.implicit_stencils_loop(r)
+    for sel in (None, (7, 4321), (2, 5000), (1, 2)):
+        Rr = R if sel is None else R[:, sel[0]:sel[1]]
+        a, b = (1, len(r)) if sel is None else sel
+        d2 = Rr.T @ D.T @ D @ Rr
+        for got, want in ((d2.Delta.dl, st["alpha_t"][a - 1:b - 1]), (d2.Delta.d, -2 * st["beta"][a - 1:b]),
+                          (d2.Delta.du, st["alpha"][a - 1:b - 1]), (d2.M.dl, st["m_dl"][a - 1:b - 1]), (d2.M.d, st["m_d"][a - 1:b]),
+                          (d2.M.du, st["m_du"][a - 1:b - 1])):
+            assert np.array_equal(got.cpu().numpy(), want), sel
+
+
+# ----------------------------------------------------------------------------------------------
+# Host-pointer forms (SURVEY §8b: every export has a device-pointer and a host-pointer form) and ADVICE r1 fixes
+# ----------------------------------------------------------------------------------------------
+def test_host_pointer_forms_match_device_forms(cb):
+    import torch
+    rng = np.random.default_rng(11)
+    B = cb.BSpline(cb.ExpKnotSet(7, -2.0, 1.0, 300))
+    D = cb.Derivative()
+    # evaluation
+    x = rng.uniform(-0.1, 10.1, 5000)
+    iv, vals = B.eval_ell_host(x)
+    ivd, valsd = B.eval_ell(x)
+    assert np.array_equal(iv, ivd.cpu().numpy()) and np.array_equal(vals, valsd.cpu().numpy())
+    # assembly into a host band: plain, with operator values, Coulomb, restricted / rectangular
+    Br = B[:, 2:B.nf - 1]
+    for L, R, a, b, ops in ((B, B, 0, 0, ()), (B, B, 1, 1, ()), (B, B, 0, 0, (cb.QuasiDiagonal(np.sin),)),
+                            (B, B, 0, 0, (cb.CoulombPotential(2.0),)), (Br, B, 0, 1, ())):
+        host = cb.diffop_host(L, R, a, b, ops)
+        dev = cb.diffop(L, R, a, b, list(ops)).data.cpu().numpy()
+        assert np.array_equal(host, dev)
+    # banded apply from host buffers (pageable and pinned), alpha / beta
+    T = B.T @ D.T @ D @ B
+    X = np.asfortranarray(rng.standard_normal((B.nf, 37)))
+    Y0 = np.asfortranarray(rng.standard_normal((B.nf, 37)))
+    Yd = cb.ColMajor.from_numpy(Y0)
+    cb.mul(Yd, T, cb.ColMajor.from_numpy(X), 0.5, -2.0)
+    Yh = Y0.copy(order="F")
+    T.mul_host(Yh, X, 0.5, -2.0)
+    assert np.array_equal(Yh, Yd.numpy())
+    Xp = torch.from_numpy(np.ascontiguousarray(X.T)).pin_memory()
+    Yp = torch.empty_like(Xp).pin_memory()
+    T.mul_host(Yp.numpy().T, Xp.numpy().T)
+    cb.mul(Yd, T, cb.ColMajor.from_numpy(X))
+    assert np.array_equal(Yp.numpy().T, Yd.numpy())
+    # density from host buffers, incl. 1 x P broadcasting and several tiles
+    B8 = cb.BSpline(cb.LinearKnotSet(8, 0, 5, 500))
+    rho = cb.Density(B8, nlhs=70, nrhs=70)
+    f, g = (np.asfortranarray(rng.standard_normal((B8.nf, 70))) for _ in range(2))
+    dev = rho.copyto(cb.ColMajor.from_numpy(f), cb.ColMajor.from_numpy(g)).numpy()
+    assert np.array_equal(rho.copyto_host(f, g), dev)
+    dev1 = rho.copyto(cb.ColMajor.from_numpy(f[:, :1]), cb.ColMajor.from_numpy(g)).numpy()
+    assert np.array_equal(rho.copyto_host(np.asfortranarray(f[:, :1]), g), dev1)
+
+
+def test_host_entries_order_after_producer_stream(cb):
+    """the host-buffer entries run on private non-blocking streams; they must wait for the assembly that
+    is still in flight on the caller's (non-default) stream."""
+    import torch
+    rng = np.random.default_rng(12)
+    t = cbo.julia_range(0, 50, 501)
+    O = cbo.FEDVROracle(t, 10)
+    Xh = np.asfortranarray(rng.standard_normal((O.N, 64)))
+    ref = O.apply(O.blocks(2), Xh)
+    s = torch.cuda.Stream()
+    D = cb.Derivative()
+    for _ in range(3):
+        with torch.cuda.stream(s):
+            torch.cuda._sleep(20_000_000)                             # ~10 ms of work ahead of the assembly on this stream
+            F = cb.FEDVR(t, 10)
+            A = F.T @ D.T @ D @ F
+            Yh = np.full_like(Xh, np.nan)
+            A.mul_host(Yh, Xh)                                        # no synchronisation by the caller
+        assert relerr(Yh, ref) <= 1e-12
+    R = cb.StaggeredFiniteDifferences(200_000, 1e-2)
+    Xr = np.asfortranarray(rng.standard_normal((200_000, 8)))
+    with torch.cuda.stream(s):
+        torch.cuda._sleep(20_000_000)
+        Lp = R.T @ D.T @ D @ R
+        Yr = np.full_like(Xr, np.nan)
+        Lp.mul_host(Yr, Xr)
+    al, be, _, _ = cbo.fd_staggered_uniform(200_000)
+    dv, ev = cbo.fd_laplacian(al, be, 1e-2)
+    assert relerr(Yr, cbo.tridiag_apply(ev, dv, ev, Xr)) <= 1e-12
+    # factorisations created inside a side stream read a band produced on that stream
+    B = cb.BSpline(cb.LinearKnotSet(5, 0, 1, 200))
+    with torch.cuda.stream(s):
+        torch.cuda._sleep(20_000_000)
+        S = B.T @ B
+        Fc = S.cholesky()
+        Flu = cb.BandLU(S)
+        Xs = cb.ColMajor.from_numpy(rng.standard_normal((B.nf, 5)))
+        X0 = Xs.numpy()
+        Fc.ldiv(Xs)
+        s.synchronize()
+    assert relerr(Xs.numpy(), np.linalg.solve(S.dense(), X0)) <= 1e-11
+    del Flu
+
+
+def test_aliasing_and_diagonal_operator_values(cb):
+    """mul!(x, M, x) goes through a temporary (ShiftAndInvert, DiagonalOperator); DiagonalOperator's matrix
+    for orthogonal bases holds the nodal values f(x) g(x) (copyto!(M::Diagonal, rho) = C .* rho.rho)."""
+    rng = np.random.default_rng(13)
+    B = cb.BSpline(cb.LinearKnotSet(5, 0, 1, 60))
+    D = cb.Derivative()
+    T = (B.T @ D.T @ D @ B) / -2
+    M = cb.ShiftAndInvert(T, B, -1.0)
+    X = rng.standard_normal((B.nf, 4))
+    want = cb.ColMajor.zeros(B.nf, 4)
+    M.mul(want, cb.ColMajor.from_numpy(X))
+    xy = cb.ColMajor.from_numpy(X)
+    M.mul(xy, xy)
+    assert relerr(xy.numpy(), want.numpy()) <= 1e-13
+    c = rng.standard_normal(B.nf)
+    L = cb.DiagonalOperator(B, c, nrhs=4)
+    want = cb.ColMajor.zeros(B.nf, 4)
+    L.mul(want, cb.ColMajor.from_numpy(X))
+    xy = cb.ColMajor.from_numpy(X)
+    L.mul(xy, xy)
+    assert relerr(xy.numpy(), want.numpy()) <= 1e-13
+    # orthogonal bases: Matrix(L) = Diagonal(f(x) .* g(x)) for FE-DVR and a non-uniform staggered grid
+    f = lambda x: np.sin(x) + 2
+    g = lambda x: np.exp(-0.1 * x)
+    F = cb.FEDVR(cbo.julia_range(0, 5, 6), [4, 5, 3, 6, 4])
+    r = 0.1 * np.arange(1, 41) ** 1.3
+    for Rb in (F, F[:, 2:F.N - 1], cb.StaggeredFiniteDifferences(r), cb.StaggeredFiniteDifferences(30, 0.2), cb.FiniteDifferences(30, 0.2)):
+        Lo = cb.DiagonalOperator(Rb, Rb.ldiv(f).numpy()[:, 0])
+        Md = Lo.matrix(Rb.ldiv(g))
+        assert isinstance(Md, cb.Diagonal)
+        P = Rb.parent_basis
+        a, b = Rb.indices()
+        x = np.asarray(P.locs())[a - 1:b]
+        np.testing.assert_allclose(Md.dense(), np.diag(f(x) * g(x)), rtol=1e-13)
+
+
+def test_bandlu_rejects_unsupported_bandwidth_at_create(cb):
+    import torch
+    band = torch.ones((64, 32), dtype=torch.float64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        cb.BandLU(cb.BandedMatrix(band, 64, 64, 16, 15))
+    band = torch.ones((64, 31), dtype=torch.float64, device="cuda")
+    band[:, 15] = 100.0
+    F = cb.BandLU(cb.BandedMatrix(band, 64, 64, 15, 15))               # l + u = 30: factor and solve fit
+    X = cb.ColMajor.from_numpy(np.ones((64, 3)))
+    F.ldiv(X)
+    assert np.all(np.isfinite(X.numpy()))
