@@ -62,6 +62,7 @@ _SIGNATURES = {
     "cb_fedvr_to_skyline": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
     "cb_fedvr_to_tridiag": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     "cb_fedvr_apply": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
+    "cb_fedvr_assemble_apply": (cint, [vp, vp, vp, vp, vp, vp, vp, i64, cint, cint, cint, vp, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_fedvr_apply_host": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),
     "cb_fd_derivative": (cint, [cint, cint, vp, vp, i64, dbl, i64, i64, dbl, cint, vp, vp, vp, vp]),
     "cb_fd_derivative_banded": (cint, [cint, cint, vp, vp, i64, dbl, i64, i64, i64, i64, dbl, cint, vp, vp]),

@@ -1594,8 +1594,15 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     int rc = check_apply_args("cb_banded_apply", m, n, X, ldx, nvec, Y, ldy);
     if (rc) return rc;
     CB_REQUIRE(band != nullptr, "cb_banded_apply: NULL band");
-    CB_REQUIRE(l + u + 1 >= 1 && l > -n - 1 && u > -m - 1, "cb_banded_apply: invalid bandwidths (%d,%d)", l, u);
+    CB_REQUIRE(l + u + 1 >= 1, "cb_banded_apply: invalid bandwidths (%d,%d)", l, u);
     if (m == 0 || nvec == 0) return CB_OK;
+    if (-l > n - 1 || -u > m - 1) {
+        // every stored band lies outside the m x n matrix (BandedMatrices allows it: operators between restrictions
+        // that do not overlap, test/fd/derivatives.jl:36-59): A = 0, Y <- beta Y
+        if (beta == 0.0) CB_CUDA(cudaMemset2DAsync(Y, sizeof(double) * ldy, 0, sizeof(double) * m, nvec, (cudaStream_t)stream));
+        else if (beta != 1.0) return cb_axpby(m, nvec, 0.0, Y, ldy, beta, Y, ldy, stream);
+        return CB_OK;
+    }
     // BandedMatrices allows negative l or u (bands entirely above/below the diagonal, e.g.
     // src/fd_operators.jl:16); the window arithmetic below is valid for them as long as l+u >= 0.
     const int W = l + u + 1;
@@ -1692,6 +1699,18 @@ int cb_fedvr_apply(const double *blocks, const i64 *estart, const int32_t *order
     fedvr_apply_generic_kernel<<<grid, 128, 0, st>>>(blocks, estart, order, boff, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
     CB_LAUNCH_CHECK();
     return CB_OK;
+}
+
+// derop! followed by mul! in one call: the two launches are enqueued back to back from C (the host side of a step is
+// then one foreign call instead of the operator algebra of the caller's language).
+int cb_fedvr_assemble_apply(const double *x, const double *wcat, const double *nrm,
+                            const i64 *estart, const int32_t *order, const i64 *boff, const i64 *woff,
+                            i64 nel, int uniform_order, int max_order, int nder, double *blocks,
+                            i64 first, i64 last, const double *X, i64 ldx, i64 nvec,
+                            double alpha, double beta, double *Y, i64 ldy, void *stream) {
+    int rc = cb_fedvr_assemble(x, wcat, nrm, estart, order, boff, woff, nel, uniform_order, max_order, nder, blocks, stream);
+    if (rc) return rc;
+    return cb_fedvr_apply(blocks, estart, order, boff, nel, uniform_order, first, last, X, ldx, nvec, alpha, beta, Y, ldy, stream);
 }
 
 int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,

@@ -177,6 +177,21 @@ class FEDVR(_FEDVROrRestricted):
             self._ops[nder] = blocks
         return self._ops[nder]
 
+    def derop_mul(self, nder: int, Y, X, alpha: float = 1.0, beta: float = 0.0):
+        """``mul!(Y, derop!(A, B, nder), X, alpha, beta)`` in one foreign call (``cb_fedvr_assemble_apply``): the
+        operator is re-assembled into its cached block array and applied; returns the FEDVRMatrix."""
+        from .operators import ColMajor
+        Xc = X if isinstance(X, ColMajor) else ColMajor(X)
+        Yc = Y if isinstance(Y, ColMajor) else ColMajor(Y)
+        if nder not in self._ops:
+            self._ops[nder] = torch.empty(int(np.sum(self.order ** 2)), dtype=torch.float64, device=self.device)
+        blocks = self._ops[nder]
+        _lib.call("cb_fedvr_assemble_apply", _ptr(self.d_x), _ptr(self.d_wcat), _ptr(self.d_n), _ptr(self.d_estart),
+                  _ptr(self.d_order), _ptr(self.d_boff), _ptr(self.d_woff), self.nel, self.uniform_order,
+                  int(self.order.max()), nder, _ptr(blocks), 1, self.N, _ptr(Xc.data), Xc.ld, Xc.nvec, float(alpha), float(beta),
+                  _ptr(Yc.data), Yc.ld, _stream())
+        return FEDVRMatrix(self, blocks, 1, self.N)
+
     # -- block structure (src/fedvr.jl:82-176), host integer logic ----------
     def element_boundaries(self):
         return np.concatenate([[1], self.estart + self.order]).astype(np.int64)

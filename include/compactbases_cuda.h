@@ -211,6 +211,13 @@ int cb_fedvr_apply(const double *blocks, const cb_i64 *estart, const int32_t *or
                    cb_i64 first, cb_i64 last,
                    const double *X, cb_i64 ldx, cb_i64 nvec,
                    double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
+/* derop!(A, B, nder) followed by mul!(Y, A, X, alpha, beta): cb_fedvr_assemble + cb_fedvr_apply enqueued by one
+ * call (`blocks` receives the operator). */
+int cb_fedvr_assemble_apply(const double *x, const double *wcat, const double *nrm,
+                            const cb_i64 *estart, const int32_t *order, const cb_i64 *boff, const cb_i64 *woff,
+                            cb_i64 nel, int uniform_order, int max_order, int nder, double *blocks,
+                            cb_i64 first, cb_i64 last, const double *X, cb_i64 ldx, cb_i64 nvec,
+                            double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
 /* Host-buffer forms (`*_apply_host`): X_host/Y_host in host memory (pinned for PCIe speed, see
  * cb_host_register; pageable arrays work, staged by the driver); the vector batch is streamed through the
  * device in tiles on the library's own copy streams (H2D, kernel, D2H of consecutive tiles overlap).

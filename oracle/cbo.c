@@ -686,6 +686,20 @@ void cbo_banded_lstsq(const double *table, const i64 *iv, i64 ni, int q, int k,
     free(R); free(y); free(row); free(br);
 }
 
+/* The same over chunks of right-hand sides on several threads (every thread repeats the QR of V for its chunk):
+ * the "OpenMP over all host cores" form of the CPU baseline. */
+void cbo_banded_lstsq_mt(const double *table, const i64 *iv, i64 ni, int q, int k,
+                         i64 col0, i64 ncols, const double *Bm, i64 ldb, i64 P, double *out, i64 ldo)
+{
+    int nt = g_threads;
+    if (nt > P) nt = (int)(P > 0 ? P : 1);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int c = 0; c < nt; ++c) {
+        i64 p0 = P * c / nt, p1 = P * (c + 1) / nt;
+        if (p1 > p0) cbo_banded_lstsq(table, iv, ni, q, k, col0, ncols, Bm + ldb * p0, ldb, p1 - p0, out + ldo * p0, ldo);
+    }
+}
+
 /* b = w .* conj(V f) .* (V g) at the nodes (src/densities.jl:158-162), V restricted to columns col0+1..col0+ncols;
  * f: ncols x Pf, g: ncols x Pg with Pf == Pg or one of them 1 (:57-72).  Bm: nquad x max(Pf,Pg). */
 void cbo_density_nodal(const double *table, const i64 *iv, i64 ni, int q, int k, i64 col0, i64 ncols,
@@ -693,6 +707,7 @@ void cbo_density_nodal(const double *table, const i64 *iv, i64 ni, int q, int k,
                        double *Bm, i64 ldb)
 {
     const i64 P = Pf > Pg ? Pf : Pg;
+#pragma omp parallel for schedule(static) num_threads(g_threads)
     for (i64 p = 0; p < P; ++p) {
         const double *fc = f + ldf * (Pf == 1 ? 0 : p), *gc = g + ldg * (Pg == 1 ? 0 : p);
         for (i64 c = 0; c < ni; ++c)

@@ -669,8 +669,9 @@ def banded_lstsq(tab, iv, k, q, Bm, col0, ncols):
     Bm = np.asfortranarray(np.atleast_2d(np.asarray(Bm, dtype=np.float64).T).T).copy(order="F")
     nq, P = Bm.shape
     out = np.zeros((ncols, P), order="F")
-    lib().cbo_banded_lstsq(_p(tab), _p(iv, ip), i64(len(iv)), C.c_int(q), C.c_int(k), i64(col0), i64(ncols),
-                           _p(Bm), i64(nq), i64(P), _p(out), i64(ncols))
+    fn = lib().cbo_banded_lstsq_mt if int(lib().cbo_get_threads()) > 1 else lib().cbo_banded_lstsq
+    fn(_p(tab), _p(iv, ip), i64(len(iv)), C.c_int(q), C.c_int(k), i64(col0), i64(ncols),
+       _p(Bm), i64(nq), i64(P), _p(out), i64(ncols))
     return out
 
 
