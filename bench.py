@@ -460,6 +460,7 @@ def config_c3(cx: Ctx, cpu: bool, comm):
             modes = {}
             for halo in ("fused", "exchange", "recompute"):
                 kw = dict(halo=halo, comm=comm if halo != "exchange" else None)
+                cx.barrier()
                 lo, hi, Tb = assemble_interval_sharded(B, B, 1, 1, cx.rank, cx.world, **kw)
                 lo, hi, Vb = assemble_interval_sharded(B, B, 0, 0, cx.rank, cx.world, coulomb_Z=1.0, **kw)
                 eT = relerr(Tb.cpu().numpy(), full_T[lo:hi].cpu().numpy())
@@ -833,6 +834,7 @@ def run_gpu(args):
     for name, fn in (("C1", lambda: config_c1(cx, cpu)), ("C3", lambda: config_c3(cx, cpu, comm)),
                      ("C4", lambda: config_c4(cx, cpu)), ("C5", lambda: config_c5(cx, cpu))):
         if name.lower() in want:
+            cx.barrier()                                    # ranks enter every config together (rank 0 alone does the CPU legs)
             t0 = time.perf_counter()
             configs[name] = fn()
             configs[name]["n_gpus"] = world

@@ -81,11 +81,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// waits until *p >= want; gives up after ~2 s (a peer that never launched must not hang the GPU)
+// waits until *p >= want; gives up after ~15 s (a peer that never launched must not hang the GPU for good, but ranks of one
+// job may legitimately be seconds apart: host-side work between calls, first-call initialisation)
 __device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long want, int *status) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > 4000000000ll) { atomicExch(status, 1); break; }
+        if (clock64() - t0 > 30000000000ll) { atomicExch(status, 1); break; }
         __nanosleep(64);
     }
 }
@@ -803,6 +804,9 @@ static int ensure_rc_index() {
     return CB_OK;
 }
 
+int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int coulomb, double Z, i64 rowL0, i64 mm, i64 colR0,
+                         i64 nn, int u, i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st);   // assemble_stream.cu
+
 static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
                            int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
                            i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, void *stream,
@@ -828,6 +832,11 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     if (col_hi == col_lo) return CB_OK;
     { int rc_ = ensure_rc_index(); if (rc_) return rc_; }
     cudaStream_t st = (cudaStream_t)stream;
+    // ---- streaming kernel (assemble_stream.cu): the same basis on both sides, a == b <= 1, no fused halo ----
+    if (!halo && a == b && L->k == R->k && L->ml == R->ml && L->nf == R->nf) {
+        const int src = cb_asm_stream_launch(R, a, opvals, coulomb, Z, rowL0, m, colR0, n, u, col_lo, col_hi, s_lo, s_hi, band, st);
+        if (src >= 0) return src;
+    }
     AsmArgs A;
     A.kvL = make_knot_view(L); A.kvR = make_knot_view(R);
     A.kL = L->k; A.kR = R->k; A.nfL = L->nf; A.nfR = R->nf;

@@ -28,14 +28,14 @@ for nint in (200_000, 1_600_000):
         assert eT <= 1e-13 and eV <= 1e-13, (halo, eT, eV)
         Tb, Vb = torch.empty_like(T), torch.empty_like(V)
         for _ in range(3):
-            assemble_interval_sharded(B, B, 1, 1, rank, world, out=Tb, **kw)
+            Tb = assemble_interval_sharded(B, B, 1, 1, rank, world, out=Tb, **kw)[2]
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         e0.record()
         for _ in range(reps):
-            assemble_interval_sharded(B, B, 1, 1, rank, world, out=Tb, **kw)
-            assemble_interval_sharded(B, B, 0, 0, rank, world, coulomb_Z=1.0, out=Vb, **kw)
+            Tb = assemble_interval_sharded(B, B, 1, 1, rank, world, out=Tb, **kw)[2]     # (halo="exchange" returns a new tensor)
+            Vb = assemble_interval_sharded(B, B, 0, 0, rank, world, coulomb_Z=1.0, out=Vb, **kw)[2]
         e1.record(); torch.cuda.synchronize()
         ms = tmax(e0.elapsed_time(e1) / reps)
         assert comm.status() == 0
