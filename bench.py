@@ -114,8 +114,16 @@ class ClockSampler:
 _CPU_STATE = {}
 
 
+_ALL_CPUS = None         # affinity of the process before bench.py bound it to the GPU's NUMA node
+
+
 def _cbo(threads=True):
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm may use every host core
+    if _ALL_CPUS is not None:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)              # the CPU legs are not confined to the GPU's NUMA node
+        except OSError:
+            pass
     if "oracle.cbo" not in sys.modules:
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import cbo
@@ -254,6 +262,8 @@ class Ctx:
 
 
 def pinned(torch, shape, dtype=None):
+    from compactbases_jl_b200.numa import bind_to_gpu_numa
+    bind_to_gpu_numa(torch.cuda.current_device())          # (a CPU leg may have widened the affinity again)
     return torch.empty(shape, dtype=dtype or torch.float64, pin_memory=True)
 
 
@@ -753,6 +763,11 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # pinned staging buffers next to the GPU: run on (and first-touch from) the CPUs of the GPU's NUMA node
+    from compactbases_jl_b200.numa import bind_to_gpu_numa
+    global _ALL_CPUS
+    _ALL_CPUS = os.sched_getaffinity(0)
+    numa_info = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import compactbases_jl_b200 as cb
@@ -876,6 +891,7 @@ def run_gpu(args):
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
             "fp64_peak_tflops_measured": cx.fp64_peak,
+            "host": {"cpus": os.cpu_count(), "numa_binding_rank0": numa_info},
             "configs": configs,
             "kernels": kernels,
         }

@@ -8,23 +8,26 @@
 // in full although they are symmetric, and the gather was one thread per band entry with ten predicated steps.
 //
 // Here a CTA owns a contiguous range of columns and walks through the knot intervals they live on in steps of NS
-// intervals, keeping the local matrices of the last NS + K - 1 intervals in a shared-memory ring:
+// intervals, keeping the local matrices of the last 2 NS + K - 1 intervals in a shared-memory ring.  A step has two
+// segments (two CTA barriers):
 //
-//   phase 0  knot window and reciprocal knot differences of the step (one table per step, shared by all nodes)
-//   phase 1  one thread per (interval, node pair): one Cox-de Boor sweep for both nodes on the 2(K-1) knot
-//            distances (3 FP64 operations per entry), m derivative levels; the K values per node go to a
-//            node-major table (even nodes first: conflict-free 16-byte stores)
-//   phase 2a two threads per interval (one per half of the nodes): the K(K+1)/2 entries of the UPPER triangle of the
-//            interval's local matrix  M_s[a][b] = sum_l w_l op(x_l) N_a(x_l) N_b(x_l)  in registers — each table value
-//            is read once, 16 bytes at a time, consecutive lanes in different banks; the two halves are added with
-//            one shuffle and stored to the ring
-//   phase 2b one thread per completed column: its 2K-1 band entries are sums over the column's K intervals of
-//            compile-time-indexed ring entries (no index arithmetic in the loop), intervals in increasing order —
-//            the same sum whatever the partition into CTAs, ranks or steps; the columns go to a staging tile and
-//            leave the SM as one contiguous, fully coalesced copy
-//
-// Three CTA barriers per step; the gather of step t-1 shares a segment with phase 0 of step t.  Halo work is the
-// K - 1 intervals at the end of a CTA's range (1.3 % at the C3 size).
+//   segment A  every thread is one (interval, node pair): one Cox-de Boor sweep for both nodes on the 2(K-1) knot
+//              distances (3 FP64 operations per level entry, reciprocal support widths from the step's table, shared by
+//              the interval's q nodes), m derivative levels; the K values per node go to a node-major table (even
+//              nodes first: conflict-free 16-byte stores).  The columns gathered one segment earlier leave the SM as
+//              one contiguous, fully coalesced copy.
+//   segment B  three roles side by side, warp-specialised:
+//              * local matrices: two threads per interval, each a row range of the UPPER triangle of
+//                M_s[a][b] = sum_l w_l op(x_l) N_a(x_l) N_b(x_l)  in registers; lanes are consecutive intervals, so the
+//                16-byte table reads of a warp fall into different banks;
+//              * gather: one thread per column completed by the previous steps: its 2K-1 band entries are sums over
+//                the column's K intervals of compile-time-indexed ring entries, intervals in increasing order — the
+//                same sum whatever the partition into CTAs, ranks or steps;
+//              * tables of the NEXT step: knot windows and reciprocal knot differences from knots that were fetched
+//                into registers during segment A.
+// Nothing on the critical path waits for global memory: knots and interval ordinals of step t+1 are loaded at the
+// start of segment A of step t, the nodes / weights of its phase-1 items arrive by cp.async during segment B.  Halo
+// work is the K - 1 intervals at the end of a CTA's range (1.3 % at the C3 size).
 #include "bspline_core.cuh"
 
 struct StreamArgs {
@@ -113,18 +116,71 @@ __device__ __forceinline__ void stream_sweep_pair(const StreamTab &T, int sl, do
     }
 }
 
+// Row split of the upper triangle between the two threads of an interval in phase 2a: rows [0, AS) hold about half
+// of the K(K+1)/2 entries.
+template <int K> struct StreamSplit {
+    static constexpr int as() {
+        int best = 1, bestd = 1 << 30;
+        for (int s = 1; s < K; ++s) {
+            int e = 0;
+            for (int a = 0; a < s; ++a) e += K - a;
+            int d = 2 * e - K * (K + 1) / 2;
+            d = d < 0 ? -d : d;
+            if (d < bestd) { bestd = d; best = s; }
+        }
+        return best;
+    }
+    static constexpr int AS = as();
+};
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// phase 2a for the rows [A0, A1) of the upper triangle of one interval's local matrix
+template <int K, int A0, int A1>
+__device__ __forceinline__ void stream_local_rows(const double *tv, const double *wl, int q, double *m) {
+    using G = StreamGeom<K>;
+    constexpr int KP2 = G::KP2, KH = G::KH;
+    constexpr int E0 = G::sidx(A0, A0), E1 = A1 < K ? G::sidx(A1, A1) : G::NE;
+    double acc[E1 - E0];
+#pragma unroll
+    for (int i = 0; i < E1 - E0; ++i) acc[i] = 0.0;
+#pragma unroll 2
+    for (int p = 0; p < q; ++p) {
+        double n[KP2];
+        const double2 *t2 = reinterpret_cast<const double2 *>(tv + p * KP2);
+#pragma unroll
+        for (int a = A0 / 2; a < KH; ++a) { const double2 v = t2[a]; n[2 * a] = v.x; n[2 * a + 1] = v.y; }
+        const double wv = wl[p];
+#pragma unroll
+        for (int a = A0; a < A1; ++a) {
+            const double lw = wv * n[a];
+#pragma unroll
+            for (int b = a; b < K; ++b) acc[G::sidx(a, b) - E0] = fma(lw, n[b], acc[G::sidx(a, b) - E0]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < E1 - E0; ++i) m[E0 + i] = acc[i];
+}
+
 template <int K, int M>
 __global__ void __launch_bounds__(STREAM_MAX_THREADS, 1)
 bspline_assemble_stream_kernel(StreamArgs A) {
     extern __shared__ __align__(16) double sm[];
     using G = StreamGeom<K>;
     constexpr int QH = G::QH, KP2 = G::KP2, KH = G::KH, W = G::W, NE = G::NE, MSP = G::MSP, PIV = G::PIV, QPW = G::QPW;
-    constexpr int NH = (NE + 1) / 2;
-    const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
-    const int q = A.q, NS = A.NS, RING = NS + K - 1, CAP = RING;
+    constexpr int AS = StreamSplit<K>::AS;
+    const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5;
+    const int q = A.q, NS = A.NS, NSR = (NS + 31) & ~31, RING = 2 * NS + K - 1, CAP = NS + K - 1;
     const int NKP = (NS + 2 * K + 2) / 2 * 2;
     const int ml = A.kv.ml;
     const i64 n_tt = A.kv.n_tt;
+    // roles of the second segment of a step: warps [0, W2B) local matrices, [W2B, WP0) gather, [WP0, ..) tables
+    const int W2B = 2 * NSR / 32, WP0 = W2B + (CAP + 31) / 32;
+    const int P0T = NT - 32 * WP0;
     // shared memory carve-up (every region starts on a 16-byte boundary)
     double *TV = sm;                                         // [NS][PIV]   node-major tables, even nodes first
     double *WL = TV + (size_t)NS * PIV;                      // [NS][QPW]   (-1)^m w op at the node positions
@@ -132,7 +188,9 @@ bspline_assemble_stream_kernel(StreamArgs A) {
     double *OUT = MS + (((size_t)RING * MSP + 1) & ~(size_t)1);   // [CAP][W] staging tile of completed columns
     double *KN = OUT + (((size_t)CAP * W + 1) & ~(size_t)1); // [2][NKP + 2]
     double *RD = KN + 2 * (NKP + 2);                         // [2][K * NKP + 2]
-    int *sOrd = reinterpret_cast<int *>(RD + (size_t)2 * (K * NKP + 2));   // [NS]
+    double *RAW = RD + (size_t)2 * (K * NKP + 2);            // [NKP] knots of the next step
+    double *NODE = RAW + NKP;                                // [NT][6] x0 x1 w0 w1 o0 o1 of the next step's phase-1 items
+    int *sOrd = reinterpret_cast<int *>(NODE + (size_t)NT * 6);   // [2][NS]
     StreamTab T;
     T.sm = sm; T.kn = (int)(KN - sm); T.rd = (int)(RD - sm); T.pitch = NKP;
     T.kn_copy = ((NKP / 2) | 1) * 2; T.rd_copy = ((K * NKP / 2) | 1) * 2;
@@ -150,91 +208,83 @@ bspline_assemble_stream_kernel(StreamArgs A) {
     if (sB > A.s_hi - 1) sB = A.s_hi - 1;
     const i64 ntot = sB >= sA ? sB - sA + 1 : 0;
     const int nsteps = (int)((ntot + NS - 1) / NS);
-    i64 jnext = j0;
-
-    for (int t = 0; t <= nsteps; ++t) {
-        const bool live = t < nsteps;
-        const i64 s0 = sA + (i64)t * NS;
-        const int ns = live ? (int)(sB - s0 + 1 < NS ? sB - s0 + 1 : NS) : 0;
-        // ---- this thread's phase-1 item: node data fetched now, used after the barrier ----
-        const int sl1 = tid / QH, lp1 = tid - sl1 * QH;
-        const bool has1 = 2 * lp1 + 1 < q;
-        int c1 = -1;
-        double x0 = 1.0, x1 = 1.0, w0 = 1.0, w1 = 1.0, o0 = 1.0, o1 = 1.0;
+    auto step_ns = [&](int t) -> int {
+        if (t >= nsteps) return 0;
+        const i64 left = sB - (sA + (i64)t * NS) + 1;
+        return (int)(left < NS ? left : NS);
+    };
+    // knots / interval ordinals of step t: global -> shared (prologue), or global -> registers -> shared (steady state)
+    auto raw_index = [&](int t, int i) -> i64 { return sA + (i64)t * NS + ml - K + i; };
+    // tables of step t from RAW (threads first, first + stride, ...)
+    auto build_tables = [&](int ns, int first, int stride) {
+        const int NP = ns + 2 * K;
+        for (int idx = first; idx < K * NP; idx += stride) {
+            const int j = idx / NP, p = idx - j * NP;
+            const double lo = RAW[p];
+            if (j == 0) {
+                KN[p] = lo;
+                if (p > 0) KN[T.kn_copy + p - 1] = lo;
+            } else if (p + j < NP) {
+                const double dk = RAW[p + j] - lo;
+                const double v = dk != 0.0 ? fast_rcp(dk) : 0.0;   // zero widths only feed empty intervals / absent functions
+                RD[j * NKP + p] = v;
+                if (p > 0) RD[T.rd_copy + j * NKP + p - 1] = v;
+            }
+        }
+    };
+    // this thread's phase-1 item
+    const int sl1 = tid / QH, lp1 = tid - sl1 * QH;
+    const bool has1 = 2 * lp1 + 1 < q;
+    double *node = NODE + (size_t)tid * 6;
+    auto prefetch_nodes = [&](int ns, const int *ord) {       // node data of the coming step: global -> NODE (async)
         if (tid < ns * QH) {
-            c1 = A.ord[s0 + sl1 + ml - 1];
-            if (c1 >= 0) {
-                const i64 g0 = (i64)c1 * q + 2 * lp1, g1 = has1 ? g0 + 1 : g0;
-                x0 = A.x[g0]; x1 = A.x[g1];
-                if (A.coulomb != 2) { w0 = A.w[g0]; w1 = A.w[g1]; }
-                if (A.opvals) { o0 = A.opvals[g0]; o1 = A.opvals[g1]; }
+            const int c = ord[sl1];
+            if (c >= 0) {
+                const i64 g0 = (i64)c * q + 2 * lp1, g1 = has1 ? g0 + 1 : g0;
+                cp_async8(node + 0, A.x + g0); cp_async8(node + 1, A.x + g1);
+                if (A.coulomb != 2) { cp_async8(node + 2, A.w + g0); cp_async8(node + 3, A.w + g1); }
+                if (A.opvals) { cp_async8(node + 4, A.opvals + g0); cp_async8(node + 5, A.opvals + g1); }
             }
         }
-        // ---- phase 0: tables of step t ----
-        for (int e = tid; e < ns; e += NT) sOrd[e] = A.ord[s0 + e + ml - 1];
-        if (live) {
-            for (int j = warp; j < K; j += nwarps) {
-                for (int p = lane; p < ns + 2 * K; p += 32) {
-                    const double lo = A.kv.at(s0 + ml - K + p);
-                    if (j == 0) {
-                        KN[p] = lo;
-                        if (p > 0) KN[T.kn_copy + p - 1] = lo;
-                    } else if (p + j < ns + 2 * K) {
-                        const double dk = A.kv.at(s0 + ml - K + p + j) - lo;
-                        const double v = dk != 0.0 ? fast_rcp(dk) : 0.0;   // zero widths only feed empty intervals / absent functions
-                        RD[j * NKP + p] = v;
-                        if (p > 0) RD[T.rd_copy + j * NKP + p - 1] = v;
-                    }
-                }
-            }
+        cp_async_commit();
+    };
+
+    // ---- prologue: tables and node data of step 0 ----
+    {
+        const int ns = step_ns(0);
+        if (ns > 0) {
+            for (int i = tid; i < ns + 2 * K; i += NT) RAW[i] = A.kv.at(raw_index(0, i));
+            for (int e = tid; e < ns; e += NT) sOrd[e] = A.ord[sA + e + ml - 1];
         }
-        // ---- phase 2b: columns completed by step t-1 (everything that is left after the last step) ----
-        const i64 s_end = s0 - 1 < sB ? s0 - 1 : sB;          // last interval whose local matrix is in the ring
-        i64 jl = live ? s_end - (K - 1) - foff + 1 : j1;      // exclusive: columns with f0 + K - 1 <= s_end
-        if (jl > j1) jl = j1;
-        if (jl < jnext) jl = jnext;
-        bool first = true;
-        while (true) {
-            const int nem = (int)(jl - jnext < CAP ? jl - jnext : CAP);
-            if (tid < nem) {
-                const i64 j = jnext + tid, f0 = j + foff;
-                double acc[W];
-#pragma unroll
-                for (int d = 0; d < W; ++d) acc[d] = 0.0;
-                int slot = (int)((f0 - sA) % RING);
-                if (slot < 0) slot += RING;
-#pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    const i64 s = f0 + r;
-                    if (s >= sA && s <= s_end) {
-                        const double *m = MS + (size_t)slot * MSP;
-#pragma unroll
-                        for (int a = 0; a < K; ++a) acc[a + r] += m[G::sidx(a, K - 1 - r)];
-                    }
-                    slot = slot + 1 == RING ? 0 : slot + 1;
-                }
-                // band slot d of column j holds row i = j - u + d; with (l, u) = (K-1+ij, K-1-ij) slot d is run entry d
-#pragma unroll
-                for (int d = 0; d < W; ++d) {
-                    const i64 i = j - A.u + d;
-                    OUT[tid * W + d] = (i >= 0 && i < A.mm) ? acc[d] : 0.0;
-                }
-            }
-            __syncthreads();
-            {
-                double *dst = A.band + (size_t)(jnext - A.col_lo) * W;
-                for (int e = tid; e < nem * W; e += NT) dst[e] = OUT[e];
-            }
-            jnext += nem;
-            first = false;
-            if (jnext >= jl) break;
-            __syncthreads();
+        __syncthreads();
+        if (ns > 0) build_tables(ns, tid, NT);
+        prefetch_nodes(ns, sOrd);
+        __syncthreads();
+    }
+    i64 jnext = j0, pend_j = j0;
+    int pend_n = 0;
+
+    for (int t = 0;; ++t) {
+        const int ns = step_ns(t), ns_next = step_ns(t + 1);
+        const i64 s0 = sA + (i64)t * NS;
+        const int *ord_cur = sOrd + (t & 1) * NS;
+        int *ord_next = sOrd + ((t + 1) & 1) * NS;
+        // ======== segment A: node tables of step t; the columns gathered in the previous segment leave the SM ========
+        double raw_next = 0.0; int ord_n = -1;
+        if (tid < ns_next + 2 * K) raw_next = A.kv.at(raw_index(t + 1, tid));          // lands while phase 1 runs
+        if (tid < ns_next) ord_n = A.ord[s0 + NS + tid + ml - 1];
+        if (pend_n > 0) {
+            double *dst = A.band + (size_t)(pend_j - A.col_lo) * W;
+            for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[e];
+            pend_n = 0;
         }
-        (void)first;
-        if (!live) break;
-        // ---- phase 1: node tables ----
-        if (c1 >= 0) {
-            if (!A.opvals && A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
+        cp_async_wait_all();
+        if (tid < ns * QH && ord_cur[sl1] >= 0) {
+            const double x0 = node[0], x1 = node[1];
+            double w0 = 1.0, w1 = 1.0, o0 = 1.0, o1 = 1.0;
+            if (A.coulomb != 2) { w0 = node[2]; w1 = node[3]; }
+            if (A.opvals) { o0 = node[4]; o1 = node[5]; }
+            else if (A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
             double N0[K], N1[K];
             stream_sweep_pair<K, M>(T, sl1, x0, x1, N0, N1);
             double2 *te = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + lp1 * KP2);
@@ -247,57 +297,97 @@ bspline_assemble_stream_kernel(StreamArgs A) {
             WL[sl1 * QPW + lp1] = (sgn * w0) * o0;
             if (has1) WL[sl1 * QPW + QH + lp1] = (sgn * w1) * o1;
         }
+        if (tid < ns_next + 2 * K) RAW[tid] = raw_next;
+        if (tid < ns_next) ord_next[tid] = ord_n;
         __syncthreads();
-        // ---- phase 2a: upper triangle of the local matrix, two threads (node halves) per interval ----
-        if (tid < ((2 * ns + 31) & ~31)) {
-            const int sl = tid >> 1, h = tid & 1;
-            const bool act = sl < ns && sOrd[sl < ns ? sl : 0] >= 0;
-            double acc[NE];
-#pragma unroll
-            for (int i = 0; i < NE; ++i) acc[i] = 0.0;
-            if (act) {
-                const int pb = h ? QH : 0, pe = h ? q : QH;     // even nodes | odd nodes
-                const double *tv = TV + (size_t)sl * PIV;
-                const double *wl = WL + sl * QPW;
-                for (int p = pb; p < pe; ++p) {
-                    double n[KP2];
-                    const double2 *t2 = reinterpret_cast<const double2 *>(tv + p * KP2);
-#pragma unroll
-                    for (int a = 0; a < KH; ++a) { const double2 v = t2[a]; n[2 * a] = v.x; n[2 * a + 1] = v.y; }
-                    const double wv = wl[p];
-#pragma unroll
-                    for (int a = 0; a < K; ++a) {
-                        const double lw = wv * n[a];
-#pragma unroll
-                        for (int b = a; b < K; ++b) acc[G::sidx(a, b)] = fma(lw, n[b], acc[G::sidx(a, b)]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NE; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
+        // ======== segment B: three roles side by side ========
+        prefetch_nodes(ns_next, ord_next);
+        if (warp < W2B) {
+            // ---- local matrices of step t: thread (interval, row half) ----
+            const int h = tid >= NSR ? 1 : 0, sl = tid - h * NSR;
             if (sl < ns) {
                 int slot = (int)((s0 + sl - sA) % RING);
                 double *m = MS + (size_t)slot * MSP;
-                if (h == 0) {
-#pragma unroll
-                    for (int i = 0; i < NH; ++i) m[i] = acc[i];
+                if (ord_cur[sl] < 0) {
+                    if (h == 0) { for (int i = 0; i < G::sidx(AS, AS); ++i) m[i] = 0.0; }
+                    else { for (int i = G::sidx(AS, AS); i < NE; ++i) m[i] = 0.0; }
                 } else {
-#pragma unroll
-                    for (int i = NH; i < NE; ++i) m[i] = acc[i];
+                    const double *tv = TV + (size_t)sl * PIV;
+                    const double *wl = WL + sl * QPW;
+                    // node positions: even nodes 0..QH-1, odd nodes QH..q-1 (contiguous)
+                    if (h == 0) stream_local_rows<K, 0, AS>(tv, wl, q, m);
+                    else stream_local_rows<K, AS, K>(tv, wl, q, m);
                 }
             }
+        } else if (warp < WP0) {
+            // ---- gather: columns completed by the steps before t (everything that is left once all steps are done) ----
+            const i64 s_done = t == 0 ? sA - 1 : (sA + (i64)t * NS - 1 < sB ? sA + (i64)t * NS - 1 : sB);
+            i64 jl = t >= nsteps ? j1 : s_done - (K - 1) - foff + 1;      // exclusive: columns with f0 + K - 1 <= s_done
+            if (jl > j1) jl = j1;
+            if (jl < jnext) jl = jnext;
+            const int nem = (int)(jl - jnext < CAP ? jl - jnext : CAP);
+            const int e2 = tid - 32 * W2B;
+            if (e2 < nem) {
+                const i64 j = jnext + e2, f0 = j + foff;
+                double acc[W];
+#pragma unroll
+                for (int d = 0; d < W; ++d) acc[d] = 0.0;
+                int slot = (int)((f0 - sA) % RING);
+                if (slot < 0) slot += RING;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const i64 s = f0 + r;
+                    if (s >= sA && s <= s_done) {
+                        const double *m = MS + (size_t)slot * MSP;
+#pragma unroll
+                        for (int a = 0; a < K; ++a) acc[a + r] += m[G::sidx(a, K - 1 - r)];
+                    }
+                    slot = slot + 1 == RING ? 0 : slot + 1;
+                }
+                // band slot d of column j holds row i = j - u + d; with (l, u) = (K-1+ij, K-1-ij) slot d is run entry d
+#pragma unroll
+                for (int d = 0; d < W; ++d) {
+                    const i64 i = j - A.u + d;
+                    OUT[e2 * W + d] = (i >= 0 && i < A.mm) ? acc[d] : 0.0;
+                }
+            }
+        } else if (ns_next > 0) {
+            build_tables(ns_next, tid - 32 * WP0, P0T);
+        }
+        {   // CTA-uniform bookkeeping of the gather (every thread computes the same numbers)
+            const i64 s_done = t == 0 ? sA - 1 : (sA + (i64)t * NS - 1 < sB ? sA + (i64)t * NS - 1 : sB);
+            i64 jl = t >= nsteps ? j1 : s_done - (K - 1) - foff + 1;
+            if (jl > j1) jl = j1;
+            if (jl < jnext) jl = jnext;
+            const int nem = (int)(jl - jnext < CAP ? jl - jnext : CAP);
+            pend_j = jnext; pend_n = nem; jnext += nem;
         }
         __syncthreads();
+        if (t >= nsteps && jnext >= j1) break;
     }
+    if (pend_n > 0) {
+        double *dst = A.band + (size_t)(pend_j - A.col_lo) * W;
+        for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[e];
+    }
+}
+
+static int stream_threads(int K, int NS) {
+    const int QH = (K + 2) / 2, NSR = (NS + 31) & ~31, CAP = NS + K - 1;
+    int nt = NS * QH;                                       // phase 1: one thread per (interval, node pair)
+    const int roles = 2 * NSR + (CAP + 31) / 32 * 32 + 32;  // segment B: local matrices, gather, at least one table warp
+    if (roles > nt) nt = roles;
+    if (NS + 2 * K > nt) nt = NS + 2 * K;                   // knot prefetch: one knot per thread
+    return (nt + 31) / 32 * 32;
 }
 
 static size_t stream_smem_bytes(int K, int NS) {
     const int QH = (K + 2) / 2, KP2 = (K + 1) / 2 * 2, W = 2 * K - 1, NE = K * (K + 1) / 2, MSP = NE | 1;
     const int PIV0 = 2 * QH * KP2, PIV = PIV0 + ((2 - PIV0 % 4) + 4) % 4, QPW = (2 * QH) | 1;
-    const int RING = NS + K - 1, NKP = (NS + 2 * K + 2) / 2 * 2;
+    const int RING = 2 * NS + K - 1, CAP = NS + K - 1, NKP = (NS + 2 * K + 2) / 2 * 2;
     size_t d = (size_t)NS * PIV + (((size_t)NS * QPW + 1) & ~(size_t)1) + (((size_t)RING * MSP + 1) & ~(size_t)1) +
-               (((size_t)RING * W + 1) & ~(size_t)1) + 2 * (size_t)(NKP + 2) + 2 * (size_t)(K * NKP + 2);
-    return d * sizeof(double) + sizeof(int) * (size_t)NS + 16;
+               (((size_t)CAP * W + 1) & ~(size_t)1) + 2 * (size_t)(NKP + 2) + 2 * (size_t)(K * NKP + 2) + (size_t)NKP +
+               (size_t)stream_threads(K, NS) * 6;
+    return d * sizeof(double) + sizeof(int) * 2 * (size_t)NS + 16;
 }
 
 static int stream_ns_override() {
@@ -318,20 +408,30 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
     if (K < 2 || K > 11 || m < 0 || m > 1 || m >= K) return -1;
     if ((B->q + 1) / 2 != (K + 2) / 2) return -1;
     int NS = 64;
-    const int QH = (K + 2) / 2;
-    if (NS * QH > STREAM_MAX_THREADS) NS = STREAM_MAX_THREADS / QH;
     const int ov = stream_ns_override();
     if (ov == 0) return -1;
-    if (ov > 0) NS = ov * QH > STREAM_MAX_THREADS ? STREAM_MAX_THREADS / QH : ov;
+    if (ov > 0) NS = ov;
     if (NS < K) NS = K;
-    while (NS > K && stream_smem_bytes(K, NS) > 220 * 1024) --NS;
+    while (NS > K && (stream_threads(K, NS) > STREAM_MAX_THREADS || stream_smem_bytes(K, NS) > 220 * 1024)) --NS;
+    if (stream_threads(K, NS) > STREAM_MAX_THREADS || stream_smem_bytes(K, NS) > 220 * 1024) return -1;
+    if (col_hi <= col_lo) return CB_OK;
+    const int nt = stream_threads(K, NS);
+    // columns without support in the interval range [s_lo, s_hi) are zero; the kernel gets the others
+    {
+        const int W = 2 * K - 1;
+        const i64 foff = colR0 + 1 - B->ml;
+        i64 jf = s_lo - (K - 1) - foff, jl = s_hi - foff;
+        if (jf < col_lo) jf = col_lo;
+        if (jf > col_hi) jf = col_hi;
+        if (jl > col_hi) jl = col_hi;
+        if (jl < jf) jl = jf;
+        if (jf > col_lo) CB_CUDA(cudaMemsetAsync(band, 0, sizeof(double) * (size_t)W * (size_t)(jf - col_lo), st));
+        if (jl < col_hi) CB_CUDA(cudaMemsetAsync(band + (size_t)W * (size_t)(jl - col_lo), 0, sizeof(double) * (size_t)W * (size_t)(col_hi - jl), st));
+        band += (size_t)W * (size_t)(jf - col_lo);
+        col_lo = jf; col_hi = jl;
+        if (col_hi <= col_lo) return CB_OK;
+    }
     const i64 ncol = col_hi - col_lo;
-    if (ncol <= 0) return CB_OK;
-    int nt = NS * QH;
-    if (2 * NS > nt) nt = 2 * NS;
-    if (NS + K - 1 > nt) nt = NS + K - 1;
-    nt = (nt + 31) / 32 * 32;
-    if (nt > STREAM_MAX_THREADS) return -1;
     i64 ncta = (ncol + NS - 1) / NS;
     if (ncta > CB_NUM_SMS) ncta = CB_NUM_SMS;
     StreamArgs A;
