@@ -55,6 +55,18 @@ template <int K> struct StreamGeom {
     static constexpr int PIV0 = 2 * QH * KP2;
     static constexpr int PIV = PIV0 + ((2 - PIV0 % 4) + 4) % 4;   // = 2 (mod 4): lanes of consecutive intervals hit different banks
     static constexpr int QPW = (2 * QH) | 1;
+    // table row of node 2 lp / 2 lp + 1 of an interval.  Any one-to-one map onto the rows 0 .. q-1 is valid (the local
+    // matrices sum over the rows in storage order); for K = 10 the rows are permuted so that the 16-byte table stores of
+    // a quarter-warp (6 node pairs of one interval + 2 of the next) fall into different banks
+    // (scripts: exhaustive search, 128 instead of 192 wavefronts per 384 threads and store).
+    __host__ __device__ static constexpr int row_even(int lp) {
+        if (K == 10) return (lp & 1) ? 6 - (lp >> 1) : 2 - (lp >> 1);          // 2 6 1 5 0 4
+        return lp;
+    }
+    __host__ __device__ static constexpr int row_odd(int lp) {
+        if (K == 10) return lp == 0 ? 3 : (lp >= 4 ? 3 + lp : 7 + lp);          // 3 8 9 10 7 (8: unused pad pair)
+        return QH + lp;
+    }
     // upper-triangle index of (a, b), a <= b
     __host__ __device__ static constexpr int sidx(int a, int b) { return a <= b ? a * K - a * (a - 1) / 2 + (b - a) : b * K - b * (b - 1) / 2 + (a - b); }
 };
@@ -218,8 +230,10 @@ bspline_assemble_stream_kernel(StreamArgs A) {
     // tables of step t from RAW (threads first, first + stride, ...)
     auto build_tables = [&](int ns, int first, int stride) {
         const int NP = ns + 2 * K;
-        for (int idx = first; idx < K * NP; idx += stride) {
-            const int j = idx / NP, p = idx - j * NP;
+        const int per = stride / K;                         // threads per level (the host gives the role >= K threads)
+        const int j = first / per;
+        if (j >= K) return;
+        for (int p = first - j * per; p < NP; p += per) {
             const double lo = RAW[p];
             if (j == 0) {
                 KN[p] = lo;
@@ -287,15 +301,16 @@ bspline_assemble_stream_kernel(StreamArgs A) {
             else if (A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
             double N0[K], N1[K];
             stream_sweep_pair<K, M>(T, sl1, x0, x1, N0, N1);
-            double2 *te = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + lp1 * KP2);
-            double2 *to = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + (QH + lp1) * KP2);
+            const int re = G::row_even(lp1), ro = G::row_odd(lp1);
+            double2 *te = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + re * KP2);
+            double2 *to = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + ro * KP2);
 #pragma unroll
             for (int a = 0; a < KH; ++a) {
                 te[a] = make_double2(N0[2 * a], 2 * a + 1 < K ? N0[2 * a + 1] : 0.0);
                 if (has1) to[a] = make_double2(N1[2 * a], 2 * a + 1 < K ? N1[2 * a + 1] : 0.0);
             }
-            WL[sl1 * QPW + lp1] = (sgn * w0) * o0;
-            if (has1) WL[sl1 * QPW + QH + lp1] = (sgn * w1) * o1;
+            WL[sl1 * QPW + re] = (sgn * w0) * o0;
+            if (has1) WL[sl1 * QPW + ro] = (sgn * w1) * o1;
         }
         if (tid < ns_next + 2 * K) RAW[tid] = raw_next;
         if (tid < ns_next) ord_next[tid] = ord_n;
@@ -345,10 +360,13 @@ bspline_assemble_stream_kernel(StreamArgs A) {
                     slot = slot + 1 == RING ? 0 : slot + 1;
                 }
                 // band slot d of column j holds row i = j - u + d; with (l, u) = (K-1+ij, K-1-ij) slot d is run entry d
+                const i64 i0 = j - A.u;
+                if (i0 >= 0 && i0 + W <= A.mm) {
 #pragma unroll
-                for (int d = 0; d < W; ++d) {
-                    const i64 i = j - A.u + d;
-                    OUT[e2 * W + d] = (i >= 0 && i < A.mm) ? acc[d] : 0.0;
+                    for (int d = 0; d < W; ++d) OUT[e2 * W + d] = acc[d];
+                } else {
+#pragma unroll
+                    for (int d = 0; d < W; ++d) OUT[e2 * W + d] = (i0 + d >= 0 && i0 + d < A.mm) ? acc[d] : 0.0;
                 }
             }
         } else if (ns_next > 0) {
@@ -374,7 +392,7 @@ bspline_assemble_stream_kernel(StreamArgs A) {
 static int stream_threads(int K, int NS) {
     const int QH = (K + 2) / 2, NSR = (NS + 31) & ~31, CAP = NS + K - 1;
     int nt = NS * QH;                                       // phase 1: one thread per (interval, node pair)
-    const int roles = 2 * NSR + (CAP + 31) / 32 * 32 + 32;  // segment B: local matrices, gather, at least one table warp
+    const int roles = 2 * NSR + (CAP + 31) / 32 * 32 + 32;  // segment B: local matrices, gather, at least one table warp (>= K threads)
     if (roles > nt) nt = roles;
     if (NS + 2 * K > nt) nt = NS + 2 * K;                   // knot prefetch: one knot per thread
     return (nt + 31) / 32 * 32;
@@ -432,27 +450,35 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
         if (col_hi <= col_lo) return CB_OK;
     }
     const i64 ncol = col_hi - col_lo;
+    const size_t smem = stream_smem_bytes(K, NS);
     i64 ncta = (ncol + NS - 1) / NS;
-    if (ncta > CB_NUM_SMS) ncta = CB_NUM_SMS;
     StreamArgs A;
     A.kv = make_knot_view(B);
     A.q = B->q; A.x = B->d_x; A.w = B->d_w; A.ord = B->d_ord;
     A.opvals = opvals; A.coulomb = coulomb; A.Z = Z;
     A.rowL0 = rowL0; A.mm = mm; A.colR0 = colR0; A.nn = nn; A.u = u;
     A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
-    A.cpc = (ncol + ncta - 1) / ncta;
     A.NS = NS;
     A.band = band;
-    const size_t smem = stream_smem_bytes(K, NS);
 #define CB_STREAM_CASE(KT)                                                                                       \
     case KT: {                                                                                                   \
         if (m == 0) {                                                                                            \
             auto kern = bspline_assemble_stream_kernel<KT, 0>;                                                   \
             CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            int per_sm = 1;                                                                                      \
+            CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));                     \
+            if (per_sm < 1) per_sm = 1;                                                                          \
+            if (ncta > (i64)CB_NUM_SMS * per_sm) ncta = (i64)CB_NUM_SMS * per_sm;                               \
+            A.cpc = (ncol + ncta - 1) / ncta;                                                                    \
             kern<<<(int)ncta, nt, smem, st>>>(A);                                                                \
         } else {                                                                                                 \
             auto kern = bspline_assemble_stream_kernel<KT, 1>;                                                   \
             CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+            int per_sm = 1;                                                                                      \
+            CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));                     \
+            if (per_sm < 1) per_sm = 1;                                                                          \
+            if (ncta > (i64)CB_NUM_SMS * per_sm) ncta = (i64)CB_NUM_SMS * per_sm;                               \
+            A.cpc = (ncol + ncta - 1) / ncta;                                                                    \
             kern<<<(int)ncta, nt, smem, st>>>(A);                                                                \
         }                                                                                                        \
     } break;

@@ -277,6 +277,12 @@ __global__ void csc_fill_kernel(const uint32_t *__restrict__ idx_sorted, const d
     }
 }
 
+// hand-written counting-sort path (csc.cu)
+bool cb_csc_fast_applicable(int k, i64 nx, i64 ncols);
+size_t cb_csc_fast_scratch_bytes(i64 nx, i64 ncols);
+int cb_csc_fast(const int32_t *interval, const double *vals, i64 nx, int k, i64 nf, i64 col0, i64 ncols,
+                void *scratch, i64 *colptr, i64 *rowval, double *nzval, cudaStream_t st);
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -459,6 +465,26 @@ int cb_bspline_eval_csc(const cb_bspline *B, const double *x, i64 nx, i64 col0, 
     if (tot >= ((i64)1 << 31)) { cb_set_error("cb_bspline_eval_csc: nx*k >= 2^31, split the point batch"); return CB_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
+    if (cb_csc_fast_applicable(B->k, nx, ncols)) {
+        // one scratch block from the stream-ordered pool: rows of K1 (vals, intervals) + the counters of the counting sort
+        const size_t b_vals = sizeof(double) * (size_t)tot, b_iv = (sizeof(int32_t) * (size_t)nx + 15) & ~(size_t)15;
+        char *scr = nullptr;
+        CB_CUDA(cudaMallocAsync(&scr, b_vals + b_iv + cb_csc_fast_scratch_bytes(nx, ncols), st));
+        double *f_vals = reinterpret_cast<double *>(scr);
+        int32_t *f_iv = reinterpret_cast<int32_t *>(scr + b_vals);
+        int frc = cb_bspline_eval(B, x, nx, 0, f_iv, f_vals, stream);
+        if (frc == CB_OK) frc = cb_csc_fast(f_iv, f_vals, nx, B->k, B->nf, col0, ncols, scr + b_vals + b_iv, colptr, rowval, nzval, st);
+        i64 lastf = 1;
+        cudaError_t fe = frc == CB_OK ? cudaMemcpyAsync(&lastf, colptr + ncols, sizeof(i64), cudaMemcpyDeviceToHost, st) : cudaSuccess;
+        cudaFreeAsync(scr, st);
+        const cudaError_t fe2 = cudaStreamSynchronize(st);
+        if (frc != CB_OK) return frc;
+        if (fe == cudaSuccess) fe = fe2;
+        if (fe != cudaSuccess) { cb_set_error("cb_bspline_eval_csc: %s", cudaGetErrorString(fe)); return CB_ERR_CUDA; }
+        if (nnz_host) *nnz_host = lastf - 1;
+        return CB_OK;
+    }
+    // large column counts: radix sort of (column, entry) keys (library sort)
     int32_t *d_iv = nullptr; double *d_vals = nullptr; uint32_t *d_keys = nullptr, *d_idx = nullptr; void *d_tmp = nullptr;
     i64 n1 = tot ? tot : 1;
     CB_CUDA(cudaMallocAsync(&d_iv, sizeof(int32_t) * (nx ? nx : 1), st));

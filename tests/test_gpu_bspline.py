@@ -93,6 +93,34 @@ def test_eval_csc_structure_exact(cb, name, make):
         assert np.all(S.nzval.cpu().numpy() != 0)                  # exact zeros are not stored
 
 
+@pytest.mark.parametrize("order", ["random", "sorted", "knots", "clustered"])
+def test_eval_csc_counting_sort_large_batches(cb, order):
+    """B[x,:] as SparseMatrixCSC through the hand-written counting sort (csrc/csc.cu) on batches of many blocks:
+    unsorted points, sorted points (one block's points share a column: long runs), every knot as a point (exact
+    zeros are dropped, src/bsplines.jl:217-224) and points clustered in three intervals; full basis and a restriction.
+    colptr / rowval bit-exact against the oracle."""
+    t = cb.LinearKnotSet(7, 0, 100, 1000)
+    B = cb.BSpline(t)
+    te = cbo.expand_knots(t.t, 7)
+    rng = np.random.default_rng(21)
+    if order == "random":
+        x = rng.uniform(-1.0, 101.0, 200_003)                        # some points outside the support
+    elif order == "sorted":
+        x = np.sort(rng.uniform(0.0, 100.0, 150_001))
+    elif order == "knots":
+        x = np.concatenate([np.asarray(t.t), np.asarray(t.t)[::-1], rng.uniform(0, 100, 5000)])
+    else:
+        x = np.concatenate([rng.uniform(3.0, 3.1, 40_000), rng.uniform(50.0, 50.2, 40_000), rng.uniform(99.9, 100.0, 20_000)])
+        rng.shuffle(x)
+    for col0, ncols in [(0, B.nf), (3, B.nf - 10)]:
+        S = B.eval_csc(x, col0, ncols)
+        cp, rv, nz = cbo.bspline_eval_csc(te, 7, 7, x, col0, ncols)
+        assert np.array_equal(S.colptr.cpu().numpy(), cp)
+        assert np.array_equal(S.rowval.cpu().numpy(), rv)
+        np.testing.assert_allclose(S.nzval.cpu().numpy(), nz, rtol=RTOL, atol=1e-300)
+        assert np.all(S.nzval.cpu().numpy() != 0)
+
+
 def test_docs_golden_eval(cb, golden):
     g = golden["docs"]["usage_eval"]
     B = cb.BSpline(cb.LinearKnotSet(g["k"], g["a"], g["b"], g["N"]))
