@@ -130,102 +130,140 @@ scan_apply_kernel(uint32_t *__restrict__ v, i64 n, const unsigned long long *__r
     unsigned long long wpre = 0;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wpre += ws[w];
     unsigned long long run = tile_pre[blockIdx.x] + wpre + inc - s;
+    i64 col = base / nblk, rem = base - col * nblk;           // element base + e is (column col, block rem)
 #pragma unroll
     for (int e = 0; e < SCAN_E; ++e) {
         const i64 i = base + e;
         if (i < n) {
             v[i] = (uint32_t)run;
-            if (i % nblk == 0) colptr[i / nblk] = (i64)run + 1;
+            if (rem == 0) colptr[col] = (i64)run + 1;
         }
         run += x[e];
+        if (++rem == nblk) { rem = 0; ++col; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) colptr[ncols] = (i64)(*total) + 1;
 }
 
 // ---- scatter ----
-// shared memory: wcnt[CSC_WARPS][ncols] (u16), dbase[ncols] (u32: position of the block's run in rowval / nzval),
-// cstart[ncols + 1] (u32: first slot of the column's run inside the block), then the staged entries
-// sval[CSC_P * k], srow[CSC_P * k] (u16: point inside the block), scol[CSC_P * k] (u16)
-__global__ void __launch_bounds__(CSC_P)
-csc_scatter_kernel(const int32_t *__restrict__ interval, const double *__restrict__ vals, i64 nx, int k, i64 nf,
+// shared memory: sval[CSC_P * k] staged values, dbase[ncols] (u32: position of the block's run in rowval / nzval),
+// cstart[ncols + 1] (u32: first slot of the column's run inside the block), wcnt[CSC_WARPS][ncols] (u16: entries of a
+// warp in a column, then the warp's offset inside the column's run), srow / scol[CSC_P * k] (u16)
+template <int K>
+__global__ void __launch_bounds__(CSC_P, 2)
+csc_scatter_kernel(const int32_t *__restrict__ interval, const double *__restrict__ vals, i64 nx, i64 nf,
                    i64 col0, int ncols, i64 nblk, const uint32_t *__restrict__ offs /*[ncols][nblk]*/,
                    i64 *__restrict__ rowval, double *__restrict__ nzval) {
     extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ unsigned wtot[CSC_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nslot = CSC_P * k;
+    constexpr int nslot = CSC_P * K;
     double *sval = reinterpret_cast<double *>(smraw);
     uint32_t *dbase = reinterpret_cast<uint32_t *>(sval + nslot);
     uint32_t *cstart = dbase + ncols;
-    uint16_t *wcnt = reinterpret_cast<uint16_t *>(cstart + ncols + 1);
-    uint16_t *srow = wcnt + (size_t)CSC_WARPS * ncols;
+    uint16_t *wcnt = reinterpret_cast<uint16_t *>(cstart + ncols + 1 + ((ncols + 1) & 1));   // 4-byte words below: even count
+    uint16_t *srow = wcnt + (size_t)CSC_WARPS * (ncols + (ncols & 1));
     uint16_t *scol = srow + nslot;
+    const int ncp = ncols + (ncols & 1);            // u16 row pitch of wcnt (even: rows start on a word)
+    const int cpt = (ncols + CSC_P - 1) / CSC_P;    // columns per thread in the block-wide scan (consecutive)
     for (i64 b = blockIdx.x; b < nblk; b += gridDim.x) {
-        for (int i = threadIdx.x; i < CSC_WARPS * ncols; i += CSC_P) wcnt[i] = 0;
-        for (int c = threadIdx.x; c < ncols; c += CSC_P) dbase[c] = offs[(size_t)c * nblk + b];
-        __syncthreads();
-        // this thread's point and its (at most CB_KMAX) entries
+        {
+            uint32_t *wz = reinterpret_cast<uint32_t *>(wcnt);
+            for (int i = threadIdx.x; i < CSC_WARPS * ncp / 2; i += CSC_P) wz[i] = 0u;
+        }
+        // positions of the block's runs: one 4-byte gather per column (stride nblk), asynchronous — they are needed last
+        for (int c = threadIdx.x; c < ncols; c += CSC_P)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dbase + c)),
+                         "l"(offs + (size_t)c * nblk + b) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // this thread's point and its K entries
         const i64 p = b * CSC_P + threadIdx.x;
         int I = 0;
         if (p < nx) I = interval[p];
-        double v[CB_KMAX];
-        int col[CB_KMAX];
-        unsigned short rk[CB_KMAX];
+        double v[K];
+        int colv[K];
+        unsigned vm = 0;                             // valid entries (column inside the restriction, value != 0)
 #pragma unroll
-        for (int a = 0; a < CB_KMAX; ++a) {
-            v[a] = 0.0; col[a] = -1; rk[a] = 0;
-            if (a < k && I > 0) {
-                v[a] = vals[p * k + a];
-                col[a] = csc_entry_col(I, a, k, nf, col0, ncols, v[a]);
+        for (int a = 0; a < K; ++a) {
+            v[a] = 0.0; colv[a] = -1;
+            if (I > 0) {
+                v[a] = vals[p * K + a];
+                colv[a] = csc_entry_col(I, a, K, nf, col0, ncols, v[a]);
+                if (colv[a] >= 0) vm |= 1u << a;
             }
         }
-        // rank inside the warp: lane after lane (ascending rows) bumps the warp's counters
-        uint16_t *wc = wcnt + (size_t)warp * ncols;
-        for (int L = 0; L < 32; ++L) {
-            if (lane == L) {
+        // rank inside the warp = number of lower lanes (earlier rows) with an entry in the same column.  Lane L' holds
+        // the columns I' - K + 1 + a'; its entry a' = a - (I' - I) is in my column a, so its valid mask shifted by
+        // I' - I lines up with mine.  Lanes further than K-1 intervals away (the usual case for unsorted points) are
+        // skipped by a warp-uniform test.
+        unsigned char rk[K];
 #pragma unroll
-                for (int a = 0; a < CB_KMAX; ++a)
-                    if (col[a] >= 0) { rk[a] = wc[col[a]]; wc[col[a]] = rk[a] + 1; }
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        // per column: counters of the warps -> offsets of the warps inside the column's run; run length -> cstart
-        for (int c = threadIdx.x; c < ncols; c += CSC_P) {
-            unsigned run = 0;
-            for (int w = 0; w < CSC_WARPS; ++w) {
-                const unsigned t = wcnt[(size_t)w * ncols + c];
-                wcnt[(size_t)w * ncols + c] = (uint16_t)run;
-                run += t;
-            }
-            cstart[c] = run;                        // run length for now
-        }
-        __syncthreads();
-        // exclusive scan of the run lengths over the columns (one warp; ncols is a few thousand at most)
-        if (warp == 0) {
-            unsigned carry = 0;
-            for (int base = 0; base < ncols; base += 32) {
-                const int c = base + lane;
-                const unsigned x = c < ncols ? cstart[c] : 0u;
-                unsigned inc = x;
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
+        for (int a = 0; a < K; ++a) rk[a] = 0;
+        unsigned above = 0;                          // my columns that a higher lane also holds
+        for (int Lp = 0; Lp < 32; ++Lp) {
+            const int Ip = __shfl_sync(0xffffffffu, I, Lp);
+            const unsigned vp = __shfl_sync(0xffffffffu, vm, Lp);
+            const int d = Ip - I;
+            if (Lp != lane && d > -K && d < K && vp != 0u && vm != 0u) {
+                const unsigned sh = (d >= 0 ? (vp << d) : (vp >> (-d))) & vm;
+                if (Lp < lane) {
+#pragma unroll
+                    for (int a = 0; a < K; ++a) rk[a] += (sh >> a) & 1u;
+                } else {
+                    above |= sh;
                 }
-                if (c < ncols) cstart[c] = carry + inc - x;
-                carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (lane == 0) cstart[ncols] = carry;
         }
+        __syncthreads();                             // wcnt zeroed
+        // the highest lane of a (warp, column) knows the count
+        uint16_t *wc = wcnt + (size_t)warp * ncp;
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+            if (((vm >> a) & 1u) && !((above >> a) & 1u)) wc[colv[a]] = (uint16_t)(rk[a] + 1);
+        __syncthreads();
+        // per column: counts of the warps -> offsets of the warps inside the column's run, run length -> block scan
+        unsigned mine[8];                            // cpt <= 8 (ncols <= 4096)
+        unsigned tsum = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            mine[e] = 0;
+            const int c = threadIdx.x * cpt + e;
+            if (e < cpt && c < ncols) {
+                unsigned run = 0;
+                for (int w = 0; w < CSC_WARPS; ++w) {
+                    const unsigned t = wcnt[(size_t)w * ncp + c];
+                    wcnt[(size_t)w * ncp + c] = (uint16_t)run;
+                    run += t;
+                }
+                mine[e] = run;
+                tsum += run;
+            }
+        }
+        unsigned inc = tsum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        unsigned pre = inc - tsum;
+        for (int w = 0; w < warp; ++w) pre += wtot[w];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = threadIdx.x * cpt + e;
+            if (e < cpt && c < ncols) { cstart[c] = pre; pre += mine[e]; }
+        }
+        if (threadIdx.x == CSC_P - 1) cstart[ncols] = pre;
         __syncthreads();
         // place the entries in (column, row) order
 #pragma unroll
-        for (int a = 0; a < CB_KMAX; ++a)
-            if (col[a] >= 0) {
-                const unsigned s = cstart[col[a]] + wc[col[a]] + rk[a];
+        for (int a = 0; a < K; ++a)
+            if ((vm >> a) & 1u) {
+                const unsigned s = cstart[colv[a]] + wc[colv[a]] + rk[a];
                 sval[s] = v[a];
                 srow[s] = (uint16_t)threadIdx.x;
-                scol[s] = (uint16_t)col[a];
+                scol[s] = (uint16_t)colv[a];
             }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
         const unsigned tot = cstart[ncols];
         const i64 row0 = b * CSC_P + 1;             // 1-based row of the block's first point
@@ -240,13 +278,13 @@ csc_scatter_kernel(const int32_t *__restrict__ interval, const double *__restric
 }
 
 static size_t csc_scatter_smem(int k, int ncols) {
-    const size_t nslot = (size_t)CSC_P * k;
-    return nslot * 8 + (size_t)ncols * 4 + ((size_t)ncols + 1) * 4 + (size_t)CSC_WARPS * ncols * 2 + nslot * 2 + nslot * 2 + 32;
+    const size_t nslot = (size_t)CSC_P * k, ncp = (size_t)ncols + (ncols & 1);
+    return nslot * 8 + (size_t)ncols * 4 + ((size_t)ncols + 2) * 4 + (size_t)CSC_WARPS * ncp * 2 + nslot * 2 + nslot * 2 + 32;
 }
 
 // True if the hand-written path applies (else the caller falls back to the radix-sort path of bspline.cu).
 bool cb_csc_fast_applicable(int k, i64 nx, i64 ncols) {
-    if (ncols < 1 || ncols > 16384 || nx < 1) return false;
+    if (ncols < 1 || ncols > 8 * CSC_P || nx < 1 || k < 1 || k > CB_KMAX) return false;
     const i64 nblk = (nx + CSC_P - 1) / CSC_P;
     if (nblk * ncols > ((i64)1 << 27)) return false;          // 512 MB of counters
     return csc_scatter_smem(k, (int)ncols) <= 200 * 1024;
@@ -275,12 +313,22 @@ int cb_csc_fast(const int32_t *interval, const double *vals, i64 nx, int k, i64 
     CB_LAUNCH_CHECK();
     if (rowval && nzval) {
         const size_t smem = csc_scatter_smem(k, (int)ncols);
-        CB_CUDA(cudaFuncSetAttribute(csc_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csc_scatter_kernel, CSC_P, smem));
-        if (per_sm < 1) per_sm = 1;
-        const i64 cap = (i64)CB_NUM_SMS * per_sm;
-        csc_scatter_kernel<<<(int)(nblk < cap ? nblk : cap), CSC_P, smem, st>>>(interval, vals, nx, k, nf, col0, (int)ncols, nblk, cnt, rowval, nzval);
+#define CB_CSC_CASE(KT)                                                                                              \
+    case KT: {                                                                                                       \
+        auto kern = csc_scatter_kernel<KT>;                                                                          \
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        int per_sm = 1;                                                                                              \
+        CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CSC_P, smem));                          \
+        if (per_sm < 1) per_sm = 1;                                                                                  \
+        const i64 cap = (i64)CB_NUM_SMS * per_sm;                                                                    \
+        kern<<<(int)(nblk < cap ? nblk : cap), CSC_P, smem, st>>>(interval, vals, nx, nf, col0, (int)ncols, nblk, cnt, rowval, nzval); \
+    } break;
+        switch (k) {
+            CB_CSC_CASE(1) CB_CSC_CASE(2) CB_CSC_CASE(3) CB_CSC_CASE(4) CB_CSC_CASE(5) CB_CSC_CASE(6) CB_CSC_CASE(7) CB_CSC_CASE(8)
+            CB_CSC_CASE(9) CB_CSC_CASE(10) CB_CSC_CASE(11) CB_CSC_CASE(12) CB_CSC_CASE(13) CB_CSC_CASE(14) CB_CSC_CASE(15) CB_CSC_CASE(16)
+            default: cb_set_error("cb_bspline_eval_csc: order k=%d outside 1..%d", k, CB_KMAX); return CB_ERR_UNSUPPORTED;
+        }
+#undef CB_CSC_CASE
         CB_LAUNCH_CHECK();
     }
     return CB_OK;
