@@ -51,45 +51,7 @@ __device__ void bspline_all_rt(int k, const double *tw, double x, int m, double 
 // 28-52), which the reference stores as a sparse matrix in memory, never
 // leaves the SM.
 // ---------------------------------------------------------------------------
-// Fused halo exchange of an interval-sharded assembly.  A rank sums its own intervals into every
-// column that touches them.  Its first n_push columns belong to the LEFT neighbour: they are stored straight into that
-// neighbour's mailbox over NVLink (peer-mapped memory) and, once every tile that holds such a column has finished, a
-// flag is raised there.  Its last n_recv columns also live on the RIGHT neighbour's intervals: the tiles that hold them
-// wait for the local flag (the right neighbour handles its pushed tiles first, these tiles come last, so the wait is
-// normally over before it starts) and add the mailbox to their own sums.  No host round trip, no collective launch.
-// Mailboxes are double-buffered by call parity; `ack` words tell the pusher that the buffer of two calls ago has been
-// consumed.  Every spin is bounded (status word).
-struct AsmHalo {
-    int n_push, n_recv;
-    int n_push_tiles, n_recv_tiles;
-    double *push_cols;                      // peer: left neighbour's mailbox columns of this parity
-    unsigned long long *push_flag;          // peer: its flag of this parity
-    const double *recv_cols;                // local mailbox columns of this parity
-    unsigned long long *recv_flag;          // local flag of this parity (written by the right neighbour)
-    unsigned long long *ack_out;            // peer: right neighbour's ack word of this parity (we write the epoch after consuming)
-    unsigned long long *ack_in;             // local ack word of this parity (the left neighbour consumed that epoch)
-    unsigned long long epoch;
-    unsigned int *counters;                 // local: [0] pushed tiles finished, [1] receiving tiles finished
-    int *status;                            // local: non-zero after a spin timeout
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// waits until *p >= want; gives up after ~15 s (a peer that never launched must not hang the GPU for good, but ranks of one
-// job may legitimately be seconds apart: host-side work between calls, first-call initialisation)
-__device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long want, int *status) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > 30000000000ll) { atomicExch(status, 1); break; }
-        __nanosleep(64);
-    }
-}
+#include "asm_halo.cuh"
 
 struct AsmArgs {
     KnotView kvL, kvR;
@@ -805,7 +767,8 @@ static int ensure_rc_index() {
 }
 
 int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int coulomb, double Z, i64 rowL0, i64 mm, i64 colR0,
-                         i64 nn, int u, i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st);   // assemble_stream.cu
+                         i64 nn, int u, i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st,
+                         const AsmHalo *halo);   // assemble_stream.cu
 
 static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
                            int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
@@ -832,9 +795,9 @@ static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int 
     if (col_hi == col_lo) return CB_OK;
     { int rc_ = ensure_rc_index(); if (rc_) return rc_; }
     cudaStream_t st = (cudaStream_t)stream;
-    // ---- streaming kernel (assemble_stream.cu): the same basis on both sides, a == b <= 1, no fused halo ----
-    if (!halo && a == b && L->k == R->k && L->ml == R->ml && L->nf == R->nf) {
-        const int src = cb_asm_stream_launch(R, a, opvals, coulomb, Z, rowL0, m, colR0, n, u, col_lo, col_hi, s_lo, s_hi, band, st);
+    // ---- streaming kernel (assemble_stream.cu): the same basis on both sides, a == b <= 1 ----
+    if (a == b && L->k == R->k && L->ml == R->ml && L->nf == R->nf) {
+        const int src = cb_asm_stream_launch(R, a, opvals, coulomb, Z, rowL0, m, colR0, n, u, col_lo, col_hi, s_lo, s_hi, band, st, halo);
         if (src >= 0) return src;
     }
     AsmArgs A;

@@ -29,6 +29,7 @@
 // start of segment A of step t, the nodes / weights of its phase-1 items arrive by cp.async during segment B.  Halo
 // work is the K - 1 intervals at the end of a CTA's range (1.3 % at the C3 size).
 #include "bspline_core.cuh"
+#include "asm_halo.cuh"
 
 struct StreamArgs {
     KnotView kv;
@@ -43,6 +44,7 @@ struct StreamArgs {
     i64 cpc;                      // columns per CTA
     int NS;                       // intervals per step
     double *band;                 // column col_lo at band[0]
+    AsmHalo H;                    // interval-sharded assembly: fused halo exchange over peer memory (all zero: none)
 };
 
 constexpr int STREAM_MAX_THREADS = 384;
@@ -178,6 +180,45 @@ __device__ __forceinline__ void stream_local_rows(const double *tv, const double
     for (int i = 0; i < E1 - E0; ++i) m[E0 + i] = acc[i];
 }
 
+// The completed columns [pj, pj + pn) leave the SM.  Plain case: one contiguous, fully coalesced copy.  With a fused halo
+// (asm_halo.cuh) the first n_push columns of the call go to the left neighbour's mailbox instead, and the last n_recv
+// columns first add what the right neighbour pushed; the flags are raised / awaited by this CTA alone (the host makes
+// steps long enough for each group to sit in one emission of one CTA).  All conditions are CTA-uniform.
+template <int W>
+__device__ __forceinline__ void stream_copy_out(const StreamArgs &A, const double *OUT, i64 pj, int pn, int tid, int NT) {
+    const AsmHalo &H = A.H;
+    const bool psh = H.n_push > 0 && pj < A.col_lo + H.n_push;
+    const bool rcv = H.n_recv > 0 && pj + pn > A.col_hi - H.n_recv;
+    double *dst = A.band + (size_t)(pj - A.col_lo) * W;
+    if (!psh && !rcv) {
+        for (int e = tid; e < pn * W; e += NT) dst[e] = OUT[e];
+        return;
+    }
+    if (tid == 0) {
+        if (rcv) halo_spin(H.recv_flag, H.epoch, H.status);
+        if (psh && H.epoch > 2) halo_spin(H.ack_in, H.epoch - 2, H.status);      // the buffer of this parity has been consumed
+    }
+    __syncthreads();
+    const i64 push_end = A.col_lo + H.n_push, recv_beg = A.col_hi - H.n_recv;
+    for (int e = tid; e < pn * W; e += NT) {
+        const int jj = e / W;
+        const i64 j = pj + jj;
+        double v = OUT[e];
+        if (H.n_push > 0 && j < push_end) {
+            H.push_cols[(size_t)(j - A.col_lo) * W + (e - jj * W)] = v;
+        } else {
+            if (H.n_recv > 0 && j >= recv_beg) v += __ldcv(H.recv_cols + (size_t)(j - recv_beg) * W + (e - jj * W));
+            dst[e] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        if (psh && pj + pn >= push_end) st_release_sys(H.push_flag, H.epoch);     // every pushed column has left
+        if (rcv && pj + pn >= A.col_hi) st_release_sys(H.ack_out, H.epoch);       // mailbox consumed
+    }
+}
+
 template <int K, int M>
 __global__ void __launch_bounds__(STREAM_MAX_THREADS, 1)
 bspline_assemble_stream_kernel(StreamArgs A) {
@@ -288,8 +329,7 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         if (tid < ns_next + 2 * K) raw_next = A.kv.at(raw_index(t + 1, tid));          // lands while phase 1 runs
         if (tid < ns_next) ord_n = A.ord[s0 + NS + tid + ml - 1];
         if (pend_n > 0) {
-            double *dst = A.band + (size_t)(pend_j - A.col_lo) * W;
-            for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[e];
+            stream_copy_out<W>(A, OUT, pend_j, pend_n, tid, NT);
             pend_n = 0;
         }
         cp_async_wait_all();
@@ -383,10 +423,7 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         __syncthreads();
         if (t >= nsteps && jnext >= j1) break;
     }
-    if (pend_n > 0) {
-        double *dst = A.band + (size_t)(pend_j - A.col_lo) * W;
-        for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[e];
-    }
+    if (pend_n > 0) stream_copy_out<W>(A, OUT, pend_j, pend_n, tid, NT);
 }
 
 static int stream_threads(int K, int NS) {
@@ -421,7 +458,7 @@ static int stream_ns_override() {
 // (the caller then takes the tiled / generic kernels of assemble.cu).
 int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int coulomb, double Z,
                          i64 rowL0, i64 mm, i64 colR0, i64 nn, int u,
-                         i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st) {
+                         i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st, const AsmHalo *halo) {
     const int K = B->k;
     if (K < 2 || K > 11 || m < 0 || m > 1 || m >= K) return -1;
     if ((B->q + 1) / 2 != (K + 2) / 2) return -1;
@@ -435,7 +472,8 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
     if (col_hi <= col_lo) return CB_OK;
     const int nt = stream_threads(K, NS);
     // columns without support in the interval range [s_lo, s_hi) are zero; the kernel gets the others
-    {
+    // (an interval-sharded call passes exactly the columns that touch its range: nothing to clip)
+    if (!halo) {
         const int W = 2 * K - 1;
         const i64 foff = colR0 + 1 - B->ml;
         i64 jf = s_lo - (K - 1) - foff, jl = s_hi - foff;
@@ -460,6 +498,13 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
     A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
     A.NS = NS;
     A.band = band;
+    memset(&A.H, 0, sizeof(A.H));
+    if (halo) {
+        A.H = *halo;
+        // the pushed columns must leave with the first emission of the first CTA, the receiving ones arrive with the
+        // last emission of the last CTA: both hold when a step covers at least 2K - 1 columns and CTAs are longer than that
+        if (NS < 2 * K || ncol < 4 * (i64)K) return -1;
+    }
 #define CB_STREAM_CASE(KT)                                                                                       \
     case KT: {                                                                                                   \
         if (m == 0) {                                                                                            \
