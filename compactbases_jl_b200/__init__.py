@@ -13,7 +13,7 @@ from .quadrature import gausslegendre, gausslobatto, num_quadrature_points
 from .lazy import CoulombDerivative, Derivative, QuasiDiagonal, materialize
 from .operators import (BandCholesky, BandLU, BandedMatrix, BlockSkylineMatrix, ColMajor, Diagonal, FEDVRMatrix, ImplicitDerivative, LinearOperator, ShiftAndInvert,
                         SymTridiagonal, Tridiagonal, as_banded, axpby, batched_dot, factorize, inner_product, mul, norm)
-from .bsplines import BSpline, CoulombPotential, RestrictedBSpline, SparseMatrixCSC, diffop, diffop_host
+from .bsplines import BSpline, CoulombPotential, RestrictedBSpline, SparseMatrixCSC, diffop, diffop_host, hamiltonian_bands
 from .fedvr import FEDVR, RestrictedFEDVR
 from .finite_differences import (FiniteDifferences, ImplicitFiniteDifferences, RestrictedFiniteDifferences,
                                  StaggeredFiniteDifferences)
@@ -21,7 +21,7 @@ from .densities import Density, DiagonalOperator, FunctionProduct
 
 __all__ = [
     "ArbitraryKnotSet", "ExpKnotSet", "LinearKnotSet", "BSpline", "RestrictedBSpline", "SparseMatrixCSC",
-    "CoulombPotential", "diffop", "diffop_host", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
+    "CoulombPotential", "diffop", "diffop_host", "hamiltonian_bands", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
     "RestrictedFiniteDifferences", "Derivative", "QuasiDiagonal", "CoulombDerivative", "materialize",
     "BandedMatrix", "BlockSkylineMatrix", "BandCholesky", "LinearOperator", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
     "Density", "FunctionProduct", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "batched_dot", "inner_product", "norm", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",

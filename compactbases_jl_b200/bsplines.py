@@ -211,6 +211,24 @@ def diffop(L, R, a: int, b: int, ops=()):
     return dest
 
 
+def hamiltonian_bands(R, op=None, out=None):
+    """``(R'*QuasiDiagonal(op)*R, R'*D'*D*R)`` from one launch (``cb_bspline_assemble_pair``): what a radial
+    Hamiltonian needs (test/bsplines/operators.jl:15-22, docs/src/bsplines/eigenproblems.md).  ``op``: None (mass
+    matrix), a QuasiDiagonal / callable / nodal-value tensor, or a CoulombPotential (evaluated on chip).  The entries
+    are bit-identical to ``R.T @ op @ R`` and ``R.T @ D.T @ D @ R``."""
+    P = R.parent_basis
+    k = R.order()
+    n = R.ncols
+    V, T = out if out is not None else (BandedMatrix.undef(n, n, k - 1, k - 1, P.device), BandedMatrix.undef(n, n, k - 1, k - 1, P.device))
+    opvals, coulomb, Z = None, 0, 0.0
+    if isinstance(op, CoulombPotential):
+        coulomb, Z = 1, float(op.Z)
+    elif op is not None:
+        opvals = P.nodal_values(op.diag if isinstance(op, QuasiDiagonal) else op)
+    _lib.call("cb_bspline_assemble_pair", P.handle, _ptr(opvals), coulomb, Z, R.col0, n, _ptr(V.data), _ptr(T.data), _stream())
+    return V, T
+
+
 def diffop_host(L, R, a: int, b: int, ops=()) -> np.ndarray:
     """``diffop!`` into a HOST BandedMatrix (``cb_bspline_assemble_host``): returns the band data as an (n, l+u+1)
     numpy array (column-major (l+u+1) x n).  ops: QuasiDiagonal factors (callables are evaluated on the host at

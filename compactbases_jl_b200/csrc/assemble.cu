@@ -768,7 +768,7 @@ static int ensure_rc_index() {
 
 int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int coulomb, double Z, i64 rowL0, i64 mm, i64 colR0,
                          i64 nn, int u, i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st,
-                         const AsmHalo *halo);   // assemble_stream.cu
+                         const AsmHalo *halo, double *band2 = nullptr);   // assemble_stream.cu
 
 static int assemble_common(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals,
                            int coulomb, double Z, i64 rowL0, i64 m, i64 colR0, i64 n, int l, int u,
@@ -909,6 +909,26 @@ int cb_bspline_assemble_part(const cb_bspline *L, const cb_bspline *R, int a, in
                              i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band_cols, void *stream) {
     return assemble_common(L, R, a, b, opvals, coulomb, Z, rowL0, m, colR0, n, l, u, col_lo, col_hi, s_lo, s_hi,
                            band_cols, stream);
+}
+
+// The Hamiltonian pair of a (restricted) basis R = B[:, col0+1 : col0+n]: R'*QuasiDiagonal(op)*R and R'*D'*D*R.  One
+// kernel evaluates values and first derivatives of the basis at every node with a shared Cox-de Boor sweep and builds
+// both bands (assemble_stream.cu, mode 2); outside that kernel's range the two matrices are assembled one after the other.
+int cb_bspline_assemble_pair(const cb_bspline *B, const double *opvals, int coulomb, double Z,
+                             i64 col0, i64 n, double *bandV, double *bandT, void *stream) {
+    CB_REQUIRE(B != nullptr && bandV != nullptr && bandT != nullptr, "cb_bspline_assemble_pair: NULL argument");
+    CB_REQUIRE(col0 >= 0 && n >= 0 && col0 + n <= B->nf, "cb_bspline_assemble_pair: restriction outside 1..nf");
+    CB_REQUIRE(coulomb == 0 || coulomb == 1, "cb_bspline_assemble_pair: coulomb must be 0 or 1");
+    if (n == 0) return CB_OK;
+    const int k = B->k;
+    if (k >= 2) {
+        const int src = cb_asm_stream_launch(B, 2, opvals, coulomb, Z, col0, n, col0, n, k - 1, 0, n, 0, B->n_tt - 1, bandV,
+                                             (cudaStream_t)stream, nullptr, bandT);
+        if (src >= 0) return src;
+    }
+    int rc = assemble_common(B, B, 0, 0, opvals, coulomb, Z, col0, n, col0, n, k - 1, k - 1, 0, n, 0, B->n_tt - 1, bandV, stream);
+    if (rc) return rc;
+    return assemble_common(B, B, 1, 1, nullptr, 0, 0.0, col0, n, col0, n, k - 1, k - 1, 0, n, 0, B->n_tt - 1, bandT, stream);
 }
 
 // Host-pointer convenience form: the band is assembled on the device and copied into a host

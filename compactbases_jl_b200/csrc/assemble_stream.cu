@@ -44,6 +44,7 @@ struct StreamArgs {
     i64 cpc;                      // columns per CTA
     int NS;                       // intervals per step
     double *band;                 // column col_lo at band[0]
+    double *band2;                // pair mode: the derivative matrix (band gets the potential matrix)
     AsmHalo H;                    // interval-sharded assembly: fused halo exchange over peer memory (all zero: none)
 };
 
@@ -112,9 +113,9 @@ __device__ __forceinline__ void stream_sweep_pair(const StreamTab &T, int sl, do
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
             for (int r = 0; r < j; ++r) {
-                const double t0 = N0[r] * rc[r], t1 = N1[r] * rc[r];
+                const double t0 = __dmul_rn(N0[r], rc[r]), t1 = __dmul_rn(N1[r], rc[r]);
                 N0[r] = fma(dh0[r], t0, s0); N1[r] = fma(dh1[r], t1, s1);
-                s0 = dl0[K - j + r] * t0; s1 = dl1[K - j + r] * t1;
+                s0 = __dmul_rn(dl0[K - j + r], t0); s1 = __dmul_rn(dl1[K - j + r], t1);
             }
             N0[j] = s0; N1[j] = s1;
         } else {
@@ -122,10 +123,83 @@ __device__ __forceinline__ void stream_sweep_pair(const StreamTab &T, int sl, do
 #pragma unroll
             for (int r = 0; r <= j; ++r) {
                 double q0 = 0.0, q1 = 0.0;
-                if (r < j) { q0 = N0[r] * rc[r]; q1 = N1[r] * rc[r]; }
-                N0[r] = (double)j * (p0_ - q0); N1[r] = (double)j * (p1_ - q1);
+                // (rounded products: the same numbers as the value + derivative sweep below, whatever the compiler contracts)
+                if (r < j) { q0 = __dmul_rn(N0[r], rc[r]); q1 = __dmul_rn(N1[r], rc[r]); }
+                N0[r] = (double)j * __dsub_rn(p0_, q0); N1[r] = (double)j * __dsub_rn(p1_, q1);
                 p0_ = q0; p1_ = q1;
             }
+        }
+    }
+}
+
+// Values AND first derivatives of the K live functions at the two nodes from one sweep (the Hamiltonian pair
+// B'VB, B'D'DB): the levels 1 .. K-2 are shared, the last level gives the values (Cox-de Boor step) and the
+// derivatives ((K-1) * difference of the scaled order-(K-1) functions) from the same products t_r = N_r / width_r.
+// Same operations as stream_sweep_pair<K, 0> / <K, 1>, hence bit-identical tables.  Rows are stored as they are formed.
+template <int K>
+__device__ __forceinline__ void stream_sweep_pair_vd(const StreamTab &T, int sl, double x0, double x1, bool has1,
+                                                     double2 *ve, double2 *vo, double2 *de, double2 *dd) {
+    double dh0[K], dh1[K], dl0[K], dl1[K];
+    {
+        const double2 *k2 = reinterpret_cast<const double2 *>(T.sm + T.kn + (sl & 1) * T.kn_copy + (sl & ~1));
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            const double2 v = k2[t];
+            if (2 * t < K) { dl0[2 * t] = x0 - v.x; dl1[2 * t] = x1 - v.x; }
+            else { dh0[2 * t - K] = v.x - x0; dh1[2 * t - K] = v.x - x1; }
+            if (2 * t + 1 < K) { dl0[2 * t + 1] = x0 - v.y; dl1[2 * t + 1] = x1 - v.y; }
+            else { dh0[2 * t + 1 - K] = v.y - x0; dh1[2 * t + 1 - K] = v.y - x1; }
+        }
+    }
+    double N0[K], N1[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) { N0[r] = 0.0; N1[r] = 0.0; }
+    N0[0] = 1.0; N1[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= K - 2; ++j) {
+        const int p0 = sl + K - j;
+        const double2 *r2 = reinterpret_cast<const double2 *>(T.sm + T.rd + (p0 & 1) * T.rd_copy + j * T.pitch + (p0 & ~1));
+        double rc[K];
+#pragma unroll
+        for (int h = 0; h < (j + 1) / 2; ++h) { const double2 v = r2[h]; rc[2 * h] = v.x; if (2 * h + 1 < K) rc[2 * h + 1] = v.y; }
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            const double t0 = N0[r] * rc[r], t1 = N1[r] * rc[r];
+            N0[r] = fma(dh0[r], t0, s0); N1[r] = fma(dh1[r], t1, s1);
+            s0 = dl0[K - j + r] * t0; s1 = dl1[K - j + r] * t1;
+        }
+        N0[j] = s0; N1[j] = s1;
+    }
+    // last level, j = K - 1: t[r] = N[r] / width, r < K - 1
+    double t0[K + 1], t1[K + 1];                    // t[r + 1] holds t_r; t[0] = t_{-1} = 0, t[K] = t_{K-1} = 0
+    {
+        constexpr int j = K - 1;
+        const int p0 = sl + K - j;
+        const double2 *r2 = reinterpret_cast<const double2 *>(T.sm + T.rd + (p0 & 1) * T.rd_copy + j * T.pitch + (p0 & ~1));
+        double rc[K];
+#pragma unroll
+        for (int h = 0; h < (j + 1) / 2; ++h) { const double2 v = r2[h]; rc[2 * h] = v.x; if (2 * h + 1 < K) rc[2 * h + 1] = v.y; }
+        t0[0] = 0.0; t1[0] = 0.0; t0[K] = 0.0; t1[K] = 0.0;
+#pragma unroll
+        for (int r = 0; r < K - 1; ++r) { t0[r + 1] = __dmul_rn(N0[r], rc[r]); t1[r + 1] = __dmul_rn(N1[r], rc[r]); }
+    }
+    auto val = [&](const double (&dh)[K], const double (&dl)[K], const double (&t)[K + 1], int r) -> double {
+        // N_r = dh[r] t_r + dl[r] t_{r-1}   (the sweep's  fma(dh[r], t_r, s_r),  s_r = dl[r] * t_{r-1};  N_{K-1} = s_{K-1})
+        if (r >= K) return 0.0;
+        const double s = r >= 1 ? __dmul_rn(dl[r], t[r]) : 0.0;
+        return r < K - 1 ? fma(dh[r], t[r + 1], s) : s;
+    };
+    auto der = [&](const double (&t)[K + 1], int r) -> double {
+        return r < K ? (double)(K - 1) * __dsub_rn(t[r], t[r + 1]) : 0.0;
+    };
+#pragma unroll
+    for (int a = 0; a < (K + 1) / 2; ++a) {
+        ve[a] = make_double2(val(dh0, dl0, t0, 2 * a), val(dh0, dl0, t0, 2 * a + 1));
+        de[a] = make_double2(der(t0, 2 * a), der(t0, 2 * a + 1));
+        if (has1) {
+            vo[a] = make_double2(val(dh1, dl1, t1, 2 * a), val(dh1, dl1, t1, 2 * a + 1));
+            dd[a] = make_double2(der(t1, 2 * a), der(t1, 2 * a + 1));
         }
     }
 }
@@ -226,20 +300,23 @@ bspline_assemble_stream_kernel(StreamArgs A) {
     using G = StreamGeom<K>;
     constexpr int QH = G::QH, KP2 = G::KP2, KH = G::KH, W = G::W, NE = G::NE, MSP = G::MSP, PIV = G::PIV, QPW = G::QPW;
     constexpr int AS = StreamSplit<K>::AS;
+    constexpr int NM = M == 2 ? 2 : 1;                     // M == 2: the pair (values | first derivatives) from one sweep
     const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5;
     const int q = A.q, NS = A.NS, NSR = (NS + 31) & ~31, RING = 2 * NS + K - 1, CAP = NS + K - 1;
     const int NKP = (NS + 2 * K + 2) / 2 * 2;
     const int ml = A.kv.ml;
     const i64 n_tt = A.kv.n_tt;
     // roles of the second segment of a step: warps [0, W2B) local matrices, [W2B, WP0) gather, [WP0, ..) tables
-    const int W2B = 2 * NSR / 32, WP0 = W2B + (CAP + 31) / 32;
+    const int W2A = 2 * NSR / 32, W2B = NM * W2A, GW = (CAP + 31) / 32, WP0 = W2B + NM * GW;
     const int P0T = NT - 32 * WP0;
     // shared memory carve-up (every region starts on a 16-byte boundary)
-    double *TV = sm;                                         // [NS][PIV]   node-major tables, even nodes first
-    double *WL = TV + (size_t)NS * PIV;                      // [NS][QPW]   (-1)^m w op at the node positions
-    double *MS = WL + (((size_t)NS * QPW + 1) & ~(size_t)1); // [RING][MSP] upper triangles of the local matrices
-    double *OUT = MS + (((size_t)RING * MSP + 1) & ~(size_t)1);   // [CAP][W] staging tile of completed columns
-    double *KN = OUT + (((size_t)CAP * W + 1) & ~(size_t)1); // [2][NKP + 2]
+    const size_t TVS = (size_t)NS * PIV, WLS = ((size_t)NS * QPW + 1) & ~(size_t)1, MSS = ((size_t)RING * MSP + 1) & ~(size_t)1,
+                 OUTS = ((size_t)CAP * W + 1) & ~(size_t)1;
+    double *TV = sm;                                         // [NM][NS][PIV]   node-major tables, even nodes first
+    double *WL = TV + NM * TVS;                              // [NM][NS][QPW]   (-1)^m w op at the node positions
+    double *MS = WL + NM * WLS;                              // [NM][RING][MSP] upper triangles of the local matrices
+    double *OUT = MS + NM * MSS;                             // [NM][CAP][W]    staging tiles of completed columns
+    double *KN = OUT + NM * OUTS;                            // [2][NKP + 2]
     double *RD = KN + 2 * (NKP + 2);                         // [2][K * NKP + 2]
     double *RAW = RD + (size_t)2 * (K * NKP + 2);            // [NKP] knots of the next step
     double *NODE = RAW + NKP;                                // [NT][6] x0 x1 w0 w1 o0 o1 of the next step's phase-1 items
@@ -330,6 +407,10 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         if (tid < ns_next) ord_n = A.ord[s0 + NS + tid + ml - 1];
         if (pend_n > 0) {
             stream_copy_out<W>(A, OUT, pend_j, pend_n, tid, NT);
+            if (NM == 2) {
+                double *dst = A.band2 + (size_t)(pend_j - A.col_lo) * W;
+                for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[OUTS + e];
+            }
             pend_n = 0;
         }
         cp_async_wait_all();
@@ -339,18 +420,25 @@ bspline_assemble_stream_kernel(StreamArgs A) {
             if (A.coulomb != 2) { w0 = node[2]; w1 = node[3]; }
             if (A.opvals) { o0 = node[4]; o1 = node[5]; }
             else if (A.coulomb == 1) { o0 = -A.Z * fast_rcp(x0); o1 = -A.Z * fast_rcp(x1); }
-            double N0[K], N1[K];
-            stream_sweep_pair<K, M>(T, sl1, x0, x1, N0, N1);
             const int re = G::row_even(lp1), ro = G::row_odd(lp1);
             double2 *te = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + re * KP2);
             double2 *to = reinterpret_cast<double2 *>(TV + (size_t)sl1 * PIV + ro * KP2);
+            if (NM == 2) {
+                stream_sweep_pair_vd<K>(T, sl1, x0, x1, has1, te, to, te + TVS / 2, to + TVS / 2);
+                WL[sl1 * QPW + re] = w0 * o0;                       // potential term
+                WL[WLS + sl1 * QPW + re] = -w0;                     // (-1)^1 <B'|B'>, src/bspline_derivatives.jl:14
+                if (has1) { WL[sl1 * QPW + ro] = w1 * o1; WL[WLS + sl1 * QPW + ro] = -w1; }
+            } else {
+                double N0[K], N1[K];
+                stream_sweep_pair<K, (M == 2 ? 0 : M)>(T, sl1, x0, x1, N0, N1);
 #pragma unroll
-            for (int a = 0; a < KH; ++a) {
-                te[a] = make_double2(N0[2 * a], 2 * a + 1 < K ? N0[2 * a + 1] : 0.0);
-                if (has1) to[a] = make_double2(N1[2 * a], 2 * a + 1 < K ? N1[2 * a + 1] : 0.0);
+                for (int a = 0; a < KH; ++a) {
+                    te[a] = make_double2(N0[2 * a], 2 * a + 1 < K ? N0[2 * a + 1] : 0.0);
+                    if (has1) to[a] = make_double2(N1[2 * a], 2 * a + 1 < K ? N1[2 * a + 1] : 0.0);
+                }
+                WL[sl1 * QPW + re] = (sgn * w0) * o0;
+                if (has1) WL[sl1 * QPW + ro] = (sgn * w1) * o1;
             }
-            WL[sl1 * QPW + re] = (sgn * w0) * o0;
-            if (has1) WL[sl1 * QPW + ro] = (sgn * w1) * o1;
         }
         if (tid < ns_next + 2 * K) RAW[tid] = raw_next;
         if (tid < ns_next) ord_next[tid] = ord_n;
@@ -358,17 +446,19 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         // ======== segment B: three roles side by side ========
         prefetch_nodes(ns_next, ord_next);
         if (warp < W2B) {
-            // ---- local matrices of step t: thread (interval, row half) ----
-            const int h = tid >= NSR ? 1 : 0, sl = tid - h * NSR;
+            // ---- local matrices of step t: thread (matrix, row half, interval) ----
+            const int mi = NM == 2 ? warp / W2A : 0;
+            const int tm = tid - mi * 2 * NSR;
+            const int h = tm >= NSR ? 1 : 0, sl = tm - h * NSR;
             if (sl < ns) {
                 int slot = (int)((s0 + sl - sA) % RING);
-                double *m = MS + (size_t)slot * MSP;
+                double *m = MS + mi * MSS + (size_t)slot * MSP;
                 if (ord_cur[sl] < 0) {
                     if (h == 0) { for (int i = 0; i < G::sidx(AS, AS); ++i) m[i] = 0.0; }
                     else { for (int i = G::sidx(AS, AS); i < NE; ++i) m[i] = 0.0; }
                 } else {
-                    const double *tv = TV + (size_t)sl * PIV;
-                    const double *wl = WL + sl * QPW;
+                    const double *tv = TV + mi * TVS + (size_t)sl * PIV;
+                    const double *wl = WL + mi * WLS + sl * QPW;
                     // node positions: even nodes 0..QH-1, odd nodes QH..q-1 (contiguous)
                     if (h == 0) stream_local_rows<K, 0, AS>(tv, wl, q, m);
                     else stream_local_rows<K, AS, K>(tv, wl, q, m);
@@ -381,7 +471,10 @@ bspline_assemble_stream_kernel(StreamArgs A) {
             if (jl > j1) jl = j1;
             if (jl < jnext) jl = jnext;
             const int nem = (int)(jl - jnext < CAP ? jl - jnext : CAP);
-            const int e2 = tid - 32 * W2B;
+            const int gi = NM == 2 ? (warp - W2B) / GW : 0;        // which matrix this gather warp serves
+            const int e2 = tid - 32 * (W2B + gi * GW);
+            const double *MSg = MS + gi * MSS;
+            double *OUTg = OUT + gi * OUTS;
             if (e2 < nem) {
                 const i64 j = jnext + e2, f0 = j + foff;
                 double acc[W];
@@ -393,7 +486,7 @@ bspline_assemble_stream_kernel(StreamArgs A) {
                 for (int r = 0; r < K; ++r) {
                     const i64 s = f0 + r;
                     if (s >= sA && s <= s_done) {
-                        const double *m = MS + (size_t)slot * MSP;
+                        const double *m = MSg + (size_t)slot * MSP;
 #pragma unroll
                         for (int a = 0; a < K; ++a) acc[a + r] += m[G::sidx(a, K - 1 - r)];
                     }
@@ -403,10 +496,10 @@ bspline_assemble_stream_kernel(StreamArgs A) {
                 const i64 i0 = j - A.u;
                 if (i0 >= 0 && i0 + W <= A.mm) {
 #pragma unroll
-                    for (int d = 0; d < W; ++d) OUT[e2 * W + d] = acc[d];
+                    for (int d = 0; d < W; ++d) OUTg[e2 * W + d] = acc[d];
                 } else {
 #pragma unroll
-                    for (int d = 0; d < W; ++d) OUT[e2 * W + d] = (i0 + d >= 0 && i0 + d < A.mm) ? acc[d] : 0.0;
+                    for (int d = 0; d < W; ++d) OUTg[e2 * W + d] = (i0 + d >= 0 && i0 + d < A.mm) ? acc[d] : 0.0;
                 }
             }
         } else if (ns_next > 0) {
@@ -423,25 +516,31 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         __syncthreads();
         if (t >= nsteps && jnext >= j1) break;
     }
-    if (pend_n > 0) stream_copy_out<W>(A, OUT, pend_j, pend_n, tid, NT);
+    if (pend_n > 0) {
+        stream_copy_out<W>(A, OUT, pend_j, pend_n, tid, NT);
+        if (NM == 2) {
+            double *dst = A.band2 + (size_t)(pend_j - A.col_lo) * W;
+            for (int e = tid; e < pend_n * W; e += NT) dst[e] = OUT[OUTS + e];
+        }
+    }
 }
 
-static int stream_threads(int K, int NS) {
+static int stream_threads(int K, int NS, int NM = 1) {
     const int QH = (K + 2) / 2, NSR = (NS + 31) & ~31, CAP = NS + K - 1;
     int nt = NS * QH;                                       // phase 1: one thread per (interval, node pair)
-    const int roles = 2 * NSR + (CAP + 31) / 32 * 32 + 32;  // segment B: local matrices, gather, at least one table warp (>= K threads)
+    const int roles = NM * (2 * NSR + (CAP + 31) / 32 * 32) + 32;  // segment B: local matrices, gather, at least one table warp (>= K threads)
     if (roles > nt) nt = roles;
     if (NS + 2 * K > nt) nt = NS + 2 * K;                   // knot prefetch: one knot per thread
     return (nt + 31) / 32 * 32;
 }
 
-static size_t stream_smem_bytes(int K, int NS) {
+static size_t stream_smem_bytes(int K, int NS, int NM = 1) {
     const int QH = (K + 2) / 2, KP2 = (K + 1) / 2 * 2, W = 2 * K - 1, NE = K * (K + 1) / 2, MSP = NE | 1;
     const int PIV0 = 2 * QH * KP2, PIV = PIV0 + ((2 - PIV0 % 4) + 4) % 4, QPW = (2 * QH) | 1;
     const int RING = 2 * NS + K - 1, CAP = NS + K - 1, NKP = (NS + 2 * K + 2) / 2 * 2;
-    size_t d = (size_t)NS * PIV + (((size_t)NS * QPW + 1) & ~(size_t)1) + (((size_t)RING * MSP + 1) & ~(size_t)1) +
-               (((size_t)CAP * W + 1) & ~(size_t)1) + 2 * (size_t)(NKP + 2) + 2 * (size_t)(K * NKP + 2) + (size_t)NKP +
-               (size_t)stream_threads(K, NS) * 6;
+    size_t d = NM * ((size_t)NS * PIV + (((size_t)NS * QPW + 1) & ~(size_t)1) + (((size_t)RING * MSP + 1) & ~(size_t)1) +
+                     (((size_t)CAP * W + 1) & ~(size_t)1)) + 2 * (size_t)(NKP + 2) + 2 * (size_t)(K * NKP + 2) + (size_t)NKP +
+               (size_t)stream_threads(K, NS, NM) * 6;
     return d * sizeof(double) + sizeof(int) * 2 * (size_t)NS + 16;
 }
 
@@ -456,21 +555,30 @@ static int stream_ns_override() {
 
 // Returns CB_OK after launching, a CB_ERR_* code on failure, or -1 when the request is outside this kernel's range
 // (the caller then takes the tiled / generic kernels of assemble.cu).
+// m = 0 / 1: one matrix of derivative order m; m = 2: the pair (band <- potential matrix with op, band2 <- derivative
+// matrix (-1) <B'|B'>) from one sweep.
 int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int coulomb, double Z,
                          i64 rowL0, i64 mm, i64 colR0, i64 nn, int u,
-                         i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st, const AsmHalo *halo) {
+                         i64 col_lo, i64 col_hi, i64 s_lo, i64 s_hi, double *band, cudaStream_t st, const AsmHalo *halo,
+                         double *band2 = nullptr) {
     const int K = B->k;
-    if (K < 2 || K > 11 || m < 0 || m > 1 || m >= K) return -1;
+    const int NM = m == 2 ? 2 : 1;
+    if (K < 2 || K > 11 || m < 0 || m > 2 || (m == 1 && m >= K)) return -1;
     if ((B->q + 1) / 2 != (K + 2) / 2) return -1;
+    if (m == 2 && (halo || !band2)) return -1;
+    // The pair kernel holds two rings and two tables, which halves its step (NS = 32 at K = 10): at the C3 size it is
+    // slower than two launches with full steps (219 vs 182 us), on short column ranges (launch-bound: C1, 17 vs 26 us) it wins.
+    if (m == 2 && (col_hi - col_lo) > (i64)CB_NUM_SMS * 512) return -1;
     int NS = 64;
     const int ov = stream_ns_override();
     if (ov == 0) return -1;
     if (ov > 0) NS = ov;
     if (NS < K) NS = K;
-    while (NS > K && (stream_threads(K, NS) > STREAM_MAX_THREADS || stream_smem_bytes(K, NS) > 220 * 1024)) --NS;
-    if (stream_threads(K, NS) > STREAM_MAX_THREADS || stream_smem_bytes(K, NS) > 220 * 1024) return -1;
+    auto fits = [&](int ns) { return stream_threads(K, ns, NM) <= STREAM_MAX_THREADS && stream_smem_bytes(K, ns, NM) <= 220 * 1024; };
+    while (NS > K && !fits(NS)) --NS;
+    if (!fits(NS)) return -1;
     if (col_hi <= col_lo) return CB_OK;
-    const int nt = stream_threads(K, NS);
+    const int nt = stream_threads(K, NS, NM);
     // columns without support in the interval range [s_lo, s_hi) are zero; the kernel gets the others
     // (an interval-sharded call passes exactly the columns that touch its range: nothing to clip)
     if (!halo) {
@@ -481,14 +589,18 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
         if (jf > col_hi) jf = col_hi;
         if (jl > col_hi) jl = col_hi;
         if (jl < jf) jl = jf;
-        if (jf > col_lo) CB_CUDA(cudaMemsetAsync(band, 0, sizeof(double) * (size_t)W * (size_t)(jf - col_lo), st));
-        if (jl < col_hi) CB_CUDA(cudaMemsetAsync(band + (size_t)W * (size_t)(jl - col_lo), 0, sizeof(double) * (size_t)W * (size_t)(col_hi - jl), st));
+        for (int b = 0; b < NM; ++b) {
+            double *bb = b == 0 ? band : band2;
+            if (jf > col_lo) CB_CUDA(cudaMemsetAsync(bb, 0, sizeof(double) * (size_t)W * (size_t)(jf - col_lo), st));
+            if (jl < col_hi) CB_CUDA(cudaMemsetAsync(bb + (size_t)W * (size_t)(jl - col_lo), 0, sizeof(double) * (size_t)W * (size_t)(col_hi - jl), st));
+        }
         band += (size_t)W * (size_t)(jf - col_lo);
+        if (band2) band2 += (size_t)W * (size_t)(jf - col_lo);
         col_lo = jf; col_hi = jl;
         if (col_hi <= col_lo) return CB_OK;
     }
     const i64 ncol = col_hi - col_lo;
-    const size_t smem = stream_smem_bytes(K, NS);
+    const size_t smem = stream_smem_bytes(K, NS, NM);
     i64 ncta = (ncol + NS - 1) / NS;
     StreamArgs A;
     A.kv = make_knot_view(B);
@@ -498,6 +610,7 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
     A.col_lo = col_lo; A.col_hi = col_hi; A.s_lo = s_lo; A.s_hi = s_hi;
     A.NS = NS;
     A.band = band;
+    A.band2 = band2;
     memset(&A.H, 0, sizeof(A.H));
     if (halo) {
         A.H = *halo;
@@ -505,34 +618,29 @@ int cb_asm_stream_launch(const cb_bspline *B, int m, const double *opvals, int c
         // last emission of the last CTA: both hold when a step covers at least 2K - 1 columns and CTAs are longer than that
         if (NS < 2 * K || ncol < 4 * (i64)K) return -1;
     }
+    auto launch = [&](auto kern) -> int {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (ncta > (i64)CB_NUM_SMS * per_sm) ncta = (i64)CB_NUM_SMS * per_sm;
+        A.cpc = (ncol + ncta - 1) / ncta;
+        kern<<<(int)ncta, nt, smem, st>>>(A);
+        return CB_OK;
+    };
+    int lrc = -1;
 #define CB_STREAM_CASE(KT)                                                                                       \
-    case KT: {                                                                                                   \
-        if (m == 0) {                                                                                            \
-            auto kern = bspline_assemble_stream_kernel<KT, 0>;                                                   \
-            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-            int per_sm = 1;                                                                                      \
-            CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));                     \
-            if (per_sm < 1) per_sm = 1;                                                                          \
-            if (ncta > (i64)CB_NUM_SMS * per_sm) ncta = (i64)CB_NUM_SMS * per_sm;                               \
-            A.cpc = (ncol + ncta - 1) / ncta;                                                                    \
-            kern<<<(int)ncta, nt, smem, st>>>(A);                                                                \
-        } else {                                                                                                 \
-            auto kern = bspline_assemble_stream_kernel<KT, 1>;                                                   \
-            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-            int per_sm = 1;                                                                                      \
-            CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));                     \
-            if (per_sm < 1) per_sm = 1;                                                                          \
-            if (ncta > (i64)CB_NUM_SMS * per_sm) ncta = (i64)CB_NUM_SMS * per_sm;                               \
-            A.cpc = (ncol + ncta - 1) / ncta;                                                                    \
-            kern<<<(int)ncta, nt, smem, st>>>(A);                                                                \
-        }                                                                                                        \
-    } break;
+    case KT:                                                                                                     \
+        lrc = m == 0 ? launch(bspline_assemble_stream_kernel<KT, 0>)                                             \
+            : m == 1 ? launch(bspline_assemble_stream_kernel<KT, 1>) : launch(bspline_assemble_stream_kernel<KT, 2>); \
+        break;
     switch (K) {
         CB_STREAM_CASE(2) CB_STREAM_CASE(3) CB_STREAM_CASE(4) CB_STREAM_CASE(5) CB_STREAM_CASE(6)
         CB_STREAM_CASE(7) CB_STREAM_CASE(8) CB_STREAM_CASE(9) CB_STREAM_CASE(10) CB_STREAM_CASE(11)
         default: return -1;
     }
 #undef CB_STREAM_CASE
+    if (lrc) return lrc;
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

@@ -144,6 +144,14 @@ int cb_bspline_assemble_part(const cb_bspline *L, const cb_bspline *R, int a, in
 int cb_bspline_assemble_host(const cb_bspline *L, const cb_bspline *R, int a, int b, const double *opvals_host,
                              int coulomb, double Z, cb_i64 rowL0, cb_i64 m, cb_i64 colR0, cb_i64 n, int l, int u,
                              double *band_host, void *stream);
+/* The two operators of a radial Hamiltonian on the (restricted) basis R = B[:, col0+1 : col0+n] in one launch:
+ *   bandV <- R' * QuasiDiagonal(op) * R   (src/bsplines.jl:300-310; opvals / coulomb / Z as in cb_bspline_assemble_part)
+ *   bandT <- R' * D' * D * R              (src/bspline_derivatives.jl:48-63, diffop! with a = b = 1)
+ * Both are (2k-1) x n BandedMatrix data arrays (l = u = k-1).  Values and first derivatives of the basis functions at
+ * the quadrature nodes come from one Cox-de Boor sweep, so the pair costs about 1.3 single assemblies; the entries are
+ * bit-identical to the two separate calls (test/bsplines/operators.jl:15-22 builds exactly this pair). */
+int cb_bspline_assemble_pair(const cb_bspline *B, const double *opvals, int coulomb, double Z,
+                             cb_i64 col0, cb_i64 n, double *bandV, double *bandT, void *stream);
 /* BandedMatrix(l=u=1) -> Tridiagonal(dl,d,du): the k == 2 && m == n case of
  * Matrix(undef, A, B) (src/bsplines.jl:258-262). */
 int cb_band_to_tridiag(const double *band, cb_i64 n, double *dl, double *d, double *du, void *stream);

@@ -25,7 +25,23 @@ for (K, ks, nint, check) in ((10, cb.ExpKnotSet(10, -3.0, 2.0, 200_000), 200_000
     for _ in range(10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 1e3)
-    msg = f"K={K} nint={nint} NS={os.environ.get('CB_ASM_STREAM_NS', 'default')}: V+T {np.mean(ts):.1f} us (min {np.min(ts):.1f})"
+    V2 = torch.empty_like(V); T2 = torch.empty_like(T)
+    def pair():
+        _lib.call("cb_bspline_assemble_pair", B.handle, None, 1, 1.0, 0, B.nf, _ptr(V2), _ptr(T2), st)
+    for _ in range(3): pair()
+    torch.cuda.synchronize()
+    tp = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pair(); e1.record(); torch.cuda.synchronize(); tp.append(e0.elapsed_time(e1) * 1e3)
+    same = bool(torch.equal(V, V2) and torch.equal(T, T2))
+    if not same:
+        dv, dt = (V - V2).abs(), (T - T2).abs()
+        print(f"  V: {int((dv > 0).sum())} of {dv.numel()} differ, max {float(dv.max()):.3e} (scale {float(V.abs().max()):.3e}); "
+              f"T: {int((dt > 0).sum())} differ, max {float(dt.max()):.3e} (scale {float(T.abs().max()):.3e})", flush=True)
+        iv = torch.nonzero(dv > 0)[:5].tolist(); it = torch.nonzero(dt > 0)[:5].tolist()
+        print("  first V diffs", iv, "first T diffs", it, flush=True)
+    msg = f"K={K} nint={nint} NS={os.environ.get('CB_ASM_STREAM_NS', 'default')}: V+T {np.mean(ts):.1f} us (min {np.min(ts):.1f}); pair {np.mean(tp):.1f} us (min {np.min(tp):.1f}) identical={same}"
     if check:
         cbo.set_threads(cbo.max_threads())
         te = cbo.expand_knots(np.asarray(ks.t), K); xq, wq = cbo.lgwt(te, K + 1)

@@ -394,3 +394,37 @@ def test_fused_halo_exchange_single_device_emulation(cb, world):
             lo, hi, cols = assemble_interval_sharded(R, R, 1, 1, r, world, halo="recompute", comm=comms[r])
             got[lo:hi] = cols
         assert torch.equal(got, full["T"])
+
+
+@pytest.mark.parametrize("k,nint,kind", [(2, 9, "lin"), (3, 17, "lin"), (4, 40, "exp"), (7, 300, "lin"), (10, 777, "exp"), (11, 150, "lin"), (12, 60, "lin")])
+def test_hamiltonian_pair_matches_separate_assemblies(cb, k, nint, kind):
+    """cb_bspline_assemble_pair (values + derivatives from one Cox-de Boor sweep) against the two separate
+    materialisations R'*V*R and R'*D'*D*R (bit-identical inside the streaming kernel's range, k <= 11) and against the
+    oracle; full basis, a Dirichlet restriction (test/bsplines/operators.jl:15-22), Coulomb / nodal-value / no operator."""
+    t = cb.LinearKnotSet(k, 0.5, 7.5, nint) if kind == "lin" else cb.ExpKnotSet(k, -2.0, 1.0, nint)
+    B = cb.BSpline(t)
+    D = cb.Derivative()
+    te = cbo.expand_knots(t.t, k)
+    q = cbo.num_quadrature_points(k, 3)
+    xq, wq = cbo.lgwt(te, q)
+    for R in (B, B[:, 2:B.nf - 1]):
+        for op, opf in ((cb.CoulombPotential(2.0), lambda x: -2.0 / x), (cb.QuasiDiagonal(lambda x: np.sin(x) + 2), lambda x: np.sin(x) + 2),
+                        (None, None)):
+            V, T = cb.hamiltonian_bands(R, op)
+            Vs = (R.T @ op @ R) if op is not None else (R.T @ R)
+            Ts = R.T @ D.T @ D @ R
+            assert V.bandwidths() == (k - 1, k - 1) and T.bandwidths() == (k - 1, k - 1)
+            if k == 2:
+                pass                                                # Matrix(undef, A, B) is a Tridiagonal for k = 2 (src/bsplines.jl:258-262)
+            elif k <= 11:
+                assert torch_equal(V.data, Vs.data) and torch_equal(T.data, Ts.data)
+            else:
+                assert relerr(V.data.cpu().numpy(), Vs.data.cpu().numpy()) <= RTOL and relerr(T.data.cpu().numpy(), Ts.data.cpu().numpy()) <= RTOL
+            Vo, _, _ = cbo.bspline_assemble(te, k, te, k, xq, wq, q, 0, 0, None if opf is None else opf(xq), R.col0, R.ncols, R.col0, R.ncols)
+            To, _, _ = cbo.bspline_assemble(te, k, te, k, xq, wq, q, 1, 1, None, R.col0, R.ncols, R.col0, R.ncols)
+            assert relerr(V.data.cpu().numpy(), Vo) <= RTOL and relerr(T.data.cpu().numpy(), To) <= RTOL
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a, b))
