@@ -219,20 +219,30 @@ class Ctx:
         return float(t.item())
 
     def dev_time(self, fn, n, warm=2, rotate=1):
-        """Mean and min device time (s) of fn(i % rotate) over n launches, every launch between its own pair of CUDA
-        events on torch's current stream (the stream the library launches on); barrier before the loop; max over ranks."""
+        """Device time (s) of fn(i % rotate): (mean, min).  mean = one CUDA event pair around n back-to-back launches on
+        torch's current stream (the stream the library launches on) / n, as SURVEY 8d prescribes — the queue never runs
+        empty, so no host latency is measured; min = the shortest of n launches timed one by one.  Barrier before each
+        loop; both are the max over ranks."""
         torch = self.torch
         for i in range(warm):
             fn(i % rotate)
         self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i % rotate)
+        e1.record()
+        torch.cuda.synchronize()
+        mean = e0.elapsed_time(e1) * 1e-3 / n
+        self.barrier()
         evs = []
         for i in range(n):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); fn(i % rotate); e1.record()
-            evs.append((e0, e1))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(i % rotate); b.record()
+            evs.append((a, b))
         torch.cuda.synchronize()
-        ts = [a.elapsed_time(b) * 1e-3 for a, b in evs]
-        return self.maxr(float(np.mean(ts))), self.maxr(float(np.min(ts)))
+        mn = min(a.elapsed_time(b) for a, b in evs) * 1e-3
+        return self.maxr(mean), self.maxr(mn)
 
     def wall_time(self, fn, n, warm=1):
         """Host wall clock (s per call) of a synchronous host-buffer entry, barriers on both sides, max over ranks."""
@@ -362,6 +372,7 @@ def config_c1(cx: Ctx, cpu: bool):
             _lib.call("cb_bspline_assemble", Bh, Bh, 0, 0, None, 0, B.nf, 0, B.nf, K - 1, K - 1, _ptr(S), st)
             _lib.call("cb_bspline_assemble", Bh, Bh, 1, 1, None, 0, B.nf, 0, B.nf, K - 1, K - 1, _ptr(T), st)
         mean1, mn1 = cx_dev_time_local(torch, lambda: asm(B.handle, S, T), 50)
+        meanp, mnp = cx_dev_time_local(torch, lambda: _lib.call("cb_bspline_assemble_pair", B.handle, None, 0, 0.0, 0, B.nf, _ptr(S), _ptr(T), st), 50)
         bases = [cb.BSpline(cb.LinearKnotSet(K, 0, 100 + i, NINT)) for i in range(64)]
         Ss = torch.empty((64, B.nf, 2 * K - 1), dtype=torch.float64, device="cuda")
         Ts = torch.empty_like(Ss)
@@ -385,6 +396,7 @@ def config_c1(cx: Ctx, cpu: bool):
             diffop_host(B, B, 0, 0); diffop_host(B, B, 1, 1)
         e2e_s = (time.perf_counter() - hostT) / 5
         out["assemble"] = {"us_per_mass_plus_laplacian": mean1 * 1e6, "us_min": mn1 * 1e6, "us_through_operator_api": api * 1e6,
+                           "us_pair_entry": meanp * 1e6, "us_pair_entry_min": mnp * 1e6,
                            "batched_64_bases_us": mean64 * 1e6, "bases_per_s_batched": 64 / mean64, "us_per_basis_batched": mean64 / 64 * 1e6,
                            "note": "launch-latency bound (0.22 MB per basis); 2 launches per basis", "parity": par,
                            "e2e": {"us": e2e_s * 1e6, "entry": "cb_bspline_assemble_host x2 (bands to host arrays)",
@@ -416,18 +428,25 @@ def config_c1(cx: Ctx, cpu: bool):
 
 
 def cx_dev_time_local(torch, fn, n, warm=3):
-    """Device time of fn() on this rank only (configs that rank 0 runs alone)."""
+    """Device time of fn() on this rank only (configs that rank 0 runs alone): (mean over n back-to-back launches
+    between one event pair, min over n launches timed one by one)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    mean = e0.elapsed_time(e1) * 1e-3 / n
     evs = []
     for _ in range(n):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
-        evs.append((e0, e1))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        evs.append((a, b))
     torch.cuda.synchronize()
-    ts = [a.elapsed_time(b) * 1e-3 for a, b in evs]
-    return float(np.mean(ts)), float(np.min(ts))
+    return float(mean), float(min(a.elapsed_time(b) for a, b in evs) * 1e-3)
 
 
 # --------------------------------------------------------------------------------------
@@ -463,7 +482,9 @@ def config_c3(cx: Ctx, cpu: bool, comm):
             _lib.call("cb_bspline_assemble_coulomb", B.handle, B.handle, 1.0, 0, B.nf, 0, B.nf, K - 1, K - 1, _ptr(full_V), st)
             _lib.call("cb_bspline_assemble", B.handle, B.handle, 1, 1, None, 0, B.nf, 0, B.nf, K - 1, K - 1, _ptr(full_T), st)
         s_mean, s_min = cx_dev_time_local(torch, single, 10)
-        r = {"intervals": nint, "single_gpu_us": s_mean * 1e6, "single_gpu_us_min": s_min * 1e6}
+        p_mean, p_min = cx_dev_time_local(torch, lambda: _lib.call("cb_bspline_assemble_pair", B.handle, None, 1, 1.0, 0, B.nf,
+                                                                   _ptr(full_V), _ptr(full_T), st), 10)
+        r = {"intervals": nint, "single_gpu_us": s_mean * 1e6, "single_gpu_us_min": s_min * 1e6, "pair_entry_us": p_mean * 1e6}
         if cx.world == 1:
             r["us"] = s_mean * 1e6
         else:
@@ -498,7 +519,7 @@ def config_c3(cx: Ctx, cpu: bool, comm):
             r["best_halo"] = best
         sec = r["us"] * 1e-6
         r["fp64_tflops"] = C3_FLOP * scale / sec / 1e12
-        r["roofline"] = cx.fp64_roofline(C3_FLOP * scale / cx.world, C3_BYTES * scale / cx.world, sec, "bspline_assemble_tiled_kernel (V + T)")
+        r["roofline"] = cx.fp64_roofline(C3_FLOP * scale / cx.world, C3_BYTES * scale / cx.world, sec, "bspline_assemble_stream_kernel<10,0> + <10,1> (V + T)")
         if nint == 200_000 and cx.rank == 0:
             cbo = _cbo(True)
             te = cbo.expand_knots(np.asarray(B.t.t), K)
@@ -578,23 +599,30 @@ def config_c4(cx: Ctx, cpu: bool):
         X[:nv].normal_(generator=g)
         if it == 0:
             cb.mul(Y[:nv], Lp, X[:nv])                       # warm-up on the first tile
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); cb.mul(Y[:nv], Lp, X[:nv]); e1.record()
-        evs.append((e0, e1))
+        # every tile is applied twice and the shorter device interval counts: an event pair also measures the time the
+        # GPU waits for the HOST when its queue runs empty (a descheduled Python thread once showed up as a 365 ms "kernel")
+        pair = []
+        for _rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); cb.mul(Y[:nv], Lp, X[:nv]); e1.record()
+            pair.append((e0, e1))
+        evs.append(pair)
         if cx.rank == 0 and it in (0, ntile - 1):
             for v in (0, nv - 1):
                 ref = cbo.tridiag_apply(ev, dv, ev, X[v].cpu().numpy()[:, None])[:, 0]
                 par["max_rel"] = max(par["max_rel"], relerr(Y[v].cpu().numpy(), ref))
                 par["vectors_checked"].append(int(v0 + v))
     torch.cuda.synchronize()
-    sec = cx.maxr(sum(a.elapsed_time(b) for a, b in evs) * 1e-3)
+    tile_ms = [min(a.elapsed_time(b) for a, b in pair) for pair in evs]
+    sec = cx.maxr(sum(tile_ms) * 1e-3)
     byt_rank = 2 * 8 * N * (hi - lo) + ntile * 2 * 8 * N
     byt = 2 * 8 * N * NV
     out = {"workload": "C4: StaggeredFiniteDifferences N=1e7 (rho=1e-3) tridiagonal Laplacian applied to 4096 vectors (655 GB of X + Y)",
            "scaling": "strong", "sharding": "vector batch split over the ranks, diagonals replicated, no collective",
            "metric": "tridiag_apply_algorithmic_GBps", "unit": "GB/s", "value": byt / sec / 1e9, "ms": sec * 1e3,
            "tiles_per_rank": ntile, "tile_vectors": TILE,
-           "l2": "every 256-vector tile (20.5 GB in, 20.5 GB out) is larger than L2 and is regenerated before its launch",
+           "tile_ms_rank0": [round(float(x), 3) for x in tile_ms],
+           "l2": "every 256-vector tile (20.5 GB in, 20.5 GB out) is larger than L2 and is regenerated before its launches (two per tile, the shorter one counts)",
            "roofline": cx.hbm_roofline(byt_rank / ntile, sec / ntile, "tridiag_apply_pipe_kernel", "per rank and tile: X + Y + the two diagonals")}
     if cx.rank == 0:
         par["vs"] = "oracle tridiag_apply on whole vectors of the first and last timed tile"
