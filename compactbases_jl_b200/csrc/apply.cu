@@ -398,8 +398,12 @@ constexpr int BT_KSMAX = 8;                         // k-steps the pipelined ker
 #endif
 constexpr int BTP_ROWS = BTP_NROWS;                 // rows per tile of the pipelined kernel
 constexpr int BTP_VEC = BTP_NVEC;                   // vectors per tile (<= 32: one loader / storer lane per column)
-constexpr int BTP_RB = BTP_ROWS / 8 / BTP_NG;       // 8-row blocks per compute warp
-constexpr int BTP_NAV = (BTP_ROWS / 8) * BT_KSMAX * 32 / (32 * BTP_NG);   // A-fragment entries per compute thread
+#ifndef BTP_GROUPS
+#define BTP_GROUPS 1                                // independent compute groups working on consecutive pipeline stages (see below)
+#endif
+constexpr int BTP_NGG = BTP_NG / BTP_GROUPS;        // warps per compute group
+constexpr int BTP_RB = BTP_ROWS / 8 / BTP_NGG;      // 8-row blocks per compute warp
+constexpr int BTP_NAV = (BTP_ROWS / 8) * BT_KSMAX * 32 / (32 * BTP_NGG);   // A-fragment entries per compute thread
 #ifndef BT_GRIDCAP
 #define BT_GRIDCAP 1024                             // CTAs per SM in the grid at most (items beyond that are strided)
 #endif
@@ -496,10 +500,16 @@ __device__ unsigned long long fe_prof[8];
 #endif
 // ---------------------------------------------------------------------------
 // K7, warp-specialised TMA pipeline (same structure as the K8 pipeline below, which has the measurements): one
-// persistent CTA per SM; a loader warp keeps a ring of x windows filled with one bulk copy per vector column, BT_NG
+// persistent CTA per SM; a loader warp keeps a ring of x windows filled with one bulk copy per vector column, the
 // compute warps multiply a window by the band tile's A fragments (staged once per work item) and write the 128 result
 // rows over the window in place (rows l .. l+127 of the window are the tile's own rows), a storer warp streams them
-// out with bulk copies.  Work item = (row tile, chunk of vector tiles) as in banded_apply_kernel; items are dealt
+// out with bulk copies.  The compute warps can be split into BTP_GROUPS independent groups that take the pipeline
+// stages in turn (group g: every BTP_GROUPS-th vector tile, own copy of the A fragments, own named barrier), so that one
+// group multiplies the next window while the other sits in the barrier + write-back of its tile.  Measured (round 2,
+// gpurun_out/bench_r2v.json): two groups of four warps are SLOWER than one group of eight — k = 7, 1006 x 65 536:
+// 211 vs 193 us; C3, 200 009 x 256: 206 vs 182 us — a tile then takes twice as long per group and the two groups
+// contend for the same DMMA pipe, while 2 x 8 warps do not fit the register file at 158 registers per thread.  The
+// default stays one group.  Work item = (row tile, chunk of vector tiles) as in banded_apply_kernel; items are dealt
 // round-robin to the CTAs.  Columns whose window starts on an odd element are copied from one element earlier
 // (16-byte alignment of bulk copies): window row r of column v sits at xs[col(v) + par_v + r].  Requires l, u >= 0,
 // l + u + 1 <= 25, beta == 0 and X, Y of equal 16-byte phase per column; the launcher falls back to
@@ -515,13 +525,14 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     const int xrows = BTP_ROWS + l + u;
     const int wrows = xrows + 3;                    // + the k padding of the last row block
     const int STAGE = BTP_VEC * P0;
-    double *as = sm + (size_t)nstg * STAGE;         // [BTP_ROWS/8][KS][32] A fragments of the current item
-    uint64_t *bars = reinterpret_cast<uint64_t *>(as + (BTP_ROWS / 8) * KS * 32);
+    const int ASZ = (BTP_ROWS / 8) * KS * 32;
+    double *as_all = sm + (size_t)nstg * STAGE;     // [BTP_GROUPS][BTP_ROWS/8][KS][32] A fragments of the groups' current items
+    uint64_t *bars = reinterpret_cast<uint64_t *>(as_all + BTP_GROUPS * ASZ);
     uint64_t *full = bars, *done = bars + nstg, *empty = bars + 2 * nstg;
     const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nstg; ++s) { mbar_init(full + s, 1); mbar_init(done + s, BTP_NG); mbar_init(empty + s, 1); }
+        for (int s = 0; s < nstg; ++s) { mbar_init(full + s, 1); mbar_init(done + s, BTP_NGG); mbar_init(empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -544,44 +555,49 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
     // hitting the same residue of row tiles — the clipped first / last row tiles then spread evenly over the CTAs
     auto item_coords = [&](i64 item, i64 &vc, i64 &rt) { vc = item / nrt; rt = (item - vc * nrt + vc) % nrt; };
     if (w < BTP_NG) {
-        // ================= compute warps ======================================================
+        // ================= compute warps: group grp takes the tiles with (running tile count) % BTP_GROUPS == grp ====
+        const int grp = w / BTP_NGG, wg = w - grp * BTP_NGG;          // group, warp inside the group
+        const int tg = (int)threadIdx.x - grp * 32 * BTP_NGG;         // thread inside the group
+        double *as = as_all + grp * ASZ;
         const int gq = lane >> 2, tq = lane & 3;
         const double wscale = alpha;                // beta == 0 (launcher): alpha is folded into the tile
         // A fragments of a row tile: as[rb][ks][lane] = A(i0 + 8rb + g, i0 + 8rb - l + 4ks + t), 0 outside band/matrix.
         // Each thread fetches its BTP_NAV entries of the NEXT item into registers while the last vector tile of the
-        // current item is multiplied, so the band's memory latency is off the tile loop.
+        // current item is in flight, so the band's memory latency is off the tile loop.
         double av[BTP_NAV];
         auto fetch_frags = [&](i64 item_) {
             i64 vc_, rt_; item_coords(item_, vc_, rt_);
             const i64 i0_ = rt_ * BTP_ROWS;
 #pragma unroll
             for (int t = 0; t < BTP_NAV; ++t) {
-                const int e = threadIdx.x + t * 32 * BTP_NG;
+                const int e = tg + t * 32 * BTP_NGG;
                 const int ln = e & 31, ks = (e >> 5) % KS, rb = (e >> 5) / KS;
                 const i64 i = i0_ + 8 * rb + (ln >> 2), j = i0_ + 8 * rb - l + 4 * ks + (ln & 3);
-                av[t] = (e < (BTP_ROWS / 8) * KS * 32 && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
+                av[t] = (e < ASZ && i < m && j >= 0 && j < n && j - i <= u && i - j <= l)
                             ? __ldg(band + (u + i - j) + (i64)W * j) : 0.0;
             }
         };
         if ((i64)blockIdx.x < nitems) fetch_frags(blockIdx.x);
+        unsigned tcount = 0;                         // tiles seen so far (all groups see the same sequence)
         for (i64 item = blockIdx.x; item < nitems; item += gridDim.x) {
             i64 vc, rt; item_coords(item, vc, rt);
             const i64 i0 = rt * BTP_ROWS, g0 = i0 - l;
-            named_bar_sync(1, 32 * BTP_NG);          // the previous item's fragments are no longer read
+            named_bar_sync(1 + grp, 32 * BTP_NGG);   // the group's previous item's fragments are no longer read
 #pragma unroll
             for (int t = 0; t < BTP_NAV; ++t) {
-                const int e = threadIdx.x + t * 32 * BTP_NG;
-                if (e < (BTP_ROWS / 8) * KS * 32) as[e] = av[t];
+                const int e = tg + t * 32 * BTP_NGG;
+                if (e < ASZ) as[e] = av[t];
             }
-            named_bar_sync(1, 32 * BTP_NG);
+            named_bar_sync(1 + grp, 32 * BTP_NGG);
             FE_PROF_L(7);
             const i64 vt_end = (vc + 1) * vchunk < nvt ? (vc + 1) * vchunk : nvt;
-            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage()) {
+            for (i64 vt = vc * vchunk; vt < vt_end; ++vt, next_stage(), ++tcount) {
+                if (vt + 1 == vt_end && item + gridDim.x < nitems) fetch_frags(item + gridDim.x);
+                if ((int)(tcount % BTP_GROUPS) != grp) continue;      // the other group's tile
                 const i64 v0 = vt * BTP_VEC;
                 double *xs = sm + (size_t)stage * STAGE;
                 const int par_r = col_parity(g0, v0 + gq);
                 const int par_c0 = col_parity(g0, v0 + 2 * tq), par_c1 = col_parity(g0, v0 + 2 * tq + 1);
-                if (vt + 1 == vt_end && item + gridDim.x < nitems) fetch_frags(item + gridDim.x);
                 mbar_wait(full + stage, phase);
                 FE_PROF_L(2);
                 // A dependent DMMA has ~180 cycles of latency: the k-steps of the warp's BTP_RB row blocks advance
@@ -592,8 +608,8 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
 #pragma unroll
                     for (int nt = 0; nt < BTP_VEC / 8; ++nt) { c[q][nt][0] = 0.0; c[q][nt][1] = 0.0; }
                 {
-                    const double *af = as + w * BTP_RB * KS * 32 + lane;
-                    const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * w * BTP_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
+                    const double *af = as + wg * BTP_RB * KS * 32 + lane;
+                    const double *xb = xs + gq * P0 + fe_swz(gq) + par_r + 8 * wg * BTP_RB + tq;   // + q*8 + nt*8*P0 + 4*ks
                     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                         for (int q = 0; q < BTP_RB; ++q) {
@@ -605,11 +621,11 @@ banded_apply_pipe_kernel(const double *__restrict__ band, i64 m, i64 n, int l, i
                     }
                 }
                 FE_PROF_L(3);
-                named_bar_sync(1, 32 * BTP_NG);      // every warp has read the window
+                named_bar_sync(1 + grp, 32 * BTP_NGG);   // every warp of the group has read the window
                 FE_PROF_L(4);
 #pragma unroll
                 for (int q = 0; q < BTP_RB; ++q) {
-                    const int row = l + (w * BTP_RB + q) * 8 + gq;         // window row of the output row
+                    const int row = l + (wg * BTP_RB + q) * 8 + gq;        // window row of the output row
                     double *y0 = xs + (2 * tq) * P0 + fe_swz(2 * tq) + par_c0 + row;
                     double *y1 = xs + (2 * tq + 1) * P0 + fe_swz(2 * tq + 1) + par_c1 + row;
 #pragma unroll
@@ -1618,7 +1634,7 @@ int cb_banded_apply(const double *band, i64 m, i64 n, int l, int u,
     if (l >= 0 && u >= 0 && KS <= BT_KSMAX && beta == 0.0 &&
         ((reinterpret_cast<uintptr_t>(X) ^ reinterpret_cast<uintptr_t>(Y)) & 15) == 0 && ((ldx ^ ldy) & 1) == 0) {
         const int P0 = (BTP_ROWS + l + u + 3 + 2 + 12 + 15) / 16 * 16;      // window + k padding + parity shift / rounding + skew
-        const size_t stage_b = sizeof(double) * BTP_VEC * P0, as_b = sizeof(double) * (BTP_ROWS / 8) * KS * 32;
+        const size_t stage_b = sizeof(double) * BTP_VEC * P0, as_b = sizeof(double) * BTP_GROUPS * (BTP_ROWS / 8) * KS * 32;
         int nstg = (int)((227 * 1024 - as_b - 256) / stage_b);
         if (nstg > 6) nstg = 6;
         if (nstg >= 2) {
