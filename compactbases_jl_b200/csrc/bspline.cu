@@ -419,16 +419,37 @@ int cb_bspline_eval_host(const cb_bspline *B, const double *xh, i64 nx, int m,
                          int32_t *ih, double *vh) {
     CB_REQUIRE(B != nullptr, "cb_bspline_eval_host: NULL basis");
     if (nx == 0) return CB_OK;
-    double *dx = nullptr, *dv = nullptr; int32_t *di = nullptr;
-    CB_CUDA(cudaMalloc(&dx, sizeof(double) * nx));
-    CB_CUDA(cudaMalloc(&dv, sizeof(double) * nx * B->k));
-    CB_CUDA(cudaMalloc(&di, sizeof(int32_t) * nx));
+    // one scratch block from the stream-ordered pool, asynchronous copies (PCIe speed from pinned arrays), points in
+    // chunks on two streams so that the upload of one chunk overlaps the evaluation / download of the other
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
+    static cudaStream_t hs[64][2] = {};
+    int dev = 0;
+    CB_CUDA(cudaGetDevice(&dev));
+    CB_REQUIRE(dev >= 0 && dev < 64, "cb_bspline_eval_host: device index %d out of range", dev);
+    for (int i = 0; i < 2; ++i)
+        if (!hs[dev][i]) CB_CUDA(cudaStreamCreateWithFlags(&hs[dev][i], cudaStreamNonBlocking));
+    const i64 chunk = nx > (i64)1 << 18 ? (nx + 7) / 8 : nx;          // ~8 chunks for large batches
+    const size_t b_x = sizeof(double) * (size_t)chunk, b_v = sizeof(double) * (size_t)chunk * B->k, b_i = (sizeof(int32_t) * (size_t)chunk + 15) & ~(size_t)15;
+    char *scr[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) CB_CUDA(cudaMallocAsync(&scr[i], b_x + b_v + b_i, hs[dev][i]));
     int rc = CB_OK;
-    cudaError_t e = cudaMemcpy(dx, xh, sizeof(double) * nx, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) rc = cb_bspline_eval(B, dx, nx, m, di, dv, nullptr);
-    if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpy(ih, di, sizeof(int32_t) * nx, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpy(vh, dv, sizeof(double) * nx * B->k, cudaMemcpyDeviceToHost);
-    cudaFree(dx); cudaFree(dv); cudaFree(di);
+    cudaError_t e = cudaSuccess;
+    i64 c = 0;
+    for (i64 p0 = 0; p0 < nx && e == cudaSuccess && rc == CB_OK; p0 += chunk, ++c) {
+        const int i = (int)(c & 1);
+        const i64 np = p0 + chunk <= nx ? chunk : nx - p0;
+        double *dx = reinterpret_cast<double *>(scr[i]), *dv = reinterpret_cast<double *>(scr[i] + b_x);
+        int32_t *di = reinterpret_cast<int32_t *>(scr[i] + b_x + b_v);
+        e = cudaMemcpyAsync(dx, xh + p0, sizeof(double) * np, cudaMemcpyHostToDevice, hs[dev][i]);
+        if (e == cudaSuccess) rc = cb_bspline_eval(B, dx, np, m, di, dv, hs[dev][i]);
+        if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpyAsync(ih + p0, di, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, hs[dev][i]);
+        if (e == cudaSuccess && rc == CB_OK) e = cudaMemcpyAsync(vh + p0 * B->k, dv, sizeof(double) * np * B->k, cudaMemcpyDeviceToHost, hs[dev][i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeAsync(scr[i], hs[dev][i]);
+        const cudaError_t e2 = cudaStreamSynchronize(hs[dev][i]);
+        if (e == cudaSuccess) e = e2;
+    }
     if (e != cudaSuccess) { cb_set_error("cb_bspline_eval_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     return rc;
 }

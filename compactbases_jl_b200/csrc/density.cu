@@ -1131,15 +1131,19 @@ int cb_density_apply_host(const cb_density *D, const double *f_host, i64 ldf, i6
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     const size_t tile_b = sizeof(double) * (size_t)n * (size_t)tp, col_b = sizeof(double) * (size_t)n;
+    // staging buffers come from the stream-ordered pool on the producer stream (kept between calls: no cudaMalloc /
+    // cudaFree round trips, which cost more than the transfers of a small batch); the private streams wait for `ready`
+    { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
+    const cudaStream_t ps = (cudaStream_t)stream;
     for (int b = 0; b < NB; ++b) {
         step(cudaStreamCreateWithFlags(&st[b], cudaStreamNonBlocking));
-        if (Pf > 1) step(cudaMalloc(&df[b], tile_b));
-        if (Pg > 1) step(cudaMalloc(&dg[b], tile_b));
-        step(cudaMalloc(&dr[b], tile_b));
+        if (Pf > 1) step(cudaMallocAsync(&df[b], tile_b, ps));
+        if (Pg > 1) step(cudaMallocAsync(&dg[b], tile_b, ps));
+        step(cudaMallocAsync(&dr[b], tile_b, ps));
     }
     step(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    if (Pf == 1) { step(cudaMalloc(&f1, col_b)); if (e == cudaSuccess) step(cudaMemcpyAsync(f1, f_host, col_b, cudaMemcpyHostToDevice, (cudaStream_t)stream)); }
-    if (Pg == 1) { step(cudaMalloc(&g1, col_b)); if (e == cudaSuccess) step(cudaMemcpyAsync(g1, g_host, col_b, cudaMemcpyHostToDevice, (cudaStream_t)stream)); }
+    if (Pf == 1) { step(cudaMallocAsync(&f1, col_b, ps)); if (e == cudaSuccess) step(cudaMemcpyAsync(f1, f_host, col_b, cudaMemcpyHostToDevice, ps)); }
+    if (Pg == 1) { step(cudaMallocAsync(&g1, col_b, ps)); if (e == cudaSuccess) step(cudaMemcpyAsync(g1, g_host, col_b, cudaMemcpyHostToDevice, ps)); }
     if (e == cudaSuccess) step(cudaEventRecord(ready, (cudaStream_t)stream));
     for (int b = 0; b < NB && e == cudaSuccess; ++b) step(cudaStreamWaitEvent(st[b], ready, 0));
     auto copy2d = [&](double *dst, i64 ldd, const double *src, i64 lds, i64 nv, cudaMemcpyKind kind, cudaStream_t s_) {
@@ -1158,9 +1162,12 @@ int cb_density_apply_host(const cb_density *D, const double *f_host, i64 ldf, i6
     }
     for (int b = 0; b < NB; ++b) {
         if (st[b]) { cudaError_t e2 = cudaStreamSynchronize(st[b]); if (e == cudaSuccess) e = e2; cudaStreamDestroy(st[b]); }
-        cudaFree(df[b]); cudaFree(dg[b]); cudaFree(dr[b]);
+        if (df[b]) cudaFreeAsync(df[b], ps);
+        if (dg[b]) cudaFreeAsync(dg[b], ps);
+        if (dr[b]) cudaFreeAsync(dr[b], ps);
     }
-    cudaFree(f1); cudaFree(g1);
+    if (f1) cudaFreeAsync(f1, ps);
+    if (g1) cudaFreeAsync(g1, ps);
     if (ready) cudaEventDestroy(ready);
     if (e != cudaSuccess) { cb_set_error("cb_density_apply_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     return rc;

@@ -235,3 +235,57 @@ def _allgather_ragged(parts, cols, group):
         if r == rank:
             parts[r].copy_(cols)
         dist.broadcast(parts[r], _global_rank(r, group), group=group)
+
+
+# ---- K4 / K5: FE-DVR element shards and finite-difference node shards ---------------------------------
+def fedvr_assemble_sharded(F, nder: int, rank: int, world: int, out: torch.Tensor | None = None):
+    """``derop!(A, B, nder)`` for the elements ``batch_range(nel, rank, world)`` of the FE-DVR basis F on this rank's GPU.
+    Element blocks only need the (replicated) grid, weights and bridge normalisation of the basis, so there is nothing to
+    exchange: the shared bridge entries are sums of two neighbouring corners and are formed when the operator is applied
+    or exported.  Returns ``(e_lo, e_hi, blocks)`` with ``blocks`` the slice ``boff[e_lo] : boff[e_hi]`` of the full
+    block array."""
+    from . import _lib
+    from .operators import _ptr, _stream
+    P = F.parent_basis
+    e_lo, e_hi = batch_range(P.nel, rank, world)
+    nloc = e_hi - e_lo
+    o2 = P.order.astype(object) ** 2
+    b0 = int(P.boff[e_lo]) if e_lo < P.nel else int(sum(o2))
+    b1 = int(P.boff[e_hi]) if e_hi < P.nel else int(sum(o2))
+    blocks = out if out is not None else torch.empty(b1 - b0, dtype=torch.float64, device=P.device)
+    if nloc == 0:
+        return e_lo, e_hi, blocks
+    if P.uniform_order > 0:
+        o = P.uniform_order
+        _lib.call("cb_fedvr_assemble", P.d_x.data_ptr() + 8 * e_lo * (o - 1), P.d_wcat.data_ptr() + 8 * e_lo * o,
+                  P.d_n.data_ptr() + 8 * e_lo * (o - 1), None, None, None, None, nloc, o, o, nder, _ptr(blocks), _stream())
+    else:
+        # per-element arrays hold absolute offsets: shift the array pointers by e_lo elements and the block base so that
+        # blocks[boff[e_lo]] is the first entry written
+        _lib.call("cb_fedvr_assemble", _ptr(P.d_x), _ptr(P.d_wcat), _ptr(P.d_n), P.d_estart.data_ptr() + 8 * e_lo,
+                  P.d_order.data_ptr() + 4 * e_lo, P.d_boff.data_ptr() + 8 * e_lo, P.d_woff.data_ptr() + 8 * e_lo, nloc, 0,
+                  int(P.order[e_lo:e_hi].max()), nder, blocks.data_ptr() - 8 * b0, _stream())
+    return e_lo, e_hi, blocks
+
+
+def fd_derivative_sharded(R, nder: int, rank: int, world: int, Z: float = 0.0, ell: int = 0):
+    """Rows ``batch_range(N, rank, world)`` of the (Sym)Tridiagonal derivative operator of the finite-difference grid R
+    (``cb_fd_derivative`` on a node range; stencils depend on the replicated grid only).  Returns
+    ``(lo, hi, dl, d, du)``: ``d[i]`` = A[lo+i, lo+i], ``du[i]`` = A[lo+i, lo+i+1], ``dl[i]`` = A[lo+i+1, lo+i]; the
+    off-diagonals have ``hi - lo`` entries (one fewer on the last rank)."""
+    from . import _lib
+    from .operators import _ptr, _stream
+    P = R.parent_basis
+    N = P.N
+    lo, hi = batch_range(N, rank, world)
+    n = hi - lo
+    ext = n + (1 if hi < N else 0)                  # one more node: the coupling of row hi-1 to row hi
+    dev = P.device
+    d = torch.empty(max(ext, 1), dtype=torch.float64, device=dev)
+    dl = torch.empty(max(ext - 1, 1), dtype=torch.float64, device=dev)
+    du = torch.empty(max(ext - 1, 1), dtype=torch.float64, device=dev)
+    if n > 0:
+        _lib.call("cb_fd_derivative", P.scheme, nder, _ptr(P.d_r), None, N, float(P.step), lo, ext, float(Z), int(ell),
+                  _ptr(dl), _ptr(d), _ptr(du), _stream())
+    noff = ext - 1 if n > 0 else 0
+    return lo, hi, dl[:noff], d[:n], du[:noff]

@@ -770,3 +770,15 @@ def test_bandlu_rejects_unsupported_bandwidth_at_create(cb):
     X = cb.ColMajor.from_numpy(np.ones((64, 3)))
     F.ldiv(X)
     assert np.all(np.isfinite(X.numpy()))
+
+
+def test_eval_host_large_batch_in_chunks(cb):
+    """cb_bspline_eval_host on a batch that is streamed in several chunks over two copy streams (> 2^18 points)."""
+    t = cb.LinearKnotSet(5, -1.0, 3.0, 200)
+    B = cb.BSpline(t)
+    x = np.random.default_rng(3).uniform(-1.2, 3.2, 700_001)
+    iv, vals = B.eval_ell_host(x)
+    ivd, valsd = B.eval_ell(x)
+    assert np.array_equal(iv, ivd.cpu().numpy()) and np.array_equal(vals, valsd.cpu().numpy())
+    ivo, valo = cbo.bspline_eval_ell(cbo.expand_knots(t.t, 5), 5, 5, x[:5000])
+    assert np.array_equal(iv[:5000], ivo) and relerr(vals[:5000], valo) <= RTOL

@@ -460,3 +460,33 @@ def test_fedvr_tridiagonal_destination(cb):
             T = A.skyline()
             assert isinstance(T, cb.Tridiagonal)
             assert np.array_equal(T.dense(), A.dense())
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_fedvr_and_fd_assembly_shards_reassemble_bit_exact(cb, world):
+    """K4 / K5 shards: element ranges of the FE-DVR blocks and node ranges of the finite-difference
+    stencils, one call per rank; the concatenation is bit-identical to the single assembly (uniform and mixed orders,
+    nder = 1, 2; Cartesian, staggered uniform and staggered non-uniform grids with the Coulomb correction on rank 0)."""
+    import torch
+    from compactbases_jl_b200.sharding import fedvr_assemble_sharded, fd_derivative_sharded
+    D = cb.Derivative()
+    for order in (7, np.array([4, 6, 3, 5, 7, 4, 6, 2, 5, 9, 3, 4, 8])):
+        nel = 13 if not np.isscalar(order) else 37
+        F = cb.FEDVR(cbo.julia_range(0.0, 5.0, nel + 1), order)
+        for nder in (1, 2):
+            full = F.derop(nder).clone()
+            parts = [fedvr_assemble_sharded(F, nder, r, world) for r in range(world)]
+            assert [p[0] for p in parts[1:]] == [p[1] for p in parts[:-1]] and parts[0][0] == 0 and parts[-1][1] == F.nel
+            assert torch.equal(torch.cat([p[2] for p in parts]), full)
+    grids = [cb.FiniteDifferences(1000, 0.01), cb.StaggeredFiniteDifferences(1001, 0.02),
+             cb.StaggeredFiniteDifferences(0.01 * np.arange(1, 778) ** 1.3)]
+    for R in grids:
+        for nder, Z in ((1, 0.0), (2, 0.0), (2, 1.0)):
+            if Z and isinstance(R, cb.FiniteDifferences):
+                continue
+            CD = cb.CoulombDerivative(D, Z, 0)
+            A = (R.T @ D @ R) if nder == 1 else ((R.T @ CD.T @ CD @ R) if Z else (R.T @ D.T @ D @ R))
+            parts = [fd_derivative_sharded(R, nder, r, world, Z=Z) for r in range(world)]
+            d = torch.cat([p[3] for p in parts]); du = torch.cat([p[4] for p in parts]); dl = torch.cat([p[2] for p in parts])
+            fd, fdu, fdl = A.d, A.du, A.dl
+            assert torch.equal(d, fd) and torch.equal(du, fdu) and torch.equal(dl, fdl)
