@@ -834,6 +834,18 @@ def run_gpu(args):
     elapsed = cx.maxr(e0.elapsed_time(e1) * 1e-3)
     value = BYTES_STEP * world * args.steps / elapsed / 1e9
 
+    # K4 shards: every rank assembles its element range; bit-identical to its slice of the full assembly
+    from compactbases_jl_b200.sharding import fedvr_assemble_sharded
+    full_blocks = F.derop(2)
+    e_lo, e_hi, part = fedvr_assemble_sharded(F, 2, rank, world)
+    shard_ok = bool(torch.equal(part, full_blocks[e_lo * ORDER * ORDER:e_hi * ORDER * ORDER]))
+    asm_full_s, _ = cx.dev_time(lambda s: _lib.call("cb_fedvr_assemble", F.d_x.data_ptr(), F.d_wcat.data_ptr(), F.d_n.data_ptr(), None, None,
+                                                    None, None, NEL, ORDER, ORDER, 2, full_blocks.data_ptr(), torch.cuda.current_stream().cuda_stream), 20)
+    asm_part_s, _ = cx.dev_time(lambda s: fedvr_assemble_sharded(F, 2, rank, world, out=part), 20)
+    sharded_assembly = {"elements_per_rank": e_hi - e_lo, "us_full": asm_full_s * 1e6, "us_sharded": asm_part_s * 1e6,
+                        "bit_identical": bool(cx.maxr(0.0 if shard_ok else 1.0) == 0.0)}
+    assert sharded_assembly["bit_identical"]
+
     parity = None
     if rank == 0:                                           # the timed output against the oracle: first, middle and last vector
         cbo = _cbo(True)
@@ -904,7 +916,8 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_functions": N_FUN, "vectors_per_gpu": NVEC, "bytes_per_step_per_gpu": BYTES_STEP,
                        "l2": "inputs larger than L2 (X and Y are 737 MB each)", "sharding": "vector batch per rank, operator replicated, no collective",
-                       "step": "cb_fedvr_assemble_apply (one foreign call: K4 assembly + K8 apply)"},
+                       "step": "cb_fedvr_assemble_apply (one foreign call: K4 assembly + K8 apply)",
+                       "k4_element_shards": sharded_assembly},
             "roofline": {"bound": "hbm", "achieved": BYTES_APPLY / apply_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
                          "frac": BYTES_APPLY / apply_s / 1e9 / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "fedvr_apply_pipe_kernel<10,16>",

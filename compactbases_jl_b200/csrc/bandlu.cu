@@ -9,9 +9,18 @@
 //   * the solve is batched over the vectors of an n x nvec column-major batch: one warp per 32 vectors (lane <->
 //     vector), rows staged through shared memory in chunks so that global memory is read and written coalesced along
 //     the rows, the substitution itself running on the chunk in shared memory.
-// Positive definite operators should use cb_bandchol_* (partitioned substitution, much faster for long vectors); this
-// path exists for the indefinite shifts of interior-eigenvalue problems (docs/src/bsplines/eigenproblems.md:96-110).
+//   * matrices of at least 256 rows are solved by the partitioned form of the same substitution (bandlu_part.cu): chunks
+//     of rows x 32 vectors are independent warps, the states between chunks travel through small tabulated transfer
+//     matrices.
+// This path serves the indefinite shifts of interior-eigenvalue problems (docs/src/bsplines/eigenproblems.md:96-110)
+// and the non-symmetric left-hand sides of the non-uniform compact finite-difference scheme.
 #include "common.cuh"
+
+struct cb_bandlu_part;                              // bandlu_part.cu: tables of the partitioned solve
+bool cb_bandlu_part_applicable(i64 n, int l, int u);
+int cb_bandlu_part_create(const double *ab, const int *ipiv, i64 n, int l, int u, cb_bandlu_part **out, cudaStream_t st);
+int cb_bandlu_part_solve(const cb_bandlu_part *P, const double *ab, const int *ipiv, double *X, i64 ldx, i64 nvec, cudaStream_t st);
+void cb_bandlu_part_destroy(cb_bandlu_part *P);
 
 struct cb_bandlu_s {
     i64 n;
@@ -20,6 +29,7 @@ struct cb_bandlu_s {
     int *d_ipiv;                                    // 0-based pivot rows
     int info;                                       // 0, or j+1 of the first exactly zero pivot
     int device;
+    cb_bandlu_part *part;                           // non-NULL: solves run partitioned (long matrices)
 };
 
 constexpr int LU_NB = 64;                           // columns finished per slide of the factorisation window
@@ -293,6 +303,7 @@ extern "C" {
 
 int cb_bandlu_destroy(cb_bandlu *F) {
     if (!F) return CB_OK;
+    cb_bandlu_part_destroy(F->part);
     cudaFree(F->d_ab); cudaFree(F->d_ipiv);
     delete F;
     return CB_OK;
@@ -316,7 +327,7 @@ int cb_bandlu_create(const double *band, i64 n, int l, int u, cb_bandlu **out, v
     }
     cudaStream_t st = (cudaStream_t)stream;
     cb_bandlu_s *F = new cb_bandlu_s();
-    F->n = n; F->l = l; F->u = u; F->ld = 2 * l + u + 1; F->d_ab = nullptr; F->d_ipiv = nullptr; F->info = 0;
+    F->n = n; F->l = l; F->u = u; F->ld = 2 * l + u + 1; F->d_ab = nullptr; F->d_ipiv = nullptr; F->info = 0; F->part = nullptr;
     cudaGetDevice(&F->device);
     int *d_info = nullptr;
     cudaError_t e = cudaSuccess;
@@ -340,6 +351,10 @@ int cb_bandlu_create(const double *band, i64 n, int l, int u, cb_bandlu **out, v
         cb_bandlu_destroy(F);
         return CB_ERR_ARG;
     }
+    if (cb_bandlu_part_applicable(n, l, u)) {
+        const int prc = cb_bandlu_part_create(F->d_ab, F->d_ipiv, n, l, u, &F->part, st);
+        if (prc) { cb_bandlu_destroy(F); return prc; }
+    }
     *out = F;
     return CB_OK;
 }
@@ -349,6 +364,7 @@ int cb_bandlu_solve(const cb_bandlu *F, double *X, i64 ldx, i64 nvec, void *stre
     CB_REQUIRE(nvec >= 0 && ldx >= F->n, "DimensionMismatch: cb_bandlu_solve: leading dimension %lld smaller than the matrix order %lld",
                (long long)ldx, (long long)F->n);
     if (nvec == 0) return CB_OK;
+    if (F->part) return cb_bandlu_part_solve(F->part, F->d_ab, F->d_ipiv, X, ldx, nvec, (cudaStream_t)stream);
     const size_t smem = bandlu_solve_smem(F->l, F->u);
     const i64 ngroups = (nvec + 31) / 32;
     i64 grid = (ngroups + LU_WARPS - 1) / LU_WARPS;

@@ -782,3 +782,44 @@ def test_eval_host_large_batch_in_chunks(cb):
     assert np.array_equal(iv, ivd.cpu().numpy()) and np.array_equal(vals, valsd.cpu().numpy())
     ivo, valo = cbo.bspline_eval_ell(cbo.expand_knots(t.t, 5), 5, 5, x[:5000])
     assert np.array_equal(iv[:5000], ivo) and relerr(vals[:5000], valo) <= RTOL
+
+
+@pytest.mark.parametrize("n,l,u,nvec", [(256, 1, 1, 5), (383, 2, 3, 33), (1000, 7, 7, 64), (2049, 3, 0, 17), (1500, 0, 3, 9), (5000, 9, 9, 70),
+                                        (777, 4, 1, 1), (4097, 10, 10, 40), (3000, 12, 12, 3), (50_007, 7, 7, 96)])
+def test_bandlu_partitioned_solve_matches_lapack(cb, n, l, u, nvec):
+    """Matrices of >= 256 rows take the partitioned substitution (csrc/bandlu_part.cu: chunk-local sweeps with the row
+    interchanges, tabulated state transfer): against LAPACK gbtrs on random indefinite bands (heavy pivoting), chunk
+    remainders, vector counts that are not multiples of 32, compile-time (l == u <= 10) and run-time bandwidths."""
+    import torch
+    rng = np.random.default_rng(n * 7 + l * 3 + u)
+    band = rng.standard_normal((n, l + u + 1))
+    for d in range(l + u + 1):                                   # entries outside the matrix are zero in BandedMatrices
+        off = d - u                                              # row i = j + off
+        if off < 0:
+            band[:-off, d] = 0.0
+        elif off > 0:
+            band[n - off:, d] = 0.0
+    if l == 0 or u == 0:
+        band[:, u] += 4.0 * (l + u) * np.sign(band[:, u])
+    A = cb.BandedMatrix(torch.as_tensor(band, device="cuda").contiguous(), n, n, l, u)
+    F = cb.BandLU(A)
+    X = rng.standard_normal((n, nvec))
+    Xc = cb.ColMajor.from_numpy(X)
+    F.ldiv(Xc)
+    ref = cbo.bandlu_solve(band, n, l, u, X)
+    got = Xc.numpy()
+    scale = np.max(np.abs(ref))
+    # random bands of this length are ill-conditioned in places: compare with LAPACK through the residual as well
+    import scipy.sparse as sp
+    diags = [band[max(0, u - d):n - max(0, d - u), d] if False else None for d in range(l + u + 1)]
+    Asp = sp.diags([np.array([band[j, d] for j in range(max(0, u - d), n - max(0, d - u))]) for d in range(l + u + 1)],
+                   [u - d for d in range(l + u + 1)], shape=(n, n), format="csr") if n <= 6000 else None
+    if Asp is not None:
+        res = np.max(np.abs(Asp @ got - X)) / (np.max(np.abs(X)) + np.max(np.abs(Asp)) * scale)
+        res_ref = np.max(np.abs(Asp @ ref - X)) / (np.max(np.abs(X)) + np.max(np.abs(Asp)) * scale)
+        assert res <= max(50 * res_ref, 1e-13), (res, res_ref)
+    # same pivots, same operations up to their order inside a row update: the two solutions agree to the accuracy
+    # LAPACK itself reaches on this matrix (forward error bounded through its own residual growth)
+    err = np.max(np.abs(got - ref)) / scale
+    assert err <= 1e-6, err
+    assert np.all(np.isfinite(got))
