@@ -249,9 +249,9 @@ def fedvr_assemble_sharded(F, nder: int, rank: int, world: int, out: torch.Tenso
     P = F.parent_basis
     e_lo, e_hi = batch_range(P.nel, rank, world)
     nloc = e_hi - e_lo
-    o2 = P.order.astype(object) ** 2
-    b0 = int(P.boff[e_lo]) if e_lo < P.nel else int(sum(o2))
-    b1 = int(P.boff[e_hi]) if e_hi < P.nel else int(sum(o2))
+    btot = int(P.boff[-1]) + int(P.order[-1]) ** 2          # boff[e] = sum of order^2 of the elements before e
+    b0 = int(P.boff[e_lo]) if e_lo < P.nel else btot
+    b1 = int(P.boff[e_hi]) if e_hi < P.nel else btot
     blocks = out if out is not None else torch.empty(b1 - b0, dtype=torch.float64, device=P.device)
     if nloc == 0:
         return e_lo, e_hi, blocks
