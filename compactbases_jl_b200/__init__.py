@@ -18,6 +18,8 @@ from .fedvr import FEDVR, RestrictedFEDVR
 from .finite_differences import (FiniteDifferences, ImplicitFiniteDifferences, RestrictedFiniteDifferences,
                                  StaggeredFiniteDifferences)
 from .densities import Density, DiagonalOperator, FunctionProduct
+from .complex_ops import (ComplexColMajor, ComplexOperator, ComplexScaledFEDVR, cmul, complex_ldiv, complex_linear_operator,
+                          complex_potential)
 
 __all__ = [
     "ArbitraryKnotSet", "ExpKnotSet", "LinearKnotSet", "BSpline", "RestrictedBSpline", "SparseMatrixCSC",

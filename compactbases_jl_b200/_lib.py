@@ -58,6 +58,9 @@ _SIGNATURES = {
     "cb_bspline_assemble_host": (cint, [vp, vp, cint, cint, vp, cint, dbl, i64, i64, i64, i64, cint, cint, vp, vp]),
     "cb_bspline_assemble_pair": (cint, [vp, vp, cint, dbl, i64, i64, vp, vp, vp]),
     "cb_band_to_tridiag": (cint, [vp, i64, vp, vp, vp, vp]),
+    "cb_complex_split": (cint, [vp, i64, i64, i64, vp, i64, vp]),
+    "cb_complex_combine": (cint, [vp, vp, i64, i64, i64, dbl, dbl, dbl, dbl, vp, i64, vp]),
+    "cb_fedvr_assemble_complex": (cint, [vp, vp, vp, vp, vp, vp, vp, i64, cint, cint, cint, i64, dbl, vp, vp, vp]),
     "cb_fedvr_assemble": (cint, [vp, vp, vp, vp, vp, vp, vp, i64, cint, cint, cint, vp, vp]),
     "cb_fedvr_to_dense": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp]),
     "cb_fedvr_to_skyline": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp]),

@@ -309,6 +309,28 @@ int cb_batched_dot(const double *U, cb_i64 ldu, const double *W, cb_i64 ldw, cb_
                    double scale, double *out, void *stream);
 
 /* ------------------------------------------------------------------------
+ * ComplexF64.  The reference runs every basis with T = ComplexF64 (test/linear_operators.jl:1-35:
+ * complex potential, complex coefficients) and has a complex-scaled FE-DVR basis (src/fedvr.jl:17-37,95-96).  A complex
+ * operator is a PAIR of real device operators A = Ar + i Ai (assembly is linear in the potential; FE-DVR blocks come as
+ * two real block arrays); a complex batch Z (n x nvec ComplexF64, column-major, interleaved re / im — Julia's layout;
+ * leading dimensions in complex elements) is split into the real batch R = [Re | Im] of 2 nvec vectors, the real apply
+ * entries above run on R, and one call recombines:
+ *   T1 = Ar R, T2 = Ai R (NULL for a real operator):   Y = alpha (T1[Re] - T2[Im] + i (T1[Im] + T2[Re])) + beta Y
+ * with complex alpha, beta (beta == 0: Y is not read). */
+int cb_complex_split(const double *Z, cb_i64 ldz, cb_i64 n, cb_i64 nvec, double *R, cb_i64 ldr, void *stream);
+int cb_complex_combine(const double *T1, const double *T2, cb_i64 ldt, cb_i64 n, cb_i64 nvec,
+                       double alpha_re, double alpha_im, double beta_re, double beta_im,
+                       double *Y, cb_i64 ldy, void *stream);
+/* derop!(A, B, nder) for the complex-scaled FE-DVR basis (src/fedvr_derivatives.jl:15-63 with complex nodes x and
+ * normalisation nrm — interleaved re / im — and real weights wcat): elements e >= first_rotated (0-based; i0 - 1 of the
+ * reference) are divided by sqrt(e^{i phi}) (:55); Julia's dot conjugates the transposed derivative in the second-order
+ * form.  blocks_re / blocks_im: the two real block arrays of cb_fedvr_assemble's layout. */
+int cb_fedvr_assemble_complex(const double *x, const double *wcat, const double *nrm,
+                              const cb_i64 *estart, const int32_t *order, const cb_i64 *boff, const cb_i64 *woff,
+                              cb_i64 nel, int uniform_order, int max_order, int nder, cb_i64 first_rotated, double phi,
+                              double *blocks_re, double *blocks_im, void *stream);
+
+/* ------------------------------------------------------------------------
  * Mutual densities (src/densities.jl).  rho = C * (conj(RV f) .* (LV g)).
  * ---------------------------------------------------------------------- */
 typedef struct cb_density_s cb_density;

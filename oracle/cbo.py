@@ -847,3 +847,77 @@ def implicit_derivative_apply_general(Delta, M, c, X, alpha=1.0, beta=0.0, Y=Non
     if beta != 0.0:
         rhs = rhs + beta * np.asarray(Y, dtype=np.float64)
     return c * np.linalg.solve(M, rhs)
+
+
+# ---- complex-scaled FE-DVR (src/fedvr.jl:9-53, src/fedvr_derivatives.jl:15-57), numpy restatement ------------------------
+# PARITY UNPINNED: the reference holds no golden values for the complex-scaled operators (test/fedvr/complex_scaling.jl
+# checks complex_rotate and real_locs only, src/fedvr_derivatives.jl:55 carries a "TODO Check if correct"); this is a
+# literal transcription of the Julia loops, including the dropped rotation of the nodes (src/quadrature.jl:25-27 calls
+# change_interval! without its gamma argument) and the conjugation inside LinearAlgebra.dot.
+def fedvr_complex_fields(t, order, t0, phi):
+    t = np.asarray(t, dtype=np.float64)
+    nel = len(t) - 1
+    order = np.full(nel, order, dtype=np.int64) if np.isscalar(order) else np.asarray(order, dtype=np.int64)
+    idx = np.nonzero(t >= t0)[0]
+    if idx.size == 0:
+        raise ValueError("Complex scaling starting point outside grid")
+    i0 = int(idx[0]) + 1
+    t0 = t[i0 - 1]
+    eiphi = np.exp(1j * phi)
+    xs, ws = [], []
+    for i in range(nel):
+        xi, wr = gausslobatto(int(order[i]))
+        a, b = t[i] - t0, t[i + 1] - t0
+        tt_ = (xi + 1) / 2
+        xloc = np.array([np.float64(_fma(tv, b, _fma(-tv, a, a))) for tv in tt_])     # gamma = one(T): no rotation
+        xs.append((t0 + xloc).astype(np.complex128))
+        ws.append((b - a) * wr / 2)
+    rot = lambda i, v: eiphi * v if i + 1 >= i0 else v + 0j
+    ns = [1.0 / np.sqrt(rot(i, w_)) for i, w_ in enumerate(ws)]
+    for i in range(nel - 1):
+        v = 1.0 / np.sqrt(rot(i, ws[i][-1]) + rot(i + 1, ws[i + 1][0]))
+        ns[i][-1] = v
+        ns[i + 1][0] = v
+    return dict(order=order, i0=i0, t0=t0, eiphi=eiphi, x=xs, w=ws, n=ns)
+
+
+def fedvr_complex_element(xi, wi, ni, nder, rotated, eiphi):
+    """diff(B, n, i) (src/fedvr_derivatives.jl:43-57) for one element with complex nodes xi, real weights wi, complex
+    normalisation ni."""
+    o = len(xi)
+    Lp = np.zeros((o, o), dtype=np.complex128)
+    for m in range(o):                                   # lagrangeder!, :15-31
+        Lp[m, m] = ((1 if m == o - 1 else 0) - (1 if m == 0 else 0)) / (2 * wi[m])
+        for mp in range(o):
+            if mp == m:
+                continue
+            f = 1.0 + 0j
+            for k in range(o):
+                if k == m or k == mp:
+                    continue
+                f *= (xi[mp] - xi[k]) / (xi[m] - xi[k])
+            Lp[m, mp] = f / (xi[m] - xi[mp])
+    Lt = np.eye(o, dtype=np.complex128) if nder == 1 else -Lp
+    D = np.zeros((o, o), dtype=np.complex128)
+    for m in range(o):                                   # diff!, :33-41 (dot conjugates its first argument)
+        for mp in range(o):
+            D[m, mp] = ni[m] * ni[mp] * np.vdot(Lt[m, :], wi * Lp[mp, :])
+    if rotated:
+        D = D / np.sqrt(eiphi)
+    return D
+
+
+def fedvr_complex_dense(fields, nder):
+    """The matrix set_elements! builds from the complex element blocks (bridge entries summed)."""
+    order = fields["order"]
+    N = int(np.sum(order - 1)) + 1
+    A = np.zeros((N, N), dtype=np.complex128)
+    start = 0
+    blocks = []
+    for i in range(len(order)):
+        o = int(order[i])
+        D = fedvr_complex_element(fields["x"][i], fields["w"][i], fields["n"][i], nder, i + 1 >= fields["i0"], fields["eiphi"])
+        A[start:start + o, start:start + o] += D
+        blocks.append(D)
+        start += o - 1
+    return A, blocks

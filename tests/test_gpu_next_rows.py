@@ -831,3 +831,92 @@ def test_bandlu_partitioned_solve_matches_lapack(cb, n, l, u, nvec):
     err = np.max(np.abs(got - ref)) / scale
     assert err <= 1e-6, err
     assert np.all(np.isfinite(got))
+
+
+# ---------------------------------------------------------------------------
+# ComplexF64
+# ---------------------------------------------------------------------------
+COMPLEX_BASES = [
+    ("fd", lambda cb: cb.FiniteDifferences(100, 10.0 / 101)),
+    ("sfd_uniform", lambda cb: cb.StaggeredFiniteDifferences(100, 10.0 / 99.5)),
+    ("sfd_nonuniform", lambda cb: cb.StaggeredFiniteDifferences(np.cumsum(np.minimum(0.1 + 0.01 * np.arange(160), 0.2))[:120])),
+    ("fedvr", lambda cb: cb.FEDVR(cbo.julia_range(0.0, 10.0, 100), 4)),
+    ("bsplines", lambda cb: cb.BSpline(cb.LinearKnotSet(5, 0, 10.0, 100))),
+]
+
+
+def crelerr(a, b):
+    a, b = np.asarray(a, dtype=np.complex128), np.asarray(b, dtype=np.complex128)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("name,make", COMPLEX_BASES, ids=[c[0] for c in COMPLEX_BASES])
+def test_complex_linear_operator(cb, name, make):
+    """test/linear_operators.jl:1-35 with T = ComplexF64: V = LinearOperator(R'*QuasiDiagonal(f.(x))*R, R) with
+    f = exp(i pi/4) sin(2 pi x / L) applied to the coefficients of o(x) = 1 gives the coefficients of f, u ~ fc; plus
+    the complex mul! against a dense complex product with complex alpha, beta."""
+    R = make(cb)
+    L = 10.0
+    gamma = np.exp(1j * np.pi / 4)
+    f = lambda x: gamma * np.sin(2 * np.pi * np.asarray(x) / L)
+    one = lambda x: np.ones_like(np.asarray(x, dtype=np.float64)) + 0j
+    fc = cb.complex_ldiv(R, f)
+    oc = cb.complex_ldiv(R, one)
+    V = cb.complex_linear_operator(cb.complex_potential(R, f), R)
+    m = R.size()
+    assert V.shape == (m, m)
+    u = cb.ComplexColMajor.zeros(m, 1)
+    cb.cmul(u, V, oc)
+    un, fn = u.numpy()[:, 0], fc.numpy()[:, 0]
+    assert np.linalg.norm(un - fn) <= 2e-8 * np.linalg.norm(fn), np.linalg.norm(un - fn) / np.linalg.norm(fn)   # isapprox: rtol = sqrt(eps)
+    # mul! with complex scalars against the dense complex operator (no metric)
+    A = cb.complex_potential(R, f)
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((m, 5)) + 1j * rng.standard_normal((m, 5))
+    Y0 = rng.standard_normal((m, 5)) + 1j * rng.standard_normal((m, 5))
+    Y = cb.ComplexColMajor.from_numpy(Y0)
+    al, be = 0.5 - 2.0j, -1.5 + 0.25j
+    cb.cmul(Y, A, cb.ComplexColMajor.from_numpy(X), al, be)
+    ref = al * (A.dense() @ X) + be * Y0
+    assert crelerr(Y.numpy(), ref) <= RTOL
+    # a real operator on complex coefficients
+    D = cb.Derivative()
+    T = R.T @ D.T @ D @ R
+    Yr = cb.ComplexColMajor.zeros(m, 5)
+    cb.cmul(Yr, T, cb.ComplexColMajor.from_numpy(X))
+    Td = T.dense() if hasattr(T, "dense") else None
+    assert crelerr(Yr.numpy(), Td @ X) <= RTOL
+
+
+def test_complex_scaled_fedvr(cb):
+    """test/fedvr/complex_scaling.jl (complex_rotate, real_locs, the ArgumentError) and the complex element matrices /
+    their application against a literal numpy transcription of src/fedvr_derivatives.jl:15-57."""
+    t = cbo.julia_range(0.0, 20.0, 71)
+    C = cb.ComplexScaledFEDVR(t, 10, t0=10.0, phi=np.pi / 3)
+    assert C.t0 >= 10.0
+    with pytest.raises(ValueError):
+        cb.ComplexScaledFEDVR(t, 10, t0=30.0, phi=np.pi / 3)
+    assert C.complex_rotate(5) == 5
+    assert abs(C.complex_rotate(15) - (C.t0 + (15 - C.t0) * np.exp(1j * np.pi / 3))) <= 1e-15
+    Rr = cb.FEDVR(cbo.julia_range(0.0, 20.0, 11), 10)
+    Rc = cb.ComplexScaledFEDVR(cbo.julia_range(0.0, 20.0, 11), 10, t0=10.0, phi=np.pi / 3)
+    assert np.linalg.norm(Rc.real_locs() - Rr.x) == 0
+    D = cb.Derivative()
+    for order in (10, np.array([4, 6, 3, 5, 7, 4, 6, 2, 5, 9])):
+        tt = cbo.julia_range(0.0, 20.0, 11)
+        B = cb.ComplexScaledFEDVR(tt, order, t0=7.0, phi=np.pi / 5)
+        fields = cbo.fedvr_complex_fields(tt, order, 7.0, np.pi / 5)
+        assert B.i0 == fields["i0"]
+        xo = np.concatenate([fields["x"][0]] + [v[1:] for v in fields["x"][1:]])
+        no = np.concatenate([fields["n"][0]] + [v[1:] for v in fields["n"][1:]])
+        assert np.array_equal(B.x, xo) and crelerr(B.n, no) <= 1e-15
+        rng = np.random.default_rng(5)
+        X = rng.standard_normal((B.N, 6)) + 1j * rng.standard_normal((B.N, 6))
+        for nder, A in ((1, B.T @ D @ B), (2, B.T @ D.T @ D @ B)):
+            ref, blocks = cbo.fedvr_complex_dense(fields, nder)
+            bre, bim = B.derop(nder)
+            got = bre.cpu().numpy() + 1j * bim.cpu().numpy()
+            want = np.concatenate([b.ravel(order="F") for b in blocks])
+            assert crelerr(got, want) <= RTOL
+            Y = A @ cb.ComplexColMajor.from_numpy(X)
+            assert crelerr(Y.numpy(), ref @ X) <= RTOL

@@ -566,3 +566,18 @@ def test_density_banded_qr_equals_dense_pinv():
         r1 = cbo.density_bspline(V[:, 1:nf - 2], f[:nf - 3], g[:nf - 3, :1])
         r2 = cbo.density_bspline_qr(t, k, x, q, f[:nf - 3], g[:nf - 3, :1], None, 1, nf - 3)
         assert np.max(np.abs(r1 - r2)) <= 1e-12 * np.max(np.abs(r1))
+
+
+def test_complex_fedvr_restatement_reduces_to_the_real_one():
+    """The numpy transcription of the complex-scaled FE-DVR element matrices (parity unpinned in the reference) must
+    reproduce the pinned real restatement when the rotation angle vanishes (e^{i phi} = 1, scaling from the first
+    element: same offset t0 = t[1] in element_grid)."""
+    t = cbo.julia_range(0.0, 7.0, 9)
+    for order in (5, np.array([3, 4, 2, 6, 5, 3, 4, 7])):
+        fields = cbo.fedvr_complex_fields(t, order, 0.0, 0.0)
+        O = cbo.FEDVROracle(t, order)
+        for nder in (1, 2):
+            A, _ = cbo.fedvr_complex_dense(fields, nder)
+            ref = O.dense(O.blocks(nder))
+            assert np.max(np.abs(A.imag)) == 0.0
+            assert np.max(np.abs(A.real - ref)) <= 1e-12 * np.max(np.abs(ref))
