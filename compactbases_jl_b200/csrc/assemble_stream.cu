@@ -293,10 +293,25 @@ __device__ __forceinline__ void stream_copy_out(const StreamArgs &A, const doubl
     }
 }
 
+#ifdef STREAM_PROF
+__device__ unsigned long long stream_prof[8];      // cycles of thread 0 of every CTA: [0] segment A, [1] segment B, [2] steps
+#define SPROF(i) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&stream_prof[i], (unsigned long long)(t__ - tprof)); tprof = t__; } } while (0)
+extern "C" int cb_debug_stream_prof(unsigned long long *out, int reset) {
+    cudaMemcpyFromSymbol(out, stream_prof, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(stream_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define SPROF(i) do { } while (0)
+#endif
+
 template <int K, int M>
 __global__ void __launch_bounds__(STREAM_MAX_THREADS, 1)
 bspline_assemble_stream_kernel(StreamArgs A) {
     extern __shared__ __align__(16) double sm[];
+#ifdef STREAM_PROF
+    long long tprof = clock64();
+#endif
     using G = StreamGeom<K>;
     constexpr int QH = G::QH, KP2 = G::KP2, KH = G::KH, W = G::W, NE = G::NE, MSP = G::MSP, PIV = G::PIV, QPW = G::QPW;
     constexpr int AS = StreamSplit<K>::AS;
@@ -442,7 +457,9 @@ bspline_assemble_stream_kernel(StreamArgs A) {
         }
         if (tid < ns_next + 2 * K) RAW[tid] = raw_next;
         if (tid < ns_next) ord_next[tid] = ord_n;
+        SPROF(3);                                       // thread 0's own work in segment A
         __syncthreads();
+        SPROF(0);                                       // + waiting for the slowest warp
         // ======== segment B: three roles side by side ========
         prefetch_nodes(ns_next, ord_next);
         if (warp < W2B) {
@@ -513,7 +530,12 @@ bspline_assemble_stream_kernel(StreamArgs A) {
             const int nem = (int)(jl - jnext < CAP ? jl - jnext : CAP);
             pend_j = jnext; pend_n = nem; jnext += nem;
         }
+        SPROF(4);
         __syncthreads();
+        SPROF(1);
+#ifdef STREAM_PROF
+        if (threadIdx.x == 0) atomicAdd(&stream_prof[2], 1ull);
+#endif
         if (t >= nsteps && jnext >= j1) break;
     }
     if (pend_n > 0) {

@@ -201,15 +201,18 @@ csc_scatter_kernel(const int32_t *__restrict__ interval, const double *__restric
         unsigned above = 0;                          // my columns that a higher lane also holds
         for (int Lp = 0; Lp < 32; ++Lp) {
             const int Ip = __shfl_sync(0xffffffffu, I, Lp);
-            const unsigned vp = __shfl_sync(0xffffffffu, vm, Lp);
             const int d = Ip - I;
-            if (Lp != lane && d > -K && d < K && vp != 0u && vm != 0u) {
-                const unsigned sh = (d >= 0 ? (vp << d) : (vp >> (-d))) & vm;
-                if (Lp < lane) {
+            const bool near = Lp != lane && d > -K && d < K && Ip > 0 && vm != 0u;
+            if (__any_sync(0xffffffffu, near)) {     // warp-uniform: unsorted points rarely share columns inside a warp
+                const unsigned vp = __shfl_sync(0xffffffffu, vm, Lp);
+                if (near && vp != 0u) {
+                    const unsigned sh = (d >= 0 ? (vp << d) : (vp >> (-d))) & vm;
+                    if (Lp < lane) {
 #pragma unroll
-                    for (int a = 0; a < K; ++a) rk[a] += (sh >> a) & 1u;
-                } else {
-                    above |= sh;
+                        for (int a = 0; a < K; ++a) rk[a] += (sh >> a) & 1u;
+                    } else {
+                        above |= sh;
+                    }
                 }
             }
         }
