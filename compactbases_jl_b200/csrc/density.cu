@@ -844,32 +844,44 @@ density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, doub
     }
 }
 
-// B3: x_j = zloc_j + SB[j] . sb_c (+ addto): no recurrence.  One thread per row and DS_FIXP pairs: the spike row
-// stays in registers, the states are warp-uniform loads, X is read and written along the rows.
-constexpr int DS_FIXP = 16;
+// B3: x_j = zloc_j + SB[j] . sb_c (+ addto): no recurrence.  A CTA takes 256 rows of one chunk and a tile of DS_FIXP pairs:
+// the chunk's incoming states of those pairs sit in shared memory ([pair][8]: two 16-byte broadcast reads fetch four
+// components), the spike row of a thread's row stays in registers, X is read and written along the rows.  (One thread
+// per row with the states as warp-uniform global loads issued nine memory instructions per element: 2.5 ms at C5.)
+constexpr int DS_FIXP = 32;
 
 template <int K>
 __global__ void __launch_bounds__(256)
 density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
                        const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
-    constexpr int S = K > 1 ? K - 1 : 1;
+    constexpr int S = K > 1 ? K - 1 : 1, SP = (S + 1) / 2 * 2;
+    __shared__ __align__(16) double sst[DS_FIXP * SP];
     const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
-    for (i64 pg = blockIdx.y; pg < npg; pg += gridDim.y) {
-        const i64 pa = pg * DS_FIXP, pb = pa + DS_FIXP < P ? pa + DS_FIXP : P;
-        for (i64 j = blockIdx.x * (i64)blockDim.x + threadIdx.x; j < n; j += (i64)gridDim.x * blockDim.x) {
-            i64 c = j / DS_CH; if (c > nchunk - 1) c = nchunk - 1;
-            double sr[S];
+    const i64 nrb = (n + 255) / 256;                // row blocks: 256 rows, never across a chunk boundary (DS_CH = 256) except in the last chunk
+    for (i64 item = blockIdx.x; item < nrb * npg; item += gridDim.x) {
+        const i64 rb = item % nrb, pg = item / nrb;
+        const i64 pa = pg * DS_FIXP;
+        const int np = (int)(pa + DS_FIXP < P ? DS_FIXP : P - pa);
+        i64 c = rb * 256 / DS_CH; if (c > nchunk - 1) c = nchunk - 1;
+        __syncthreads();
+        for (int e = threadIdx.x; e < DS_FIXP * SP; e += 256) {
+            const int pp = e / SP, i = e - pp * SP;
+            sst[e] = (pp < np && i < S) ? St[(c * S + i) * P + pa + pp] : 0.0;
+        }
+        __syncthreads();
+        const i64 j = rb * 256 + threadIdx.x;
+        if (j >= n) continue;
+        double sr[SP];
 #pragma unroll
-            for (int i = 0; i < S; ++i) sr[i] = sb[j * S + i];
-            const double *st = St + c * S * P;
+        for (int i = 0; i < SP; ++i) sr[i] = i < S ? sb[j * S + i] : 0.0;
 #pragma unroll 4
-            for (i64 p = pa; p < pb; ++p) {
-                double v = X[j + ldx * p];
+        for (int pp = 0; pp < np; ++pp) {
+            double v = X[j + ldx * (pa + pp)];
+            const double2 *s2 = reinterpret_cast<const double2 *>(sst + pp * SP);
 #pragma unroll
-                for (int i = 0; i < S; ++i) v = fma(sr[i], st[i * P + p], v);
-                if (addto) v += addto[j + lda * p];
-                X[j + ldx * p] = v;
-            }
+            for (int h = 0; h < SP / 2; ++h) { const double2 t = s2[h]; v = fma(sr[2 * h], t.x, v); v = fma(sr[2 * h + 1], t.y, v); }
+            if (addto) v += addto[j + lda * (pa + pp)];
+            X[j + ldx * (pa + pp)] = v;
         }
     }
 }
@@ -1020,9 +1032,8 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #endif
-    const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
-    dim3 gfix((unsigned)cb_grid_for(n, 256, 2), (unsigned)(npg < 4096 ? npg : 4096));
-    density_bwd_fix_kernel<K><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
+    const i64 nfix = ((n + 255) / 256) * ((P + DS_FIXP - 1) / DS_FIXP);
+    density_bwd_fix_kernel<K><<<(unsigned)(nfix < (i64)CB_NUM_SMS * 32 ? nfix : (i64)CB_NUM_SMS * 32), 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
     cudaError_t e = cudaGetLastError();
     if (!ws_fwd) cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { cb_set_error("cb_density_apply: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
