@@ -1,6 +1,7 @@
 // bspline.cu — B-spline basis handle, lgwt, batched evaluation (K1), CSC export
 // (K1b), fused spline evaluation and quadrature tables (K2).
 #include <cub/cub.cuh>
+#include <mutex>
 
 #include "bspline_core.cuh"
 
@@ -423,6 +424,8 @@ int cb_bspline_eval_host(const cb_bspline *B, const double *xh, i64 nx, int m,
     // chunks on two streams so that the upload of one chunk overlaps the evaluation / download of the other
     { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
     static cudaStream_t hs[64][2] = {};
+    static std::mutex hs_mu;                         // the copy streams are shared: host-buffer calls are serialised
+    std::lock_guard<std::mutex> hs_lock(hs_mu);
     int dev = 0;
     CB_CUDA(cudaGetDevice(&dev));
     CB_REQUIRE(dev >= 0 && dev < 64, "cb_bspline_eval_host: device index %d out of range", dev);

@@ -74,10 +74,13 @@ class _FEDVROrRestricted:
     def _materialize(self, L, middle):
         if not isinstance(L, _FEDVROrRestricted) or L.parent_basis is not self.parent_basis:
             raise ValueError("Cannot multiply functions on different grids")
-        if (L.first, L.last) != (self.first, self.last):
-            raise NotImplementedError("FE-DVR operators between different restrictions")
+        # The reference's materialisers (src/fedvr_derivatives.jl:66-97) check the parents only and build the destination
+        # from B alone (Matrix(undef, B), derop!(dest, B, n)): the restriction of the adjoint factor is ignored.  Same here.
         P = self.parent_basis
         mid = list(middle)
+        same = (L.first, L.last) == (self.first, self.last)
+        if not same and (not mid or all(isinstance(f, QuasiDiagonal) for f in mid)):
+            raise NotImplementedError("FE-DVR mass / potential matrices between different restrictions")
         if not mid:                                  # mass matrix = identity, src/fedvr.jl:331-333
             return Diagonal(torch.ones(self.size(), dtype=torch.float64, device=P.device))
         if all(isinstance(f, QuasiDiagonal) for f in mid):   # src/fedvr_operators.jl:158-185

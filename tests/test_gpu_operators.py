@@ -490,3 +490,16 @@ def test_fedvr_and_fd_assembly_shards_reassemble_bit_exact(cb, world):
             d = torch.cat([p[3] for p in parts]); du = torch.cat([p[4] for p in parts]); dl = torch.cat([p[2] for p in parts])
             fd, fdu, fdl = A.d, A.du, A.dl
             assert torch.equal(d, fd) and torch.equal(du, fdu) and torch.equal(dl, fdl)
+
+
+def test_fedvr_derivative_uses_the_right_hand_restriction(cb):
+    """src/fedvr_derivatives.jl:66-97: the materialisers of A'*D*B / A'*D'*D*B only compare the parents and size the result
+    by B (Matrix(undef, B); derop!(dest, B, n)) — whatever the restriction of A."""
+    F = cb.FEDVR(cbo.julia_range(0.0, 3.0, 7), 5)
+    D = cb.Derivative()
+    A, B = F[:, 1:F.N - 2], F[:, 2:F.N - 1]
+    got = (A.T @ D.T @ D @ B).dense()
+    ref = (B.T @ D.T @ D @ B).dense()
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        cb.FEDVR(cbo.julia_range(0.0, 3.0, 8), 5).T @ D @ B
