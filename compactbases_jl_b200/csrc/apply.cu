@@ -1201,6 +1201,9 @@ fedvr_apply_pipe_kernel(const double *__restrict__ blocks, i64 nel, i64 first0 /
                     af[mt][ks] = (have && gq + 8 * mt < O && 4 * ks + tq < O && (mt == 0 || g < ET))
                                      ? __ldg(b + 4 * ks * O + 8 * mt) : 0.0;
         };
+        // launched behind cb_fedvr_assemble with programmatic stream serialisation (cb_fedvr_assemble_apply): the loader
+        // already fills the ring with x tiles while the assembly grid drains; the blocks are read after it has completed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         if (vt < nvt) load_frags(et * ET);
         for (; vt < nvt; parity ^= 1) {
             const i64 eA = et * ET;
@@ -1475,6 +1478,9 @@ static int check_apply_args(const char *who, i64 m, i64 n, const double *X, i64 
     return CB_OK;
 }
 
+// set by cb_fedvr_assemble_apply around its apply launch: the pipeline kernel may start while the assembly kernel drains
+static thread_local bool g_fedvr_after_assembly = false;
+
 template <int O>
 static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, const double *X, i64 ldx, i64 nvec,
                         double alpha, double beta, double *Y, i64 ldy, cudaStream_t st) {
@@ -1494,7 +1500,18 @@ static int launch_fedvr(const double *blocks, i64 nel, i64 first0, i64 nrows, co
         CB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
         const i64 ntiles = ((nel + P::ET - 1) / P::ET) * ((nvec + FE_TV - 1) / FE_TV);
         const int pgrid = (int)(ntiles < CB_NUM_SMS ? ntiles : CB_NUM_SMS);
-        pk<<<pgrid, P::THREADS, P::SMEM, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+        if (g_fedvr_after_assembly) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)pgrid); cfg.blockDim = dim3((unsigned)P::THREADS);
+            cfg.dynamicSmemBytes = P::SMEM; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CB_CUDA(cudaLaunchKernelEx(&cfg, pk, blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy));
+        } else {
+            pk<<<pgrid, P::THREADS, P::SMEM, st>>>(blocks, nel, first0, nrows, X, ldx, nvec, alpha, beta, Y, ldy);
+        }
         CB_LAUNCH_CHECK();
         return CB_OK;
     }
@@ -1726,7 +1743,11 @@ int cb_fedvr_assemble_apply(const double *x, const double *wcat, const double *n
                             double alpha, double beta, double *Y, i64 ldy, void *stream) {
     int rc = cb_fedvr_assemble(x, wcat, nrm, estart, order, boff, woff, nel, uniform_order, max_order, nder, blocks, stream);
     if (rc) return rc;
-    return cb_fedvr_apply(blocks, estart, order, boff, nel, uniform_order, first, last, X, ldx, nvec, alpha, beta, Y, ldy, stream);
+    static const bool serial = getenv("CB_FEDVR_NO_PDL") != nullptr;
+    g_fedvr_after_assembly = !serial;
+    rc = cb_fedvr_apply(blocks, estart, order, boff, nel, uniform_order, first, last, X, ldx, nvec, alpha, beta, Y, ldy, stream);
+    g_fedvr_after_assembly = false;
+    return rc;
 }
 
 int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,

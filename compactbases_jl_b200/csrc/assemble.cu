@@ -590,6 +590,119 @@ fedvr_assemble_kernel(const double *__restrict__ x, const double *__restrict__ w
     }
 }
 
+// Uniform element order O <= 16: floor(32 / O) elements per warp, one lane per ROW m of an element.  The lane keeps the
+// element's nodes, its reciprocal differences 1 / (x_m - x_k) and its row of L' in registers with compile-time
+// indices (no shared-memory tables, no index divisions); only the rows of (w .* L') that every other row of the element
+// needs pass through shared memory.  Same operations in the same order as fedvr_assemble_kernel — bit-identical —
+// at a sixth of the warp instructions (the one-warp-per-element kernel is issue-bound: 1382 warp instructions per
+// element at order 10, 19 of 32 lanes active).
+#ifndef FEG_WARPS_PER_BLOCK
+#define FEG_WARPS_PER_BLOCK 1
+#endif
+#ifndef FEG_MAXREG
+#define FEG_MAXREG 255
+#endif
+constexpr int FEG_WARPS = FEG_WARPS_PER_BLOCK;
+
+template <int O>
+__global__ void __launch_bounds__(FEG_WARPS * 32)
+#if FEG_MAXREG < 255
+__maxnreg__(FEG_MAXREG)
+#endif
+fedvr_assemble_rows_kernel(const double *__restrict__ x, const double *__restrict__ wcat, const double *__restrict__ nrm,
+                           i64 nel, int nder, double *__restrict__ blocks) {
+    constexpr int G = 32 / O;                       // elements per warp
+    constexpr int OP = O + (O & 1);                 // row stride (even: rows are read as double2)
+    __shared__ __align__(16) double sD[FEG_WARPS][G * O * OP];      // rows of x_m - x_k
+    __shared__ __align__(16) double sL[FEG_WARPS][G * O * OP];      // rows of L'
+    __shared__ __align__(16) double sW[FEG_WARPS][G * O * OP];      // rows of w .* L' (second derivative)
+    __shared__ __align__(16) double sV[FEG_WARPS][2][G * OP];       // w and n of the elements
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool lane_used = lane < G * O;
+    const int g = lane_used ? lane / O : 0, m = lane_used ? lane - g * O : 0;
+    double *dif = sD[warp] + g * (O * OP), *raw = sL[warp] + g * (O * OP), *rows = sW[warp] + g * (O * OP);
+    double *wv = sV[warp][0] + g * OP, *nv = sV[warp][1] + g * OP;
+    const i64 ngroups = (nel + G - 1) / G;
+    // a dependent launch (the apply pipeline of cb_fedvr_assemble_apply) may take the SMs this grid leaves
+    asm volatile("griddepcontrol.launch_dependents;");
+    for (i64 grp = (i64)blockIdx.x * FEG_WARPS + warp; grp < ngroups; grp += (i64)gridDim.x * FEG_WARPS) {
+        const i64 e0 = grp * G + g;
+        const bool live = lane_used && e0 < nel;
+        const i64 e = e0 < nel ? e0 : nel - 1;
+        const double *xe = x + e * (O - 1);
+        const double xm = xe[m], wm = wcat[e * O + m], nm = nrm[e * (O - 1) + m];
+        double r[O], one_at_m[O];
+        // r[k] = 1 / (x_m - x_k); the k == m slot holds 0 and its factor below becomes fma(d, 0, 1) = 1 exactly
+#pragma unroll
+        for (int k = 0; k < O; ++k) {
+            const double dk = xm - xe[k];
+            if (lane_used) dif[m * OP + k] = dk;
+            // own slot: +0.0 becomes 1.0 through the exponent bits (a select on the denominator is folded away by the
+            // compiler, and 1 / 0 sends the whole warp through the slow path of the division)
+            const double q = 1.0 / __hiloint2double(__double2hiint(dk) | (k == m ? 0x3ff00000 : 0), __double2loint(dk));
+            r[k] = k == m ? 0.0 : q;
+            one_at_m[k] = k == m ? 1.0 : 0.0;
+        }
+        if (lane_used) { wv[m] = wm; nv[m] = nm; }
+        // (delta_{m,O} - delta_{m,1}) / (2 w_m): the zero numerators would take the slow path of the division
+        const double hw = 1.0 / (2 * wm);
+        const double diag = m == O - 1 ? hw : (m == 0 ? -hw : 0.0);
+        __syncwarp();
+        // L'[m, mp]  (src/fedvr_derivatives.jl:15-31)
+#pragma unroll
+        for (int mp = 0; mp < O; ++mp) {
+            double dmp[OP];
+#pragma unroll
+            for (int k2 = 0; k2 < OP / 2; ++k2) {
+                const double2 v = reinterpret_cast<const double2 *>(dif + mp * OP)[k2];
+                dmp[2 * k2] = v.x; dmp[2 * k2 + 1] = v.y;
+            }
+            double f = 1.0;
+#pragma unroll
+            for (int k = 0; k < O; ++k) {
+                if (k == mp) continue;
+                f = __dmul_rn(f, __fma_rn(dmp[k], r[k], one_at_m[k]));
+            }
+            const double v = mp == m ? diag : __dmul_rn(f, r[mp]);
+            if (lane_used) {
+                raw[m * OP + mp] = v;
+                if (nder != 1) rows[m * OP + mp] = __dmul_rn(wv[mp], v);
+            }
+        }
+        if ((O & 1) && lane_used) { raw[m * OP + O] = 0.0; rows[m * OP + O] = 0.0; }
+        __syncwarp();
+        if (nder == 1) {
+            // D[m, mp] = n_m n_mp w_m L'[mp, m]
+#pragma unroll
+            for (int mp = 0; mp < O; ++mp) {
+                const double s = __dmul_rn(wm, raw[mp * OP + m]);
+                if (live) blocks[e * (i64)(O * O) + mp * O + m] = __dmul_rn(__dmul_rn(nm, nv[mp]), s);
+            }
+        } else {
+            // D[m, mp] = n_m n_mp sum_q (-L'[m, q]) (w_q L'[mp, q])   (:33-57)
+            double nl[OP];
+#pragma unroll
+            for (int q2 = 0; q2 < OP / 2; ++q2) {
+                const double2 v = reinterpret_cast<const double2 *>(raw + m * OP)[q2];
+                nl[2 * q2] = -v.x; nl[2 * q2 + 1] = -v.y;
+            }
+#pragma unroll
+            for (int mp = 0; mp < O; ++mp) {
+                const double2 *row = reinterpret_cast<const double2 *>(rows + mp * OP);
+                double s = 0.0;
+#pragma unroll
+                for (int q2 = 0; q2 < OP / 2; ++q2) {
+                    const double2 v = row[q2];
+                    s = __fma_rn(nl[2 * q2], v.x, s);
+                    if (2 * q2 + 1 < O) s = __fma_rn(nl[2 * q2 + 1], v.y, s);
+                }
+                if (live) blocks[e * (i64)(O * O) + mp * O + m] = __dmul_rn(__dmul_rn(nm, nv[mp]), s);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K5: finite-difference stencils, one thread per node.  Round-to-nearest
 // intrinsics keep the reference's operation order (no contraction), so the
@@ -988,6 +1101,23 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
         return CB_OK;
     };
     int lrc = CB_OK;
+    // uniform orders up to 16: several elements per warp, one lane per row (CB_FEDVR_ASM_WARP=1 keeps the
+    // one-warp-per-element kernel for comparisons; the two are bit-identical)
+    static const bool per_warp = getenv("CB_FEDVR_ASM_WARP") != nullptr;
+    if (uniform_order >= 2 && uniform_order <= 16 && !per_warp) {
+        auto launch_rows = [&](auto kern, int per_task) {
+            const int g = cb_grid_for((nel + per_task - 1) / per_task, FEG_WARPS, 64);
+            kern<<<g, FEG_WARPS * 32, 0, (cudaStream_t)stream>>>(x, wcat, nrm, nel, nder, blocks);
+        };
+        switch (uniform_order) {
+#define CB_FEG(OO) case OO: launch_rows(fedvr_assemble_rows_kernel<OO>, 32 / OO); break;
+            CB_FEG(2) CB_FEG(3) CB_FEG(4) CB_FEG(5) CB_FEG(6) CB_FEG(7) CB_FEG(8) CB_FEG(9) CB_FEG(10)
+            CB_FEG(11) CB_FEG(12) CB_FEG(13) CB_FEG(14) CB_FEG(15) CB_FEG(16)
+#undef CB_FEG
+        }
+        CB_LAUNCH_CHECK();
+        return CB_OK;
+    }
     switch (uniform_order) {
 #define CB_FEA(OO) case OO: lrc = launch(fedvr_assemble_kernel<OO>); break;
         CB_FEA(2) CB_FEA(3) CB_FEA(4) CB_FEA(5) CB_FEA(6) CB_FEA(7) CB_FEA(8) CB_FEA(9) CB_FEA(10)

@@ -503,3 +503,30 @@ def test_fedvr_derivative_uses_the_right_hand_restriction(cb):
     assert got.shape == ref.shape and np.array_equal(got, ref)
     with pytest.raises(ValueError):
         cb.FEDVR(cbo.julia_range(0.0, 3.0, 8), 5).T @ D @ B
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", list(range(2, 17)))
+def test_fedvr_rows_kernel_bit_identical_to_generic(cb, order):
+    """Uniform orders <= 16 take the several-elements-per-warp kernel (fedvr_assemble_rows_kernel); the generic
+    one-warp-per-element kernel (per-element order arrays) must give the same bits, for element counts that leave
+    partially filled warps, and both must meet the oracle."""
+    import torch
+    from compactbases_jl_b200 import _lib
+    from compactbases_jl_b200.operators import _ptr, _stream
+    rng = np.random.default_rng(order)
+    for nel in (1, 2, 3, 5, 16, 17, 333):
+        t = np.concatenate([[0.0], np.cumsum(rng.uniform(0.05, 2.0, nel))]) + 900.0
+        B = cb.FEDVR(t, order)
+        assert B.uniform_order == order
+        for nder in (1, 2):
+            out = []
+            for uni in (order, 0):
+                blocks = torch.full((nel * order * order,), float("nan"), dtype=torch.float64, device="cuda")
+                _lib.call("cb_fedvr_assemble", _ptr(B.d_x), _ptr(B.d_wcat), _ptr(B.d_n), _ptr(B.d_estart), _ptr(B.d_order),
+                          _ptr(B.d_boff), _ptr(B.d_woff), nel, uni, order, nder, _ptr(blocks), _stream())
+                out.append(blocks.cpu().numpy())
+            assert np.array_equal(out[0], out[1]), (order, nel, nder)
+        if nel in (5, 17):
+            O = cbo.FEDVROracle(t, order)
+            assert relerr(out[0], O.blocks(2)) <= RTOL
