@@ -118,6 +118,11 @@ __global__ void density_cholesky_kernel(const double *__restrict__ gband, i64 n,
                 if (j + p >= n) bw[j * k + p] = 0.0;
 }
 
+__device__ __forceinline__ void ds_cp16(double *smem_dst, const double *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 __device__ __forceinline__ void ds_cp8(double *smem_dst, const double *gsrc) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -135,6 +140,9 @@ __device__ __forceinline__ void ds_cp8(double *smem_dst, const double *gsrc) {
 // (function) dimension of f, g and rho; table and weight entries are
 // warp-uniform loads.
 // ---------------------------------------------------------------------------
+#ifndef DR_NODES
+#define DR_NODES 3
+#endif
 constexpr int DR_WARPS = 4;
 constexpr int DR_CH = 256;
 constexpr int DR_TILE = 32 * 33;                   // doubles per warp tile (odd pitch)
@@ -160,13 +168,13 @@ __host__ __device__ inline i64 ds_chunk_end(i64 c, i64 nchunk, i64 n);
 template <int K, int MODE, int QT, bool FUSE = false>
 __global__ void __launch_bounds__(DR_WARPS * 32)
 density_rhs_kernel(DensArgs A) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     constexpr int NT = MODE == 1 ? 4 : 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = QT > 0 ? QT : A.q;
-    const int TS = q * K + q;                       // one interval's table + node weights
+    const int TS = (q * K + q + 1) & ~1;            // one interval's table + node weights (even: rows are read as double2)
     constexpr int SORD = (FUSE ? 2 : 1) * DR_CH + K + 2;         // intervals of a chunk (the solver's last chunk takes the remainder)
-    double *sf = sm + (size_t)warp * (NT * DR_TILE + 2 * TS + (SORD + 1) / 2), *sg = sf + DR_TILE, *so = sg + DR_TILE;
+    double *sf = sm + (size_t)warp * (NT * DR_TILE + 2 * TS + (SORD + 3) / 4 * 2), *sg = sf + DR_TILE, *so = sg + DR_TILE;
     double *sr = MODE == 1 ? so + DR_TILE : so;
     double *stab = sf + NT * DR_TILE;               // [2][TS]: the interval being used and the next one (cp.async)
     int *sord = reinterpret_cast<int *>(stab + 2 * TS);   // [DR_CH + K + 2] ordinals of the chunk's intervals
@@ -234,7 +242,13 @@ density_rhs_kernel(DensArgs A) {
             if (c_ >= 0) {
                 const double *src = A.table + (i64)c_ * q * K;
                 double *dst = stab + buf_ * TS;
-                for (int e = lane; e < q * K; e += 32) ds_cp8(dst + e, src + e);
+                if (QT > 0 && ((QT * K) & 1) == 0) {
+#pragma unroll
+                    for (int e = 0; e < (QT * K / 2 + 31) / 32; ++e)
+                        if (32 * e + lane < QT * K / 2) ds_cp16(dst + 2 * (32 * e + lane), src + 2 * (32 * e + lane));
+                } else {
+                    for (int e = lane; e < q * K; e += 32) ds_cp8(dst + e, src + e);
+                }
                 if (A.wv) for (int e = lane; e < q; e += 32) ds_cp8(dst + q * K + e, A.wv + (i64)c_ * q + e);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -243,14 +257,25 @@ density_rhs_kernel(DensArgs A) {
         __syncwarp();
         int c = ordof(s0), c_nxt = ordof(s0 + 1), buf = 0;
         issue_tab(c, 0);
+        // (Unrolling this loop K times so that the window rotates through the registers instead of being shifted — 56
+        // moves per interval — was measured: 23.5 ms instead of 19.7 ms at C5; the 8-fold body thrashes the instruction
+        // cache with two out-of-phase warps per scheduler.)
         for (i64 s = s0; s <= s1; ++s) {
             const int c_nn = ordof(s + 2);
             double cfr[K];                                          // FUSE: factor row of the function completed by this interval
             if (FUSE) {
                 const i64 fe_ = s + ml - K + 1;
                 const i64 jr = fe_ >= fa && fe_ < fb ? fe_ - (A.col0 + 1) : 0;
+                if ((K & 1) == 0) {
 #pragma unroll
-                for (int p = 0; p < K; ++p) cfr[p] = __ldg(A.fwt + jr * K + p);
+                    for (int p = 0; p < K; p += 2) {
+                        const double2 c2 = __ldg(reinterpret_cast<const double2 *>(A.fwt + jr * K + p));
+                        cfr[p] = c2.x; cfr[p + 1] = c2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < K; ++p) cfr[p] = __ldg(A.fwt + jr * K + p);
+                }
             }
             issue_tab(c_nxt, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -268,16 +293,43 @@ density_rhs_kernel(DensArgs A) {
             ++tpos;
             if (c >= 0) {
                 const double *tab = stab + buf * TS, *wq = tab + q * K;
-                // two nodes per iteration: independent FMA chains keep the FP64 pipe busy
+                // DR_NODES nodes per iteration: independent FMA chains keep the FP64 pipe busy (table rows as double2)
                 int l = 0;
+                auto ldrow = [&](double (&t_)[K], int l_) {
+                    if ((K & 1) == 0) {
+#pragma unroll
+                        for (int a = 0; a < K; a += 2) {
+                            const double2 v2 = *reinterpret_cast<const double2 *>(tab + l_ * K + a);
+                            t_[a] = v2.x; t_[a + 1] = v2.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < K; ++a) t_[a] = tab[l_ * K + a];
+                    }
+                };
+#if DR_NODES == 3
+#pragma unroll
+                for (; l + 2 < q; l += 3) {
+                    double u0 = 0.0, v0 = 0.0, z0 = 0.0, u1 = 0.0, v1 = 0.0, z1 = 0.0, u2 = 0.0, v2 = 0.0, z2 = 0.0, ta[K], tb[K], tc[K];
+                    ldrow(ta, l); ldrow(tb, l + 1); ldrow(tc, l + 2);
+#pragma unroll
+                    for (int a = 0; a < K; ++a) {
+                        u0 = fma(ta[a], fw[a], u0); v0 = fma(ta[a], gw[a], v0);
+                        u1 = fma(tb[a], fw[a], u1); v1 = fma(tb[a], gw[a], v1);
+                        u2 = fma(tc[a], fw[a], u2); v2 = fma(tc[a], gw[a], v2);
+                        if (MODE == 1) { z0 = fma(ta[a], rw[a], z0); z1 = fma(tb[a], rw[a], z1); z2 = fma(tc[a], rw[a], z2); }
+                    }
+                    double t0 = u0 * v0, t1 = u1 * v1, t2 = u2 * v2;
+                    if (A.wv) { t0 *= wq[l]; t1 *= wq[l + 1]; t2 *= wq[l + 2]; }
+                    if (MODE == 1) { t0 -= z0; t1 -= z1; t2 -= z2; }
+#pragma unroll
+                    for (int a = 0; a < K; ++a) acc[a] = fma(tc[a], t2, fma(tb[a], t1, fma(ta[a], t0, acc[a])));
+                }
+#endif
 #pragma unroll
                 for (; l + 1 < q; l += 2) {
                     double u0 = 0.0, v0 = 0.0, z0 = 0.0, u1 = 0.0, v1 = 0.0, z1 = 0.0, ta[K], tb[K];
-#pragma unroll
-                    for (int a = 0; a < K; ++a) {
-                        ta[a] = tab[l * K + a];
-                        tb[a] = tab[(l + 1) * K + a];
-                    }
+                    ldrow(ta, l); ldrow(tb, l + 1);
 #pragma unroll
                     for (int a = 0; a < K; ++a) {
                         u0 = fma(ta[a], fw[a], u0); v0 = fma(ta[a], gw[a], v0);
@@ -984,7 +1036,7 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
     i64 blocks = (items + DR_WARPS - 1) / DR_WARPS;
     int grid = (int)(blocks < (i64)CB_NUM_SMS * 64 ? blocks : (i64)CB_NUM_SMS * 64);
     const int sord = (fuse ? 2 : 1) * DR_CH + K + 2;
-    size_t smem = sizeof(double) * DR_WARPS * ((MODE == 1 ? 4 : 3) * DR_TILE + 2 * (A.q * K + A.q) + (sord + 1) / 2);
+    size_t smem = sizeof(double) * DR_WARPS * ((MODE == 1 ? 4 : 3) * DR_TILE + 2 * ((A.q * K + A.q + 1) & ~1) + (sord + 3) / 4 * 2);
     auto launch = [&](auto kern) -> int {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, DR_WARPS * 32, smem, st>>>(A);
