@@ -143,6 +143,9 @@ __device__ __forceinline__ void ds_cp8(double *smem_dst, const double *gsrc) {
 #ifndef DR_NODES
 #define DR_NODES 3
 #endif
+#ifndef DS_FIX_UNROLL
+#define DS_FIX_UNROLL 8
+#endif
 constexpr int DR_WARPS = 4;
 constexpr int DR_CH = 256;
 constexpr int DR_TILE = 32 * 33;                   // doubles per warp tile (odd pitch)
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(32)
 density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
                          const double *__restrict__ St, double *__restrict__ E) {
     constexpr int NB = 2, S = K - 1, CW = 2 * K - 1;
-    __shared__ DsRing<CW, NB> R;
+    __shared__ __align__(16) DsRing<CW, NB> R;
     const int lane = threadIdx.x;
     const i64 p0 = (i64)blockIdx.x * 32, c = blockIdx.y;
     const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
@@ -864,7 +867,22 @@ density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, doub
 #pragma unroll
         for (int r = 31; r >= 0; --r) {
             if (r < rows) {
-                const double *cf = &R.sc[bb][r * CW];
+                // the row's 2K-1 coefficients as double2 (r is a compile-time constant: so is the parity of the row start)
+                double cf[CW];
+                {
+                    const double *cs = &R.sc[bb][r * CW];
+                    const int odd = (r * CW) & 1;
+                    if (odd) cf[0] = cs[0];
+#pragma unroll
+                    for (int i = odd; i < CW; i += 2) {
+                        if (i + 1 < CW) {
+                            const double2 t2 = *reinterpret_cast<const double2 *>(cs + i);
+                            cf[i] = t2.x; cf[i + 1] = t2.y;
+                        } else {
+                            cf[i] = cs[i];
+                        }
+                    }
+                }
                 double y = xr[r], y2 = 0.0;                           // y_j = yloc_j + SF[j] . s_c
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
@@ -901,9 +919,10 @@ density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, doub
 // components), the spike row of a thread's row stays in registers, X is read and written along the rows.  (One thread
 // per row with the states as warp-uniform global loads issued nine memory instructions per element: 2.5 ms at C5.)
 constexpr int DS_FIXP = 32;
+constexpr int DS_FIXU = DS_FIX_UNROLL;       // loads in flight per thread (4: 41 KB per SM, short of the latency-bandwidth product)
 
-template <int K>
-__global__ void __launch_bounds__(256)
+template <int K, bool ADD>
+__global__ void __launch_bounds__(256, 3)
 density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
                        const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
     constexpr int S = K > 1 ? K - 1 : 1, SP = (S + 1) / 2 * 2;
@@ -926,14 +945,29 @@ density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double 
         double sr[SP];
 #pragma unroll
         for (int i = 0; i < SP; ++i) sr[i] = i < S ? sb[j * S + i] : 0.0;
-#pragma unroll 4
-        for (int pp = 0; pp < np; ++pp) {
-            double v = X[j + ldx * (pa + pp)];
-            const double2 *s2 = reinterpret_cast<const double2 *>(sst + pp * SP);
+        // DS_FIXU columns at a time: all their loads first (X is read and written through the same pointer, so the
+        // compiler keeps every load behind the previous column's store and one load per thread was in flight:
+        // long-scoreboard stalls of 55 warps per issue, 0.5 of the HBM rate)
+        for (int pb = 0; pb < np; pb += DS_FIXU) {
+            double v[DS_FIXU], ad[DS_FIXU];
 #pragma unroll
-            for (int h = 0; h < SP / 2; ++h) { const double2 t = s2[h]; v = fma(sr[2 * h], t.x, v); v = fma(sr[2 * h + 1], t.y, v); }
-            if (addto) v += addto[j + lda * (pa + pp)];
-            X[j + ldx * (pa + pp)] = v;
+            for (int u = 0; u < DS_FIXU; ++u) {
+                const int pp = pb + u;
+                v[u] = pp < np ? X[j + ldx * (pa + pp)] : 0.0;
+                ad[u] = (ADD && pp < np) ? addto[j + lda * (pa + pp)] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < DS_FIXU; ++u) {
+                const double2 *s2 = reinterpret_cast<const double2 *>(sst + (pb + u) * SP);
+                double w = v[u];
+#pragma unroll
+                for (int h = 0; h < SP / 2; ++h) { const double2 t = s2[h]; w = fma(sr[2 * h], t.x, w); w = fma(sr[2 * h + 1], t.y, w); }
+                if (ADD) w += ad[u];
+                v[u] = w;
+            }
+#pragma unroll
+            for (int u = 0; u < DS_FIXU; ++u)
+                if (pb + u < np) X[j + ldx * (pa + pb + u)] = v[u];
         }
     }
 }
@@ -1085,7 +1119,9 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #endif
     const i64 nfix = ((n + 255) / 256) * ((P + DS_FIXP - 1) / DS_FIXP);
-    density_bwd_fix_kernel<K><<<(unsigned)(nfix < (i64)CB_NUM_SMS * 32 ? nfix : (i64)CB_NUM_SMS * 32), 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
+    const unsigned gfix = (unsigned)(nfix < (i64)CB_NUM_SMS * 32 ? nfix : (i64)CB_NUM_SMS * 32);
+    if (addto) density_bwd_fix_kernel<K, true><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
+    else density_bwd_fix_kernel<K, false><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
     cudaError_t e = cudaGetLastError();
     if (!ws_fwd) cudaFreeAsync(ws, st);
     if (e != cudaSuccess) { cb_set_error("cb_density_apply: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
