@@ -373,10 +373,20 @@ lp_final_kernel(LuPart F, double *__restrict__ X, i64 ldx, i64 nvec, const doubl
     for (i64 row = a + threadIdx.x; row < b; row += blockDim.x) {
         double sb[LP_MAXS];
         for (int i = 0; i < kv; ++i) sb[i] = __ldg(F.SB + row * kv + i);
-        for (i64 v = va; v < vb; ++v) {
-            double x = X[v * ldx + row];
-            for (int i = 0; i < kv; ++i) x = fma(sb[i], __ldg(Sb + ((c + 1) * kv + i) * nvec + v), x);
-            X[v * ldx + row] = x;
+        // four vectors at a time, their loads first: X is read and written through the same pointer, so the compiler
+        // keeps every load behind the previous vector's store
+        for (i64 v = va; v < vb; v += 4) {
+            double x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = v + u < vb ? X[(v + u) * ldx + row] : 0.0;
+            for (int i = 0; i < kv; ++i) {
+                const double *sp = Sb + ((c + 1) * kv + i) * nvec + v;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = fma(sb[i], v + u < vb ? __ldg(sp + u) : 0.0, x[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (v + u < vb) X[(v + u) * ldx + row] = x[u];
         }
     }
 }
