@@ -263,21 +263,24 @@ density_rhs_kernel(DensArgs A) {
         // (Unrolling this loop K times so that the window rotates through the registers instead of being shifted — 56
         // moves per interval — was measured: 23.5 ms instead of 19.7 ms at C5; the 8-fold body thrashes the instruction
         // cache with two out-of-phase warps per scheduler.)
-        for (i64 s = s0; s <= s1; ++s) {
-            const int c_nn = ordof(s + 2);
+        // 32-bit interval counter si = s - s0: function fe = fa + si - (K-1) is completed by interval si >= K-1 (the index
+        // arithmetic of the loop was a sixth of its instructions with 64-bit counters)
+        const int nint = (int)(s1 - s0) + 1;
+        const double *fwrow = FUSE ? A.fwt + (fa - (A.col0 + 1)) * K : nullptr;    // factor row of function fa
+        for (int si = 0; si < nint; ++si) {
+            const int c_nn = sord[si + 2];
             double cfr[K];                                          // FUSE: factor row of the function completed by this interval
             if (FUSE) {
-                const i64 fe_ = s + ml - K + 1;
-                const i64 jr = fe_ >= fa && fe_ < fb ? fe_ - (A.col0 + 1) : 0;
+                const double *fr = fwrow + (si >= K - 1 ? si - (K - 1) : 0) * K;
                 if ((K & 1) == 0) {
 #pragma unroll
                     for (int p = 0; p < K; p += 2) {
-                        const double2 c2 = __ldg(reinterpret_cast<const double2 *>(A.fwt + jr * K + p));
+                        const double2 c2 = __ldg(reinterpret_cast<const double2 *>(fr + p));
                         cfr[p] = c2.x; cfr[p + 1] = c2.y;
                     }
                 } else {
 #pragma unroll
-                    for (int p = 0; p < K; ++p) cfr[p] = __ldg(A.fwt + jr * K + p);
+                    for (int p = 0; p < K; ++p) cfr[p] = __ldg(fr + p);
                 }
             }
             issue_tab(c_nxt, buf ^ 1);
@@ -289,7 +292,7 @@ density_rhs_kernel(DensArgs A) {
             // slot tpos is read now; when the read position enters a half, the other half (fully consumed) is refilled
             // (the copies join the cp.async group committed with the next table and have landed long before slot
             // tpos + 16 is read)
-            if ((tpos & 15) == 0 && s > s0) { issue_half(next_half); ++next_half; }
+            if ((tpos & 15) == 0 && si > 0) { issue_half(next_half); ++next_half; }
             fw[K - 1] = sf[lane * 33 + tpos]; gw[K - 1] = sg[lane * 33 + tpos];
             rw[K - 1] = MODE == 1 ? sr[lane * 33 + tpos] : 0.0;
             acc[K - 1] = 0.0;
@@ -363,8 +366,7 @@ density_rhs_kernel(DensArgs A) {
             }
             __syncwarp();                                           // table buffer free for the copy after next
             c = c_nxt; c_nxt = c_nn; buf ^= 1;
-            const i64 fe = s + ml - K + 1;                          // slot 0 has seen its last interval
-            if (fe >= fa && fe < fb) {
+            if (si >= K - 1) {                                      // slot 0 has seen its last interval: function fa + si - (K-1)
                 double rv = acc[0];
                 if (FUSE) {                                         // density_fwd_local_kernel's row step, same order of operations
                     double a0 = rv * cfr[0], a1 = 0.0;
@@ -381,7 +383,7 @@ density_rhs_kernel(DensArgs A) {
                 }
                 so[lane * 33 + opos] = rv;
                 ++opos;
-                if (opos == 32 || fe == fb - 1) {
+                if (opos == 32 || si == nint - 1) {
                     __syncwarp();
                     for (int pp = 0; pp < 32; ++pp) {
                         const i64 p = p0 + pp;
