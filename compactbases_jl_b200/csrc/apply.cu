@@ -1415,6 +1415,28 @@ __global__ void fedvr_to_dense_kernel(const double *__restrict__ blocks, const i
     }
 }
 
+// Band export of the (restricted) operator: BandedMatrices storage band[(u + i - j) + (l + u + 1) j] with
+// l = u = w >= max order - 1 (an element couples its own functions only, so the operator is banded with half
+// bandwidth o - 1).  band must be zero-initialised; the two corners that meet on a bridge function are added atomically
+// (two addends: the sum does not depend on their order).
+__global__ void fedvr_to_band_kernel(const double *__restrict__ blocks, const i64 *__restrict__ estart,
+                                     const int32_t *__restrict__ order, const i64 *__restrict__ boff,
+                                     i64 nel, i64 first0, i64 nrows, int w, double *__restrict__ band) {
+    for (i64 e = blockIdx.x; e < nel; e += gridDim.x) {
+        const int o = order[e];
+        const double *b = blocks + boff[e];
+        for (int t = threadIdx.x; t < o * o; t += blockDim.x) {
+            const int mm = t % o, mp = t / o;
+            const i64 gi = estart[e] + mm - first0, gj = estart[e] + mp - first0;
+            if (gi < 0 || gi >= nrows || gj < 0 || gj >= nrows) continue;
+            double *dst = band + (w + gi - gj) + (i64)(2 * w + 1) * gj;
+            const bool shared_corner = (mm == mp) && ((mm == 0 && e > 0) || (mm == o - 1 && e < nel - 1));
+            if (shared_corner) atomicAdd(dst, b[t]);
+            else *dst = b[t];
+        }
+    }
+}
+
 // Export into BlockBandedMatrices' BlockSkylineMatrix storage (Matrix(undef, B) + set_elements!,
 // src/fedvr_operators.jl:17-30,87-134,148-154).  The skyline keeps, per block column J, the block rows kfirst[J]..klast[J]
 // stacked into one dense column-major panel of cstride[J] rows that begins at data[cstart[J]]; blk_cum are the
@@ -1758,6 +1780,19 @@ int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *or
     cudaStream_t st = (cudaStream_t)stream;
     CB_CUDA(cudaMemsetAsync(A, 0, sizeof(double) * nrows * nrows, st));
     fedvr_to_dense_kernel<<<(unsigned)(nel < 4096 ? nel : 4096), 128, 0, st>>>(blocks, estart, order, boff, nel, first - 1, nrows, A);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
+int cb_fedvr_to_band(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
+                     i64 nel, i64 first, i64 last, int w, double *band, void *stream) {
+    CB_REQUIRE(blocks && estart && order && boff && band, "cb_fedvr_to_band: NULL argument");
+    CB_REQUIRE(first >= 1 && last >= first, "cb_fedvr_to_band: invalid restriction");
+    CB_REQUIRE(w >= 1 && w < CB_FEDVR_OMAX, "cb_fedvr_to_band: half bandwidth must be >= max order - 1");
+    const i64 nrows = last - first + 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CB_CUDA(cudaMemsetAsync(band, 0, sizeof(double) * (size_t)nrows * (2 * w + 1), st));
+    fedvr_to_band_kernel<<<(unsigned)(nel < 8192 ? nel : 8192), 128, 0, st>>>(blocks, estart, order, boff, nel, first - 1, nrows, w, band);
     CB_LAUNCH_CHECK();
     return CB_OK;
 }

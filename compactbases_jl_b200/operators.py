@@ -224,6 +224,8 @@ def as_banded(A) -> BandedMatrix:
     if isinstance(A, Diagonal):
         n = A.diag.shape[0]
         return BandedMatrix(A.diag.reshape(n, 1).contiguous(), n, n, 0, 0)
+    if isinstance(A, FEDVRMatrix):
+        return A.banded()
     raise NotImplementedError(f"no band storage for {type(A).__name__}")
 
 
@@ -256,8 +258,6 @@ class ShiftAndInvert:
             metric = B.S if hasattr(B, "S") else B.T @ B
         elif B is not None and not isinstance(B, (BandedMatrix, Tridiagonal, Diagonal)):
             metric = None                                            # FE-DVR, finite differences: I
-        if isinstance(A, FEDVRMatrix):
-            raise NotImplementedError("ShiftAndInvert of a BlockSkylineMatrix (FE-DVR) is outside the accelerated path")
         if isinstance(A, ImplicitDerivative):
             # factorize(d - sigma*I) = ImplicitFactorization(factorize(c*Delta - sigma*M), M), ldiv!: y = M x, then the
             # tridiagonal solve (src/finite_differences.jl:398-444)
@@ -624,6 +624,31 @@ class FEDVRMatrix:
         _lib.call("cb_fedvr_to_dense", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
                   self.first, self.last, _ptr(A), _stream())
         return A.cpu().numpy().T.copy()
+
+    def scaled(self, a: float) -> "FEDVRMatrix":
+        return FEDVRMatrix(self.basis, self.blocks * float(a), self.first, self.last)
+
+    def __mul__(self, a):
+        return self.scaled(a)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, a):
+        return self.scaled(1.0 / float(a))
+
+    def __neg__(self):
+        return self.scaled(-1.0)
+
+    def banded(self) -> "BandedMatrix":
+        """The operator as a ``BandedMatrix`` with l = u = max order - 1 (``cb_fedvr_to_band``): an element couples only
+        its own functions.  This is what ``factorize(A - sigma*I)`` of ``ShiftAndInvert`` works on for FE-DVR
+        (src/linear_operators.jl:185-236; the reference factorises the BlockSkylineMatrix itself)."""
+        b = self.basis
+        w = max(int(b.order.max()) - 1, 1)
+        A = BandedMatrix.undef(self.n, self.n, w, w, self.blocks.device)
+        _lib.call("cb_fedvr_to_band", _ptr(self.blocks), _ptr(b.d_estart), _ptr(b.d_order), _ptr(b.d_boff), b.nel,
+                  self.first, self.last, w, _ptr(A.data), _stream())
+        return A
 
     def skyline(self):
         """The operator as the reference's own destination: ``BlockSkylineMatrix`` of ``Matrix(undef, B)``

@@ -187,6 +187,13 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
 int cb_fedvr_to_dense(const double *blocks, const cb_i64 *estart, const int32_t *order,
                       const cb_i64 *boff, cb_i64 nel, cb_i64 first, cb_i64 last,
                       double *A, void *stream);
+/* The same operator as a BandedMatrix with l = u = w (>= max order - 1), data (2w+1) x (last-first+1)
+ * column-major: the form factorize(A - sigma*I) of ShiftAndInvert takes for FE-DVR operators
+ * (src/linear_operators.jl:185-236, test/linear_operators.jl:72-88 "FE-DVR"); feeds cb_bandchol_* / cb_bandldl_* /
+ * cb_bandlu_*. */
+int cb_fedvr_to_band(const double *blocks, const cb_i64 *estart, const int32_t *order,
+                     const cb_i64 *boff, cb_i64 nel, cb_i64 first, cb_i64 last, int w,
+                     double *band, void *stream);
 /* The same operator in the reference's own destination types (the body of derop!(A, B, n) =
  * set_elements!(difffun(B, n), A, B), src/fedvr_derivatives.jl:62-63, src/fedvr_operators.jl:40-154):
  *

@@ -236,6 +236,37 @@ def test_shift_and_invert_bspline_particle_in_a_box(cb):
         cb.ShiftAndInvert(T, Br, 1.0, method="cholesky")
 
 
+def test_shift_and_invert_fedvr_particle_in_a_box(cb):
+    """test/linear_operators.jl:72-88 ("FE-DVR": FEDVR(range(0, stop=L, length=N), 4)[:, 2:end-1], tolerance 8e-11):
+    the FE-DVR operator goes to band storage (cb_fedvr_to_band, l = u = order - 1) and factorize(A - sigma*I) is the
+    banded Cholesky / L D L' / pivoted LU of the library."""
+    Lbox, N = 10.0, 100
+    F = cb.FEDVR(cbo.julia_range(0, Lbox, N), 4)
+    R = F[:, 2:F.N - 1]
+    D = cb.Derivative()
+    T = (R.T @ D.T @ D @ R) / -2
+    n = T.n
+    Tb = T.banded()
+    assert (Tb.l, Tb.u) == (3, 3) and np.array_equal(Tb.dense(), T.dense())
+    rng = np.random.default_rng(45)
+    X = rng.standard_normal((n, 6))
+    for sigma in (0.0, -0.7, 0.3):                                    # 0.3: interior shift, indefinite
+        M = cb.ShiftAndInvert(T, R, sigma)
+        got = (M @ cb.ColMajor.from_numpy(X)).numpy()
+        assert relerr(got, cbo.shift_invert_apply(T.dense(), None, sigma, X)) <= 1e-10
+    theta = _subspace_eigs(cb.ShiftAndInvert(T, R, 0.0), n, 5, 60, 5)
+    exact = (np.arange(1, 6) * np.pi / Lbox) ** 2 / 2
+    assert np.linalg.norm(1.0 / theta - exact) < 8e-11                # the reference's tolerance
+    # mixed orders: the band takes the largest order
+    Fm = cb.FEDVR(cbo.julia_range(-10.0, 10.0, 10), [4, 3, 4, 2, 5, 4, 2, 4, 8])
+    Am = Fm.T @ D.T @ D @ Fm
+    Ab = Am.banded()
+    assert (Ab.l, Ab.u) == (7, 7) and np.array_equal(Ab.dense(), Am.dense())
+    Xm = rng.standard_normal((Am.n, 3))
+    got = (cb.ShiftAndInvert(Am, Fm, 0.5) @ cb.ColMajor.from_numpy(Xm)).numpy()
+    assert relerr(got, cbo.shift_invert_apply(Am.dense(), None, 0.5, Xm)) <= 1e-9
+
+
 def test_shift_and_invert_finite_differences(cb):
     Lbox, N = 10.0, 100
     R = cb.FiniteDifferences(N, Lbox / (N + 1))
