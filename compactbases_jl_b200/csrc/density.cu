@@ -632,6 +632,9 @@ density_spike_kernel(const double *__restrict__ fw, const double *__restrict__ b
 
 // Shared-memory ring of one warp: tiles of 32 rows x 32 pairs (transposed through shared memory so that global
 // traffic runs along the contiguous row dimension) and the CW coefficients of each row.
+#ifndef DS_TILE_LDG
+#define DS_TILE_LDG 1
+#endif
 template <int CW, int NB>
 struct DsRing {
     double sx[NB][32][33];
@@ -644,10 +647,36 @@ __device__ __forceinline__ void ds_issue(DsRing<CW, NB> &R, int b, i64 row0, i64
     const int lane = threadIdx.x;
     const i64 j = row0 + lane;
     if (j < row_end) {
+        // running pointers: the 64-bit index arithmetic and the bound test per copy were a third of the sweeps' instructions
+        const int nv = (int)(P - p0 < 32 ? P - p0 : 32);
+        const double *src = X + j + ldx * p0;
+        double *dst = &R.sx[b][0][lane];
+#if DS_TILE_LDG
+        // plain loads, eight in flight per lane, then the transposing stores: 8-byte cp.async copies queue up in the LSU
+        // (the sweeps moved 2.7 TB/s with them, whatever the occupancy, the tile shape or the instruction count)
+        if (nv == 32) {
+#pragma unroll
+            for (int p8 = 0; p8 < 32; p8 += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (i64)u * ldx);
+                src += 8 * ldx;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[(p8 + u) * 33] = v[u];
+            }
+        } else {
+            for (int pp = 0; pp < nv; ++pp, src += ldx) dst[pp * 33] = __ldg(src);
+        }
+#else
+        if (nv == 32) {
 #pragma unroll 8
-        for (int pp = 0; pp < 32; ++pp)
-            if (p0 + pp < P) ds_cp8(&R.sx[b][pp][lane], X + j + ldx * (p0 + pp));
+            for (int pp = 0; pp < 32; ++pp, src += ldx) ds_cp8(dst + pp * 33, src);
+        } else {
+            for (int pp = 0; pp < nv; ++pp, src += ldx) ds_cp8(dst + pp * 33, src);
+        }
+#endif
     }
+    if (ct == nullptr) return;                      // a second pair set of the same rows shares the coefficient tile
     const i64 c0 = row0 * CW, cend = row_end * CW;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -662,9 +691,15 @@ __device__ __forceinline__ void ds_store(const DsRing<CW, NB> &R, int b, i64 row
     const int lane = threadIdx.x;
     const i64 j = row0 + lane;
     if (j < row_end) {
+        const int nv = (int)(P - p0 < 32 ? P - p0 : 32);
+        double *dstg = X + j + ldx * p0;
+        const double *srcs = &R.sx[b][0][lane];
+        if (nv == 32) {
 #pragma unroll 8
-        for (int pp = 0; pp < 32; ++pp)
-            if (p0 + pp < P) X[j + ldx * (p0 + pp)] = R.sx[b][pp][lane];
+            for (int pp = 0; pp < 32; ++pp, dstg += ldx) *dstg = srcs[pp * 33];
+        } else {
+            for (int pp = 0; pp < nv; ++pp, dstg += ldx) *dstg = srcs[pp * 33];
+        }
     }
 }
 
@@ -695,22 +730,27 @@ density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, doub
         double xr[32];
 #pragma unroll
         for (int r = 0; r < 32; ++r) xr[r] = R.sx[bb][lane][r];
+        auto row_step = [&](const int r) {
+            const double *cf = &R.sc[bb][r * K];
+            double acc = xr[r] * cf[0], acc2 = 0.0;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            if (r < rows) {
-                const double *cf = &R.sc[bb][r * K];
-                double acc = xr[r] * cf[0], acc2 = 0.0;
-#pragma unroll
-                for (int p = K - 1; p >= 2; --p) {
-                    if (p & 1) acc2 = fma(-cf[p], yw[p], acc2); else acc = fma(-cf[p], yw[p], acc);
-                }
-                acc += acc2;
-                if (K > 1) acc = fma(-cf[1], yw[1], acc);
-#pragma unroll
-                for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
-                if (K > 1) yw[1] = acc;
-                xr[r] = acc;
+            for (int p = K - 1; p >= 2; --p) {
+                if (p & 1) acc2 = fma(-cf[p], yw[p], acc2); else acc = fma(-cf[p], yw[p], acc);
             }
+            acc += acc2;
+            if (K > 1) acc = fma(-cf[1], yw[1], acc);
+#pragma unroll
+            for (int p = K - 1; p >= 2; --p) yw[p] = yw[p - 1];
+            if (K > 1) yw[1] = acc;
+            xr[r] = acc;
+        };
+        if (rows == 32) {                           // full tile: no per-row bound test, the window shifts are renamed away
+#pragma unroll
+            for (int r = 0; r < 32; ++r) row_step(r);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (r < rows) row_step(r);
         }
 #pragma unroll
         for (int r = 0; r < 32; ++r) R.sx[bb][lane][r] = xr[r];
@@ -835,85 +875,98 @@ density_state_cp_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const d
     }
 }
 
-// FB: spike correction of the forward sweep fused with the local backward sweep of every chunk.
+// FB: spike correction of the forward sweep fused with the local backward sweep of every chunk, two pairs per lane
+// (64 pairs per warp): the 2K-1 coefficients of a row are the same for every pair (8 LDS.128 per row and warp), so a
+// lane takes two independent pairs per coefficient row — half the coefficient loads per pair, two dependency chains to
+// interleave; tile values stay in shared memory (one LDS / STS per row and pair).
+// Measured at C5 (2.5 ms of the 17.7 ms job, 2.8 TB/s): the time did not move (+-1 %) with 9 or 16 resident warps per
+// SM, half the instructions (running pointers instead of 64-bit index arithmetic per copy, unconditional full tiles
+// whose window shifts are renamed away), plain loads instead of 8-byte cp.async, 512 contiguous bytes per pair and trip
+// instead of 256, one or two pairs per lane, or L2 prefetches of 1-2 KB per pair ahead of the tiles.  What is left is the
+// access pattern itself: 256-byte pieces of columns that lie 400 KB apart.
 template <int K>
-__global__ void __launch_bounds__(32)
-density_bwd_local_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
-                         const double *__restrict__ St, double *__restrict__ E) {
-    constexpr int NB = 2, S = K - 1, CW = 2 * K - 1;
-    __shared__ __align__(16) DsRing<CW, NB> R;
+__global__ void __launch_bounds__(32, 12)
+density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+                          const double *__restrict__ St, double *__restrict__ E) {
+    constexpr int S = K - 1, CW = 2 * K - 1;
+    __shared__ __align__(16) DsRing<CW, 2> R;      // sx[h]: pairs p0 + 32 h .. + 31; sc[0]: the rows' coefficients
     const int lane = threadIdx.x;
-    const i64 p0 = (i64)blockIdx.x * 32, c = blockIdx.y;
+    const i64 p0 = (i64)blockIdx.x * 64, c = blockIdx.y;
     const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
     const i64 ntile = (b - a + 31) / 32;
-    double sin[K], zw[K];
+    double sin[2][K], zw[2][K];
 #pragma unroll
-    for (int p = 0; p < K; ++p) { zw[p] = 0.0; sin[p] = 0.0; }
-    if (p0 + lane < P) {
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int i = 0; i < S; ++i) sin[i] = St[(c * S + i) * P + p0 + lane];
+        for (int p = 0; p < K; ++p) { zw[h][p] = 0.0; sin[h][p] = 0.0; }
+        if (p0 + 32 * h + lane < P) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) sin[h][i] = St[(c * S + i) * P + p0 + 32 * h + lane];
+        }
     }
-    ds_issue(R, 0, a + 32 * (ntile - 1), b, X, ldx, p0, P, cfb);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (i64 t = ntile - 1, it = 0; t >= 0; --t, ++it) {
-        const int bb = (int)(it & 1);
-        if (t > 0) ds_issue(R, bb ^ 1, a + 32 * (t - 1), b, X, ldx, p0, P, cfb);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
+    for (i64 t = ntile - 1; t >= 0; --t) {
         const i64 row0 = a + 32 * t;
         const int rows = b - row0 < 32 ? (int)(b - row0) : 32;
-        double xr[32];
+        ds_issue(R, 0, row0, b, X, ldx, p0, P, cfb);
+        ds_issue(R, 1, row0, b, X, ldx, p0 + 32, P, (const double *)nullptr);
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        auto row_step = [&](const int r) {
+            double cf[CW];
+            {
+                const double *cs = &R.sc[0][r * CW];
+                const int odd = (r * CW) & 1;
+                if (odd) cf[0] = cs[0];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) xr[r] = R.sx[bb][lane][r];
-#pragma unroll
-        for (int r = 31; r >= 0; --r) {
-            if (r < rows) {
-                // the row's 2K-1 coefficients as double2 (r is a compile-time constant: so is the parity of the row start)
-                double cf[CW];
-                {
-                    const double *cs = &R.sc[bb][r * CW];
-                    const int odd = (r * CW) & 1;
-                    if (odd) cf[0] = cs[0];
-#pragma unroll
-                    for (int i = odd; i < CW; i += 2) {
-                        if (i + 1 < CW) {
-                            const double2 t2 = *reinterpret_cast<const double2 *>(cs + i);
-                            cf[i] = t2.x; cf[i + 1] = t2.y;
-                        } else {
-                            cf[i] = cs[i];
-                        }
+                for (int i = odd; i < CW; i += 2) {
+                    if (i + 1 < CW) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(cs + i);
+                        cf[i] = t2.x; cf[i + 1] = t2.y;
+                    } else {
+                        cf[i] = cs[i];
                     }
                 }
-                double y = xr[r], y2 = 0.0;                           // y_j = yloc_j + SF[j] . s_c
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double y = R.sx[h][lane][r], y2 = 0.0;                // y_j = yloc_j + SF[j] . s_c
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
-                    if (i & 1) y2 = fma(cf[K + i], sin[i], y2); else y = fma(cf[K + i], sin[i], y);
+                    if (i & 1) y2 = fma(cf[K + i], sin[h][i], y2); else y = fma(cf[K + i], sin[h][i], y);
                 }
                 y += y2;
                 double acc = y * cf[0], acc2 = 0.0;
 #pragma unroll
                 for (int p = K - 1; p >= 2; --p) {
-                    if (p & 1) acc2 = fma(-cf[p], zw[p], acc2); else acc = fma(-cf[p], zw[p], acc);
+                    if (p & 1) acc2 = fma(-cf[p], zw[h][p], acc2); else acc = fma(-cf[p], zw[h][p], acc);
                 }
                 acc += acc2;
-                if (K > 1) acc = fma(-cf[1], zw[1], acc);
+                if (K > 1) acc = fma(-cf[1], zw[h][1], acc);
 #pragma unroll
-                for (int p = K - 1; p >= 2; --p) zw[p] = zw[p - 1];
-                if (K > 1) zw[1] = acc;
-                xr[r] = acc;
+                for (int p = K - 1; p >= 2; --p) zw[h][p] = zw[h][p - 1];
+                if (K > 1) zw[h][1] = acc;
+                R.sx[h][lane][r] = acc;
             }
+        };
+        if (rows == 32) {
+#pragma unroll
+            for (int r = 31; r >= 0; --r) row_step(r);
+        } else {
+#pragma unroll
+            for (int r = 31; r >= 0; --r)
+                if (r < rows) row_step(r);
         }
-#pragma unroll
-        for (int r = 0; r < 32; ++r) R.sx[bb][lane][r] = xr[r];
         __syncwarp();
-        ds_store(R, bb, row0, b, X, ldx, p0, P);
+        ds_store(R, 0, row0, b, X, ldx, p0, P);
+        ds_store(R, 1, row0, b, X, ldx, p0 + 32, P);
         __syncwarp();
     }
-    if (p0 + lane < P) {
 #pragma unroll
-        for (int p = 1; p < K; ++p) E[(c * S + (p - 1)) * P + p0 + lane] = zw[p];
-    }
+    for (int h = 0; h < 2; ++h)
+        if (p0 + 32 * h + lane < P) {
+#pragma unroll
+            for (int p = 1; p < K; ++p) E[(c * S + (p - 1)) * P + p0 + 32 * h + lane] = zw[h][p];
+        }
 }
 
 // B3: x_j = zloc_j + SB[j] . sb_c (+ addto): no recurrence.  A CTA takes 256 rows of one chunk and a tile of DS_FIXP pairs:
@@ -1112,12 +1165,12 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
     constexpr int PPW = 32 / ((K > 1 ? K - 1 : 1) <= 8 ? 8 : 16);
     const unsigned sblocks = (unsigned)((P + PPW - 1) / PPW);
     density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tf, M, P, E, St, +1);
-    density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
     density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #else
     const unsigned sblocks = (unsigned)((P + DS_STATE_THREADS - 1) / DS_STATE_THREADS);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tf, M, P, E, St, +1);
-    density_bwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #endif
     const i64 nfix = ((n + 255) / 256) * ((P + DS_FIXP - 1) / DS_FIXP);
