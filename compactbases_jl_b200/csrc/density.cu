@@ -161,6 +161,9 @@ struct DensArgs {
     // FUSE: the local forward sweep of the partitioned solve (density_fwd_local_kernel, F1) runs on the rows as they are
     // produced — `out` receives yloc instead of r and E the chunks' final states; chunks are the solver's (ds_chunk_*)
     const double *fwt; double *E; i64 nchunk_ds;
+    // FUSE: yloc goes to the solver's tiled intermediate T[(pair group * ncols + row) * 32 + pair in group] (dst_tiled),
+    // a row of 32 pairs being one coalesced 256-byte store, instead of through a transposing tile into `out`
+    double *out_tiled;
 };
 
 // QT > 0: the node count is the compile-time constant QT (the default q = K + 1): the node loops unroll and the
@@ -381,6 +384,9 @@ density_rhs_kernel(DensArgs A) {
                     if (K > 1) yw[1] = a0;
                     rv = a0;
                 }
+                if (FUSE && A.out_tiled != nullptr) {
+                    if (p0 + lane < A.P) A.out_tiled[((pg * A.ncols) + (fa - (A.col0 + 1)) + (si - (K - 1))) * 32 + lane] = rv;
+                } else {
                 so[lane * 33 + opos] = rv;
                 ++opos;
                 if (opos == 32 || si == nint - 1) {
@@ -391,6 +397,7 @@ density_rhs_kernel(DensArgs A) {
                     }
                     __syncwarp();
                     obase += opos; opos = 0;
+                }
                 }
             }
         }
@@ -676,7 +683,18 @@ __device__ __forceinline__ void ds_issue(DsRing<CW, NB> &R, int b, i64 row0, i64
         }
 #endif
     }
-    if (ct == nullptr) return;                      // a second pair set of the same rows shares the coefficient tile
+    const i64 c0 = row0 * CW, cend = row_end * CW;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+        const i64 e = c0 + lane + 32 * i;
+        if (e < cend) ds_cp8(&R.sc[b][lane + 32 * i], ct + e);
+    }
+}
+
+// the coefficient rows of a tile alone
+template <int CW, int NB>
+__device__ __forceinline__ void ds_issue_coef(DsRing<CW, NB> &R, int b, i64 row0, i64 row_end, const double *__restrict__ ct) {
+    const int lane = threadIdx.x;
     const i64 c0 = row0 * CW, cend = row_end * CW;
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -707,7 +725,7 @@ __device__ __forceinline__ void ds_store(const DsRing<CW, NB> &R, int b, i64 row
 template <int K>
 __global__ void __launch_bounds__(32)
 density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
-                         double *__restrict__ E) {
+                         double *__restrict__ E, double *__restrict__ T) {
     constexpr int NB = 2, S = K - 1;
     __shared__ DsRing<K, NB> R;
     const int lane = threadIdx.x;
@@ -752,10 +770,13 @@ density_fwd_local_kernel(const double *__restrict__ fwt, i64 n, i64 nchunk, doub
             for (int r = 0; r < 32; ++r)
                 if (r < rows) row_step(r);
         }
+        // the swept rows go to the tiled intermediate of the solve: a row of the 32 pairs is one coalesced store
+        {
+            double *trow = T + ((i64)blockIdx.x * n + row0) * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) R.sx[bb][lane][r] = xr[r];
-        __syncwarp();
-        ds_store(R, bb, row0, b, X, ldx, p0, P);
+            for (int r = 0; r < 32; ++r)
+                if (r < rows) trow[r * 32] = xr[r];
+        }
         __syncwarp();
     }
     if (p0 + lane < P) {
@@ -886,7 +907,7 @@ density_state_cp_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const d
 // access pattern itself: 256-byte pieces of columns that lie 400 KB apart.
 template <int K>
 __global__ void __launch_bounds__(32, 12)
-density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
+density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ T, i64 P,
                           const double *__restrict__ St, double *__restrict__ E) {
     constexpr int S = K - 1, CW = 2 * K - 1;
     __shared__ __align__(16) DsRing<CW, 2> R;      // sx[h]: pairs p0 + 32 h .. + 31; sc[0]: the rows' coefficients
@@ -907,8 +928,19 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
     for (i64 t = ntile - 1; t >= 0; --t) {
         const i64 row0 = a + 32 * t;
         const int rows = b - row0 < 32 ? (int)(b - row0) : 32;
-        ds_issue(R, 0, row0, b, X, ldx, p0, P, cfb);
-        ds_issue(R, 1, row0, b, X, ldx, p0 + 32, P, (const double *)nullptr);
+        // a tile of the intermediate is rows x 32 contiguous doubles per pair group: 16-byte copies, no transposition
+        // (element (r, lane) of pair set h sits at sx[h] + r * 32 + lane: conflict-free for the sweep)
+        const int nch = rows * 16;                  // 16-byte pieces of a tile
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double *tg = T + ((2 * (i64)blockIdx.x + h) * n + row0) * 32;
+            double *ts = &R.sx[h][0][0];
+            if (p0 + 32 * h < P) {
+#pragma unroll 4
+                for (int e = lane; e < nch; e += 32) ds_cp16(ts + 2 * e, tg + 2 * e);
+            }
+        }
+        ds_issue_coef(R, 0, row0, b, cfb);
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         auto row_step = [&](const int r) {
@@ -929,7 +961,7 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                double y = R.sx[h][lane][r], y2 = 0.0;                // y_j = yloc_j + SF[j] . s_c
+                double y = (&R.sx[h][0][0])[r * 32 + lane], y2 = 0.0;    // y_j = yloc_j + SF[j] . s_c
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     if (i & 1) y2 = fma(cf[K + i], sin[h][i], y2); else y = fma(cf[K + i], sin[h][i], y);
@@ -945,7 +977,7 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
 #pragma unroll
                 for (int p = K - 1; p >= 2; --p) zw[h][p] = zw[h][p - 1];
                 if (K > 1) zw[h][1] = acc;
-                R.sx[h][lane][r] = acc;
+                (&R.sx[h][0][0])[r * 32 + lane] = acc;
             }
         };
         if (rows == 32) {
@@ -957,8 +989,16 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
                 if (r < rows) row_step(r);
         }
         __syncwarp();
-        ds_store(R, 0, row0, b, X, ldx, p0, P);
-        ds_store(R, 1, row0, b, X, ldx, p0 + 32, P);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double *tg = T + ((2 * (i64)blockIdx.x + h) * n + row0) * 32;
+            const double *ts = &R.sx[h][0][0];
+            if (p0 + 32 * h < P) {
+#pragma unroll 4
+                for (int e = lane; e < nch; e += 32)
+                    *reinterpret_cast<double2 *>(tg + 2 * e) = *reinterpret_cast<const double2 *>(ts + 2 * e);
+            }
+        }
         __syncwarp();
     }
 #pragma unroll
@@ -978,8 +1018,8 @@ constexpr int DS_FIXU = DS_FIX_UNROLL;       // loads in flight per thread (4: 4
 
 template <int K, bool ADD>
 __global__ void __launch_bounds__(256, 3)
-density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double *__restrict__ X, i64 ldx, i64 P,
-                       const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
+density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, const double *__restrict__ T, double *__restrict__ X,
+                       i64 ldx, i64 P, const double *__restrict__ St, const double *__restrict__ addto, i64 lda) {
     constexpr int S = K > 1 ? K - 1 : 1, SP = (S + 1) / 2 * 2;
     __shared__ __align__(16) double sst[DS_FIXP * SP];
     const i64 npg = (P + DS_FIXP - 1) / DS_FIXP;
@@ -1000,15 +1040,22 @@ density_bwd_fix_kernel(const double *__restrict__ sb, i64 n, i64 nchunk, double 
         double sr[SP];
 #pragma unroll
         for (int i = 0; i < SP; ++i) sr[i] = i < S ? sb[j * S + i] : 0.0;
-        // DS_FIXU columns at a time: all their loads first (X is read and written through the same pointer, so the
-        // compiler keeps every load behind the previous column's store and one load per thread was in flight:
-        // long-scoreboard stalls of 55 warps per issue, 0.5 of the HBM rate)
+        // DS_FIXU columns at a time, all their loads first.  The swept values come from the tiled intermediate — a
+        // thread's 32 pairs of row j are 256 contiguous bytes — and leave in the caller's column-major layout.  (When
+        // this kernel still read and wrote X in place the compiler kept every load behind the previous column's store:
+        // one load per thread in flight, long-scoreboard stalls of 55 warps per issue, 0.5 of the HBM rate.)
+        const double *trow = T + (pg * n + j) * 32;
         for (int pb = 0; pb < np; pb += DS_FIXU) {
             double v[DS_FIXU], ad[DS_FIXU];
+            static_assert(DS_FIXU % 2 == 0 && DS_FIXP == 32, "tiled intermediate: 32 pairs per group, double2 loads");
+#pragma unroll
+            for (int u = 0; u < DS_FIXU; u += 2) {
+                const double2 t2 = *reinterpret_cast<const double2 *>(trow + pb + u);
+                v[u] = t2.x; v[u + 1] = t2.y;
+            }
 #pragma unroll
             for (int u = 0; u < DS_FIXU; ++u) {
                 const int pp = pb + u;
-                v[u] = pp < np ? X[j + ldx * (pa + pp)] : 0.0;
                 ad[u] = (ADD && pp < np) ? addto[j + lda * (pa + pp)] : 0.0;
             }
 #pragma unroll
@@ -1114,7 +1161,7 @@ static DensArgs make_args(const cb_density *D, const cb_bspline *, const double 
     A.f = f; A.ldf = ldf; A.Pf = Pf; A.g = g; A.ldg = ldg; A.Pg = Pg;
     A.rho_in = nullptr; A.ldri = 0; A.out = nullptr; A.ldo = 0;
     A.P = Pf > Pg ? Pf : Pg;
-    A.fwt = nullptr; A.E = nullptr; A.nchunk_ds = 0;
+    A.fwt = nullptr; A.E = nullptr; A.nchunk_ds = 0; A.out_tiled = nullptr;
     return A;
 }
 
@@ -1143,7 +1190,7 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
 // fused into the producer of X (density_rhs_kernel<FUSE>): X holds yloc, F1 is skipped; the caller frees ws_fwd.
 template <int K>
 static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const double *addto, i64 lda, cudaStream_t st,
-                        double *ws_fwd = nullptr) {
+                        double *ws_fwd = nullptr, double *T_fwd = nullptr) {
     const i64 n = D->ncols, ptiles = (P + 31) / 32;
     if (D->d_cfb == nullptr || K == 1) {            // short problems: one warp per 32 pairs walks all rows
         density_solve_kernel<K><<<(int)ptiles, 32, 0, st>>>(D->d_fw, D->d_bw, n, X, ldx, P, addto, lda);
@@ -1158,27 +1205,34 @@ static int launch_solve(const cb_density *D, double *X, i64 ldx, i64 P, const do
         CB_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * M * S * P, st));
     }
     double *E = ws, *St = ws + M * S * P;
+    // the tiled intermediate T[(pair group * n + row) * 32 + pair in group] between the sweeps (cb_density_tiled_bytes)
+    double *T = T_fwd;
+    if (!T) {
+        int prc = cb_keep_scratch_pool(); if (prc) return prc;
+        CB_CUDA(cudaMallocAsync(&T, sizeof(double) * (size_t)ptiles * n * 32, st));
+    }
     // grid.y = chunks <= 65535 is checked at plan time
     dim3 grid((unsigned)ptiles, (unsigned)M);
-    if (!ws_fwd) density_fwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_fw, n, M, X, ldx, P, E);
+    if (!ws_fwd) density_fwd_local_kernel<K><<<grid, 32, 0, st>>>(D->d_fw, n, M, X, ldx, P, E, T);
 #if DS_STATE_CP
     constexpr int PPW = 32 / ((K > 1 ? K - 1 : 1) <= 8 ? 8 : 16);
     const unsigned sblocks = (unsigned)((P + PPW - 1) / PPW);
     density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tf, M, P, E, St, +1);
-    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, T, P, St, E);
     density_state_cp_kernel<K><<<sblocks, 32, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #else
     const unsigned sblocks = (unsigned)((P + DS_STATE_THREADS - 1) / DS_STATE_THREADS);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tf, M, P, E, St, +1);
-    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, X, ldx, P, St, E);
+    density_bwd_local2_kernel<K><<<dim3((unsigned)((P + 63) / 64), (unsigned)M), 32, 0, st>>>(D->d_cfb, n, M, T, P, St, E);
     density_state_kernel<K><<<sblocks, DS_STATE_THREADS, 0, st>>>(D->d_tb, M, P, E, St, -1);
 #endif
     const i64 nfix = ((n + 255) / 256) * ((P + DS_FIXP - 1) / DS_FIXP);
     const unsigned gfix = (unsigned)(nfix < (i64)CB_NUM_SMS * 32 ? nfix : (i64)CB_NUM_SMS * 32);
-    if (addto) density_bwd_fix_kernel<K, true><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
-    else density_bwd_fix_kernel<K, false><<<gfix, 256, 0, st>>>(D->d_sb, n, M, X, ldx, P, St, addto, lda);
+    if (addto) density_bwd_fix_kernel<K, true><<<gfix, 256, 0, st>>>(D->d_sb, n, M, T, X, ldx, P, St, addto, lda);
+    else density_bwd_fix_kernel<K, false><<<gfix, 256, 0, st>>>(D->d_sb, n, M, T, X, ldx, P, St, addto, lda);
     cudaError_t e = cudaGetLastError();
     if (!ws_fwd) cudaFreeAsync(ws, st);
+    if (!T_fwd) cudaFreeAsync(T, st);
     if (e != cudaSuccess) { cb_set_error("cb_density_apply: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     return CB_OK;
 }
@@ -1291,16 +1345,18 @@ int cb_density_apply(const cb_density *D, const double *f, i64 ldf, i64 Pf,
     A.out = rho; A.ldo = ldr;
     // partitioned plans: the right-hand side kernel runs the solver's local forward sweep on the rows it produces (one
     // pass over the batch less: 2.5 of 21.8 ms at C5)
-    double *ws = nullptr;
+    double *ws = nullptr, *Tt = nullptr;
     if (D->d_cfb != nullptr && D->nchunk >= 2 && D->k > 1) {
         { int prc = cb_keep_scratch_pool(); if (prc) return prc; }
         CB_CUDA(cudaMallocAsync(&ws, sizeof(double) * 2 * D->nchunk * (D->k - 1) * P, st));
-        A.fwt = D->d_fw; A.E = ws; A.nchunk_ds = D->nchunk;
+        CB_CUDA(cudaMallocAsync(&Tt, sizeof(double) * (size_t)((P + 31) / 32) * D->ncols * 32, st));
+        A.fwt = D->d_fw; A.E = ws; A.nchunk_ds = D->nchunk; A.out_tiled = Tt;
     }
     CB_DISPATCH_KD(D->k, rc = (launch_rhs<K, 0>(A, st)));
-    if (rc == CB_OK) CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, rho, ldr, P, nullptr, 0, st, ws));
+    if (rc == CB_OK) CB_DISPATCH_KD(D->k, rc = launch_solve<K>(D, rho, ldr, P, nullptr, 0, st, ws, Tt));
     if (ws) cudaFreeAsync(ws, st);
-    A.fwt = nullptr; A.E = nullptr; A.nchunk_ds = 0;
+    if (Tt) cudaFreeAsync(Tt, st);
+    A.fwt = nullptr; A.E = nullptr; A.nchunk_ds = 0; A.out_tiled = nullptr;
     if (rc) return rc;
     if (D->refine > 0) {
         double *tmp = nullptr;
