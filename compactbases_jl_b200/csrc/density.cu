@@ -896,25 +896,33 @@ density_state_cp_kernel(const double *__restrict__ T, i64 nchunk, i64 P, const d
     }
 }
 
-// FB: spike correction of the forward sweep fused with the local backward sweep of every chunk, two pairs per lane
-// (64 pairs per warp): the 2K-1 coefficients of a row are the same for every pair (8 LDS.128 per row and warp), so a
-// lane takes two independent pairs per coefficient row — half the coefficient loads per pair, two dependency chains to
-// interleave; tile values stay in shared memory (one LDS / STS per row and pair).
-// Measured at C5 (2.5 ms of the 17.7 ms job, 2.8 TB/s): the time did not move (+-1 %) with 9 or 16 resident warps per
-// SM, half the instructions (running pointers instead of 64-bit index arithmetic per copy, unconditional full tiles
-// whose window shifts are renamed away), plain loads instead of 8-byte cp.async, 512 contiguous bytes per pair and trip
-// instead of 256, one or two pairs per lane, or L2 prefetches of 1-2 KB per pair ahead of the tiles.  What is left is the
-// access pattern itself: 256-byte pieces of columns that lie 400 KB apart.
+// FB: spike correction of the forward sweep fused with the local backward sweep of every chunk, on the tiled
+// intermediate T[(pair group * n + row) * 32 + pair in group].  Two pairs per lane (64 pairs per warp): the 2K-1
+// coefficients of a row are the same for every pair (8 LDS.128 per row and warp), so a lane takes two independent pairs
+// per coefficient row — half the coefficient loads per pair, two dependency chains to interleave.  Rows move in pieces
+// of DB_R = 16 (16-byte cp.async, a piece of a pair group is 4 KB contiguous, no transposition) through two buffers:
+// the next piece is in flight while the current one is swept, the swept piece goes back with plain stores.
+// History at C5 (job 17.7 ms): on the caller's column-major layout (256-byte pieces of columns 400 KB apart, transposing
+// shared-memory tiles) this sweep took 2.5 ms whatever was tried — 9 or 16 resident warps, half the instructions, plain
+// loads instead of 8-byte cp.async, 512-byte pieces, L2 prefetches; the tiled layout brought 2.2 ms (3.6 TB/s), the double
+// buffer nothing measurable on top.
+constexpr int DB_R = 16;
 template <int K>
-__global__ void __launch_bounds__(32, 12)
+struct DsBwdTile {
+    double x[2][2][DB_R * 32];                     // [buffer][pair set][row][lane]
+    double c[2][DB_R * (2 * K - 1)];               // [buffer][row][2K-1]
+};
+
+template <int K>
+__global__ void __launch_bounds__(32, 9)
 density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, double *__restrict__ T, i64 P,
                           const double *__restrict__ St, double *__restrict__ E) {
     constexpr int S = K - 1, CW = 2 * K - 1;
-    __shared__ __align__(16) DsRing<CW, 2> R;      // sx[h]: pairs p0 + 32 h .. + 31; sc[0]: the rows' coefficients
+    __shared__ __align__(16) DsBwdTile<K> R;
     const int lane = threadIdx.x;
     const i64 p0 = (i64)blockIdx.x * 64, c = blockIdx.y;
     const i64 a = ds_chunk_begin(c), b = ds_chunk_end(c, nchunk, n);
-    const i64 ntile = (b - a + 31) / 32;
+    const i64 npc = (b - a + DB_R - 1) / DB_R;     // pieces of the chunk
     double sin[2][K], zw[2][K];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -925,28 +933,36 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
             for (int i = 0; i < S; ++i) sin[h][i] = St[(c * S + i) * P + p0 + 32 * h + lane];
         }
     }
-    for (i64 t = ntile - 1; t >= 0; --t) {
-        const i64 row0 = a + 32 * t;
-        const int rows = b - row0 < 32 ? (int)(b - row0) : 32;
-        // a tile of the intermediate is rows x 32 contiguous doubles per pair group: 16-byte copies, no transposition
-        // (element (r, lane) of pair set h sits at sx[h] + r * 32 + lane: conflict-free for the sweep)
-        const int nch = rows * 16;                  // 16-byte pieces of a tile
+    // requests piece t (rows a + DB_R t ..) into buffer bf
+    auto issue = [&](i64 t, int bf) {
+        const i64 row0 = a + DB_R * t;
+        const int rows = b - row0 < DB_R ? (int)(b - row0) : DB_R;
+        const int nch = rows * 16;                  // 16-byte pieces of a pair set
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double *tg = T + ((2 * (i64)blockIdx.x + h) * n + row0) * 32;
-            double *ts = &R.sx[h][0][0];
             if (p0 + 32 * h < P) {
 #pragma unroll 4
-                for (int e = lane; e < nch; e += 32) ds_cp16(ts + 2 * e, tg + 2 * e);
+                for (int e = lane; e < nch; e += 32) ds_cp16(&R.x[bf][h][2 * e], tg + 2 * e);
             }
         }
-        ds_issue_coef(R, 0, row0, b, cfb);
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        const i64 c0 = row0 * CW;
+        const int ne = rows * CW;
+        for (int e = lane; e < ne; e += 32) ds_cp8(&R.c[bf][e], cfb + c0 + e);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(npc - 1, 0);
+    for (i64 t = npc - 1, it = 0; t >= 0; --t, ++it) {
+        const int bf = (int)(it & 1);
+        if (t > 0) issue(t - 1, bf ^ 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
+        const i64 row0 = a + DB_R * t;
+        const int rows = b - row0 < DB_R ? (int)(b - row0) : DB_R;
         auto row_step = [&](const int r) {
             double cf[CW];
             {
-                const double *cs = &R.sc[0][r * CW];
+                const double *cs = &R.c[bf][r * CW];
                 const int odd = (r * CW) & 1;
                 if (odd) cf[0] = cs[0];
 #pragma unroll
@@ -961,7 +977,7 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                double y = (&R.sx[h][0][0])[r * 32 + lane], y2 = 0.0;    // y_j = yloc_j + SF[j] . s_c
+                double y = R.x[bf][h][r * 32 + lane], y2 = 0.0;          // y_j = yloc_j + SF[j] . s_c
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     if (i & 1) y2 = fma(cf[K + i], sin[h][i], y2); else y = fma(cf[K + i], sin[h][i], y);
@@ -977,29 +993,29 @@ density_bwd_local2_kernel(const double *__restrict__ cfb, i64 n, i64 nchunk, dou
 #pragma unroll
                 for (int p = K - 1; p >= 2; --p) zw[h][p] = zw[h][p - 1];
                 if (K > 1) zw[h][1] = acc;
-                (&R.sx[h][0][0])[r * 32 + lane] = acc;
+                R.x[bf][h][r * 32 + lane] = acc;
             }
         };
-        if (rows == 32) {
+        if (rows == DB_R) {                         // full piece: no per-row bound test, the window shifts are renamed away
 #pragma unroll
-            for (int r = 31; r >= 0; --r) row_step(r);
+            for (int r = DB_R - 1; r >= 0; --r) row_step(r);
         } else {
 #pragma unroll
-            for (int r = 31; r >= 0; --r)
+            for (int r = DB_R - 1; r >= 0; --r)
                 if (r < rows) row_step(r);
         }
         __syncwarp();
+        const int nch = rows * 16;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             double *tg = T + ((2 * (i64)blockIdx.x + h) * n + row0) * 32;
-            const double *ts = &R.sx[h][0][0];
             if (p0 + 32 * h < P) {
 #pragma unroll 4
                 for (int e = lane; e < nch; e += 32)
-                    *reinterpret_cast<double2 *>(tg + 2 * e) = *reinterpret_cast<const double2 *>(ts + 2 * e);
+                    *reinterpret_cast<double2 *>(tg + 2 * e) = *reinterpret_cast<const double2 *>(&R.x[bf][h][2 * e]);
             }
         }
-        __syncwarp();
+        __syncwarp();                               // buffer bf is requested again by the next trip's issue
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
