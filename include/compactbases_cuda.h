@@ -355,7 +355,11 @@ int cb_density_destroy(cb_density *D);
 int cb_density_set_refine(cb_density *D, int steps);
 /* copyto!(rho, f, g) (src/densities.jl:156-164).  f is nf x Pf, g is nf x Pg,
  * Pf==Pg or one of them 1 (broadcast, :57-72); rho is nf x max(Pf,Pg).
- * conj is accepted for ABI completeness (real Float64: no-op). */
+ * conj is accepted for ABI completeness (real Float64: no-op).
+ * Stream-ordered scratch from the device's memory pool (released on the stream
+ * before the call returns): 32 * ncols * ceil(P / 32) doubles for the tiled
+ * intermediate of the partitioned solve (one more array of the batch's size)
+ * plus 2 * (ncols / 256) * (k - 1) * P doubles of chunk states. */
 int cb_density_apply(const cb_density *D, const double *f, cb_i64 ldf, cb_i64 Pf,
                      const double *g, cb_i64 ldg, cb_i64 Pg, int conj,
                      double *rho, cb_i64 ldr, void *stream);
