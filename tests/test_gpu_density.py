@@ -123,3 +123,30 @@ def test_density_config5_scaled_properties(cb):
     ones = torch.ones((1, nf), dtype=torch.float64, device="cuda")
     r_1 = cb.Density(B, nlhs=1, nrhs=P).copyto(cb.ColMajor(ones), cb.ColMajor(g)).data
     assert torch.max(torch.abs(r_1 - g)).item() <= 1e-11 * torch.max(torch.abs(g)).item()
+
+
+def test_density_partitioned_batches_are_independent_of_their_grouping(cb):
+    """The partitioned solve groups the pairs by 32 (tiled intermediate) and by 64 (two pairs per lane in the backward
+    sweep): a pair's result must not depend on the batch it travels in — sub-batches that end inside a group give the
+    same bits as the full batch — and the stand-alone banded solve (LinearOperator's metric inverse) takes the same
+    route."""
+    t = cb.LinearKnotSet(7, 0, 10, 700)                    # 706 functions: two chunks
+    B = cb.BSpline(t)
+    nf, P = B.nf, 97
+    rng = np.random.default_rng(77)
+    f, g = rng.standard_normal((nf, P)), rng.standard_normal((nf, P))
+    full = cb.Density(B, nlhs=P, nrhs=P).copyto(cb.ColMajor.from_numpy(f), cb.ColMajor.from_numpy(g)).numpy()
+    for Ps in (1, 31, 32, 33, 64, 65, 96):
+        sub = cb.Density(B, nlhs=Ps, nrhs=Ps).copyto(cb.ColMajor.from_numpy(f[:, :Ps]), cb.ColMajor.from_numpy(g[:, :Ps])).numpy()
+        assert np.array_equal(sub, full[:, :Ps]), Ps
+    te, q, x, w = oracle_basis(t)
+    V = cbo.basis_matrix(te, t.k, x, q)
+    assert relerr(full[:, 90:], cbo.density_bspline(V, f[:, 90:], g[:, 90:])) <= RTOL
+    # S \ (S c) = c through cb_bandchol_solve for ragged batches
+    S = B.T @ B
+    C = rng.standard_normal((nf, 70))
+    Y = cb.ColMajor.from_numpy(np.zeros((nf, 70)))
+    cb.mul(Y, S, cb.ColMajor.from_numpy(C))
+    F = cb.factorize(S, "cholesky")
+    F.ldiv(Y)
+    assert relerr(Y.numpy(), C) <= 1e-11
