@@ -362,31 +362,51 @@ lp_bwd_local_kernel(LuPart F, double *__restrict__ X, i64 ldx, i64 nvec, const d
     lp_store_rows(xs, X, ldx, v0, nv, a, kv, nb, lane);
 }
 
-// B3: x_j = zloc_j + SB[j] . db_c;  thread <-> row, loop over the vectors of the block's slice
-__global__ void __launch_bounds__(128)
+// B3: x_j = zloc_j + SB[j] . db_c.  A CTA takes 256 rows (four chunks) and 32 vectors: the chunks' incoming states of
+// those vectors sit in shared memory ([chunk][vector][KVP], zero-padded: 16-byte broadcast reads), a thread keeps the
+// spike row of its row in registers (KVP is a compile-time bound: with the run-time kv the row lived in local memory
+// and every FMA fetched its state component with a global load — 179 M warp instructions for 0.8 GB), and reads eight
+// vectors before it stores any (X is read and written through the same pointer).
+constexpr int LF_V = 32, LF_U = 8;
+template <int KVP>
+__global__ void __launch_bounds__(256, 2)
 lp_final_kernel(LuPart F, double *__restrict__ X, i64 ldx, i64 nvec, const double *__restrict__ Sb) {
+    __shared__ __align__(16) double sst[(256 / LP_CH) * LF_V * KVP];
     const int kv = F.kv;
-    const i64 c = blockIdx.y;
-    if (c + 1 >= F.nchunk) return;                  // the last chunk has no incoming state
-    const i64 a = lp_begin(c), b = lp_end(c, F.nchunk, F.n);
-    const i64 vper = (nvec + gridDim.x - 1) / gridDim.x, va = blockIdx.x * vper, vb = va + vper < nvec ? va + vper : nvec;
-    for (i64 row = a + threadIdx.x; row < b; row += blockDim.x) {
-        double sb[LP_MAXS];
-        for (int i = 0; i < kv; ++i) sb[i] = __ldg(F.SB + row * kv + i);
-        // four vectors at a time, their loads first: X is read and written through the same pointer, so the compiler
-        // keeps every load behind the previous vector's store
-        for (i64 v = va; v < vb; v += 4) {
-            double x[4];
+    const i64 nrb = (F.n + 255) / 256, nvg = (nvec + LF_V - 1) / LF_V;
+    for (i64 item = blockIdx.x; item < nrb * nvg; item += gridDim.x) {
+        const i64 rb = item % nrb, vg = item / nrb;
+        const i64 va = vg * LF_V;
+        const int nv = (int)(va + LF_V < nvec ? LF_V : nvec - va);
+        const i64 c0 = rb * (256 / LP_CH);          // first chunk of the row block
+        __syncthreads();
+        for (int e = threadIdx.x; e < (256 / LP_CH) * LF_V * KVP; e += 256) {
+            const int lc = e / (LF_V * KVP), v = (e / KVP) % LF_V, i = e % KVP;
+            const i64 c = c0 + lc;                  // the state that enters chunk c is that of chunk c + 1
+            sst[e] = (i < kv && v < nv && c + 1 < F.nchunk) ? Sb[((c + 1) * kv + i) * nvec + va + v] : 0.0;
+        }
+        __syncthreads();
+        const i64 row = rb * 256 + threadIdx.x;
+        if (row >= F.n) continue;
+        const int lc = threadIdx.x / LP_CH;
+        if (c0 + lc + 1 >= F.nchunk) continue;      // the last chunk has no incoming state
+        double sb[KVP];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = v + u < vb ? X[(v + u) * ldx + row] : 0.0;
-            for (int i = 0; i < kv; ++i) {
-                const double *sp = Sb + ((c + 1) * kv + i) * nvec + v;
+        for (int i = 0; i < KVP; ++i) sb[i] = i < kv ? __ldg(F.SB + row * kv + i) : 0.0;
+        const double *sc = sst + (size_t)lc * LF_V * KVP;
+        for (int vb = 0; vb < nv; vb += LF_U) {
+            double x[LF_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = fma(sb[i], v + u < vb ? __ldg(sp + u) : 0.0, x[u]);
+            for (int u = 0; u < LF_U; ++u) x[u] = vb + u < nv ? X[(va + vb + u) * ldx + row] : 0.0;
+#pragma unroll
+            for (int u = 0; u < LF_U; ++u) {
+                const double2 *s2 = reinterpret_cast<const double2 *>(sc + (vb + u) * KVP);
+#pragma unroll
+                for (int h = 0; h < KVP / 2; ++h) { const double2 t = s2[h]; x[u] = fma(sb[2 * h], t.x, x[u]); x[u] = fma(sb[2 * h + 1], t.y, x[u]); }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (v + u < vb) X[(v + u) * ldx + row] = x[u];
+            for (int u = 0; u < LF_U; ++u)
+                if (vb + u < nv) X[(va + vb + u) * ldx + row] = x[u];
         }
     }
 }
@@ -502,8 +522,11 @@ int cb_bandlu_part_solve(const cb_bandlu_part *P, const double *ab, const int *i
             lp_tails_kernel<<<cb_grid_for((i64)per * kv, 256, 16), 256, 0, st>>>(F, X, ldx, nvec, E, H2);
             k2<<<grid, 32, smem, st>>>(F, X, ldx, nvec, E, H2, Eb);
             lp_launch_state(P->TB, M, kv, nvec, Eb, -1, st);
-            unsigned gx = (unsigned)(nvec < 8 ? nvec : 8);
-            lp_final_kernel<<<dim3(gx, (unsigned)M), 128, 0, st>>>(F, X, ldx, nvec, Eb);
+            const i64 nitem = ((P->n + 255) / 256) * ((nvec + LF_V - 1) / LF_V);
+            const unsigned gf = (unsigned)(nitem < (i64)CB_NUM_SMS * 16 ? nitem : (i64)CB_NUM_SMS * 16);
+            if (kv <= 8) lp_final_kernel<8><<<gf, 256, 0, st>>>(F, X, ldx, nvec, Eb);
+            else if (kv <= 16) lp_final_kernel<16><<<gf, 256, 0, st>>>(F, X, ldx, nvec, Eb);
+            else lp_final_kernel<32><<<gf, 256, 0, st>>>(F, X, ldx, nvec, Eb);
         }
     });
     cudaFreeAsync(scr, st);
