@@ -119,6 +119,38 @@ def complex_ldiv(R, f) -> ComplexColMajor:
     return ComplexColMajor(torch.complex(cr.data[:, :cr.n].contiguous(), ci.data[:, :ci.n].contiguous()))
 
 
+def complex_density(rho, f: ComplexColMajor, g: ComplexColMajor) -> ComplexColMajor:
+    """``copyto!(rho, f, g)`` for ComplexF64 coefficient batches (src/densities.jl:156-185 with ``T = ComplexF64``):
+    ``Density`` conjugates its first factor, ``FunctionProduct{false}`` does not.  The projection onto the basis is a
+    real linear map, so the complex density is four real ones on the split batches [Re | Im]:
+    ``conj(f) g = (fr gr + fi gi) + i (fr gi - fi gr)``,  ``f g = (fr gr - fi gi) + i (fr gi + fi gr)``;
+    every real density is the same ``cb_density_apply`` / ``cb_density_orthogonal`` call (the object ``rho`` carries the
+    plan), the sums are ``cb_axpby``.  Column broadcasting (one of the factors with a single column) carries over."""
+    from .operators import axpby
+    if f.n != rho.n or g.n != rho.n:
+        raise DimensionMismatch(f"DimensionMismatch: basis has {rho.n} functions, got {f.n} and {g.n} rows")
+    if f.nvec != g.nvec and 1 not in (f.nvec, g.nvec):
+        raise DimensionMismatch(f"DimensionMismatch: {f.nvec} and {g.nvec} columns")
+    fs, gs = f.split(), g.split()
+    fr, fi = ColMajor(fs.data[:f.nvec]), ColMajor(fs.data[f.nvec:])
+    gr, gi = ColMajor(gs.data[:g.nvec]), ColMajor(gs.data[g.nvec:])
+    P = max(f.nvec, g.nvec)
+    dev = f.data.device
+    out = torch.empty((2 * P, rho.n), dtype=torch.float64, device=dev)       # [Re | Im] of the density
+    re, im = ColMajor(out[:P]), ColMajor(out[P:])
+    tmp = ColMajor(torch.empty((P, rho.n), dtype=torch.float64, device=dev))
+    sgn = 1.0 if rho.conjugated else -1.0
+    rho.copyto(fr, gr, re)
+    rho.copyto(fi, gi, tmp)
+    axpby(re, tmp, sgn, 1.0)                        # Re: fr gr +- fi gi
+    rho.copyto(fr, gi, im)
+    rho.copyto(fi, gr, tmp)
+    axpby(im, tmp, -sgn, 1.0)                       # Im: fr gi -+ fi gr
+    Z = ComplexColMajor.zeros(rho.n, P, dev)
+    _lib.call("cb_complex_combine", _ptr(out), None, rho.n, rho.n, P, 1.0, 0.0, 0.0, 0.0, Z.data.data_ptr(), Z.ld, _stream())
+    return Z
+
+
 def cmul(Y: ComplexColMajor, A, X: ComplexColMajor, alpha: complex = 1.0, beta: complex = 0.0):
     """``mul!`` for complex batches; A may be a ComplexOperator or any real device operator."""
     if not isinstance(A, ComplexOperator):

@@ -951,3 +951,34 @@ def test_complex_scaled_fedvr(cb):
             assert crelerr(got, want) <= RTOL
             Y = A @ cb.ComplexColMajor.from_numpy(X)
             assert crelerr(Y.numpy(), ref @ X) <= RTOL
+
+
+@pytest.mark.parametrize("name,make", COMPLEX_BASES, ids=[c[0] for c in COMPLEX_BASES])
+def test_complex_density(cb, name, make):
+    """Density / FunctionProduct{false} of ComplexF64 coefficient batches (src/densities.jl:48-101, 156-185 with
+    T = ComplexF64) against the direct complex evaluation: rho = C (conj(V f) .* (V g)) with the dense pinv for
+    B-splines, the diagonal C of the orthogonal bases otherwise; one-column broadcasting included."""
+    R = make(cb)
+    n = R.size() if callable(getattr(R, "size", None)) else R.N
+    rng = np.random.default_rng(91)
+    P = 5
+    f = rng.standard_normal((n, P)) + 1j * rng.standard_normal((n, P))
+    g = rng.standard_normal((n, P)) + 1j * rng.standard_normal((n, P))
+    if isinstance(R, cb.BSpline):
+        te, q, x, w = oracle_basis(R.t)
+        V = cbo.basis_matrix(te, R.t.k, x, q)
+        proj = np.linalg.pinv(V)
+        ref = lambda a, b, conj: proj @ ((np.conj(V @ a) if conj else V @ a) * (V @ b))
+    else:
+        rho0 = cb.Density(R, nlhs=1, nrhs=1)
+        c = np.ones(n) if rho0.c is None else rho0.c.cpu().numpy()
+        ref = lambda a, b, conj: c[:, None] * (np.conj(a) if conj else a) * b
+    for conj in (True, False):
+        rho = cb.FunctionProduct(R, nlhs=P, nrhs=P, conjugated=conj)
+        got = cb.complex_density(rho, cb.ComplexColMajor.from_numpy(f), cb.ComplexColMajor.from_numpy(g)).numpy()
+        assert crelerr(got, ref(f, g, conj)) <= 1e-12, (name, conj)
+    rho = cb.Density(R, nlhs=1, nrhs=P)
+    got = cb.complex_density(rho, cb.ComplexColMajor.from_numpy(f[:, :1]), cb.ComplexColMajor.from_numpy(g)).numpy()
+    assert crelerr(got, ref(f[:, :1], g, True)) <= 1e-12
+    with pytest.raises(cb.DimensionMismatch):
+        cb.complex_density(rho, cb.ComplexColMajor.from_numpy(f[:, :2]), cb.ComplexColMajor.from_numpy(g))
