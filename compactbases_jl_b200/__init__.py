@@ -18,7 +18,7 @@ from .fedvr import FEDVR, RestrictedFEDVR
 from .finite_differences import (FiniteDifferences, ImplicitFiniteDifferences, RestrictedFiniteDifferences,
                                  StaggeredFiniteDifferences)
 from .densities import Density, DiagonalOperator, FunctionProduct
-from .complex_ops import (ComplexColMajor, ComplexOperator, ComplexScaledFEDVR, cmul, complex_density, complex_ldiv, complex_linear_operator,
+from .complex_ops import (ComplexColMajor, ComplexDiagonalOperator, ComplexOperator, ComplexScaledFEDVR, cmul, complex_density, complex_ldiv, complex_linear_operator,
                           complex_potential)
 
 __all__ = [
@@ -26,6 +26,6 @@ __all__ = [
     "CoulombPotential", "diffop", "diffop_host", "hamiltonian_bands", "FEDVR", "RestrictedFEDVR", "FiniteDifferences", "StaggeredFiniteDifferences",
     "RestrictedFiniteDifferences", "Derivative", "QuasiDiagonal", "CoulombDerivative", "materialize",
     "BandedMatrix", "BlockSkylineMatrix", "BandCholesky", "LinearOperator", "Tridiagonal", "SymTridiagonal", "Diagonal", "FEDVRMatrix", "ColMajor", "mul",
-    "Density", "FunctionProduct", "complex_density", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "batched_dot", "inner_product", "norm", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
+    "Density", "FunctionProduct", "complex_density", "ComplexDiagonalOperator", "DiagonalOperator", "ShiftAndInvert", "BandLU", "factorize", "batched_dot", "inner_product", "norm", "ImplicitFiniteDifferences", "ImplicitDerivative", "as_banded", "axpby", "DimensionMismatch", "CudaError", "gausslegendre", "gausslobatto",
     "num_quadrature_points",
 ]

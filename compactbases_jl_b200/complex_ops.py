@@ -119,13 +119,15 @@ def complex_ldiv(R, f) -> ComplexColMajor:
     return ComplexColMajor(torch.complex(cr.data[:, :cr.n].contiguous(), ci.data[:, :ci.n].contiguous()))
 
 
-def complex_density(rho, f: ComplexColMajor, g: ComplexColMajor) -> ComplexColMajor:
+def complex_density(rho, f: ComplexColMajor, g: ComplexColMajor, out: ComplexColMajor | None = None,
+                    alpha: complex = 1.0, beta: complex = 0.0) -> ComplexColMajor:
     """``copyto!(rho, f, g)`` for ComplexF64 coefficient batches (src/densities.jl:156-185 with ``T = ComplexF64``):
     ``Density`` conjugates its first factor, ``FunctionProduct{false}`` does not.  The projection onto the basis is a
     real linear map, so the complex density is four real ones on the split batches [Re | Im]:
     ``conj(f) g = (fr gr + fi gi) + i (fr gi - fi gr)``,  ``f g = (fr gr - fi gi) + i (fr gi + fi gr)``;
     every real density is the same ``cb_density_apply`` / ``cb_density_orthogonal`` call (the object ``rho`` carries the
-    plan), the sums are ``cb_axpby``.  Column broadcasting (one of the factors with a single column) carries over."""
+    plan), the sums are ``cb_axpby``.  Column broadcasting (one of the factors with a single column) carries over.
+    ``out``, ``alpha``, ``beta``: ``out = alpha * rho + beta * out`` (what ``DiagonalOperator``'s ``mul!`` needs)."""
     from .operators import axpby
     if f.n != rho.n or g.n != rho.n:
         raise DimensionMismatch(f"DimensionMismatch: basis has {rho.n} functions, got {f.n} and {g.n} rows")
@@ -136,8 +138,8 @@ def complex_density(rho, f: ComplexColMajor, g: ComplexColMajor) -> ComplexColMa
     gr, gi = ColMajor(gs.data[:g.nvec]), ColMajor(gs.data[g.nvec:])
     P = max(f.nvec, g.nvec)
     dev = f.data.device
-    out = torch.empty((2 * P, rho.n), dtype=torch.float64, device=dev)       # [Re | Im] of the density
-    re, im = ColMajor(out[:P]), ColMajor(out[P:])
+    re_im = torch.empty((2 * P, rho.n), dtype=torch.float64, device=dev)     # [Re | Im] of the density
+    re, im = ColMajor(re_im[:P]), ColMajor(re_im[P:])
     tmp = ColMajor(torch.empty((P, rho.n), dtype=torch.float64, device=dev))
     sgn = 1.0 if rho.conjugated else -1.0
     rho.copyto(fr, gr, re)
@@ -146,9 +148,40 @@ def complex_density(rho, f: ComplexColMajor, g: ComplexColMajor) -> ComplexColMa
     rho.copyto(fr, gi, im)
     rho.copyto(fi, gr, tmp)
     axpby(im, tmp, -sgn, 1.0)                       # Im: fr gi -+ fi gr
-    Z = ComplexColMajor.zeros(rho.n, P, dev)
-    _lib.call("cb_complex_combine", _ptr(out), None, rho.n, rho.n, P, 1.0, 0.0, 0.0, 0.0, Z.data.data_ptr(), Z.ld, _stream())
+    Z = ComplexColMajor.zeros(rho.n, P, dev) if out is None else out
+    if Z.n != rho.n or Z.nvec != P:
+        raise DimensionMismatch(f"DimensionMismatch: the density is {rho.n} x {P}, the destination {Z.n} x {Z.nvec}")
+    a, b = complex(alpha), complex(beta)
+    _lib.call("cb_complex_combine", _ptr(re_im), None, rho.n, rho.n, P, a.real, a.imag, b.real, b.imag,
+              Z.data.data_ptr(), Z.ld, _stream())
     return Z
+
+
+class ComplexDiagonalOperator:
+    """``DiagonalOperator(f)`` with ComplexF64 coefficients (src/linear_operators.jl:85-173; the "Diagonal" operators of
+    test/linear_operators.jl:1-35 with T = ComplexF64): ``mul!(y, L, x, alpha, beta)`` is the unconjugated product
+    ``FunctionProduct{false}`` of the two expansions, ``y = alpha * (coefficients of f*x) + beta * y``."""
+
+    def __init__(self, R, diag: ComplexColMajor, nrhs=None, w=None):
+        from .densities import FunctionProduct
+        self.R = R
+        self.rho = FunctionProduct(R, R, 1, nrhs, w, conjugated=False)
+        self.n = self.rho.n
+        if diag.n != self.n or diag.nvec != 1:
+            raise DimensionMismatch(f"DimensionMismatch: the basis has {self.n} functions, diag has {diag.n} x {diag.nvec}")
+        self.diag = diag
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def mul(self, Y: ComplexColMajor, X: ComplexColMajor, alpha: complex = 1.0, beta: complex = 0.0):
+        if X.n != self.n or Y.n != self.n or X.nvec != Y.nvec:
+            raise DimensionMismatch(f"DimensionMismatch: operator of order {self.n}, X {X.n}x{X.nvec}, Y {Y.n}x{Y.nvec}")
+        return complex_density(self.rho, self.diag, X, out=Y, alpha=alpha, beta=beta)
+
+    def __matmul__(self, X: ComplexColMajor):
+        return self.mul(ComplexColMajor.zeros(self.n, X.nvec, X.data.device), X)
 
 
 def cmul(Y: ComplexColMajor, A, X: ComplexColMajor, alpha: complex = 1.0, beta: complex = 0.0):

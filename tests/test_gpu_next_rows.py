@@ -982,3 +982,31 @@ def test_complex_density(cb, name, make):
     assert crelerr(got, ref(f[:, :1], g, True)) <= 1e-12
     with pytest.raises(cb.DimensionMismatch):
         cb.complex_density(rho, cb.ComplexColMajor.from_numpy(f[:, :2]), cb.ComplexColMajor.from_numpy(g))
+
+
+@pytest.mark.parametrize("name,make", COMPLEX_BASES, ids=[c[0] for c in COMPLEX_BASES])
+def test_complex_diagonal_operator(cb, name, make):
+    """test/linear_operators.jl:1-35, "Diagonal" operators with T = ComplexF64: DiagonalOperator(R * (R \\ f.(x))) applied
+    to the coefficients of o(x) = 1 gives the coefficients of f = exp(i pi/4) sin(2 pi x / L); plus mul! with complex
+    alpha, beta against the complex product of the expansions."""
+    R = make(cb)
+    L = 10.0
+    gamma = np.exp(1j * np.pi / 4)
+    f = lambda x: gamma * np.sin(2 * np.pi * np.asarray(x) / L)
+    one = lambda x: np.ones_like(np.asarray(x, dtype=np.float64)) + 0j
+    fc, oc = cb.complex_ldiv(R, f), cb.complex_ldiv(R, one)
+    V = cb.ComplexDiagonalOperator(R, fc)
+    m = R.size()
+    assert V.shape == (m, m)
+    u = V @ oc
+    un, fn = u.numpy()[:, 0], fc.numpy()[:, 0]
+    assert np.linalg.norm(un - fn) <= 2e-8 * np.linalg.norm(fn)          # isapprox: rtol = sqrt(eps)
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((m, 4)) + 1j * rng.standard_normal((m, 4))
+    Y0 = rng.standard_normal((m, 4)) + 1j * rng.standard_normal((m, 4))
+    al, be = 0.5 - 2.0j, -1.5 + 0.25j
+    Y = cb.ComplexColMajor.from_numpy(Y0)
+    cb.ComplexDiagonalOperator(R, fc, nrhs=4).mul(Y, cb.ComplexColMajor.from_numpy(X), al, be)
+    rho = cb.FunctionProduct(R, nlhs=1, nrhs=4, conjugated=False)
+    prod = cb.complex_density(rho, fc, cb.ComplexColMajor.from_numpy(X)).numpy()
+    assert crelerr(Y.numpy(), al * prod + be * Y0) <= RTOL
