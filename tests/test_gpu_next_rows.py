@@ -873,6 +873,7 @@ COMPLEX_BASES = [
     ("sfd_nonuniform", lambda cb: cb.StaggeredFiniteDifferences(np.cumsum(np.minimum(0.1 + 0.01 * np.arange(160), 0.2))[:120])),
     ("fedvr", lambda cb: cb.FEDVR(cbo.julia_range(0.0, 10.0, 100), 4)),
     ("bsplines", lambda cb: cb.BSpline(cb.LinearKnotSet(5, 0, 10.0, 100))),
+    ("implicit_fd", lambda cb: cb.ImplicitFiniteDifferences(100, 10.0 / 101)),
 ]
 
 
