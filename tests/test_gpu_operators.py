@@ -530,3 +530,38 @@ def test_fedvr_rows_kernel_bit_identical_to_generic(cb, order):
         if nel in (5, 17):
             O = cbo.FEDVROracle(t, order)
             assert relerr(out[0], O.blocks(2)) <= RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order,nel,nvec", [(10, 400, 64), (10, 37, 5), (4, 300, 33), (16, 50, 32), ([4, 3, 4, 2, 5, 4, 2, 4, 8], 9, 7)])
+def test_fedvr_assemble_apply_one_call(cb, order, nel, nvec):
+    """cb_fedvr_assemble_apply (derop! followed by mul! in one foreign call; the apply pipeline is launched behind the
+    assembly grid with programmatic stream serialisation and waits for it before reading the blocks): same bits as the
+    two separate calls, repeatedly (the blocks are rewritten by every call), with alpha / beta, and within tolerance of the
+    oracle."""
+    import torch
+    t = cbo.julia_range(0.0, 25.0, nel + 1)
+    B = cb.FEDVR(t, order)
+    D = cb.Derivative()
+    rng = np.random.default_rng(nel)
+    X = rng.standard_normal((B.N, nvec))
+    Xc = cb.ColMajor.from_numpy(X)
+    for nder, A in ((2, B.T @ D.T @ D @ B), (1, B.T @ D @ B)):
+        ref_blocks = A.blocks.clone()
+        Ysep = cb.ColMajor.from_numpy(np.zeros((B.N, nvec)))
+        cb.mul(Ysep, A, Xc)
+        for rep in range(3):
+            B._ops[nder].fill_(float("nan"))                     # the call must rebuild the operator
+            Y = cb.ColMajor.from_numpy(np.full((B.N, nvec), np.nan))
+            A2 = B.derop_mul(nder, Y, Xc)
+            torch.cuda.synchronize()
+            assert torch.equal(A2.blocks, ref_blocks)
+            assert np.array_equal(Y.numpy(), Ysep.numpy()), (nder, rep)
+        Y0 = rng.standard_normal((B.N, nvec))
+        Yb = cb.ColMajor.from_numpy(Y0)
+        B.derop_mul(nder, Yb, Xc, 0.5, -2.0)
+        Yc = cb.ColMajor.from_numpy(Y0)
+        cb.mul(Yc, A, Xc, 0.5, -2.0)
+        assert np.array_equal(Yb.numpy(), Yc.numpy())
+        O = cbo.FEDVROracle(t, order)
+        assert relerr(Ysep.numpy(), O.apply(O.blocks(nder), X)) <= RTOL
