@@ -243,3 +243,23 @@ def test_block_skyline_layout_host_logic():
                 for j in range(rows[J]):
                     d[st + j * S.stride[J]:st + j * S.stride[J] + rows[K]] = blkA[:, j]
         assert np.array_equal(S.dense(), A)
+
+
+def test_batch_range_entry_matches_the_host_mirror():
+    """cb_batch_range (host-only entry: contiguous shares of points / vectors / pairs) against sharding.batch_range:
+    shares are contiguous, cover [0, n) and differ by at most one."""
+    from compactbases_jl_b200 import _lib
+    from compactbases_jl_b200.sharding import batch_range
+    lib = _lib.load()
+    for n in (0, 1, 7, 8, 1000, 4096, 10 ** 7 + 3):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for rank in range(world):
+                lo, hi = C.c_int64(-1), C.c_int64(-1)
+                assert lib.cb_batch_range(n, rank, world, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == batch_range(n, rank, world)
+                assert lo.value == prev and hi.value - lo.value in (n // world, n // world + 1)
+                prev = hi.value
+            assert prev == n
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    assert lib.cb_batch_range(10, 3, 3, C.byref(lo), C.byref(hi)) != 0          # rank outside the world

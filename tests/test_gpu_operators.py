@@ -565,3 +565,31 @@ def test_fedvr_assemble_apply_one_call(cb, order, nel, nvec):
         assert np.array_equal(Yb.numpy(), Yc.numpy())
         O = cbo.FEDVROracle(t, order)
         assert relerr(Ysep.numpy(), O.apply(O.blocks(nder), X)) <= RTOL
+
+
+@pytest.mark.gpu
+def test_host_register_entries(cb):
+    """cb_host_register / cb_host_unregister pin caller-owned host arrays for the *_host entries (what a Julia host does
+    with its Arrays): registered and pageable buffers give the same bits; unregistering twice is an error."""
+    import ctypes as C
+    from compactbases_jl_b200 import _lib
+    t = cbo.julia_range(0, 50, 301)
+    B = cb.FEDVR(t, 5)
+    D = cb.Derivative()
+    A = B.T @ D.T @ D @ B
+    rng = np.random.default_rng(19)
+    X = np.asfortranarray(rng.standard_normal((B.N, 20)))
+    Yp = np.asfortranarray(np.zeros((B.N, 20)))
+    A.mul_host(Yp, X)                                                  # pageable
+    Yr = np.asfortranarray(np.zeros((B.N, 20)))
+    lib = _lib.load()
+    for arr in (X, Yr):
+        assert lib.cb_host_register(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)) == 0
+    try:
+        A.mul_host(Yr, X)
+    finally:
+        for arr in (X, Yr):
+            assert lib.cb_host_unregister(C.c_void_p(arr.ctypes.data)) == 0
+    assert np.array_equal(Yr, Yp)
+    assert lib.cb_host_unregister(C.c_void_p(X.ctypes.data)) != 0
+    assert lib.cb_host_register(None, C.c_size_t(16)) != 0
