@@ -171,19 +171,25 @@ struct DensArgs {
 __host__ __device__ inline i64 ds_chunk_begin(i64 c);
 __host__ __device__ inline i64 ds_chunk_end(i64 c, i64 nchunk, i64 n);
 
+// The fused form (no output tile: 73 KB of shared memory per CTA) runs three CTAs per SM where the window fits 168
+// registers without spilling (k <= 10 with the default node count, k <= 8 otherwise): 12 instead of 8 warps per SM,
+// C5 16.8 -> 16.4 ms; the compiler used 216-236 registers only because it could.
 template <int K, int MODE, int QT, bool FUSE = false>
-__global__ void __launch_bounds__(DR_WARPS * 32)
+__global__ void __launch_bounds__(DR_WARPS * 32, FUSE ? ((K <= 8 || (QT > 0 && K <= 10)) ? 3 : 2) : 1)
 density_rhs_kernel(DensArgs A) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int NT = MODE == 1 ? 4 : 3;
+    constexpr int NT = FUSE ? 2 : (MODE == 1 ? 4 : 3);   // FUSE writes the tiled intermediate directly: no output tile
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = QT > 0 ? QT : A.q;
     const int TS = (q * K + q + 1) & ~1;            // one interval's table + node weights (even: rows are read as double2)
     constexpr int SORD = (FUSE ? 2 : 1) * DR_CH + K + 2;         // intervals of a chunk (the solver's last chunk takes the remainder)
-    double *sf = sm + (size_t)warp * (NT * DR_TILE + 2 * TS + (SORD + 3) / 4 * 2), *sg = sf + DR_TILE, *so = sg + DR_TILE;
+    constexpr int SW = (SORD + 31) / 32;           // words of the chunk's non-empty-interval mask
+    double *sf = sm + (size_t)warp * (NT * DR_TILE + 2 * TS + (SW + 3) / 4 * 2), *sg = sf + DR_TILE, *so = sg + DR_TILE;
     double *sr = MODE == 1 ? so + DR_TILE : so;
     double *stab = sf + NT * DR_TILE;               // [2][TS]: the interval being used and the next one (cp.async)
-    int *sord = reinterpret_cast<int *>(stab + 2 * TS);   // [DR_CH + K + 2] ordinals of the chunk's intervals
+    // which of the chunk's intervals are non-empty (bit e: interval s0 + e); their ordinals are consecutive, so the
+    // mask and the ordinal of the first one replace a table of SORD ordinals (2 KB per warp: the third CTA per SM)
+    unsigned *smask = reinterpret_cast<unsigned *>(stab + 2 * TS);
     const i64 nchunk = FUSE ? A.nchunk_ds : (A.ncols + DR_CH - 1) / DR_CH;
     const i64 npg = (A.P + 31) / 32;
     const int ml = A.ml;
@@ -223,9 +229,18 @@ density_rhs_kernel(DensArgs A) {
         asm volatile("cp.async.wait_all;" ::: "memory");           // no copy of the previous item is still landing
         __syncwarp();                                               // the previous item is done with the rings
         issue_half(0); issue_half(1);
-        for (int e = lane; e < SORD; e += 32) {
-            const i64 s_ = fa - ml + e;
-            sord[e] = (s_ >= 0 && s_ <= A.n_tt - 2) ? A.ord[s_ + ml - 1] : -1;
+        int nord = 0;                                               // ordinal of the next non-empty interval
+        {
+            bool found = false;
+#pragma unroll
+            for (int w_ = 0; w_ < SW; ++w_) {
+                const int e = 32 * w_ + lane;
+                const i64 s_ = fa - ml + e;
+                const int o = (e < SORD && s_ >= 0 && s_ <= A.n_tt - 2) ? A.ord[s_ + ml - 1] : -1;
+                const unsigned m = __ballot_sync(0xffffffffu, o >= 0);
+                if (lane == 0) smask[w_] = m;
+                if (!found && m != 0u) { nord = __shfl_sync(0xffffffffu, o, __ffs(m) - 1); found = true; }
+            }
         }
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -243,7 +258,8 @@ density_rhs_kernel(DensArgs A) {
         i64 obase = fa;                                             // function of output tile row 0
         // The k x q table of an interval is the same for every pair: it is copied to shared memory one
         // interval ahead (its L2 latency would otherwise stall the two resident warps per scheduler).
-        auto ordof = [&](i64 s_) -> int { return sord[s_ - s0]; };   // s0 <= s_ <= s1 + 2
+        // ordinal of interval s0 + e or -1; to be called with e = 0, 1, 2, ... in this order
+        auto take = [&](int e) -> int { return ((smask[e >> 5] >> (e & 31)) & 1u) ? nord++ : -1; };
         auto issue_tab = [&](int c_, int buf_) {
             if (c_ >= 0) {
                 const double *src = A.table + (i64)c_ * q * K;
@@ -261,7 +277,7 @@ density_rhs_kernel(DensArgs A) {
         };
         asm volatile("cp.async.wait_group 0;" ::: "memory");        // nothing of the previous item is still landing
         __syncwarp();
-        int c = ordof(s0), c_nxt = ordof(s0 + 1), buf = 0;
+        int c = take(0), c_nxt = take(1), buf = 0;
         issue_tab(c, 0);
         // (Unrolling this loop K times so that the window rotates through the registers instead of being shifted — 56
         // moves per interval — was measured: 23.5 ms instead of 19.7 ms at C5; the 8-fold body thrashes the instruction
@@ -271,7 +287,7 @@ density_rhs_kernel(DensArgs A) {
         const int nint = (int)(s1 - s0) + 1;
         const double *fwrow = FUSE ? A.fwt + (fa - (A.col0 + 1)) * K : nullptr;    // factor row of function fa
         for (int si = 0; si < nint; ++si) {
-            const int c_nn = sord[si + 2];
+            const int c_nn = take(si + 2);
             double cfr[K];                                          // FUSE: factor row of the function completed by this interval
             if (FUSE) {
                 const double *fr = fwrow + (si >= K - 1 ? si - (K - 1) : 0) * K;
@@ -384,7 +400,7 @@ density_rhs_kernel(DensArgs A) {
                     if (K > 1) yw[1] = a0;
                     rv = a0;
                 }
-                if (FUSE && A.out_tiled != nullptr) {
+                if (FUSE) {
                     if (p0 + lane < A.P) A.out_tiled[((pg * A.ncols) + (fa - (A.col0 + 1)) + (si - (K - 1))) * 32 + lane] = rv;
                 } else {
                 so[lane * 33 + opos] = rv;
@@ -1188,7 +1204,8 @@ static int launch_rhs(const DensArgs &A, cudaStream_t st) {
     i64 blocks = (items + DR_WARPS - 1) / DR_WARPS;
     int grid = (int)(blocks < (i64)CB_NUM_SMS * 64 ? blocks : (i64)CB_NUM_SMS * 64);
     const int sord = (fuse ? 2 : 1) * DR_CH + K + 2;
-    size_t smem = sizeof(double) * DR_WARPS * ((MODE == 1 ? 4 : 3) * DR_TILE + 2 * ((A.q * K + A.q + 1) & ~1) + (sord + 3) / 4 * 2);
+    if (fuse) CB_REQUIRE(A.out_tiled != nullptr, "cb_density_apply: the fused right-hand side writes the tiled intermediate");
+    size_t smem = sizeof(double) * DR_WARPS * ((fuse ? 2 : (MODE == 1 ? 4 : 3)) * DR_TILE + 2 * ((A.q * K + A.q + 1) & ~1) + ((sord + 31) / 32 + 3) / 4 * 2);
     auto launch = [&](auto kern) -> int {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, DR_WARPS * 32, smem, st>>>(A);
