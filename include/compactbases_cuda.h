@@ -227,7 +227,9 @@ int cb_fedvr_apply(const double *blocks, const cb_i64 *estart, const int32_t *or
                    const double *X, cb_i64 ldx, cb_i64 nvec,
                    double alpha, double beta, double *Y, cb_i64 ldy, void *stream);
 /* derop!(A, B, nder) followed by mul!(Y, A, X, alpha, beta): cb_fedvr_assemble + cb_fedvr_apply enqueued by one
- * call (`blocks` receives the operator). */
+ * call (`blocks` receives the operator).  The apply pipeline is launched behind the assembly kernel with
+ * programmatic stream serialisation: it fetches X while the assembly drains and waits for the blocks before it
+ * reads them; X and Y must not overlap the node / weight / block arrays. */
 int cb_fedvr_assemble_apply(const double *x, const double *wcat, const double *nrm,
                             const cb_i64 *estart, const int32_t *order, const cb_i64 *boff, const cb_i64 *woff,
                             cb_i64 nel, int uniform_order, int max_order, int nder, double *blocks,
