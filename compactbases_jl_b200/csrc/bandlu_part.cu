@@ -91,9 +91,14 @@ __device__ __forceinline__ void lp_forward_local(const LuPart &F, double *xs, co
                 if (r == p) { const double t = w[0]; w[0] = w[r]; w[r] = t; }
             const double xj = w[0];
             xs[s * 33 + lane] = xj;
-            const int lm = (int)(LT < F.n - 1 - (a + s) ? LT : F.n - 1 - (a + s));
+            if (F.n - 1 - (a + s) >= LT) {                   // the usual row: every multiplier exists
 #pragma unroll
-            for (int r = 1; r <= LT; ++r) w[r - 1] = r <= lm ? fma(-lj[r], xj, w[r]) : w[r];
+                for (int r = 1; r <= LT; ++r) w[r - 1] = fma(-lj[r], xj, w[r]);
+            } else {
+                const int lm = (int)(F.n - 1 - (a + s));
+#pragma unroll
+                for (int r = 1; r <= LT; ++r) w[r - 1] = r <= lm ? fma(-lj[r], xj, w[r]) : w[r];
+            }
             w[LT] = nxt;
         }
 #pragma unroll
@@ -135,9 +140,14 @@ __device__ __forceinline__ void lp_backward_local(const LuPart &F, double *xs, c
             const double xj = w[0] * uj[0];
             xs[s * 33 + lane] = xj;
             const i64 j = a + sj;
-            const int um = (int)(KVT < j ? KVT : j);         // rows above the matrix do not exist
+            if (j >= KVT) {                                  // the usual row: no per-entry bound test (two instructions per entry)
 #pragma unroll
-            for (int d = 1; d <= KVT; ++d) w[d - 1] = d <= um ? fma(-uj[d], xj, w[d]) : w[d];
+                for (int d = 1; d <= KVT; ++d) w[d - 1] = fma(-uj[d], xj, w[d]);
+            } else {
+                const int um = (int)j;                       // rows above the matrix do not exist
+#pragma unroll
+                for (int d = 1; d <= KVT; ++d) w[d - 1] = d <= um ? fma(-uj[d], xj, w[d]) : w[d];
+            }
             w[KVT] = nxt;
         }
 #pragma unroll
@@ -347,11 +357,24 @@ lp_bwd_local_kernel(LuPart F, double *__restrict__ X, i64 ldx, i64 nvec, const d
     __syncwarp();
     lp_invert_diag(F, fac, nb, lane);
     if (c > 0) {
-        for (int r = 0; r < nb; ++r) {
-            const double *sf = sfs + r * l;
-            double y = xs[(kv + r) * 33 + lane];
-            for (int i = 0; i < l; ++i) y = fma(sf[i], d[i], y);
-            xs[(kv + r) * 33 + lane] = y;
+        if constexpr (LT > 0) {                              // l = LT: the state stays in registers, the sum unrolls
+            double dr[LT];
+#pragma unroll
+            for (int i = 0; i < LT; ++i) dr[i] = d[i];
+            for (int r = 0; r < nb; ++r) {
+                const double *sf = sfs + r * LT;
+                double y = xs[(kv + r) * 33 + lane];
+#pragma unroll
+                for (int i = 0; i < LT; ++i) y = fma(sf[i], dr[i], y);
+                xs[(kv + r) * 33 + lane] = y;
+            }
+        } else {
+            for (int r = 0; r < nb; ++r) {
+                const double *sf = sfs + r * l;
+                double y = xs[(kv + r) * 33 + lane];
+                for (int i = 0; i < l; ++i) y = fma(sf[i], d[i], y);
+                xs[(kv + r) * 33 + lane] = y;
+            }
         }
     }
     __syncwarp();
