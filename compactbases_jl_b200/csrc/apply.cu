@@ -1784,6 +1784,58 @@ int cb_fedvr_to_dense(const double *blocks, const i64 *estart, const int32_t *or
     return CB_OK;
 }
 
+// FE-DVR basis functions at points (src/fedvr.jl:211-222, 272-295): the functions of the element that contains x,
+//   chi_{i,m}(x) = n_m prod_{j != m} (x - x_j) / (x_m - x_j),
+// evaluated in the reference's order (one quotient per factor, round-to-nearest: bit-identical to the scalar loop).  A point
+// on an interior element boundary belongs to the element to its right — the one whose values the reference's column
+// loop writes last; both give n for the bridge function and exact zeros for the others.  One thread per point.
+__global__ void fedvr_eval_kernel(const double *__restrict__ xn, const double *__restrict__ nrm, const double *__restrict__ t,
+                                  const i64 *__restrict__ estart, const int32_t *__restrict__ order, i64 nel, int omax,
+                                  const double *__restrict__ xq, i64 nx, int32_t *__restrict__ elem, double *__restrict__ vals) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < nx; p += (i64)gridDim.x * blockDim.x) {
+        const double x = xq[p];
+        double *v = vals + p * omax;
+        if (!(x >= t[0] && x <= t[nel])) {              // outside the basis (or NaN): no entries
+            elem[p] = 0;
+            for (int m = 0; m < omax; ++m) v[m] = 0.0;
+            continue;
+        }
+        i64 lo = 0, hi = nel;                           // last element e with t[e] <= x (the last one at x = t[nel])
+        while (hi - lo > 1) {
+            const i64 mid = (lo + hi) >> 1;
+            if (t[mid] <= x) lo = mid; else hi = mid;
+        }
+        const i64 e = lo;
+        const int o = order[e];
+        const double *xe = xn + estart[e], *ne = nrm + estart[e];
+        elem[p] = (int32_t)(e + 1);
+        for (int m = 0; m < omax; ++m) {
+            double chi = 0.0;
+            if (m < o) {
+                chi = ne[m];
+                const double xm = xe[m];
+                for (int j = 0; j < o; ++j) {
+                    if (j == m) continue;
+                    chi = __dmul_rn(chi, __ddiv_rn(__dsub_rn(x, xe[j]), __dsub_rn(xm, xe[j])));
+                }
+            }
+            v[m] = chi;
+        }
+    }
+}
+
+int cb_fedvr_eval(const double *xn, const double *nrm, const double *t, const i64 *estart, const int32_t *order,
+                  i64 nel, int max_order, const double *xq, i64 nx, int32_t *elem, double *vals, void *stream) {
+    CB_REQUIRE(nx >= 0 && nel >= 1, "cb_fedvr_eval: bad sizes");
+    if (nx == 0) return CB_OK;
+    CB_REQUIRE(xn && nrm && t && estart && order && xq && elem && vals, "cb_fedvr_eval: NULL argument");
+    CB_REQUIRE(max_order >= 2, "cb_fedvr_eval: element order must be >= 2");
+    if (max_order > CB_FEDVR_OMAX) { cb_set_error("cb_fedvr_eval: element order %d > %d", max_order, CB_FEDVR_OMAX); return CB_ERR_UNSUPPORTED; }
+    fedvr_eval_kernel<<<cb_grid_for(nx, 128, 16), 128, 0, (cudaStream_t)stream>>>(xn, nrm, t, estart, order, nel, max_order, xq, nx, elem, vals);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 int cb_fedvr_to_band(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
                      i64 nel, i64 first, i64 last, int w, double *band, void *stream) {
     CB_REQUIRE(blocks && estart && order && boff && band, "cb_fedvr_to_band: NULL argument");

@@ -170,6 +170,33 @@ class FEDVR(_FEDVROrRestricted):
             return f.to(self.device, torch.float64)
         return to_device(np.asarray(f(self.x), dtype=np.float64), self.device)
 
+    def eval(self, x):
+        """``B[x, :]`` in row form (``cb_fedvr_eval``; getindex, src/fedvr.jl:211-222, 272-295): for every point the
+        1-based element that contains it (0 outside the basis) and the values of that element's functions (function
+        ``estart[e] + m + 1``, zero-padded to the largest order).  x: device tensor or array."""
+        xq = x if isinstance(x, torch.Tensor) else to_device(np.asarray(x, dtype=np.float64), self.device)
+        xq = xq.to(self.device, torch.float64).contiguous()
+        nx, omax = xq.numel(), int(self.order.max())
+        if not hasattr(self, "d_t"):
+            self.d_t = to_device(np.asarray(self.t, dtype=np.float64), self.device)
+        elem = torch.empty(nx, dtype=torch.int32, device=self.device)
+        vals = torch.empty((nx, omax), dtype=torch.float64, device=self.device)
+        _lib.call("cb_fedvr_eval", _ptr(self.d_x), _ptr(self.d_n), _ptr(self.d_t), _ptr(self.d_estart), _ptr(self.d_order),
+                  self.nel, omax, _ptr(xq), nx, _ptr(elem), _ptr(vals), _stream())
+        return elem, vals
+
+    def eval_dense(self, x, first: int = 1, last: int | None = None) -> np.ndarray:
+        """``Matrix(B[x, first:last])`` on the host (tests, small bases): scatters the row form."""
+        last = self.N if last is None else last
+        elem, vals = self.eval(x)
+        e, v = elem.cpu().numpy(), vals.cpu().numpy()
+        out = np.zeros((e.size, self.N))
+        for p in np.nonzero(e)[0]:
+            el = e[p] - 1
+            o = int(self.order[el])
+            out[p, self.estart[el]:self.estart[el] + o] = v[p, :o]
+        return out[:, first - 1:last]
+
     def derop(self, nder: int) -> torch.Tensor:
         """``derop!(A, B, n)`` (src/fedvr_derivatives.jl:62-63): all element blocks."""
         if nder not in self._ops:

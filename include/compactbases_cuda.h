@@ -187,6 +187,13 @@ int cb_fedvr_assemble(const double *x, const double *wcat, const double *nrm,
 int cb_fedvr_to_dense(const double *blocks, const cb_i64 *estart, const int32_t *order,
                       const cb_i64 *boff, cb_i64 nel, cb_i64 first, cb_i64 last,
                       double *A, void *stream);
+/* B[x, :] for FE-DVR bases (getindex, src/fedvr.jl:211-222, 272-295), row form: for every point the (1-based) element
+ * that contains it (0: outside the basis) and the values of that element's order[e] functions, vals[p * max_order + m]
+ * (function estart[e] + m + 1 of the basis; zero-padded to max_order).  t: the nel + 1 element boundaries (device).  A
+ * point on an interior boundary is reported with the element to its right. */
+int cb_fedvr_eval(const double *x_nodes, const double *nrm, const double *t, const cb_i64 *estart,
+                  const int32_t *order, cb_i64 nel, int max_order, const double *xq, cb_i64 nx,
+                  int32_t *elem, double *vals, void *stream);
 /* The same operator as a BandedMatrix with l = u = w (>= max order - 1), data (2w+1) x (last-first+1)
  * column-major: the form factorize(A - sigma*I) of ShiftAndInvert takes for FE-DVR operators
  * (src/linear_operators.jl:185-236, test/linear_operators.jl:72-88 "FE-DVR"); feeds cb_bandchol_* / cb_bandldl_* /

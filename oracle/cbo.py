@@ -854,6 +854,28 @@ def implicit_derivative_apply_general(Delta, M, c, X, alpha=1.0, beta=0.0, Y=Non
 # checks complex_rotate and real_locs only, src/fedvr_derivatives.jl:55 carries a "TODO Check if correct"); this is a
 # literal transcription of the Julia loops, including the dropped rotation of the nodes (src/quadrature.jl:25-27 calls
 # change_interval! without its gamma argument) and the conjugation inside LinearAlgebra.dot.
+def fedvr_eval_dense(O, xq):
+    """B[x, :] of an FE-DVR basis as a dense matrix, following getindex (src/fedvr.jl:211-222, 272-295): column by
+    column over (element i, function m), chi = n_m prod_{j != m} (x - x_j) / (x_m - x_j) for the points in the closed
+    element; a bridge function is written by both its elements (the right one last).  O: FEDVROracle."""
+    xq = np.asarray(xq, dtype=np.float64)
+    out = np.zeros((xq.size, O.N))
+    for i in range(O.nel):
+        o = int(O.order[i])
+        xi = O.x[O.estart[i]:O.estart[i] + o]
+        ni = O.n[O.estart[i]:O.estart[i] + o]
+        inside = np.nonzero((xq >= O.t[i]) & (xq <= O.t[i + 1]))[0]
+        for m in range(o):
+            for p in inside:
+                chi = ni[m]
+                for j in range(o):
+                    if j == m:
+                        continue
+                    chi = chi * ((xq[p] - xi[j]) / (xi[m] - xi[j]))
+                out[p, O.estart[i] + m] = chi
+    return out
+
+
 def fedvr_complex_fields(t, order, t0, phi):
     t = np.asarray(t, dtype=np.float64)
     nel = len(t) - 1

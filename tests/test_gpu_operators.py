@@ -593,3 +593,32 @@ def test_host_register_entries(cb):
     assert np.array_equal(Yr, Yp)
     assert lib.cb_host_unregister(C.c_void_p(X.ctypes.data)) != 0
     assert lib.cb_host_register(None, C.c_size_t(16)) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [2, 5, 10, [4, 3, 4, 2, 5, 4, 2, 4, 8]])
+def test_fedvr_basis_function_evaluation(cb, order):
+    """B[x, :] for FE-DVR (getindex, src/fedvr.jl:211-222, 272-295; test/fedvr/basics.jl: B[0.0, 1] != 0, the first
+    function of the restriction B[:, 2:end-1] vanishes at the end points): bit-identical to the scalar loop, element
+    boundaries and end points included, points outside the basis give empty rows, and the expansion of a smooth function
+    reproduces it between the nodes (test/interpolation.jl)."""
+    nel = 9
+    t = cbo.julia_range(0.0, 20.0, nel + 1)
+    B = cb.FEDVR(t, order)
+    O = cbo.FEDVROracle(t, order)
+    rng = np.random.default_rng(3)
+    xq = np.concatenate([rng.uniform(0, 20, 200), np.asarray(t), B.x[::3], [-0.5, 20.5, np.nan]])
+    got = B.eval_dense(xq)
+    ref = cbo.fedvr_eval_dense(O, xq[:-3])
+    assert np.array_equal(got[:-3], ref)
+    assert not got[-3:].any()
+    assert got[200, 0] != 0.0 and got[200 + nel, -1] != 0.0                  # B[0.0, 1], B[20.0, end]
+    Br = B.eval_dense(xq, 2, B.N - 1)
+    assert Br[200, 0] == 0.0 and Br[200 + nel, -1] == 0.0                     # restricted basis at the end points
+    elem, _ = B.eval(xq)
+    e = elem.cpu().numpy()
+    assert e[200] == 1 and e[200 + nel] == nel and np.array_equal(e[201:200 + nel], np.arange(2, nel + 1))
+    if not isinstance(order, list) and order >= 5:
+        f = lambda r: np.exp(-0.1 * r) * np.sin(r)
+        c = f(B.x) / B.n                                                       # R \ f for FE-DVR (src/fedvr.jl:369-412)
+        assert np.max(np.abs(got[:200] @ c - f(xq[:200]))) <= (2e-3 if order == 5 else 1e-5)   # interpolation error of 2.2-wide elements
