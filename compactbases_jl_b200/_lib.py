@@ -65,6 +65,7 @@ _SIGNATURES = {
     "cb_fedvr_to_dense": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp]),
     "cb_fedvr_to_band": (cint, [vp, vp, vp, vp, i64, i64, i64, cint, vp, vp]),
     "cb_fedvr_eval": (cint, [vp, vp, vp, vp, vp, i64, cint, vp, i64, vp, vp, vp]),
+    "cb_fd_eval": (cint, [vp, vp, i64, vp, i64, vp, vp, vp]),
     "cb_fedvr_to_skyline": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
     "cb_fedvr_to_tridiag": (cint, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
     "cb_fedvr_apply": (cint, [vp, vp, vp, vp, i64, cint, i64, i64, vp, i64, i64, dbl, dbl, vp, i64, vp]),

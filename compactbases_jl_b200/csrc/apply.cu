@@ -1836,6 +1836,50 @@ int cb_fedvr_eval(const double *xn, const double *nrm, const double *t, const i6
     return CB_OK;
 }
 
+// Finite-difference basis functions at points (getindex, src/finite_differences.jl:63-93): function j is the tent over
+// (l_{j-1}, l_j, l_{j+1}) times weight(B, j), tent(x, a, b, c) = 1 - clamp((b-x)/(b-a), 0, 1) - clamp((b-x)/(b-c), 0, 1),
+// with the mirrored neighbours 2 l_1 - l_2 and 2 l_n - l_{n-1} beyond the ends.  At most two functions are non-zero at
+// a point: first[p] = j (1-based; 0: none) and vals[2 p], vals[2 p + 1] = functions j and j + 1.  One thread per point.
+__device__ __forceinline__ double fd_clamp01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+__device__ __forceinline__ double fd_tent(double x, double a, double b, double c) {
+    return __dsub_rn(__dsub_rn(1.0, fd_clamp01(__ddiv_rn(__dsub_rn(b, x), __dsub_rn(b, a)))),
+                     fd_clamp01(__ddiv_rn(__dsub_rn(b, x), __dsub_rn(b, c))));
+}
+__global__ void fd_eval_kernel(const double *__restrict__ l, const double *__restrict__ w, i64 n,
+                               const double *__restrict__ xq, i64 nx, int32_t *__restrict__ first, double *__restrict__ vals) {
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < nx; p += (i64)gridDim.x * blockDim.x) {
+        const double x = xq[p];
+        const double lo_ext = __dsub_rn(__dmul_rn(2.0, l[0]), l[1]), hi_ext = __dsub_rn(__dmul_rn(2.0, l[n - 1]), l[n - 2]);
+        first[p] = 0; vals[2 * p] = 0.0; vals[2 * p + 1] = 0.0;
+        if (!(x >= lo_ext && x <= hi_ext)) continue;
+        // j0: last node with l[j0] <= x (0-based; -1 left of the first node)
+        i64 lo = -1, hi = n;
+        while (hi - lo > 1) {
+            const i64 mid = (lo + hi) >> 1;
+            if (l[mid] <= x) lo = mid; else hi = mid;
+        }
+        auto node = [&](i64 j) { return j < 0 ? lo_ext : (j >= n ? hi_ext : l[j]); };
+        const i64 ja = lo < 0 ? 0 : lo;                 // first function that can be non-zero at x
+        first[p] = (int32_t)(ja + 1);
+        for (int u = 0; u < 2; ++u) {
+            const i64 j = ja + u;
+            if (j >= n || (lo < 0 && u == 1)) break;
+            const double v = __dmul_rn(w ? w[j] : 1.0, fd_tent(x, node(j - 1), node(j), node(j + 1)));
+            vals[2 * p + u] = v;
+        }
+    }
+}
+
+int cb_fd_eval(const double *nodes, const double *weights, i64 n, const double *xq, i64 nx, int32_t *first, double *vals,
+               void *stream) {
+    CB_REQUIRE(nx >= 0 && n >= 2, "cb_fd_eval: a grid needs at least two nodes");
+    if (nx == 0) return CB_OK;
+    CB_REQUIRE(nodes && xq && first && vals, "cb_fd_eval: NULL argument");
+    fd_eval_kernel<<<cb_grid_for(nx, 256, 16), 256, 0, (cudaStream_t)stream>>>(nodes, weights, n, xq, nx, first, vals);
+    CB_LAUNCH_CHECK();
+    return CB_OK;
+}
+
 int cb_fedvr_to_band(const double *blocks, const i64 *estart, const int32_t *order, const i64 *boff,
                      i64 nel, i64 first, i64 last, int w, double *band, void *stream) {
     CB_REQUIRE(blocks && estart && order && boff && band, "cb_fedvr_to_band: NULL argument");

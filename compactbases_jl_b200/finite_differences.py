@@ -213,6 +213,31 @@ class AbstractFiniteDifferences(_FDOrRestricted):
         h[1:-1] = (r[2:] - r[:-2]) / 2
         return 1 / np.sqrt(h)
 
+    def eval(self, x):
+        """``B[x, :]`` in row form (``cb_fd_eval``; getindex, src/finite_differences.jl:63-93): the 1-based first function
+        that can be non-zero at every point (0: none) and the values of it and of the next one."""
+        xq = x if isinstance(x, torch.Tensor) else to_device(np.asarray(x, dtype=np.float64), self.device)
+        xq = xq.to(self.device, torch.float64).contiguous()
+        nx = xq.numel()
+        wv = self.vandermonde_diag()
+        d_w = None if wv is None else to_device(np.asarray(wv, dtype=np.float64), self.device)
+        first = torch.empty(nx, dtype=torch.int32, device=self.device)
+        vals = torch.empty((nx, 2), dtype=torch.float64, device=self.device)
+        _lib.call("cb_fd_eval", _ptr(self.d_nodes), None if d_w is None else _ptr(d_w), self.N, _ptr(xq), nx,
+                  _ptr(first), _ptr(vals), _stream())
+        return first, vals
+
+    def eval_dense(self, x, first: int = 1, last: int | None = None) -> np.ndarray:
+        """``Matrix(B[x, first:last])`` on the host (tests, small grids)."""
+        last = self.N if last is None else last
+        f, v = self.eval(x)
+        f, v = f.cpu().numpy(), v.cpu().numpy()
+        out = np.zeros((f.size, self.N + 1))
+        idx = np.nonzero(f)[0]
+        out[idx, f[idx] - 1] = v[idx, 0]
+        out[idx, f[idx]] = v[idx, 1]
+        return out[:, first - 1:last]
+
     def mass_value(self):
         return self.step                               # src/finite_differences.jl:141-143
 

@@ -194,6 +194,11 @@ int cb_fedvr_to_dense(const double *blocks, const cb_i64 *estart, const int32_t 
 int cb_fedvr_eval(const double *x_nodes, const double *nrm, const double *t, const cb_i64 *estart,
                   const int32_t *order, cb_i64 nel, int max_order, const double *xq, cb_i64 nx,
                   int32_t *elem, double *vals, void *stream);
+/* B[x, :] for finite-difference bases (getindex, src/finite_differences.jl:63-93), row form: first[p] = the (1-based)
+ * first function that can be non-zero at x_p (0: none), vals[2p], vals[2p+1] = weight * tent of that function and the
+ * next.  nodes: the n grid points (device); weights: weights(B) (device) or NULL on uniform grids. */
+int cb_fd_eval(const double *nodes, const double *weights, cb_i64 n, const double *xq, cb_i64 nx,
+               int32_t *first, double *vals, void *stream);
 /* The same operator as a BandedMatrix with l = u = w (>= max order - 1), data (2w+1) x (last-first+1)
  * column-major: the form factorize(A - sigma*I) of ShiftAndInvert takes for FE-DVR operators
  * (src/linear_operators.jl:185-236, test/linear_operators.jl:72-88 "FE-DVR"); feeds cb_bandchol_* / cb_bandldl_* /

@@ -854,6 +854,24 @@ def implicit_derivative_apply_general(Delta, M, c, X, alpha=1.0, beta=0.0, Y=Non
 # checks complex_rotate and real_locs only, src/fedvr_derivatives.jl:55 carries a "TODO Check if correct"); this is a
 # literal transcription of the Julia loops, including the dropped rotation of the nodes (src/quadrature.jl:25-27 calls
 # change_interval! without its gamma argument) and the conjugation inside LinearAlgebra.dot.
+def fd_eval_dense(l, w, xq):
+    """B[x, :] of a finite-difference basis as a dense matrix (getindex, src/finite_differences.jl:63-93): column j is
+    weight_j * tent(x, l_{j-1}, l_j, l_{j+1}) on the points of [a, c], the neighbours mirrored beyond the ends."""
+    l = np.asarray(l, dtype=np.float64)
+    xq = np.asarray(xq, dtype=np.float64)
+    n = l.size
+    out = np.zeros((xq.size, n))
+    clamp = lambda v: min(max(v, 0.0), 1.0)
+    for j in range(n):
+        b = l[j]
+        a = l[j - 1] if j > 0 else 2 * b - l[j + 1]
+        c = l[j + 1] if j < n - 1 else 2 * b - l[j - 1]
+        wj = 1.0 if w is None else w[j]
+        for p in np.nonzero((xq >= a) & (xq <= c))[0]:
+            out[p, j] = wj * (1 - clamp((b - xq[p]) / (b - a)) - clamp((b - xq[p]) / (b - c)))
+    return out
+
+
 def fedvr_eval_dense(O, xq):
     """B[x, :] of an FE-DVR basis as a dense matrix, following getindex (src/fedvr.jl:211-222, 272-295): column by
     column over (element i, function m), chi = n_m prod_{j != m} (x - x_j) / (x_m - x_j) for the points in the closed

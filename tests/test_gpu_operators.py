@@ -622,3 +622,32 @@ def test_fedvr_basis_function_evaluation(cb, order):
         f = lambda r: np.exp(-0.1 * r) * np.sin(r)
         c = f(B.x) / B.n                                                       # R \ f for FE-DVR (src/fedvr.jl:369-412)
         assert np.max(np.abs(got[:200] @ c - f(xq[:200]))) <= (2e-3 if order == 5 else 1e-5)   # interpolation error of 2.2-wide elements
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cartesian", "staggered_uniform", "staggered_nonuniform"])
+def test_fd_basis_function_evaluation(cb, kind):
+    """B[x, :] for finite-difference bases (getindex, src/finite_differences.jl:63-93; test/fd/basis_functions.jl): the
+    weighted tents, bit-identical to the scalar formula, grid points, the mirrored end intervals and points outside
+    included; the expansion of a function is its piecewise-linear interpolant."""
+    if kind == "cartesian":
+        R = cb.FiniteDifferences(40, 0.25)
+    elif kind == "staggered_uniform":
+        R = cb.StaggeredFiniteDifferences(40, 0.25)
+    else:
+        R = cb.StaggeredFiniteDifferences(np.cumsum(np.minimum(0.1 + 0.01 * np.arange(60), 0.2))[:40])
+    l = np.asarray(R.locs())
+    w = R.vandermonde_diag()
+    rng = np.random.default_rng(4)
+    ext = l[1] - l[0]
+    xq = np.concatenate([rng.uniform(l[0] - ext, l[-1] + (l[-1] - l[-2]), 300), l, [l[0] - 2 * ext, l[-1] + 10.0, np.nan]])
+    got = R.eval_dense(xq)
+    ref = cbo.fd_eval_dense(l, w, xq[:-3])
+    assert np.array_equal(got[:-3], ref)
+    assert not got[-3:].any()
+    wv = np.ones(l.size) if w is None else np.asarray(w)
+    assert np.array_equal(np.diag(got[300:300 + l.size]), wv)                  # B[l_j, j] = weight_j, neighbours vanish
+    inside = (xq[:300] >= l[0]) & (xq[:300] <= l[-1])
+    f = lambda r: np.sin(r) + 0.3 * r
+    c = f(l) / wv                                                              # R \\ f (src/finite_differences.jl:452-458)
+    assert np.max(np.abs((got[:300] @ c)[inside] - np.interp(xq[:300][inside], l, f(l)))) <= 1e-13
