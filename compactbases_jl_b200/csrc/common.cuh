@@ -24,6 +24,7 @@ int cb_keep_scratch_pool();                    // errors.cu: keep the stream-ord
         if (e__ != cudaSuccess) {                                                \
             cb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,           \
                          cudaGetErrorString(e__));                               \
+            (void)cudaGetLastError(); /* reported here: a later launch check must not see it again */ \
             return CB_ERR_CUDA;                                                  \
         }                                                                        \
     } while (0)

@@ -593,6 +593,10 @@ def test_host_register_entries(cb):
     assert np.array_equal(Yr, Yp)
     assert lib.cb_host_unregister(C.c_void_p(X.ctypes.data)) != 0
     assert lib.cb_host_register(None, C.c_size_t(16)) != 0
+    # a failed runtime call is reported once: the next entry's launch check must not see it again
+    Yd = cb.ColMajor.from_numpy(np.zeros((B.N, 20)))
+    cb.mul(Yd, A, cb.ColMajor.from_numpy(X))
+    assert np.array_equal(Yd.numpy(), Yp)
 
 
 @pytest.mark.gpu
